@@ -1,0 +1,182 @@
+/* muse_b200.h — C ABI of libmuse_b200.so, the B200 (sm_100a) backend for the per-simulation
+ * hot path of MUSE.
+ *
+ * The reference (MuseInference.jl, pure Julia) has no FFI: its extension seam is multiple
+ * dispatch on `AbstractMuseProblem` (/root/reference/src/interface.jl:4) and the three mapped
+ * blocks `pmap(pool, ...) do ... end` of
+ *     muse!   /root/reference/src/muse.jl:169-176
+ *     get_H!  /root/reference/src/muse.jl:417-423 and 426-442 (+ pjacobian, src/util.jl:9-26)
+ *     get_J!  /root/reference/src/muse.jl:508-525
+ * A batched GPU backend replaces exactly those blocks.  Each entry point below cites the
+ * reference lines it replaces; INTEGRATION.md shows the Julia `ccall` stubs and the Python
+ * ctypes binding (museinference.jl_b200/_capi.py) that binds them.
+ *
+ * Conventions
+ *   - all functions return 0 on success or a negative MUSE_E* code; the message is available
+ *     from muse_b200_last_error(); no C++ exception crosses this boundary;
+ *   - all numeric data is FP64 (the reference computes in Float64, src/muse.jl:152);
+ *   - host matrices are dense row-major, "sim-major": row k = simulation k, d contiguous values;
+ *   - the caller owns every host pointer (valid for the duration of the call only); the library
+ *     owns all device memory until muse_b200_destroy();
+ *   - calls are synchronous unless the name ends in _async; a handle is not thread-safe;
+ *   - one handle drives one GPU and owns the contiguous shard [sim_offset, sim_offset+nsims)
+ *     of the global simulation index space (one process per GPU; the tiny cross-rank exchange
+ *     of scores is done by the host with NCCL);
+ *   - there is NO CPU fallback: without a CUDA device create() fails with MUSE_ENODEVICE.
+ *
+ * Unit numbering inside a handle: unit 0 is the observed data (`rng === nothing`,
+ * src/muse.jl:170); unit 1+k is local simulation k (global index sim_offset+k).
+ */
+#ifndef MUSE_B200_H
+#define MUSE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MUSE_B200_ABI_VERSION 1
+
+/* error codes */
+#define MUSE_OK            0
+#define MUSE_EINVAL       -1   /* bad argument */
+#define MUSE_ENODEVICE    -2   /* no CUDA device / wrong architecture */
+#define MUSE_ECUDA        -3   /* CUDA runtime error (see last_error) */
+#define MUSE_ENOMEM       -4
+#define MUSE_EUNSUPPORTED -5   /* model outside the registered families */
+#define MUSE_ESTATE       -6   /* call order violated (e.g. no draws installed) */
+
+/* registered model families */
+#define MUSE_FAMILY_FUNNEL     1   /* src/simple.jl:58-76: z~N(0,e^θ I), x~N(z,I); scalar θ            */
+#define MUSE_FAMILY_HIERGAUSS  2   /* z~N(μ,e^{2ℓ} I), x~N(z,I); θ=(μ,ℓ)                               */
+#define MUSE_FAMILY_CORRGAUSS  3   /* z~N(0,e^θ Σ₀), x~N(z,I); scalar θ; P=Σ₀⁻¹, L=chol Σ₀ supplied    */
+
+/* warm-start modes for the latent MAP (what the reference passes as z₀ to ẑ_at_θ) */
+#define MUSE_START_ZEROS   0   /* zero(z)                 src/muse.jl:151, src/interface.jl:184-186 */
+#define MUSE_START_PREV    1   /* previous ẑ of the unit  src/muse.jl:169,181 (ẑs carried over)     */
+#define MUSE_START_TRUTH   2   /* the simulated z         src/muse.jl:511                           */
+#define MUSE_START_USER    3   /* user z₀ (muse_b200_set_z0), the `z₀` keyword                     */
+
+/* per-unit solver status (Optim's convergence flags, src/interface.jl:168-171) */
+#define MUSE_STATUS_G_CONVERGED   0   /* ‖∇z‖_∞ ≤ atol                                   */
+#define MUSE_STATUS_XF_CONVERGED  1   /* x or f stopped changing exactly (x_tol=f_tol=0) */
+#define MUSE_STATUS_MAXITER       2   /* 1000 iterations: Optim.converged == false       */
+#define MUSE_STATUS_LS_FAILED     3   /* line search exception: optimisation stopped     */
+#define MUSE_STATUS_NONFINITE     4   /* non-finite objective / gradient                 */
+
+#define MUSE_MAX_NTHETA 8
+
+typedef struct muse_handle muse_handle;
+
+typedef struct muse_cfg {
+    int32_t abi_version;     /* MUSE_B200_ABI_VERSION */
+    int32_t family;          /* MUSE_FAMILY_* */
+    int32_t d;               /* latent (= data) dimension */
+    int32_t ntheta;          /* 1 (funnel, corrgauss) or 2 (hiergauss) */
+    int32_t nsims;           /* local simulations owned by this handle (rows of the draw arrays) */
+    int32_t device;          /* CUDA device ordinal */
+    int64_t sim_offset;      /* global index of local simulation 0 */
+    int32_t nsims_h;         /* sims of the get_H! shard held as extra draw rows; 0 → the H shard is the
+                                first sims of the local shard (single-GPU default) */
+    int32_t reserved0;
+    int64_t h_sim_offset;    /* global index of H-shard simulation 0 (used when nsims_h > 0) */
+    int32_t lbfgs_m;         /* L-BFGS memory; 0 → 10 (Optim.LBFGS default) */
+    int32_t max_iters;       /* 0 → 1000 (Optim.Options default) */
+    int32_t group;           /* threads cooperating on one MAP solve: 0 auto, 32 = warp, else CTA size */
+    int32_t cluster;         /* CTAs per thread-block cluster cooperating on one solve: 0 auto, 1,2,4,8 */
+    const double* P;         /* corrgauss: Σ₀⁻¹, d×d row-major host pointer; else NULL */
+    const double* L;         /* corrgauss: chol(Σ₀) lower, d×d row-major host pointer; else NULL */
+    void* stream;            /* cudaStream_t to launch on, or NULL → library-owned stream */
+} muse_cfg;
+
+/* per-kernel-class device timing, measured with CUDA events on the launch stream */
+typedef struct muse_profile {
+    int64_t launches;        /* kernels launched since the last reset */
+    int64_t solve_launches;  /* launches of the persistent MAP+score solver kernel */
+    double  solve_ms;        /* summed device time of those launches (events) */
+    double  solve_units;     /* MAP+score units they processed */
+    double  solve_bytes;     /* algorithmic bytes they account for */
+    int64_t draw_launches;
+    double  draw_ms;
+    int64_t other_launches;
+    double  other_ms;
+} muse_profile;
+
+int  muse_b200_abi_version(void);
+
+/* lifetime ------------------------------------------------------------------------------- */
+int  muse_b200_create(const muse_cfg* cfg, muse_handle** out);
+int  muse_b200_destroy(muse_handle* h);
+const char* muse_b200_last_error(const muse_handle* h);   /* h may be NULL: last create() error */
+int  muse_b200_set_stream(muse_handle* h, void* cuda_stream);
+
+/* inputs --------------------------------------------------------------------------------- */
+/* observed data `prob.x` (src/simple.jl:5; used at src/muse.jl:170) */
+int  muse_b200_set_data(muse_handle* h, const double* x_dat /* d */);
+/* parity mode: base normals of the local sims, ξ (latent) and ν (noise), nsims×d each, plus the
+ * master stream's own draw (the sim `sample_x_z(prob, copy(rng), θ)` makes at src/muse.jl:151,418).
+ * Replaces `split_rng` (src/util.jl:85-92): sim k sees the same normals at every θ. */
+int  muse_b200_set_draws(muse_handle* h, const double* xi, const double* nu,
+                         const double* xi_master /* d */, const double* nu_master /* d */);
+/* parity mode, multi-GPU only: base normals of the get_H! shard (nsims_h×d each) */
+int  muse_b200_set_draws_h(muse_handle* h, const double* xi_h, const double* nu_h);
+/* throughput mode: Philox4x32-10 + Box–Muller on the device, keyed by (seed, global sim index,
+ * stream, element pair) so results do not depend on how sims are sharded over GPUs. */
+int  muse_b200_seed_draws(muse_handle* h, uint64_t seed);
+/* read back draws (tests): rows [first, first+count) of ξ and ν; row index nsims = master draw */
+int  muse_b200_get_draws(muse_handle* h, int32_t first, int32_t count, double* xi_out, double* nu_out);
+/* user start guess z₀ (`z₀` keyword of muse!/get_J!/get_H!, src/muse.jl:117, 309, 488) */
+int  muse_b200_set_z0(muse_handle* h, const double* z0 /* d */);
+
+/* the hot path --------------------------------------------------------------------------- */
+/* Body of the mapped blocks src/muse.jl:169-176 (include_data=1, warm start ZEROS/PREV) and
+ * src/muse.jl:508-514 (include_data=0, warm start TRUTH): for the data unit (optional) and local
+ * sims [first_sim, first_sim+count):
+ *     x ← prob.x  |  sample_x_z(rng_k, theta_sim).x
+ *     ẑ ← argmin_z −logLike(x, z, theta_eval) by L-BFGS(m)+HagerZhang from the chosen start until
+ *         ‖∇z‖_∞ ≤ atol                                   (src/interface.jl:162-166)
+ *     g ← ∇θ logLike(x, ẑ, theta_eval)                    (src/simple.jl:92)
+ * Outputs are indexed by unit in the order [data?, sims...]; any output pointer may be NULL.
+ * ẑ stays resident on the device (warm start of the next call; muse_b200_get_maps). */
+int  muse_b200_map_score(muse_handle* h, const double* theta_sim, const double* theta_eval,
+                         double atol, int32_t include_data, int32_t warm_start,
+                         int32_t first_sim, int32_t count,
+                         double* g_out      /* units × ntheta */,
+                         int32_t* iters_out /* units: L-BFGS iterations      */,
+                         int32_t* fg_out    /* units: value+gradient evaluations */,
+                         double* gnorm_out  /* units: final ‖∇z‖_∞           */,
+                         int32_t* status_out/* units: MUSE_STATUS_*          */);
+/* same work enqueued on the stream without a host sync; results stay in device buffers until
+ * muse_b200_fetch() copies them out (bench: device-resident timing). */
+int  muse_b200_map_score_async(muse_handle* h, const double* theta_sim, const double* theta_eval,
+                               double atol, int32_t include_data, int32_t warm_start,
+                               int32_t first_sim, int32_t count);
+int  muse_b200_fetch(muse_handle* h, int32_t units, double* g_out, int32_t* iters_out,
+                     int32_t* fg_out, double* gnorm_out, int32_t* status_out);
+
+/* Finite-difference branch of get_H! (src/muse.jl:417-442 + pjacobian src/util.jl:9-26 with
+ * fdm = central_fdm(3,1) and an explicit step): one fiducial MAP of the master-stream draw from
+ * zero(z) (the reference computes nsims_H identical copies, :417-423), then for the first
+ * nsims_H sims of the H shard (cfg.nsims_h / h_sim_offset; by default the local shard) and each θ-component n: sims at theta0 ± step[n]·e_n (same base normals), MAP and
+ * score at theta0 from the fiducial start; column n = (½ g₊ − ½ g₋)/step[n].  The centre
+ * evaluation, which central_fdm multiplies by 0, is not executed.
+ * Hs_out[k][i][n] = ∂ g_i / ∂ θ_n of sim k (row-major ntheta×ntheta per sim). */
+int  muse_b200_fd_jacobian(muse_handle* h, const double* theta0, const double* step,
+                           int32_t nsims_H, double atol,
+                           double* Hs_out /* nsims_H × ntheta × ntheta */,
+                           int32_t* status_out /* nsims_H × ntheta × 2, may be NULL */);
+
+/* MAPs of units [first_unit, first_unit+count) (unit 0 = data) — `save_MAPs`, src/muse.jl:139-143,219 */
+int  muse_b200_get_maps(muse_handle* h, int32_t first_unit, int32_t count, double* z_out /* count × d */);
+
+/* diagnostics ---------------------------------------------------------------------------- */
+int  muse_b200_profile_reset(muse_handle* h, int32_t enable);
+int  muse_b200_profile_get(muse_handle* h, muse_profile* out);
+/* geometry chosen for the solver: threads per solve group, CTAs per cluster, resident groups */
+int  muse_b200_geometry(muse_handle* h, int32_t* group_threads, int32_t* cluster, int32_t* groups);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MUSE_B200_H */

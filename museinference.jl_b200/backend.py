@@ -1,0 +1,179 @@
+"""NumPy-facing wrapper of one libmuse_b200 handle (one GPU, one shard of simulations).
+
+Thin by design: every method is one C-ABI call (include/muse_b200.h) with host NumPy buffers in
+and out.  The arithmetic happens in the CUDA kernels; nothing here computes on the N×d batch.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from ._capi import MuseBackendError
+
+FAMILY_IDS = {"funnel": _capi.FAMILY_FUNNEL, "hiergauss": _capi.FAMILY_HIERGAUSS, "corrgauss": _capi.FAMILY_CORRGAUSS}
+FAMILY_NTHETA = {"funnel": 1, "hiergauss": 2, "corrgauss": 1}
+
+
+def _f64(a, shape=None):
+    arr = np.ascontiguousarray(a, dtype=np.float64)
+    if shape is not None and arr.shape != shape:
+        raise ValueError(f"expected array of shape {shape}, got {arr.shape}")
+    return arr
+
+
+def _dp(arr):
+    return arr.ctypes.data_as(_capi.c_double_p) if arr is not None else None
+
+
+def _ip(arr):
+    return arr.ctypes.data_as(_capi.c_int32_p) if arr is not None else None
+
+
+class B200Backend:
+    def __init__(self, family: str, d: int, nsims: int, *, sim_offset: int = 0, nsims_h: int = 0,
+                 h_sim_offset: int = 0, device: int = 0, group: int = 0, cluster: int = 0, stream=None,
+                 lbfgs_m: int = 0, max_iters: int = 0, P=None, L=None):
+        if family not in FAMILY_IDS:
+            raise MuseBackendError(-5, f"model family {family!r} is outside the registered families "
+                                       f"{sorted(FAMILY_IDS)}; Turing/Soss-defined models are not supported")
+        self._lib = _capi.load_library()
+        self.family, self.d, self.nsims = family, int(d), int(nsims)
+        self.ntheta = FAMILY_NTHETA[family]
+        self.nsims_h = int(nsims_h)
+        self._P = _f64(P, (d, d)) if P is not None else None
+        self._L = _f64(L, (d, d)) if L is not None else None
+        cfg = _capi.muse_cfg(
+            abi_version=_capi.ABI_VERSION, family=FAMILY_IDS[family], d=self.d, ntheta=self.ntheta,
+            nsims=self.nsims, device=int(device), sim_offset=int(sim_offset), nsims_h=self.nsims_h, reserved0=0,
+            h_sim_offset=int(h_sim_offset), lbfgs_m=int(lbfgs_m), max_iters=int(max_iters), group=int(group),
+            cluster=int(cluster), P=_dp(self._P), L=_dp(self._L), stream=C.c_void_p(stream) if stream else None)
+        self._h = C.c_void_p()
+        rc = self._lib.muse_b200_create(C.byref(cfg), C.byref(self._h))
+        if rc != 0:
+            msg = self._lib.muse_b200_last_error(None).decode()
+            self._h = None
+            raise MuseBackendError(rc, msg)
+
+    # ------------------------------------------------------------------ plumbing
+    def _check(self, rc):
+        if rc != 0:
+            raise MuseBackendError(rc, self._lib.muse_b200_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.muse_b200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def set_stream(self, stream):
+        self._check(self._lib.muse_b200_set_stream(self._h, C.c_void_p(stream) if stream else None))
+
+    # ------------------------------------------------------------------ inputs
+    def set_data(self, x):
+        x = _f64(x, (self.d,))
+        self._check(self._lib.muse_b200_set_data(self._h, _dp(x)))
+
+    def set_draws(self, xi, nu, xi_master, nu_master):
+        xi = _f64(xi, (self.nsims, self.d))
+        nu = _f64(nu, (self.nsims, self.d))
+        xm, nm = _f64(xi_master, (self.d,)), _f64(nu_master, (self.d,))
+        self._check(self._lib.muse_b200_set_draws(self._h, _dp(xi), _dp(nu), _dp(xm), _dp(nm)))
+
+    def set_draws_h(self, xi_h, nu_h):
+        xi_h = _f64(xi_h, (self.nsims_h, self.d))
+        nu_h = _f64(nu_h, (self.nsims_h, self.d))
+        self._check(self._lib.muse_b200_set_draws_h(self._h, _dp(xi_h), _dp(nu_h)))
+
+    def seed_draws(self, seed: int):
+        self._check(self._lib.muse_b200_seed_draws(self._h, C.c_uint64(int(seed))))
+
+    def get_draws(self, first: int, count: int):
+        xi = np.empty((count, self.d))
+        nu = np.empty((count, self.d))
+        self._check(self._lib.muse_b200_get_draws(self._h, first, count, _dp(xi), _dp(nu)))
+        return xi, nu
+
+    def set_z0(self, z0):
+        z0 = _f64(z0, (self.d,))
+        self._check(self._lib.muse_b200_set_z0(self._h, _dp(z0)))
+
+    # ------------------------------------------------------------------ hot path
+    def _theta(self, th):
+        th = np.ascontiguousarray(np.atleast_1d(np.asarray(th, dtype=np.float64)))
+        if th.shape != (self.ntheta,):
+            raise ValueError(f"θ must have {self.ntheta} component(s)")
+        return th
+
+    def map_score(self, theta_sim, theta_eval, atol, *, include_data: bool, warm_start: int,
+                  first_sim: int = 0, count: int | None = None):
+        count = self.nsims - first_sim if count is None else count
+        units = count + (1 if include_data else 0)
+        ts, te = self._theta(theta_sim), self._theta(theta_eval)
+        g = np.empty((units, self.ntheta))
+        iters = np.empty(units, dtype=np.int32)
+        fg = np.empty(units, dtype=np.int32)
+        gnorm = np.empty(units)
+        status = np.empty(units, dtype=np.int32)
+        self._check(self._lib.muse_b200_map_score(self._h, _dp(ts), _dp(te), float(atol), int(bool(include_data)),
+                                                  int(warm_start), int(first_sim), int(count), _dp(g), _ip(iters),
+                                                  _ip(fg), _dp(gnorm), _ip(status)))
+        return dict(g=g, iters=iters, fg_evals=fg, gnorm=gnorm, status=status)
+
+    def map_score_async(self, theta_sim, theta_eval, atol, *, include_data: bool, warm_start: int,
+                        first_sim: int = 0, count: int | None = None):
+        count = self.nsims - first_sim if count is None else count
+        ts, te = self._theta(theta_sim), self._theta(theta_eval)
+        self._check(self._lib.muse_b200_map_score_async(self._h, _dp(ts), _dp(te), float(atol),
+                                                        int(bool(include_data)), int(warm_start), int(first_sim),
+                                                        int(count)))
+        return count + (1 if include_data else 0)
+
+    def fetch(self, units: int):
+        g = np.empty((units, self.ntheta))
+        iters = np.empty(units, dtype=np.int32)
+        fg = np.empty(units, dtype=np.int32)
+        gnorm = np.empty(units)
+        status = np.empty(units, dtype=np.int32)
+        self._check(self._lib.muse_b200_fetch(self._h, int(units), _dp(g), _ip(iters), _ip(fg), _dp(gnorm), _ip(status)))
+        return dict(g=g, iters=iters, fg_evals=fg, gnorm=gnorm, status=status)
+
+    def fd_jacobian(self, theta0, step, nsims_H: int, atol):
+        t0 = self._theta(theta0)
+        st = self._theta(step)
+        Hs = np.empty((nsims_H, self.ntheta, self.ntheta))
+        status = np.empty((nsims_H, self.ntheta, 2), dtype=np.int32)
+        self._check(self._lib.muse_b200_fd_jacobian(self._h, _dp(t0), _dp(st), int(nsims_H), float(atol), _dp(Hs),
+                                                    _ip(status)))
+        return Hs, status
+
+    def get_maps(self, first_unit: int, count: int):
+        z = np.empty((count, self.d))
+        self._check(self._lib.muse_b200_get_maps(self._h, int(first_unit), int(count), _dp(z)))
+        return z
+
+    # ------------------------------------------------------------------ diagnostics
+    def profile_reset(self, enable: bool = True):
+        self._check(self._lib.muse_b200_profile_reset(self._h, int(enable)))
+
+    def profile(self) -> dict:
+        p = _capi.muse_profile()
+        self._check(self._lib.muse_b200_profile_get(self._h, C.byref(p)))
+        return {name: getattr(p, name) for name, _ in _capi.muse_profile._fields_}
+
+    def geometry(self) -> dict:
+        a, b, c = C.c_int32(), C.c_int32(), C.c_int32()
+        self._check(self._lib.muse_b200_geometry(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return dict(group_threads=a.value, cluster=b.value, groups=c.value)

@@ -1,0 +1,591 @@
+// muse_api.cu — the C ABI of libmuse_b200.so (include/muse_b200.h).
+//
+// Host-side glue only: argument checking, device-memory ownership, θ → kernel-constant
+// conversion, launch of the persistent solver, result copies.  All arithmetic on the N×d batch
+// happens in the CUDA kernels (muse_iso_solver.cu, muse_draws.cu).  There is no CPU fallback:
+// every entry point needs a live CUDA context on an sm_100 device.
+#include <cmath>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "muse_common.cuh"
+
+using namespace muse;
+
+struct muse_handle {
+    muse_cfg cfg{};
+    int ld = 0;
+    int rows = 0;               // 1 + nsims (unit 0 = data)
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    Geometry geo{};
+    bool have_data = false, have_draws = false, have_z0 = false;
+
+    // device arrays
+    double *xi = nullptr, *nu = nullptr;          // (nsims+1) × ld, last row = master draw
+    double *xi_h = nullptr, *nu_h = nullptr;      // nsims_h × ld: draws of the get_H! shard (multi-GPU)
+    bool have_draws_h = false;
+    double *xdat = nullptr, *z0user = nullptr;    // ld
+    double *x = nullptr, *zA = nullptr, *zB = nullptr;   // rows × ld
+    int* zstate = nullptr;                        // rows
+    double *sbuf = nullptr, *dxh = nullptr, *dgh = nullptr;   // per-slot scratch
+    // outputs (device + pinned host mirror), capacity out_cap items
+    int out_cap = 0;
+    double *g_d = nullptr, *gnorm_d = nullptr, *f_d = nullptr;
+    int *iters_d = nullptr, *fg_d = nullptr, *status_d = nullptr;
+    double *g_h = nullptr, *gnorm_h = nullptr;
+    int *iters_h = nullptr, *fg_h = nullptr, *status_h = nullptr;
+    // finite-difference scratch
+    int h_cap = 0;
+    double *xH = nullptr, *zHA = nullptr, *zHB = nullptr;
+    double *xfid = nullptr, *zfidA = nullptr, *zfidB = nullptr;
+    int* zfid_state = nullptr;
+
+    // profiling
+    bool prof = false;
+    struct Rec { cudaEvent_t a, b; int cls; double units, bytes; };
+    std::vector<Rec> recs;
+    muse_profile acc{};
+};
+
+static thread_local std::string g_create_err;
+
+#define MUSE_FAIL(h, code, msg)        \
+    do {                               \
+        (h)->err = (msg);              \
+        return (code);                 \
+    } while (0)
+
+#define CUDA_TRY(h, expr)                                                                     \
+    do {                                                                                      \
+        cudaError_t e__ = (expr);                                                             \
+        if (e__ != cudaSuccess) {                                                             \
+            (h)->err = std::string(#expr) + ": " + cudaGetErrorString(e__);                   \
+            return e__ == cudaErrorMemoryAllocation ? MUSE_ENOMEM : MUSE_ECUDA;               \
+        }                                                                                     \
+    } while (0)
+
+static int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+// θ → constants of the isotropic families (host libm, so oracle and kernel see identical scalars)
+static int theta_consts(const muse_cfg& c, const double* th_sim, const double* th_eval, IsoSample* smp, IsoEval* ev) {
+    const double d = (double)c.d;
+    if (c.family == MUSE_FAMILY_FUNNEL) {
+        if (smp) { smp->sig = std::exp(0.5 * th_sim[0]); smp->mu = 0.0; }
+        if (ev) { ev->a = std::exp(-th_eval[0]); ev->mu = 0.0; ev->half_cst = 0.5 * d * th_eval[0]; }
+        return 0;
+    }
+    if (c.family == MUSE_FAMILY_HIERGAUSS) {
+        if (smp) { smp->sig = std::exp(th_sim[1]); smp->mu = th_sim[0]; }
+        if (ev) { ev->a = std::exp(-2.0 * th_eval[1]); ev->mu = th_eval[0]; ev->half_cst = d * th_eval[1]; }
+        return 0;
+    }
+    return -1;
+}
+
+static int ensure_outputs(muse_handle* h, int items) {
+    if (items <= h->out_cap) return 0;
+    cudaFree(h->g_d); cudaFree(h->gnorm_d); cudaFree(h->f_d); cudaFree(h->iters_d); cudaFree(h->fg_d); cudaFree(h->status_d);
+    cudaFreeHost(h->g_h); cudaFreeHost(h->gnorm_h); cudaFreeHost(h->iters_h); cudaFreeHost(h->fg_h); cudaFreeHost(h->status_h);
+    h->out_cap = 0;
+    const size_t n = (size_t)items;
+    CUDA_TRY(h, cudaMalloc(&h->g_d, n * h->cfg.ntheta * sizeof(double)));
+    CUDA_TRY(h, cudaMalloc(&h->gnorm_d, n * sizeof(double)));
+    CUDA_TRY(h, cudaMalloc(&h->f_d, n * sizeof(double)));
+    CUDA_TRY(h, cudaMalloc(&h->iters_d, n * sizeof(int)));
+    CUDA_TRY(h, cudaMalloc(&h->fg_d, n * sizeof(int)));
+    CUDA_TRY(h, cudaMalloc(&h->status_d, n * sizeof(int)));
+    CUDA_TRY(h, cudaMallocHost(&h->g_h, n * h->cfg.ntheta * sizeof(double)));
+    CUDA_TRY(h, cudaMallocHost(&h->gnorm_h, n * sizeof(double)));
+    CUDA_TRY(h, cudaMallocHost(&h->iters_h, n * sizeof(int)));
+    CUDA_TRY(h, cudaMallocHost(&h->fg_h, n * sizeof(int)));
+    CUDA_TRY(h, cudaMallocHost(&h->status_h, n * sizeof(int)));
+    h->out_cap = items;
+    return 0;
+}
+
+static void fill_common(muse_handle* h, SolveLaunch& L) {
+    std::memset(&L, 0, sizeof(L));
+    L.d = h->cfg.d;
+    L.ld = h->ld;
+    L.ntheta = h->cfg.ntheta;
+    L.family = h->cfg.family;
+    L.lbfgs_m = h->cfg.lbfgs_m;
+    L.max_iters = h->cfg.max_iters;
+    L.xi = h->xi;
+    L.nu = h->nu;
+    L.xdat = h->xdat;
+    L.master_row = h->cfg.nsims;
+    L.sbuf = h->sbuf;
+    L.dxh = h->dxh;
+    L.dgh = h->dgh;
+    L.g_out = h->g_d;
+    L.iters_out = h->iters_d;
+    L.fg_out = h->fg_d;
+    L.gnorm_out = h->gnorm_d;
+    L.f_out = h->f_d;
+    L.status_out = h->status_d;
+}
+
+static int launch_solver(muse_handle* h, const SolveLaunch& L, double bytes) {
+    muse_handle::Rec r{};
+    if (h->prof) {
+        CUDA_TRY(h, cudaEventCreate(&r.a));
+        CUDA_TRY(h, cudaEventCreate(&r.b));
+        CUDA_TRY(h, cudaEventRecord(r.a, h->stream));
+    }
+    CUDA_TRY(h, launch_iso_solver(L, h->geo, h->stream));
+    h->acc.launches += 1;
+    h->acc.solve_launches += 1;
+    if (h->prof) {
+        CUDA_TRY(h, cudaEventRecord(r.b, h->stream));
+        r.cls = 0;
+        r.units = L.nitems;
+        r.bytes = bytes;
+        h->recs.push_back(r);
+    }
+    return 0;
+}
+
+extern "C" {
+
+int muse_b200_abi_version(void) { return MUSE_B200_ABI_VERSION; }
+
+const char* muse_b200_last_error(const muse_handle* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+int muse_b200_create(const muse_cfg* cfg, muse_handle** out) {
+    if (!cfg || !out) { g_create_err = "null argument"; return MUSE_EINVAL; }
+    *out = nullptr;
+    if (cfg->abi_version != MUSE_B200_ABI_VERSION) { g_create_err = "ABI version mismatch"; return MUSE_EINVAL; }
+    if (cfg->family == MUSE_FAMILY_CORRGAUSS) {
+        g_create_err = "corrgauss (F3) is not built yet in this round: dense Σ₀⁻¹z DGEMM path pending";
+        return MUSE_EUNSUPPORTED;
+    }
+    if (cfg->family != MUSE_FAMILY_FUNNEL && cfg->family != MUSE_FAMILY_HIERGAUSS) {
+        g_create_err = "model outside the registered families (funnel, hiergauss, corrgauss); "
+                       "Turing/Soss-defined models are not supported by the B200 backend";
+        return MUSE_EUNSUPPORTED;
+    }
+    const int want_nt = cfg->family == MUSE_FAMILY_HIERGAUSS ? 2 : 1;
+    if (cfg->ntheta != want_nt) { g_create_err = "ntheta does not match the family"; return MUSE_EINVAL; }
+    if (cfg->d < 1 || cfg->nsims < 0 || cfg->nsims_h < 0) { g_create_err = "d must be ≥ 1 and nsims, nsims_h ≥ 0"; return MUSE_EINVAL; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        g_create_err = "no CUDA device: libmuse_b200 has no CPU fallback";
+        return MUSE_ENODEVICE;
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) { g_create_err = "bad device ordinal"; return MUSE_EINVAL; }
+    cudaDeviceProp prop{};
+    if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess || prop.major != 10) {
+        cudaGetLastError();
+        g_create_err = "device is not compute capability 10.x (kernels are built for sm_100a only)";
+        return MUSE_ENODEVICE;
+    }
+    muse_handle* h = new (std::nothrow) muse_handle();
+    if (!h) { g_create_err = "out of host memory"; return MUSE_ENOMEM; }
+    h->cfg = *cfg;
+    if (h->cfg.lbfgs_m <= 0) h->cfg.lbfgs_m = 10;
+    if (h->cfg.lbfgs_m > 16) h->cfg.lbfgs_m = 16;
+    if (h->cfg.max_iters <= 0) h->cfg.max_iters = 1000;
+    h->ld = round_up(cfg->d, 32);
+    h->rows = cfg->nsims + 1;
+
+    auto fail = [&](int code) {
+        g_create_err = h->err;
+        muse_b200_destroy(h);
+        return code;
+    };
+#define CREATE_TRY(expr)                                                      \
+    do {                                                                      \
+        cudaError_t e__ = (expr);                                             \
+        if (e__ != cudaSuccess) {                                             \
+            h->err = std::string(#expr) + ": " + cudaGetErrorString(e__);     \
+            return fail(e__ == cudaErrorMemoryAllocation ? MUSE_ENOMEM : MUSE_ECUDA); \
+        }                                                                     \
+    } while (0)
+
+    CREATE_TRY(cudaSetDevice(cfg->device));
+    if (cfg->stream) {
+        h->stream = (cudaStream_t)cfg->stream;
+    } else {
+        CREATE_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        h->own_stream = true;
+    }
+    CREATE_TRY(iso_solver_geometry(cfg->d, cfg->group, cfg->cluster, cfg->device, &h->geo));
+
+    const size_t ld = (size_t)h->ld, rows = (size_t)h->rows, B = sizeof(double);
+    CREATE_TRY(cudaMalloc(&h->xi, rows * ld * B));
+    CREATE_TRY(cudaMalloc(&h->nu, rows * ld * B));
+    if (cfg->nsims_h > 0) {
+        CREATE_TRY(cudaMalloc(&h->xi_h, (size_t)cfg->nsims_h * ld * B));
+        CREATE_TRY(cudaMalloc(&h->nu_h, (size_t)cfg->nsims_h * ld * B));
+        CREATE_TRY(cudaMemsetAsync(h->xi_h, 0, (size_t)cfg->nsims_h * ld * B, h->stream));
+        CREATE_TRY(cudaMemsetAsync(h->nu_h, 0, (size_t)cfg->nsims_h * ld * B, h->stream));
+    }
+    CREATE_TRY(cudaMalloc(&h->xdat, ld * B));
+    CREATE_TRY(cudaMalloc(&h->z0user, ld * B));
+    CREATE_TRY(cudaMalloc(&h->x, rows * ld * B));
+    CREATE_TRY(cudaMalloc(&h->zA, rows * ld * B));
+    CREATE_TRY(cudaMalloc(&h->zB, rows * ld * B));
+    CREATE_TRY(cudaMalloc(&h->zstate, rows * sizeof(int)));
+    const size_t slots = (size_t)h->geo.groups, m = (size_t)h->cfg.lbfgs_m;
+    CREATE_TRY(cudaMalloc(&h->sbuf, slots * ld * B));
+    CREATE_TRY(cudaMalloc(&h->dxh, slots * m * ld * B));
+    CREATE_TRY(cudaMalloc(&h->dgh, slots * m * ld * B));
+    CREATE_TRY(cudaMalloc(&h->xfid, ld * B));
+    CREATE_TRY(cudaMalloc(&h->zfidA, ld * B));
+    CREATE_TRY(cudaMalloc(&h->zfidB, ld * B));
+    CREATE_TRY(cudaMalloc(&h->zfid_state, sizeof(int)));
+    CREATE_TRY(cudaMemsetAsync(h->xi, 0, rows * ld * B, h->stream));
+    CREATE_TRY(cudaMemsetAsync(h->nu, 0, rows * ld * B, h->stream));
+    CREATE_TRY(cudaMemsetAsync(h->xdat, 0, ld * B, h->stream));
+    CREATE_TRY(cudaMemsetAsync(h->z0user, 0, ld * B, h->stream));
+    CREATE_TRY(cudaMemsetAsync(h->zstate, 0, rows * sizeof(int), h->stream));
+    CREATE_TRY(cudaMemsetAsync(h->zfid_state, 0, sizeof(int), h->stream));
+    if (ensure_outputs(h, h->rows) != 0) return fail(MUSE_ECUDA);
+    CREATE_TRY(cudaStreamSynchronize(h->stream));
+#undef CREATE_TRY
+    *out = h;
+    return MUSE_OK;
+}
+
+int muse_b200_destroy(muse_handle* h) {
+    if (!h) return MUSE_OK;
+    cudaSetDevice(h->cfg.device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (auto& r : h->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    cudaFree(h->xi); cudaFree(h->nu); cudaFree(h->xi_h); cudaFree(h->nu_h); cudaFree(h->xdat); cudaFree(h->z0user);
+    cudaFree(h->x); cudaFree(h->zA); cudaFree(h->zB); cudaFree(h->zstate);
+    cudaFree(h->sbuf); cudaFree(h->dxh); cudaFree(h->dgh);
+    cudaFree(h->g_d); cudaFree(h->gnorm_d); cudaFree(h->f_d); cudaFree(h->iters_d); cudaFree(h->fg_d); cudaFree(h->status_d);
+    cudaFreeHost(h->g_h); cudaFreeHost(h->gnorm_h); cudaFreeHost(h->iters_h); cudaFreeHost(h->fg_h); cudaFreeHost(h->status_h);
+    cudaFree(h->xH); cudaFree(h->zHA); cudaFree(h->zHB);
+    cudaFree(h->xfid); cudaFree(h->zfidA); cudaFree(h->zfidB); cudaFree(h->zfid_state);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    cudaGetLastError();
+    delete h;
+    return MUSE_OK;
+}
+
+int muse_b200_set_stream(muse_handle* h, void* s) {
+    if (!h) return MUSE_EINVAL;
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (h->own_stream) { cudaStreamDestroy(h->stream); h->own_stream = false; }
+    if (s) {
+        h->stream = (cudaStream_t)s;
+    } else {
+        CUDA_TRY(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        h->own_stream = true;
+    }
+    return MUSE_OK;
+}
+
+int muse_b200_set_data(muse_handle* h, const double* x_dat) {
+    if (!h || !x_dat) return MUSE_EINVAL;
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    CUDA_TRY(h, cudaMemcpyAsync(h->xdat, x_dat, (size_t)h->cfg.d * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->have_data = true;
+    return MUSE_OK;
+}
+
+int muse_b200_set_z0(muse_handle* h, const double* z0) {
+    if (!h || !z0) return MUSE_EINVAL;
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    CUDA_TRY(h, cudaMemcpyAsync(h->z0user, z0, (size_t)h->cfg.d * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->have_z0 = true;
+    return MUSE_OK;
+}
+
+int muse_b200_set_draws(muse_handle* h, const double* xi, const double* nu, const double* xi_m, const double* nu_m) {
+    if (!h || !xi_m || !nu_m || (h->cfg.nsims > 0 && (!xi || !nu))) return MUSE_EINVAL;
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    const size_t w = (size_t)h->cfg.d * sizeof(double), pitch = (size_t)h->ld * sizeof(double);
+    const size_t n = (size_t)h->cfg.nsims;
+    if (n) {
+        CUDA_TRY(h, cudaMemcpy2DAsync(h->xi, pitch, xi, w, w, n, cudaMemcpyHostToDevice, h->stream));
+        CUDA_TRY(h, cudaMemcpy2DAsync(h->nu, pitch, nu, w, w, n, cudaMemcpyHostToDevice, h->stream));
+    }
+    CUDA_TRY(h, cudaMemcpyAsync(h->xi + n * h->ld, xi_m, w, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(h->nu + n * h->ld, nu_m, w, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->have_draws = true;
+    return MUSE_OK;
+}
+
+int muse_b200_seed_draws(muse_handle* h, uint64_t seed) {
+    if (!h) return MUSE_EINVAL;
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    muse_handle::Rec r{};
+    if (h->prof) {
+        CUDA_TRY(h, cudaEventCreate(&r.a));
+        CUDA_TRY(h, cudaEventCreate(&r.b));
+        CUDA_TRY(h, cudaEventRecord(r.a, h->stream));
+    }
+    CUDA_TRY(h, launch_philox_draws(h->xi, h->nu, h->cfg.nsims + 1, h->cfg.d, h->ld, seed, h->cfg.sim_offset,
+                                    h->cfg.nsims, h->stream));
+    h->acc.launches += 1;
+    h->acc.draw_launches += 1;
+    if (h->cfg.nsims_h > 0) {
+        CUDA_TRY(h, launch_philox_draws(h->xi_h, h->nu_h, h->cfg.nsims_h, h->cfg.d, h->ld, seed, h->cfg.h_sim_offset,
+                                        -1, h->stream));
+        h->acc.launches += 1;
+        h->acc.draw_launches += 1;
+        h->have_draws_h = true;
+    }
+    if (h->prof) {
+        CUDA_TRY(h, cudaEventRecord(r.b, h->stream));
+        r.cls = 1;
+        h->recs.push_back(r);
+    }
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->have_draws = true;
+    return MUSE_OK;
+}
+
+int muse_b200_set_draws_h(muse_handle* h, const double* xi_h, const double* nu_h) {
+    if (!h || !xi_h || !nu_h) return MUSE_EINVAL;
+    if (h->cfg.nsims_h <= 0) MUSE_FAIL(h, MUSE_ESTATE, "handle was created without a separate H shard (nsims_h = 0)");
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    const size_t w = (size_t)h->cfg.d * sizeof(double), pitch = (size_t)h->ld * sizeof(double);
+    CUDA_TRY(h, cudaMemcpy2DAsync(h->xi_h, pitch, xi_h, w, w, (size_t)h->cfg.nsims_h, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemcpy2DAsync(h->nu_h, pitch, nu_h, w, w, (size_t)h->cfg.nsims_h, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->have_draws_h = true;
+    return MUSE_OK;
+}
+
+int muse_b200_get_draws(muse_handle* h, int32_t first, int32_t count, double* xi_out, double* nu_out) {
+    if (!h || first < 0 || count < 0 || first + count > h->cfg.nsims + 1) return MUSE_EINVAL;
+    if (!h->have_draws) MUSE_FAIL(h, MUSE_ESTATE, "no draws installed (set_draws / seed_draws)");
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    const size_t w = (size_t)h->cfg.d * sizeof(double), pitch = (size_t)h->ld * sizeof(double);
+    if (count && xi_out)
+        CUDA_TRY(h, cudaMemcpy2DAsync(xi_out, w, h->xi + (size_t)first * h->ld, pitch, w, count, cudaMemcpyDeviceToHost, h->stream));
+    if (count && nu_out)
+        CUDA_TRY(h, cudaMemcpy2DAsync(nu_out, w, h->nu + (size_t)first * h->ld, pitch, w, count, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return MUSE_OK;
+}
+
+int muse_b200_map_score_async(muse_handle* h, const double* theta_sim, const double* theta_eval, double atol,
+                              int32_t include_data, int32_t warm_start, int32_t first_sim, int32_t count) {
+    if (!h || !theta_sim || !theta_eval) return MUSE_EINVAL;
+    if (first_sim < 0 || count < 0 || first_sim + count > h->cfg.nsims) MUSE_FAIL(h, MUSE_EINVAL, "sim range outside the handle's shard");
+    if (warm_start < MUSE_START_ZEROS || warm_start > MUSE_START_USER) MUSE_FAIL(h, MUSE_EINVAL, "bad warm_start");
+    if (include_data && !h->have_data) MUSE_FAIL(h, MUSE_ESTATE, "observed data not set (muse_b200_set_data)");
+    if (count > 0 && !h->have_draws) MUSE_FAIL(h, MUSE_ESTATE, "no draws installed (set_draws / seed_draws)");
+    if (warm_start == MUSE_START_USER && !h->have_z0) MUSE_FAIL(h, MUSE_ESTATE, "user z0 not set (muse_b200_set_z0)");
+    const int items = count + (include_data ? 1 : 0);
+    if (items == 0) return MUSE_OK;
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    SolveLaunch L;
+    fill_common(h, L);
+    L.nitems = items;
+    L.mode = 0;
+    L.include_data = include_data ? 1 : 0;
+    L.first_sim = first_sim;
+    L.atol = atol;
+    if (theta_consts(h->cfg, theta_sim, theta_eval, &L.smp[0], &L.ev) != 0) MUSE_FAIL(h, MUSE_EUNSUPPORTED, "family");
+    switch (warm_start) {
+        case MUSE_START_ZEROS: L.start_kind = kStartZero; break;
+        case MUSE_START_PREV: L.start_kind = kStartOwn; break;
+        case MUSE_START_TRUTH: L.start_kind = kStartTruth; break;
+        default: L.start_kind = kStartSharedKeep; L.zshared = h->z0user; break;
+    }
+    L.x = h->x;
+    L.zA = h->zA;
+    L.zB = h->zB;
+    L.zstate = h->zstate;
+    // algorithmic bytes: per sim read ξ, ν (16d) [+ z₀ 8d], write ẑ (8d); data unit reads x (8d)
+    const double d8 = 8.0 * h->cfg.d;
+    const double z0b = (warm_start == MUSE_START_PREV || warm_start == MUSE_START_USER) ? d8 : 0.0;
+    const double bytes = count * (3 * d8 + z0b) + (include_data ? (2 * d8 + z0b) : 0.0);
+    return launch_solver(h, L, bytes);
+}
+
+int muse_b200_fetch(muse_handle* h, int32_t units, double* g_out, int32_t* iters_out, int32_t* fg_out,
+                    double* gnorm_out, int32_t* status_out) {
+    if (!h || units < 0 || units > h->out_cap) return MUSE_EINVAL;
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    const size_t n = (size_t)units;
+    if (n) {
+        if (g_out) CUDA_TRY(h, cudaMemcpyAsync(h->g_h, h->g_d, n * h->cfg.ntheta * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        if (iters_out) CUDA_TRY(h, cudaMemcpyAsync(h->iters_h, h->iters_d, n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        if (fg_out) CUDA_TRY(h, cudaMemcpyAsync(h->fg_h, h->fg_d, n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        if (gnorm_out) CUDA_TRY(h, cudaMemcpyAsync(h->gnorm_h, h->gnorm_d, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        if (status_out) CUDA_TRY(h, cudaMemcpyAsync(h->status_h, h->status_d, n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    }
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (n) {
+        if (g_out && g_out != h->g_h) std::memcpy(g_out, h->g_h, n * h->cfg.ntheta * sizeof(double));
+        if (iters_out && iters_out != h->iters_h) std::memcpy(iters_out, h->iters_h, n * sizeof(int));
+        if (fg_out && fg_out != h->fg_h) std::memcpy(fg_out, h->fg_h, n * sizeof(int));
+        if (gnorm_out && gnorm_out != h->gnorm_h) std::memcpy(gnorm_out, h->gnorm_h, n * sizeof(double));
+        if (status_out && status_out != h->status_h) std::memcpy(status_out, h->status_h, n * sizeof(int));
+    }
+    return MUSE_OK;
+}
+
+int muse_b200_map_score(muse_handle* h, const double* theta_sim, const double* theta_eval, double atol,
+                        int32_t include_data, int32_t warm_start, int32_t first_sim, int32_t count, double* g_out,
+                        int32_t* iters_out, int32_t* fg_out, double* gnorm_out, int32_t* status_out) {
+    const int rc = muse_b200_map_score_async(h, theta_sim, theta_eval, atol, include_data, warm_start, first_sim, count);
+    if (rc != MUSE_OK) return rc;
+    return muse_b200_fetch(h, count + (include_data ? 1 : 0), g_out, iters_out, fg_out, gnorm_out, status_out);
+}
+
+int muse_b200_fd_jacobian(muse_handle* h, const double* theta0, const double* step, int32_t nsims_H, double atol,
+                          double* Hs_out, int32_t* status_out) {
+    if (!h || !theta0 || !step || !Hs_out) return MUSE_EINVAL;
+    const bool hshard = h->cfg.nsims_h > 0;
+    if (nsims_H < 0 || nsims_H > (hshard ? h->cfg.nsims_h : h->cfg.nsims)) MUSE_FAIL(h, MUSE_EINVAL, "nsims_H outside the handle's H shard");
+    if (!h->have_draws || (hshard && !h->have_draws_h)) MUSE_FAIL(h, MUSE_ESTATE, "no draws installed (set_draws[_h] / seed_draws)");
+    const int nt = h->cfg.ntheta;
+    for (int n = 0; n < nt; ++n)
+        if (!(step[n] != 0.0) || !std::isfinite(step[n])) MUSE_FAIL(h, MUSE_EINVAL, "finite-difference step must be finite and non-zero");
+    if (nsims_H == 0) return MUSE_OK;
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    const int items = nsims_H * nt * 2;
+    const size_t ld = (size_t)h->ld, B = sizeof(double);
+    if (items > h->h_cap) {
+        cudaFree(h->xH); cudaFree(h->zHA); cudaFree(h->zHB);
+        h->xH = h->zHA = h->zHB = nullptr;
+        h->h_cap = 0;
+        CUDA_TRY(h, cudaMalloc(&h->xH, (size_t)items * ld * B));
+        CUDA_TRY(h, cudaMalloc(&h->zHA, (size_t)items * ld * B));
+        CUDA_TRY(h, cudaMalloc(&h->zHB, (size_t)items * ld * B));
+        h->h_cap = items;
+    }
+    if (ensure_outputs(h, items) != 0) return MUSE_ECUDA;
+    const double d8 = 8.0 * h->cfg.d;
+
+    // (1) fiducial MAP of the master stream's draw from zero(z)   — src/muse.jl:417-423
+    SolveLaunch F;
+    fill_common(h, F);
+    F.nitems = 1;
+    F.mode = 2;
+    F.atol = atol;
+    F.start_kind = kStartZero;
+    if (theta_consts(h->cfg, theta0, theta0, &F.smp[0], &F.ev) != 0) MUSE_FAIL(h, MUSE_EUNSUPPORTED, "family");
+    F.x = h->xfid;
+    F.zA = h->zfidA;
+    F.zB = h->zfidB;
+    F.zstate = h->zfid_state;
+    CUDA_TRY(h, cudaMemsetAsync(h->zfid_state, 0, sizeof(int), h->stream));
+    int rc = launch_solver(h, F, 3 * d8);
+    if (rc != 0) return rc;
+    int fid_state = 0;
+    CUDA_TRY(h, cudaMemcpyAsync(&fid_state, h->zfid_state, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    const double* zfid = fid_state == kZA ? h->zfidA : (fid_state == kZB ? h->zfidB : nullptr);
+    if (!zfid) {   // converged at the zero start
+        CUDA_TRY(h, cudaMemsetAsync(h->zfidA, 0, ld * B, h->stream));
+        zfid = h->zfidA;
+    }
+
+    // (2) virtual sims at θ₀ ± h_n e_n, MAP + score at θ₀ from the fiducial start — src/muse.jl:426-433
+    SolveLaunch L;
+    fill_common(h, L);
+    L.nitems = items;
+    L.mode = 1;
+    L.atol = atol;
+    L.start_kind = kStartShared;
+    L.zshared = zfid;
+    if (hshard) { L.xi = h->xi_h; L.nu = h->nu_h; }
+    if (theta_consts(h->cfg, theta0, theta0, nullptr, &L.ev) != 0) MUSE_FAIL(h, MUSE_EUNSUPPORTED, "family");
+    for (int n = 0; n < nt; ++n) {
+        for (int s = 0; s < 2; ++s) {
+            double th[kMaxTheta];
+            for (int i = 0; i < nt; ++i) th[i] = theta0[i];
+            const double eps = 0.0 + step[n] * (s ? 1.0 : -1.0);     // x .+ step .* grid  [EXT FiniteDifferences]
+            th[n] = theta0[n] + eps;                                 // src/util.jl:15
+            theta_consts(h->cfg, th, theta0, &L.smp[2 * n + s], nullptr);
+        }
+    }
+    L.x = h->xH;
+    L.zA = h->zHA;
+    L.zB = h->zHB;
+    L.zstate = nullptr;
+    rc = launch_solver(h, L, items * 4 * d8);
+    if (rc != 0) return rc;
+    rc = muse_b200_fetch(h, items, h->g_h, nullptr, nullptr, nullptr, status_out ? h->status_h : nullptr);
+    if (rc != 0) return rc;
+    if (status_out) std::memcpy(status_out, h->status_h, (size_t)items * sizeof(int));
+    // (3) central_fdm(3,1): sum(fs .* [-1/2, 0, 1/2]) / step   — src/util.jl:13-19
+    for (int k = 0; k < nsims_H; ++k)
+        for (int n = 0; n < nt; ++n) {
+            const double* gm = h->g_h + ((size_t)(k * nt + n) * 2 + 0) * nt;
+            const double* gp = h->g_h + ((size_t)(k * nt + n) * 2 + 1) * nt;
+            for (int i = 0; i < nt; ++i) {
+                double acc = gm[i] * -0.5;
+                acc = acc + 0.0;
+                acc = acc + gp[i] * 0.5;
+                Hs_out[((size_t)k * nt + i) * nt + n] = acc / step[n];
+            }
+        }
+    return MUSE_OK;
+}
+
+int muse_b200_get_maps(muse_handle* h, int32_t first_unit, int32_t count, double* z_out) {
+    if (!h || !z_out || first_unit < 0 || count < 0 || first_unit + count > h->rows) return MUSE_EINVAL;
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    std::vector<int> st((size_t)count);
+    if (count) CUDA_TRY(h, cudaMemcpyAsync(st.data(), h->zstate + first_unit, (size_t)count * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    const size_t w = (size_t)h->cfg.d * sizeof(double);
+    for (int i = 0; i < count; ++i) {
+        double* dst = z_out + (size_t)i * h->cfg.d;
+        const size_t off = (size_t)(first_unit + i) * h->ld;
+        if (st[i] == kZA) CUDA_TRY(h, cudaMemcpyAsync(dst, h->zA + off, w, cudaMemcpyDeviceToHost, h->stream));
+        else if (st[i] == kZB) CUDA_TRY(h, cudaMemcpyAsync(dst, h->zB + off, w, cudaMemcpyDeviceToHost, h->stream));
+        else std::memset(dst, 0, w);
+    }
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return MUSE_OK;
+}
+
+int muse_b200_profile_reset(muse_handle* h, int32_t enable) {
+    if (!h) return MUSE_EINVAL;
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    for (auto& r : h->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    h->recs.clear();
+    h->acc = muse_profile{};
+    h->prof = enable != 0;
+    return MUSE_OK;
+}
+
+int muse_b200_profile_get(muse_handle* h, muse_profile* out) {
+    if (!h || !out) return MUSE_EINVAL;
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    for (auto& r : h->recs) {
+        float ms = 0.f;
+        CUDA_TRY(h, cudaEventElapsedTime(&ms, r.a, r.b));
+        if (r.cls == 0) { h->acc.solve_ms += ms; h->acc.solve_units += r.units; h->acc.solve_bytes += r.bytes; }
+        else if (r.cls == 1) h->acc.draw_ms += ms;
+        else { h->acc.other_ms += ms; }
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    h->recs.clear();
+    *out = h->acc;
+    return MUSE_OK;
+}
+
+int muse_b200_geometry(muse_handle* h, int32_t* group_threads, int32_t* cluster, int32_t* groups) {
+    if (!h) return MUSE_EINVAL;
+    if (group_threads) *group_threads = h->geo.group_threads;
+    if (cluster) *cluster = h->geo.cluster;
+    if (groups) *groups = h->geo.groups;
+    return MUSE_OK;
+}
+
+}  // extern "C"

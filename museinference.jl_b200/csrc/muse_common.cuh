@@ -1,0 +1,95 @@
+// muse_common.cuh — shared declarations of libmuse_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+#include "../../include/muse_b200.h"
+
+namespace muse {
+
+constexpr int kMaxTheta = MUSE_MAX_NTHETA;
+constexpr int kMaxThetaSim = 2 * MUSE_MAX_NTHETA + 1;   // θ_sim table: θ₀ and θ₀ ± h_n e_n
+
+// ---- isotropic-Gaussian-latent families (F1 funnel, F2 hierarchical Gaussian) ------------
+//   -logLike(x,z|θ) = ½ [ Σ (x-z)² + a Σ (z-μ)² ] + half_cst
+//   F1: a = e^{-θ},  μ = 0, half_cst = ½ d θ      (/root/reference/src/simple.jl:66-68)
+//   F2: a = e^{-2ℓ}, μ = μ, half_cst = d ℓ        
+struct IsoEval {
+    double a;
+    double mu;
+    double half_cst;
+};
+//   sample: z = mu + sig ξ,  x = z + ν            (src/simple.jl:61-65)
+struct IsoSample {
+    double sig;
+    double mu;
+};
+
+// where the start vector z₀ of a unit comes from
+enum StartKind : int {
+    kStartZero = 0,        // z₀ ≡ 0, never read from memory
+    kStartOwn = 1,         // the unit's current resident ẑ
+    kStartTruth = 2,       // the simulated latent (materialised into the unit's buffer A)
+    kStartShared = 3,      // one vector shared by all units (user z₀ / fiducial ẑ), read-only
+    kStartSharedKeep = 4,  // shared vector, materialised into buffer A so the unit keeps it
+};
+
+// which buffer holds a unit's resident ẑ
+enum ZState : int { kZZero = 0, kZA = 1, kZB = 2 };
+
+// One launch of the persistent solver.
+struct SolveLaunch {
+    int d;
+    int ld;              // row stride (doubles) of every N×d array
+    int ntheta;
+    int family;
+    int nitems;
+    int mode;            // 0: units (data? + sims), 1: finite-difference virtual sims
+    int include_data;    // mode 0
+    int first_sim;       // mode 0
+    int start_kind;      // StartKind
+    int lbfgs_m;
+    int max_iters;
+    double atol;
+    IsoEval ev;                      // at θ_eval
+    IsoSample smp[kMaxThetaSim];     // mode 0: [0]; mode 1: index 2n+s ↔ θ₀ ∓/± h_n e_n
+    // inputs
+    const double* xi;    // nsims+1 rows (row nsims = master draw)
+    const double* nu;
+    const double* xdat;  // d
+    const double* zshared;  // d (user z₀ or fiducial ẑ)
+    int master_row;      // row of the master draw in xi/nu
+    // per-unit resident state (mode 0 rows: unit index; mode 1 rows: item index in H scratch)
+    double* x;           // materialised x, rows × ld
+    double* zA;
+    double* zB;
+    int* zstate;         // rows
+    // per-slot scratch (L-BFGS history, search direction), one slot per resident group
+    double* sbuf;        // slots × ld
+    double* dxh;         // slots × m × ld
+    double* dgh;         // slots × m × ld
+    // outputs, indexed by item
+    double* g_out;       // nitems × ntheta
+    int* iters_out;
+    int* fg_out;
+    double* gnorm_out;
+    double* f_out;
+    int* status_out;
+};
+
+struct Geometry {
+    int group_threads;   // threads per CTA taking part in a solve (32 → one warp per solve)
+    int cta_threads;
+    int cluster;         // CTAs per cluster (≥1); group = cluster × cta when group_threads > 32
+    int groups;          // resident solve groups (= scratch slots)
+    int grid;            // CTAs launched
+};
+
+cudaError_t launch_iso_solver(const SolveLaunch& L, const Geometry& geo, cudaStream_t st);
+cudaError_t iso_solver_geometry(int d, int want_group, int want_cluster, int device, Geometry* geo);
+cudaError_t launch_philox_draws(double* xi, double* nu, int rows, int d, int ld, uint64_t seed,
+                                int64_t sim_offset, int master_row, cudaStream_t st);
+
+}  // namespace muse

@@ -1,0 +1,322 @@
+"""``muse`` / ``muse!`` / ``get_J!`` / ``get_H!`` / ``MuseResult`` on the B200 backend.
+
+Host-side mirror of /root/reference/src/muse.jl with the same names, keyword arguments, defaults
+and result fields; Python spells the in-place variants ``muse_``, ``get_J_``, ``get_H_`` (also
+reachable as ``getattr(module, "muse!")`` etc.).  The three mapped blocks of the reference
+(src/muse.jl:169-176, 417-442, 508-525) — everything that touches the N×d batch — are single calls
+into libmuse_b200 (``backend.map_score`` / ``backend.fd_jacobian``); what remains here is the
+O(nθ²) outer-solver arithmetic of src/muse.jl:159-166, 183-232, 411-413, 446, 529, 535-549, kept on
+the host exactly as in the reference.
+
+Keyword names: ASCII spellings are canonical, the reference's Unicode spellings are accepted too
+(``θ_rtol``, ``∇z_logLike_atol``, ``α``, ``z₀``, ``H⁻¹_like′``, ``H⁻¹_update``).
+"""
+from __future__ import annotations
+
+import math
+import pickle
+import time
+from dataclasses import dataclass, field
+from typing import Optional
+
+import numpy as np
+
+from . import _capi
+from .parallel import LocalPool
+from .problem import AbstractMuseProblem, BaseDraws, SimpleMuseProblem
+from ._capi import MuseBackendError
+
+_KW_ALIASES = {
+    "θ_rtol": "theta_rtol", "∇z_logLike_atol": "gradz_logLike_atol", "α": "alpha", "z₀": "z0",
+    "H⁻¹_like′": "H_inv_like", "H⁻¹_update": "H_inv_update", "θ₀": "theta0",
+}
+
+
+def _ascii_kwargs(kw: dict) -> dict:
+    return {_KW_ALIASES.get(k, k): v for k, v in kw.items()}
+
+
+@dataclass
+class MuseResult:
+    """src/muse.jl:29-42.  ``theta`` ↔ θ, ``Sigma``/``Sigma_inv`` ↔ Σ/Σ⁻¹, ``dist`` is the
+    (mean, covariance) of the Normal/MvNormal the reference builds (src/muse.jl:542-546)."""
+
+    theta: Optional[np.ndarray] = None
+    H: Optional[np.ndarray] = None
+    J: Optional[np.ndarray] = None
+    Sigma_inv: Optional[np.ndarray] = None
+    Sigma: Optional[np.ndarray] = None
+    dist: Optional[tuple] = None
+    history: list = field(default_factory=list)
+    gs: list = field(default_factory=list)
+    Hs: list = field(default_factory=list)
+    metadata: dict = field(default_factory=dict)
+    rng: object = None
+    time: float = 0.0
+
+    def __repr__(self):   # src/muse.jl:45-59
+        if self.theta is None:
+            return "MuseResult()"
+        if self.Sigma is not None:
+            sd = np.sqrt(np.diag(self.Sigma))
+            return "MuseResult(" + ", ".join(f"{t:.4g}±{s:.3g}" for t, s in zip(self.theta, sd)) + ")"
+        return "MuseResult(" + ", ".join(f"{t:.4g}" for t in self.theta) + ")"
+
+
+def _check_problem(prob):
+    if not isinstance(prob, SimpleMuseProblem):
+        raise MuseBackendError(-5, f"{type(prob).__name__} is not supported by the B200 backend: only "
+                                   "SimpleMuseProblem over a registered family (funnel, hiergauss, corrgauss); "
+                                   "Turing/Soss-defined models raise, there is no CPU fallback")
+
+
+def _check_status(out, what, skip_errors=False):
+    """src/interface.jl:168-171: non-convergence warns, a non-finite objective is an error."""
+    bad = np.flatnonzero(out["status"] == _capi.STATUS_NONFINITE)
+    if bad.size and not skip_errors:
+        raise FloatingPointError(f"{what}: MAP solution failed with a non-finite objective for unit(s) {bad[:8].tolist()}")
+    return bad
+
+
+# =============================================================================== muse
+def muse(prob, theta0, **kwargs):
+    """src/muse.jl:107."""
+    return muse_(MuseResult(), prob, theta0, **kwargs)
+
+
+def muse_(result: MuseResult, prob: AbstractMuseProblem, theta0=None, **kwargs):
+    """``muse!`` — src/muse.jl:112-250."""
+    kw = _ascii_kwargs(kwargs)
+    rng = kw.pop("rng", None)
+    z0 = kw.pop("z0", None)
+    maxsteps = kw.pop("maxsteps", 50)
+    theta_rtol = kw.pop("theta_rtol", 1e-1)
+    atol = kw.pop("gradz_logLike_atol", 1e-2)
+    nsims = kw.pop("nsims", 100)
+    alpha = kw.pop("alpha", 0.7)
+    kw.pop("progress", False)
+    pool = kw.pop("pool", None) or LocalPool()
+    regularize = kw.pop("regularize", None) or (lambda t: t)
+    H_inv_like = kw.pop("H_inv_like", None)
+    H_inv_update = kw.pop("H_inv_update", "sims")
+    broyden_memory = kw.pop("broyden_memory", math.inf)
+    checkpoint_filename = kw.pop("checkpoint_filename", None)
+    get_covariance = kw.pop("get_covariance", False)
+    save_MAPs = kw.pop("save_MAPs", False)
+    if kw:
+        raise TypeError(f"muse!: unknown keyword argument(s) {sorted(kw)}")
+    _check_problem(prob)
+
+    # :134  rng: given, else the result's, else a fresh default seed
+    if rng is None:
+        rng = result.rng if result.rng is not None else 0
+    result.rng = rng
+    # :135-136 (identity transform)
+    theta = prob.standardize_theta(result.theta if result.theta is not None else theta0)
+    theta_unreg = theta.copy()
+    history = result.history
+    alpha_fn = alpha if callable(alpha) else (lambda i: alpha)                     # :145-149
+
+    nh_total = max(1, nsims // 10) if get_covariance else 0
+    be = prob.backend_for(nsims, rng, pool, nh_total)
+    first_pass = True                                                              # :151 ẑs = zeros | z₀
+    if z0 is not None:
+        be.set_z0(z0)
+
+    for i in range(len(history) + 1, maxsteps + 1):                                # :159
+        t0 = time.perf_counter()
+        if i > 2:                                                                  # :163-166
+            dth = history[-1]["theta"] - history[-2]["theta"]
+            q = -(dth @ history[-1]["H_inv_post"] @ dth)
+            if q < 0:
+                raise ValueError("DomainError: sqrt of a negative number in the θ convergence test (src/muse.jl:165)")
+            if math.sqrt(q) < theta_rtol:
+                break
+
+        # MUSE gradient: the mapped block :169-176 is one backend call on this rank's shard
+        warm = (_capi.START_USER if z0 is not None else _capi.START_ZEROS) if first_pass else _capi.START_PREV
+        out = be.map_score(theta, theta, atol, include_data=True, warm_start=warm)
+        first_pass = False
+        _check_status(out, "muse!")
+        g_like_dat = out["g"][0].copy()                                            # :177
+        g_like_sims = pool.allgather_rows(out["g"][1:], nsims)                     # the one exchange step
+
+        g_like = g_like_dat - np.mean(g_like_sims, axis=0)                         # :183
+        g_prior = np.asarray(prob.prior.grad(theta), dtype=np.float64)             # :184
+        g_post = g_like + g_prior                                                  # :185
+
+        h_inv_like_sims = -1.0 / np.var(g_like_sims, axis=0, ddof=1)               # :188
+        H_inv_like_sims = np.diag(h_inv_like_sims)                                 # :189
+        if H_inv_like is None or H_inv_update == "sims":                           # :190-191
+            H_inv_like = H_inv_like_sims
+        elif i > 2 and H_inv_update in ("broyden", "diagonal_broyden"):            # :192-205
+            j0 = int(max(2, i - broyden_memory))
+            H_inv_like = history[j0 - 2]["H_inv_like_sims"]
+            for j in range(j0, i):
+                d_th = history[j - 1]["theta"] - history[j - 2]["theta"]
+                d_g = history[j - 1]["g_like"] - history[j - 2]["g_like"]
+                H_inv_like = H_inv_like + np.outer((d_th - H_inv_like @ d_g) / (d_th @ H_inv_like @ d_g), d_th) @ H_inv_like
+                if H_inv_update == "diagonal_broyden":
+                    H_inv_like = np.diag(np.diag(H_inv_like))
+
+        H_prior = np.asarray(prob.prior.hess(theta), dtype=np.float64)             # :207
+        H_inv_post = np.linalg.inv(np.linalg.inv(H_inv_like) + H_prior)            # :208
+
+        t = time.perf_counter() - t0
+        entry = dict(                                                              # :211-221
+            theta=theta.copy(), theta_unreg=theta_unreg.copy(),
+            g_like_sims=g_like_sims.copy(), g_like_dat=g_like_dat, g_like=g_like, g_prior=g_prior, g_post=g_post,
+            H_inv_post=H_inv_post, H_prior=H_prior, H_inv_like=np.array(H_inv_like, copy=True),
+            H_inv_like_sims=H_inv_like_sims,
+            z_history_dat=dict(iters=int(out["iters"][0]), fg_evals=int(out["fg_evals"][0]),
+                               gnorm=float(out["gnorm"][0]), status=int(out["status"][0])),
+            z_history_sims=dict(iters=out["iters"][1:].copy(), fg_evals=out["fg_evals"][1:].copy(),
+                                gnorm=out["gnorm"][1:].copy(), status=out["status"][1:].copy()),
+            t=t, z_dat=None, z_sims=None,
+        )
+        if save_MAPs:                                                              # :139-143, 219
+            keep = save_MAPs if callable(save_MAPs) else (lambda z: z)
+            entry["z_dat"] = keep(be.get_maps(0, 1)[0])
+            entry["z_sims"] = keep(be.get_maps(1, be.nsims))
+        history.append(entry)
+
+        theta_unreg = theta - alpha_fn(i) * (H_inv_post @ g_post)                  # :224
+        theta = prob.standardize_theta(regularize(theta_unreg))                    # :226-227
+
+        result.theta = theta_unreg.copy()                                          # :230
+        result.gs = [g.copy() for g in g_like_sims]                                # :231
+        result.time += t                                                           # :232
+        if checkpoint_filename is not None and pool.rank == 0:                     # :234
+            with open(checkpoint_filename, "wb") as fh:
+                pickle.dump(result, fh)
+
+    if get_covariance:                                                             # :244-247
+        get_J_(result, prob, rng=rng, nsims=nsims, gradz_logLike_atol=atol, pool=pool, _nh_total=nh_total)
+        get_H_(result, prob, rng=rng, nsims=max(1, nsims // 10), gradz_logLike_atol=atol, pool=pool, _nsims_total=nsims)
+    return result
+
+
+# =============================================================================== get_J!
+def get_J_(result: MuseResult, prob: AbstractMuseProblem, theta0=None, **kwargs):
+    """``get_J!`` — src/muse.jl:484-532."""
+    kw = _ascii_kwargs(kwargs)
+    z0 = kw.pop("z0", None)
+    atol = kw.pop("gradz_logLike_atol", 1e-2)
+    rng = kw.pop("rng", None)
+    nsims = kw.pop("nsims", 100)
+    pool = kw.pop("pool", None) or LocalPool()
+    kw.pop("progress", False)
+    skip_errors = kw.pop("skip_errors", False)
+    nh_total = kw.pop("_nh_total", 0)
+    if kw:
+        raise TypeError(f"get_J!: unknown keyword argument(s) {sorted(kw)}")
+    _check_problem(prob)
+    if rng is None:
+        rng = result.rng if result.rng is not None else 0
+    theta0 = prob.standardize_theta(theta0 if theta0 is not None else result.theta)   # :498
+    nsims_existing = len(result.gs)
+    nsims_remaining = nsims - nsims_existing                                       # :499-500
+    if nsims_remaining > 0:
+        # rngs = split_rng(rng, nsims)[nsims_existing+1:end]  (:506) → global sims [existing, nsims)
+        be = prob.backend_for(nsims, rng, pool, nh_total)
+        off, cnt = pool.shard(nsims)
+        lo = max(nsims_existing, off) - off
+        hi = cnt
+        n_local = max(0, hi - lo)
+        if z0 is not None:
+            be.set_z0(z0)
+        warm = _capi.START_USER if z0 is not None else _capi.START_TRUTH           # :511
+        out = be.map_score(theta0, theta0, atol, include_data=False, warm_start=warm, first_sim=lo, count=n_local)
+        bad = _check_status(out, "get_J!", skip_errors)
+        g_local = out["g"]
+        if pool.world == 1:
+            g_new = np.delete(g_local, bad, axis=0) if bad.size else g_local       # skipmissing (:508)
+        else:
+            # gather blocks of the *full* partition; ranks pad the part below nsims_existing with NaN rows
+            full = np.full((cnt, prob.ntheta), np.nan)
+            full[lo:] = g_local
+            if bad.size:
+                full[lo + bad] = np.nan
+            allg = pool.allgather_rows(full, nsims)[nsims_existing:]
+            g_new = allg[~np.isnan(allg).any(axis=1)]
+        result.gs.extend(g.copy() for g in g_new)
+    gs = np.array(result.gs)
+    if theta0.size == 1:
+        result.J = np.array([[np.var(gs[:, 0], ddof=1)]])                          # :529 var
+    else:
+        result.J = np.cov(gs, rowvar=False, ddof=1)                                # :529 cov(SimpleCovariance(corrected=true))
+    finalize_result_(result, prob)
+    return result
+
+
+# =============================================================================== get_H!
+def get_H_(result: MuseResult, prob: AbstractMuseProblem, theta0=None, **kwargs):
+    """``get_H!`` finite-difference branch — src/muse.jl:296-333, 407-450."""
+    kw = _ascii_kwargs(kwargs)
+    atol = kw.pop("gradz_logLike_atol", 1e-2)
+    rng = kw.pop("rng", None)
+    nsims = kw.pop("nsims", 10)
+    step = kw.pop("step", None)
+    pool = kw.pop("pool", None) or LocalPool()
+    kw.pop("pmap_over", None)
+    kw.pop("progress", False)
+    skip_errors = kw.pop("skip_errors", False)
+    z0 = kw.pop("z0", None)
+    nsims_total = kw.pop("_nsims_total", 0)
+    if kw.pop("implicit_diff", False):
+        raise MuseBackendError(-5, "implicit_diff=true (experimental in the reference, src/muse.jl:287, 335-405) "
+                                   "is not provided by the B200 backend")
+    if kw.pop("fdm", None) is not None:
+        raise MuseBackendError(-5, "only fdm = central_fdm(3,1) (the reference default, src/muse.jl:300) is provided")
+    if z0 is not None:
+        raise MuseBackendError(-5, "get_H!: a user z₀ is not supported; the fiducial start is zero(z) (src/muse.jl:419)")
+    if kw:
+        raise TypeError(f"get_H!: unknown keyword argument(s) {sorted(kw)}")
+    _check_problem(prob)
+    if rng is None:
+        rng = result.rng if result.rng is not None else 0
+    theta0 = prob.standardize_theta(theta0 if theta0 is not None else result.theta)   # :315
+    nsims_existing = len(result.Hs)
+    nsims_remaining = nsims - nsims_existing                                       # :317-319
+    if nsims_remaining <= 0:
+        return result
+    t0 = time.perf_counter()
+    if step is None and len(result.gs) > 0:                                        # :411-413
+        step = 0.1 / np.std(np.array(result.gs), axis=0, ddof=1)
+    if step is None:
+        raise MuseBackendError(-5, "get_H!: pass `step` or run get_J!/muse! first; FiniteDifferences' adaptive "
+                                   "step estimation is not provided")
+    step = prob.standardize_theta(step)
+
+    # rngs = split_rng(rng, nsims_remaining)  (:323): the first nsims_remaining child streams
+    n_total = max(nsims_total, nsims_remaining)
+    be = prob.backend_for(n_total, rng, pool, nsims_remaining)
+    _, hcnt = pool.shard(nsims_remaining)
+    Hs_local, status = be.fd_jacobian(theta0, step, hcnt, atol)                    # :417-442 + src/util.jl:9-26
+    bad_local = np.flatnonzero((status.reshape(hcnt, -1) == _capi.STATUS_NONFINITE).any(axis=1))
+    if bad_local.size and not skip_errors:
+        raise FloatingPointError("get_H!: MAP solution failed with a non-finite objective")
+    nt = prob.ntheta
+    flat = Hs_local.reshape(hcnt, nt * nt).copy()
+    if bad_local.size:
+        flat[bad_local] = np.nan
+    allH = pool.allgather_rows(flat, nsims_remaining)
+    allH = allH[~np.isnan(allH).any(axis=1)]
+    result.Hs.extend(h.reshape(nt, nt).copy() for h in allH)
+
+    result.H = np.mean(np.array(result.Hs), axis=0)                                # :446
+    result.time += time.perf_counter() - t0
+    finalize_result_(result, prob)
+    return result
+
+
+# =============================================================================== finalize_result!
+def finalize_result_(result: MuseResult, prob: AbstractMuseProblem):
+    """src/muse.jl:535-549."""
+    H, J, theta = result.H, result.J, result.theta
+    if H is not None and J is not None and theta is not None:
+        H_prior = -np.asarray(prob.prior.hess(theta), dtype=np.float64)            # :539
+        result.Sigma_inv = H.T @ np.linalg.inv(J) @ H + H_prior                    # :540
+        result.Sigma = np.linalg.inv(result.Sigma_inv)                             # :541
+        result.dist = (np.array(theta, copy=True), result.Sigma.copy())            # :542-546
+    return result

@@ -1,0 +1,154 @@
+"""Problem types of the B200 backend — the host-side mirror of the reference's problem interface.
+
+``AbstractMuseProblem`` (/root/reference/src/interface.jl:4) is the reference's extension point;
+``SimpleMuseProblem`` (src/simple.jl:4-12, 79-89) is the concrete type behind the registered
+families.  The reference stores Julia closures (``sample_x_z``, ``logLike``, AD gradients); a
+GPU backend cannot introspect closures, so the model is *named*: one of the registered families
+whose sampling rule, log-density and analytic ∇z / ∇θ are compiled into the CUDA kernels
+(csrc/muse_iso_solver.cu).  Anything else — in particular Turing/Soss-defined models
+(src/turing.jl, src/soss.jl) — raises ``MuseBackendError`` (EUNSUPPORTED); there is no generic /
+CPU path.
+
+θ-transforms are the identity for ``SimpleMuseProblem`` (src/interface.jl:20, 28, 134).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+from ._capi import MuseBackendError
+from .backend import B200Backend, FAMILY_NTHETA
+
+
+class AbstractMuseProblem:
+    """src/interface.jl:4."""
+
+
+# ----------------------------------------------------------------------------- priors (logPriorθ)
+class FlatPrior:
+    """``logPriorθ(θ) = 0`` — the default (src/interface.jl:121, src/simple.jl:79)."""
+
+    def logp(self, theta):
+        return 0.0
+
+    def grad(self, theta):
+        return np.zeros(np.size(theta))
+
+    def hess(self, theta):
+        return np.zeros((np.size(theta), np.size(theta)))
+
+
+class NormalPrior:
+    """Independent Normal(mean, sigma) per θ-component, e.g. the funnel's ``-θ^2/(2*3^2)``
+    (src/simple.jl:69-71).  Gradient and Hessian are analytic (the reference uses ForwardDiff,
+    src/muse.jl:184, 207, 539)."""
+
+    def __init__(self, mean=0.0, sigma=3.0):
+        self.mean, self.sigma = mean, sigma
+
+    def _ms(self, theta):
+        t = np.atleast_1d(np.asarray(theta, dtype=np.float64))
+        return t, np.broadcast_to(np.asarray(self.mean, dtype=np.float64), t.shape), \
+            np.broadcast_to(np.asarray(self.sigma, dtype=np.float64), t.shape)
+
+    def logp(self, theta):
+        t, m, s = self._ms(theta)
+        return float(-np.sum((t - m) ** 2 / (2.0 * s ** 2)))
+
+    def grad(self, theta):
+        t, m, s = self._ms(theta)
+        return -(t - m) / s ** 2
+
+    def hess(self, theta):
+        t, m, s = self._ms(theta)
+        return np.diag(-1.0 / s ** 2)
+
+
+# ----------------------------------------------------------------------------- base normals
+@dataclass
+class BaseDraws:
+    """Explicit base normals (parity mode): row k of ``xi`` / ``nu`` are the latent / noise
+    normals of child stream k; ``xi_master`` / ``nu_master`` the master stream's own draw.
+    Stands in for the ``rng`` keyword (src/muse.jl:116, 134; split semantics src/util.jl:85-92)."""
+
+    xi: np.ndarray
+    nu: np.ndarray
+    xi_master: np.ndarray
+    nu_master: np.ndarray
+
+
+# ----------------------------------------------------------------------------- problem
+class SimpleMuseProblem(AbstractMuseProblem):
+    """``SimpleMuseProblem(x, family; logPriorθ)`` for a registered family.
+
+    Parameters
+    ----------
+    x        observed data, length d            (``prob.x``, src/simple.jl:5)
+    family   "funnel" | "hiergauss" | "corrgauss"
+    prior    object with ``logp/grad/hess`` (``logPriorθ``); default flat
+    group, cluster   solver geometry overrides (0 = auto), see DESIGN.md §3
+    """
+
+    def __init__(self, x, family: str = "funnel", prior=None, *, P=None, L=None, group: int = 0,
+                 cluster: int = 0, backend_factory=None):
+        if family not in FAMILY_NTHETA:
+            raise MuseBackendError(-5, f"model family {family!r} is not registered with the B200 backend; "
+                                       "Turing/Soss-defined models are not supported and there is no CPU fallback")
+        self.x = np.ascontiguousarray(x, dtype=np.float64)
+        if self.x.ndim != 1:
+            raise ValueError("x must be a vector")
+        self.family = family
+        self.d = self.x.size
+        self.ntheta = FAMILY_NTHETA[family]
+        self.prior = prior or FlatPrior()
+        self.P, self.L = P, L
+        self.group, self.cluster = group, cluster
+        self._backend_factory = backend_factory or B200Backend
+        self._backend = None
+        self._backend_key = None
+
+    # src/interface.jl:134
+    def standardize_theta(self, theta):
+        t = np.atleast_1d(np.asarray(theta, dtype=np.float64)).copy()
+        if t.shape != (self.ntheta,):
+            raise ValueError(f"θ must have {self.ntheta} component(s) for family {self.family!r}")
+        return t
+
+    def logPrior(self, theta):
+        return self.prior.logp(theta)
+
+    # ------------------------------------------------------------------ backend management
+    def backend_for(self, nsims_total: int, rng, pool, nsims_h_total: int = 0):
+        """Handle holding this rank's shard of ``nsims_total`` sims (and of the first
+        ``nsims_h_total`` sims for get_H!) with the draws of ``rng`` installed."""
+        off, cnt = pool.shard(nsims_total)
+        hoff, hcnt = pool.shard(nsims_h_total) if (pool.world > 1 and nsims_h_total > 0) else (0, 0)
+        key = (nsims_total, off, cnt, hoff, hcnt, id(rng) if not isinstance(rng, (int, np.integer)) else int(rng),
+               pool.device)
+        if self._backend is not None and self._backend_key == key:
+            return self._backend
+        if self._backend is not None:
+            self._backend.close()
+        be = self._backend_factory(self.family, self.d, cnt, sim_offset=off, nsims_h=hcnt, h_sim_offset=hoff,
+                                   device=pool.device, group=self.group, cluster=self.cluster, P=self.P, L=self.L)
+        be.set_data(self.x)
+        if isinstance(rng, (int, np.integer)):
+            be.seed_draws(int(rng))
+        elif isinstance(rng, BaseDraws):
+            if rng.xi.shape[0] < nsims_total:
+                raise ValueError("BaseDraws holds fewer simulations than requested")
+            be.set_draws(rng.xi[off:off + cnt], rng.nu[off:off + cnt], rng.xi_master, rng.nu_master)
+            if hcnt:
+                be.set_draws_h(rng.xi[hoff:hoff + hcnt], rng.nu[hoff:hoff + hcnt])
+        else:
+            raise TypeError("rng must be an integer seed or a BaseDraws")
+        self._backend, self._backend_key = be, key
+        return be
+
+    def close(self):
+        if self._backend is not None:
+            self._backend.close()
+            self._backend = None
+            self._backend_key = None

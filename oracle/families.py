@@ -1,0 +1,155 @@
+"""Registered model families (oracle side; TEST INFRASTRUCTURE ONLY, see oracle/__init__.py).
+
+Each family supplies what a ``SimpleMuseProblem`` holds as closures
+(/root/reference/src/simple.jl:4-12, 79-95): ``sample_x_z``, ``logLike``,
+``∇θ_logLike`` and ``logLike_and_∇z_logLike``.  The reference obtains the two
+gradients by automatic differentiation of ``logLike`` (src/simple.jl:84-85); here they
+are the analytic derivatives of the same expression, checked against central
+differences in tests/test_oracle_families.py.
+
+F1  Neal's funnel             /root/reference/src/simple.jl:58-76, docs/src/index.md:154-168
+F2  hierarchical Gaussian     SURVEY.md §8(a) row F2 (BASELINE.json config 4; not in the reference)
+F3  dense correlated Gaussian SURVEY.md §8(a) row F3 (BASELINE.json config 5; not in the reference)
+
+Sampling is expressed on *base normals* (ξ, ν) so that common-random-number semantics
+(src/util.jl:85-92) are explicit: the latent draws come first, then the noise draws
+(src/simple.jl:62-63).
+
+All functions minimise  f(z) = -logLike(x, z, θ)  exactly as the default ``ẑ_at_θ`` does
+(src/interface.jl:163: ``z -> .-logLike_and_∇z_logLike(prob, x, z, θ)``).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+class Funnel:
+    """F1: z ~ N(0, e^θ I_d), x ~ N(z, I_d); scalar θ."""
+
+    name = "funnel"
+    family_id = 1
+    ntheta = 1
+
+    def __init__(self, d: int):
+        self.d = int(d)
+
+    # src/simple.jl:61-65
+    def sample(self, theta, xi, nu):
+        th = float(np.asarray(theta).reshape(-1)[0])
+        z = np.exp(0.5 * th) * xi
+        x = z + nu
+        return x, z
+
+    # src/simple.jl:66-68:  -(1//2) * (sum((x .- z).^2) + sum(z.^2) / exp(θ) + d*θ)
+    def neg_loglike(self, x, z, theta):
+        th = float(np.asarray(theta).reshape(-1)[0])
+        r = x - z
+        return 0.5 * (np.dot(r, r) + np.dot(z, z) / np.exp(th) + self.d * th)
+
+    def neg_loglike_and_grad(self, x, z, theta):
+        th = float(np.asarray(theta).reshape(-1)[0])
+        a = np.exp(-th)
+        r = x - z
+        f = 0.5 * (np.dot(r, r) + a * np.dot(z, z) + self.d * th)
+        g = -r + a * z
+        return f, g
+
+    # ∇θ logLike = ½ e^{-θ} Σ z² − d/2
+    def score(self, x, z, theta):
+        th = float(np.asarray(theta).reshape(-1)[0])
+        return np.array([0.5 * np.exp(-th) * np.dot(z, z) - 0.5 * self.d])
+
+    def exact_map(self, x, theta):
+        th = float(np.asarray(theta).reshape(-1)[0])
+        return x / (1.0 + np.exp(-th))
+
+
+class HierGauss:
+    """F2: z ~ N(μ, e^{2ℓ} I_d), x ~ N(z, I_d); θ = (μ, ℓ = log σ)."""
+
+    name = "hiergauss"
+    family_id = 2
+    ntheta = 2
+
+    def __init__(self, d: int):
+        self.d = int(d)
+
+    def sample(self, theta, xi, nu):
+        mu, ell = (float(t) for t in np.asarray(theta).reshape(-1))
+        z = mu + np.exp(ell) * xi
+        x = z + nu
+        return x, z
+
+    def neg_loglike(self, x, z, theta):
+        return self.neg_loglike_and_grad(x, z, theta)[0]
+
+    def neg_loglike_and_grad(self, x, z, theta):
+        mu, ell = (float(t) for t in np.asarray(theta).reshape(-1))
+        a = np.exp(-2.0 * ell)
+        r = x - z
+        w = z - mu
+        f = 0.5 * (np.dot(r, r) + a * np.dot(w, w) + 2.0 * self.d * ell)
+        g = -r + a * w
+        return f, g
+
+    def score(self, x, z, theta):
+        mu, ell = (float(t) for t in np.asarray(theta).reshape(-1))
+        a = np.exp(-2.0 * ell)
+        w = z - mu
+        return np.array([a * np.sum(w), a * np.dot(w, w) - self.d])
+
+    def exact_map(self, x, theta):
+        mu, ell = (float(t) for t in np.asarray(theta).reshape(-1))
+        a = np.exp(-2.0 * ell)
+        return (x + mu * a) / (1.0 + a)
+
+
+class CorrGauss:
+    """F3: z ~ N(0, e^θ Σ₀), x ~ N(z, I_d); scalar θ; P = Σ₀⁻¹ and L = chol(Σ₀) are inputs."""
+
+    name = "corrgauss"
+    family_id = 3
+    ntheta = 1
+
+    def __init__(self, d: int, P: np.ndarray, L: np.ndarray):
+        self.d = int(d)
+        self.P = np.ascontiguousarray(P, dtype=np.float64)
+        self.L = np.ascontiguousarray(L, dtype=np.float64)
+        assert self.P.shape == (d, d) and self.L.shape == (d, d)
+
+    def sample(self, theta, xi, nu):
+        th = float(np.asarray(theta).reshape(-1)[0])
+        z = np.exp(0.5 * th) * (self.L @ xi)
+        x = z + nu
+        return x, z
+
+    def neg_loglike(self, x, z, theta):
+        return self.neg_loglike_and_grad(x, z, theta)[0]
+
+    def neg_loglike_and_grad(self, x, z, theta):
+        th = float(np.asarray(theta).reshape(-1)[0])
+        a = np.exp(-th)
+        r = x - z
+        Pz = self.P @ z
+        f = 0.5 * (np.dot(r, r) + a * np.dot(z, Pz) + self.d * th)
+        g = -r + a * Pz
+        return f, g
+
+    def score(self, x, z, theta):
+        th = float(np.asarray(theta).reshape(-1)[0])
+        return np.array([0.5 * np.exp(-th) * np.dot(z, self.P @ z) - 0.5 * self.d])
+
+    def exact_map(self, x, theta):
+        th = float(np.asarray(theta).reshape(-1)[0])
+        A = np.eye(self.d) + np.exp(-th) * self.P
+        return np.linalg.solve(A, x)
+
+
+def make_family(name: str, d: int, **consts):
+    if name == "funnel":
+        return Funnel(d)
+    if name == "hiergauss":
+        return HierGauss(d)
+    if name == "corrgauss":
+        return CorrGauss(d, consts["P"], consts["L"])
+    raise ValueError(f"unknown family {name!r}")

@@ -1,0 +1,352 @@
+"""MUSE outer solver + covariance (oracle side; TEST INFRASTRUCTURE ONLY).
+
+Line-by-line NumPy restatement of
+
+    muse!             /root/reference/src/muse.jl:112-250
+    get_H! (FD path)  /root/reference/src/muse.jl:296-333, 407-450
+    get_J!            /root/reference/src/muse.jl:484-532
+    finalize_result!  /root/reference/src/muse.jl:535-549
+    pjacobian         /root/reference/src/util.jl:9-26
+    split_rng         /root/reference/src/util.jl:85-92   (semantics: sim k ↔ fixed base normals)
+
+Differences from the reference that are *representation only*:
+  * θ is always a 1-D float64 array (length nθ); "θ isa Number" branches of the reference
+    (src/muse.jl:189, 446, 529) are selected by ``nθ == 1`` and give identical numbers.
+  * RNG objects are replaced by ``Draws`` (base normals ξ_k, ν_k per sim plus the master
+    stream's own draw), see oracle/__init__.py.
+  * Prior gradient / Hessian come from a prior object with analytic derivatives instead of
+    ForwardDiff (src/muse.jl:184, 207, 539).
+  * θ-transforms are the identity (true of SimpleMuseProblem, src/interface.jl:20, 28), so the
+    primed and unprimed quantities coincide; both names are kept in the history for clarity.
+
+Quirks reproduced on purpose:
+  * convergence test ``sqrt(-(Δθ' H⁻¹_post Δθ)) < θ_rtol`` uses the *inverse* Hessian (:165);
+  * ``result.gs`` are the scores at the θ *before* the last update (:231);
+  * ``get_J!`` after ``muse!`` with the same nsims runs no new sims (:499-502);
+  * ``get_H!``'s fiducial solves all use the master stream's own draw because the closure
+    argument shadows nothing (``rngs`` vs ``rng``, :417-418), start from ``zero(z)`` (:419,
+    src/interface.jl:184-186) and only serve as start points;
+  * ``get_H!`` re-splits from the start on resume (:323), unlike ``get_J!`` (:506);
+  * central_fdm(3,1) with an explicit step evaluates the centre point and multiplies it by 0.
+"""
+from __future__ import annotations
+
+import math
+import time
+from dataclasses import dataclass, field
+from typing import Callable, Optional
+
+import numpy as np
+
+from .lbfgs import lbfgs_minimize
+from .philox import philox_normals, MASTER_INDEX
+
+
+# ----------------------------------------------------------------------------- priors
+class FlatPrior:
+    """logPriorθ ≡ 0 (reference default, src/interface.jl:121)."""
+
+    def logp(self, theta):
+        return 0.0
+
+    def grad(self, theta):
+        return np.zeros_like(np.asarray(theta, dtype=np.float64))
+
+    def hess(self, theta):
+        n = np.asarray(theta).size
+        return np.zeros((n, n))
+
+
+class NormalPrior:
+    """Independent N(mean, sigma) per component; the funnel example uses N(0, 3)
+    (src/simple.jl:69-71: ``-θ^2/(2*3^2)``)."""
+
+    def __init__(self, mean=0.0, sigma=3.0):
+        self.mean = mean
+        self.sigma = sigma
+
+    def logp(self, theta):
+        t = np.asarray(theta, dtype=np.float64)
+        return float(-np.sum((t - self.mean) ** 2 / (2 * np.asarray(self.sigma) ** 2)))
+
+    def grad(self, theta):
+        t = np.asarray(theta, dtype=np.float64)
+        return -(t - self.mean) / np.asarray(self.sigma) ** 2
+
+    def hess(self, theta):
+        t = np.asarray(theta, dtype=np.float64)
+        return np.diag(np.broadcast_to(-1.0 / np.asarray(self.sigma, dtype=np.float64) ** 2, t.shape).copy())
+
+
+# ----------------------------------------------------------------------------- draws
+@dataclass
+class Draws:
+    """Base normals: row k of ``xi``/``nu`` belongs to child stream k (0-based);
+    ``xi_master``/``nu_master`` is the master stream's own draw."""
+
+    xi: np.ndarray
+    nu: np.ndarray
+    xi_master: np.ndarray
+    nu_master: np.ndarray
+
+    @property
+    def nsims(self):
+        return self.xi.shape[0]
+
+    @staticmethod
+    def from_philox(seed: int, nsims: int, d: int, offset: int = 0) -> "Draws":
+        xi = np.stack([philox_normals(seed, offset + k, 0, d) for k in range(nsims)]) if nsims else np.zeros((0, d))
+        nu = np.stack([philox_normals(seed, offset + k, 1, d) for k in range(nsims)]) if nsims else np.zeros((0, d))
+        return Draws(xi, nu, philox_normals(seed, MASTER_INDEX, 0, d), philox_normals(seed, MASTER_INDEX, 1, d))
+
+    @staticmethod
+    def from_numpy(seed: int, nsims: int, d: int) -> "Draws":
+        rng = np.random.Generator(np.random.Philox(seed))
+        xi = rng.standard_normal((nsims, d))
+        nu = rng.standard_normal((nsims, d))
+        return Draws(xi, nu, rng.standard_normal(d), rng.standard_normal(d))
+
+
+# ----------------------------------------------------------------------------- problem
+class OracleProblem:
+    """Plays the role of ``SimpleMuseProblem`` (src/simple.jl:4-12) for a registered family."""
+
+    def __init__(self, family, x, draws: Draws, prior=None):
+        self.family = family
+        self.x = np.asarray(x, dtype=np.float64)
+        self.draws = draws
+        self.prior = prior or FlatPrior()
+
+    # sample_x_z(prob, rng_k, θ)  — src/simple.jl:95
+    def sample_x_z(self, k, theta):
+        if k == "master":
+            return self.family.sample(theta, self.draws.xi_master, self.draws.nu_master)
+        return self.family.sample(theta, self.draws.xi[k], self.draws.nu[k])
+
+    # ẑ_at_θ  — src/interface.jl:162-166
+    def z_at_theta(self, x, z0, theta, atol):
+        soln = lbfgs_minimize(lambda z: self.family.neg_loglike_and_grad(x, z, theta), z0, g_tol=atol)
+        return soln.minimizer, soln
+
+    # ∇θ_logLike  — src/simple.jl:92
+    def grad_theta(self, x, z, theta):
+        return self.family.score(x, z, theta)
+
+    # ẑ_guess_from_truth — src/interface.jl:184-186
+    def z_guess_from_truth(self, x, z, theta):
+        return np.zeros_like(z)
+
+
+def map_score_unit(prob: OracleProblem, x, z0, theta, atol):
+    """Body of the mapped block src/muse.jl:170-175 for one unit."""
+    zhat, soln = prob.z_at_theta(x, z0, theta, atol)
+    g = prob.grad_theta(x, zhat, theta)
+    return zhat, g, soln
+
+
+# ----------------------------------------------------------------------------- result
+@dataclass
+class MuseResult:
+    """src/muse.jl:29-42."""
+
+    theta: Optional[np.ndarray] = None
+    H: Optional[np.ndarray] = None
+    J: Optional[np.ndarray] = None
+    Sigma_inv: Optional[np.ndarray] = None
+    Sigma: Optional[np.ndarray] = None
+    dist: Optional[tuple] = None        # (mean vector, covariance matrix)
+    history: list = field(default_factory=list)
+    gs: list = field(default_factory=list)
+    Hs: list = field(default_factory=list)
+    metadata: dict = field(default_factory=dict)
+    time: float = 0.0
+
+
+def _var_corrected(rows: np.ndarray) -> np.ndarray:
+    """Elementwise ``var`` with N-1 (Statistics.var of a vector of vectors)."""
+    return np.var(rows, axis=0, ddof=1)
+
+
+# ----------------------------------------------------------------------------- muse!
+def muse(prob, theta0, **kw):
+    """src/muse.jl:107."""
+    return muse_bang(MuseResult(), prob, theta0, **kw)
+
+
+def muse_bang(result: MuseResult, prob: OracleProblem, theta0=None, *, z0=None, maxsteps=50,
+              theta_rtol=1e-1, gradz_logLike_atol=1e-2, nsims=100, alpha=0.7,
+              regularize: Callable = lambda t: t, H_inv_like=None, H_inv_update="sims",
+              broyden_memory=math.inf, get_covariance=False, save_MAPs=False):
+    # :135-136
+    theta = np.atleast_1d(np.asarray(result.theta if result.theta is not None else theta0, dtype=np.float64)).copy()
+    theta_unreg = theta.copy()
+    history = result.history
+    ntheta = theta.size
+    alpha_fn = alpha if callable(alpha) else (lambda i, _a=alpha: _a)   # :145-149
+
+    # :151  (one throw-away sample from the master stream, only for the shape)
+    zshape = prob.sample_x_z("master", theta)[1]
+    zs = [np.array(z0, dtype=np.float64, copy=True) if z0 is not None else np.zeros_like(zshape)
+          for _ in range(nsims + 1)]
+
+    for i in range(len(history) + 1, maxsteps + 1):                       # :159
+        t0 = time.perf_counter()
+        if i > 2:                                                         # :163-166
+            dth = history[-1]["theta"] - history[-2]["theta"]
+            q = -(dth @ history[-1]["H_inv_post"] @ dth)
+            if q < 0:
+                raise ValueError("sqrt of a negative number in the θ convergence test (DomainError in the reference)")
+            if math.sqrt(q) < theta_rtol:
+                break
+
+        # MUSE gradient  :169-176  (unit 0 = data, units 1..nsims = sims)
+        gs_all, zs_new, hists = [], [], []
+        for u in range(nsims + 1):
+            x = prob.x if u == 0 else prob.sample_x_z(u - 1, theta)[0]
+            zhat, g, soln = map_score_unit(prob, x, zs[u], theta, gradz_logLike_atol)
+            gs_all.append(g)
+            zs_new.append(zhat)
+            hists.append(soln)
+        g_like_dat = gs_all[0]
+        g_like_sims = np.array(gs_all[1:])                                # :177-180
+        zs = zs_new                                                       # :181
+
+        g_like = g_like_dat - np.mean(g_like_sims, axis=0)                # :183
+        g_prior = prob.prior.grad(theta)                                  # :184
+        g_post = g_like + g_prior                                         # :185
+
+        h_inv_like_sims = -1.0 / _var_corrected(g_like_sims)              # :188
+        H_inv_like_sims = np.diag(h_inv_like_sims)                        # :189
+        if H_inv_like is None or H_inv_update == "sims":                  # :190-191
+            H_inv_like = H_inv_like_sims
+        elif i > 2 and H_inv_update in ("broyden", "diagonal_broyden"):   # :192-205
+            j0 = int(max(2, i - broyden_memory))
+            H_inv_like = history[j0 - 2]["H_inv_like_sims"]
+            for j in range(j0, i):
+                dth = history[j - 1]["theta"] - history[j - 2]["theta"]
+                dgl = history[j - 1]["g_like"] - history[j - 2]["g_like"]
+                H_inv_like = H_inv_like + np.outer((dth - H_inv_like @ dgl) / (dth @ H_inv_like @ dgl), dth) @ H_inv_like
+                if H_inv_update == "diagonal_broyden":
+                    H_inv_like = np.diag(np.diag(H_inv_like))
+
+        H_prior = prob.prior.hess(theta)                                  # :207
+        H_inv_post = np.linalg.inv(np.linalg.inv(H_inv_like) + H_prior)   # :208
+
+        t = time.perf_counter() - t0
+        history.append(dict(                                              # :211-221
+            theta=theta.copy(), theta_unreg=theta_unreg.copy(),
+            g_like_sims=g_like_sims.copy(), g_like_dat=g_like_dat.copy(), g_like=g_like.copy(),
+            g_prior=g_prior.copy(), g_post=g_post.copy(),
+            H_inv_post=H_inv_post.copy(), H_prior=H_prior.copy(), H_inv_like=H_inv_like.copy(),
+            H_inv_like_sims=H_inv_like_sims.copy(),
+            z_history_dat=hists[0], z_history_sims=hists[1:], t=t,
+            z_dat=zs[0].copy() if save_MAPs else None,
+            z_sims=[z.copy() for z in zs[1:]] if save_MAPs else None,
+        ))
+
+        theta_unreg = theta - alpha_fn(i) * (H_inv_post @ g_post)         # :224
+        theta = np.atleast_1d(np.asarray(regularize(theta_unreg), dtype=np.float64))   # :226-227
+
+        result.theta = theta_unreg.copy()                                 # :230
+        result.gs = [g.copy() for g in g_like_sims]                       # :231
+        result.time += t                                                  # :232
+
+    if get_covariance:                                                    # :244-247
+        get_J_bang(result, prob, nsims=nsims, gradz_logLike_atol=gradz_logLike_atol)
+        get_H_bang(result, prob, nsims=max(1, nsims // 10), gradz_logLike_atol=gradz_logLike_atol)
+    return result
+
+
+# ----------------------------------------------------------------------------- get_J!
+def get_J_bang(result: MuseResult, prob: OracleProblem, theta0=None, *, z0=None,
+               gradz_logLike_atol=1e-2, nsims=100):
+    theta0 = np.atleast_1d(np.asarray(theta0 if theta0 is not None else result.theta, dtype=np.float64))   # :498
+    nsims_existing = len(result.gs)
+    nsims_remaining = nsims - nsims_existing
+    if nsims_remaining > 0:
+        for k in range(nsims_existing, nsims):                            # :506 rngs[nsims_existing+1:end]
+            x, z = prob.sample_x_z(k, theta0)                             # :510
+            zstart = np.array(z0, dtype=np.float64) if z0 is not None else z   # :511
+            _, g, _ = map_score_unit(prob, x, zstart, theta0, gradz_logLike_atol)   # :512-513
+            result.gs.append(g)
+    gs = np.array(result.gs)
+    if theta0.size == 1:
+        result.J = np.array([[np.var(gs[:, 0], ddof=1)]])                 # :529 var
+    else:
+        result.J = np.cov(gs, rowvar=False, ddof=1)                       # :529 cov(SimpleCovariance(corrected=true))
+    finalize_result_bang(result, prob)
+    return result
+
+
+# ----------------------------------------------------------------------------- get_H!
+def pjacobian(f, theta0, step):
+    """src/util.jl:9-26 with fdm = central_fdm(3,1) and an explicit step per component.
+    [EXT FiniteDifferences 0.12] grid = [-1, 0, 1], coefs = [-1/2, 0, 1/2]; with an explicit
+    step the estimate is ``sum(fs .* coefs) / step`` where fs = f.(0 .+ step .* grid)."""
+    x = np.array(theta0, dtype=np.float64, copy=True)
+    cols = []
+    grid = (-1.0, 0.0, 1.0)
+    coefs = (-0.5, 0.0, 0.5)
+    for n in range(x.size):
+        h = float(step[n])
+        fs = []
+        for gpt in grid:
+            eps = 0.0 + h * gpt
+            xn = x[n]
+            x[n] = xn + eps
+            fs.append(np.array(f(x.copy()), dtype=np.float64, copy=True))
+            x[n] = xn
+        acc = fs[0] * coefs[0]
+        acc = acc + fs[1] * coefs[1]
+        acc = acc + fs[2] * coefs[2]
+        cols.append(acc / h)
+    return np.stack(cols, axis=1)
+
+
+def get_H_bang(result: MuseResult, prob: OracleProblem, theta0=None, *, gradz_logLike_atol=1e-2,
+               nsims=10, step=None, z0=None):
+    theta0 = np.atleast_1d(np.asarray(theta0 if theta0 is not None else result.theta, dtype=np.float64))   # :315
+    nsims_existing = len(result.Hs)
+    nsims_remaining = nsims - nsims_existing
+    if nsims_remaining <= 0:
+        return result
+    t0 = time.perf_counter()
+    ks = list(range(nsims_remaining))                                     # :323 split_rng(rng, nsims_remaining)
+
+    if step is None and len(result.gs) > 0:                               # :411-413
+        step = 0.1 / np.std(np.array(result.gs), axis=0, ddof=1)
+    if step is None:
+        raise ValueError("oracle: adaptive FiniteDifferences step not restated; pass `step` or run get_J! first")
+    step = np.atleast_1d(np.asarray(step, dtype=np.float64))
+
+    # fiducial MAPs  :417-423  (every one is the MAP of the master stream's own draw)
+    zfids = []
+    for _ in ks:
+        x, z = prob.sample_x_z("master", theta0)
+        zstart = np.array(z0, dtype=np.float64) if z0 is not None else prob.z_guess_from_truth(x, z, theta0)
+        zfid, _ = prob.z_at_theta(x, zstart, theta0, gradz_logLike_atol)
+        zfids.append(zfid)
+
+    # FD Jacobian per sim  :426-433
+    for zfid, k in zip(zfids, ks):
+        def f(theta, _k=k, _z=zfid):
+            x, _ = prob.sample_x_z(_k, theta)                             # sim generated at θ
+            zhat, _ = prob.z_at_theta(x, _z, theta0, gradz_logLike_atol)  # MAP at fiducial θ₀
+            return prob.grad_theta(x, zhat, theta0)                       # score at fiducial θ₀
+        result.Hs.append(pjacobian(f, theta0, step))
+
+    result.H = np.mean(np.array(result.Hs), axis=0)                       # :446
+    result.time += time.perf_counter() - t0
+    finalize_result_bang(result, prob)
+    return result
+
+
+# ----------------------------------------------------------------------------- finalize_result!
+def finalize_result_bang(result: MuseResult, prob: OracleProblem):
+    H, J, theta = result.H, result.J, result.theta
+    if H is not None and J is not None and theta is not None:
+        H_prior = -prob.prior.hess(theta)                                 # :539
+        result.Sigma_inv = H.T @ np.linalg.inv(J) @ H + H_prior           # :540
+        result.Sigma = np.linalg.inv(result.Sigma_inv)                    # :541
+        result.dist = (theta.copy(), result.Sigma.copy())                 # :542-546
+    return result

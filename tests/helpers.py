@@ -1,0 +1,29 @@
+"""Shared test helpers: build matching (oracle, backend) problem pairs on identical base normals."""
+import numpy as np
+
+import oracle as O
+
+
+def make_family(name, d):
+    return O.make_family(name, d)
+
+
+def theta_true(name):
+    return np.array([0.0]) if name == "funnel" else np.array([0.0, 0.0])
+
+
+def theta_start(name):
+    return np.array([1.0]) if name == "funnel" else np.array([0.5, 0.3])
+
+
+def make_inputs(name, d, nsims, seed=1234, data_seed=99):
+    """Philox base normals for nsims sims + master, and observed data drawn at θ_true."""
+    fam = make_family(name, d)
+    draws = O.Draws.from_philox(seed, nsims, d)
+    xd, _ = fam.sample(theta_true(name), O.philox_normals(data_seed, 0, 0, d), O.philox_normals(data_seed, 0, 1, d))
+    return fam, draws, xd
+
+
+def oracle_problem(name, d, nsims, seed=1234, prior=None):
+    fam, draws, xd = make_inputs(name, d, nsims, seed)
+    return O.OracleProblem(fam, xd, draws, prior), fam, draws, xd

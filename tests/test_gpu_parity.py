@@ -1,0 +1,132 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on identical base normals.
+
+Tolerances (BASELINE.json north_star): per-sim ẑ_i and g_i within rtol 1e-8; θ̂, J, H, Σ within
+rtol 1e-6.  All FP64.
+"""
+import numpy as np
+import pytest
+
+import oracle as O
+from helpers import make_inputs, oracle_problem, theta_start
+
+pytestmark = pytest.mark.gpu
+
+RTOL_SIM = 1e-8
+RTOL_EST = 1e-6
+
+
+def _backend(name, d, nsims, draws, xd, **kw):
+    import museinference_jl_b200 as m
+    be = m.B200Backend(name, d, nsims, **kw)
+    be.set_data(xd)
+    be.set_draws(draws.xi, draws.nu, draws.xi_master, draws.nu_master)
+    return be
+
+
+def test_device_philox_matches_oracle():
+    import museinference_jl_b200 as m
+    d, n, seed, off = 1000, 7, 0xDEADBEEF12345, 40
+    be = m.B200Backend("funnel", d, n, sim_offset=off)
+    be.seed_draws(seed)
+    xi, nu = be.get_draws(0, n + 1)
+    for k in range(n):
+        np.testing.assert_allclose(xi[k], O.philox_normals(seed, off + k, 0, d), rtol=0, atol=2e-13)
+        np.testing.assert_allclose(nu[k], O.philox_normals(seed, off + k, 1, d), rtol=0, atol=2e-13)
+    np.testing.assert_allclose(xi[n], O.philox_normals(seed, O.philox.MASTER_INDEX, 0, d), rtol=0, atol=2e-13)
+    np.testing.assert_allclose(nu[n], O.philox_normals(seed, O.philox.MASTER_INDEX, 1, d), rtol=0, atol=2e-13)
+    be.close()
+
+
+@pytest.mark.parametrize("name,d,group", [("funnel", 512, 0), ("funnel", 513, 0), ("funnel", 512, 256),
+                                          ("hiergauss", 700, 0), ("funnel", 5000, 0), ("hiergauss", 4096, 512)])
+def test_map_score_cold_warm_truth(name, d, group):
+    nsims = 24
+    fam, draws, xd = make_inputs(name, d, nsims)
+    prob = O.OracleProblem(fam, xd, draws)
+    be = _backend(name, d, nsims, draws, xd, group=group)
+    th0 = theta_start(name)
+    atol = 1e-2
+
+    # cold pass (src/muse.jl:169-176 with ẑs = zeros)
+    out = be.map_score(th0, th0, atol, include_data=True, warm_start=0)
+    zs = be.get_maps(0, nsims + 1)
+    ref_z = []
+    for u in range(nsims + 1):
+        x = xd if u == 0 else prob.sample_x_z(u - 1, th0)[0]
+        zh, g, soln = O.map_score_unit(prob, x, np.zeros(d), th0, atol)
+        ref_z.append(zh)
+        np.testing.assert_allclose(out["g"][u], g, rtol=RTOL_SIM)
+        np.testing.assert_allclose(zs[u], zh, rtol=RTOL_SIM, atol=1e-12)
+        assert out["iters"][u] == soln.iterations and out["fg_evals"][u] == soln.f_calls
+        assert out["status"][u] == 0
+
+    # warm pass at a moved θ (src/muse.jl:181: ẑs carried over)
+    th1 = th0 - 0.3
+    out = be.map_score(th1, th1, atol, include_data=True, warm_start=1)
+    zs = be.get_maps(0, nsims + 1)
+    for u in range(nsims + 1):
+        x = xd if u == 0 else prob.sample_x_z(u - 1, th1)[0]
+        zh, g, soln = O.map_score_unit(prob, x, ref_z[u], th1, atol)
+        np.testing.assert_allclose(out["g"][u], g, rtol=RTOL_SIM)
+        np.testing.assert_allclose(zs[u], zh, rtol=RTOL_SIM, atol=1e-12)
+        assert out["iters"][u] == soln.iterations and out["fg_evals"][u] == soln.f_calls
+
+    # truth start on a sub-range (src/muse.jl:508-514)
+    out = be.map_score(th1, th1, atol, include_data=False, warm_start=2, first_sim=5, count=11)
+    for i in range(11):
+        x, z = prob.sample_x_z(5 + i, th1)
+        zh, g, soln = O.map_score_unit(prob, x, z, th1, atol)
+        np.testing.assert_allclose(out["g"][i], g, rtol=RTOL_SIM)
+        assert out["iters"][i] == soln.iterations and out["fg_evals"][i] == soln.f_calls
+    be.close()
+
+
+def test_zero_iteration_warm_start_keeps_previous_map():
+    """A start point that already satisfies ‖∇z‖_∞ ≤ atol is returned unchanged (0 iterations)."""
+    name, d, nsims = "funnel", 512, 8
+    fam, draws, xd = make_inputs(name, d, nsims)
+    be = _backend(name, d, nsims, draws, xd)
+    th = np.array([0.7])
+    be.map_score(th, th, 1e-2, include_data=True, warm_start=0)
+    z1 = be.get_maps(0, nsims + 1)
+    out = be.map_score(th + 1e-7, th + 1e-7, 1e-2, include_data=True, warm_start=1)
+    z2 = be.get_maps(0, nsims + 1)
+    assert (out["iters"] == 0).all() and (out["fg_evals"] == 1).all()
+    np.testing.assert_array_equal(z1, z2)
+    be.close()
+
+
+@pytest.mark.parametrize("name,d", [("funnel", 512), ("hiergauss", 1024)])
+def test_fd_jacobian_matches_oracle(name, d):
+    nsims, nH = 20, 6
+    fam, draws, xd = make_inputs(name, d, nsims)
+    prob = O.OracleProblem(fam, xd, draws)
+    be = _backend(name, d, nsims, draws, xd)
+    th0 = theta_start(name)
+    step = np.full(th0.shape, 0.01) * (1 + np.arange(th0.size))
+    Hs, status = be.fd_jacobian(th0, step, nH, 1e-2)
+    res = O.MuseResult(theta=th0.copy())
+    O.get_H_bang(res, prob, th0, nsims=nH, step=step, gradz_logLike_atol=1e-2)
+    assert (status == 0).all()
+    for k in range(nH):
+        np.testing.assert_allclose(Hs[k], res.Hs[k], rtol=1e-6, atol=1e-6 * np.abs(res.Hs[k]).max())
+    be.close()
+
+
+@pytest.mark.parametrize("name,d,nsims", [("funnel", 512, 100), ("hiergauss", 2048, 60)])
+def test_full_muse_matches_oracle(name, d, nsims):
+    import museinference_jl_b200 as m
+    prior_o = O.NormalPrior(0, 3) if name == "funnel" else None
+    prior_p = m.NormalPrior(0, 3) if name == "funnel" else None
+    oprob, fam, draws, xd = oracle_problem(name, d, nsims, prior=prior_o)
+    ref = O.muse(oprob, theta_start(name), nsims=nsims, get_covariance=True)
+    prob = m.SimpleMuseProblem(xd, name, prior_p)
+    rng = m.BaseDraws(draws.xi, draws.nu, draws.xi_master, draws.nu_master)
+    res = m.muse(prob, theta_start(name), rng=rng, nsims=nsims, get_covariance=True)
+    assert len(res.history) == len(ref.history)
+    np.testing.assert_allclose(res.theta, ref.theta, rtol=RTOL_EST)
+    np.testing.assert_allclose(res.J, ref.J, rtol=RTOL_EST)
+    np.testing.assert_allclose(res.H, ref.H, rtol=RTOL_EST, atol=RTOL_EST * np.abs(ref.H).max())
+    np.testing.assert_allclose(res.Sigma, ref.Sigma, rtol=10 * RTOL_EST, atol=RTOL_EST * np.abs(ref.Sigma).max())
+    np.testing.assert_allclose(np.array(res.gs), np.array(ref.gs), rtol=RTOL_SIM)
+    prob.close()
