@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""bench.py — MUSE sims/sec (MAP+score) on B200, with roofline and a CPU baseline beside it.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--scaling weak|strong]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[2], the config the metric is quoted on at 1/2/4/8 B200; it fits one
+GPU): Neal's funnel, 2^16 latent dims, nsims = 2048 per GPU, full solve θ̂ / J / H
+(``muse(prob, 1.0; nsims, get_covariance=true)``, prior N(0,3), ∇z_logLike_atol = 1e-2, data at
+θ_true = 0).  One *step* = one such full solve.  The metric counts the MAP+score units actually
+executed (outer iterations × (nsims+1) + 1 fiducial + 2·nθ·(nsims÷10) finite-difference solves; the
+reference's redundant centre evaluations and duplicate fiducial solves are neither executed nor
+counted) divided by the device time of the step.
+
+value   device-resident: base normals and data already in HBM, K steps bracketed by CUDA events on
+        the launch stream (barrier + synchronize on both sides), max over ranks.
+e2e     the same solve through the public API with host buffers: every step uploads the observed
+        data from pinned host memory, regenerates the base normals from the seed on the device
+        (the reference draws them inside sample_x_z), solves, and reads all results back.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+D = 65536
+NSIMS_PER_GPU = 2048
+THETA0 = 1.0
+ATOL = 1e-2
+DATA_SEED = 20261017
+SIM_SEED = 314159
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--d", type=int, default=D)
+    ap.add_argument("--nsims", type=int, default=NSIMS_PER_GPU, help="sims per GPU (weak) or in total (strong)")
+    ap.add_argument("--family", default="funnel", choices=["funnel", "hiergauss"])
+    ap.add_argument("--group", type=int, default=0)
+    ap.add_argument("--cluster", type=int, default=0)
+    ap.add_argument("--cpu-sims", type=int, default=0, help="sims in the bounded CPU sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def observed_data(family, d):
+    """Synthetic observation at θ_true (0 for the funnel, (0,0) for hiergauss); host NumPy, seeded."""
+    rng = np.random.Generator(np.random.Philox(DATA_SEED))
+    xi, nu = rng.standard_normal(d), rng.standard_normal(d)
+    return xi + nu      # sig = 1, mu = 0 at θ_true for both families
+
+
+def theta_start(family):
+    return np.array([THETA0]) if family == "funnel" else np.array([0.5, 0.3])
+
+
+# ----------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [t.strip() for t in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def cpu_solve_rate(family, d, nsims, nthreads, reps=1):
+    """Full solve with the oracle's C port on the host cores; returns (units/s, units, seconds, threads)."""
+    import oracle as O
+    from oracle import cmuse, cport
+
+    cport.build()
+    fam = O.make_family(family, d)
+    rng = np.random.Generator(np.random.Philox(SIM_SEED))
+    draws = O.Draws(rng.standard_normal((nsims, d)), rng.standard_normal((nsims, d)),
+                    rng.standard_normal(d), rng.standard_normal(d))
+    prior = O.NormalPrior(0, 3) if family == "funnel" else O.FlatPrior()
+    prob = O.OracleProblem(fam, observed_data(family, d), draws, prior)
+    threads = nthreads or cport.max_threads()
+    best = None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        _, units = cmuse.muse_cpu(prob, theta_start(family), nsims=nsims, gradz_logLike_atol=ATOL, nthreads=threads)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return units / best, units, best, threads
+
+
+def run_reference(args):
+    """--impl reference: the CPU implementation of the path (oracle C port; the Julia reference cannot
+    run in this image) on all host threads, each step a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    nsims = args.cpu_sims or 256
+    for _ in range(args.warmup):
+        cpu_solve_rate(args.family, args.d, min(nsims, 32), 0)
+    rates, secs, units, threads = [], 0.0, 0, 0
+    for _ in range(args.steps):
+        r, u, dt, threads = cpu_solve_rate(args.family, args.d, nsims, 0)
+        rates.append(r)
+        secs += dt
+        units += u
+    value = units / secs
+    sample = f"full solve (θ̂,J,H) of {args.family} d={args.d} on nsims={nsims} (subset of {args.nsims}); C port, analytic gradients"
+    line = {
+        "impl": "reference", "metric": "MUSE sims/sec (MAP+score)", "value": value, "unit": "sims/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.family} d={args.d} nsims={args.nsims}/GPU full solve θ̂/J/H (BASELINE configs[2])",
+                   "cpu_sample_nsims": nsims},
+        "cpu_baseline": {"value": value, "unit": "sims/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    import museinference_jl_b200 as m
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 backend has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        pool = m.ShardPool(device=local_rank)
+    else:
+        pool = m.LocalPool()
+        pool.device = local_rank
+    m.build_library()
+
+    nsims_total = args.nsims * world if args.scaling == "weak" else args.nsims
+    family, d = args.family, args.d
+    stream = torch.cuda.Stream()          # the library launches on this stream; events are recorded on it
+    torch.cuda.set_stream(stream)
+    x_host = torch.from_numpy(observed_data(family, d)).pin_memory()
+    prior = m.NormalPrior(0, 3) if family == "funnel" else m.FlatPrior()
+    prob = m.SimpleMuseProblem(x_host.numpy(), family, prior, group=args.group, cluster=args.cluster,
+                               stream=stream.cuda_stream)
+    th0 = theta_start(family)
+
+    def solve(seed):
+        return m.muse(prob, th0, rng=seed, nsims=nsims_total, gradz_logLike_atol=ATOL, get_covariance=True, pool=pool)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-resident arm ("value") ---------------------------------------------------
+    res = None
+    for _ in range(args.warmup):
+        res = solve(SIM_SEED)
+    be = prob._backend
+    sampler = ClockSampler(local_rank)
+    sync_all()
+    be.profile_reset(True)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        res = solve(SIM_SEED)
+    e1.record(stream)
+    sync_all()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = e0.elapsed_time(e1)
+    prof = be.profile()
+    be.profile_reset(False)
+    units_local = prof["solve_units"]
+
+    # ---- end-to-end arm ("e2e"): host data in, results out, draws regenerated from the seed ----
+    h2d = d * 8 + th0.size * 8
+    d2h = 0
+    sync_all()
+    t0 = time.perf_counter()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record(stream)
+    units_e2e = 0.0
+    be.profile_reset(True)
+    for s in range(args.steps):
+        prob.set_data(x_host.numpy())            # H2D of the step's input from pinned host memory
+        r = solve(SIM_SEED + 1 + (s % 2))        # new seed ⇒ base normals regenerated on the device
+        d2h = (len(r.gs) * th0.size + len(r.Hs) * th0.size ** 2) * 8 + (len(r.history) * (nsims_total // world + 1) * 20)
+    e3.record(stream)
+    sync_all()
+    ms_e2e = max(e2.elapsed_time(e3), 1e3 * (time.perf_counter() - t0))
+    prof_e = be.profile()
+    be.profile_reset(False)
+    units_e2e = prof_e["solve_units"]
+
+    # ---- reduce over ranks -----------------------------------------------------------------
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = t.tolist()
+        u = torch.tensor([units_local, units_e2e, prof["solve_ms"], prof["solve_bytes"], float(prof["launches"])],
+                         dtype=torch.float64, device="cuda")
+        dist.all_reduce(u, op=dist.ReduceOp.SUM)
+        units_all, units_e2e_all, solve_ms_sum, solve_bytes_sum, launches_sum = u.tolist()
+    else:
+        units_all, units_e2e_all = units_local, units_e2e
+        solve_ms_sum, solve_bytes_sum, launches_sum = prof["solve_ms"], prof["solve_bytes"], float(prof["launches"])
+
+    if rank == 0:
+        peaks, peak_src = {}, "fallback"
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+                peaks = json.load(fh)
+            peak_src = "measured"
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        achieved = (solve_bytes_sum / 1e9) / (solve_ms_sum / 1e3) if solve_ms_sum > 0 else 0.0
+        # traffic: dram bytes per solver launch from the committed ncu capture, if present
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "r01_solver_traffic.json")) as fh:
+                traffic = json.load(fh).get("dram_bytes_per_launch_avg")
+        except Exception:
+            pass
+        geo = be.geometry()
+        value = units_all / (ms / 1e3)
+        line = {
+            "metric": "MUSE sims/sec (MAP+score)", "value": value, "unit": "sims/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {
+                "workload": f"{family} d={d} nsims={args.nsims}{'/GPU' if args.scaling == 'weak' else ' total'} "
+                            f"full solve θ̂/J/H, θ₀={th0.tolist()}, atol={ATOL} (BASELINE configs[2])",
+                "nsims_total": nsims_total, "outer_iterations": len(res.history),
+                "units_per_step": units_all / args.steps, "l2": "inputs_larger_than_l2 (ξ,ν: %.2f GB per GPU)" % (2 * args.nsims * d * 8 / 1e9 if args.scaling == "weak" else 2 * nsims_total / world * d * 8 / 1e9),
+                "solver_geometry": geo, "theta_hat": [float(t) for t in res.theta],
+                "sigma": [float(s) for s in np.sqrt(np.diag(res.Sigma))],
+            },
+            "clocks": clocks,
+            "e2e": {"value": units_e2e_all / (ms_e2e / 1e3), "unit": "sims/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
+                    "note": "draws regenerated on device from the seed each step (reference draws inside sample_x_z)"},
+            "gpu_launches": int(launches_sum),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                         "kernel": "iso_solver_kernel (persistent MAP+score solver)",
+                         "algorithmic_bytes_per_launch": solve_bytes_sum / max(1, prof["solve_launches"] * world),
+                         "avg_launch_ms": solve_ms_sum / max(1, prof["solve_launches"] * world),
+                         "kernel_share_of_step": solve_ms_sum / world / ms},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            nsims_cpu = args.cpu_sims or 256
+            rate, units, secs, threads = cpu_solve_rate(family, d, nsims_cpu, 0)
+            line["cpu_baseline"] = {
+                "value": rate, "unit": "sims/s", "cores": threads, "kind": "port",
+                "sample": f"full solve (θ̂,J,H) on nsims={nsims_cpu} of the same shape, {units} units in {secs:.2f}s; "
+                          "oracle C port with analytic gradients (faster than the Julia reference's AD path)"}
+        print(json.dumps(line))
+    prob.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -481,15 +481,6 @@ int muse_b200_fd_jacobian(muse_handle* h, const double* theta0, const double* st
     CUDA_TRY(h, cudaMemsetAsync(h->zfid_state, 0, sizeof(int), h->stream));
     int rc = launch_solver(h, F, 3 * d8);
     if (rc != 0) return rc;
-    int fid_state = 0;
-    CUDA_TRY(h, cudaMemcpyAsync(&fid_state, h->zfid_state, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-    const double* zfid = fid_state == kZA ? h->zfidA : (fid_state == kZB ? h->zfidB : nullptr);
-    if (!zfid) {   // converged at the zero start
-        CUDA_TRY(h, cudaMemsetAsync(h->zfidA, 0, ld * B, h->stream));
-        zfid = h->zfidA;
-    }
-
     // (2) virtual sims at θ₀ ± h_n e_n, MAP + score at θ₀ from the fiducial start — src/muse.jl:426-433
     SolveLaunch L;
     fill_common(h, L);
@@ -497,7 +488,10 @@ int muse_b200_fd_jacobian(muse_handle* h, const double* theta0, const double* st
     L.mode = 1;
     L.atol = atol;
     L.start_kind = kStartShared;
-    L.zshared = zfid;
+    L.zshared = nullptr;
+    L.zshared_state = h->zfid_state;     // picked on the device: no host sync between the two launches
+    L.zsharedA = h->zfidA;
+    L.zsharedB = h->zfidB;
     if (hshard) { L.xi = h->xi_h; L.nu = h->nu_h; }
     if (theta_consts(h->cfg, theta0, theta0, nullptr, &L.ev) != 0) MUSE_FAIL(h, MUSE_EUNSUPPORTED, "family");
     for (int n = 0; n < nt; ++n) {

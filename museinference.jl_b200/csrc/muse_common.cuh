@@ -60,6 +60,11 @@ struct SolveLaunch {
     const double* nu;
     const double* xdat;  // d
     const double* zshared;  // d (user z₀ or fiducial ẑ)
+    // alternative: the shared start is the resident ẑ of an earlier launch on the same stream
+    // (fiducial solve → FD sims, no host sync in between): pick A/B/zero from *zshared_state
+    const int* zshared_state;
+    const double* zsharedA;
+    const double* zsharedB;
     int master_row;      // row of the master draw in xi/nu
     // per-unit resident state (mode 0 rows: unit index; mode 1 rows: item index in H scratch)
     double* x;           // materialised x, rows × ld

@@ -22,6 +22,18 @@ struct Group {
     static constexpr int kWarps = CTA_THREADS / 32;
     static constexpr int kGroupsPerCta = WARP_GROUP ? kWarps : 1;
     static constexpr int kSize = WARP_GROUP ? 32 : CTA_THREADS * CLUSTER;
+    static constexpr bool kWarpGroup = WARP_GROUP;
+
+    // controller → workers hand-off: named barrier 1 over the whole CTA (the controller warp and
+    // the worker warps arrive from different program locations, which bar.sync permits)
+    static __device__ __forceinline__ void cmd_barrier() {
+        asm volatile("bar.sync 1, %0;" ::"n"(CTA_THREADS) : "memory");
+    }
+    // end of a sweep that has no reduction: every thread is done with the command slot
+    __device__ __forceinline__ void sync_exec() {
+        if (WARP_GROUP) __syncwarp();
+        else __syncthreads();
+    }
 
     struct Smem {
         double wpart[2][kWarps][kRedMax];

@@ -12,11 +12,14 @@
 //
 // Design.  One launch solves all units.  A *group* of threads (a warp, a CTA or a
 // thread-block cluster, by latent dimension) owns one unit at a time and runs the complete
-// L-BFGS(m) + Hager–Zhang algorithm for it in "direct style": the scalar optimiser logic is
-// executed redundantly and uniformly by every thread of the group, and each objective
-// evaluation is one cooperative, 128-bit vectorised sweep over the unit's rows in HBM with a
-// fixed-tree all-reduce (muse_group.cuh).  No host round trip, no inter-kernel state machine;
-// units that need more iterations simply keep their group longer.
+// L-BFGS(m) + Hager–Zhang algorithm for it.  The scalar optimiser logic is written in direct
+// style (it reads like oracle/lbfgs.py + oracle/hagerzhang.py) and runs only in the *controller*
+// warp of each CTA; every objective evaluation is a *sweep* command the controller broadcasts
+// through shared memory and that all warps execute cooperatively: one 128-bit vectorised pass
+// over the unit's rows with a fixed-tree all-reduce (muse_group.cuh).  No host round trip, no
+// inter-kernel state machine; units that need more iterations simply keep their group longer.
+// (Keeping the scalar state in one warp matters: when every thread carried it, its spills and
+// stack traffic added ~30 % DRAM writes — profiles/r01_*.)
 //
 // Traffic minimisation.  For these families ∇z is elementwise in (x_j, z_j), so the gradient is
 // never stored: it is recomputed wherever it is needed.  Fusions, in reference terms:
@@ -53,22 +56,38 @@ __device__ __forceinline__ double eps_of(double x) {   // Julia eps(x::Float64)
 }
 __device__ __forceinline__ bool fin(double x) { return isfinite(x); }
 
-// ---- per-unit context ------------------------------------------------------------------
-struct Unit {
-    const double* xi;      // null for the data unit
-    const double* nu;
-    const double* xsrc;    // materialised x to read (data: xdat; sims: == xw after INIT)
-    double* xw;            // where INIT materialises x (null for data)
-    const double* zcur;    // current iterate (null ⇒ z ≡ 0)
-    double* zalt;          // buffer the next committed iterate goes to
-    double* zother;        // the unit's other own buffer (becomes zalt after a flip)
-    double* zA;
-    IsoSample smp;
-    int start_kind;
+// ---- sweep commands ---------------------------------------------------------------------
+enum Op : int {
+    kOpInit = 0,     // sample + f,g at z₀ + score sums + first trial           → red[7]
+    kOpTrial,        // φ(c), φ'(c) [+ commit]                                   → red[7]
+    kOpHist,         // dx = c·s → w1, dg = ∇f(v2) − ∇f(v1) → w2                 → red[2] = dx·dg, dg·dg
+    kOpGrad,         // sbuf ← ∇f(zcur)
+    kOpDot,          // red[0] = v1 · sbuf
+    kOpAxpy,         // sbuf ← sbuf + c·v1
+    kOpScale,        // sbuf ← c·sbuf
+    kOpNegDotG,      // sbuf ← −sbuf; red[0] = ∇f(zcur) · sbuf
+    kOpExit,
 };
 
-struct Red7 {
-    double e, dphi, gg, gmax, s1, s2, xchg;
+struct Cmd {
+    int op;
+    int commit;
+    int lazy;          // search direction s ≡ −∇f(zcur), not stored
+    int start_kind;
+    double c;
+    IsoSample smp;
+    const double* xi;  // null for the data unit
+    const double* nu;
+    const double* xsrc;   // materialised x (data: xdat; sims: the unit's x row once INIT has run)
+    double* xw;           // where INIT materialises x (null for data)
+    const double* zcur;   // current iterate (null ⇒ z ≡ 0)
+    double* zalt;         // buffer a committed iterate goes to
+    double* zA;           // the unit's buffer A (INIT materialises a truth / user start there)
+    double* sbuf;         // search direction / two-loop work vector (slot scratch)
+    const double* v1;
+    const double* v2;
+    double* w1;
+    double* w2;
 };
 
 // elementwise pieces:  g = a (z-μ) - (x-z);   e = (x-z)² + a (z-μ)²
@@ -84,144 +103,247 @@ __device__ __forceinline__ Elem elem(double x, double z, const IsoEval& ev) {
     o.w = w;
     return o;
 }
+__device__ __forceinline__ double2 ld2(const double* p, int i) {
+    return p ? *reinterpret_cast<const double2*>(p + 2 * (size_t)i) : make_double2(0.0, 0.0);
+}
+__device__ __forceinline__ void st2(double* p, int i, double2 v) {
+    *reinterpret_cast<double2*>(p + 2 * (size_t)i) = v;
+}
+
+// ---- the sweeps (executed by every thread of the group) -----------------------------------
+// red: [e0, gg0, gmax0, s1, s2, e1, dphi1]
+template <class G>
+__device__ __forceinline__ void sweep_init(G& grp, const SolveLaunch& L, const Cmd& c, double (&red)[7]) {
+    const IsoEval ev = L.ev;
+    const IsoSample sp = c.smp;
+    const double *xi = c.xi, *nu = c.nu, *xsrc = c.xsrc, *zcur = c.zcur;
+    double *xw = c.xw, *zA = c.zA;
+    const bool sim = (xi != nullptr);
+    const int sk = c.start_kind;
+    const int npairs = L.d >> 1;
+    double e0 = 0, gg0 = 0, gmax0 = 0, s1 = 0, s2 = 0, e1 = 0, dphi1 = 0;
+    auto body = [&](double x, double z0) {
+        const Elem a = elem(x, z0, ev);
+        e0 += a.e;
+        gg0 = fma(a.g, a.g, gg0);
+        gmax0 = fmax(gmax0, fabs(a.g));
+        s1 += a.w;
+        s2 = fma(a.w, a.w, s2);
+        const double z1 = z0 - a.g;
+        const Elem b = elem(x, z1, ev);
+        e1 += b.e;
+        dphi1 = fma(b.g, -a.g, dphi1);
+    };
+#pragma unroll 2
+    for (int p = grp.tid; p < npairs; p += G::kSize) {
+        double2 x, z0;
+        if (sim) {
+            const double2 a = ld2(xi, p), b = ld2(nu, p);
+            const double zt0 = fma(sp.sig, a.x, sp.mu), zt1 = fma(sp.sig, a.y, sp.mu);
+            x = make_double2(zt0 + b.x, zt1 + b.y);
+            st2(xw, p, x);
+            if (sk == kStartTruth) {
+                z0 = make_double2(zt0, zt1);
+                st2(zA, p, z0);
+            } else {
+                z0 = ld2(zcur, p);
+                if (sk == kStartSharedKeep) st2(zA, p, z0);
+            }
+        } else {
+            x = ld2(xsrc, p);
+            z0 = ld2(zcur, p);
+            if (sk == kStartSharedKeep) st2(zA, p, z0);
+        }
+        body(x.x, z0.x);
+        body(x.y, z0.y);
+    }
+    if ((L.d & 1) && grp.tid == 0) {
+        const int j = L.d - 1;
+        double x, z0;
+        if (sim) {
+            const double zt = fma(sp.sig, xi[j], sp.mu);
+            x = zt + nu[j];
+            xw[j] = x;
+            if (sk == kStartTruth) { z0 = zt; zA[j] = z0; }
+            else { z0 = zcur ? zcur[j] : 0.0; if (sk == kStartSharedKeep) zA[j] = z0; }
+        } else {
+            x = xsrc[j];
+            z0 = zcur ? zcur[j] : 0.0;
+            if (sk == kStartSharedKeep) zA[j] = z0;
+        }
+        body(x, z0);
+    }
+    red[0] = e0; red[1] = gg0; red[2] = gmax0; red[3] = s1; red[4] = s2; red[5] = e1; red[6] = dphi1;
+    grp.template allreduce<7, 0x04u>(red);
+}
+
+// zt = zcur + c·s with s = −∇f(zcur) (lazy) or sbuf.  red: [e, dphi, gg, gmax, s1, s2, xchg]
+template <class G, bool LAZY>
+__device__ __forceinline__ void sweep_trial(G& grp, const SolveLaunch& L, const Cmd& cm, double (&red)[7]) {
+    const IsoEval ev = L.ev;
+    const double c = cm.c;
+    const bool commit = cm.commit != 0;
+    const double *xsrc = cm.xsrc, *zcur = cm.zcur, *sb = cm.sbuf;
+    double* zalt = cm.zalt;
+    const int npairs = L.d >> 1;
+    double e = 0, dphi = 0, gg_ = 0, gmax_ = 0, s1_ = 0, s2_ = 0, xchg = 0;
+    auto body = [&](double x, double z, double s) -> double {
+        if (LAZY) s = -elem(x, z, ev).g;
+        const double zt = fma(c, s, z);
+        const Elem b = elem(x, zt, ev);
+        e += b.e;
+        dphi = fma(b.g, s, dphi);
+        gg_ = fma(b.g, b.g, gg_);
+        gmax_ = fmax(gmax_, fabs(b.g));
+        s1_ += b.w;
+        s2_ = fma(b.w, b.w, s2_);
+        xchg = fmax(xchg, fabs(zt - z));
+        return zt;
+    };
+#pragma unroll 2
+    for (int p = grp.tid; p < npairs; p += G::kSize) {
+        const double2 x = ld2(xsrc, p);
+        const double2 z = ld2(zcur, p);
+        double2 s = make_double2(0.0, 0.0);
+        if (!LAZY) s = ld2(sb, p);
+        double2 zt;
+        zt.x = body(x.x, z.x, s.x);
+        zt.y = body(x.y, z.y, s.y);
+        if (commit) st2(zalt, p, zt);
+    }
+    if ((L.d & 1) && grp.tid == 0) {
+        const int j = L.d - 1;
+        const double zt = body(xsrc[j], zcur ? zcur[j] : 0.0, LAZY ? 0.0 : sb[j]);
+        if (commit) zalt[j] = zt;
+    }
+    red[0] = e; red[1] = dphi; red[2] = gg_; red[3] = gmax_; red[4] = s1_; red[5] = s2_; red[6] = xchg;
+    grp.template allreduce<7, 0x48u>(red);
+}
+
+template <class G, class F>
+__device__ __forceinline__ void for_each_elem(G& grp, const SolveLaunch& L, F&& fn) {
+    const int npairs = L.d >> 1;
+    for (int p = grp.tid; p < npairs; p += G::kSize) { fn(2 * p); fn(2 * p + 1); }
+    if ((L.d & 1) && grp.tid == 0) fn(L.d - 1);
+}
+
+// slow-path vector operations (only reached when a unit needs more than one L-BFGS iteration)
+template <class G>
+__device__ __noinline__ void sweep_misc(G& grp, const SolveLaunch& L, const Cmd& c, double (&red)[7]) {
+    const IsoEval ev = L.ev;
+    const double* x = c.xsrc;
+    double* sb = c.sbuf;
+    auto grad = [&](const double* z, int j) { return elem(x[j], z ? z[j] : 0.0, ev).g; };
+    switch (c.op) {
+        case kOpHist: {
+            double a = 0, b = 0;
+            const double alpha = c.c;
+            const double *zp = c.v1, *zn = c.v2;
+            double *dx = c.w1, *dg = c.w2;
+            const bool lazy = c.lazy != 0;
+            for_each_elem(grp, L, [&](int j) {
+                const double gp = grad(zp, j), gn = grad(zn, j);
+                const double s = lazy ? -gp : sb[j];
+                const double dxj = alpha * s, dgj = gn - gp;
+                dx[j] = dxj;
+                dg[j] = dgj;
+                a = fma(dxj, dgj, a);
+                b = fma(dgj, dgj, b);
+            });
+            double r2[2] = {a, b};
+            grp.template allreduce<2, 0u>(r2);
+            red[0] = r2[0];
+            red[1] = r2[1];
+            break;
+        }
+        case kOpGrad: {
+            const double* z = c.zcur;
+            for_each_elem(grp, L, [&](int j) { sb[j] = grad(z, j); });
+            grp.sync_exec();
+            break;
+        }
+        case kOpDot: {
+            double a = 0;
+            const double* v = c.v1;
+            for_each_elem(grp, L, [&](int j) { a = fma(v[j], sb[j], a); });
+            double r1[1] = {a};
+            grp.template allreduce<1, 0u>(r1);
+            red[0] = r1[0];
+            break;
+        }
+        case kOpAxpy: {
+            const double cf = c.c;
+            const double* v = c.v1;
+            for_each_elem(grp, L, [&](int j) { sb[j] = fma(cf, v[j], sb[j]); });
+            grp.sync_exec();
+            break;
+        }
+        case kOpScale: {
+            const double cf = c.c;
+            for_each_elem(grp, L, [&](int j) { sb[j] *= cf; });
+            grp.sync_exec();
+            break;
+        }
+        case kOpNegDotG: {
+            double a = 0;
+            const double* z = c.zcur;
+            for_each_elem(grp, L, [&](int j) {
+                const double s = -sb[j];
+                sb[j] = s;
+                a = fma(grad(z, j), s, a);
+            });
+            double r1[1] = {a};
+            grp.template allreduce<1, 0u>(r1);
+            red[0] = r1[0];
+            break;
+        }
+        default: break;
+    }
+}
 
 template <class G>
-struct Solver {
+__device__ __noinline__ void run_op(G& grp, const SolveLaunch& L, const Cmd& c, double (&red)[7]) {
+    if (c.op == kOpInit) sweep_init(grp, L, c, red);
+    else if (c.op == kOpTrial) {
+        if (c.lazy) sweep_trial<G, true>(grp, L, c, red);
+        else sweep_trial<G, false>(grp, L, c, red);
+    } else sweep_misc(grp, L, c, red);
+}
+
+// ---- the controller: scalar L-BFGS + Hager–Zhang, one warp per CTA ------------------------
+struct Red7 {
+    double e, dphi, gg, gmax, s1, s2, xchg;
+};
+
+template <class G>
+struct Controller {
     G& grp;
     const SolveLaunch& L;
-    const int npairs;      // full double2 pairs
-    const bool tail;       // odd d: one trailing scalar element
-    Unit u;
-    double* sbuf;          // slot scratch: search direction (materialised when history is used)
+    Cmd* scmd;             // shared-memory command slot (CTA / cluster groups)
+    Cmd cur;               // the unit's pointers + the command being built
+    double* zother;        // the unit's other own buffer (becomes zalt after a flip)
     double* dxh;
     double* dgh;
-    // scalar optimiser state (identical in all threads of the group)
+    // scalar optimiser state
     double f, gg, gmax, s1, s2;
-    bool lazy_s;           // s ≡ -∇f(zcur), not stored
     int fg_evals;
-    // prefetch of the first trial (INIT sweep)
-    bool pre_valid;
+    bool pre_valid;        // first trial prefetched by the INIT sweep
     double pre_phi, pre_dphi;
-    // last committed trial
-    double com_alpha;      // NaN ⇒ none
+    double com_alpha;      // last committed trial (NaN ⇒ none)
     Red7 com;
-    double last_eval_alpha;
+    double last_eval_alpha, last_phi, last_dphi;
 
-    __device__ Solver(G& g, const SolveLaunch& l)
-        : grp(g), L(l), npairs(l.d >> 1), tail(l.d & 1) {}
+    __device__ Controller(G& g, const SolveLaunch& l, Cmd* s) : grp(g), L(l), scmd(s) {}
 
-    // ------------------------------------------------------------------ element access
-    __device__ __forceinline__ double2 ld2(const double* p, int i) const {
-        return p ? *reinterpret_cast<const double2*>(p + 2 * (size_t)i) : make_double2(0.0, 0.0);
-    }
-    __device__ __forceinline__ void st2(double* p, int i, double2 v) const {
-        *reinterpret_cast<double2*>(p + 2 * (size_t)i) = v;
-    }
-
-    // ------------------------------------------------------------------ INIT sweep
-    // sample + f,g at z₀ + score sums at z₀ + first trial (c = 1 along -g₀).
-    // red: [e0, gg0, gmax0, s1, s2, e1, dphi1]
-    __device__ __noinline__ void init_sweep(double (&red)[7]) {
-        const IsoEval ev = L.ev;
-        const IsoSample sp = u.smp;
-        const bool sim = (u.xi != nullptr);
-        const int sk = u.start_kind;
-        double e0 = 0, gg0 = 0, gmax0 = 0, s1 = 0, s2 = 0, e1 = 0, dphi1 = 0;
-        auto body = [&](double x, double z0) {
-            const Elem a = elem(x, z0, ev);
-            e0 += a.e;
-            gg0 = fma(a.g, a.g, gg0);
-            gmax0 = fmax(gmax0, fabs(a.g));
-            s1 += a.w;
-            s2 = fma(a.w, a.w, s2);
-            const double z1 = z0 - a.g;
-            const Elem b = elem(x, z1, ev);
-            e1 += b.e;
-            dphi1 = fma(b.g, -a.g, dphi1);
-        };
-#pragma unroll 2
-        for (int p = grp.tid; p < npairs; p += G::kSize) {
-            double2 x, z0;
-            if (sim) {
-                const double2 xi = ld2(u.xi, p), nu = ld2(u.nu, p);
-                const double zt0 = fma(sp.sig, xi.x, sp.mu), zt1 = fma(sp.sig, xi.y, sp.mu);
-                x = make_double2(zt0 + nu.x, zt1 + nu.y);
-                st2(u.xw, p, x);
-                if (sk == kStartTruth) {
-                    z0 = make_double2(zt0, zt1);
-                    st2(u.zA, p, z0);
-                } else {
-                    z0 = ld2(u.zcur, p);
-                    if (sk == kStartSharedKeep) st2(u.zA, p, z0);
-                }
-            } else {
-                x = ld2(u.xsrc, p);
-                z0 = ld2(u.zcur, p);
-                if (sk == kStartSharedKeep) st2(u.zA, p, z0);
-            }
-            body(x.x, z0.x);
-            body(x.y, z0.y);
+    // broadcast `cur` and execute it with the whole group
+    __device__ __noinline__ void issue(double (&red)[7]) {
+        if (G::kWarpGroup) {
+            run_op(grp, L, cur, red);
+        } else {
+            if ((threadIdx.x & 31) == 0) *scmd = cur;
+            G::cmd_barrier();
+            run_op(grp, L, *scmd, red);
         }
-        if (tail && grp.tid == 0) {
-            const int j = L.d - 1;
-            double x, z0;
-            if (sim) {
-                const double zt = fma(sp.sig, u.xi[j], sp.mu);
-                x = zt + u.nu[j];
-                u.xw[j] = x;
-                if (sk == kStartTruth) { z0 = zt; u.zA[j] = z0; }
-                else { z0 = u.zcur ? u.zcur[j] : 0.0; if (sk == kStartSharedKeep) u.zA[j] = z0; }
-            } else {
-                x = u.xsrc[j];
-                z0 = u.zcur ? u.zcur[j] : 0.0;
-                if (sk == kStartSharedKeep) u.zA[j] = z0;
-            }
-            body(x, z0);
-        }
-        red[0] = e0; red[1] = gg0; red[2] = gmax0; red[3] = s1; red[4] = s2; red[5] = e1; red[6] = dphi1;
-        grp.template allreduce<7, 0x04u>(red);
-    }
-
-    // ------------------------------------------------------------------ TRIAL sweep
-    // zt = zcur + c·s with s = -∇f(zcur) (lazy) or sbuf; returns φ(c), φ'(c) and, when
-    // `commit`, writes zt to zalt and returns the quantities needed to accept it.
-    template <bool LAZY>
-    __device__ void trial_sweep(double c, bool commit, Red7& out) {
-        const IsoEval ev = L.ev;
-        double e = 0, dphi = 0, gg_ = 0, gmax_ = 0, s1_ = 0, s2_ = 0, xchg = 0;
-        auto body = [&](double x, double z, double s) -> double {
-            if (LAZY) s = -elem(x, z, ev).g;
-            const double zt = fma(c, s, z);
-            const Elem b = elem(x, zt, ev);
-            e += b.e;
-            dphi = fma(b.g, s, dphi);
-            gg_ = fma(b.g, b.g, gg_);
-            gmax_ = fmax(gmax_, fabs(b.g));
-            s1_ += b.w;
-            s2_ = fma(b.w, b.w, s2_);
-            xchg = fmax(xchg, fabs(zt - z));
-            return zt;
-        };
-#pragma unroll 2
-        for (int p = grp.tid; p < npairs; p += G::kSize) {
-            const double2 x = ld2(u.xsrc, p);
-            const double2 z = ld2(u.zcur, p);
-            double2 s = make_double2(0.0, 0.0);
-            if (!LAZY) s = ld2(sbuf, p);
-            double2 zt;
-            zt.x = body(x.x, z.x, s.x);
-            zt.y = body(x.y, z.y, s.y);
-            if (commit) st2(u.zalt, p, zt);
-        }
-        if (tail && grp.tid == 0) {
-            const int j = L.d - 1;
-            const double zt = body(u.xsrc[j], u.zcur ? u.zcur[j] : 0.0, LAZY ? 0.0 : sbuf[j]);
-            if (commit) u.zalt[j] = zt;
-        }
-        double red[7] = {e, dphi, gg_, gmax_, s1_, s2_, xchg};
-        grp.template allreduce<7, 0x48u>(red);
-        out.e = red[0]; out.dphi = red[1]; out.gg = red[2]; out.gmax = red[3];
-        out.s1 = red[4]; out.s2 = red[5]; out.xchg = red[6];
     }
 
     // φ, φ' at step c (Hager–Zhang's ϕdϕ).  Counts one value+gradient evaluation unless the
@@ -243,21 +365,23 @@ struct Solver {
             dphi = last_dphi;
             return;
         }
-        Red7 r;
-        if (lazy_s) trial_sweep<true>(c, commit, r);
-        else trial_sweep<false>(c, commit, r);
-        phi = fma(0.5, r.e, L.ev.half_cst);
-        dphi = r.dphi;
+        double red[7];
+        cur.op = kOpTrial;
+        cur.c = c;
+        cur.commit = commit ? 1 : 0;
+        issue(red);
+        phi = fma(0.5, red[0], L.ev.half_cst);
+        dphi = red[1];
         if (c != last_eval_alpha) fg_evals += 1;
         last_eval_alpha = c;
         last_phi = phi;
         last_dphi = dphi;
         if (commit) {
             com_alpha = c;
-            com = r;
+            com.e = red[0]; com.dphi = red[1]; com.gg = red[2]; com.gmax = red[3];
+            com.s1 = red[4]; com.s2 = red[5]; com.xchg = red[6];
         }
     }
-    double last_phi, last_dphi;
 
     // ------------------------------------------------------------------ Hager–Zhang
     // [EXT LineSearches.jl src/hagerzhang.jl] delta=.1 sigma=.9 alphamax=Inf rho=5 epsilon=1e-6
@@ -300,7 +424,7 @@ struct Solver {
         b_is_c = (bb.al == c.al);   // bisect! left ib == ic
     }
 
-    // returns status: 0 ok (alpha, phi_alpha set), 1 LineSearchException (alpha = ex.alpha)
+    // returns 0 ok (alpha, phi_alpha set), 1 LineSearchException (alpha = ex.alpha)
     __device__ __noinline__ int hager_zhang(double c, double phi_0, double dphi_0, double& alpha, double& phi_alpha) {
         constexpr double rho = 5.0, epsilon = 1e-6, gamma = 0.66, psi3 = 0.1;
         constexpr int linesearchmax = 50, iterfinitemax = 53;   // ceil(-log2(eps))
@@ -343,8 +467,7 @@ struct Solver {
                 nc.al = pc.al * rho;
                 phidphi(nc.al, false, nc.phi, nc.dphi);
                 iterfinite = 1;
-                while (!(fin(nc.phi) && fin(nc.dphi)) && nc.al > next_up(cold.al) &&
-                       iterfinite < iterfinitemax) {
+                while (!(fin(nc.phi) && fin(nc.dphi)) && nc.al > next_up(cold.al) && iterfinite < iterfinitemax) {
                     iterfinite += 1;
                     nc.al = (cold.al + nc.al) / 2.0;
                     phidphi(nc.al, false, nc.phi, nc.dphi);
@@ -425,111 +548,65 @@ struct Solver {
         return 1;
     }
 
-    // ------------------------------------------------------------------ generic vector sweeps
-    // (history path: only reached when a unit needs more than one L-BFGS iteration)
-    __device__ double grad_at(const double* x, const double* z, int j) const {
-        return elem(x[j], z ? z[j] : 0.0, L.ev).g;
-    }
-    template <class F>
-    __device__ void for_each(F&& fn) {
-        for (int p = grp.tid; p < npairs; p += G::kSize) { fn(2 * p); fn(2 * p + 1); }
-        if (tail && grp.tid == 0) fn(L.d - 1);
-    }
-    __device__ double reduce1(double v) {
-        double r[1] = {v};
-        grp.template allreduce<1, 0u>(r);
-        return r[0];
-    }
-
-    // accept sweep: z_new = zcur + α s → zalt, with everything an accepted point needs
-    __device__ __noinline__ void accept_sweep(double alpha, bool need_eval) {
-        Red7 r;
-        if (lazy_s) trial_sweep<true>(alpha, true, r);
-        else trial_sweep<false>(alpha, true, r);
-        com = r;
-        com_alpha = alpha;
-        if (need_eval) fg_evals += 1;
-    }
-
-    // update_h!: dx = α s, dg = ∇f(z_new) - ∇f(z_prev) into history slot idx; returns dx·dg, dg·dg
-    __device__ __noinline__ void history_sweep(double alpha, const double* zprev, const double* znew, int idx,
-                                  double& dxdg, double& dgdg) {
-        double* dx = dxh + (size_t)idx * L.ld;
-        double* dg = dgh + (size_t)idx * L.ld;
-        double a = 0, b = 0;
-        const bool lazy = lazy_s;
-        for_each([&](int j) {
-            const double gp = grad_at(u.xsrc, zprev, j);
-            const double gn = grad_at(u.xsrc, znew, j);
-            const double s = lazy ? -gp : sbuf[j];
-            const double dxj = alpha * s;
-            const double dgj = gn - gp;
-            dx[j] = dxj;
-            dg[j] = dgj;
-            a = fma(dxj, dgj, a);
-            b = fma(dgj, dgj, b);
-        });
-        double r[2] = {a, b};
-        grp.template allreduce<2, 0u>(r);
-        dxdg = r[0];
-        dgdg = r[1];
-    }
-
-    // twoloop!: s ← -H·∇f(zcur) into sbuf; returns ∇f·s
-    __device__ __noinline__ double twoloop(int pseudo_iter, const double* rho, const double* dxdg_h, const double* dgdg_h,
-                              double* alpha_tl) {
+    // ------------------------------------------------------------------ L-BFGS pieces
+    // twoloop!: s ← −H·∇f(zcur) into sbuf; returns ∇f·s   [EXT Optim.jl l_bfgs.jl twoloop!]
+    __device__ __noinline__ double twoloop(int pseudo_iter, const double* rho, const double* dxdg_h,
+                                           const double* dgdg_h, double* alpha_tl) {
         const int m = L.lbfgs_m;
         const int lower = pseudo_iter - m, upper = pseudo_iter - 1;
-        const double* z = u.zcur;
-        for_each([&](int j) { sbuf[j] = grad_at(u.xsrc, z, j); });
+        double red[7];
+        cur.op = kOpGrad;
+        issue(red);
         for (int index = upper; index >= lower; --index) {
             if (index < 1) continue;
             const int i = (index - 1) % m;
-            const double* dx = dxh + (size_t)i * L.ld;
-            const double* dg = dgh + (size_t)i * L.ld;
-            double acc = 0;
-            for_each([&](int j) { acc = fma(dx[j], sbuf[j], acc); });
-            const double al = rho[i] * reduce1(acc);
+            cur.op = kOpDot;
+            cur.v1 = dxh + (size_t)i * L.ld;
+            issue(red);
+            const double al = rho[i] * red[0];
             alpha_tl[i] = al;
-            for_each([&](int j) { sbuf[j] = fma(-al, dg[j], sbuf[j]); });
+            cur.op = kOpAxpy;
+            cur.c = -al;
+            cur.v1 = dgh + (size_t)i * L.ld;
+            issue(red);
         }
         if (pseudo_iter > 1) {     // scaleinvH0
             const int i = (upper - 1) % m;
-            const double scaling = dxdg_h[i] / dgdg_h[i];
-            for_each([&](int j) { sbuf[j] *= scaling; });
+            cur.op = kOpScale;
+            cur.c = dxdg_h[i] / dgdg_h[i];
+            issue(red);
         }
         for (int index = lower; index <= upper; ++index) {
             if (index < 1) continue;
             const int i = (index - 1) % m;
-            const double* dx = dxh + (size_t)i * L.ld;
-            const double* dg = dgh + (size_t)i * L.ld;
-            double acc = 0;
-            for_each([&](int j) { acc = fma(dg[j], sbuf[j], acc); });
-            const double beta = rho[i] * reduce1(acc);
-            const double cf = alpha_tl[i] - beta;
-            for_each([&](int j) { sbuf[j] = fma(dx[j], cf, sbuf[j]); });
+            cur.op = kOpDot;
+            cur.v1 = dgh + (size_t)i * L.ld;
+            issue(red);
+            const double beta = rho[i] * red[0];
+            cur.op = kOpAxpy;
+            cur.c = alpha_tl[i] - beta;
+            cur.v1 = dxh + (size_t)i * L.ld;
+            issue(red);
         }
-        double acc = 0;
-        for_each([&](int j) {
-            const double s = -sbuf[j];
-            sbuf[j] = s;
-            acc = fma(grad_at(u.xsrc, z, j), s, acc);
-        });
-        return reduce1(acc);
+        cur.op = kOpNegDotG;
+        issue(red);
+        return red[0];
     }
 
     // ------------------------------------------------------------------ one unit
-    __device__ void solve(int item, int row, int* zstate_row) {
+    // `cur` holds the unit's pointers (xi, nu, xsrc, xw, zcur, zalt, zA, sbuf, smp, start_kind).
+    __device__ __noinline__ void solve(int item, int* zstate_row) {
         const IsoEval ev = L.ev;
         double red[7];
-        pre_valid = false;
         com_alpha = NAN;
         last_eval_alpha = NAN;
         last_phi = last_dphi = NAN;
-        fg_evals = 0;
 
-        init_sweep(red);
-        if (u.xw) u.xsrc = u.xw;
+        cur.op = kOpInit;
+        cur.lazy = 1;
+        cur.commit = 0;
+        issue(red);
+        if (cur.xw) cur.xsrc = cur.xw;
         f = fma(0.5, red[0], ev.half_cst);
         gg = red[1];
         gmax = red[2];
@@ -539,13 +616,12 @@ struct Solver {
         pre_valid = true;
         pre_phi = fma(0.5, red[5], ev.half_cst);
         pre_dphi = red[6];
-        lazy_s = true;
 
         // where the start vector now lives
         int zst;    // ZState of the current iterate if it is one of the unit's own buffers, else -1
-        if (u.start_kind == kStartZero) zst = kZZero;
-        else if (u.start_kind == kStartOwn) zst = *zstate_row;
-        else if (u.start_kind == kStartTruth || u.start_kind == kStartSharedKeep) { zst = kZA; u.zcur = u.zA; }
+        if (cur.start_kind == kStartZero) zst = kZZero;
+        else if (cur.start_kind == kStartOwn) zst = *zstate_row;
+        else if (cur.start_kind == kStartTruth || cur.start_kind == kStartSharedKeep) { zst = kZA; cur.zcur = cur.zA; }
         else zst = -1;
 
         int status = MUSE_STATUS_G_CONVERGED;
@@ -554,7 +630,7 @@ struct Solver {
         bool converged = gmax <= L.atol;
         if (stopped) status = MUSE_STATUS_NONFINITE;
 
-        // L-BFGS bookkeeping (registers / local arrays; m ≤ 16)
+        // L-BFGS bookkeeping (m ≤ 16)
         double rho[16], dxdg_h[16], dgdg_h[16], alpha_tl[16];
         int pseudo_iter = 0;
         int counter_f_tol = 0;
@@ -564,16 +640,16 @@ struct Solver {
             pseudo_iter += 1;
             double dphi_0;
             if (pseudo_iter > 1) {
-                lazy_s = false;
+                cur.lazy = 0;
                 dphi_0 = twoloop(pseudo_iter, rho, dxdg_h, dgdg_h, alpha_tl);
                 pre_valid = false;
             } else {
-                lazy_s = true;
+                cur.lazy = 1;
                 dphi_0 = -gg;
             }
             if (dphi_0 >= 0.0 && pseudo_iter > 1) {      // reset_search_direction!
                 pseudo_iter = 1;
-                lazy_s = true;
+                cur.lazy = 1;
                 dphi_0 = -gg;
             }
             const double phi_0 = f;
@@ -581,27 +657,34 @@ struct Solver {
             com_alpha = NAN;
             last_eval_alpha = NAN;
             double alpha, phi_alpha;
-            const int ls = hager_zhang(1.0, phi_0, dphi_0, alpha, phi_alpha);
+            const int ls = hager_zhang(1.0, phi_0, dphi_0, alpha, phi_alpha);   // InitialStatic(alpha = 1)
             pre_valid = false;
 
-            const double* zprev = u.zcur;
+            const double* zprev = cur.zcur;
             if (alpha == 0.0) {
-                // x unchanged (dx = 0): value_gradient! is a cache hit only if 0 was the last point
-                com.xchg = 0.0;
+                com.xchg = 0.0;                           // x unchanged
                 if (ls != 0) { status = MUSE_STATUS_LS_FAILED; break; }
-                // f, gg, gmax, s1, s2 unchanged
             } else {
-                if (!(com_alpha == alpha)) accept_sweep(alpha, ls == 0 && !(last_eval_alpha == alpha));
+                if (!(com_alpha == alpha)) {              // accepted point is not the last committed trial
+                    const bool need_eval = (ls == 0) && !(last_eval_alpha == alpha);
+                    cur.op = kOpTrial;
+                    cur.c = alpha;
+                    cur.commit = 1;
+                    issue(red);
+                    com.e = red[0]; com.dphi = red[1]; com.gg = red[2]; com.gmax = red[3];
+                    com.s1 = red[4]; com.s2 = red[5]; com.xchg = red[6];
+                    com_alpha = alpha;
+                    if (need_eval) fg_evals += 1;
+                }
                 // flip buffers
-                double* newcur = u.zalt;
-                u.zalt = u.zother;
-                u.zother = newcur;
-                u.zcur = newcur;
-                zst = (newcur == u.zA) ? kZA : kZB;
+                double* newcur = cur.zalt;
+                cur.zalt = zother;
+                zother = newcur;
+                cur.zcur = newcur;
+                zst = (newcur == cur.zA) ? kZA : kZB;
                 if (ls != 0) {      // linesearch exception: x moved, objective not re-evaluated
                     status = MUSE_STATUS_LS_FAILED;
-                    // report the score at the point actually returned
-                    s1 = com.s1; s2 = com.s2; gmax = com.gmax;
+                    s1 = com.s1; s2 = com.s2; gmax = com.gmax;   // report at the point returned
                     break;
                 }
                 f = fma(0.5, com.e, ev.half_cst);
@@ -610,7 +693,7 @@ struct Solver {
                 s1 = com.s1;
                 s2 = com.s2;
             }
-            // assess_convergence
+            // assess_convergence  [EXT Optim.jl]
             const bool x_conv = com.xchg <= 0.0;
             const bool f_conv = fabs(f - f_prev) <= 0.0;
             const bool g_conv = gmax <= L.atol;
@@ -624,8 +707,14 @@ struct Solver {
                     pseudo_iter = 0;                     // dx·dg = 0 ⇒ rho = Inf
                 } else {
                     const int idx = (pseudo_iter - 1) % L.lbfgs_m;
-                    double dxdg, dgdg;
-                    history_sweep(alpha, zprev, u.zcur, idx, dxdg, dgdg);
+                    cur.op = kOpHist;
+                    cur.c = alpha;
+                    cur.v1 = zprev;
+                    cur.v2 = cur.zcur;
+                    cur.w1 = dxh + (size_t)idx * L.ld;
+                    cur.w2 = dgh + (size_t)idx * L.ld;
+                    issue(red);
+                    const double dxdg = red[0], dgdg = red[1];
                     const double rho_it = 1.0 / dxdg;
                     if (isinf(rho_it)) pseudo_iter = 0;
                     else { rho[idx] = rho_it; dxdg_h[idx] = dxdg; dgdg_h[idx] = dgdg; }
@@ -636,8 +725,7 @@ struct Solver {
             status = MUSE_STATUS_MAXITER;
 
         // outputs
-        const bool leader = (grp.tid == 0);
-        if (leader) {
+        if (grp.tid == 0) {
             if (zstate_row && zst >= 0) *zstate_row = zst;
             double* g = L.g_out + (size_t)item * L.ntheta;
             if (L.family == MUSE_FAMILY_FUNNEL) {
@@ -652,7 +740,74 @@ struct Solver {
             L.f_out[item] = f;
             L.status_out[item] = status;
         }
-        (void)row;
+    }
+
+    // ------------------------------------------------------------------ unit setup
+    __device__ __noinline__ void run_items() {
+        const int gi = grp.group_index();
+        const int gn = grp.group_count();
+        const size_t ld = (size_t)L.ld;
+        cur.sbuf = L.sbuf + (size_t)gi * ld;
+        dxh = L.dxh + (size_t)gi * L.lbfgs_m * ld;
+        dgh = L.dgh + (size_t)gi * L.lbfgs_m * ld;
+        cur.v1 = cur.v2 = nullptr;
+        cur.w1 = cur.w2 = nullptr;
+        cur.c = 0.0;
+
+        const double* zshared = L.zshared;
+        if (L.zshared_state) {       // shared start = result of an earlier launch (fiducial ẑ)
+            const int st = *L.zshared_state;
+            zshared = st == kZA ? L.zsharedA : (st == kZB ? L.zsharedB : nullptr);
+        }
+
+        for (int item = gi; item < L.nitems; item += gn) {
+            int row, draw, tsel = 0;
+            if (L.mode == 0) {
+                if (L.include_data && item == 0) { row = 0; draw = -1; }
+                else {
+                    const int k = L.first_sim + item - (L.include_data ? 1 : 0);
+                    row = 1 + k;
+                    draw = k;
+                }
+            } else if (L.mode == 1) {
+                // finite-difference virtual sims: item = (k·ntheta + n)·2 + sgn, θ_sim = smp[2n + sgn]
+                tsel = item % (2 * L.ntheta);
+                row = item;
+                draw = item / (2 * L.ntheta);
+            } else {
+                // the master stream's own draw (fiducial solve of get_H!, src/muse.jl:418)
+                row = 0;
+                draw = L.master_row;
+            }
+            cur.smp = L.smp[tsel];
+            cur.start_kind = (draw < 0 && L.start_kind == kStartTruth) ? kStartZero : L.start_kind;
+            cur.xi = draw >= 0 ? L.xi + (size_t)draw * ld : nullptr;
+            cur.nu = draw >= 0 ? L.nu + (size_t)draw * ld : nullptr;
+            cur.xw = draw >= 0 ? L.x + (size_t)row * ld : nullptr;
+            cur.xsrc = draw >= 0 ? cur.xw : L.xdat;
+            double* zA = L.zA + (size_t)row * ld;
+            double* zB = L.zB + (size_t)row * ld;
+            cur.zA = zA;
+            int* zs = L.zstate ? L.zstate + row : nullptr;
+            switch (cur.start_kind) {
+                case kStartOwn: {
+                    const int st = *zs;
+                    cur.zcur = st == kZZero ? nullptr : (st == kZA ? zA : zB);
+                    cur.zalt = st == kZA ? zB : zA;
+                    zother = st == kZA ? zA : zB;
+                    break;
+                }
+                case kStartShared:
+                    cur.zcur = zshared; cur.zalt = zA; zother = zB; break;
+                case kStartSharedKeep:
+                    cur.zcur = zshared; cur.zalt = zB; zother = zA; break;
+                case kStartTruth:
+                    cur.zcur = nullptr; cur.zalt = zB; zother = zA; break;
+                default:   // zeros
+                    cur.zcur = nullptr; cur.zalt = zA; zother = zB; break;
+            }
+            solve(item, zs);
+        }
     }
 };
 
@@ -661,65 +816,25 @@ __global__ void __launch_bounds__(CTA_THREADS, (CTA_THREADS >= 1024 ? 1 : (CTA_T
 iso_solver_kernel(const __grid_constant__ SolveLaunch L) {
     using G = Group<CTA_THREADS, WARP_GROUP, CLUSTER>;
     __shared__ typename G::Smem smem;
+    __shared__ Cmd scmd;
     G grp(&smem);
-    Solver<G> S(grp, L);
-    const int gi = grp.group_index();
-    const int gn = grp.group_count();
-    const size_t ld = (size_t)L.ld;
-    S.sbuf = L.sbuf + (size_t)gi * ld;
-    S.dxh = L.dxh + (size_t)gi * L.lbfgs_m * ld;
-    S.dgh = L.dgh + (size_t)gi * L.lbfgs_m * ld;
 
-    for (int item = gi; item < L.nitems; item += gn) {
-        Unit& u = S.u;
-        int row;
-        int draw;     // row in xi/nu, -1 = observed data
-        int tsel = 0;
-        if (L.mode == 0) {
-            if (L.include_data && item == 0) { row = 0; draw = -1; }
-            else {
-                const int k = L.first_sim + item - (L.include_data ? 1 : 0);
-                row = 1 + k;
-                draw = k;
-            }
-        } else if (L.mode == 1) {
-            // finite-difference virtual sims: item = (k·ntheta + n)·2 + sgn, θ_sim = smp[2n + sgn]
-            tsel = item % (2 * L.ntheta);
-            row = item;
-            draw = item / (2 * L.ntheta);
-        } else {
-            // the master stream's own draw (fiducial solve of get_H!, src/muse.jl:418)
-            row = 0;
-            draw = L.master_row;
+    if (WARP_GROUP || (threadIdx.x >> 5) == 0) {
+        // controller warp (every warp, for warp groups)
+        Controller<G> ctl(grp, L, &scmd);
+        ctl.run_items();
+        if (!WARP_GROUP) {
+            if ((threadIdx.x & 31) == 0) scmd.op = kOpExit;
+            G::cmd_barrier();
         }
-        u.smp = L.smp[tsel];
-        u.start_kind = (draw < 0 && L.start_kind == kStartTruth) ? kStartZero : L.start_kind;
-        u.xi = draw >= 0 ? L.xi + (size_t)draw * ld : nullptr;
-        u.nu = draw >= 0 ? L.nu + (size_t)draw * ld : nullptr;
-        u.xw = draw >= 0 ? L.x + (size_t)row * ld : nullptr;
-        u.xsrc = draw >= 0 ? u.xw : L.xdat;
-        u.zA = L.zA + (size_t)row * ld;
-        double* zB = L.zB + (size_t)row * ld;
-        int* zs = L.zstate ? L.zstate + row : nullptr;
-        switch (u.start_kind) {
-            case kStartOwn: {
-                const int st = *zs;
-                u.zcur = st == kZZero ? nullptr : (st == kZA ? u.zA : zB);
-                u.zalt = st == kZA ? zB : u.zA;
-                u.zother = st == kZA ? u.zA : zB;
-                if (st == kZZero) { u.zalt = u.zA; u.zother = zB; }
-                break;
-            }
-            case kStartShared:
-                u.zcur = L.zshared; u.zalt = u.zA; u.zother = zB; break;
-            case kStartSharedKeep:
-                u.zcur = L.zshared; u.zalt = zB; u.zother = u.zA; break;
-            case kStartTruth:
-                u.zcur = nullptr; u.zalt = zB; u.zother = u.zA; break;
-            default:   // zeros
-                u.zcur = nullptr; u.zalt = u.zA; u.zother = zB; break;
+    } else {
+        // worker warps: execute the sweeps the controller broadcasts
+        for (;;) {
+            G::cmd_barrier();
+            if (scmd.op == kOpExit) break;
+            double red[7];
+            run_op(grp, L, scmd, red);
         }
-        S.solve(item, row, zs);
     }
     if (CLUSTER > 1) cg::this_cluster().sync();   // keep DSMEM alive until every CTA is done
 }

@@ -48,8 +48,8 @@ class MuseResult:
     Sigma: Optional[np.ndarray] = None
     dist: Optional[tuple] = None
     history: list = field(default_factory=list)
-    gs: list = field(default_factory=list)
-    Hs: list = field(default_factory=list)
+    gs: object = field(default_factory=list)      # N×nθ array once filled (one row per sim)
+    Hs: object = field(default_factory=list)      # n_H×nθ×nθ array once filled
     metadata: dict = field(default_factory=dict)
     rng: object = None
     time: float = 0.0
@@ -184,7 +184,7 @@ def muse_(result: MuseResult, prob: AbstractMuseProblem, theta0=None, **kwargs):
         theta = prob.standardize_theta(regularize(theta_unreg))                    # :226-227
 
         result.theta = theta_unreg.copy()                                          # :230
-        result.gs = [g.copy() for g in g_like_sims]                                # :231
+        result.gs = g_like_sims.copy()                                             # :231 (N×nθ array, one row per sim)
         result.time += t                                                           # :232
         if checkpoint_filename is not None and pool.rank == 0:                     # :234
             with open(checkpoint_filename, "wb") as fh:
@@ -239,8 +239,9 @@ def get_J_(result: MuseResult, prob: AbstractMuseProblem, theta0=None, **kwargs)
                 full[lo + bad] = np.nan
             allg = pool.allgather_rows(full, nsims)[nsims_existing:]
             g_new = allg[~np.isnan(allg).any(axis=1)]
-        result.gs.extend(g.copy() for g in g_new)
-    gs = np.array(result.gs)
+        old = np.asarray(result.gs, dtype=np.float64).reshape(-1, prob.ntheta)
+        result.gs = np.concatenate([old, np.asarray(g_new).reshape(-1, prob.ntheta)], axis=0)
+    gs = np.asarray(result.gs, dtype=np.float64).reshape(-1, prob.ntheta)
     if theta0.size == 1:
         result.J = np.array([[np.var(gs[:, 0], ddof=1)]])                          # :529 var
     else:
@@ -282,7 +283,7 @@ def get_H_(result: MuseResult, prob: AbstractMuseProblem, theta0=None, **kwargs)
         return result
     t0 = time.perf_counter()
     if step is None and len(result.gs) > 0:                                        # :411-413
-        step = 0.1 / np.std(np.array(result.gs), axis=0, ddof=1)
+        step = 0.1 / np.std(np.asarray(result.gs, dtype=np.float64).reshape(-1, prob.ntheta), axis=0, ddof=1)
     if step is None:
         raise MuseBackendError(-5, "get_H!: pass `step` or run get_J!/muse! first; FiniteDifferences' adaptive "
                                    "step estimation is not provided")
@@ -302,9 +303,10 @@ def get_H_(result: MuseResult, prob: AbstractMuseProblem, theta0=None, **kwargs)
         flat[bad_local] = np.nan
     allH = pool.allgather_rows(flat, nsims_remaining)
     allH = allH[~np.isnan(allH).any(axis=1)]
-    result.Hs.extend(h.reshape(nt, nt).copy() for h in allH)
+    oldH = np.asarray(result.Hs, dtype=np.float64).reshape(-1, nt, nt)
+    result.Hs = np.concatenate([oldH, allH.reshape(-1, nt, nt)], axis=0)           # (n_H × nθ × nθ array)
 
-    result.H = np.mean(np.array(result.Hs), axis=0)                                # :446
+    result.H = np.mean(result.Hs, axis=0)                                          # :446
     result.time += time.perf_counter() - t0
     finalize_result_(result, prob)
     return result

@@ -89,10 +89,11 @@ class SimpleMuseProblem(AbstractMuseProblem):
     family   "funnel" | "hiergauss" | "corrgauss"
     prior    object with ``logp/grad/hess`` (``logPriorθ``); default flat
     group, cluster   solver geometry overrides (0 = auto), see DESIGN.md §3
+    stream   raw cudaStream_t to launch on (e.g. ``torch.cuda.current_stream().cuda_stream``)
     """
 
     def __init__(self, x, family: str = "funnel", prior=None, *, P=None, L=None, group: int = 0,
-                 cluster: int = 0, backend_factory=None):
+                 cluster: int = 0, stream=None, backend_factory=None):
         if family not in FAMILY_NTHETA:
             raise MuseBackendError(-5, f"model family {family!r} is not registered with the B200 backend; "
                                        "Turing/Soss-defined models are not supported and there is no CPU fallback")
@@ -108,6 +109,9 @@ class SimpleMuseProblem(AbstractMuseProblem):
         self._backend_factory = backend_factory or B200Backend
         self._backend = None
         self._backend_key = None
+        self._rng_key = None
+        self._data_dirty = True
+        self.stream = stream
 
     # src/interface.jl:134
     def standardize_theta(self, theta):
@@ -120,31 +124,45 @@ class SimpleMuseProblem(AbstractMuseProblem):
         return self.prior.logp(theta)
 
     # ------------------------------------------------------------------ backend management
+    def set_data(self, x):
+        """Replace the observed data (host buffer); uploaded on the next backend use."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        if x.shape != (self.d,):
+            raise ValueError("x has the wrong length")
+        self.x = x
+        self._data_dirty = True
+
     def backend_for(self, nsims_total: int, rng, pool, nsims_h_total: int = 0):
         """Handle holding this rank's shard of ``nsims_total`` sims (and of the first
-        ``nsims_h_total`` sims for get_H!) with the draws of ``rng`` installed."""
+        ``nsims_h_total`` sims for get_H!) with the draws of ``rng`` installed.  The handle (device
+        memory) is reused while the shard geometry is unchanged; a new ``rng`` only re-installs draws."""
         off, cnt = pool.shard(nsims_total)
         hoff, hcnt = pool.shard(nsims_h_total) if (pool.world > 1 and nsims_h_total > 0) else (0, 0)
-        key = (nsims_total, off, cnt, hoff, hcnt, id(rng) if not isinstance(rng, (int, np.integer)) else int(rng),
-               pool.device)
-        if self._backend is not None and self._backend_key == key:
-            return self._backend
-        if self._backend is not None:
-            self._backend.close()
-        be = self._backend_factory(self.family, self.d, cnt, sim_offset=off, nsims_h=hcnt, h_sim_offset=hoff,
-                                   device=pool.device, group=self.group, cluster=self.cluster, P=self.P, L=self.L)
-        be.set_data(self.x)
-        if isinstance(rng, (int, np.integer)):
-            be.seed_draws(int(rng))
-        elif isinstance(rng, BaseDraws):
-            if rng.xi.shape[0] < nsims_total:
-                raise ValueError("BaseDraws holds fewer simulations than requested")
-            be.set_draws(rng.xi[off:off + cnt], rng.nu[off:off + cnt], rng.xi_master, rng.nu_master)
-            if hcnt:
-                be.set_draws_h(rng.xi[hoff:hoff + hcnt], rng.nu[hoff:hoff + hcnt])
-        else:
-            raise TypeError("rng must be an integer seed or a BaseDraws")
-        self._backend, self._backend_key = be, key
+        gkey = (nsims_total, off, cnt, hoff, hcnt, pool.device)
+        rkey = ("seed", int(rng)) if isinstance(rng, (int, np.integer)) else ("draws", id(rng))
+        if self._backend is None or self._backend_key != gkey:
+            if self._backend is not None:
+                self._backend.close()
+            self._backend = self._backend_factory(
+                self.family, self.d, cnt, sim_offset=off, nsims_h=hcnt, h_sim_offset=hoff, device=pool.device,
+                group=self.group, cluster=self.cluster, stream=self.stream, P=self.P, L=self.L)
+            self._backend_key, self._rng_key, self._data_dirty = gkey, None, True
+        be = self._backend
+        if self._data_dirty:
+            be.set_data(self.x)
+            self._data_dirty = False
+        if self._rng_key != rkey:
+            if isinstance(rng, (int, np.integer)):
+                be.seed_draws(int(rng))
+            elif isinstance(rng, BaseDraws):
+                if rng.xi.shape[0] < nsims_total:
+                    raise ValueError("BaseDraws holds fewer simulations than requested")
+                be.set_draws(rng.xi[off:off + cnt], rng.nu[off:off + cnt], rng.xi_master, rng.nu_master)
+                if hcnt:
+                    be.set_draws_h(rng.xi[hoff:hoff + hcnt], rng.nu[hoff:hoff + hcnt])
+            else:
+                raise TypeError("rng must be an integer seed or a BaseDraws")
+            self._rng_key = rkey
         return be
 
     def close(self):

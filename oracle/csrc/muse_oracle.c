@@ -17,16 +17,17 @@
  * Gradients are analytic (the reference differentiates logLike with ForwardDiff/Zygote,
  * src/simple.jl:84-85, which is strictly slower: ⌈d/12⌉ sweeps per ∇z with ForwardDiff).
  *
- * Units are independent; they are distributed over OpenMP threads (the reference's default pool
- * is a serial map, src/util.jl:73-76; its parallel path is Distributed.pmap over processes).
+ * Units are independent; they are distributed dynamically over POSIX threads (libgomp is not in
+ * this image).  The reference's default pool is a serial map, src/util.jl:73-76; its parallel path
+ * is Distributed.pmap over processes.
  */
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
-#ifdef _OPENMP
-#include <omp.h>
-#endif
+#include <pthread.h>
+#include <stdatomic.h>
+#include <unistd.h>
 
 #define FAM_FUNNEL 1
 #define FAM_HIER 2
@@ -357,66 +358,87 @@ static int lbfgs(work_t* w, const model_t* mdl, const double* xdata, double g_to
 /* ---- batch entry point -------------------------------------------------------------------
  * start_mode: 0 zeros, 1 z_inout holds the start (previous ẑ), 2 truth (simulated z).
  * z_inout: units × d (may be NULL for modes 0/2 if MAPs are not wanted). */
+typedef struct {
+    int family, d, nsims, ntheta, units, include_data, start_mode;
+    const double *xi, *nu, *xdat;
+    double sig, smu, atol;
+    model_t mdl;
+    double *z_inout, *g_out, *gnorm_out;
+    int *iters_out, *fg_out, *status_out;
+    atomic_int next;
+} job_t;
+
+static void* worker(void* arg) {
+    job_t* J = (job_t*)arg;
+    const int d = J->d;
+    work_t* w = work_new(d, 10);
+    double* x = (double*)malloc(sizeof(double) * d);
+    for (;;) {
+        const int u = atomic_fetch_add(&J->next, 1);
+        if (u >= J->units) break;
+        const int is_data = J->include_data && u == 0;
+        const int k = u - (J->include_data ? 1 : 0);
+        const double* xs;
+        if (is_data) {
+            xs = J->xdat;
+            if (J->start_mode == 1) memcpy(w->x, J->z_inout + (size_t)u * d, sizeof(double) * d);
+            else memset(w->x, 0, sizeof(double) * d);
+        } else {
+            const double *xk = J->xi + (size_t)k * d, *nk = J->nu + (size_t)k * d;
+            for (int j = 0; j < d; ++j) {
+                const double zt = J->smu + J->sig * xk[j];
+                x[j] = zt + nk[j];
+                if (J->start_mode == 2) w->x[j] = zt;
+            }
+            xs = x;
+            if (J->start_mode == 1) memcpy(w->x, J->z_inout + (size_t)u * d, sizeof(double) * d);
+            else if (J->start_mode == 0) memset(w->x, 0, sizeof(double) * d);
+        }
+        int fc = 0, st = 0;
+        double gres = 0.0;
+        const int it = lbfgs(w, &J->mdl, xs, J->atol, 1000, &fc, &gres, &st);
+        score(&J->mdl, w->x, J->g_out + (size_t)u * J->ntheta);
+        if (J->z_inout) memcpy(J->z_inout + (size_t)u * d, w->x, sizeof(double) * d);
+        if (J->iters_out) J->iters_out[u] = it;
+        if (J->fg_out) J->fg_out[u] = fc;
+        if (J->gnorm_out) J->gnorm_out[u] = gres;
+        if (J->status_out) J->status_out[u] = st;
+    }
+    free(x);
+    work_free(w);
+    return NULL;
+}
+
+int muse_oracle_max_threads(void) {
+    const long n = sysconf(_SC_NPROCESSORS_ONLN);
+    return n > 0 ? (int)n : 1;
+}
+
 int muse_oracle_map_score(int family, int d, int nsims, const double* xi, const double* nu, const double* xdat,
                           const double* theta_sim, const double* theta_eval, double atol, int include_data,
                           int start_mode, double* z_inout, double* g_out, int* iters_out, int* fg_out,
                           double* gnorm_out, int* status_out, int nthreads) {
     if (family != FAM_FUNNEL && family != FAM_HIER) return -5;
-    const int ntheta = family == FAM_FUNNEL ? 1 : 2;
-    const int units = nsims + (include_data ? 1 : 0);
-    model_t mdl;
-    model_at(&mdl, family, d, theta_eval);
-    const double sig = family == FAM_FUNNEL ? exp(0.5 * theta_sim[0]) : exp(theta_sim[1]);
-    const double smu = family == FAM_FUNNEL ? 0.0 : theta_sim[0];
-#ifdef _OPENMP
-    if (nthreads > 0) omp_set_num_threads(nthreads);
-#else
-    (void)nthreads;
-#endif
-#pragma omp parallel
-    {
-        work_t* w = work_new(d, 10);
-        double* x = (double*)malloc(sizeof(double) * d);
-#pragma omp for schedule(dynamic, 1)
-        for (int u = 0; u < units; ++u) {
-            const int is_data = include_data && u == 0;
-            const int k = u - (include_data ? 1 : 0);
-            const double* xs;
-            if (is_data) {
-                xs = xdat;
-                if (start_mode == 1) memcpy(w->x, z_inout + (size_t)u * d, sizeof(double) * d);
-                else memset(w->x, 0, sizeof(double) * d);
-            } else {
-                const double *xk = xi + (size_t)k * d, *nk = nu + (size_t)k * d;
-                for (int j = 0; j < d; ++j) {
-                    const double zt = smu + sig * xk[j];
-                    x[j] = zt + nk[j];
-                    if (start_mode == 2) w->x[j] = zt;
-                }
-                xs = x;
-                if (start_mode == 1) memcpy(w->x, z_inout + (size_t)u * d, sizeof(double) * d);
-                else if (start_mode == 0) memset(w->x, 0, sizeof(double) * d);
-            }
-            int fc = 0, st = 0;
-            double gres = 0.0;
-            const int it = lbfgs(w, &mdl, xs, atol, 1000, &fc, &gres, &st);
-            score(&mdl, w->x, g_out + (size_t)u * ntheta);
-            if (z_inout) memcpy(z_inout + (size_t)u * d, w->x, sizeof(double) * d);
-            if (iters_out) iters_out[u] = it;
-            if (fg_out) fg_out[u] = fc;
-            if (gnorm_out) gnorm_out[u] = gres;
-            if (status_out) status_out[u] = st;
-        }
-        free(x);
-        work_free(w);
-    }
+    job_t J;
+    memset(&J, 0, sizeof(J));
+    J.family = family; J.d = d; J.nsims = nsims;
+    J.ntheta = family == FAM_FUNNEL ? 1 : 2;
+    J.include_data = include_data ? 1 : 0;
+    J.units = nsims + J.include_data;
+    J.start_mode = start_mode;
+    J.xi = xi; J.nu = nu; J.xdat = xdat; J.atol = atol;
+    model_at(&J.mdl, family, d, theta_eval);
+    J.sig = family == FAM_FUNNEL ? exp(0.5 * theta_sim[0]) : exp(theta_sim[1]);
+    J.smu = family == FAM_FUNNEL ? 0.0 : theta_sim[0];
+    J.z_inout = z_inout; J.g_out = g_out; J.gnorm_out = gnorm_out;
+    J.iters_out = iters_out; J.fg_out = fg_out; J.status_out = status_out;
+    atomic_init(&J.next, 0);
+    int nt = nthreads > 0 ? nthreads : muse_oracle_max_threads();
+    if (nt > J.units) nt = J.units > 0 ? J.units : 1;
+    if (nt <= 1) { worker(&J); return 0; }
+    pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * nt);
+    for (int i = 0; i < nt; ++i) pthread_create(&th[i], NULL, worker, &J);
+    for (int i = 0; i < nt; ++i) pthread_join(th[i], NULL);
+    free(th);
     return 0;
-}
-
-int muse_oracle_max_threads(void) {
-#ifdef _OPENMP
-    return omp_get_max_threads();
-#else
-    return 1;
-#endif
 }
