@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--family", default="funnel", choices=["funnel", "hiergauss"])
     ap.add_argument("--group", type=int, default=0)
     ap.add_argument("--cluster", type=int, default=0)
+    ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 register-loop, 2 TMA, 3 TMA + resident x")
     ap.add_argument("--cpu-sims", type=int, default=0, help="sims in the bounded CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -193,7 +194,7 @@ def run_b200(args):
     torch.cuda.set_stream(stream)
     x_host = torch.from_numpy(observed_data(family, d)).pin_memory()
     prior = m.NormalPrior(0, 3) if family == "funnel" else m.FlatPrior()
-    prob = m.SimpleMuseProblem(x_host.numpy(), family, prior, group=args.group, cluster=args.cluster,
+    prob = m.SimpleMuseProblem(x_host.numpy(), family, prior, group=args.group, cluster=args.cluster, kernel=args.kernel,
                                stream=stream.cuda_stream)
     th0 = theta_start(family)
 

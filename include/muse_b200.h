@@ -79,7 +79,8 @@ typedef struct muse_cfg {
     int64_t sim_offset;      /* global index of local simulation 0 */
     int32_t nsims_h;         /* sims of the get_H! shard held as extra draw rows; 0 → the H shard is the
                                 first sims of the local shard (single-GPU default) */
-    int32_t reserved0;
+    int32_t kernel;          /* solver kernel: 0 auto, 1 register-loop, 2 TMA pipeline, 3 TMA pipeline with x
+                                resident in cluster shared memory */
     int64_t h_sim_offset;    /* global index of H-shard simulation 0 (used when nsims_h > 0) */
     int32_t lbfgs_m;         /* L-BFGS memory; 0 → 10 (Optim.LBFGS default) */
     int32_t max_iters;       /* 0 → 1000 (Optim.Options default) */

@@ -31,7 +31,7 @@ class muse_cfg(C.Structure):
     _fields_ = [
         ("abi_version", C.c_int32), ("family", C.c_int32), ("d", C.c_int32), ("ntheta", C.c_int32),
         ("nsims", C.c_int32), ("device", C.c_int32), ("sim_offset", C.c_int64),
-        ("nsims_h", C.c_int32), ("reserved0", C.c_int32), ("h_sim_offset", C.c_int64),
+        ("nsims_h", C.c_int32), ("kernel", C.c_int32), ("h_sim_offset", C.c_int64),
         ("lbfgs_m", C.c_int32), ("max_iters", C.c_int32), ("group", C.c_int32), ("cluster", C.c_int32),
         ("P", c_double_p), ("L", c_double_p), ("stream", C.c_void_p),
     ]

@@ -34,7 +34,7 @@ def _ip(arr):
 class B200Backend:
     def __init__(self, family: str, d: int, nsims: int, *, sim_offset: int = 0, nsims_h: int = 0,
                  h_sim_offset: int = 0, device: int = 0, group: int = 0, cluster: int = 0, stream=None,
-                 lbfgs_m: int = 0, max_iters: int = 0, P=None, L=None):
+                 lbfgs_m: int = 0, max_iters: int = 0, kernel: int = 0, P=None, L=None):
         if family not in FAMILY_IDS:
             raise MuseBackendError(-5, f"model family {family!r} is outside the registered families "
                                        f"{sorted(FAMILY_IDS)}; Turing/Soss-defined models are not supported")
@@ -46,7 +46,7 @@ class B200Backend:
         self._L = _f64(L, (d, d)) if L is not None else None
         cfg = _capi.muse_cfg(
             abi_version=_capi.ABI_VERSION, family=FAMILY_IDS[family], d=self.d, ntheta=self.ntheta,
-            nsims=self.nsims, device=int(device), sim_offset=int(sim_offset), nsims_h=self.nsims_h, reserved0=0,
+            nsims=self.nsims, device=int(device), sim_offset=int(sim_offset), nsims_h=self.nsims_h, kernel=int(kernel),
             h_sim_offset=int(h_sim_offset), lbfgs_m=int(lbfgs_m), max_iters=int(max_iters), group=int(group),
             cluster=int(cluster), P=_dp(self._P), L=_dp(self._L), stream=C.c_void_p(stream) if stream else None)
         self._h = C.c_void_p()

@@ -29,7 +29,8 @@ struct muse_handle {
     double *xi_h = nullptr, *nu_h = nullptr;      // nsims_h × ld: draws of the get_H! shard (multi-GPU)
     bool have_draws_h = false;
     double *xdat = nullptr, *z0user = nullptr;    // ld
-    double *x = nullptr, *zA = nullptr, *zB = nullptr;   // rows × ld
+    double *xslot = nullptr;                             // slots × ld (x of the unit in flight, per group)
+    double *zA = nullptr, *zB = nullptr;                 // rows × ld
     int* zstate = nullptr;                        // rows
     double *sbuf = nullptr, *dxh = nullptr, *dgh = nullptr;   // per-slot scratch
     // outputs (device + pinned host mirror), capacity out_cap items
@@ -40,8 +41,8 @@ struct muse_handle {
     int *iters_h = nullptr, *fg_h = nullptr, *status_h = nullptr;
     // finite-difference scratch
     int h_cap = 0;
-    double *xH = nullptr, *zHA = nullptr, *zHB = nullptr;
-    double *xfid = nullptr, *zfidA = nullptr, *zfidB = nullptr;
+    double *zHA = nullptr, *zHB = nullptr;
+    double *zfidA = nullptr, *zfidB = nullptr;
     int* zfid_state = nullptr;
 
     // profiling
@@ -120,6 +121,11 @@ static void fill_common(muse_handle* h, SolveLaunch& L) {
     L.xdat = h->xdat;
     L.master_row = h->cfg.nsims;
     L.sbuf = h->sbuf;
+    L.xslot = h->xslot;
+    L.ch = h->geo.ch;
+    L.stages = h->geo.stages;
+    L.resident = h->geo.resident;
+    L.slice_cap = h->geo.slice_cap;
     L.dxh = h->dxh;
     L.dgh = h->dgh;
     L.g_out = h->g_d;
@@ -137,7 +143,8 @@ static int launch_solver(muse_handle* h, const SolveLaunch& L, double bytes) {
         CUDA_TRY(h, cudaEventCreate(&r.b));
         CUDA_TRY(h, cudaEventRecord(r.a, h->stream));
     }
-    CUDA_TRY(h, launch_iso_solver(L, h->geo, h->stream));
+    if (h->geo.tma) CUDA_TRY(h, launch_iso_tma(L, h->geo, h->stream));
+    else CUDA_TRY(h, launch_iso_solver(L, h->geo, h->stream));
     h->acc.launches += 1;
     h->acc.solve_launches += 1;
     if (h->prof) {
@@ -215,7 +222,16 @@ int muse_b200_create(const muse_cfg* cfg, muse_handle** out) {
         CREATE_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         h->own_stream = true;
     }
-    CREATE_TRY(iso_solver_geometry(cfg->d, cfg->group, cfg->cluster, cfg->device, &h->geo));
+    {
+        // kernel choice: small d → one warp per unit, register loops; large d → TMA pipeline
+        int kernel = cfg->kernel;
+        if (kernel == 0) kernel = (cfg->d <= 4096 || cfg->group == 32) ? 1 : 2;
+        if (kernel == 1) {
+            CREATE_TRY(iso_solver_geometry(cfg->d, cfg->group, cfg->cluster, cfg->device, &h->geo));
+        } else {
+            CREATE_TRY(iso_tma_geometry(cfg->d, h->ld, cfg->group, cfg->cluster, kernel == 3 ? 1 : 0, cfg->device, &h->geo));
+        }
+    }
 
     const size_t ld = (size_t)h->ld, rows = (size_t)h->rows, B = sizeof(double);
     CREATE_TRY(cudaMalloc(&h->xi, rows * ld * B));
@@ -228,15 +244,14 @@ int muse_b200_create(const muse_cfg* cfg, muse_handle** out) {
     }
     CREATE_TRY(cudaMalloc(&h->xdat, ld * B));
     CREATE_TRY(cudaMalloc(&h->z0user, ld * B));
-    CREATE_TRY(cudaMalloc(&h->x, rows * ld * B));
     CREATE_TRY(cudaMalloc(&h->zA, rows * ld * B));
     CREATE_TRY(cudaMalloc(&h->zB, rows * ld * B));
     CREATE_TRY(cudaMalloc(&h->zstate, rows * sizeof(int)));
     const size_t slots = (size_t)h->geo.groups, m = (size_t)h->cfg.lbfgs_m;
+    CREATE_TRY(cudaMalloc(&h->xslot, slots * ld * B));
     CREATE_TRY(cudaMalloc(&h->sbuf, slots * ld * B));
     CREATE_TRY(cudaMalloc(&h->dxh, slots * m * ld * B));
     CREATE_TRY(cudaMalloc(&h->dgh, slots * m * ld * B));
-    CREATE_TRY(cudaMalloc(&h->xfid, ld * B));
     CREATE_TRY(cudaMalloc(&h->zfidA, ld * B));
     CREATE_TRY(cudaMalloc(&h->zfidB, ld * B));
     CREATE_TRY(cudaMalloc(&h->zfid_state, sizeof(int)));
@@ -259,12 +274,12 @@ int muse_b200_destroy(muse_handle* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (auto& r : h->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     cudaFree(h->xi); cudaFree(h->nu); cudaFree(h->xi_h); cudaFree(h->nu_h); cudaFree(h->xdat); cudaFree(h->z0user);
-    cudaFree(h->x); cudaFree(h->zA); cudaFree(h->zB); cudaFree(h->zstate);
+    cudaFree(h->xslot); cudaFree(h->zA); cudaFree(h->zB); cudaFree(h->zstate);
     cudaFree(h->sbuf); cudaFree(h->dxh); cudaFree(h->dgh);
     cudaFree(h->g_d); cudaFree(h->gnorm_d); cudaFree(h->f_d); cudaFree(h->iters_d); cudaFree(h->fg_d); cudaFree(h->status_d);
     cudaFreeHost(h->g_h); cudaFreeHost(h->gnorm_h); cudaFreeHost(h->iters_h); cudaFreeHost(h->fg_h); cudaFreeHost(h->status_h);
-    cudaFree(h->xH); cudaFree(h->zHA); cudaFree(h->zHB);
-    cudaFree(h->xfid); cudaFree(h->zfidA); cudaFree(h->zfidB); cudaFree(h->zfid_state);
+    cudaFree(h->zHA); cudaFree(h->zHB);
+    cudaFree(h->zfidA); cudaFree(h->zfidB); cudaFree(h->zfid_state);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     cudaGetLastError();
     delete h;
@@ -399,7 +414,6 @@ int muse_b200_map_score_async(muse_handle* h, const double* theta_sim, const dou
         case MUSE_START_TRUTH: L.start_kind = kStartTruth; break;
         default: L.start_kind = kStartSharedKeep; L.zshared = h->z0user; break;
     }
-    L.x = h->x;
     L.zA = h->zA;
     L.zB = h->zB;
     L.zstate = h->zstate;
@@ -455,10 +469,9 @@ int muse_b200_fd_jacobian(muse_handle* h, const double* theta0, const double* st
     const int items = nsims_H * nt * 2;
     const size_t ld = (size_t)h->ld, B = sizeof(double);
     if (items > h->h_cap) {
-        cudaFree(h->xH); cudaFree(h->zHA); cudaFree(h->zHB);
-        h->xH = h->zHA = h->zHB = nullptr;
+        cudaFree(h->zHA); cudaFree(h->zHB);
+        h->zHA = h->zHB = nullptr;
         h->h_cap = 0;
-        CUDA_TRY(h, cudaMalloc(&h->xH, (size_t)items * ld * B));
         CUDA_TRY(h, cudaMalloc(&h->zHA, (size_t)items * ld * B));
         CUDA_TRY(h, cudaMalloc(&h->zHB, (size_t)items * ld * B));
         h->h_cap = items;
@@ -474,7 +487,6 @@ int muse_b200_fd_jacobian(muse_handle* h, const double* theta0, const double* st
     F.atol = atol;
     F.start_kind = kStartZero;
     if (theta_consts(h->cfg, theta0, theta0, &F.smp[0], &F.ev) != 0) MUSE_FAIL(h, MUSE_EUNSUPPORTED, "family");
-    F.x = h->xfid;
     F.zA = h->zfidA;
     F.zB = h->zfidB;
     F.zstate = h->zfid_state;
@@ -503,7 +515,6 @@ int muse_b200_fd_jacobian(muse_handle* h, const double* theta0, const double* st
             theta_consts(h->cfg, th, theta0, &L.smp[2 * n + s], nullptr);
         }
     }
-    L.x = h->xH;
     L.zA = h->zHA;
     L.zB = h->zHB;
     L.zstate = nullptr;

@@ -52,6 +52,11 @@ struct SolveLaunch {
     int start_kind;      // StartKind
     int lbfgs_m;
     int max_iters;
+    // TMA kernel geometry (muse_iso_tma.cu); all zero for the register-loop kernel
+    int ch;              // elements per pipeline chunk
+    int stages;          // pipeline depth
+    int resident;        // 1: the unit's x is kept in shared memory (never written to HBM on the fast path)
+    int slice_cap;       // elements of resident x per CTA
     double atol;
     IsoEval ev;                      // at θ_eval
     IsoSample smp[kMaxThetaSim];     // mode 0: [0]; mode 1: index 2n+s ↔ θ₀ ∓/± h_n e_n
@@ -67,7 +72,7 @@ struct SolveLaunch {
     const double* zsharedB;
     int master_row;      // row of the master draw in xi/nu
     // per-unit resident state (mode 0 rows: unit index; mode 1 rows: item index in H scratch)
-    double* x;           // materialised x, rows × ld
+    double* xslot;       // materialised x of the unit in flight: one row per resident group (slots × ld)
     double* zA;
     double* zB;
     int* zstate;         // rows
@@ -90,9 +95,15 @@ struct Geometry {
     int cluster;         // CTAs per cluster (≥1); group = cluster × cta when group_threads > 32
     int groups;          // resident solve groups (= scratch slots)
     int grid;            // CTAs launched
+    // TMA kernel
+    int tma;             // 1: bulk-async pipeline kernel (muse_iso_tma.cu)
+    int ch, stages, resident, slice_cap;
+    int smem_bytes;      // dynamic shared memory per CTA
 };
 
 cudaError_t launch_iso_solver(const SolveLaunch& L, const Geometry& geo, cudaStream_t st);
+cudaError_t launch_iso_tma(const SolveLaunch& L, const Geometry& geo, cudaStream_t st);
+cudaError_t iso_tma_geometry(int d, int ld, int want_group, int want_cluster, int want_resident, int device, Geometry* geo);
 cudaError_t iso_solver_geometry(int d, int want_group, int want_cluster, int device, Geometry* geo);
 cudaError_t launch_philox_draws(double* xi, double* nu, int rows, int d, int ld, uint64_t seed,
                                 int64_t sim_offset, int master_row, cudaStream_t st);

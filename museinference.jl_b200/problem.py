@@ -93,7 +93,7 @@ class SimpleMuseProblem(AbstractMuseProblem):
     """
 
     def __init__(self, x, family: str = "funnel", prior=None, *, P=None, L=None, group: int = 0,
-                 cluster: int = 0, stream=None, backend_factory=None):
+                 cluster: int = 0, kernel: int = 0, stream=None, backend_factory=None):
         if family not in FAMILY_NTHETA:
             raise MuseBackendError(-5, f"model family {family!r} is not registered with the B200 backend; "
                                        "Turing/Soss-defined models are not supported and there is no CPU fallback")
@@ -105,7 +105,7 @@ class SimpleMuseProblem(AbstractMuseProblem):
         self.ntheta = FAMILY_NTHETA[family]
         self.prior = prior or FlatPrior()
         self.P, self.L = P, L
-        self.group, self.cluster = group, cluster
+        self.group, self.cluster, self.kernel = group, cluster, kernel
         self._backend_factory = backend_factory or B200Backend
         self._backend = None
         self._backend_key = None
@@ -145,7 +145,7 @@ class SimpleMuseProblem(AbstractMuseProblem):
                 self._backend.close()
             self._backend = self._backend_factory(
                 self.family, self.d, cnt, sim_offset=off, nsims_h=hcnt, h_sim_offset=hoff, device=pool.device,
-                group=self.group, cluster=self.cluster, stream=self.stream, P=self.P, L=self.L)
+                group=self.group, cluster=self.cluster, kernel=self.kernel, stream=self.stream, P=self.P, L=self.L)
             self._backend_key, self._rng_key, self._data_dirty = gkey, None, True
         be = self._backend
         if self._data_dirty:

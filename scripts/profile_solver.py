@@ -13,7 +13,8 @@ d = int(os.environ.get("MUSE_D", 65536))
 n = int(os.environ.get("MUSE_N", 2048))
 group = int(os.environ.get("MUSE_GROUP", 0))
 cluster = int(os.environ.get("MUSE_CLUSTER", 0))
-be = m.B200Backend("funnel", d, n, group=group, cluster=cluster)
+kernel = int(os.environ.get("MUSE_KERNEL", 0))
+be = m.B200Backend("funnel", d, n, group=group, cluster=cluster, kernel=kernel)
 rng = np.random.Generator(np.random.Philox(1))
 be.set_data(rng.standard_normal(d) * 1.4)
 be.seed_draws(42)

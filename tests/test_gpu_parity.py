@@ -37,13 +37,21 @@ def test_device_philox_matches_oracle():
     be.close()
 
 
-@pytest.mark.parametrize("name,d,group", [("funnel", 512, 0), ("funnel", 513, 0), ("funnel", 512, 256),
-                                          ("hiergauss", 700, 0), ("funnel", 5000, 0), ("hiergauss", 4096, 512)])
-def test_map_score_cold_warm_truth(name, d, group):
+# (family, d, group threads, cluster, kernel): kernel 1 = register loops, 2 = TMA pipeline, 3 = TMA + resident x
+GEOMS = [
+    ("funnel", 512, 0, 0, 0), ("funnel", 513, 0, 0, 0), ("funnel", 512, 256, 1, 1), ("hiergauss", 700, 0, 0, 0),
+    ("funnel", 5000, 0, 0, 0), ("hiergauss", 4096, 512, 1, 1), ("funnel", 4098, 512, 2, 1),
+    ("funnel", 5000, 256, 1, 2), ("funnel", 5001, 512, 2, 2), ("hiergauss", 9000, 512, 1, 2),
+    ("hiergauss", 4096, 256, 4, 3), ("funnel", 20001, 512, 8, 3), ("funnel", 3000, 256, 1, 3),
+]
+
+
+@pytest.mark.parametrize("name,d,group,cluster,kernel", GEOMS)
+def test_map_score_cold_warm_truth(name, d, group, cluster, kernel):
     nsims = 24
     fam, draws, xd = make_inputs(name, d, nsims)
     prob = O.OracleProblem(fam, xd, draws)
-    be = _backend(name, d, nsims, draws, xd, group=group)
+    be = _backend(name, d, nsims, draws, xd, group=group, cluster=cluster, kernel=kernel)
     th0 = theta_start(name)
     atol = 1e-2
 
@@ -96,12 +104,14 @@ def test_zero_iteration_warm_start_keeps_previous_map():
     be.close()
 
 
-@pytest.mark.parametrize("name,d", [("funnel", 512), ("hiergauss", 1024)])
-def test_fd_jacobian_matches_oracle(name, d):
+@pytest.mark.parametrize("name,d,kw", [("funnel", 512, {}), ("hiergauss", 1024, {}),
+                                       ("funnel", 6000, dict(group=256, cluster=2, kernel=3)),
+                                       ("hiergauss", 5000, dict(group=512, cluster=1, kernel=2))])
+def test_fd_jacobian_matches_oracle(name, d, kw):
     nsims, nH = 20, 6
     fam, draws, xd = make_inputs(name, d, nsims)
     prob = O.OracleProblem(fam, xd, draws)
-    be = _backend(name, d, nsims, draws, xd)
+    be = _backend(name, d, nsims, draws, xd, **kw)
     th0 = theta_start(name)
     step = np.full(th0.shape, 0.01) * (1 + np.arange(th0.size))
     Hs, status = be.fd_jacobian(th0, step, nH, 1e-2)
@@ -110,6 +120,30 @@ def test_fd_jacobian_matches_oracle(name, d):
     assert (status == 0).all()
     for k in range(nH):
         np.testing.assert_allclose(Hs[k], res.Hs[k], rtol=1e-6, atol=1e-6 * np.abs(res.Hs[k]).max())
+    be.close()
+
+
+@pytest.mark.parametrize("kw", [{}, dict(group=32), dict(group=256, cluster=1, kernel=1), dict(group=256, cluster=2, kernel=2),
+                                dict(group=512, cluster=4, kernel=3)])
+def test_history_path_runs_and_stays_at_the_map(kw):
+    """atol far below round-off forces iterations ≥ 2: two-loop recursion over the (dx, dg) history,
+    direction resets, x/f stagnation exits (and, for kernel 3, the spill of resident x).  The iterate
+    must stay at the closed-form MAP and the score must agree with the oracle run the same way."""
+    name, d, nsims = "funnel", 3000, 12
+    fam, draws, xd = make_inputs(name, d, nsims)
+    prob = O.OracleProblem(fam, xd, draws)
+    be = _backend(name, d, nsims, draws, xd, **kw)
+    th = np.array([0.8])
+    out = be.map_score(th, th, 1e-300, include_data=True, warm_start=0)
+    zs = be.get_maps(0, nsims + 1)
+    assert (out["iters"] >= 2).all()
+    assert np.isin(out["status"], [0, 1, 3]).all()
+    for u in range(nsims + 1):
+        x = xd if u == 0 else prob.sample_x_z(u - 1, th)[0]
+        np.testing.assert_allclose(zs[u], fam.exact_map(x, th), rtol=1e-12, atol=1e-13)
+        _, g, soln = O.map_score_unit(prob, x, np.zeros(d), th, 1e-300)
+        assert soln.iterations >= 2
+        np.testing.assert_allclose(out["g"][u], g, rtol=1e-9)
     be.close()
 
 
