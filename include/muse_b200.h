@@ -174,6 +174,9 @@ int  muse_b200_get_maps(muse_handle* h, int32_t first_unit, int32_t count, doubl
 /* diagnostics ---------------------------------------------------------------------------- */
 int  muse_b200_profile_reset(muse_handle* h, int32_t enable);
 int  muse_b200_profile_get(muse_handle* h, muse_profile* out);
+/* diagnostics: per-unit timeline of the solver's controller (16 SM-clock stamps per unit of the last
+ * launch).  out == NULL arms the facility for up to `items` units (0 disarms); otherwise copies. */
+int  muse_b200_debug_timeline(muse_handle* h, int32_t items, int64_t* out);
 /* geometry chosen for the solver: threads per solve group, CTAs per cluster, resident groups */
 int  muse_b200_geometry(muse_handle* h, int32_t* group_threads, int32_t* cluster, int32_t* groups);
 

@@ -67,6 +67,7 @@ SIGNATURES = {
     "muse_b200_get_maps": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, c_double_p]),
     "muse_b200_profile_reset": (C.c_int, [C.c_void_p, C.c_int32]),
     "muse_b200_profile_get": (C.c_int, [C.c_void_p, C.POINTER(muse_profile)]),
+    "muse_b200_debug_timeline": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int64)]),
     "muse_b200_geometry": (C.c_int, [C.c_void_p, c_int32_p, c_int32_p, c_int32_p]),
 }
 

@@ -173,6 +173,15 @@ class B200Backend:
         self._check(self._lib.muse_b200_profile_get(self._h, C.byref(p)))
         return {name: getattr(p, name) for name, _ in _capi.muse_profile._fields_}
 
+    def debug_timeline(self, items: int, fetch: bool = False):
+        """Arm (fetch=False) or read (fetch=True) the controller timeline: items × 16 SM-clock stamps."""
+        if not fetch:
+            self._check(self._lib.muse_b200_debug_timeline(self._h, int(items), None))
+            return None
+        out = np.zeros((items, 16), dtype=np.int64)
+        self._check(self._lib.muse_b200_debug_timeline(self._h, int(items), out.ctypes.data_as(C.POINTER(C.c_int64))))
+        return out
+
     def geometry(self) -> dict:
         a, b, c = C.c_int32(), C.c_int32(), C.c_int32()
         self._check(self._lib.muse_b200_geometry(self._h, C.byref(a), C.byref(b), C.byref(c)))

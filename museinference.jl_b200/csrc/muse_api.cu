@@ -45,6 +45,9 @@ struct muse_handle {
     double *zfidA = nullptr, *zfidB = nullptr;
     int* zfid_state = nullptr;
 
+    long long* dbg = nullptr;   // diagnostics timeline (muse_b200_debug_timeline)
+    int dbg_cap = 0;
+
     // profiling
     bool prof = false;
     struct Rec { cudaEvent_t a, b; int cls; double units, bytes; };
@@ -134,6 +137,7 @@ static void fill_common(muse_handle* h, SolveLaunch& L) {
     L.gnorm_out = h->gnorm_d;
     L.f_out = h->f_d;
     L.status_out = h->status_d;
+    L.dbg = h->dbg;
 }
 
 static int launch_solver(muse_handle* h, const SolveLaunch& L, double bytes) {
@@ -225,7 +229,7 @@ int muse_b200_create(const muse_cfg* cfg, muse_handle** out) {
     {
         // kernel choice: small d → one warp per unit, register loops; large d → TMA pipeline
         int kernel = cfg->kernel;
-        if (kernel == 0) kernel = (cfg->d <= 4096 || cfg->group == 32) ? 1 : 2;
+        if (kernel == 0) kernel = 1;   // the TMA pipeline (2, 3) reaches the traffic floor but is still latency-bound
         if (kernel == 1) {
             CREATE_TRY(iso_solver_geometry(cfg->d, cfg->group, cfg->cluster, cfg->device, &h->geo));
         } else {
@@ -279,6 +283,7 @@ int muse_b200_destroy(muse_handle* h) {
     cudaFree(h->g_d); cudaFree(h->gnorm_d); cudaFree(h->f_d); cudaFree(h->iters_d); cudaFree(h->fg_d); cudaFree(h->status_d);
     cudaFreeHost(h->g_h); cudaFreeHost(h->gnorm_h); cudaFreeHost(h->iters_h); cudaFreeHost(h->fg_h); cudaFreeHost(h->status_h);
     cudaFree(h->zHA); cudaFree(h->zHB);
+    cudaFree(h->dbg);
     cudaFree(h->zfidA); cudaFree(h->zfidB); cudaFree(h->zfid_state);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     cudaGetLastError();
@@ -582,6 +587,26 @@ int muse_b200_profile_get(muse_handle* h, muse_profile* out) {
     }
     h->recs.clear();
     *out = h->acc;
+    return MUSE_OK;
+}
+
+int muse_b200_debug_timeline(muse_handle* h, int32_t items, int64_t* out) {
+    if (!h || items < 0) return MUSE_EINVAL;
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (!out) {   // (re)arm: allocate room for `items` units; items = 0 disarms
+        cudaFree(h->dbg);
+        h->dbg = nullptr;
+        h->dbg_cap = 0;
+        if (items > 0) {
+            CUDA_TRY(h, cudaMalloc(&h->dbg, (size_t)items * 16 * sizeof(long long)));
+            CUDA_TRY(h, cudaMemset(h->dbg, 0, (size_t)items * 16 * sizeof(long long)));
+            h->dbg_cap = items;
+        }
+        return MUSE_OK;
+    }
+    if (items > h->dbg_cap) return MUSE_EINVAL;
+    CUDA_TRY(h, cudaMemcpy(out, h->dbg, (size_t)items * 16 * sizeof(long long), cudaMemcpyDeviceToHost));
     return MUSE_OK;
 }
 

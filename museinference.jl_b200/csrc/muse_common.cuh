@@ -87,6 +87,7 @@ struct SolveLaunch {
     double* gnorm_out;
     double* f_out;
     int* status_out;
+    long long* dbg;      // optional timeline: 16 clock64 stamps per item (diagnostics), or null
 };
 
 struct Geometry {

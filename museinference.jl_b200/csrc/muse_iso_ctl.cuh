@@ -45,8 +45,8 @@ struct Cmd {
     int commit;
     int lazy;          // search direction s ≡ −∇f(zcur), not stored
     int start_kind;
+    int item;          // unit index of the launch (diagnostics)
     int resident;      // TMA kernel: x of this unit is held in shared memory (valid while zcur is the start)
-    int pad_;
     double c;
     IsoSample smp;
     const double* xi;  // null for the data unit
@@ -483,9 +483,14 @@ struct Controller {
 
     // ------------------------------------------------------------------ one unit
     // `cur` holds the unit's pointers (xi, nu, xsrc, xw, zcur, zalt, zA, sbuf, smp, start_kind).
+    __device__ __forceinline__ void stamp(int item, int k) {
+        if (L.dbg && grp.tid == 0) L.dbg[(size_t)item * 16 + k] = clock64();
+    }
+
     __device__ __noinline__ void solve(int item, int* zstate_row) {
         const IsoEval ev = L.ev;
         double red[7];
+        stamp(item, 0);
         com_alpha = NAN;
         last_eval_alpha = NAN;
         last_phi = last_dphi = NAN;
@@ -494,6 +499,7 @@ struct Controller {
         cur.lazy = 1;
         cur.commit = 0;
         issue(red);
+        stamp(item, 1);
         if (cur.xw) cur.xsrc = cur.xw;
         f = fma(0.5, red[0], ev.half_cst);
         gg = red[1];
@@ -546,7 +552,9 @@ struct Controller {
             com_alpha = NAN;
             last_eval_alpha = NAN;
             double alpha, phi_alpha;
+            stamp(item, 2);
             const int ls = hager_zhang(1.0, phi_0, dphi_0, alpha, phi_alpha);   // InitialStatic(alpha = 1)
+            stamp(item, 3);
             pre_valid = false;
 
             const double* zprev = cur.zcur;
@@ -616,6 +624,7 @@ struct Controller {
             status = MUSE_STATUS_MAXITER;
 
         // outputs
+        stamp(item, 4);
         if (grp.tid == 0) {
             if (zstate_row && zst >= 0) *zstate_row = zst;
             double* g = L.g_out + (size_t)item * L.ntheta;
@@ -631,6 +640,7 @@ struct Controller {
             L.f_out[item] = f;
             L.status_out[item] = status;
         }
+        stamp(item, 5);
     }
 
     // ------------------------------------------------------------------ unit setup
@@ -671,6 +681,7 @@ struct Controller {
                 row = 0;
                 draw = L.master_row;
             }
+            cur.item = item;
             cur.smp = L.smp[tsel];
             cur.resident = (L.resident && draw >= 0) ? 1 : 0;
             cur.start_kind = (draw < 0 && L.start_kind == kStartTruth) ? kStartZero : L.start_kind;

@@ -125,7 +125,7 @@ __device__ __forceinline__ void sweep_init(G& grp, const SolveLaunch& L, const C
 }
 
 // zt = zcur + c·s with s = −∇f(zcur) (lazy) or sbuf.  red: [e, dphi, gg, gmax, s1, s2, xchg]
-template <class G, bool LAZY>
+template <class G, bool LAZY, bool ZNULL>
 __device__ __forceinline__ void sweep_trial(G& grp, const SolveLaunch& L, const Cmd& cm, double (&red)[7]) {
     const IsoEval ev = L.ev;
     const double c = cm.c;
@@ -148,7 +148,7 @@ __device__ __forceinline__ void sweep_trial(G& grp, const SolveLaunch& L, const 
         xchg = fmax(xchg, fabs(zt - z));
         return zt;
     };
-    constexpr int U = kBatch;
+    constexpr int U = (LAZY && ZNULL) ? 2 * kBatch : kBatch;   // cold start: only x is loaded, keep as many bytes in flight
     for (int p0 = grp.tid; p0 < npairs; p0 += U * G::kSize) {
         double2 x[U], z[U], sv[U];
 #pragma unroll
@@ -156,7 +156,7 @@ __device__ __forceinline__ void sweep_trial(G& grp, const SolveLaunch& L, const 
             const int p = p0 + u * G::kSize;
             const bool ok = p < npairs;
             x[u] = ok ? ld2_hint(xsrc, p, pol.last) : make_double2(0.0, 0.0);
-            z[u] = (ok && zcur) ? ld2_hint(zcur, p, pol.first) : make_double2(0.0, 0.0);
+            z[u] = (!ZNULL && ok) ? ld2_hint(zcur, p, pol.first) : make_double2(0.0, 0.0);
             sv[u] = (!LAZY && ok) ? ld2(sb, p) : make_double2(0.0, 0.0);
         }
 #pragma unroll
@@ -172,7 +172,7 @@ __device__ __forceinline__ void sweep_trial(G& grp, const SolveLaunch& L, const 
     }
     if ((L.d & 1) && grp.tid == 0) {
         const int j = L.d - 1;
-        const double zt = body(xsrc[j], zcur ? zcur[j] : 0.0, LAZY ? 0.0 : sb[j]);
+        const double zt = body(xsrc[j], (!ZNULL && zcur) ? zcur[j] : 0.0, LAZY ? 0.0 : sb[j]);
         if (commit) zalt[j] = zt;
     }
     red[0] = e; red[1] = dphi; red[2] = gg_; red[3] = gmax_; red[4] = s1_; red[5] = s2_; red[6] = xchg;
@@ -196,8 +196,13 @@ template <class G>
 __device__ __noinline__ void run_op(G& grp, const SolveLaunch& L, const Cmd& c, double (&red)[7]) {
     if (c.op == kOpInit) sweep_init(grp, L, c, red);
     else if (c.op == kOpTrial) {
-        if (c.lazy) sweep_trial<G, true>(grp, L, c, red);
-        else sweep_trial<G, false>(grp, L, c, red);
+        if (c.lazy) {
+            if (c.zcur) sweep_trial<G, true, false>(grp, L, c, red);
+            else sweep_trial<G, true, true>(grp, L, c, red);
+        } else {
+            if (c.zcur) sweep_trial<G, false, false>(grp, L, c, red);
+            else sweep_trial<G, false, true>(grp, L, c, red);
+        }
     } else sweep_misc(grp, L, c, red, StridedIter<G>{grp, L});
 }
 
@@ -309,6 +314,8 @@ cudaError_t occupancy_variant(int device, int* groups, int* grid) {
 #define MUSE_VARIANTS(X)      \
     X(128, true, 1)           \
     X(256, false, 1)          \
+    X(256, false, 2)          \
+    X(256, false, 4)          \
     X(512, false, 1)          \
     X(1024, false, 1)         \
     X(512, false, 2)          \
@@ -317,11 +324,7 @@ cudaError_t occupancy_variant(int device, int* groups, int* grid) {
 
 cudaError_t iso_solver_geometry(int d, int want_group, int want_cluster, int device, Geometry* geo) {
     int group = want_group, cluster = want_cluster;
-    if (group <= 0) {
-        if (d <= 2048) group = 32;
-        else if (d <= 16384) group = 256;
-        else group = 512;
-    }
+    if (group <= 0) group = (d <= 2048) ? 32 : 256;   // measured on C3 (profiles/r01): 256 threads × 2 CTAs/SM
     if (cluster <= 0) cluster = 1;
     if (group == 32) cluster = 1;
     geo->group_threads = group;

@@ -176,6 +176,8 @@ __device__ __forceinline__ void consumer_init(G& grp, const SolveLaunch& L, cons
         e1 += b.e;
         dphi1 = fma(b.g, -a.g, dphi1);
     };
+    const bool dbg = L.dbg && ct == 0 && rank == 0;
+    if (dbg) L.dbg[(size_t)c.item * 16 + 6] = clock64();
     consume<NC, CLUSTER, true>(L, P, rank, ct, [&](int j, int q2, const double* buf, int lc) {
         const double2 a = lds2(buf + q2);
         double2 x, z0 = make_double2(0.0, 0.0);
@@ -197,9 +199,12 @@ __device__ __forceinline__ void consumer_init(G& grp, const SolveLaunch& L, cons
         body(x.x, z0.x);
         if (j + 1 < d) body(x.y, z0.y);
     });
+    if (dbg) L.dbg[(size_t)c.item * 16 + 7] = clock64();
     __threadfence();
+    if (dbg) L.dbg[(size_t)c.item * 16 + 8] = clock64();
     red[0] = e0; red[1] = gg0; red[2] = gmax0; red[3] = s1; red[4] = s2; red[5] = e1; red[6] = dphi1;
     grp.template allreduce<7, 0x04u>(red);
+    if (dbg) L.dbg[(size_t)c.item * 16 + 9] = clock64();
 }
 
 template <int NC, int CLUSTER, class G, bool RING>
@@ -227,6 +232,8 @@ __device__ __forceinline__ void consumer_trial(G& grp, const SolveLaunch& L, con
         xchg = fmax(xchg, fabs(zt - z));
         return zt;
     };
+    const bool dbg = L.dbg && ct == 0 && rank == 0;
+    if (dbg) L.dbg[(size_t)cm.item * 16 + 10] = clock64();
     consume<NC, CLUSTER, RING>(L, P, rank, ct, [&](int j, int q2, const double* buf, int lc) {
         const double2 x = resident ? lds2(resx + (size_t)lc * ch + q2) : lds2(buf + q2);
         double2 z = make_double2(0.0, 0.0), s = make_double2(0.0, 0.0);
@@ -239,9 +246,12 @@ __device__ __forceinline__ void consumer_trial(G& grp, const SolveLaunch& L, con
         zt.y = (j + 1 < d) ? body(x.y, z.y, s.y) : 0.0;
         if (commit) st2_hint(zalt, j >> 1, zt, pol.first);
     });
+    if (dbg) L.dbg[(size_t)cm.item * 16 + 11] = clock64();
     if (commit) __threadfence();
+    if (dbg) L.dbg[(size_t)cm.item * 16 + 12] = clock64();
     red[0] = e; red[1] = dphi; red[2] = gg_; red[3] = gmax_; red[4] = s1_; red[5] = s2_; red[6] = xchg;
     grp.template allreduce<7, 0x48u>(red);
+    if (dbg) L.dbg[(size_t)cm.item * 16 + 13] = clock64();
 }
 
 // element iteration of the slow-path ops in the TMA kernel's ownership
@@ -469,7 +479,7 @@ cudaError_t iso_tma_geometry(int d, int ld, int want_group, int want_cluster, in
         else if (want_resident > 0) return cudaErrorInvalidConfiguration;
     }
     if (!resident) {
-        stages = budget / 2 / (3 * ch * 8);      // leave room for two CTAs per SM
+        stages = budget / (nc <= 256 ? 2 : 1) / (3 * ch * 8);      // NC=256: leave room for two CTAs per SM
         if (stages > 8) stages = 8;
         if (stages < 2) stages = 2;
     }
