@@ -1,0 +1,87 @@
+"""Test double for ``B200Backend`` built on the CPU oracle (tests only).
+
+Lets the host-side driver (museinference.jl_b200/muse.py, parallel.py) run on a machine without a
+GPU: same method signatures and semantics as the real backend, per-sim work done by oracle/*.py.
+"""
+import numpy as np
+
+import oracle as O
+
+
+class FakeBackend:
+    def __init__(self, family, d, nsims, *, sim_offset=0, nsims_h=0, h_sim_offset=0, device=0, group=0, cluster=0,
+                 kernel=0, stream=None, lbfgs_m=0, max_iters=0, P=None, L=None):
+        self.family, self.d, self.nsims, self.nsims_h = family, d, nsims, nsims_h
+        self.sim_offset, self.h_sim_offset = sim_offset, h_sim_offset
+        self.fam = O.make_family(family, d)
+        self.ntheta = self.fam.ntheta
+        self.x = None
+        self.draws = None
+        self.draws_h = None
+        self.z = [np.zeros(d) for _ in range(nsims + 1)]
+        self.z0 = None
+        self.calls = []
+
+    def close(self):
+        pass
+
+    def set_data(self, x):
+        self.x = np.array(x, dtype=np.float64)
+
+    def set_draws(self, xi, nu, xm, nm):
+        self.draws = O.Draws(np.array(xi), np.array(nu), np.array(xm), np.array(nm))
+
+    def set_draws_h(self, xi, nu):
+        self.draws_h = (np.array(xi), np.array(nu))
+
+    def seed_draws(self, seed):
+        self.draws = O.Draws.from_philox(seed, self.nsims, self.d, offset=self.sim_offset)
+        if self.nsims_h:
+            h = O.Draws.from_philox(seed, self.nsims_h, self.d, offset=self.h_sim_offset)
+            self.draws_h = (h.xi, h.nu)
+
+    def set_z0(self, z0):
+        self.z0 = np.array(z0, dtype=np.float64)
+
+    def _prob(self):
+        return O.OracleProblem(self.fam, self.x if self.x is not None else np.zeros(self.d), self.draws)
+
+    def map_score(self, theta_sim, theta_eval, atol, *, include_data, warm_start, first_sim=0, count=None):
+        count = self.nsims - first_sim if count is None else count
+        prob = self._prob()
+        units = ([0] if include_data else []) + [1 + first_sim + i for i in range(count)]
+        self.calls.append(("map_score", tuple(np.atleast_1d(theta_eval)), include_data, warm_start, first_sim, count))
+        g, it, fg, gn, st = [], [], [], [], []
+        for u in units:
+            if u == 0:
+                x, ztrue = prob.x, None
+            else:
+                x, ztrue = prob.sample_x_z(u - 1, theta_sim)
+            if warm_start == 0:
+                z0 = np.zeros(self.d)
+            elif warm_start == 1:
+                z0 = self.z[u]
+            elif warm_start == 2:
+                z0 = ztrue if ztrue is not None else np.zeros(self.d)
+            else:
+                z0 = self.z0
+            zh, gi, soln = O.map_score_unit(prob, x, z0, theta_eval, atol)
+            self.z[u] = zh
+            g.append(gi); it.append(soln.iterations); fg.append(soln.f_calls); gn.append(soln.g_residual)
+            st.append(0 if soln.g_converged else (1 if soln.converged else 2))
+        return dict(g=np.array(g).reshape(len(units), self.ntheta), iters=np.array(it, dtype=np.int32),
+                    fg_evals=np.array(fg, dtype=np.int32), gnorm=np.array(gn), status=np.array(st, dtype=np.int32))
+
+    def fd_jacobian(self, theta0, step, nsims_H, atol):
+        if self.nsims_h:
+            dr = O.Draws(self.draws_h[0], self.draws_h[1], self.draws.xi_master, self.draws.nu_master)
+        else:
+            dr = self.draws
+        prob = O.OracleProblem(self.fam, self.x, dr)
+        res = O.MuseResult(theta=np.array(theta0, dtype=np.float64))
+        O.get_H_bang(res, prob, theta0, nsims=nsims_H, step=np.atleast_1d(step), gradz_logLike_atol=atol)
+        Hs = np.array(res.Hs).reshape(nsims_H, self.ntheta, self.ntheta)
+        return Hs, np.zeros((nsims_H, self.ntheta, 2), dtype=np.int32)
+
+    def get_maps(self, first_unit, count):
+        return np.array(self.z[first_unit:first_unit + count])

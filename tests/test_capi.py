@@ -1,0 +1,83 @@
+"""The C-ABI library builds for sm_100a without a GPU, loads, and exports every symbol include/muse_b200.h
+declares; without a CUDA device it fails loudly (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    with open(os.path.join(ROOT, "include", "muse_b200.h")) as fh:
+        src = fh.read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(muse_b200_\w+)\s*\(", src)))
+
+
+def test_header_symbols_are_exported_and_bound(lib_built):
+    import museinference_jl_b200 as m
+    from importlib import import_module
+    capi = import_module(m.__name__ + "._capi")
+    declared = _declared_symbols()
+    assert len(declared) >= 20
+    raw = C.CDLL(m.library_path())
+    for name in declared:
+        assert hasattr(raw, name), f"{name} declared in include/muse_b200.h but not exported"
+    assert sorted(capi.SIGNATURES) == declared, "ctypes binding and header disagree"
+    assert raw.muse_b200_abi_version() == capi.ABI_VERSION
+
+
+def test_cfg_struct_layout_matches_header():
+    import museinference_jl_b200 as m
+    from importlib import import_module
+    capi = import_module(m.__name__ + "._capi")
+    with open(os.path.join(ROOT, "include", "muse_b200.h")) as fh:
+        src = fh.read()
+    body = re.search(r"typedef struct muse_cfg \{(.*?)\} muse_cfg;", src, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = re.findall(r"(\w+)\s*;", body)
+    assert names == [n for n, _ in capi.muse_cfg._fields_]
+
+
+def test_library_is_built_for_sm_100a_only(lib_built):
+    import subprocess
+    import museinference_jl_b200 as m
+    out = subprocess.run(["cuobjdump", "--list-elf", m.library_path()], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_no_cuda_device_fails_loudly(lib_built):
+    """On a box without a GPU create() must return ENODEVICE (and never compute on the CPU)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA device present")
+    import museinference_jl_b200 as m
+    with pytest.raises(m.MuseBackendError) as ei:
+        m.B200Backend("funnel", 64, 4)
+    assert ei.value.code == -2 and "no CPU fallback" in str(ei.value)
+
+
+def test_unregistered_family_raises():
+    import museinference_jl_b200 as m
+    with pytest.raises(m.MuseBackendError) as ei:
+        m.SimpleMuseProblem([0.0, 1.0], "turing-model")
+    assert ei.value.code == -5
+
+    class Other(m.AbstractMuseProblem):
+        pass
+    with pytest.raises(m.MuseBackendError):
+        m.muse(Other(), [0.0])
+
+
+def test_product_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "museinference.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                with open(os.path.join(dirpath, f)) as fh:
+                    txt = fh.read()
+                assert not re.search(r"^\s*(import|from)\s+oracle\b", txt, flags=re.M), f
+                assert "muse_oracle" not in txt, f

@@ -1,0 +1,104 @@
+"""Host-side driver (museinference.jl_b200/muse.py: the mirror of muse!/get_J!/get_H!/finalize_result!,
+/root/reference/src/muse.jl:112-250, 296-333, 407-450, 484-549) against the oracle's restatement, with the
+per-simulation blocks served by a test double (tests/fake_backend.py) so that it runs without a GPU."""
+import os
+import pickle
+
+import numpy as np
+import pytest
+
+import oracle as O
+from fake_backend import FakeBackend
+from helpers import oracle_problem, theta_start
+
+
+def _pair(name, d, nsims, prior=False, seed=1234):
+    import museinference_jl_b200 as m
+    oprob, fam, draws, xd = oracle_problem(name, d, nsims, seed=seed, prior=O.NormalPrior(0, 3) if prior else None)
+    prob = m.SimpleMuseProblem(xd, name, m.NormalPrior(0, 3) if prior else None, backend_factory=FakeBackend)
+    rng = m.BaseDraws(draws.xi, draws.nu, draws.xi_master, draws.nu_master)
+    return m, oprob, prob, rng
+
+
+@pytest.mark.parametrize("name,d,nsims,prior", [("funnel", 128, 40, True), ("hiergauss", 200, 30, False)])
+def test_muse_driver_matches_oracle(name, d, nsims, prior):
+    m, oprob, prob, rng = _pair(name, d, nsims, prior)
+    ref = O.muse(oprob, theta_start(name), nsims=nsims, get_covariance=True)
+    res = m.muse(prob, theta_start(name), rng=rng, nsims=nsims, get_covariance=True)
+    assert len(res.history) == len(ref.history)
+    np.testing.assert_allclose(res.theta, ref.theta, rtol=1e-12)
+    np.testing.assert_allclose(res.J, ref.J, rtol=1e-12)
+    np.testing.assert_allclose(res.H, ref.H, rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(res.Sigma, ref.Sigma, rtol=1e-10, atol=1e-14)
+    np.testing.assert_allclose(np.array(res.gs), np.array(ref.gs), rtol=1e-13)
+    for a, b in zip(res.history, ref.history):
+        for key in ("theta", "g_like", "g_post", "H_inv_post", "H_inv_like_sims"):
+            np.testing.assert_allclose(a[key], b[key], rtol=1e-12)
+    # call pattern of the mapped blocks: cold pass, warm pass, then no new sims for J, FD solves for H
+    calls = [c for c in prob._backend.calls if c[0] == "map_score"]
+    assert [c[3] for c in calls] == [0] + [1] * (len(ref.history) - 1)     # START_ZEROS, then START_PREV
+    assert "MuseResult(" in repr(res)
+
+
+def test_unicode_keywords_and_broyden():
+    m, oprob, prob, rng = _pair("funnel", 64, 20, True)
+    kw = {"θ_rtol": 0.0, "∇z_logLike_atol": 1e-3, "α": 0.5, "H⁻¹_update": "broyden", "H⁻¹_like′": np.array([[-0.05]])}
+    res = m.muse(prob, [1.0], rng=rng, nsims=20, maxsteps=4, **kw)
+    ref = O.muse(oprob, [1.0], nsims=20, maxsteps=4, theta_rtol=0.0, gradz_logLike_atol=1e-3, alpha=0.5,
+                 H_inv_update="broyden", H_inv_like=np.array([[-0.05]]))
+    assert len(res.history) == 4
+    np.testing.assert_allclose(res.theta, ref.theta, rtol=1e-12)
+    with pytest.raises(TypeError):
+        m.muse(prob, [1.0], rng=rng, nsims=20, bogus=1)
+
+
+def test_get_J_top_up_and_get_H_resume():
+    m, oprob, prob, rng = _pair("hiergauss", 100, 30, False)
+    th = np.array([0.2, 0.1])
+    res = m.MuseResult(theta=th.copy())
+    ref = O.MuseResult(theta=th.copy())
+    getJ, getH = getattr(m, "get_J!"), getattr(m, "get_H!")
+    getJ(res, prob, rng=rng, nsims=10)
+    O.get_J_bang(ref, oprob, nsims=10)
+    np.testing.assert_allclose(res.J, ref.J, rtol=1e-12)
+    getJ(res, prob, rng=rng, nsims=30)               # top-up: sims 10..29 only (src/muse.jl:499-506)
+    O.get_J_bang(ref, oprob, nsims=30)
+    assert len(res.gs) == 30
+    np.testing.assert_allclose(res.J, ref.J, rtol=1e-12)
+    last = [c for c in prob._backend.calls if c[0] == "map_score"][-1]
+    assert last[4:] == (10, 20) and last[3] == 2     # first_sim, count, START_TRUTH (src/muse.jl:511)
+    getH(res, prob, rng=rng, nsims=4)
+    O.get_H_bang(ref, oprob, nsims=4)
+    np.testing.assert_allclose(res.H, ref.H, rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(res.Sigma, ref.Sigma, rtol=1e-9)
+    n = len(res.Hs)
+    getH(res, prob, rng=rng, nsims=4)                # nothing left to do (src/muse.jl:317-319)
+    assert len(res.Hs) == n
+
+
+def test_checkpoint_and_resume(tmp_path):
+    m, oprob, prob, rng = _pair("funnel", 64, 20, True)
+    ck = os.path.join(tmp_path, "ck.pkl")
+    full = m.muse(prob, [1.0], rng=rng, nsims=20, theta_rtol=0.0, maxsteps=4)
+    part = m.muse(prob, [1.0], rng=rng, nsims=20, theta_rtol=0.0, maxsteps=2, checkpoint_filename=ck)
+    with open(ck, "rb") as fh:
+        loaded = pickle.load(fh)
+    np.testing.assert_array_equal(loaded.theta, part.theta)
+    muse_bang = getattr(m, "muse!")
+    muse_bang(loaded, prob, rng=rng, nsims=20, theta_rtol=0.0, maxsteps=4)     # continues at length(history)+1 (:159)
+    assert len(loaded.history) == 4
+    # a resumed run restarts the MAPs from zeros (ẑs are not part of the result, src/muse.jl:151); for these
+    # families the MAP is start-independent, so the θ path is unchanged
+    np.testing.assert_allclose(loaded.theta, full.theta, rtol=1e-10)
+
+
+def test_unsupported_options_raise():
+    m, oprob, prob, rng = _pair("funnel", 32, 10, True)
+    res = m.MuseResult(theta=np.array([0.1]))
+    getH = getattr(m, "get_H!")
+    with pytest.raises(m.MuseBackendError):
+        getH(res, prob, rng=rng, nsims=2, implicit_diff=True)
+    with pytest.raises(m.MuseBackendError):
+        getH(res, prob, rng=rng, nsims=2)            # no step and no scores yet
+    with pytest.raises(ValueError):
+        m.muse(prob, [0.1, 0.2], rng=rng, nsims=10)  # wrong θ length

@@ -1,0 +1,277 @@
+"""CPU tests of the oracle (the checker) — PARITY UNPINNED, see oracle/__init__.py: the reference ships
+no golden vectors for this path (its only assertion is μ/σ < 2, /root/reference/test/runtests.jl:31,56,81),
+so the oracle is pinned by optimiser-independent known answers:
+
+  * analytic ∇z / ∇θ against central finite differences (the style of ``check_self_consistency``,
+    /root/reference/src/interface.jl:209-230);
+  * closed-form MAPs / scores / J / H of the registered families;
+  * the quirks of muse!/get_J!/get_H! read off the reference source;
+  * the reference's statistical acceptance bound replayed over seeds;
+  * the frozen fixtures under tests/golden/ (regression of the oracle itself; the GPU tests use the same files).
+"""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+import oracle as O
+from helpers import make_inputs, oracle_problem, theta_start
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _corr_consts(d, seed=5):
+    rng = np.random.Generator(np.random.Philox(seed))
+    A = rng.standard_normal((d, d))
+    S0 = A @ A.T / d + 0.1 * np.eye(d)
+    return np.linalg.inv(S0), np.linalg.cholesky(S0)
+
+
+def _family(name, d):
+    if name == "corrgauss":
+        P, L = _corr_consts(d)
+        return O.make_family(name, d, P=P, L=L)
+    return O.make_family(name, d)
+
+
+@pytest.mark.parametrize("name", ["funnel", "hiergauss", "corrgauss"])
+def test_gradients_match_central_differences(name):
+    d = 24
+    fam = _family(name, d)
+    rng = np.random.default_rng(3)
+    th = np.array([0.4]) if fam.ntheta == 1 else np.array([0.3, -0.2])
+    x, z = fam.sample(th, rng.standard_normal(d), rng.standard_normal(d))
+    z = z + 0.1 * rng.standard_normal(d)
+    f, g = fam.neg_loglike_and_grad(x, z, th)
+    assert f == pytest.approx(fam.neg_loglike(x, z, th), rel=1e-14)
+    h = 1e-5
+    for j in range(d):
+        e = np.zeros(d)
+        e[j] = h
+        fd = (fam.neg_loglike(x, z + e, th) - fam.neg_loglike(x, z - e, th)) / (2 * h)
+        assert g[j] == pytest.approx(fd, rel=2e-7, abs=2e-8)
+    s = fam.score(x, z, th)
+    for n in range(fam.ntheta):
+        e = np.zeros(fam.ntheta)
+        e[n] = h
+        fd = -(fam.neg_loglike(x, z, th + e) - fam.neg_loglike(x, z, th - e)) / (2 * h)
+        assert s[n] == pytest.approx(fd, rel=2e-7, abs=2e-7)
+
+
+@pytest.mark.parametrize("name", ["funnel", "hiergauss", "corrgauss"])
+def test_exact_map_is_stationary_and_lbfgs_reaches_it(name):
+    d = 40
+    fam = _family(name, d)
+    rng = np.random.default_rng(11)
+    th = np.array([0.7]) if fam.ntheta == 1 else np.array([0.5, 0.3])
+    x, _ = fam.sample(th, rng.standard_normal(d), rng.standard_normal(d))
+    zstar = fam.exact_map(x, th)
+    assert np.abs(fam.neg_loglike_and_grad(x, zstar, th)[1]).max() < 1e-12
+    # anisotropic Hessian (F3): an f-based line search stagnates near 1e-8 relative
+    tol = 1e-6 if name == "corrgauss" else 1e-10
+    soln = O.lbfgs_minimize(lambda z: fam.neg_loglike_and_grad(x, z, th), np.zeros(d), g_tol=tol)
+    assert soln.converged and soln.g_residual <= 10 * tol
+    np.testing.assert_allclose(soln.minimizer, zstar, rtol=1e-4 if name == "corrgauss" else 1e-7, atol=1e-6 if name == "corrgauss" else 1e-9)
+    if name != "corrgauss":
+        # isotropic Hessian: −g points at the MAP; InitialStatic(1) → bracket → secant lands exactly
+        assert soln.iterations == 1 and soln.f_calls == 3
+        np.testing.assert_allclose(soln.minimizer, zstar, rtol=1e-13, atol=1e-15)
+
+
+def test_lbfgs_zero_iterations_when_start_satisfies_gtol():
+    fam = O.Funnel(16)
+    x = np.linspace(-1, 1, 16)
+    z = fam.exact_map(x, [0.2])
+    soln = O.lbfgs_minimize(lambda zz: fam.neg_loglike_and_grad(x, zz, [0.2]), z, g_tol=1e-2)
+    assert soln.iterations == 0 and soln.f_calls == 1 and soln.g_converged
+
+
+def test_hagerzhang_on_a_quartic_satisfies_wolfe():
+    phi = lambda a: (a - 0.3) ** 4 + 0.5 * (a - 0.3) ** 2
+    dphi = lambda a: 4 * (a - 0.3) ** 3 + (a - 0.3)
+    calls = []
+
+    def phidphi(a):
+        calls.append(a)
+        return phi(a), dphi(a)
+
+    ls = O.HagerZhang()
+    alpha, val = ls(phidphi, 1.0, phi(0.0), dphi(0.0))
+    assert val == pytest.approx(phi(alpha))
+    assert phi(alpha) <= phi(0.0) + 0.1 * alpha * dphi(0.0) or abs(dphi(alpha)) <= 0.9 * abs(dphi(0.0))
+    assert dphi(alpha) >= 0.9 * dphi(0.0)
+    assert 1 <= len(calls) <= 50
+
+
+def test_hagerzhang_rejects_ascent_direction():
+    with pytest.raises(O.LineSearchException):
+        O.HagerZhang()(lambda a: (a * a + a, 2 * a + 1), 1.0, 0.0, 1.0)
+
+
+def test_funnel_closed_forms_J_H_sigma():
+    """J = Var g = d s²/2 and H = J at the evaluation θ, within Monte-Carlo error."""
+    d, nsims = 256, 400
+    prob, fam, draws, xd = oracle_problem("funnel", d, nsims, seed=5, prior=O.NormalPrior(0, 3))
+    th = np.array([0.3])
+    res = O.MuseResult(theta=th.copy())
+    O.get_J_bang(res, prob, th, nsims=nsims)
+    s = 1.0 / (1.0 + math.exp(-th[0]))
+    J_exact = d * s * s / 2
+    assert res.J[0, 0] == pytest.approx(J_exact, rel=4 * math.sqrt(2.0 / nsims))
+    O.get_H_bang(res, prob, th, nsims=40)
+    assert res.H[0, 0] == pytest.approx(J_exact, rel=0.08)
+    # per-sim score in closed form: g = ½ e^{-θ} s² ‖x‖² − d/2
+    x, _ = prob.sample_x_z(3, th)
+    assert res.gs[3][0] == pytest.approx(0.5 * math.exp(-th[0]) * s * s * x @ x - d / 2, rel=1e-12)
+    assert res.Sigma[0, 0] == pytest.approx(1.0 / (res.H[0, 0] ** 2 / res.J[0, 0] + 1 / 9.0), rel=1e-12)
+
+
+def test_fd_jacobian_closed_form_per_sim():
+    """H_k = [g(x(θ₀+h)) − g(x(θ₀−h))]/(2h) with ‖x(θ)‖² = e^θ‖ξ‖² + 2e^{θ/2}ξ·ν + ‖ν‖²."""
+    d, nsims = 128, 6
+    prob, fam, draws, _ = oracle_problem("funnel", d, nsims, seed=9)
+    th0, h = 0.4, 0.02
+    res = O.MuseResult(theta=np.array([th0]))
+    O.get_H_bang(res, prob, [th0], nsims=nsims, step=[h])
+    s = 1.0 / (1.0 + math.exp(-th0))
+    for k in range(nsims):
+        xi, nu = draws.xi[k], draws.nu[k]
+        n2 = lambda t: math.exp(t) * xi @ xi + 2 * math.exp(t / 2) * xi @ nu + nu @ nu
+        g = lambda t: 0.5 * math.exp(-th0) * s * s * n2(t) - d / 2
+        assert res.Hs[k][0, 0] == pytest.approx((g(th0 + h) - g(th0 - h)) / (2 * h), rel=1e-10)
+
+
+def test_muse_quirks_of_the_reference():
+    d, nsims = 512, 100
+    prob, *_ = oracle_problem("funnel", d, nsims, prior=O.NormalPrior(0, 3))
+    res = O.muse(prob, [1.0], nsims=nsims, get_covariance=True)
+    # the inverse-Hessian convergence test breaks at i = 3, i.e. after two updates (src/muse.jl:163-166)
+    assert len(res.history) == 2
+    # result.gs are the scores at the θ *before* the last update (src/muse.jl:231) and get_J! reuses them (:499-502)
+    np.testing.assert_array_equal(np.array(res.gs), res.history[-1]["g_like_sims"])
+    assert res.J[0, 0] == pytest.approx(np.var(np.array(res.gs)[:, 0], ddof=1), rel=1e-15)
+    s_prev = 1 / (1 + math.exp(-res.history[-1]["theta"][0]))
+    assert res.J[0, 0] == pytest.approx(d * s_prev ** 2 / 2, rel=0.5)
+    # get_H! uses max(1, nsims ÷ 10) sims (src/muse.jl:246)
+    assert len(res.Hs) == nsims // 10
+    # Σ⁻¹ = H'J⁻¹H + H_prior (src/muse.jl:540)
+    assert res.Sigma_inv[0, 0] == pytest.approx(res.H[0, 0] ** 2 / res.J[0, 0] + 1 / 9.0, rel=1e-13)
+    # resume: re-calling muse! on the result continues from length(history)+1 and stops at the same test
+    n0 = len(res.history)
+    O.muse_bang(res, prob, nsims=nsims)
+    assert len(res.history) == n0
+
+
+def test_reference_statistical_bound():
+    """/root/reference/test/runtests.jl:27-31: 512-d funnel, data at θ=0, start θ=1, prior N(0,3) ⇒ μ/σ < 2.
+    The reference asserts it for one StableRNG seed; it is a one-sided 2σ bound on an estimate that keeps
+    ≈ 0.3² of the start offset after its two updates (α = 0.7), so over seeds it holds most of the time, not always."""
+    d, nsims = 512, 100
+    fam = O.Funnel(d)
+    ratios = []
+    for seed in range(8):
+        draws = O.Draws.from_philox(1000 + seed, nsims, d)
+        xd, _ = fam.sample([0.0], O.philox_normals(2000 + seed, 0, 0, d), O.philox_normals(2000 + seed, 0, 1, d))
+        prob = O.OracleProblem(fam, xd, draws, O.NormalPrior(0, 3))
+        res = O.muse(prob, [1.0], nsims=nsims, get_covariance=True)
+        mu, sig = res.dist[0][0], math.sqrt(res.dist[1][0, 0])
+        assert sig == pytest.approx(0.125, rel=0.25)      # closed form σ ≈ 0.1249 at d = 512
+        ratios.append(mu / sig)
+    ratios = np.array(ratios)
+    # expected: θ̂ ≈ 0.26 after the two updates the inverse-Hessian test allows from θ₀ = 1 (1 → 0.56 → 0.26 in
+    # expectation, src/muse.jl:163-166, 224), i.e. ≈ +2σ of bias plus unit scatter
+    assert (ratios < 2).any() and (ratios > -1).all() and (ratios < 5).all()
+    assert 1.0 < ratios.mean() < 3.5
+
+
+def test_funnel_muse_closed_form_restatement():
+    """Optimiser-independent replay of the whole muse! iteration for F1: with
+    s = 1/(1+e^{-θ}) the score at the exact MAP is g = ½ e^{-θ} s² ‖x‖² − d/2, and
+    ‖x_k(θ)‖² = e^θ‖ξ_k‖² + 2e^{θ/2} ξ_k·ν_k + ‖ν_k‖²."""
+    d, nsims = 512, 100
+    prob, fam, draws, xd = oracle_problem("funnel", d, nsims, prior=O.NormalPrior(0, 3))
+    res = O.muse(prob, [1.0], nsims=nsims, gradz_logLike_atol=1e-2, get_covariance=True)
+    a2, ab, b2 = (draws.xi ** 2).sum(1), (draws.xi * draws.nu).sum(1), (draws.nu ** 2).sum(1)
+    score = lambda th, n2: 0.5 * math.exp(-th) / (1 + math.exp(-th)) ** 2 * n2 - d / 2
+    th, thetas, gs = 1.0, [], None
+    for i in range(1, 51):
+        if i > 2 and math.sqrt(-(thetas[-1][0] - thetas[-2][0]) ** 2 * thetas[-1][1]) < 0.1:
+            break
+        gs = score(th, math.exp(th) * a2 + 2 * math.exp(th / 2) * ab + b2)
+        g_post = score(th, xd @ xd) - gs.mean() - th / 9.0
+        Hinv = 1.0 / (-np.var(gs, ddof=1) - 1 / 9.0)
+        thetas.append((th, Hinv))
+        th = th - 0.7 * Hinv * g_post
+    assert len(res.history) == len(thetas)
+    assert res.theta[0] == pytest.approx(th, rel=1e-10)
+    np.testing.assert_allclose(np.array(res.gs)[:, 0], gs, rtol=1e-10)
+    assert res.J[0, 0] == pytest.approx(np.var(gs, ddof=1), rel=1e-10)
+
+
+def test_hiergauss_muse_recovers_truth_within_errors():
+    d, nsims = 2000, 80
+    prob, *_ = oracle_problem("hiergauss", d, nsims, seed=21)
+    res = O.muse(prob, [0.5, 0.3], nsims=nsims, get_covariance=True)
+    sd = np.sqrt(np.diag(res.Sigma))
+    assert (np.abs(res.theta) < 4 * sd).all()
+    assert res.J.shape == (2, 2) and np.allclose(res.J, res.J.T)
+
+
+def test_broyden_updates_run_and_agree_on_first_iterations():
+    prob, *_ = oracle_problem("funnel", 128, 30, prior=O.NormalPrior(0, 3))
+    a = O.muse(prob, [1.0], nsims=30, theta_rtol=0.0, maxsteps=4)
+    b = O.muse(prob, [1.0], nsims=30, theta_rtol=0.0, maxsteps=4, H_inv_update="broyden",
+               H_inv_like=np.array([[-0.02]]))
+    assert len(a.history) == len(b.history) == 4
+    assert not np.allclose(a.theta, b.theta)
+    np.testing.assert_allclose(a.history[0]["g_like"], b.history[0]["g_like"])
+
+
+@pytest.mark.parametrize("name", ["funnel_d512_n100", "funnel_d64_n16_tight", "hiergauss_d300_n40"])
+def test_golden_fixtures(name):
+    with open(os.path.join(GOLDEN, name + ".json")) as fh:
+        fix = json.load(fh)
+    c = fix["case"]
+    prior = O.NormalPrior(0, 3) if c["prior"] else None
+    prob, fam, draws, xd = oracle_problem(c["family"], c["d"], c["nsims"], seed=c["seed"], prior=prior)
+    np.testing.assert_allclose(xd[:4], fix["xdat_head"], rtol=1e-14)          # philox inputs are platform independent
+    np.testing.assert_allclose(draws.xi[0, :4], fix["xi0_head"], rtol=1e-14)
+    res = O.muse(prob, np.array(fix["theta0"]), nsims=c["nsims"], gradz_logLike_atol=c["atol"],
+                 get_covariance=True, save_MAPs=True)
+    assert len(res.history) == fix["n_outer"]
+    np.testing.assert_allclose(res.theta, fix["theta"], rtol=1e-10)
+    np.testing.assert_allclose(res.J, fix["J"], rtol=1e-10)
+    np.testing.assert_allclose(res.H, fix["H"], rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(res.Sigma, fix["Sigma"], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(np.array(res.gs), fix["gs"], rtol=1e-10)
+    h0 = res.history[0]
+    np.testing.assert_allclose(h0["g_like_sims"], fix["iter1"]["g_sims"], rtol=1e-10)
+    assert [s.iterations for s in h0["z_history_sims"]] == fix["iter1"]["iters"]
+    assert [s.f_calls for s in h0["z_history_sims"]] == fix["iter1"]["fg"]
+
+
+def test_c_port_matches_numpy_oracle():
+    from oracle import cport
+    cport.build()
+    for name, d in (("funnel", 300), ("hiergauss", 257)):
+        fam, draws, xd = make_inputs(name, d, 9)
+        prob = O.OracleProblem(fam, xd, draws)
+        th = theta_start(name)
+        out = cport.map_score(fam.family_id, draws.xi, draws.nu, xd, th, th, 1e-2, True, 0, want_z=True, nthreads=2)
+        for u in range(10):
+            x = xd if u == 0 else prob.sample_x_z(u - 1, th)[0]
+            zh, g, soln = O.map_score_unit(prob, x, np.zeros(d), th, 1e-2)
+            np.testing.assert_allclose(out["g"][u], g, rtol=1e-11)
+            np.testing.assert_allclose(out["z"][u], zh, rtol=1e-11, atol=1e-14)
+            assert out["iters"][u] == soln.iterations and out["fg_evals"][u] == soln.f_calls
+    # whole solve, threaded C body vs NumPy body
+    from oracle import cmuse
+    prob, *_ = oracle_problem("funnel", 512, 50, prior=O.NormalPrior(0, 3))
+    ref = O.muse(prob, [1.0], nsims=50, get_covariance=True)
+    res, units = cmuse.muse_cpu(prob, [1.0], nsims=50)
+    np.testing.assert_allclose(res.theta, ref.theta, rtol=1e-9)
+    np.testing.assert_allclose(res.J, ref.J, rtol=1e-9)
+    np.testing.assert_allclose(res.H, ref.H, rtol=1e-7)
+    assert units == 2 * 51 + 1 + 2 * 5
