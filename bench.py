@@ -54,7 +54,7 @@ def parse():
     ap.add_argument("--family", default="funnel", choices=["funnel", "hiergauss"])
     ap.add_argument("--group", type=int, default=0)
     ap.add_argument("--cluster", type=int, default=0)
-    ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 register-loop, 2 TMA, 3 TMA + resident x")
+    ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 generic solver only, 2 streaming kernel first")
     ap.add_argument("--cpu-sims", type=int, default=0, help="sims in the bounded CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -300,7 +300,8 @@ def run_b200(args):
             "gpu_launches": int(launches_sum),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "iso_solver_kernel (persistent MAP+score solver)",
+                         "kernel": ("iso_stream_kernel (single-pass MAP+score; + empty re-solve launch)" if prof.get("redo_units", 0) == 0 and d >= 4096 and args.kernel != 1 else "iso_solver_kernel (generic two-sweep MAP+score solver)"),
+                         "redo_units": prof.get("redo_units", 0),
                          "algorithmic_bytes_per_launch": solve_bytes_sum / max(1, prof["solve_launches"] * world),
                          "avg_launch_ms": solve_ms_sum / max(1, prof["solve_launches"] * world),
                          "kernel_share_of_step": solve_ms_sum / world / ms},

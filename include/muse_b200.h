@@ -79,8 +79,8 @@ typedef struct muse_cfg {
     int64_t sim_offset;      /* global index of local simulation 0 */
     int32_t nsims_h;         /* sims of the get_H! shard held as extra draw rows; 0 → the H shard is the
                                 first sims of the local shard (single-GPU default) */
-    int32_t kernel;          /* solver kernel: 0 auto, 1 register-loop, 2 TMA pipeline, 3 TMA pipeline with x
-                                resident in cluster shared memory */
+    int32_t kernel;          /* solver kernels: 0 auto (streaming first when d ≥ 4096), 1 generic two-sweep solver only,
+                                2 single-pass streaming kernel first, generic kernel for what it hands back */
     int64_t h_sim_offset;    /* global index of H-shard simulation 0 (used when nsims_h > 0) */
     int32_t lbfgs_m;         /* L-BFGS memory; 0 → 10 (Optim.LBFGS default) */
     int32_t max_iters;       /* 0 → 1000 (Optim.Options default) */
@@ -94,7 +94,7 @@ typedef struct muse_cfg {
 /* per-kernel-class device timing, measured with CUDA events on the launch stream */
 typedef struct muse_profile {
     int64_t launches;        /* kernels launched since the last reset */
-    int64_t solve_launches;  /* launches of the persistent MAP+score solver kernel */
+    int64_t solve_launches;  /* solver passes (streaming kernel + its re-solve launch count as one) */
     double  solve_ms;        /* summed device time of those launches (events) */
     double  solve_units;     /* MAP+score units they processed */
     double  solve_bytes;     /* algorithmic bytes they account for */
@@ -102,6 +102,7 @@ typedef struct muse_profile {
     double  draw_ms;
     int64_t other_launches;
     double  other_ms;
+    int64_t redo_units;      /* units the streaming kernel handed back to the generic kernel (since handle creation) */
 } muse_profile;
 
 int  muse_b200_abi_version(void);

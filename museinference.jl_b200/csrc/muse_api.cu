@@ -2,7 +2,7 @@
 //
 // Host-side glue only: argument checking, device-memory ownership, θ → kernel-constant
 // conversion, launch of the persistent solver, result copies.  All arithmetic on the N×d batch
-// happens in the CUDA kernels (muse_iso_solver.cu, muse_draws.cu).  There is no CPU fallback:
+// happens in the CUDA kernels (muse_iso_stream.cu, muse_iso_solver.cu, muse_draws.cu).  There is no CPU fallback:
 // every entry point needs a live CUDA context on an sm_100 device.
 #include <cmath>
 #include <cstring>
@@ -45,6 +45,11 @@ struct muse_handle {
     double *zfidA = nullptr, *zfidB = nullptr;
     int* zfid_state = nullptr;
 
+    // streaming kernel: per-(unit, segment) partial sums, arrival counters, hand-back list
+    double* gpart = nullptr;
+    int *redo_count = nullptr, *redo_items = nullptr;
+    unsigned long long* redo_total = nullptr;
+
     long long* dbg = nullptr;   // diagnostics timeline (muse_b200_debug_timeline)
     int dbg_cap = 0;
 
@@ -79,12 +84,12 @@ static int theta_consts(const muse_cfg& c, const double* th_sim, const double* t
     const double d = (double)c.d;
     if (c.family == MUSE_FAMILY_FUNNEL) {
         if (smp) { smp->sig = std::exp(0.5 * th_sim[0]); smp->mu = 0.0; }
-        if (ev) { ev->a = std::exp(-th_eval[0]); ev->mu = 0.0; ev->half_cst = 0.5 * d * th_eval[0]; }
+        if (ev) { ev->a = std::exp(-th_eval[0]); ev->mu = 0.0; ev->half_cst = 0.5 * d * th_eval[0]; ev->cspec = 1.0 / (1.0 + ev->a); }
         return 0;
     }
     if (c.family == MUSE_FAMILY_HIERGAUSS) {
         if (smp) { smp->sig = std::exp(th_sim[1]); smp->mu = th_sim[0]; }
-        if (ev) { ev->a = std::exp(-2.0 * th_eval[1]); ev->mu = th_eval[0]; ev->half_cst = d * th_eval[1]; }
+        if (ev) { ev->a = std::exp(-2.0 * th_eval[1]); ev->mu = th_eval[0]; ev->half_cst = d * th_eval[1]; ev->cspec = 1.0 / (1.0 + ev->a); }
         return 0;
     }
     return -1;
@@ -94,8 +99,14 @@ static int ensure_outputs(muse_handle* h, int items) {
     if (items <= h->out_cap) return 0;
     cudaFree(h->g_d); cudaFree(h->gnorm_d); cudaFree(h->f_d); cudaFree(h->iters_d); cudaFree(h->fg_d); cudaFree(h->status_d);
     cudaFreeHost(h->g_h); cudaFreeHost(h->gnorm_h); cudaFreeHost(h->iters_h); cudaFreeHost(h->fg_h); cudaFreeHost(h->status_h);
+    cudaFree(h->gpart); cudaFree(h->redo_items);
+    h->gpart = nullptr; h->redo_items = nullptr;
     h->out_cap = 0;
     const size_t n = (size_t)items;
+    if (h->geo.stream) {
+        CUDA_TRY(h, cudaMalloc(&h->gpart, n * (size_t)h->geo.nseg * 16 * sizeof(double)));
+        CUDA_TRY(h, cudaMalloc(&h->redo_items, n * sizeof(int)));
+    }
     CUDA_TRY(h, cudaMalloc(&h->g_d, n * h->cfg.ntheta * sizeof(double)));
     CUDA_TRY(h, cudaMalloc(&h->gnorm_d, n * sizeof(double)));
     CUDA_TRY(h, cudaMalloc(&h->f_d, n * sizeof(double)));
@@ -125,10 +136,10 @@ static void fill_common(muse_handle* h, SolveLaunch& L) {
     L.master_row = h->cfg.nsims;
     L.sbuf = h->sbuf;
     L.xslot = h->xslot;
-    L.ch = h->geo.ch;
-    L.stages = h->geo.stages;
-    L.resident = h->geo.resident;
-    L.slice_cap = h->geo.slice_cap;
+    L.gpart = h->gpart;
+    L.redo_count = h->redo_count;
+    L.redo_items = h->redo_items;
+    L.redo_total = h->redo_total;
     L.dxh = h->dxh;
     L.dgh = h->dgh;
     L.g_out = h->g_d;
@@ -147,9 +158,22 @@ static int launch_solver(muse_handle* h, const SolveLaunch& L, double bytes) {
         CUDA_TRY(h, cudaEventCreate(&r.b));
         CUDA_TRY(h, cudaEventRecord(r.a, h->stream));
     }
-    if (h->geo.tma) CUDA_TRY(h, launch_iso_tma(L, h->geo, h->stream));
-    else CUDA_TRY(h, launch_iso_solver(L, h->geo, h->stream));
-    h->acc.launches += 1;
+    if (h->geo.stream) {
+        // pass 1: single-pass speculative streaming kernel + its scalar replay; pass 2: the generic kernel re-solves
+        // the units pass 1 handed back (device-side list; normally empty, then its CTAs exit at once)
+        SolveLaunch S = L;
+        if (h->dbg_cap < h->geo.stream_grid) S.dbg = nullptr;   // the streaming kernel stamps per CTA
+        CUDA_TRY(h, cudaMemsetAsync(h->redo_count, 0, sizeof(int), h->stream));
+        CUDA_TRY(h, launch_iso_stream(S, h->geo, h->stream));
+        SolveLaunch R = L;
+        R.item_list = h->redo_items;
+        R.item_count = h->redo_count;
+        CUDA_TRY(h, launch_iso_solver(R, h->geo, h->stream));
+        h->acc.launches += 3;
+    } else {
+        CUDA_TRY(h, launch_iso_solver(L, h->geo, h->stream));
+        h->acc.launches += 1;
+    }
     h->acc.solve_launches += 1;
     if (h->prof) {
         CUDA_TRY(h, cudaEventRecord(r.b, h->stream));
@@ -227,14 +251,13 @@ int muse_b200_create(const muse_cfg* cfg, muse_handle** out) {
         h->own_stream = true;
     }
     {
-        // kernel choice: small d → one warp per unit, register loops; large d → TMA pipeline
-        int kernel = cfg->kernel;
-        if (kernel == 0) kernel = 1;   // the TMA pipeline (2, 3) reaches the traffic floor but is still latency-bound
-        if (kernel == 1) {
-            CREATE_TRY(iso_solver_geometry(cfg->d, cfg->group, cfg->cluster, cfg->device, &h->geo));
-        } else {
-            CREATE_TRY(iso_tma_geometry(cfg->d, h->ld, cfg->group, cfg->cluster, kernel == 3 ? 1 : 0, cfg->device, &h->geo));
-        }
+        // kernel choice: the generic solver's group shape follows d (one warp per unit for
+        // small d, one CTA otherwise); for d ≥ 4096 the streaming kernel runs first and the generic kernel
+        // only re-solves what it hands back.  cfg.kernel: 0 auto, 1 generic only, 2 streaming first (any d).
+        if (cfg->kernel < 0 || cfg->kernel > 2) { h->err = "cfg.kernel must be 0, 1 or 2"; return fail(MUSE_EINVAL); }
+        CREATE_TRY(iso_solver_geometry(cfg->d, cfg->group, cfg->cluster, cfg->device, &h->geo));
+        h->geo.stream = 0;
+        if (cfg->kernel == 2 || (cfg->kernel == 0 && cfg->d >= 4096)) CREATE_TRY(iso_stream_geometry(cfg->d, h->ld, cfg->device, &h->geo));
     }
 
     const size_t ld = (size_t)h->ld, rows = (size_t)h->rows, B = sizeof(double);
@@ -259,6 +282,10 @@ int muse_b200_create(const muse_cfg* cfg, muse_handle** out) {
     CREATE_TRY(cudaMalloc(&h->zfidA, ld * B));
     CREATE_TRY(cudaMalloc(&h->zfidB, ld * B));
     CREATE_TRY(cudaMalloc(&h->zfid_state, sizeof(int)));
+    CREATE_TRY(cudaMalloc(&h->redo_count, sizeof(int)));
+    CREATE_TRY(cudaMemsetAsync(h->redo_count, 0, sizeof(int), h->stream));
+    CREATE_TRY(cudaMalloc(&h->redo_total, sizeof(unsigned long long)));
+    CREATE_TRY(cudaMemsetAsync(h->redo_total, 0, sizeof(unsigned long long), h->stream));
     CREATE_TRY(cudaMemsetAsync(h->xi, 0, rows * ld * B, h->stream));
     CREATE_TRY(cudaMemsetAsync(h->nu, 0, rows * ld * B, h->stream));
     CREATE_TRY(cudaMemsetAsync(h->xdat, 0, ld * B, h->stream));
@@ -284,6 +311,7 @@ int muse_b200_destroy(muse_handle* h) {
     cudaFreeHost(h->g_h); cudaFreeHost(h->gnorm_h); cudaFreeHost(h->iters_h); cudaFreeHost(h->fg_h); cudaFreeHost(h->status_h);
     cudaFree(h->zHA); cudaFree(h->zHB);
     cudaFree(h->dbg);
+    cudaFree(h->gpart); cudaFree(h->redo_count); cudaFree(h->redo_items); cudaFree(h->redo_total);
     cudaFree(h->zfidA); cudaFree(h->zfidB); cudaFree(h->zfid_state);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     cudaGetLastError();
@@ -523,7 +551,9 @@ int muse_b200_fd_jacobian(muse_handle* h, const double* theta0, const double* st
     L.zA = h->zHA;
     L.zB = h->zHB;
     L.zstate = nullptr;
-    rc = launch_solver(h, L, items * 4 * d8);
+    L.discard_z = 1;     // `ẑ, = ẑ_at_θ(...)` is only an intermediate of the score (src/muse.jl:431-432)
+    // algorithmic bytes: read ξ, ν per virtual sim; the shared start ẑ_fid is read once (L2)
+    rc = launch_solver(h, L, items * 2 * d8 + d8);
     if (rc != 0) return rc;
     rc = muse_b200_fetch(h, items, h->g_h, nullptr, nullptr, nullptr, status_out ? h->status_h : nullptr);
     if (rc != 0) return rc;
@@ -586,6 +616,9 @@ int muse_b200_profile_get(muse_handle* h, muse_profile* out) {
         cudaEventDestroy(r.b);
     }
     h->recs.clear();
+    unsigned long long redo = 0;
+    CUDA_TRY(h, cudaMemcpy(&redo, h->redo_total, sizeof(redo), cudaMemcpyDeviceToHost));
+    h->acc.redo_units = (int64_t)redo;
     *out = h->acc;
     return MUSE_OK;
 }

@@ -20,6 +20,7 @@ struct IsoEval {
     double a;
     double mu;
     double half_cst;
+    double cspec;     // 1/(1+a): exact line minimum along −∇f for these families (speculated step)
 };
 //   sample: z = mu + sig ξ,  x = z + ν            (src/simple.jl:61-65)
 struct IsoSample {
@@ -52,11 +53,6 @@ struct SolveLaunch {
     int start_kind;      // StartKind
     int lbfgs_m;
     int max_iters;
-    // TMA kernel geometry (muse_iso_tma.cu); all zero for the register-loop kernel
-    int ch;              // elements per pipeline chunk
-    int stages;          // pipeline depth
-    int resident;        // 1: the unit's x is kept in shared memory (never written to HBM on the fast path)
-    int slice_cap;       // elements of resident x per CTA
     double atol;
     IsoEval ev;                      // at θ_eval
     IsoSample smp[kMaxThetaSim];     // mode 0: [0]; mode 1: index 2n+s ↔ θ₀ ∓/± h_n e_n
@@ -88,6 +84,19 @@ struct SolveLaunch {
     double* f_out;
     int* status_out;
     long long* dbg;      // optional timeline: 16 clock64 stamps per item (diagnostics), or null
+    // generic kernel as the re-solve pass of the streaming kernel: items come from a device-side list
+    const int* item_list;    // null: items 0..nitems-1
+    const int* item_count;   // null: nitems
+    // streaming kernel (muse_iso_stream.cu)
+    int discard_z;       // 1: ẑ is not stored (finite-difference virtual sims; the reference drops it too)
+    int seg_chunks;      // chunks per segment
+    int nseg;            // segments per unit
+    int zrows;           // 1: a z₀ row is streamed (ring stages hold 3 rows), 0: stages hold 2 rows
+    int stream_stages;
+    double* gpart;       // nitems × nseg × 16 partial sums (streaming kernel → replay kernel)
+    int* redo_count;     // number of units handed to the generic kernel by this launch
+    unsigned long long* redo_total;   // … since handle creation (diagnostics)
+    int* redo_items;
 };
 
 struct Geometry {
@@ -96,16 +105,18 @@ struct Geometry {
     int cluster;         // CTAs per cluster (≥1); group = cluster × cta when group_threads > 32
     int groups;          // resident solve groups (= scratch slots)
     int grid;            // CTAs launched
-    // TMA kernel
-    int tma;             // 1: bulk-async pipeline kernel (muse_iso_tma.cu)
-    int ch, stages, resident, slice_cap;
-    int smem_bytes;      // dynamic shared memory per CTA
+    // streaming kernel (muse_iso_stream.cu)
+    int stream;          // 1: the single-pass speculative streaming kernel is the first pass of every launch
+    int stream_grid;     // CTAs (one per SM)
+    int seg_chunks;      // chunks per segment
+    int nseg;            // segments per unit
+    int smem_bytes;      // dynamic shared memory per CTA (the ring)
 };
 
 cudaError_t launch_iso_solver(const SolveLaunch& L, const Geometry& geo, cudaStream_t st);
-cudaError_t launch_iso_tma(const SolveLaunch& L, const Geometry& geo, cudaStream_t st);
-cudaError_t iso_tma_geometry(int d, int ld, int want_group, int want_cluster, int want_resident, int device, Geometry* geo);
 cudaError_t iso_solver_geometry(int d, int want_group, int want_cluster, int device, Geometry* geo);
+cudaError_t iso_stream_geometry(int d, int ld, int device, Geometry* geo);
+cudaError_t launch_iso_stream(SolveLaunch& L, const Geometry& geo, cudaStream_t st);
 cudaError_t launch_philox_draws(double* xi, double* nu, int rows, int d, int ld, uint64_t seed,
                                 int64_t sim_offset, int master_row, cudaStream_t st);
 

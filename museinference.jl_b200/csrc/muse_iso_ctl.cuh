@@ -36,7 +36,6 @@ enum Op : int {
     kOpAxpy,         // sbuf ← sbuf + c·v1
     kOpScale,        // sbuf ← c·sbuf
     kOpNegDotG,      // sbuf ← −sbuf; red[0] = ∇f(zcur) · sbuf
-    kOpSpillX,       // resident x (shared memory) → the group's x slot row in global memory
     kOpExit,
 };
 
@@ -46,7 +45,6 @@ struct Cmd {
     int lazy;          // search direction s ≡ −∇f(zcur), not stored
     int start_kind;
     int item;          // unit index of the launch (diagnostics)
-    int resident;      // TMA kernel: x of this unit is held in shared memory (valid while zcur is the start)
     double c;
     IsoSample smp;
     const double* xi;  // null for the data unit
@@ -218,25 +216,19 @@ struct Controller {
     double com_alpha;      // last committed trial (NaN ⇒ none)
     Red7 com;
     double last_eval_alpha, last_phi, last_dphi;
+    // Streaming kernel (muse_iso_stream.cu): the issuer can only answer the sweeps of the fast path.
+    // Anything else sets `abort`; the unit is then left untouched and re-solved by the generic kernel.
+    bool abort = false;
+    bool spec_mode = false;
 
     __device__ Controller(G& g, const SolveLaunch& l, Issuer& is) : grp(g), L(l), issuer(is) {}
 
     __device__ __forceinline__ void issue(double (&red)[7]) { issuer(cur, red); }
 
-    // The unit's x may live only in shared memory during the first iteration (resident mode of the
-    // TMA kernel).  Before any operation that needs x in global memory, write it to the slot row.
-    __device__ __noinline__ void leave_resident() {
-        if (cur.resident) {
-            double red[7];
-            cur.op = kOpSpillX;
-            issue(red);
-            cur.resident = 0;
-        }
-    }
-
     // φ, φ' at step c (Hager–Zhang's ϕdϕ).  Counts one value+gradient evaluation unless the
     // point equals the last one evaluated (NLSolversBase caching semantics).
     __device__ __noinline__ void phidphi(double c, bool commit, double& phi, double& dphi) {
+        if (abort) { phi = dphi = NAN; return; }
         if (pre_valid && c == 1.0) {           // prefetched by the INIT sweep
             pre_valid = false;
             phi = pre_phi;
@@ -534,8 +526,8 @@ struct Controller {
             pseudo_iter += 1;
             double dphi_0;
             if (pseudo_iter > 1) {
+                if (spec_mode) { abort = true; break; }
                 cur.lazy = 0;
-                leave_resident();
                 dphi_0 = twoloop(pseudo_iter, rho, dxdg_h, dgdg_h, alpha_tl);
                 pre_valid = false;
             } else {
@@ -556,6 +548,7 @@ struct Controller {
             const int ls = hager_zhang(1.0, phi_0, dphi_0, alpha, phi_alpha);   // InitialStatic(alpha = 1)
             stamp(item, 3);
             pre_valid = false;
+            if (abort) break;
 
             const double* zprev = cur.zcur;
             if (alpha == 0.0) {
@@ -573,8 +566,7 @@ struct Controller {
                     com_alpha = alpha;
                     if (need_eval) fg_evals += 1;
                 }
-                // flip buffers (the resident copy of x is only addressed relative to the start vector's
-                // sweep; once the iterate moves on, continue from global memory if more work follows)
+                // flip buffers
                 double* newcur = cur.zalt;
                 cur.zalt = zother;
                 zother = newcur;
@@ -601,7 +593,7 @@ struct Controller {
             if (!fin(f) || !fin(gg)) { status = MUSE_STATUS_NONFINITE; break; }
             // update_h! (no observable effect once the loop is about to end)
             if (!converged && iter < L.max_iters) {
-                leave_resident();
+                if (spec_mode) { abort = true; break; }
                 if (alpha == 0.0) {
                     pseudo_iter = 0;                     // dx·dg = 0 ⇒ rho = Inf
                 } else {
@@ -622,6 +614,10 @@ struct Controller {
         }
         if (!converged && !stopped && status == MUSE_STATUS_G_CONVERGED && iter >= L.max_iters)
             status = MUSE_STATUS_MAXITER;
+
+        // a start vector the streaming kernel did not materialise must survive a 0-iteration solve
+        if (spec_mode && iter == 0 && (cur.start_kind == kStartTruth || cur.start_kind == kStartSharedKeep)) abort = true;
+        if (abort) return;
 
         // outputs
         stamp(item, 4);
@@ -644,6 +640,68 @@ struct Controller {
     }
 
     // ------------------------------------------------------------------ unit setup
+    // Fills `cur` / `zother` with the pointers of launch item `item` (what the reference passes to
+    // sample_x_z / ẑ_at_θ for that unit) and returns the unit's zstate cell (or null).
+    // xslot: the group's x scratch row (null in the streaming kernel, which never materialises x).
+    __device__ __forceinline__ int* setup_unit(int item, const double* zshared, double* xslot) {
+        const size_t ld = (size_t)L.ld;
+        int row, draw, tsel = 0;
+        if (L.mode == 0) {
+            if (L.include_data && item == 0) { row = 0; draw = -1; }
+            else {
+                const int k = L.first_sim + item - (L.include_data ? 1 : 0);
+                row = 1 + k;
+                draw = k;
+            }
+        } else if (L.mode == 1) {
+            // finite-difference virtual sims: item = (k·ntheta + n)·2 + sgn, θ_sim = smp[2n + sgn]
+            tsel = item % (2 * L.ntheta);
+            row = item;
+            draw = item / (2 * L.ntheta);
+        } else {
+            // the master stream's own draw (fiducial solve of get_H!, src/muse.jl:418)
+            row = 0;
+            draw = L.master_row;
+        }
+        cur.item = item;
+        cur.smp = L.smp[tsel];
+        cur.start_kind = (draw < 0 && L.start_kind == kStartTruth) ? kStartZero : L.start_kind;
+        cur.xi = draw >= 0 ? L.xi + (size_t)draw * ld : nullptr;
+        cur.nu = draw >= 0 ? L.nu + (size_t)draw * ld : nullptr;
+        cur.xw = draw >= 0 ? xslot : nullptr;
+        cur.xsrc = draw >= 0 ? cur.xw : L.xdat;
+        double* zA = L.zA ? L.zA + (size_t)row * ld : nullptr;
+        double* zB = L.zB ? L.zB + (size_t)row * ld : nullptr;
+        cur.zA = zA;
+        int* zs = L.zstate ? L.zstate + row : nullptr;
+        switch (cur.start_kind) {
+            case kStartOwn: {
+                const int st = *zs;
+                cur.zcur = st == kZZero ? nullptr : (st == kZA ? zA : zB);
+                cur.zalt = st == kZA ? zB : zA;
+                zother = st == kZA ? zA : zB;
+                break;
+            }
+            case kStartShared:
+                cur.zcur = zshared; cur.zalt = zA; zother = zB; break;
+            case kStartSharedKeep:
+                cur.zcur = zshared; cur.zalt = zB; zother = zA; break;
+            case kStartTruth:
+                cur.zcur = nullptr; cur.zalt = zB; zother = zA; break;
+            default:   // zeros
+                cur.zcur = nullptr; cur.zalt = zA; zother = zB; break;
+        }
+        return zs;
+    }
+
+    __device__ __forceinline__ const double* resolve_zshared() const {
+        if (L.zshared_state) {       // shared start = result of an earlier launch (fiducial ẑ)
+            const int st = *L.zshared_state;
+            return st == kZA ? L.zsharedA : (st == kZB ? L.zsharedB : nullptr);
+        }
+        return L.zshared;
+    }
+
     __device__ __noinline__ void run_items() {
         const int gi = grp.group_index();
         const int gn = grp.group_count();
@@ -655,61 +713,12 @@ struct Controller {
         cur.v1 = cur.v2 = nullptr;
         cur.w1 = cur.w2 = nullptr;
         cur.c = 0.0;
-
-        const double* zshared = L.zshared;
-        if (L.zshared_state) {       // shared start = result of an earlier launch (fiducial ẑ)
-            const int st = *L.zshared_state;
-            zshared = st == kZA ? L.zsharedA : (st == kZB ? L.zsharedB : nullptr);
-        }
-
-        for (int item = gi; item < L.nitems; item += gn) {
-            int row, draw, tsel = 0;
-            if (L.mode == 0) {
-                if (L.include_data && item == 0) { row = 0; draw = -1; }
-                else {
-                    const int k = L.first_sim + item - (L.include_data ? 1 : 0);
-                    row = 1 + k;
-                    draw = k;
-                }
-            } else if (L.mode == 1) {
-                // finite-difference virtual sims: item = (k·ntheta + n)·2 + sgn, θ_sim = smp[2n + sgn]
-                tsel = item % (2 * L.ntheta);
-                row = item;
-                draw = item / (2 * L.ntheta);
-            } else {
-                // the master stream's own draw (fiducial solve of get_H!, src/muse.jl:418)
-                row = 0;
-                draw = L.master_row;
-            }
-            cur.item = item;
-            cur.smp = L.smp[tsel];
-            cur.resident = (L.resident && draw >= 0) ? 1 : 0;
-            cur.start_kind = (draw < 0 && L.start_kind == kStartTruth) ? kStartZero : L.start_kind;
-            cur.xi = draw >= 0 ? L.xi + (size_t)draw * ld : nullptr;
-            cur.nu = draw >= 0 ? L.nu + (size_t)draw * ld : nullptr;
-            cur.xw = draw >= 0 ? xslot : nullptr;
-            cur.xsrc = draw >= 0 ? cur.xw : L.xdat;
-            double* zA = L.zA + (size_t)row * ld;
-            double* zB = L.zB + (size_t)row * ld;
-            cur.zA = zA;
-            int* zs = L.zstate ? L.zstate + row : nullptr;
-            switch (cur.start_kind) {
-                case kStartOwn: {
-                    const int st = *zs;
-                    cur.zcur = st == kZZero ? nullptr : (st == kZA ? zA : zB);
-                    cur.zalt = st == kZA ? zB : zA;
-                    zother = st == kZA ? zA : zB;
-                    break;
-                }
-                case kStartShared:
-                    cur.zcur = zshared; cur.zalt = zA; zother = zB; break;
-                case kStartSharedKeep:
-                    cur.zcur = zshared; cur.zalt = zB; zother = zA; break;
-                case kStartTruth:
-                    cur.zcur = nullptr; cur.zalt = zB; zother = zA; break;
-                default:   // zeros
-                    cur.zcur = nullptr; cur.zalt = zA; zother = zB; break;
-            }
+        const double* zshared = resolve_zshared();
+        // items of the launch, or the units the streaming kernel handed back (device-side list)
+        const int n = L.item_count ? *L.item_count : L.nitems;
+        for (int ii = gi; ii < n; ii += gn) {
+            const int item = L.item_list ? L.item_list[ii] : ii;
+            int* zs = setup_unit(item, zshared, xslot);
             solve(item, zs);
         }
     }

@@ -37,12 +37,14 @@ def test_device_philox_matches_oracle():
     be.close()
 
 
-# (family, d, group threads, cluster, kernel): kernel 1 = register loops, 2 = TMA pipeline, 3 = TMA + resident x
+# (family, d, group threads, cluster, kernel): kernel 1 = generic two-sweep solver only, 2 = single-pass streaming
+# kernel first (the default for d ≥ 4096), 0 = auto
 GEOMS = [
     ("funnel", 512, 0, 0, 0), ("funnel", 513, 0, 0, 0), ("funnel", 512, 256, 1, 1), ("hiergauss", 700, 0, 0, 0),
     ("funnel", 5000, 0, 0, 0), ("hiergauss", 4096, 512, 1, 1), ("funnel", 4098, 512, 2, 1),
     ("funnel", 5000, 256, 1, 2), ("funnel", 5001, 512, 2, 2), ("hiergauss", 9000, 512, 1, 2),
-    ("hiergauss", 4096, 256, 4, 3), ("funnel", 20001, 512, 8, 3), ("funnel", 3000, 256, 1, 3),
+    ("hiergauss", 4097, 0, 0, 0), ("funnel", 20001, 0, 0, 0), ("funnel", 300, 0, 0, 2), ("hiergauss", 70001, 0, 0, 0),
+    ("funnel", 65536, 0, 0, 0),
 ]
 
 
@@ -86,14 +88,17 @@ def test_map_score_cold_warm_truth(name, d, group, cluster, kernel):
         zh, g, soln = O.map_score_unit(prob, x, z, th1, atol)
         np.testing.assert_allclose(out["g"][i], g, rtol=RTOL_SIM)
         assert out["iters"][i] == soln.iterations and out["fg_evals"][i] == soln.f_calls
+    # the streaming kernel must have finished every unit itself (nothing handed back to the generic kernel)
+    assert be.profile()["redo_units"] == 0
     be.close()
 
 
-def test_zero_iteration_warm_start_keeps_previous_map():
+@pytest.mark.parametrize("d,kernel", [(512, 0), (6000, 1), (6000, 2)])
+def test_zero_iteration_warm_start_keeps_previous_map(d, kernel):
     """A start point that already satisfies ‖∇z‖_∞ ≤ atol is returned unchanged (0 iterations)."""
-    name, d, nsims = "funnel", 512, 8
+    name, nsims = "funnel", 8
     fam, draws, xd = make_inputs(name, d, nsims)
-    be = _backend(name, d, nsims, draws, xd)
+    be = _backend(name, d, nsims, draws, xd, kernel=kernel)
     th = np.array([0.7])
     be.map_score(th, th, 1e-2, include_data=True, warm_start=0)
     z1 = be.get_maps(0, nsims + 1)
@@ -101,12 +106,19 @@ def test_zero_iteration_warm_start_keeps_previous_map():
     z2 = be.get_maps(0, nsims + 1)
     assert (out["iters"] == 0).all() and (out["fg_evals"] == 1).all()
     np.testing.assert_array_equal(z1, z2)
+    # truth start with a huge atol: 0 iterations, the kept start is the simulated latent (src/muse.jl:511)
+    prob = O.OracleProblem(fam, xd, draws)
+    out = be.map_score(th, th, 1e6, include_data=False, warm_start=2)
+    assert (out["iters"] == 0).all()
+    z3 = be.get_maps(1, nsims)
+    for k in range(nsims):
+        np.testing.assert_allclose(z3[k], prob.sample_x_z(k, th)[1], rtol=1e-15)
     be.close()
 
 
 @pytest.mark.parametrize("name,d,kw", [("funnel", 512, {}), ("hiergauss", 1024, {}),
-                                       ("funnel", 6000, dict(group=256, cluster=2, kernel=3)),
-                                       ("hiergauss", 5000, dict(group=512, cluster=1, kernel=2))])
+                                       ("funnel", 6000, dict(group=256, cluster=2, kernel=1)),
+                                       ("hiergauss", 5000, {}), ("hiergauss", 40000, dict(kernel=2))])
 def test_fd_jacobian_matches_oracle(name, d, kw):
     nsims, nH = 20, 6
     fam, draws, xd = make_inputs(name, d, nsims)
@@ -123,11 +135,12 @@ def test_fd_jacobian_matches_oracle(name, d, kw):
     be.close()
 
 
-@pytest.mark.parametrize("kw", [{}, dict(group=32), dict(group=256, cluster=1, kernel=1), dict(group=256, cluster=2, kernel=2),
-                                dict(group=512, cluster=4, kernel=3)])
+@pytest.mark.parametrize("kw", [{}, dict(group=32), dict(group=256, cluster=1, kernel=1), dict(group=256, cluster=2, kernel=1),
+                                dict(kernel=2), dict(group=512, cluster=1, kernel=2)])
 def test_history_path_runs_and_stays_at_the_map(kw):
     """atol far below round-off forces iterations ≥ 2: two-loop recursion over the (dx, dg) history,
-    direction resets, x/f stagnation exits (and, for kernel 3, the spill of resident x).  The iterate
+    direction resets, x/f stagnation exits.  With kernel 2 the streaming kernel cannot finish such a unit:
+    it must hand every unit back and the generic kernel re-solves them from the untouched start.  The iterate
     must stay at the closed-form MAP and the score must agree with the oracle run the same way."""
     name, d, nsims = "funnel", 3000, 12
     fam, draws, xd = make_inputs(name, d, nsims)
@@ -138,6 +151,7 @@ def test_history_path_runs_and_stays_at_the_map(kw):
     zs = be.get_maps(0, nsims + 1)
     assert (out["iters"] >= 2).all()
     assert np.isin(out["status"], [0, 1, 3]).all()
+    assert be.profile()["redo_units"] == (nsims + 1 if kw.get("kernel") == 2 else 0)
     for u in range(nsims + 1):
         x = xd if u == 0 else prob.sample_x_z(u - 1, th)[0]
         np.testing.assert_allclose(zs[u], fam.exact_map(x, th), rtol=1e-12, atol=1e-13)
