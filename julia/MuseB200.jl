@@ -1,0 +1,178 @@
+# MuseB200.jl — Julia glue that makes libmuse_b200.so a drop-in backend of MuseInference.jl for the
+# registered model families.  UNEXECUTED: there is no Julia toolchain in the build image or on the GPU
+# box; this file is the binding a maintainer would add (INTEGRATION.md), written against
+# include/muse_b200.h.  The Python ctypes host (museinference.jl_b200/) binds the same symbols and is
+# what the tests and the benchmark run.
+#
+# It replaces exactly the three mapped blocks of the reference,
+#     muse!   src/muse.jl:169-176      get_J!  src/muse.jl:508-525      get_H!  src/muse.jl:417-442 (+ src/util.jl:9-26)
+# and keeps every other line of those functions (outer θ solver, prior terms, covariance assembly).
+module MuseB200
+
+using MuseInference
+using MuseInference: AbstractMuseProblem, MuseResult, standardizeθ, finalize_result!
+using Random, Statistics, LinearAlgebra
+
+const libmuse = get(ENV, "LIBMUSE_B200", "libmuse_b200.so")
+
+const FAMILY = Dict(:funnel => Cint(1), :hiergauss => Cint(2), :corrgauss => Cint(3))
+const START_ZEROS, START_PREV, START_TRUTH, START_USER = Cint(0), Cint(1), Cint(2), Cint(3)
+
+# mirrors `struct muse_cfg` (include/muse_b200.h)
+Base.@kwdef struct MuseCfg
+    abi_version::Cint = 1
+    family::Cint
+    d::Cint
+    ntheta::Cint
+    nsims::Cint
+    device::Cint = 0
+    sim_offset::Int64 = 0
+    nsims_h::Cint = 0
+    kernel::Cint = 0
+    h_sim_offset::Int64 = 0
+    lbfgs_m::Cint = 0
+    max_iters::Cint = 0
+    group::Cint = 0
+    cluster::Cint = 0
+    P::Ptr{Cdouble} = C_NULL
+    L::Ptr{Cdouble} = C_NULL
+    stream::Ptr{Cvoid} = C_NULL
+end
+
+struct B200Error <: Exception
+    code::Cint
+    msg::String
+end
+
+function check(h, rc)
+    rc == 0 && return
+    msg = unsafe_string(ccall((:muse_b200_last_error, libmuse), Cstring, (Ptr{Cvoid},), h))
+    throw(B200Error(rc, msg))
+end
+
+"""
+    B200MuseProblem(x, family; logPriorθ = θ -> 0)
+
+The B200 counterpart of `SimpleMuseProblem` (src/simple.jl:4-12).  A GPU backend cannot introspect Julia
+closures, so the model is *named*: `:funnel` (src/simple.jl:58-76), `:hiergauss` or `:corrgauss`.
+Any other `AbstractMuseProblem` (Turing, Soss, arbitrary closures) is not supported: calling `muse` on it
+through this backend throws; there is no CPU fallback.
+"""
+mutable struct B200MuseProblem <: AbstractMuseProblem
+    x::Vector{Float64}
+    family::Symbol
+    logPriorθ
+    handle::Ptr{Cvoid}
+    nsims::Int
+    seed::UInt64
+end
+B200MuseProblem(x, family::Symbol; logPriorθ = θ -> 0.0) =
+    (haskey(FAMILY, family) || error("model family $family is not registered with the B200 backend");
+     B200MuseProblem(collect(Float64, x), family, logPriorθ, C_NULL, 0, 0))
+MuseInference.logPriorθ(p::B200MuseProblem, θ) = p.logPriorθ(θ)
+ntheta(p::B200MuseProblem) = p.family === :hiergauss ? 2 : 1
+
+function backend!(p::B200MuseProblem, nsims::Integer, seed::UInt64)
+    if p.handle == C_NULL || p.nsims != nsims
+        p.handle != C_NULL && ccall((:muse_b200_destroy, libmuse), Cint, (Ptr{Cvoid},), p.handle)
+        cfg = Ref(MuseCfg(family = FAMILY[p.family], d = length(p.x), ntheta = ntheta(p), nsims = nsims))
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        rc = ccall((:muse_b200_create, libmuse), Cint, (Ref{MuseCfg}, Ref{Ptr{Cvoid}}), cfg, h)
+        rc == 0 || throw(B200Error(rc, unsafe_string(ccall((:muse_b200_last_error, libmuse), Cstring, (Ptr{Cvoid},), C_NULL))))
+        p.handle, p.nsims, p.seed = h[], nsims, typemax(UInt64)
+        GC.@preserve p check(p.handle, ccall((:muse_b200_set_data, libmuse), Cint, (Ptr{Cvoid}, Ptr{Cdouble}), p.handle, p.x))
+    end
+    if p.seed != seed   # split_rng (src/util.jl:85-92): the same child streams at every call for a given master rng
+        check(p.handle, ccall((:muse_b200_seed_draws, libmuse), Cint, (Ptr{Cvoid}, UInt64), p.handle, seed))
+        p.seed = seed
+    end
+    p.handle
+end
+
+# body of src/muse.jl:169-176 / 508-514 for the whole batch
+function map_score(p::B200MuseProblem, h, θsim, θeval, atol; include_data::Bool, warm_start::Cint, first_sim = 0, count = p.nsims)
+    units = count + include_data
+    g = Matrix{Float64}(undef, ntheta(p), units)          # column-major nθ × units == row-major units × nθ
+    iters = Vector{Cint}(undef, units); fg = similar(iters); status = similar(iters)
+    gnorm = Vector{Float64}(undef, units)
+    ts, te = collect(Float64, θsim), collect(Float64, θeval)
+    GC.@preserve ts te g iters fg gnorm status check(h, ccall((:muse_b200_map_score, libmuse), Cint,
+        (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Cdouble, Cint, Cint, Cint, Cint, Ptr{Cdouble}, Ptr{Cint}, Ptr{Cint}, Ptr{Cdouble}, Ptr{Cint}),
+        h, ts, te, atol, include_data, warm_start, first_sim, count, g, iters, fg, gnorm, status))
+    any(==(4), status) && error("MAP solution failed with a non-finite objective (src/interface.jl:170)")
+    (; g, iters, fg, gnorm, status)
+end
+
+seed_of(rng::AbstractRNG) = rand(copy(rng), UInt64)       # a pure function of the master rng, which is not advanced
+
+function MuseInference.muse!(result::MuseResult, prob::B200MuseProblem, θ₀ = nothing;
+        rng = nothing, maxsteps = 50, θ_rtol = 1e-1, ∇z_logLike_atol = 1e-2, nsims = 100, α = 0.7,
+        regularize = identity, get_covariance = false, kwargs...)
+    result.rng = rng = something(rng, result.rng, copy(Random.default_rng()))           # src/muse.jl:134
+    θ = θunreg = standardizeθ(prob, something(result.θ, θ₀))                            # :135
+    h = backend!(prob, nsims, seed_of(rng))
+    history = result.history
+    first_pass = true
+    for i = (length(history) + 1):maxsteps                                              # :159
+        if i > 2                                                                        # :163-166
+            Δθ = history[end].θ .- history[end-1].θ
+            sqrt(-(Δθ' * history[end].H⁻¹_post * Δθ)) < θ_rtol && break
+        end
+        out = map_score(prob, h, θ, θ, ∇z_logLike_atol; include_data = true,            # :169-176 → one ccall
+                        warm_start = first_pass ? START_ZEROS : START_PREV)
+        first_pass = false
+        g_like_dat, g_like_sims = out.g[:, 1], [out.g[:, k] for k = 2:size(out.g, 2)]
+        g_like = g_like_dat .- mean(g_like_sims)                                        # :183
+        g_prior = MuseInference.AD.gradient(MuseInference.AD.ForwardDiffBackend(), θ -> prob.logPriorθ(θ), θ)[1]
+        g_post = g_like .+ g_prior
+        H⁻¹_like = Diagonal(-1 ./ var(g_like_sims))                                     # :188-189
+        H_prior = MuseInference.AD.hessian(MuseInference.AD.ForwardDiffBackend(), θ -> prob.logPriorθ(θ), θ)[1]
+        H⁻¹_post = inv(inv(H⁻¹_like) + H_prior)                                         # :207-208
+        push!(history, (; θ, θunreg, g_like_sims, g_like_dat, g_like, g_prior, g_post, H⁻¹_post, H_prior, H⁻¹_like))
+        θunreg = θ .- α .* (H⁻¹_post * g_post)                                          # :224
+        θ = regularize(θunreg)
+        result.θ = θunreg; result.gs = g_like_sims                                      # :230-231
+    end
+    if get_covariance                                                                   # :244-247
+        MuseInference.get_J!(result, prob; rng, nsims, ∇z_logLike_atol)
+        MuseInference.get_H!(result, prob; rng, nsims = max(1, nsims ÷ 10), ∇z_logLike_atol)
+    end
+    result
+end
+
+function MuseInference.get_J!(result::MuseResult, prob::B200MuseProblem, θ₀ = nothing;
+        rng = nothing, nsims = 100, ∇z_logLike_atol = 1e-2, kwargs...)
+    rng = something(rng, result.rng, copy(Random.default_rng()))
+    θ₀ = standardizeθ(prob, something(θ₀, result.θ))                                    # :498
+    existing = length(result.gs)
+    if nsims > existing                                                                 # :499-506
+        h = backend!(prob, nsims, seed_of(rng))
+        out = map_score(prob, h, θ₀, θ₀, ∇z_logLike_atol; include_data = false, warm_start = START_TRUTH,
+                        first_sim = existing, count = nsims - existing)                 # :508-514
+        append!(result.gs, [out.g[:, k] for k = 1:size(out.g, 2)])
+    end
+    result.J = θ₀ isa Number || length(θ₀) == 1 ? var(result.gs) : cov(result.gs)       # :529
+    finalize_result!(result, prob)
+end
+
+function MuseInference.get_H!(result::MuseResult, prob::B200MuseProblem, θ₀ = nothing;
+        rng = nothing, nsims = 10, step = nothing, ∇z_logLike_atol = 1e-2, implicit_diff = false, kwargs...)
+    implicit_diff && error("implicit_diff=true is not provided by the B200 backend")
+    rng = something(rng, result.rng, copy(Random.default_rng()))
+    θ₀ = standardizeθ(prob, something(θ₀, result.θ))                                    # :315
+    remaining = nsims - length(result.Hs)
+    remaining > 0 || return result
+    step = something(step, 0.1 ./ std(result.gs))                                       # :411-413
+    h = backend!(prob, max(prob.nsims, remaining), seed_of(rng))
+    nθ = ntheta(prob)
+    Hs = Array{Float64}(undef, nθ, nθ, remaining)     # column-major (n, i, k) == C row-major [k][i][n]
+    t0, st = collect(Float64, θ₀), collect(Float64, step)
+    GC.@preserve t0 st Hs check(h, ccall((:muse_b200_fd_jacobian, libmuse), Cint,
+        (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Cint, Cdouble, Ptr{Cdouble}, Ptr{Cint}),
+        h, t0, st, remaining, ∇z_logLike_atol, Hs, C_NULL))                             # :417-442 + src/util.jl:9-26
+    append!(result.Hs, [permutedims(Hs[:, :, k]) for k = 1:remaining])
+    result.H = mean(result.Hs)                                                          # :446
+    finalize_result!(result, prob)
+end
+
+end # module
