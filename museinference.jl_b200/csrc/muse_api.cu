@@ -138,6 +138,7 @@ static void fill_common(muse_handle* h, SolveLaunch& L) {
     L.xslot = h->xslot;
     L.gpart = h->gpart;
     L.redo_count = h->redo_count;
+    L.work_next = h->redo_count + 1;
     L.redo_items = h->redo_items;
     L.redo_total = h->redo_total;
     L.dxh = h->dxh;
@@ -163,7 +164,7 @@ static int launch_solver(muse_handle* h, const SolveLaunch& L, double bytes) {
         // the units pass 1 handed back (device-side list; normally empty, then its CTAs exit at once)
         SolveLaunch S = L;
         if (h->dbg_cap < h->geo.stream_grid) S.dbg = nullptr;   // the streaming kernel stamps per CTA
-        CUDA_TRY(h, cudaMemsetAsync(h->redo_count, 0, sizeof(int), h->stream));
+        CUDA_TRY(h, cudaMemsetAsync(h->redo_count, 0, 2 * sizeof(int), h->stream));
         CUDA_TRY(h, launch_iso_stream(S, h->geo, h->stream));
         SolveLaunch R = L;
         R.item_list = h->redo_items;
@@ -282,8 +283,8 @@ int muse_b200_create(const muse_cfg* cfg, muse_handle** out) {
     CREATE_TRY(cudaMalloc(&h->zfidA, ld * B));
     CREATE_TRY(cudaMalloc(&h->zfidB, ld * B));
     CREATE_TRY(cudaMalloc(&h->zfid_state, sizeof(int)));
-    CREATE_TRY(cudaMalloc(&h->redo_count, sizeof(int)));
-    CREATE_TRY(cudaMemsetAsync(h->redo_count, 0, sizeof(int), h->stream));
+    CREATE_TRY(cudaMalloc(&h->redo_count, 2 * sizeof(int)));      // [hand-back count, streaming work counter]
+    CREATE_TRY(cudaMemsetAsync(h->redo_count, 0, 2 * sizeof(int), h->stream));
     CREATE_TRY(cudaMalloc(&h->redo_total, sizeof(unsigned long long)));
     CREATE_TRY(cudaMemsetAsync(h->redo_total, 0, sizeof(unsigned long long), h->stream));
     CREATE_TRY(cudaMemsetAsync(h->xi, 0, rows * ld * B, h->stream));

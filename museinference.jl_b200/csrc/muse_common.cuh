@@ -95,6 +95,7 @@ struct SolveLaunch {
     int stream_stages;
     double* gpart;       // nitems × nseg × 16 partial sums (streaming kernel → replay kernel)
     int* redo_count;     // number of units handed to the generic kernel by this launch
+    int* work_next;      // dynamic work counter of the streaming kernel (zeroed before every launch)
     unsigned long long* redo_total;   // … since handle creation (diagnostics)
     int* redo_items;
 };

@@ -57,11 +57,14 @@ constexpr double kSpecTol = 1e-11;
 
 // reduction slots; kMaxMask marks the max-reductions
 enum Red : int {
-    rR0 = 0, rS2_0, rS1_0, rGG0, rGM0,          // at z₀
-    rR1, rS2_1, rDP1,                           // at z₀ + s
-    rRT, rS2T, rS1T, rDPT, rGGT, rGMT, rXC,     // at z₀ + c_spec·s
+    rR0 = 0, rS2_0, rS1_0, rGG0,                // sums at z₀
+    rR1, rS2_1, rDP1,                           // sums at z₀ + s
+    rRT, rS2T, rS1T, rDPT, rGGT,                // sums at z₀ + c_spec·s
+    rGM0, rGMT, rXC,                            // maxima: ‖∇f(z₀)‖∞, ‖∇f(z₀ + c_spec·s)‖∞, max|Δz|
 };
+constexpr int kNSum = 12;                       // slots [0, kNSum) are sums, [kNSum, kNRed) maxima of non-negative values
 constexpr unsigned kMaxMask = (1u << rGM0) | (1u << rGMT) | (1u << rXC);
+static_assert(rGM0 == kNSum && rXC == kNRed - 1, "reduction slot layout");
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -277,9 +280,12 @@ iso_stream_kernel(const __grid_constant__ SolveLaunch L) {
 
     const int nchunks = (L.ld + kChunk - 1) / kChunk;
     const int nseg = L.nseg;
-    const long long total = (long long)L.nitems * nseg;
-    const int n_my = total > blockIdx.x ? (int)((total - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+    const int total = L.nitems * nseg;
 
+    // Work items (unit, segment) are handed out dynamically (one global counter, zeroed by the host before the
+    // launch): SMs differ in speed by ±15 % on this workload, a static split leaves the slow ones as a tail.
+    // The producer is the only role that talks to the counter; the others learn each item — and the end of work,
+    // an item with unit = −1 — from the descriptor ring.
     if (warp == 0) {
         // ------------------------------------------------------------------ producer
         if (lane == 0) {
@@ -291,12 +297,20 @@ iso_stream_kernel(const __grid_constant__ SolveLaunch L) {
             const uint64_t zpol = (L.start_kind == kStartShared || L.start_kind == kStartSharedKeep) ? pol.last : pol.first;
             int stage = 0;
             uint32_t phase = 0;
-            for (int i = 0; i < n_my; ++i) {
-                const long long w = blockIdx.x + (long long)i * gridDim.x;
-                const int unit = (int)(w / nseg), seg = (int)(w % nseg);
+            int w = atomicAdd(L.work_next, 1);
+            for (int i = 0;; ++i) {
+                ItemDesc& it = sh.desc[i % kDescRing];
+                if (w >= total) {      // end of work: an empty stage carrying the sentinel descriptor
+                    it.unit = -1;
+                    it.nch = 0;
+                    mbar_wait(&sh.empty[stage], phase ^ 1u);
+                    mbar_arrive(&sh.full[stage]);
+                    break;
+                }
+                const int wnext = atomicAdd(L.work_next, 1);      // fetched early: its latency hides behind this item
+                const int unit = w / nseg, seg = w % nseg;
                 u.setup_unit(unit, zshared, nullptr);
                 const Cmd& c = u.cur;
-                ItemDesc& it = sh.desc[i % kDescRing];
                 it.unit = unit;
                 it.seg = seg;
                 it.chunk0 = seg * L.seg_chunks;
@@ -322,14 +336,17 @@ iso_stream_kernel(const __grid_constant__ SolveLaunch L) {
                     if (rz) bulk_g2s(dst + 2 * kChunk, rz + base, bytes, &sh.full[stage], zpol);
                     if (++stage == stages) { stage = 0; phase ^= 1u; }
                 }
+                w = wnext;
             }
             if (dbg) dbg[3] = now_ns();
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ finisher
-        for (int i = 0; i < n_my; ++i) {
+        for (int i = 0;; ++i) {
             const int slot = i & 1;
             mbar_wait(&sh.part_full[slot], (uint32_t)(i >> 1) & 1u);
+            const int unit = sh.desc[i % kDescRing].unit, seg = sh.desc[i % kDescRing].seg;
+            if (unit < 0) break;
             double acc = 0.0;
             if (lane < kNRed) {
                 acc = sh.part[slot][0][lane];
@@ -339,7 +356,6 @@ iso_stream_kernel(const __grid_constant__ SolveLaunch L) {
                     acc = mx ? fmax(acc, o) : acc + o;
                 }
             }
-            const int unit = sh.desc[i % kDescRing].unit, seg = sh.desc[i % kDescRing].seg;
             __syncwarp();
             if (lane == 0) mbar_arrive(&sh.part_empty[slot]);
             if (lane < kNRed) L.gpart[((size_t)unit * nseg + seg) * kRedPad + lane] = acc;   // read by iso_replay_kernel
@@ -352,12 +368,20 @@ iso_stream_kernel(const __grid_constant__ SolveLaunch L) {
         const L2Policy pol = make_policies();
         int stage = 0;
         uint32_t phase = 0;
-        for (int i = 0; i < n_my; ++i) {
+        for (int i = 0;; ++i) {
             Acc A;
 #pragma unroll
             for (int k = 0; k < kNRed; ++k) A.v[k] = 0.0;
             mbar_wait(&sh.full[stage], phase);          // the item's first chunk has landed ⇒ its descriptor is visible
             const ItemDesc it = sh.desc[i % kDescRing];
+            const int slot = i & 1;
+            if (it.unit < 0) {                          // end of work: wake the finisher (mailbox protocol as for an item)
+                if (lane == 0) {
+                    mbar_wait(&sh.part_empty[slot], ((uint32_t)(i >> 1) & 1u) ^ 1u);
+                    mbar_arrive(&sh.part_full[slot]);
+                }
+                break;
+            }
             for (int k = 0; k < it.nch; ++k) {
                 if (k) mbar_wait(&sh.full[stage], phase);
                 const double* buf = ring + (size_t)stage * rows * kChunk;
@@ -375,22 +399,41 @@ iso_stream_kernel(const __grid_constant__ SolveLaunch L) {
                 if (lane == 0) mbar_arrive(&sh.empty[stage]);
                 if (++stage == stages) { stage = 0; phase ^= 1u; }
             }
-            // warp butterfly, then hand the warp's partial to the finisher
+            // Warp reduction, then the warp's partial goes to the finisher's mailbox.
+            // Sums: the xor butterfly (16, 8, 4, 2, 1) done "transposed" — at every level a lane keeps half of its
+            // slots and ships the other half — 16 shuffles instead of 60, same association tree, slot k ends in
+            // lane 2k.  Maxima (non-negative): two integer REDUX over the high and low words.
+            double sv[16];
 #pragma unroll
-            for (int k = 0; k < kNRed; ++k) {
+            for (int k = 0; k < 16; ++k) sv[k] = k < kNSum ? A.v[k] : 0.0;
 #pragma unroll
-                for (int off = 16; off > 0; off >>= 1) {
-                    const double o = __shfl_xor_sync(0xffffffffu, A.v[k], off);
-                    A.v[k] = ((kMaxMask >> k) & 1u) ? fmax(A.v[k], o) : A.v[k] + o;
+            for (int half = 8, off = 16; half >= 1; half >>= 1, off >>= 1) {
+                const bool up = (lane & off) != 0;
+#pragma unroll
+                for (int k = 0; k < half; ++k) {
+                    const double send = up ? sv[k] : sv[k + half];
+                    const double keep = up ? sv[k + half] : sv[k];
+                    sv[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
                 }
             }
-            const int slot = i & 1;
-            if (lane == 0) {
-                mbar_wait(&sh.part_empty[slot], ((uint32_t)(i >> 1) & 1u) ^ 1u);
+            sv[0] += __shfl_xor_sync(0xffffffffu, sv[0], 1);
+            double mv[kNRed - kNSum];
 #pragma unroll
-                for (int k = 0; k < kNRed; ++k) sh.part[slot][cw][k] = A.v[k];
-                mbar_arrive(&sh.part_full[slot]);
+            for (int k = 0; k < kNRed - kNSum; ++k) {
+                const unsigned hi = (unsigned)__double2hiint(A.v[kNSum + k]), lo = (unsigned)__double2loint(A.v[kNSum + k]);
+                const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+                const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+                mv[k] = __hiloint2double((int)mh, (int)ml);
             }
+            if (lane == 0) mbar_wait(&sh.part_empty[slot], ((uint32_t)(i >> 1) & 1u) ^ 1u);
+            __syncwarp();
+            if (!(lane & 1) && (lane >> 1) < kNSum) sh.part[slot][cw][lane >> 1] = sv[0];
+            if (lane == 0) {
+#pragma unroll
+                for (int k = 0; k < kNRed - kNSum; ++k) sh.part[slot][cw][kNSum + k] = mv[k];
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sh.part_full[slot]);
         }
         if (dbg && ct == 0) dbg[5] = now_ns();
     }
@@ -459,10 +502,10 @@ cudaError_t iso_stream_geometry(int d, int ld, int device, Geometry* geo) {
 }
 
 // pass 1 (streaming) + its scalar replay.  A unit is split into segments only as far as needed to give every
-// CTA ≥ ~8 work items (few units: fiducial solve, finite-difference pass); otherwise one item per unit.
+// CTA ≥ ~32 work items to balance dynamically (few units: fiducial solve, finite-difference pass ⇒ fine split).
 cudaError_t launch_iso_stream(SolveLaunch& L, const Geometry& geo, cudaStream_t st) {
     const int nchunks = (L.ld + kChunk - 1) / kChunk;
-    int want = (int)((8LL * geo.stream_grid + L.nitems - 1) / L.nitems);     // segments per unit wanted
+    int want = (int)((32LL * geo.stream_grid + L.nitems - 1) / L.nitems);    // segments per unit wanted
     if (want > geo.nseg) want = geo.nseg;
     if (want < 1) want = 1;
     L.seg_chunks = (nchunks + want - 1) / want;
