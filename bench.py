@@ -164,7 +164,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    _emit(line)
 
 
 # ----------------------------------------------------------------------------- GPU arm
@@ -198,6 +198,17 @@ def run_b200(args):
                                stream=stream.cuda_stream)
     th0 = theta_start(family)
 
+    exch = {"s": 0.0, "n": 0}
+    if world > 1:       # wall time spent in the exchange step (all-gather of the score rows), for the record
+        for name in ("allgather_device_scores", "allgather_host_rows", "allgather_rows"):
+            def timed(*a, _f=getattr(pool, name), **k):
+                t = time.perf_counter()
+                r = _f(*a, **k)
+                exch["s"] += time.perf_counter() - t
+                exch["n"] += 1
+                return r
+            setattr(pool, name, timed)
+
     def solve(seed):
         return m.muse(prob, th0, rng=seed, nsims=nsims_total, gradz_logLike_atol=ATOL, get_covariance=True, pool=pool)
 
@@ -218,11 +229,13 @@ def run_b200(args):
     if rank == 0:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    exch["s"], exch["n"] = 0.0, 0
     e0.record(stream)
     for _ in range(args.steps):
         res = solve(SIM_SEED)
     e1.record(stream)
     sync_all()
+    exch_ms_per_step, exch_per_step = 1e3 * exch["s"] / args.steps, exch["n"] / args.steps
     clocks = sampler.stop() if rank == 0 else None
     ms = e0.elapsed_time(e1)
     prof = be.profile()
@@ -290,6 +303,8 @@ def run_b200(args):
                             f"full solve θ̂/J/H, θ₀={th0.tolist()}, atol={ATOL} (BASELINE configs[2])",
                 "nsims_total": nsims_total, "outer_iterations": len(res.history),
                 "units_per_step": units_all / args.steps, "l2": "inputs_larger_than_l2 (ξ,ν: %.2f GB per GPU)" % (2 * args.nsims * d * 8 / 1e9 if args.scaling == "weak" else 2 * nsims_total / world * d * 8 / 1e9),
+                "exchange": {"allgathers_per_step": exch_per_step, "wall_ms_per_step_rank0": exch_ms_per_step,
+                             "bytes_per_allgather": nsims_total * th0.size * 8},
                 "solver_geometry": geo, "theta_hat": [float(t) for t in res.theta],
                 "sigma": [float(s) for s in np.sqrt(np.diag(res.Sigma))],
             },
@@ -313,7 +328,7 @@ def run_b200(args):
                 "value": rate, "unit": "sims/s", "cores": threads, "kind": "port",
                 "sample": f"full solve (θ̂,J,H) on nsims={nsims_cpu} of the same shape, {units} units in {secs:.2f}s; "
                           "oracle C port with analytic gradients (faster than the Julia reference's AD path)"}
-        print(json.dumps(line))
+        _emit(line)
     prob.close()
     if world > 1:
         dist.destroy_process_group()
@@ -321,6 +336,17 @@ def run_b200(args):
 
 def main():
     args = parse()
+    # Libraries (NCCL's version banner, torchrun notices) may print to stdout; the contract is ONE JSON line there.
+    # Route fd 1 to stderr for the duration of the run and emit the JSON line on the saved descriptor.
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    global _emit
+
+    def _emit(line):
+        sys.stdout.flush()
+        os.write(saved, (json.dumps(line) + "\n").encode())
+
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -157,6 +157,24 @@ int  muse_b200_map_score_async(muse_handle* h, const double* theta_sim, const do
 int  muse_b200_fetch(muse_handle* h, int32_t units, double* g_out, int32_t* iters_out,
                      int32_t* fg_out, double* gnorm_out, int32_t* status_out);
 
+/* Device address of the score matrix the last map_score[_async] produced (units × ntheta doubles, row-major, in
+ * the order [data?, sims...]); valid on the handle's stream until the next call that resizes the outputs.  Lets a
+ * multi-GPU host all-gather the scores with NCCL straight from device memory (the one exchange step of the path,
+ * src/muse.jl:177-183) without a host round trip. */
+int  muse_b200_device_scores(muse_handle* h, double** g_dev, int32_t* capacity_units);
+
+/* The exchange step across ranks (one process per GPU on one node): an NCCL all-gather of score rows, run on the
+ * handle's stream directly from the device score matrix.  Replaces the master-side gather of the reference's pmap
+ * (src/muse.jl:169, 177-183).  Rank 0 creates the id, the host distributes its 128 bytes, every rank calls
+ * comm_init on its handle.  allgather_scores sends this rank's rows [first_row, first_row + counts[rank]) and
+ * returns the concatenation over ranks (Σ counts × ntheta doubles, rank order) in out_host; allgather_rows does the
+ * same for rows held on the host (the per-sim Jacobians of get_H!, src/muse.jl:426, 446). */
+int  muse_b200_comm_unique_id(uint8_t* id_out /* 128 bytes */);
+int  muse_b200_comm_init(muse_handle* h, int32_t nranks, int32_t rank, const uint8_t* id /* 128 bytes */);
+int  muse_b200_comm_destroy(muse_handle* h);
+int  muse_b200_allgather_scores(muse_handle* h, int32_t first_row, const int32_t* counts /* nranks */, double* out_host);
+int  muse_b200_allgather_rows(muse_handle* h, const double* local_host, int32_t ncol, const int32_t* counts, double* out_host);
+
 /* Finite-difference branch of get_H! (src/muse.jl:417-442 + pjacobian src/util.jl:9-26 with
  * fdm = central_fdm(3,1) and an explicit step): one fiducial MAP of the master-stream draw from
  * zero(z) (the reference computes nsims_H identical copies, :417-423), then for the first

@@ -8,8 +8,8 @@ import subprocess
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libmuse_b200.so")
-SOURCES = ["muse_api.cu", "muse_iso_solver.cu", "muse_iso_stream.cu", "muse_draws.cu"]
-HEADERS = ["muse_common.cuh", "muse_group.cuh", "muse_iso_ctl.cuh", os.path.join("..", "..", "include", "muse_b200.h")]
+SOURCES = ["muse_api.cu", "muse_iso_solver.cu", "muse_iso_stream.cu", "muse_draws.cu", "muse_comm.cu"]
+HEADERS = ["muse_common.cuh", "muse_handle.cuh", "muse_group.cuh", "muse_iso_ctl.cuh", os.path.join("..", "..", "include", "muse_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
@@ -36,7 +36,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     """Compile the CUDA sources into ``museinference.jl_b200/libmuse_b200.so``."""
     if not force and not is_stale():
         return LIB_PATH
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", LIB_PATH, *[os.path.join(CSRC, s) for s in SOURCES]]
+    cmd = [_nvcc(), *NVCC_FLAGS, "-o", LIB_PATH, *[os.path.join(CSRC, s) for s in SOURCES], "-ldl"]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

@@ -64,6 +64,12 @@ SIGNATURES = {
     "muse_b200_map_score_async": (C.c_int, [C.c_void_p, c_double_p, c_double_p, C.c_double, C.c_int32, C.c_int32,
                                             C.c_int32, C.c_int32]),
     "muse_b200_fetch": (C.c_int, [C.c_void_p, C.c_int32, c_double_p, c_int32_p, c_int32_p, c_double_p, c_int32_p]),
+    "muse_b200_device_scores": (C.c_int, [C.c_void_p, C.POINTER(c_double_p), c_int32_p]),
+    "muse_b200_comm_unique_id": (C.c_int, [C.POINTER(C.c_uint8)]),
+    "muse_b200_comm_init": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_uint8)]),
+    "muse_b200_comm_destroy": (C.c_int, [C.c_void_p]),
+    "muse_b200_allgather_scores": (C.c_int, [C.c_void_p, C.c_int32, c_int32_p, c_double_p]),
+    "muse_b200_allgather_rows": (C.c_int, [C.c_void_p, c_double_p, C.c_int32, c_int32_p, c_double_p]),
     "muse_b200_fd_jacobian": (C.c_int, [C.c_void_p, c_double_p, c_double_p, C.c_int32, C.c_double, c_double_p, c_int32_p]),
     "muse_b200_get_maps": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, c_double_p]),
     "muse_b200_profile_reset": (C.c_int, [C.c_void_p, C.c_int32]),

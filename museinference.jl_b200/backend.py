@@ -48,7 +48,9 @@ class B200Backend:
             abi_version=_capi.ABI_VERSION, family=FAMILY_IDS[family], d=self.d, ntheta=self.ntheta,
             nsims=self.nsims, device=int(device), sim_offset=int(sim_offset), nsims_h=self.nsims_h, kernel=int(kernel),
             h_sim_offset=int(h_sim_offset), lbfgs_m=int(lbfgs_m), max_iters=int(max_iters), group=int(group),
-            cluster=int(cluster), P=_dp(self._P), L=_dp(self._L), stream=C.c_void_p(stream) if stream else None)
+            cluster=int(cluster), P=_dp(self._P), L=_dp(self._L),
+            stream=None if stream is None else C.c_void_p(int(stream) if int(stream) != 0 else 1))
+        self.comm = None
         self._h = C.c_void_p()
         rc = self._lib.muse_b200_create(C.byref(cfg), C.byref(self._h))
         if rc != 0:
@@ -79,7 +81,13 @@ class B200Backend:
         self.close()
 
     def set_stream(self, stream):
-        self._check(self._lib.muse_b200_set_stream(self._h, C.c_void_p(stream) if stream else None))
+        """``None`` → library-owned stream; an integer → that cudaStream_t (0, the legacy default stream, is passed
+        as cudaStreamLegacy so that it is not mistaken for "none")."""
+        if stream is None:
+            arg = None
+        else:
+            arg = C.c_void_p(int(stream) if int(stream) != 0 else 1)
+        self._check(self._lib.muse_b200_set_stream(self._h, arg))
 
     # ------------------------------------------------------------------ inputs
     def set_data(self, x):
@@ -149,6 +157,41 @@ class B200Backend:
         status = np.empty(units, dtype=np.int32)
         self._check(self._lib.muse_b200_fetch(self._h, int(units), _dp(g), _ip(iters), _ip(fg), _dp(gnorm), _ip(status)))
         return dict(g=g, iters=iters, fg_evals=fg, gnorm=gnorm, status=status)
+
+    def device_scores(self):
+        """(device pointer, capacity in units) of the score matrix of the last map_score[_async]."""
+        ptr = _capi.c_double_p()
+        cap = C.c_int32()
+        self._check(self._lib.muse_b200_device_scores(self._h, C.byref(ptr), C.byref(cap)))
+        return C.cast(ptr, C.c_void_p).value, cap.value
+
+    # ------------------------------------------------------------------ exchange step (multi-GPU)
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = (C.c_uint8 * 128)()
+        rc = _capi.load_library().muse_b200_comm_unique_id(buf)
+        if rc != 0:
+            raise MuseBackendError(rc, "ncclGetUniqueId failed (is libnccl.so.2 loadable?)")
+        return bytes(buf)
+
+    def comm_init(self, nranks: int, rank: int, unique_id: bytes):
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        self._check(self._lib.muse_b200_comm_init(self._h, int(nranks), int(rank), buf))
+        self.comm = (int(nranks), int(rank))
+
+    def allgather_scores(self, first_row: int, counts):
+        counts = np.ascontiguousarray(counts, dtype=np.int32)
+        out = np.empty((int(counts.sum()), self.ntheta))
+        self._check(self._lib.muse_b200_allgather_scores(self._h, int(first_row), _ip(counts), _dp(out)))
+        return out
+
+    def allgather_rows(self, local, counts):
+        counts = np.ascontiguousarray(counts, dtype=np.int32)
+        local = np.ascontiguousarray(local, dtype=np.float64)
+        ncol = local.shape[1]
+        out = np.empty((int(counts.sum()), ncol))
+        self._check(self._lib.muse_b200_allgather_rows(self._h, _dp(local), int(ncol), _ip(counts), _dp(out)))
+        return out
 
     def fd_jacobian(self, theta0, step, nsims_H: int, atol):
         t0 = self._theta(theta0)

@@ -10,55 +10,9 @@
 #include <string>
 #include <vector>
 
-#include "muse_common.cuh"
+#include "muse_handle.cuh"
 
 using namespace muse;
-
-struct muse_handle {
-    muse_cfg cfg{};
-    int ld = 0;
-    int rows = 0;               // 1 + nsims (unit 0 = data)
-    cudaStream_t stream = nullptr;
-    bool own_stream = false;
-    std::string err;
-    Geometry geo{};
-    bool have_data = false, have_draws = false, have_z0 = false;
-
-    // device arrays
-    double *xi = nullptr, *nu = nullptr;          // (nsims+1) × ld, last row = master draw
-    double *xi_h = nullptr, *nu_h = nullptr;      // nsims_h × ld: draws of the get_H! shard (multi-GPU)
-    bool have_draws_h = false;
-    double *xdat = nullptr, *z0user = nullptr;    // ld
-    double *xslot = nullptr;                             // slots × ld (x of the unit in flight, per group)
-    double *zA = nullptr, *zB = nullptr;                 // rows × ld
-    int* zstate = nullptr;                        // rows
-    double *sbuf = nullptr, *dxh = nullptr, *dgh = nullptr;   // per-slot scratch
-    // outputs (device + pinned host mirror), capacity out_cap items
-    int out_cap = 0;
-    double *g_d = nullptr, *gnorm_d = nullptr, *f_d = nullptr;
-    int *iters_d = nullptr, *fg_d = nullptr, *status_d = nullptr;
-    double *g_h = nullptr, *gnorm_h = nullptr;
-    int *iters_h = nullptr, *fg_h = nullptr, *status_h = nullptr;
-    // finite-difference scratch
-    int h_cap = 0;
-    double *zHA = nullptr, *zHB = nullptr;
-    double *zfidA = nullptr, *zfidB = nullptr;
-    int* zfid_state = nullptr;
-
-    // streaming kernel: per-(unit, segment) partial sums, arrival counters, hand-back list
-    double* gpart = nullptr;
-    int *redo_count = nullptr, *redo_items = nullptr;
-    unsigned long long* redo_total = nullptr;
-
-    long long* dbg = nullptr;   // diagnostics timeline (muse_b200_debug_timeline)
-    int dbg_cap = 0;
-
-    // profiling
-    bool prof = false;
-    struct Rec { cudaEvent_t a, b; int cls; double units, bytes; };
-    std::vector<Rec> recs;
-    muse_profile acc{};
-};
 
 static thread_local std::string g_create_err;
 
@@ -305,6 +259,7 @@ int muse_b200_destroy(muse_handle* h) {
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (auto& r : h->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    muse_comm_release(h);
     cudaFree(h->xi); cudaFree(h->nu); cudaFree(h->xi_h); cudaFree(h->nu_h); cudaFree(h->xdat); cudaFree(h->z0user);
     cudaFree(h->xslot); cudaFree(h->zA); cudaFree(h->zB); cudaFree(h->zstate);
     cudaFree(h->sbuf); cudaFree(h->dxh); cudaFree(h->dgh);
@@ -322,6 +277,7 @@ int muse_b200_destroy(muse_handle* h) {
 
 int muse_b200_set_stream(muse_handle* h, void* s) {
     if (!h) return MUSE_EINVAL;
+    if (s && h->stream == (cudaStream_t)s) return MUSE_OK;
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     if (h->own_stream) { cudaStreamDestroy(h->stream); h->own_stream = false; }
@@ -487,6 +443,13 @@ int muse_b200_map_score(muse_handle* h, const double* theta_sim, const double* t
     const int rc = muse_b200_map_score_async(h, theta_sim, theta_eval, atol, include_data, warm_start, first_sim, count);
     if (rc != MUSE_OK) return rc;
     return muse_b200_fetch(h, count + (include_data ? 1 : 0), g_out, iters_out, fg_out, gnorm_out, status_out);
+}
+
+int muse_b200_device_scores(muse_handle* h, double** g_dev, int32_t* capacity_units) {
+    if (!h || !g_dev) return MUSE_EINVAL;
+    *g_dev = h->g_d;
+    if (capacity_units) *capacity_units = h->out_cap;
+    return MUSE_OK;
 }
 
 int muse_b200_fd_jacobian(muse_handle* h, const double* theta0, const double* step, int32_t nsims_H, double atol,

@@ -1,0 +1,163 @@
+// muse_comm.cu — the one exchange step of the path, natively: an NCCL all-gather of per-sim score rows across
+// the ranks of one node (one process per GPU), straight from the solver's device output buffer, on the
+// solver's stream.
+//
+// What it replaces.  The reference gathers every per-sim result on the master through Distributed.pmap
+// (/root/reference/src/muse.jl:169, 177-183, 508, 529) and reduces there; here each rank keeps its sims' ẑ on its
+// GPU and only the N × nθ score matrix (≤ 64 KB) crosses NVLink, once per pass.  All ranks receive it and run
+// the same deterministic host arithmetic.
+//
+// NCCL is loaded lazily with dlopen("libnccl.so.2") so that single-GPU use of the library has no NCCL
+// dependency; inside a PyTorch process this resolves to the NCCL build torch has already loaded.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "muse_handle.cuh"
+
+namespace {
+
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    std::string err;
+};
+
+NcclApi* nccl_api() {
+    static NcclApi api;
+    if (api.lib || !api.err.empty()) return &api;
+    api.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!api.lib) { api.err = std::string("dlopen(libnccl.so.2): ") + dlerror(); return &api; }
+#define MUSE_SYM(field, name)                                                        \
+    api.field = reinterpret_cast<decltype(api.field)>(dlsym(api.lib, name));         \
+    if (!api.field) { api.err = std::string("dlsym(") + name + ") failed"; return &api; }
+    MUSE_SYM(GetUniqueId, "ncclGetUniqueId")
+    MUSE_SYM(CommInitRank, "ncclCommInitRank")
+    MUSE_SYM(CommDestroy, "ncclCommDestroy")
+    MUSE_SYM(AllGather, "ncclAllGather")
+    MUSE_SYM(GetErrorString, "ncclGetErrorString")
+#undef MUSE_SYM
+    return &api;
+}
+
+}  // namespace
+
+void muse_comm_release(muse_handle* h) {
+    if (h->comm) {
+        NcclApi* a = nccl_api();
+        if (a->CommDestroy) a->CommDestroy((ncclComm_t)h->comm);
+        h->comm = nullptr;
+    }
+    cudaFree(h->comm_send); cudaFree(h->comm_recv); cudaFreeHost(h->comm_host);
+    h->comm_send = h->comm_recv = h->comm_host = nullptr;
+    h->comm_cap = 0;
+}
+
+extern "C" {
+
+int muse_b200_comm_unique_id(uint8_t* out /* 128 bytes */) {
+    if (!out) return MUSE_EINVAL;
+    NcclApi* a = nccl_api();
+    if (!a->err.empty()) return MUSE_EUNSUPPORTED;
+    ncclUniqueId id;
+    if (a->GetUniqueId(&id) != ncclSuccess) return MUSE_ECUDA;
+    static_assert(sizeof(id) == 128, "ncclUniqueId size");
+    std::memcpy(out, &id, sizeof(id));
+    return MUSE_OK;
+}
+
+int muse_b200_comm_init(muse_handle* h, int32_t nranks, int32_t rank, const uint8_t* id_bytes) {
+    if (!h || !id_bytes || nranks < 1 || rank < 0 || rank >= nranks) return MUSE_EINVAL;
+    NcclApi* a = nccl_api();
+    if (!a->err.empty()) { h->err = a->err; return MUSE_EUNSUPPORTED; }
+    if (cudaSetDevice(h->cfg.device) != cudaSuccess) { h->err = "cudaSetDevice"; return MUSE_ECUDA; }
+    muse_comm_release(h);
+    ncclUniqueId id;
+    std::memcpy(&id, id_bytes, sizeof(id));
+    ncclComm_t comm = nullptr;
+    const ncclResult_t r = a->CommInitRank(&comm, nranks, id, rank);
+    if (r != ncclSuccess) { h->err = std::string("ncclCommInitRank: ") + a->GetErrorString(r); return MUSE_ECUDA; }
+    h->comm = comm;
+    h->comm_nranks = nranks;
+    h->comm_rank = rank;
+    return MUSE_OK;
+}
+
+int muse_b200_comm_destroy(muse_handle* h) {
+    if (!h) return MUSE_EINVAL;
+    cudaSetDevice(h->cfg.device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    muse_comm_release(h);
+    return MUSE_OK;
+}
+
+// gather `counts[q]` rows of `ncol` doubles from every rank q; this rank's rows come from device memory (`src_dev`)
+// or from the host (`src_host`)
+static int allgather_impl(muse_handle* h, const double* src_dev, const double* src_host, int ncol, const int32_t* counts,
+                          double* out_host) {
+    if (!h->comm) { h->err = "no communicator (muse_b200_comm_init)"; return MUSE_ESTATE; }
+    NcclApi* a = nccl_api();
+    const int R = h->comm_nranks;
+    int maxc = 1;
+    for (int r = 0; r < R; ++r) {
+        if (counts[r] < 0) return MUSE_EINVAL;
+        if (counts[r] > maxc) maxc = counts[r];
+    }
+    const int mine = counts[h->comm_rank];
+    if (cudaSetDevice(h->cfg.device) != cudaSuccess) { h->err = "cudaSetDevice"; return MUSE_ECUDA; }
+    const size_t need = (size_t)maxc * ncol;               // doubles per rank slot
+    if (need > (size_t)h->comm_cap) {
+        cudaFree(h->comm_send); cudaFree(h->comm_recv); cudaFreeHost(h->comm_host);
+        h->comm_send = h->comm_recv = h->comm_host = nullptr;
+        h->comm_cap = 0;
+        if (cudaMalloc(&h->comm_send, need * sizeof(double)) != cudaSuccess ||
+            cudaMalloc(&h->comm_recv, need * R * sizeof(double)) != cudaSuccess ||
+            cudaMallocHost(&h->comm_host, need * (R + 1) * sizeof(double)) != cudaSuccess) {
+            h->err = "allocation of the exchange buffers failed";
+            return MUSE_ENOMEM;
+        }
+        cudaMemsetAsync(h->comm_send, 0, need * sizeof(double), h->stream);
+        h->comm_cap = (int)need;
+    }
+    const size_t bytes_mine = (size_t)mine * ncol * sizeof(double);
+    if (mine && src_dev) {
+        if (cudaMemcpyAsync(h->comm_send, src_dev, bytes_mine, cudaMemcpyDeviceToDevice, h->stream) != cudaSuccess) { h->err = "cudaMemcpyAsync"; return MUSE_ECUDA; }
+    } else if (mine) {
+        double* stage = h->comm_host + need * R;            // pinned staging slot behind the receive area
+        std::memcpy(stage, src_host, bytes_mine);
+        if (cudaMemcpyAsync(h->comm_send, stage, bytes_mine, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) { h->err = "cudaMemcpyAsync"; return MUSE_ECUDA; }
+    }
+    // every rank computes the same `need` from the same counts, so the slots line up
+    const ncclResult_t r = a->AllGather(h->comm_send, h->comm_recv, need, ncclDouble, (ncclComm_t)h->comm, h->stream);
+    if (r != ncclSuccess) { h->err = std::string("ncclAllGather: ") + a->GetErrorString(r); return MUSE_ECUDA; }
+    h->acc.launches += 1;
+    if (cudaMemcpyAsync(h->comm_host, h->comm_recv, need * R * sizeof(double), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
+        cudaStreamSynchronize(h->stream) != cudaSuccess) { h->err = "exchange copy/sync failed"; return MUSE_ECUDA; }
+    size_t off = 0;
+    for (int q = 0; q < R; ++q) {
+        std::memcpy(out_host + off, h->comm_host + (size_t)q * need, (size_t)counts[q] * ncol * sizeof(double));
+        off += (size_t)counts[q] * ncol;
+    }
+    return MUSE_OK;
+}
+
+int muse_b200_allgather_scores(muse_handle* h, int32_t first_row, const int32_t* counts, double* out_host) {
+    if (!h || !counts || !out_host || first_row < 0) return MUSE_EINVAL;
+    if (h->comm && first_row + counts[h->comm_rank] > h->out_cap) { h->err = "score rows outside the device output buffer"; return MUSE_EINVAL; }
+    return allgather_impl(h, h->g_d + (size_t)first_row * h->cfg.ntheta, nullptr, h->cfg.ntheta, counts, out_host);
+}
+
+int muse_b200_allgather_rows(muse_handle* h, const double* local_host, int32_t ncol, const int32_t* counts, double* out_host) {
+    if (!h || !counts || !out_host || ncol < 1) return MUSE_EINVAL;
+    if (h->comm && counts[h->comm_rank] > 0 && !local_host) return MUSE_EINVAL;
+    return allgather_impl(h, nullptr, local_host, ncol, counts, out_host);
+}
+
+}  // extern "C"

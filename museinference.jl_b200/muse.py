@@ -135,11 +135,17 @@ def muse_(result: MuseResult, prob: AbstractMuseProblem, theta0=None, **kwargs):
 
         # MUSE gradient: the mapped block :169-176 is one backend call on this rank's shard
         warm = (_capi.START_USER if z0 is not None else _capi.START_ZEROS) if first_pass else _capi.START_PREV
-        out = be.map_score(theta, theta, atol, include_data=True, warm_start=warm)
+        if getattr(pool, "uses_device_gather", lambda: False)():
+            # multi-GPU: the scores are all-gathered with NCCL from device memory on the launch stream
+            units = be.map_score_async(theta, theta, atol, include_data=True, warm_start=warm)
+            g_like_sims = pool.allgather_device_scores(be, 1, nsims)               # the one exchange step
+            out = be.fetch(units)
+        else:
+            out = be.map_score(theta, theta, atol, include_data=True, warm_start=warm)
+            g_like_sims = pool.allgather_rows(out["g"][1:], nsims)                 # the one exchange step
         first_pass = False
         _check_status(out, "muse!")
         g_like_dat = out["g"][0].copy()                                            # :177
-        g_like_sims = pool.allgather_rows(out["g"][1:], nsims)                     # the one exchange step
 
         g_like = g_like_dat - np.mean(g_like_sims, axis=0)                         # :183
         g_prior = np.asarray(prob.prior.grad(theta), dtype=np.float64)             # :184
@@ -301,7 +307,10 @@ def get_H_(result: MuseResult, prob: AbstractMuseProblem, theta0=None, **kwargs)
     flat = Hs_local.reshape(hcnt, nt * nt).copy()
     if bad_local.size:
         flat[bad_local] = np.nan
-    allH = pool.allgather_rows(flat, nsims_remaining)
+    if getattr(pool, "uses_device_gather", lambda: False)():
+        allH = pool.allgather_host_rows(be, flat, nsims_remaining)
+    else:
+        allH = pool.allgather_rows(flat, nsims_remaining)
     allH = allH[~np.isnan(allH).any(axis=1)]
     oldH = np.asarray(result.Hs, dtype=np.float64).reshape(-1, nt, nt)
     result.Hs = np.concatenate([oldH, allH.reshape(-1, nt, nt)], axis=0)           # (n_H × nθ × nθ array)

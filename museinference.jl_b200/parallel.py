@@ -43,7 +43,12 @@ class LocalPool:
 
 
 class ShardPool:
-    """``torch.distributed`` process group: one rank per GPU."""
+    """``torch.distributed`` process group: one rank per GPU.
+
+    The exchange step is an all-gather of per-sim score rows.  With the NCCL backend it runs inside the library
+    (csrc/muse_comm.cu): ncclAllGather straight from the device output buffer on the stream the solver kernels were
+    launched on, the process group only distributes the communicator id.  With gloo (CPU tests) the rows go
+    through ``torch.distributed`` on the host."""
 
     def __init__(self, group=None, device: int | None = None):
         import torch.distributed as dist
@@ -56,13 +61,45 @@ class ShardPool:
         self.world = dist.get_world_size(group)
         self.backend = dist.get_backend(group)
         self.device = device if device is not None else 0
+        self._bufs = {}
 
     def shard(self, n):
         offs, cnts = block_partition(n, self.world)
         return offs[self.rank], cnts[self.rank]
 
+    # ------------------------------------------------------------------ staging buffers
+    def _staging(self, maxc: int, ncol: int):
+        import torch
+
+        key = (maxc, ncol)
+        b = self._bufs.get(key)
+        if b is None:
+            cuda = self.backend == "nccl"
+            dev = torch.device("cuda", self.device) if cuda else torch.device("cpu")
+            send_h = torch.zeros((maxc, ncol), dtype=torch.float64)
+            recv_h = torch.zeros((self.world, maxc, ncol), dtype=torch.float64)
+            if cuda:
+                send_h, recv_h = send_h.pin_memory(), recv_h.pin_memory()
+            b = dict(send_h=send_h, recv_h=recv_h,
+                     send_d=torch.zeros((maxc, ncol), dtype=torch.float64, device=dev) if cuda else send_h,
+                     recv_d=torch.zeros((self.world, maxc, ncol), dtype=torch.float64, device=dev) if cuda else recv_h)
+            self._bufs[key] = b
+        return b
+
+    def _finish(self, b, cnts, ncol):
+        import torch
+
+        self._dist.all_gather_into_tensor(b["recv_d"].view(-1), b["send_d"].view(-1), group=self.group)
+        if self.backend == "nccl":
+            b["recv_h"].copy_(b["recv_d"], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        out = b["recv_h"].numpy()
+        parts = [out[r, : cnts[r]] for r in range(self.world)]
+        return np.concatenate(parts, axis=0) if parts else np.zeros((0, ncol))
+
+    # ------------------------------------------------------------------ the exchange step
     def allgather_rows(self, local: np.ndarray, n_total: int) -> np.ndarray:
-        """Concatenate per-rank row blocks (block_partition order) into the global matrix."""
+        """Concatenate per-rank row blocks (block_partition order) into the global matrix (host rows in)."""
         import torch
 
         local = np.ascontiguousarray(local, dtype=np.float64)
@@ -70,17 +107,41 @@ class ShardPool:
         _, cnts = block_partition(n_total, self.world)
         if local.shape[0] != cnts[self.rank]:
             raise ValueError("local block does not match the partition")
-        maxc = max(cnts) if cnts else 0
-        dev = torch.device("cuda", self.device) if self.backend == "nccl" else torch.device("cpu")
-        buf = torch.zeros((maxc, ncol), dtype=torch.float64, device=dev)
-        if local.shape[0]:
-            buf[: local.shape[0]] = torch.from_numpy(local.reshape(local.shape[0], ncol)).to(dev)
-        out = torch.empty((self.world, maxc, ncol), dtype=torch.float64, device=dev)
-        self._dist.all_gather_into_tensor(out.view(-1), buf.view(-1), group=self.group)
-        out = out.cpu().numpy()
-        parts = [out[r, : cnts[r]] for r in range(self.world)]
-        res = np.concatenate(parts, axis=0) if parts else np.zeros((0, ncol))
+        b = self._staging(max(max(cnts), 1), ncol)
+        n = local.shape[0]
+        if n:
+            b["send_h"][:n] = torch.from_numpy(local.reshape(n, ncol))
+        if self.backend == "nccl":
+            b["send_d"].copy_(b["send_h"], non_blocking=True)
+        res = self._finish(b, cnts, ncol)
         return res if local.ndim == 2 else res[:, 0]
+
+    # ------------------------------------------------------------------ native exchange (NCCL inside the library)
+    def uses_device_gather(self) -> bool:
+        return self.backend == "nccl"
+
+    def bind(self, be):
+        """Give the handle a communicator over this group's ranks (once per handle)."""
+        if getattr(be, "comm", None) is None:
+            ids = [be.comm_unique_id() if self.rank == 0 else None]
+            self._dist.broadcast_object_list(ids, src=self._dist.get_global_rank(self.group, 0) if self.group else 0,
+                                             group=self.group)
+            be.comm_init(self.world, self.rank, ids[0])
+
+    def allgather_device_scores(self, be, first_row: int, n_total: int) -> np.ndarray:
+        """All-gather this rank's sim rows [first_row, first_row + count) of the score matrix the last
+        ``map_score_async`` left on the device (NCCL on the launch stream, inside the library); returns the
+        global N × nθ matrix on the host."""
+        _, cnts = block_partition(n_total, self.world)
+        self.bind(be)
+        return be.allgather_scores(first_row, cnts)
+
+    def allgather_host_rows(self, be, local: np.ndarray, n_total: int) -> np.ndarray:
+        _, cnts = block_partition(n_total, self.world)
+        if local.shape[0] != cnts[self.rank]:
+            raise ValueError("local block does not match the partition")
+        self.bind(be)
+        return be.allgather_rows(local, cnts)
 
     def barrier(self):
         self._dist.barrier(group=self.group)

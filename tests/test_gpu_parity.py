@@ -178,3 +178,33 @@ def test_full_muse_matches_oracle(name, d, nsims):
     np.testing.assert_allclose(res.Sigma, ref.Sigma, rtol=10 * RTOL_EST, atol=RTOL_EST * np.abs(ref.Sigma).max())
     np.testing.assert_allclose(np.array(res.gs), np.array(ref.gs), rtol=RTOL_SIM)
     prob.close()
+
+
+def test_nccl_shardpool_device_gather_matches_local_pool():
+    """World-size-1 NCCL group on this GPU: the scores travel device → all-gather → host instead of through
+    map_score's host copy; the solve must not change."""
+    import torch
+    import torch.distributed as dist
+    import museinference_jl_b200 as m
+    name, d, nsims = "funnel", 6000, 40
+    oprob, fam, draws, xd = oracle_problem(name, d, nsims, prior=O.NormalPrior(0, 3))
+    rng = m.BaseDraws(draws.xi, draws.nu, draws.xi_master, draws.nu_master)
+    prob = m.SimpleMuseProblem(xd, name, m.NormalPrior(0, 3))
+    ref = m.muse(prob, theta_start(name), rng=rng, nsims=nsims, get_covariance=True)
+    prob.close()
+    own = not dist.is_initialized()
+    if own:
+        dist.init_process_group("nccl", init_method="tcp://127.0.0.1:29533", rank=0, world_size=1,
+                                device_id=torch.device("cuda", 0))
+    try:
+        pool = m.ShardPool(device=0)
+        assert pool.uses_device_gather()
+        prob = m.SimpleMuseProblem(xd, name, m.NormalPrior(0, 3))
+        res = m.muse(prob, theta_start(name), rng=rng, nsims=nsims, get_covariance=True, pool=pool)
+        np.testing.assert_array_equal(res.theta, ref.theta)
+        np.testing.assert_array_equal(np.array(res.gs), np.array(ref.gs))
+        np.testing.assert_array_equal(res.H, ref.H)
+        prob.close()
+    finally:
+        if own:
+            dist.destroy_process_group()
