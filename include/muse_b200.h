@@ -187,6 +187,55 @@ int  muse_b200_fd_jacobian(muse_handle* h, const double* theta0, const double* s
                            double* Hs_out /* nsims_H × ntheta × ntheta */,
                            int32_t* status_out /* nsims_H × ntheta × 2, may be NULL */);
 
+/* The outer loop of muse! (src/muse.jl:159-236) for the common configuration — constant α, regularize = identity,
+ * H⁻¹_update = :sims, prior flat or independent Normal(mean, sigma) per component — run inside the library so that
+ * no interpreter sits between two passes: per iteration one map_score pass (data + local sims, start zeros / user z₀
+ * on the first, previous ẑ afterwards), the exchange step when a communicator exists (counts = sims per rank), then
+ *     g_like = g_dat − mean(g_sims)                     :183      g_post = g_like + ∇logPrior(θ)           :184-185
+ *     H⁻¹_like = Diagonal(−1 ./ var(g_sims))            :188-189  H⁻¹_post = inv(inv(H⁻¹_like) + ∇²logPrior) :207-208
+ *     θ ← θ − α H⁻¹_post g_post                         :224
+ * and the convergence test sqrt(−Δθ' H⁻¹_post Δθ) < θ_rtol (:163-166) before iteration i > 2.
+ * Histories are row-major with one row per executed iteration; *_hist arrays must hold maxsteps rows.
+ * Returns MUSE_ESTATE with a message if a unit ended with a non-finite objective (src/interface.jl:170). */
+typedef struct muse_iterate_out {
+    int32_t n_iter;          /* iterations executed */
+    double* theta_final;     /* ntheta: θ after the last update (result.θ, :230) */
+    double* theta_hist;      /* maxsteps × ntheta: θ at which iteration i evaluated */
+    double* g_dat_hist;      /* maxsteps × ntheta */
+    double* g_sims_hist;     /* maxsteps × nsims_total × ntheta (all ranks' sims, global order) */
+    double* g_like_hist;     /* maxsteps × ntheta */
+    double* g_prior_hist;    /* maxsteps × ntheta */
+    double* h_inv_like_hist; /* maxsteps × ntheta (diagonal) */
+    double* h_prior_hist;    /* maxsteps × ntheta (diagonal) */
+    double* h_inv_post_hist; /* maxsteps × ntheta (diagonal) */
+    double* seconds_hist;    /* maxsteps: wall time of the iteration (history[i].t, :210) */
+    int32_t* iters_hist;     /* maxsteps × (nsims_local + 1): per-unit L-BFGS iterations (unit 0 = data) */
+    int32_t* fg_hist;        /* maxsteps × (nsims_local + 1) */
+    double* gnorm_hist;      /* maxsteps × (nsims_local + 1) */
+    int32_t* status_hist;    /* maxsteps × (nsims_local + 1) */
+} muse_iterate_out;
+int  muse_b200_muse_iterate(muse_handle* h, const double* theta0, int32_t nsims_total, const int32_t* counts,
+                            int32_t maxsteps, double theta_rtol, double atol, double alpha, int32_t first_start,
+                            const double* prior_mean, const double* prior_sigma /* NULL: flat prior */,
+                            muse_iterate_out* out);
+
+/* The covariance stage muse!(…; get_covariance = true) runs after the loop (src/muse.jl:244-247) when no new sims are
+ * needed for J: J = var | cov(corrected) of the last scores gs (src/muse.jl:499-502, 529); step = 0.1 ./ std(gs)
+ * (:411-413); the finite-difference Jacobians of this rank's H shard (muse_b200_fd_jacobian) and their exchange;
+ * H = mean(Hs) (:446); Σ⁻¹ = H'·inv(J)·H − ∇²logPrior(θ), Σ = inv(Σ⁻¹) (finalize_result!, :535-541).
+ * counts_h = H sims per rank (NULL without a communicator). */
+typedef struct muse_cov_out {
+    double* J;          /* ntheta × ntheta */
+    double* step;       /* ntheta */
+    double* Hs;         /* nsims_h_total × ntheta × ntheta (all ranks, global sim order) */
+    double* H;          /* ntheta × ntheta */
+    double* Sigma_inv;  /* ntheta × ntheta */
+    double* Sigma;      /* ntheta × ntheta */
+} muse_cov_out;
+int  muse_b200_muse_covariance(muse_handle* h, const double* theta, const double* gs /* nsims_total × ntheta */,
+                               int32_t nsims_total, int32_t nsims_h_total, const int32_t* counts_h, double atol,
+                               const double* prior_sigma /* NULL: flat prior */, muse_cov_out* out);
+
 /* MAPs of units [first_unit, first_unit+count) (unit 0 = data) — `save_MAPs`, src/muse.jl:139-143,219 */
 int  muse_b200_get_maps(muse_handle* h, int32_t first_unit, int32_t count, double* z_out /* count × d */);
 

@@ -46,6 +46,21 @@ class muse_profile(C.Structure):
     ]
 
 
+class muse_iterate_out(C.Structure):
+    _fields_ = [
+        ("n_iter", C.c_int32), ("theta_final", c_double_p), ("theta_hist", c_double_p), ("g_dat_hist", c_double_p),
+        ("g_sims_hist", c_double_p), ("g_like_hist", c_double_p), ("g_prior_hist", c_double_p),
+        ("h_inv_like_hist", c_double_p), ("h_prior_hist", c_double_p), ("h_inv_post_hist", c_double_p),
+        ("seconds_hist", c_double_p), ("iters_hist", c_int32_p), ("fg_hist", c_int32_p), ("gnorm_hist", c_double_p),
+        ("status_hist", c_int32_p),
+    ]
+
+
+class muse_cov_out(C.Structure):
+    _fields_ = [("J", c_double_p), ("step", c_double_p), ("Hs", c_double_p), ("H", c_double_p),
+                ("Sigma_inv", c_double_p), ("Sigma", c_double_p)]
+
+
 # name → (restype, argtypes); must list every symbol include/muse_b200.h declares
 SIGNATURES = {
     "muse_b200_abi_version": (C.c_int, []),
@@ -70,6 +85,10 @@ SIGNATURES = {
     "muse_b200_comm_destroy": (C.c_int, [C.c_void_p]),
     "muse_b200_allgather_scores": (C.c_int, [C.c_void_p, C.c_int32, c_int32_p, c_double_p]),
     "muse_b200_allgather_rows": (C.c_int, [C.c_void_p, c_double_p, C.c_int32, c_int32_p, c_double_p]),
+    "muse_b200_muse_iterate": (C.c_int, [C.c_void_p, c_double_p, C.c_int32, c_int32_p, C.c_int32, C.c_double, C.c_double,
+                                         C.c_double, C.c_int32, c_double_p, c_double_p, C.POINTER(muse_iterate_out)]),
+    "muse_b200_muse_covariance": (C.c_int, [C.c_void_p, c_double_p, c_double_p, C.c_int32, C.c_int32, c_int32_p, C.c_double,
+                                            c_double_p, C.POINTER(muse_cov_out)]),
     "muse_b200_fd_jacobian": (C.c_int, [C.c_void_p, c_double_p, c_double_p, C.c_int32, C.c_double, c_double_p, c_int32_p]),
     "muse_b200_get_maps": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, c_double_p]),
     "muse_b200_profile_reset": (C.c_int, [C.c_void_p, C.c_int32]),

@@ -193,6 +193,42 @@ class B200Backend:
         self._check(self._lib.muse_b200_allgather_rows(self._h, _dp(local), int(ncol), _ip(counts), _dp(out)))
         return out
 
+    def muse_iterate(self, theta0, nsims_total: int, counts, maxsteps: int, theta_rtol, atol, alpha, first_start: int,
+                     prior_mean=None, prior_sigma=None):
+        """The outer θ loop of muse! inside the library (include/muse_b200.h: muse_b200_muse_iterate)."""
+        nt, units, N, K = self.ntheta, self.nsims + 1, int(nsims_total), int(maxsteps)
+        t0 = self._theta(theta0)
+        f = lambda *shape: np.zeros(shape)
+        e32 = lambda: np.empty((K, units), dtype=np.int32)          # only rows < n_iter are written and read
+        res = dict(theta_final=f(nt), theta_hist=f(K, nt), g_dat_hist=f(K, nt), g_sims_hist=np.empty((K, N, nt)),
+                   g_like_hist=f(K, nt), g_prior_hist=f(K, nt), h_inv_like_hist=f(K, nt), h_prior_hist=f(K, nt),
+                   h_inv_post_hist=f(K, nt), seconds_hist=f(K), iters_hist=e32(), fg_hist=e32(),
+                   gnorm_hist=np.empty((K, units)), status_hist=e32())
+        o = _capi.muse_iterate_out()
+        for name, arr in res.items():
+            setattr(o, name, _ip(arr) if arr.dtype == np.int32 else _dp(arr))
+        cnt = np.ascontiguousarray(counts, dtype=np.int32) if counts is not None else None
+        pm = self._theta(prior_mean) if prior_mean is not None else None
+        ps = self._theta(prior_sigma) if prior_sigma is not None else None
+        self._check(self._lib.muse_b200_muse_iterate(self._h, _dp(t0), N, _ip(cnt), K, float(theta_rtol), float(atol),
+                                                     float(alpha), int(first_start), _dp(pm), _dp(ps), C.byref(o)))
+        res["n_iter"] = int(o.n_iter)
+        return res
+
+    def muse_covariance(self, theta, gs, nsims_h_total: int, counts_h, atol, prior_sigma=None):
+        """J, FD Jacobians, H and Σ after the loop (include/muse_b200.h: muse_b200_muse_covariance)."""
+        nt = self.ntheta
+        th = self._theta(theta)
+        gs = _f64(gs).reshape(-1, nt)
+        res = dict(J=np.zeros((nt, nt)), step=np.zeros(nt), Hs=np.zeros((int(nsims_h_total), nt, nt)), H=np.zeros((nt, nt)),
+                   Sigma_inv=np.zeros((nt, nt)), Sigma=np.zeros((nt, nt)))
+        o = _capi.muse_cov_out(**{k: _dp(v) for k, v in res.items()})
+        cnt = np.ascontiguousarray(counts_h, dtype=np.int32) if counts_h is not None else None
+        ps = self._theta(prior_sigma) if prior_sigma is not None else None
+        self._check(self._lib.muse_b200_muse_covariance(self._h, _dp(th), _dp(gs), gs.shape[0], int(nsims_h_total), _ip(cnt),
+                                                        float(atol), _dp(ps), C.byref(o)))
+        return res
+
     def fd_jacobian(self, theta0, step, nsims_H: int, atol):
         t0 = self._theta(theta0)
         st = self._theta(step)

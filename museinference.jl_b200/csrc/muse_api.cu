@@ -49,29 +49,36 @@ static int theta_consts(const muse_cfg& c, const double* th_sim, const double* t
     return -1;
 }
 
+// Outputs live in ONE device block with a pinned host mirror of the same layout
+//   [ g: cap×nθ f64 | ‖∇z‖∞: cap f64 | f: cap f64 | iterations: cap i32 | f/g evaluations: cap i32 | status: cap i32 ]
+// so that a fetch is a single device→host copy (five small copies cost ~8 µs each on the copy engine).
 static int ensure_outputs(muse_handle* h, int items) {
     if (items <= h->out_cap) return 0;
-    cudaFree(h->g_d); cudaFree(h->gnorm_d); cudaFree(h->f_d); cudaFree(h->iters_d); cudaFree(h->fg_d); cudaFree(h->status_d);
-    cudaFreeHost(h->g_h); cudaFreeHost(h->gnorm_h); cudaFreeHost(h->iters_h); cudaFreeHost(h->fg_h); cudaFreeHost(h->status_h);
+    cudaFree(h->out_d); cudaFreeHost(h->out_h);
     cudaFree(h->gpart); cudaFree(h->redo_items);
+    h->out_d = h->out_h = nullptr;
     h->gpart = nullptr; h->redo_items = nullptr;
     h->out_cap = 0;
-    const size_t n = (size_t)items;
+    const size_t n = (size_t)items, nt = (size_t)h->cfg.ntheta;
     if (h->geo.stream) {
         CUDA_TRY(h, cudaMalloc(&h->gpart, n * (size_t)h->geo.nseg * 16 * sizeof(double)));
         CUDA_TRY(h, cudaMalloc(&h->redo_items, n * sizeof(int)));
     }
-    CUDA_TRY(h, cudaMalloc(&h->g_d, n * h->cfg.ntheta * sizeof(double)));
-    CUDA_TRY(h, cudaMalloc(&h->gnorm_d, n * sizeof(double)));
-    CUDA_TRY(h, cudaMalloc(&h->f_d, n * sizeof(double)));
-    CUDA_TRY(h, cudaMalloc(&h->iters_d, n * sizeof(int)));
-    CUDA_TRY(h, cudaMalloc(&h->fg_d, n * sizeof(int)));
-    CUDA_TRY(h, cudaMalloc(&h->status_d, n * sizeof(int)));
-    CUDA_TRY(h, cudaMallocHost(&h->g_h, n * h->cfg.ntheta * sizeof(double)));
-    CUDA_TRY(h, cudaMallocHost(&h->gnorm_h, n * sizeof(double)));
-    CUDA_TRY(h, cudaMallocHost(&h->iters_h, n * sizeof(int)));
-    CUDA_TRY(h, cudaMallocHost(&h->fg_h, n * sizeof(int)));
-    CUDA_TRY(h, cudaMallocHost(&h->status_h, n * sizeof(int)));
+    const size_t n_i = (n + 1) & ~(size_t)1;                       // keep every section 8-byte aligned
+    h->out_bytes = n * (nt + 2) * sizeof(double) + 3 * n_i * sizeof(int);
+    CUDA_TRY(h, cudaMalloc(&h->out_d, h->out_bytes));
+    CUDA_TRY(h, cudaMallocHost(&h->out_h, h->out_bytes));
+    auto carve = [&](unsigned char* base, double*& g, double*& gn, double*& f, int*& it, int*& fg, int*& st) {
+        g = reinterpret_cast<double*>(base);
+        gn = g + n * nt;
+        f = gn + n;
+        it = reinterpret_cast<int*>(f + n);
+        fg = it + n_i;
+        st = fg + n_i;
+    };
+    carve(h->out_d, h->g_d, h->gnorm_d, h->f_d, h->iters_d, h->fg_d, h->status_d);
+    double* f_h_unused;
+    carve(h->out_h, h->g_h, h->gnorm_h, f_h_unused, h->iters_h, h->fg_h, h->status_h);
     h->out_cap = items;
     return 0;
 }
@@ -263,8 +270,7 @@ int muse_b200_destroy(muse_handle* h) {
     cudaFree(h->xi); cudaFree(h->nu); cudaFree(h->xi_h); cudaFree(h->nu_h); cudaFree(h->xdat); cudaFree(h->z0user);
     cudaFree(h->xslot); cudaFree(h->zA); cudaFree(h->zB); cudaFree(h->zstate);
     cudaFree(h->sbuf); cudaFree(h->dxh); cudaFree(h->dgh);
-    cudaFree(h->g_d); cudaFree(h->gnorm_d); cudaFree(h->f_d); cudaFree(h->iters_d); cudaFree(h->fg_d); cudaFree(h->status_d);
-    cudaFreeHost(h->g_h); cudaFreeHost(h->gnorm_h); cudaFreeHost(h->iters_h); cudaFreeHost(h->fg_h); cudaFreeHost(h->status_h);
+    cudaFree(h->out_d); cudaFreeHost(h->out_h);
     cudaFree(h->zHA); cudaFree(h->zHB);
     cudaFree(h->dbg);
     cudaFree(h->gpart); cudaFree(h->redo_count); cudaFree(h->redo_items); cudaFree(h->redo_total);
@@ -419,13 +425,7 @@ int muse_b200_fetch(muse_handle* h, int32_t units, double* g_out, int32_t* iters
     if (!h || units < 0 || units > h->out_cap) return MUSE_EINVAL;
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
     const size_t n = (size_t)units;
-    if (n) {
-        if (g_out) CUDA_TRY(h, cudaMemcpyAsync(h->g_h, h->g_d, n * h->cfg.ntheta * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-        if (iters_out) CUDA_TRY(h, cudaMemcpyAsync(h->iters_h, h->iters_d, n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-        if (fg_out) CUDA_TRY(h, cudaMemcpyAsync(h->fg_h, h->fg_d, n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-        if (gnorm_out) CUDA_TRY(h, cudaMemcpyAsync(h->gnorm_h, h->gnorm_d, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-        if (status_out) CUDA_TRY(h, cudaMemcpyAsync(h->status_h, h->status_d, n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    }
+    if (n) CUDA_TRY(h, cudaMemcpyAsync(h->out_h, h->out_d, h->out_bytes, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     if (n) {
         if (g_out && g_out != h->g_h) std::memcpy(g_out, h->g_h, n * h->cfg.ntheta * sizeof(double));

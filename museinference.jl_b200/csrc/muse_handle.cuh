@@ -28,6 +28,8 @@ struct muse_handle {
     double *sbuf = nullptr, *dxh = nullptr, *dgh = nullptr;   // per-slot scratch
     // outputs (device + pinned host mirror), capacity out_cap items
     int out_cap = 0;
+    unsigned char *out_d = nullptr, *out_h = nullptr;   // one block each; the typed pointers below point into them
+    size_t out_bytes = 0;
     double *g_d = nullptr, *gnorm_d = nullptr, *f_d = nullptr;
     int *iters_d = nullptr, *fg_d = nullptr, *status_d = nullptr;
     double *g_h = nullptr, *gnorm_h = nullptr;

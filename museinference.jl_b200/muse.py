@@ -22,8 +22,8 @@ from typing import Optional
 import numpy as np
 
 from . import _capi
-from .parallel import LocalPool
-from .problem import AbstractMuseProblem, BaseDraws, SimpleMuseProblem
+from .parallel import LocalPool, block_partition
+from .problem import AbstractMuseProblem, BaseDraws, FlatPrior, NormalPrior, SimpleMuseProblem
 from ._capi import MuseBackendError
 
 _KW_ALIASES = {
@@ -63,6 +63,16 @@ class MuseResult:
         return "MuseResult(" + ", ".join(f"{t:.4g}" for t in self.theta) + ")"
 
 
+def _prior_mean_sigma(prior, ntheta):
+    """(mean, sigma) arrays of an independent-Normal prior, None for a flat prior, False for anything else."""
+    if type(prior) is FlatPrior:
+        return None
+    if type(prior) is NormalPrior:
+        return (np.broadcast_to(np.asarray(prior.mean, dtype=np.float64), (ntheta,)).copy(),
+                np.broadcast_to(np.asarray(prior.sigma, dtype=np.float64), (ntheta,)).copy())
+    return False
+
+
 def _check_problem(prob):
     if not isinstance(prob, SimpleMuseProblem):
         raise MuseBackendError(-5, f"{type(prob).__name__} is not supported by the B200 backend: only "
@@ -96,7 +106,10 @@ def muse_(result: MuseResult, prob: AbstractMuseProblem, theta0=None, **kwargs):
     alpha = kw.pop("alpha", 0.7)
     kw.pop("progress", False)
     pool = kw.pop("pool", None) or LocalPool()
-    regularize = kw.pop("regularize", None) or (lambda t: t)
+    regularize = kw.pop("regularize", None)
+    regularize_is_identity = regularize is None
+    regularize = regularize or (lambda t: t)
+    fused_driver = kw.pop("fused_driver", True)
     H_inv_like = kw.pop("H_inv_like", None)
     H_inv_update = kw.pop("H_inv_update", "sims")
     broyden_memory = kw.pop("broyden_memory", math.inf)
@@ -122,6 +135,51 @@ def muse_(result: MuseResult, prob: AbstractMuseProblem, theta0=None, **kwargs):
     first_pass = True                                                              # :151 ẑs = zeros | z₀
     if z0 is not None:
         be.set_z0(z0)
+
+    # Common configuration: the whole loop below runs inside the library (csrc/muse_driver.cu), same arithmetic,
+    # no interpreter between two passes.  Anything else (callable α, regularize, Broyden, save_MAPs, resume,
+    # checkpoints, a custom prior, a test double as backend) takes the line-by-line loop.
+    prior_ms = _prior_mean_sigma(prob.prior, prob.ntheta)
+    fused = (fused_driver and not history and not callable(alpha) and regularize_is_identity and H_inv_like is None
+             and H_inv_update == "sims" and not save_MAPs and checkpoint_filename is None and prior_ms is not False
+             and hasattr(be, "muse_iterate") and maxsteps >= 1 and nsims >= 2)
+    if fused:
+        counts = None
+        if pool.world > 1:
+            pool.bind(be)
+            counts = block_partition(nsims, pool.world)[1]
+        r = be.muse_iterate(theta, nsims, counts, maxsteps, theta_rtol, atol, alpha,
+                            _capi.START_USER if z0 is not None else _capi.START_ZEROS,
+                            *(prior_ms if prior_ms else (None, None)))
+        th_unreg_prev = theta.copy()
+        for k in range(r["n_iter"]):
+            hl, hp, hq = r["h_inv_like_hist"][k], r["h_prior_hist"][k], r["h_inv_post_hist"][k]
+            history.append(dict(
+                theta=r["theta_hist"][k].copy(), theta_unreg=th_unreg_prev,
+                g_like_sims=r["g_sims_hist"][k].copy(), g_like_dat=r["g_dat_hist"][k].copy(), g_like=r["g_like_hist"][k].copy(),
+                g_prior=r["g_prior_hist"][k].copy(), g_post=r["g_like_hist"][k] + r["g_prior_hist"][k],
+                H_inv_post=np.diag(hq), H_prior=np.diag(hp), H_inv_like=np.diag(hl), H_inv_like_sims=np.diag(hl),
+                z_history_dat=dict(iters=int(r["iters_hist"][k, 0]), fg_evals=int(r["fg_hist"][k, 0]),
+                                   gnorm=float(r["gnorm_hist"][k, 0]), status=int(r["status_hist"][k, 0])),
+                z_history_sims=dict(iters=r["iters_hist"][k, 1:].copy(), fg_evals=r["fg_hist"][k, 1:].copy(),
+                                    gnorm=r["gnorm_hist"][k, 1:].copy(), status=r["status_hist"][k, 1:].copy()),
+                t=float(r["seconds_hist"][k]), z_dat=None, z_sims=None))
+            th_unreg_prev = r["theta_hist"][k + 1].copy() if k + 1 < r["n_iter"] else r["theta_final"].copy()
+            result.time += float(r["seconds_hist"][k])
+        if r["n_iter"]:
+            result.theta = r["theta_final"].copy()                                 # :230
+            result.gs = r["g_sims_hist"][r["n_iter"] - 1].copy()                   # :231
+        maxsteps = 0                                                               # the loop below has nothing left to do
+        if get_covariance and r["n_iter"]:                                         # :244-247, same stage in the library
+            tc = time.perf_counter()
+            counts_h = block_partition(nh_total, pool.world)[1] if pool.world > 1 else None
+            c = be.muse_covariance(result.theta, result.gs, nh_total, counts_h, atol, prior_ms[1] if prior_ms else None)
+            result.J, result.H, result.Hs = c["J"], c["H"], c["Hs"]
+            result.Sigma_inv, result.Sigma = c["Sigma_inv"], c["Sigma"]
+            result.dist = (result.theta.copy(), result.Sigma.copy())               # :542-546
+            result.metadata["fd_step"] = c["step"]
+            result.time += time.perf_counter() - tc
+            return result
 
     for i in range(len(history) + 1, maxsteps + 1):                                # :159
         t0 = time.perf_counter()

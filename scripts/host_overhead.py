@@ -15,7 +15,7 @@ def wrap(name):
     def g(*a, **k):
         t = time.perf_counter(); r = f(*a, **k); acc[name] = acc.get(name, 0.0) + time.perf_counter() - t; return r
     setattr(be, name, g)
-for nm in ("map_score", "fd_jacobian"):
+for nm in ("map_score", "fd_jacobian", "muse_iterate", "muse_covariance"):
     wrap(nm)
 K = 50
 be.profile_reset(True)
@@ -24,8 +24,8 @@ for _ in range(K):
     m.muse(prob, [1.0], rng=5, nsims=n, get_covariance=True)
 wall = (time.perf_counter() - t0) / K
 p = be.profile()
-print("per solve: wall %.3f ms | in C calls %.3f ms (map_score %.3f, fd_jacobian %.3f) | solver chains (events) %.3f ms | python outside C %.3f ms"
-      % (wall * 1e3, sum(acc.values()) / K * 1e3, acc["map_score"] / K * 1e3, acc["fd_jacobian"] / K * 1e3, p["solve_ms"] / K, (wall - sum(acc.values()) / K) * 1e3))
+print("per solve: wall %.3f ms | in C calls %.3f ms %s | solver chains (events) %.3f ms | python outside C %.3f ms"
+      % (wall * 1e3, sum(acc.values()) / K * 1e3, {k: round(v / K * 1e3, 3) for k, v in acc.items()}, p["solve_ms"] / K, (wall - sum(acc.values()) / K) * 1e3))
 pr = cProfile.Profile(); pr.enable()
 for _ in range(20):
     m.muse(prob, [1.0], rng=5, nsims=n, get_covariance=True)

@@ -208,3 +208,32 @@ def test_nccl_shardpool_device_gather_matches_local_pool():
     finally:
         if own:
             dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("name,d,nsims,prior", [("funnel", 512, 100, True), ("hiergauss", 5000, 50, False), ("hiergauss", 300, 30, True)])
+def test_in_library_outer_loop_matches_line_by_line_driver(name, d, nsims, prior):
+    """muse_b200_muse_iterate (csrc/muse_driver.cu) against the Python mirror of src/muse.jl:159-236."""
+    import museinference_jl_b200 as m
+    oprob, fam, draws, xd = oracle_problem(name, d, nsims)
+    rng = m.BaseDraws(draws.xi, draws.nu, draws.xi_master, draws.nu_master)
+    pr = (lambda: m.NormalPrior([0.0, 0.1][:fam.ntheta], [3.0, 2.0][:fam.ntheta])) if prior else (lambda: None)
+    res = {}
+    for fused in (True, False):
+        prob = m.SimpleMuseProblem(xd, name, pr())
+        res[fused] = m.muse(prob, theta_start(name), rng=rng, nsims=nsims, get_covariance=True, fused_driver=fused,
+                            theta_rtol=1e-3, maxsteps=6)
+        prob.close()
+    a, b = res[True], res[False]
+    assert len(a.history) == len(b.history) >= 3
+    np.testing.assert_allclose(a.theta, b.theta, rtol=1e-12)
+    np.testing.assert_allclose(a.J, b.J, rtol=1e-12)
+    np.testing.assert_allclose(a.H, b.H, rtol=1e-10)
+    np.testing.assert_allclose(np.array(a.gs), np.array(b.gs), rtol=1e-10)
+    np.testing.assert_allclose(a.Sigma, b.Sigma, rtol=1e-9)
+    np.testing.assert_allclose(np.array(a.Hs), np.array(b.Hs), rtol=1e-8, atol=1e-9)
+    for ha, hb in zip(a.history, b.history):
+        for key in ("theta", "theta_unreg", "g_like_sims", "g_like_dat", "g_like", "g_prior", "g_post", "H_inv_post",
+                    "H_prior", "H_inv_like", "H_inv_like_sims"):
+            np.testing.assert_allclose(ha[key], hb[key], rtol=1e-11, atol=1e-300, err_msg=key)
+        assert {k: v for k, v in ha["z_history_dat"].items() if k != "gnorm"} == {k: v for k, v in hb["z_history_dat"].items() if k != "gnorm"}
+        np.testing.assert_array_equal(ha["z_history_sims"]["fg_evals"], hb["z_history_sims"]["fg_evals"])
