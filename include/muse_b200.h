@@ -240,6 +240,10 @@ int  muse_b200_muse_covariance(muse_handle* h, const double* theta, const double
 int  muse_b200_get_maps(muse_handle* h, int32_t first_unit, int32_t count, double* z_out /* count × d */);
 
 /* diagnostics ---------------------------------------------------------------------------- */
+/* The FP64 tensor-core GEMM of the correlated-Gaussian family (csrc/muse_dgemm.cu), C = A·B row-major with
+ * M % 128 == N % 128 == K % 16 == 0: on host operands (tests) and timed on device-resident operands (bench). */
+int  muse_b200_dgemm_host(const double* A, const double* B, double* C, int32_t M, int32_t N, int32_t K);
+int  muse_b200_dgemm_time(int32_t M, int32_t N, int32_t K, int32_t reps, double* ms_per_gemm);
 int  muse_b200_profile_reset(muse_handle* h, int32_t enable);
 int  muse_b200_profile_get(muse_handle* h, muse_profile* out);
 /* diagnostics: per-unit timeline of the solver's controller (16 SM-clock stamps per unit of the last

@@ -1,0 +1,181 @@
+// muse_dgemm.cu — FP64 GEMM on the tensor cores of sm_100a for the dense correlated-Gaussian family (F3).
+//
+// What it computes.  The only dense contraction on the path: for a batch of latent vectors stored as rows,
+//     Q = S · P            (rows × d) · (d × d),   P = Σ₀⁻¹ symmetric,
+// i.e. the P·s products inside ∇z logLike = (x − z) − e^{−θ} P z of F3 (in the reference
+// this is whatever AD makes of the user's `logLike`, /root/reference/src/simple.jl:85), and W = ξ · Lᵀ for
+// sample_x_z (z = e^{θ/2} L ξ, src/simple.jl:61-65 pattern).
+//
+// How.  tcgen05/TMEM has no f64 kind, so the FP64 tensor path on Blackwell is the warp-level
+// `mma.sync.aligned.m8n8k4.row.col.f64` (SASS: DMMA.8x8x4).  CTA tile 128 × 128 × 16, 8 warps as 2 (M) × 4 (N),
+// warp tile 64 × 32 = 8 × 4 MMA tiles (64 accumulator doubles per lane); operands staged in shared memory by a
+// 4-stage `cp.async` (LDGSTS) pipeline; rows padded (A: 20, B: 132 doubles) so that every fragment load is
+// bank-conflict free per half-warp.  All extents are multiples of the tile (the callers allocate padded, zero
+// filled operands), so there is no edge handling.  *Bound: FP64 tensor pipe* — 2·M·N·K flop against
+// 24·(M·K + K·N + M·N)… bytes, ≈ 400 flop/B at the C5 shape.
+#include "muse_common.cuh"
+
+namespace muse {
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 16, STAGES = 4;
+constexpr int APAD = BK + 4;      // 20 doubles per A row in shared memory
+constexpr int BPAD = BN + 4;      // 132 doubles per B row
+constexpr int A_STAGE = BM * APAD, B_STAGE = BK * BPAD;
+constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_SMEM = STAGES * (A_STAGE + B_STAGE) * (int)sizeof(double);
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                 : "+d"(c[0]), "+d"(c[1])
+                 : "d"(a), "d"(b));
+}
+
+// C[M×N] = A[M×K] · B[K×N]; row-major, leading dimensions lda/ldb/ldc; M % 128 == N % 128 == K % 16 == 0.
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+dgemm_dmma_kernel(const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ C, int K, int lda,
+                  int ldb, int ldc) {
+    extern __shared__ __align__(16) double smem[];
+    double* As = smem;
+    double* Bs = smem + STAGES * A_STAGE;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int wm = warp >> 2, wn = warp & 3;           // 2 × 4 warps
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const double* Ag = A + (size_t)m0 * lda;
+    const double* Bg = B + n0;
+
+    auto load_stage = [&](int stage, int kt) {
+        double* as = As + stage * A_STAGE;
+        double* bs = Bs + stage * B_STAGE;
+        const int k0 = kt * BK;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {                  // A: 128 rows × 8 chunks of 2 doubles
+            const int c = tid + i * GEMM_THREADS;
+            const int r = c >> 3, kc = (c & 7) * 2;
+            cp_async16(as + r * APAD + kc, Ag + (size_t)r * lda + k0 + kc);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {                  // B: 16 rows × 64 chunks
+            const int c = tid + i * GEMM_THREADS;
+            const int r = c >> 6, nc = (c & 63) * 2;
+            cp_async16(bs + r * BPAD + nc, Bg + (size_t)(k0 + r) * ldb + nc);
+        }
+    };
+
+    double acc[8][4][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    const int nk = K / BK;
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) {
+        if (s < nk) load_stage(s, s);
+        cp_async_commit();
+    }
+    const int ar = wm * 64 + (lane >> 2), ak = lane & 3;      // A fragment: row lane/4, k lane%4
+    const int bk = lane & 3, bn = wn * 32 + (lane >> 2);      // B fragment: k lane%4, col lane/4
+    for (int kt = 0; kt < nk; ++kt) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        const int nxt = kt + STAGES - 1;
+        if (nxt < nk) load_stage(nxt % STAGES, nxt);
+        cp_async_commit();
+        const double* as = As + (kt % STAGES) * A_STAGE;
+        const double* bs = Bs + (kt % STAGES) * B_STAGE;
+#pragma unroll
+        for (int k4 = 0; k4 < BK / 4; ++k4) {
+            double a[8], b[4];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = as[(ar + i * 8) * APAD + k4 * 4 + ak];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = bs[(k4 * 4 + bk) * BPAD + bn + j * 8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma(acc[i][j], a[i], b[j]);
+        }
+    }
+    cp_async_wait<0>();
+    // epilogue: lane holds C[row lane/4][cols 2·(lane%4), +1] of every 8 × 8 tile
+    const int cr = m0 + wm * 64 + (lane >> 2), cc = n0 + wn * 32 + 2 * (lane & 3);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<double2*>(C + (size_t)(cr + i * 8) * ldc + cc + j * 8) = make_double2(acc[i][j][0], acc[i][j][1]);
+}
+
+}  // namespace
+
+cudaError_t launch_dgemm(const double* A, const double* B, double* C, int M, int N, int K, int lda, int ldb, int ldc,
+                         cudaStream_t st) {
+    if (M % BM || N % BN || K % BK) return cudaErrorInvalidValue;
+    static bool prepared = false;
+    if (!prepared) {
+        cudaError_t e = cudaFuncSetAttribute(dgemm_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
+        if (e != cudaSuccess) return e;
+        prepared = true;
+    }
+    dim3 grid(N / BN, M / BM);
+    dgemm_dmma_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(A, B, C, K, lda, ldb, ldc);
+    return cudaGetLastError();
+}
+
+}  // namespace muse
+
+// ---- diagnostics entry points (tests, bench): the GEMM on host operands, and timed on device operands -----------
+extern "C" int muse_b200_dgemm_host(const double* A, const double* B, double* C, int32_t M, int32_t N, int32_t K) {
+    if (!A || !B || !C) return MUSE_EINVAL;
+    double *dA = nullptr, *dB = nullptr, *dC = nullptr;
+    const size_t sa = (size_t)M * K * 8, sb = (size_t)K * N * 8, sc = (size_t)M * N * 8;
+    int rc = MUSE_OK;
+    if (cudaMalloc(&dA, sa) != cudaSuccess || cudaMalloc(&dB, sb) != cudaSuccess || cudaMalloc(&dC, sc) != cudaSuccess) rc = MUSE_ENOMEM;
+    if (rc == MUSE_OK && (cudaMemcpy(dA, A, sa, cudaMemcpyHostToDevice) != cudaSuccess ||
+                          cudaMemcpy(dB, B, sb, cudaMemcpyHostToDevice) != cudaSuccess)) rc = MUSE_ECUDA;
+    if (rc == MUSE_OK && muse::launch_dgemm(dA, dB, dC, M, N, K, K, N, N, nullptr) != cudaSuccess) rc = MUSE_EINVAL;
+    if (rc == MUSE_OK && cudaMemcpy(C, dC, sc, cudaMemcpyDeviceToHost) != cudaSuccess) rc = MUSE_ECUDA;
+    cudaFree(dA); cudaFree(dB); cudaFree(dC);
+    cudaGetLastError();
+    return rc;
+}
+
+extern "C" int muse_b200_dgemm_time(int32_t M, int32_t N, int32_t K, int32_t reps, double* ms_per_gemm) {
+    if (!ms_per_gemm || reps < 1) return MUSE_EINVAL;
+    double *dA = nullptr, *dB = nullptr, *dC = nullptr;
+    const size_t sa = (size_t)M * K * 8, sb = (size_t)K * N * 8, sc = (size_t)M * N * 8;
+    int rc = MUSE_OK;
+    if (cudaMalloc(&dA, sa) != cudaSuccess || cudaMalloc(&dB, sb) != cudaSuccess || cudaMalloc(&dC, sc) != cudaSuccess) rc = MUSE_ENOMEM;
+    if (rc == MUSE_OK) {
+        cudaMemset(dA, 0x3f, sa);      // 0x3f3f… ≈ 4.7e-4: non-trivial operands
+        cudaMemset(dB, 0x3f, sb);
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        for (int i = 0; i < 2 && rc == MUSE_OK; ++i)
+            if (muse::launch_dgemm(dA, dB, dC, M, N, K, K, N, N, nullptr) != cudaSuccess) rc = MUSE_EINVAL;
+        cudaEventRecord(e0);
+        for (int i = 0; i < reps && rc == MUSE_OK; ++i)
+            if (muse::launch_dgemm(dA, dB, dC, M, N, K, K, N, N, nullptr) != cudaSuccess) rc = MUSE_EINVAL;
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) rc = MUSE_ECUDA;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        *ms_per_gemm = ms / reps;
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+    }
+    cudaFree(dA); cudaFree(dB); cudaFree(dC);
+    cudaGetLastError();
+    return rc;
+}

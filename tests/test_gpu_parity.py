@@ -237,3 +237,19 @@ def test_in_library_outer_loop_matches_line_by_line_driver(name, d, nsims, prior
             np.testing.assert_allclose(ha[key], hb[key], rtol=1e-11, atol=1e-300, err_msg=key)
         assert {k: v for k, v in ha["z_history_dat"].items() if k != "gnorm"} == {k: v for k, v in hb["z_history_dat"].items() if k != "gnorm"}
         np.testing.assert_array_equal(ha["z_history_sims"]["fg_evals"], hb["z_history_sims"]["fg_evals"])
+
+
+def test_dgemm_dmma_matches_numpy():
+    """The FP64 tensor-core GEMM of F3 (csrc/muse_dgemm.cu) against NumPy, FP64: rtol 1e-13 on a K = 512 contraction."""
+    import ctypes as C
+    import museinference_jl_b200 as m
+    lib = m.load_library()
+    rng = np.random.default_rng(0)
+    M, N, K = 256, 384, 512
+    A, B = rng.standard_normal((M, K)), rng.standard_normal((K, N))
+    Cm = np.empty((M, N))
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    assert lib.muse_b200_dgemm_host(dp(A), dp(B), dp(Cm), M, N, K) == 0
+    ref = A @ B
+    np.testing.assert_allclose(Cm, ref, rtol=0, atol=1e-13 * np.abs(A).max() * np.abs(B).max() * K)
+    assert lib.muse_b200_dgemm_host(dp(A), dp(B), dp(Cm), 100, N, K) != 0      # extents must be tile multiples
