@@ -103,6 +103,7 @@ typedef struct muse_profile {
     int64_t other_launches;
     double  other_ms;
     int64_t redo_units;      /* units the streaming kernel handed back to the generic kernel (since handle creation) */
+    double  solve_flops;     /* FP64 tensor-core flops of the solver launches (corrgauss: 2·rows·d² per product) */
 } muse_profile;
 
 int  muse_b200_abi_version(void);

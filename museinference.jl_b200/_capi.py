@@ -42,7 +42,7 @@ class muse_profile(C.Structure):
         ("launches", C.c_int64), ("solve_launches", C.c_int64), ("solve_ms", C.c_double),
         ("solve_units", C.c_double), ("solve_bytes", C.c_double), ("draw_launches", C.c_int64),
         ("draw_ms", C.c_double), ("other_launches", C.c_int64), ("other_ms", C.c_double),
-        ("redo_units", C.c_int64),
+        ("redo_units", C.c_int64), ("solve_flops", C.c_double),
     ]
 
 

@@ -157,11 +157,7 @@ int muse_b200_create(const muse_cfg* cfg, muse_handle** out) {
     if (!cfg || !out) { g_create_err = "null argument"; return MUSE_EINVAL; }
     *out = nullptr;
     if (cfg->abi_version != MUSE_B200_ABI_VERSION) { g_create_err = "ABI version mismatch"; return MUSE_EINVAL; }
-    if (cfg->family == MUSE_FAMILY_CORRGAUSS) {
-        g_create_err = "corrgauss (F3) is not built yet in this round: dense Σ₀⁻¹z DGEMM path pending";
-        return MUSE_EUNSUPPORTED;
-    }
-    if (cfg->family != MUSE_FAMILY_FUNNEL && cfg->family != MUSE_FAMILY_HIERGAUSS) {
+    if (cfg->family != MUSE_FAMILY_FUNNEL && cfg->family != MUSE_FAMILY_HIERGAUSS && cfg->family != MUSE_FAMILY_CORRGAUSS) {
         g_create_err = "model outside the registered families (funnel, hiergauss, corrgauss); "
                        "Turing/Soss-defined models are not supported by the B200 backend";
         return MUSE_EUNSUPPORTED;
@@ -211,6 +207,17 @@ int muse_b200_create(const muse_cfg* cfg, muse_handle** out) {
     } else {
         CREATE_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         h->own_stream = true;
+    }
+    if (cfg->family == MUSE_FAMILY_CORRGAUSS) {
+        // dense correlated Gaussian: its own state (muse_corr.cu); the isotropic kernels are not involved
+        CREATE_TRY(cudaMalloc(&h->redo_total, sizeof(unsigned long long)));
+        CREATE_TRY(cudaMemsetAsync(h->redo_total, 0, sizeof(unsigned long long), h->stream));
+        const int rc = muse_corr_create(h);
+        if (rc != MUSE_OK) return fail(rc);
+        if (ensure_outputs(h, h->rows) != 0) return fail(MUSE_ECUDA);
+        CREATE_TRY(cudaStreamSynchronize(h->stream));
+        *out = h;
+        return MUSE_OK;
     }
     {
         // kernel choice: the generic solver's group shape follows d (one warp per unit for
@@ -267,6 +274,7 @@ int muse_b200_destroy(muse_handle* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (auto& r : h->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     muse_comm_release(h);
+    muse_corr_destroy(h);
     cudaFree(h->xi); cudaFree(h->nu); cudaFree(h->xi_h); cudaFree(h->nu_h); cudaFree(h->xdat); cudaFree(h->z0user);
     cudaFree(h->xslot); cudaFree(h->zA); cudaFree(h->zB); cudaFree(h->zstate);
     cudaFree(h->sbuf); cudaFree(h->dxh); cudaFree(h->dgh);
@@ -299,6 +307,11 @@ int muse_b200_set_stream(muse_handle* h, void* s) {
 int muse_b200_set_data(muse_handle* h, const double* x_dat) {
     if (!h || !x_dat) return MUSE_EINVAL;
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    if (h->corr) {
+        const int rc = muse_corr_set_data(h, x_dat);
+        if (rc == MUSE_OK) h->have_data = true;
+        return rc;
+    }
     CUDA_TRY(h, cudaMemcpyAsync(h->xdat, x_dat, (size_t)h->cfg.d * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     h->have_data = true;
@@ -308,6 +321,11 @@ int muse_b200_set_data(muse_handle* h, const double* x_dat) {
 int muse_b200_set_z0(muse_handle* h, const double* z0) {
     if (!h || !z0) return MUSE_EINVAL;
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    if (h->corr) {
+        const int rc = muse_corr_set_z0(h, z0);
+        if (rc == MUSE_OK) h->have_z0 = true;
+        return rc;
+    }
     CUDA_TRY(h, cudaMemcpyAsync(h->z0user, z0, (size_t)h->cfg.d * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     h->have_z0 = true;
@@ -317,6 +335,11 @@ int muse_b200_set_z0(muse_handle* h, const double* z0) {
 int muse_b200_set_draws(muse_handle* h, const double* xi, const double* nu, const double* xi_m, const double* nu_m) {
     if (!h || !xi_m || !nu_m || (h->cfg.nsims > 0 && (!xi || !nu))) return MUSE_EINVAL;
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    if (h->corr) {
+        const int rc = muse_corr_set_draws(h, xi, nu, xi_m, nu_m, false);
+        if (rc == MUSE_OK) h->have_draws = true;
+        return rc;
+    }
     const size_t w = (size_t)h->cfg.d * sizeof(double), pitch = (size_t)h->ld * sizeof(double);
     const size_t n = (size_t)h->cfg.nsims;
     if (n) {
@@ -333,6 +356,11 @@ int muse_b200_set_draws(muse_handle* h, const double* xi, const double* nu, cons
 int muse_b200_seed_draws(muse_handle* h, uint64_t seed) {
     if (!h) return MUSE_EINVAL;
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    if (h->corr) {
+        const int rc = muse_corr_seed_draws(h, seed);
+        if (rc == MUSE_OK) { h->have_draws = true; h->have_draws_h = h->cfg.nsims_h > 0; }
+        return rc;
+    }
     muse_handle::Rec r{};
     if (h->prof) {
         CUDA_TRY(h, cudaEventCreate(&r.a));
@@ -364,6 +392,11 @@ int muse_b200_set_draws_h(muse_handle* h, const double* xi_h, const double* nu_h
     if (!h || !xi_h || !nu_h) return MUSE_EINVAL;
     if (h->cfg.nsims_h <= 0) MUSE_FAIL(h, MUSE_ESTATE, "handle was created without a separate H shard (nsims_h = 0)");
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    if (h->corr) {
+        const int rc = muse_corr_set_draws(h, xi_h, nu_h, nullptr, nullptr, true);
+        if (rc == MUSE_OK) h->have_draws_h = true;
+        return rc;
+    }
     const size_t w = (size_t)h->cfg.d * sizeof(double), pitch = (size_t)h->ld * sizeof(double);
     CUDA_TRY(h, cudaMemcpy2DAsync(h->xi_h, pitch, xi_h, w, w, (size_t)h->cfg.nsims_h, cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, cudaMemcpy2DAsync(h->nu_h, pitch, nu_h, w, w, (size_t)h->cfg.nsims_h, cudaMemcpyHostToDevice, h->stream));
@@ -375,6 +408,7 @@ int muse_b200_set_draws_h(muse_handle* h, const double* xi_h, const double* nu_h
 int muse_b200_get_draws(muse_handle* h, int32_t first, int32_t count, double* xi_out, double* nu_out) {
     if (!h || first < 0 || count < 0 || first + count > h->cfg.nsims + 1) return MUSE_EINVAL;
     if (!h->have_draws) MUSE_FAIL(h, MUSE_ESTATE, "no draws installed (set_draws / seed_draws)");
+    if (h->corr) MUSE_FAIL(h, MUSE_EUNSUPPORTED, "corrgauss keeps L·ξ, not ξ: get_draws is not available");
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
     const size_t w = (size_t)h->cfg.d * sizeof(double), pitch = (size_t)h->ld * sizeof(double);
     if (count && xi_out)
@@ -396,6 +430,7 @@ int muse_b200_map_score_async(muse_handle* h, const double* theta_sim, const dou
     const int items = count + (include_data ? 1 : 0);
     if (items == 0) return MUSE_OK;
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    if (h->corr) return muse_corr_map_score(h, theta_sim, theta_eval, atol, include_data, warm_start, first_sim, count);
     SolveLaunch L;
     fill_common(h, L);
     L.nitems = items;
@@ -452,6 +487,26 @@ int muse_b200_device_scores(muse_handle* h, double** g_dev, int32_t* capacity_un
     return MUSE_OK;
 }
 
+// fetch the ± scores and form central_fdm(3,1): sum(fs .* [-1/2, 0, 1/2]) / step   — src/util.jl:13-19
+static int fd_combine(muse_handle* h, const double* step, int nsims_H, double* Hs_out, int32_t* status_out) {
+    const int nt = h->cfg.ntheta, items = nsims_H * nt * 2;
+    int rc = muse_b200_fetch(h, items, h->g_h, nullptr, nullptr, nullptr, status_out ? h->status_h : nullptr);
+    if (rc != 0) return rc;
+    if (status_out) std::memcpy(status_out, h->status_h, (size_t)items * sizeof(int));
+    for (int k = 0; k < nsims_H; ++k)
+        for (int n = 0; n < nt; ++n) {
+            const double* gm = h->g_h + ((size_t)(k * nt + n) * 2 + 0) * nt;
+            const double* gp = h->g_h + ((size_t)(k * nt + n) * 2 + 1) * nt;
+            for (int i = 0; i < nt; ++i) {
+                double acc = gm[i] * -0.5;
+                acc = acc + 0.0;
+                acc = acc + gp[i] * 0.5;
+                Hs_out[((size_t)k * nt + i) * nt + n] = acc / step[n];
+            }
+        }
+    return MUSE_OK;
+}
+
 int muse_b200_fd_jacobian(muse_handle* h, const double* theta0, const double* step, int32_t nsims_H, double atol,
                           double* Hs_out, int32_t* status_out) {
     if (!h || !theta0 || !step || !Hs_out) return MUSE_EINVAL;
@@ -465,6 +520,12 @@ int muse_b200_fd_jacobian(muse_handle* h, const double* theta0, const double* st
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
     const int items = nsims_H * nt * 2;
     const size_t ld = (size_t)h->ld, B = sizeof(double);
+    if (h->corr) {
+        if (ensure_outputs(h, items) != 0) return MUSE_ECUDA;
+        const int rc = muse_corr_fd_launch(h, theta0, step, nsims_H, atol);
+        if (rc != MUSE_OK) return rc;
+        return fd_combine(h, step, nsims_H, Hs_out, status_out);
+    }
     if (items > h->h_cap) {
         cudaFree(h->zHA); cudaFree(h->zHB);
         h->zHA = h->zHB = nullptr;
@@ -519,27 +580,13 @@ int muse_b200_fd_jacobian(muse_handle* h, const double* theta0, const double* st
     // algorithmic bytes: read ξ, ν per virtual sim; the shared start ẑ_fid is read once (L2)
     rc = launch_solver(h, L, items * 2 * d8 + d8);
     if (rc != 0) return rc;
-    rc = muse_b200_fetch(h, items, h->g_h, nullptr, nullptr, nullptr, status_out ? h->status_h : nullptr);
-    if (rc != 0) return rc;
-    if (status_out) std::memcpy(status_out, h->status_h, (size_t)items * sizeof(int));
-    // (3) central_fdm(3,1): sum(fs .* [-1/2, 0, 1/2]) / step   — src/util.jl:13-19
-    for (int k = 0; k < nsims_H; ++k)
-        for (int n = 0; n < nt; ++n) {
-            const double* gm = h->g_h + ((size_t)(k * nt + n) * 2 + 0) * nt;
-            const double* gp = h->g_h + ((size_t)(k * nt + n) * 2 + 1) * nt;
-            for (int i = 0; i < nt; ++i) {
-                double acc = gm[i] * -0.5;
-                acc = acc + 0.0;
-                acc = acc + gp[i] * 0.5;
-                Hs_out[((size_t)k * nt + i) * nt + n] = acc / step[n];
-            }
-        }
-    return MUSE_OK;
+    return fd_combine(h, step, nsims_H, Hs_out, status_out);
 }
 
 int muse_b200_get_maps(muse_handle* h, int32_t first_unit, int32_t count, double* z_out) {
     if (!h || !z_out || first_unit < 0 || count < 0 || first_unit + count > h->rows) return MUSE_EINVAL;
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    if (h->corr) return muse_corr_get_maps(h, first_unit, count, z_out);
     std::vector<int> st((size_t)count);
     if (count) CUDA_TRY(h, cudaMemcpyAsync(st.data(), h->zstate + first_unit, (size_t)count * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));

@@ -1,0 +1,676 @@
+// muse_corr.cu — MAP + score for the dense correlated-Gaussian family (F3), sm_100a.
+//
+//   −logLike(x, z | θ) = ½ [ ‖x − z‖² + a·zᵀPz + d·θ ],  a = e^{−θ},  P = Σ₀⁻¹        
+//   sample:  z = e^{θ/2}·L ξ,  x = z + ν   (L = chol Σ₀);  ∇z f = (z − x) + a·P z;  ∇θ logLike = ½ a·zᵀPz − d/2
+//
+// What it replaces: the same mapped body as the other families (/root/reference/src/muse.jl:170-175, 510-513,
+// 430-432; ẑ_at_θ = Optim L-BFGS(m) + HagerZhang, src/interface.jl:162-166), for a model whose gradient is a
+// dense contraction.
+//
+// Design.  The Hessian I + a·P is anisotropic, so a solve takes ~7–15 L-BFGS iterations at atol = 1e-2.  All
+// units of a pass advance in lock-step, one iteration per round, and the objective is quadratic, so along a search
+// direction s
+//       φ(α) = f + α·g·s + ½α²·sᵀ(I + aP)s,      φ′(α) = g·s + α·sᵀ(I + aP)s,      ∇f(z + αs) = g + α(s + a·P s):
+// ONE product Q = S·P per round — a (units × d)·(d × d) DGEMM on the FP64 tensor cores (muse_dgemm.cu) — serves
+// every Hager–Zhang trial of that iteration in closed form and the gradient at the accepted point.  The scalar
+// optimiser is the same Controller code as for the other families (muse_iso_ctl.cuh) fed by a closed-form issuer;
+// iteration and evaluation counts are those of the reference algorithm (oracle parity: identical counts, ẑ to
+// ~1e-15 relative in the NumPy model of this scheme, tests/test_oracle.py::test_f3_lockstep_model).
+// Per round: DGEMM (2·units·d² flop, the bound) + one CTA-per-unit kernel doing the line search, the update of
+// z, g, the (dx, dg) history and the two-loop recursion for the next direction (≈ 2·m·d doubles read per unit).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "muse_handle.cuh"
+#include "muse_iso_ctl.cuh"
+
+using namespace muse;
+
+namespace muse {
+namespace {
+
+constexpr int kCT = 256;          // threads per unit
+constexpr int kMaxM = 16;
+
+struct WarpCtx0 {
+    int tid;
+};
+
+struct CorrState {
+    double f, gmax;
+    double rho[kMaxM], dxdg[kMaxM], dgdg[kMaxM];
+    int iter, pseudo, fg, counter_f, status, active, redo, pad;
+};
+
+// one batch of units = rows of the arrays below (row stride ld)
+struct CorrBatch {
+    int rows;            // units
+    int mpad;            // rows padded to the GEMM tile
+    double *x, *z, *g, *s, *q;      // mpad × ld
+    double *dxh, *dgh;              // m × mpad × ld
+    CorrState* st;                  // rows
+};
+
+struct CorrLaunch {
+    int d, ld, m, max_iters;
+    double a, half_cst, atol, dhalf;     // dhalf = d/2
+    CorrBatch b;
+    int row0, nrows;                     // rows [row0, row0 + nrows) take part in this pass
+    // init
+    int start_kind;                      // kStartZero / kStartOwn / kStartTruth / kStartShared(Keep)
+    int data_row;                        // row holding the data unit (−1: none)
+    int mode;                            // 0: row r ↔ draw r − 1 + draw_shift; 1: FD virtual sims, row r ↔ draw r / 2, θ_sim = sig[r % 2]
+    int draw_shift;
+    double sig[2];
+    const double *W, *nu, *xdat, *zshared;
+    int* active_count;
+    // outputs (indexed by item = row − row0)
+    double *g_out, *gnorm_out, *f_out;
+    int *iters_out, *fg_out, *status_out;
+};
+
+__device__ __forceinline__ double block_sum(double v, double* red) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    const int w = threadIdx.x >> 5;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[w] = v;
+    __syncthreads();
+    double t = red[0];
+#pragma unroll
+    for (int i = 1; i < kCT / 32; ++i) t += red[i];
+    return t;
+}
+__device__ __forceinline__ double block_max(double v, double* red) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, off));
+    const int w = threadIdx.x >> 5;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[w] = v;
+    __syncthreads();
+    double t = red[0];
+#pragma unroll
+    for (int i = 1; i < kCT / 32; ++i) t = fmax(t, red[i]);
+    return t;
+}
+
+// ---- pass set-up: x, start vector -------------------------------------------------------------------------
+__global__ void __launch_bounds__(kCT) corr_init_kernel(const CorrLaunch L) {
+    const int r = L.row0 + blockIdx.x;
+    const size_t off = (size_t)r * L.ld;
+    double *x = L.b.x + off, *z = L.b.z + off;
+    const bool data = (r == L.data_row);
+    int draw = 0;
+    double sig = L.sig[0];
+    if (!data) {
+        if (L.mode == 0) draw = r - 1 + L.draw_shift;
+        else { draw = r / 2; sig = L.sig[r & 1]; }
+    }
+    const double* w = L.W + (size_t)draw * L.ld;
+    const double* nu = L.nu + (size_t)draw * L.ld;
+    const int sk = (data && L.start_kind == kStartTruth) ? kStartZero : L.start_kind;
+    for (int j = threadIdx.x; j < L.ld; j += kCT) {
+        const bool in = j < L.d;
+        double xv = 0.0, zt = 0.0;
+        if (in) {
+            if (data) xv = L.xdat[j];
+            else { zt = sig * w[j]; xv = zt + nu[j]; }       // z = e^{θ/2} L ξ,  x = z + ν
+        }
+        x[j] = xv;
+        if (sk == kStartZero) z[j] = 0.0;
+        else if (sk == kStartTruth) z[j] = zt;
+        else if (sk == kStartShared || sk == kStartSharedKeep) z[j] = in ? L.zshared[j] : 0.0;
+        // kStartOwn: z keeps the unit's previous ẑ
+    }
+}
+
+// ---- after Q = Z·P: f, ∇f at the start, convergence at the start, first direction -----------------------------
+__global__ void __launch_bounds__(kCT) corr_start_kernel(const CorrLaunch L) {
+    __shared__ double red[kCT / 32];
+    const int r = L.row0 + blockIdx.x;
+    const size_t off = (size_t)r * L.ld;
+    const double *x = L.b.x + off, *z = L.b.z + off, *q = L.b.q + off;
+    double *g = L.b.g + off, *s = L.b.s + off;
+    double rr = 0, zq = 0, gm = 0;
+    for (int j = threadIdx.x; j < L.d; j += kCT) {
+        const double rj = x[j] - z[j];
+        const double gj = fma(L.a, q[j], -rj);
+        g[j] = gj;
+        s[j] = -gj;
+        rr = fma(rj, rj, rr);
+        zq = fma(z[j], q[j], zq);
+        gm = fmax(gm, fabs(gj));
+    }
+    rr = block_sum(rr, red);
+    zq = block_sum(zq, red);
+    gm = block_max(gm, red);
+    if (threadIdx.x == 0) {
+        CorrState& st = L.b.st[r];
+        st.f = fma(0.5, fma(L.a, zq, rr), L.half_cst);
+        st.gmax = gm;
+        st.iter = 0;
+        st.pseudo = 0;
+        st.fg = 1;
+        st.counter_f = 0;
+        st.redo = 0;
+        st.status = MUSE_STATUS_G_CONVERGED;
+        const bool finite = isfinite(st.f) && isfinite(gm);
+        if (!finite) st.status = MUSE_STATUS_NONFINITE;
+        st.active = (finite && gm > L.atol && L.max_iters > 0) ? 1 : 0;
+        if (st.active) {
+            st.iter = 1;            // the first iteration is under way: direction −g, pseudo_iteration 1
+            st.pseudo = 1;
+            atomicAdd(L.active_count, 1);
+        }
+    }
+}
+
+// closed-form line function for the Controller's Hager–Zhang
+struct QuadIssuer {
+    double f0, gs, sAs;
+    __device__ void operator()(Cmd& cur, double (&red)[7]) {
+        const double c = cur.c;
+        red[0] = 2.0 * (f0 + c * gs + 0.5 * c * c * sAs);     // phidphi: φ = ½·red[0] + half_cst with half_cst = 0
+        red[1] = gs + c * sAs;
+        red[2] = red[3] = red[4] = red[5] = red[6] = 0.0;
+    }
+};
+
+// ---- one lock-step round, after Q = S·P ---------------------------------------------------------------------
+__global__ void __launch_bounds__(kCT) corr_iter_kernel(const CorrLaunch L, const SolveLaunch Lq) {
+    extern __shared__ double vec[];             // ld doubles: working vector of the two-loop recursion
+    __shared__ double red[kCT / 32];
+    __shared__ double bc[2];
+    __shared__ int flag;
+    const int r = L.row0 + blockIdx.x;
+    CorrState& st = L.b.st[r];
+    if (!st.active) return;
+    const size_t off = (size_t)r * L.ld, hstride = (size_t)L.b.mpad * L.ld;
+    double *z = L.b.z + off, *g = L.b.g + off, *s = L.b.s + off;
+    const double* q = L.b.q + off;
+    const int m = L.m;
+
+    double gs = 0, ss = 0, sq = 0;
+    for (int j = threadIdx.x; j < L.d; j += kCT) {
+        gs = fma(g[j], s[j], gs);
+        ss = fma(s[j], s[j], ss);
+        sq = fma(s[j], q[j], sq);
+    }
+    gs = block_sum(gs, red);
+    ss = block_sum(ss, red);
+    sq = block_sum(sq, red);
+    const double sAs = fma(L.a, sq, ss);
+
+    // thread 0: reset test, Hager–Zhang on the closed-form line function
+    if (threadIdx.x == 0) {
+        flag = 0;
+        if (gs >= 0.0 && st.pseudo > 1 && !st.redo) {           // reset_search_direction!: retry this iteration along −g
+            st.pseudo = 1;
+            st.redo = 1;
+            flag = 1;
+        } else {
+            st.redo = 0;
+            WarpCtx0 ctx{0};
+            QuadIssuer qi{st.f, gs, sAs};
+            Controller<WarpCtx0, QuadIssuer> ctl(ctx, Lq, qi);
+            ctl.fg_evals = 0;
+            ctl.pre_valid = false;
+            ctl.com_alpha = NAN;
+            ctl.last_eval_alpha = NAN;
+            ctl.last_phi = ctl.last_dphi = NAN;
+            ctl.cur.lazy = 0;
+            double alpha, phi_alpha;
+            const int ls = ctl.hager_zhang(1.0, st.f, gs, alpha, phi_alpha);     // InitialStatic(alpha = 1)
+            int fg = ctl.fg_evals;
+            if (ls == 0 && alpha != 0.0 && !(ctl.last_eval_alpha == alpha)) fg += 1;   // update_g! at a point not evaluated last
+            st.fg += fg;
+            bc[0] = alpha;
+            if (ls != 0) { st.status = MUSE_STATUS_LS_FAILED; flag = 2; }
+        }
+    }
+    __syncthreads();
+    if (flag == 1) {                                   // direction reset: s ← −g, nothing else this round
+        for (int j = threadIdx.x; j < L.d; j += kCT) s[j] = -g[j];
+        return;
+    }
+    const double alpha = bc[0];
+    const int idx = (st.pseudo - 1) % m;
+    double* dx = L.b.dxh + idx * hstride + off;
+    double* dg = L.b.dgh + idx * hstride + off;
+    double gm = 0, xc = 0, dxdg = 0, dgdg = 0;
+    for (int j = threadIdx.x; j < L.d; j += kCT) {
+        const double dxj = alpha * s[j];
+        const double dgj = alpha * fma(L.a, q[j], s[j]);
+        const double zn = z[j] + dxj;
+        const double gn = g[j] + dgj;
+        xc = fmax(xc, fabs(zn - z[j]));
+        z[j] = zn;
+        g[j] = gn;
+        dx[j] = dxj;
+        dg[j] = dgj;
+        gm = fmax(gm, fabs(gn));
+        dxdg = fma(dxj, dgj, dxdg);
+        dgdg = fma(dgj, dgj, dgdg);
+    }
+    gm = block_max(gm, red);
+    xc = block_max(xc, red);
+    dxdg = block_sum(dxdg, red);
+    dgdg = block_sum(dgdg, red);
+    if (threadIdx.x == 0) {
+        const double f_prev = st.f;
+        if (flag == 2) {                               // linesearch exception: x moved, optimisation stops
+            st.gmax = gm;
+            st.active = 0;
+        } else {
+            st.f = f_prev + alpha * gs + 0.5 * alpha * alpha * sAs;
+            st.gmax = gm;
+            const bool x_conv = xc <= 0.0, f_conv = fabs(st.f - f_prev) <= 0.0, g_conv = gm <= L.atol;
+            st.counter_f = f_conv ? st.counter_f + 1 : 0;
+            const bool conv = x_conv || g_conv || st.counter_f > 1;
+            if (conv) st.status = g_conv ? MUSE_STATUS_G_CONVERGED : MUSE_STATUS_XF_CONVERGED;
+            if (!isfinite(st.f) || !isfinite(gm)) { st.status = MUSE_STATUS_NONFINITE; st.active = 0; }
+            else if (conv) st.active = 0;
+            else if (st.iter >= L.max_iters) { st.status = MUSE_STATUS_MAXITER; st.active = 0; }
+            if (st.active) {                           // update_h!, then the next iteration starts
+                const double rho_it = 1.0 / dxdg;
+                if (isinf(rho_it)) st.pseudo = 0;
+                else { st.rho[idx] = rho_it; st.dxdg[idx] = dxdg; st.dgdg[idx] = dgdg; }
+                st.iter += 1;
+                st.pseudo += 1;
+            }
+        }
+        if (!st.active) atomicSub(L.active_count, 1);
+        flag = st.active;
+    }
+    __syncthreads();
+    if (!flag) return;
+
+    // twoloop!: s ← −H·g for the next round  [EXT Optim.jl l_bfgs.jl]
+    const int pseudo = st.pseudo;
+    const int lower = pseudo - m, upper = pseudo - 1;
+    __shared__ double alpha_tl[kMaxM];
+    for (int j = threadIdx.x; j < L.d; j += kCT) vec[j] = g[j];
+    __syncthreads();
+    for (int index = upper; index >= lower; --index) {
+        if (index < 1) continue;
+        const int i = (index - 1) % m;
+        const double* dxi = L.b.dxh + i * hstride + off;
+        const double* dgi = L.b.dgh + i * hstride + off;
+        double a = 0;
+        for (int j = threadIdx.x; j < L.d; j += kCT) a = fma(dxi[j], vec[j], a);
+        a = block_sum(a, red);
+        const double al = st.rho[i] * a;
+        if (threadIdx.x == 0) alpha_tl[i] = al;
+        for (int j = threadIdx.x; j < L.d; j += kCT) vec[j] = fma(-al, dgi[j], vec[j]);
+        __syncthreads();
+    }
+    if (pseudo > 1) {                                  // scaleinvH0
+        const int i = (upper - 1) % m;
+        const double sc = st.dxdg[i] / st.dgdg[i];
+        for (int j = threadIdx.x; j < L.d; j += kCT) vec[j] *= sc;
+        __syncthreads();
+    }
+    for (int index = lower; index <= upper; ++index) {
+        if (index < 1) continue;
+        const int i = (index - 1) % m;
+        const double* dxi = L.b.dxh + i * hstride + off;
+        const double* dgi = L.b.dgh + i * hstride + off;
+        double b = 0;
+        for (int j = threadIdx.x; j < L.d; j += kCT) b = fma(dgi[j], vec[j], b);
+        b = block_sum(b, red);
+        const double cf = alpha_tl[i] - st.rho[i] * b;
+        for (int j = threadIdx.x; j < L.d; j += kCT) vec[j] = fma(cf, dxi[j], vec[j]);
+        __syncthreads();
+    }
+    for (int j = threadIdx.x; j < L.d; j += kCT) s[j] = -vec[j];
+}
+
+// ---- after Q = Ẑ·P: score and outputs --------------------------------------------------------------------------
+__global__ void __launch_bounds__(kCT) corr_score_kernel(const CorrLaunch L) {
+    __shared__ double red[kCT / 32];
+    const int r = L.row0 + blockIdx.x;
+    const size_t off = (size_t)r * L.ld;
+    const double *z = L.b.z + off, *q = L.b.q + off;
+    double zq = 0;
+    for (int j = threadIdx.x; j < L.d; j += kCT) zq = fma(z[j], q[j], zq);
+    zq = block_sum(zq, red);
+    if (threadIdx.x == 0) {
+        const CorrState& st = L.b.st[r];
+        const int item = blockIdx.x;
+        L.g_out[item] = 0.5 * L.a * zq - L.dhalf;              // ∇θ logLike = ½ e^{−θ} zᵀPz − d/2
+        L.gnorm_out[item] = st.gmax;
+        L.f_out[item] = st.f;
+        L.iters_out[item] = st.iter;
+        L.fg_out[item] = st.fg;
+        L.status_out[item] = st.status;
+    }
+}
+
+}  // namespace
+}  // namespace muse
+
+// =============================================================================== host side
+struct muse_corr_ctx {
+    int ld = 0;                       // row stride = d rounded up to the GEMM tile (128)
+    int draw_rows = 0, draw_pad = 0;  // nsims + 1 (last = master draw), padded to 128
+    int h_rows = 0, h_pad = 0;        // separate H shard (multi-GPU)
+    double *P = nullptr, *Lt = nullptr;          // ld × ld, zero padded; Lt = Lᵀ so that W = ξ·Lᵀ = (L ξᵀ)ᵀ
+    double *W = nullptr, *nu = nullptr, *tmp = nullptr;
+    double *W_h = nullptr, *nu_h = nullptr;
+    double *xdat = nullptr, *z0user = nullptr;
+    bool have_W = false, have_W_h = false;
+    CorrBatch main{}, fd{}, fid{};
+    int* active = nullptr;
+};
+
+namespace {
+
+int round_up_i(int v, int m) { return (v + m - 1) / m * m; }
+
+#define CORR_TRY(h, expr)                                                                     \
+    do {                                                                                      \
+        cudaError_t e__ = (expr);                                                             \
+        if (e__ != cudaSuccess) {                                                             \
+            (h)->err = std::string(#expr) + ": " + cudaGetErrorString(e__);                   \
+            return e__ == cudaErrorMemoryAllocation ? MUSE_ENOMEM : MUSE_ECUDA;               \
+        }                                                                                     \
+    } while (0)
+
+void free_batch(CorrBatch& b) {
+    cudaFree(b.x); cudaFree(b.z); cudaFree(b.g); cudaFree(b.s); cudaFree(b.q); cudaFree(b.dxh); cudaFree(b.dgh); cudaFree(b.st);
+    b = CorrBatch{};
+}
+
+int alloc_batch(muse_handle* h, CorrBatch& b, int rows) {
+    muse_corr_ctx* c = h->corr;
+    if (b.rows >= rows) return MUSE_OK;
+    free_batch(b);
+    const int mpad = round_up_i(rows, 128);
+    const size_t n = (size_t)mpad * c->ld * sizeof(double), m = (size_t)h->cfg.lbfgs_m;
+    CORR_TRY(h, cudaMalloc(&b.x, n));
+    CORR_TRY(h, cudaMalloc(&b.z, n));
+    CORR_TRY(h, cudaMalloc(&b.g, n));
+    CORR_TRY(h, cudaMalloc(&b.s, n));
+    CORR_TRY(h, cudaMalloc(&b.q, n));
+    CORR_TRY(h, cudaMalloc(&b.dxh, n * m));
+    CORR_TRY(h, cudaMalloc(&b.dgh, n * m));
+    CORR_TRY(h, cudaMalloc(&b.st, (size_t)mpad * sizeof(CorrState)));
+    for (double* p : {b.x, b.z, b.g, b.s, b.q}) CORR_TRY(h, cudaMemsetAsync(p, 0, n, h->stream));
+    CORR_TRY(h, cudaMemsetAsync(b.st, 0, (size_t)mpad * sizeof(CorrState), h->stream));
+    b.rows = rows;
+    b.mpad = mpad;
+    return MUSE_OK;
+}
+
+// Q[rows] = V[rows]·P over the tile-aligned superset of [row0, row0 + nrows)
+int gemm_rows(muse_handle* h, const CorrBatch& b, const double* V, int row0, int nrows) {
+    muse_corr_ctx* c = h->corr;
+    const int lo = row0 / 128 * 128, hi = round_up_i(row0 + nrows, 128);
+    const size_t off = (size_t)lo * c->ld;
+    CORR_TRY(h, launch_dgemm(V + off, c->P, b.q + off, hi - lo, c->ld, c->ld, c->ld, c->ld, c->ld, h->stream));
+    h->acc.launches += 1;
+    h->acc.solve_flops += 2.0 * (hi - lo) * (double)c->ld * c->ld;
+    return MUSE_OK;
+}
+
+// the lock-step solve of rows [row0, row0 + nrows) of batch b; outputs go to items 0..nrows−1
+int corr_solve(muse_handle* h, CorrBatch& b, CorrLaunch& L) {
+    muse_corr_ctx* c = h->corr;
+    L.d = h->cfg.d;
+    L.ld = c->ld;
+    L.m = h->cfg.lbfgs_m;
+    L.max_iters = h->cfg.max_iters;
+    L.dhalf = 0.5 * h->cfg.d;
+    L.b = b;
+    L.active_count = c->active;
+    L.g_out = h->g_d; L.gnorm_out = h->gnorm_d; L.f_out = h->f_d;
+    L.iters_out = h->iters_d; L.fg_out = h->fg_d; L.status_out = h->status_d;
+    SolveLaunch Lq;
+    std::memset(&Lq, 0, sizeof(Lq));                  // ev.half_cst = 0: the closed-form issuer returns 2φ
+    const int smem = c->ld * (int)sizeof(double);
+    static int smem_set = 0;
+    if (smem > 48 * 1024 && smem > smem_set) {
+        CORR_TRY(h, cudaFuncSetAttribute(corr_iter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        smem_set = smem;
+    }
+    muse_handle::Rec rec{};
+    if (h->prof) {
+        CORR_TRY(h, cudaEventCreate(&rec.a));
+        CORR_TRY(h, cudaEventCreate(&rec.b));
+        CORR_TRY(h, cudaEventRecord(rec.a, h->stream));
+    }
+    CORR_TRY(h, cudaMemsetAsync(c->active, 0, sizeof(int), h->stream));
+    corr_init_kernel<<<L.nrows, kCT, 0, h->stream>>>(L);
+    CORR_TRY(h, cudaGetLastError());
+    if (L.start_kind == kStartZero) {
+        CORR_TRY(h, cudaMemsetAsync(b.q + (size_t)L.row0 * c->ld, 0, (size_t)L.nrows * c->ld * sizeof(double), h->stream));
+    } else {
+        const int rc = gemm_rows(h, b, b.z, L.row0, L.nrows);
+        if (rc != MUSE_OK) return rc;
+    }
+    corr_start_kernel<<<L.nrows, kCT, 0, h->stream>>>(L);
+    CORR_TRY(h, cudaGetLastError());
+    h->acc.launches += 2;
+    const int max_rounds = 2 * h->cfg.max_iters + 8;
+    for (int round = 0; round < max_rounds; ++round) {
+        int active = 0;
+        CORR_TRY(h, cudaMemcpyAsync(&active, c->active, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CORR_TRY(h, cudaStreamSynchronize(h->stream));
+        if (active <= 0) break;
+        const int rc = gemm_rows(h, b, b.s, L.row0, L.nrows);
+        if (rc != MUSE_OK) return rc;
+        corr_iter_kernel<<<L.nrows, kCT, smem, h->stream>>>(L, Lq);
+        CORR_TRY(h, cudaGetLastError());
+        h->acc.launches += 1;
+    }
+    const int rc = gemm_rows(h, b, b.z, L.row0, L.nrows);
+    if (rc != MUSE_OK) return rc;
+    corr_score_kernel<<<L.nrows, kCT, 0, h->stream>>>(L);
+    CORR_TRY(h, cudaGetLastError());
+    h->acc.launches += 1;
+    h->acc.solve_launches += 1;
+    if (h->prof) {
+        CORR_TRY(h, cudaEventRecord(rec.b, h->stream));
+        rec.cls = 0;
+        rec.units = L.nrows;
+        rec.bytes = 0.0;
+        h->recs.push_back(rec);
+    }
+    return MUSE_OK;
+}
+
+}  // namespace
+
+int muse_corr_create(muse_handle* h) {
+    const muse_cfg& cfg = h->cfg;
+    if (!cfg.P || !cfg.L) { h->err = "corrgauss needs cfg.P = Σ₀⁻¹ and cfg.L = chol(Σ₀) (d × d, row-major)"; return MUSE_EINVAL; }
+    muse_corr_ctx* c = new (std::nothrow) muse_corr_ctx();
+    if (!c) return MUSE_ENOMEM;
+    h->corr = c;
+    const int d = cfg.d;
+    c->ld = round_up_i(d, 128);
+    c->draw_rows = cfg.nsims + 1;
+    c->draw_pad = round_up_i(c->draw_rows, 128);
+    c->h_rows = cfg.nsims_h;
+    c->h_pad = round_up_i(cfg.nsims_h > 0 ? cfg.nsims_h : 1, 128);
+    const size_t ld = c->ld, mat = ld * ld * sizeof(double), B = sizeof(double);
+    CORR_TRY(h, cudaMalloc(&c->P, mat));
+    CORR_TRY(h, cudaMalloc(&c->Lt, mat));
+    CORR_TRY(h, cudaMemsetAsync(c->P, 0, mat, h->stream));
+    CORR_TRY(h, cudaMemsetAsync(c->Lt, 0, mat, h->stream));
+    CORR_TRY(h, cudaMemcpy2DAsync(c->P, ld * B, cfg.P, (size_t)d * B, (size_t)d * B, d, cudaMemcpyHostToDevice, h->stream));
+    std::vector<double> lt((size_t)d * d);
+    for (int i = 0; i < d; ++i)
+        for (int j = 0; j < d; ++j) lt[(size_t)j * d + i] = cfg.L[(size_t)i * d + j];
+    CORR_TRY(h, cudaMemcpy2DAsync(c->Lt, ld * B, lt.data(), (size_t)d * B, (size_t)d * B, d, cudaMemcpyHostToDevice, h->stream));
+    const size_t dr = (size_t)c->draw_pad * ld * B;
+    CORR_TRY(h, cudaMalloc(&c->W, dr));
+    CORR_TRY(h, cudaMalloc(&c->nu, dr));
+    CORR_TRY(h, cudaMalloc(&c->tmp, (size_t)std::max(c->draw_pad, c->h_pad) * ld * B));
+    CORR_TRY(h, cudaMemsetAsync(c->W, 0, dr, h->stream));
+    CORR_TRY(h, cudaMemsetAsync(c->nu, 0, dr, h->stream));
+    if (cfg.nsims_h > 0) {
+        const size_t hr = (size_t)c->h_pad * ld * B;
+        CORR_TRY(h, cudaMalloc(&c->W_h, hr));
+        CORR_TRY(h, cudaMalloc(&c->nu_h, hr));
+        CORR_TRY(h, cudaMemsetAsync(c->W_h, 0, hr, h->stream));
+        CORR_TRY(h, cudaMemsetAsync(c->nu_h, 0, hr, h->stream));
+    }
+    CORR_TRY(h, cudaMalloc(&c->xdat, ld * B));
+    CORR_TRY(h, cudaMalloc(&c->z0user, ld * B));
+    CORR_TRY(h, cudaMemsetAsync(c->xdat, 0, ld * B, h->stream));
+    CORR_TRY(h, cudaMemsetAsync(c->z0user, 0, ld * B, h->stream));
+    CORR_TRY(h, cudaMalloc(&c->active, sizeof(int)));
+    int rc = alloc_batch(h, c->main, cfg.nsims + 1);
+    if (rc != MUSE_OK) return rc;
+    rc = alloc_batch(h, c->fid, 1);
+    if (rc != MUSE_OK) return rc;
+    CORR_TRY(h, cudaStreamSynchronize(h->stream));     // lt goes out of scope
+    return MUSE_OK;
+}
+
+void muse_corr_destroy(muse_handle* h) {
+    muse_corr_ctx* c = h->corr;
+    if (!c) return;
+    cudaFree(c->P); cudaFree(c->Lt); cudaFree(c->W); cudaFree(c->nu); cudaFree(c->tmp); cudaFree(c->W_h); cudaFree(c->nu_h);
+    cudaFree(c->xdat); cudaFree(c->z0user); cudaFree(c->active);
+    free_batch(c->main); free_batch(c->fd); free_batch(c->fid);
+    delete c;
+    h->corr = nullptr;
+}
+
+// ξ rows (host or already on the device in c->tmp) → W = ξ·Lᵀ
+static int corr_make_W(muse_handle* h, double* Wdst, int pad_rows) {
+    muse_corr_ctx* c = h->corr;
+    CORR_TRY(h, launch_dgemm(c->tmp, c->Lt, Wdst, pad_rows, c->ld, c->ld, c->ld, c->ld, c->ld, h->stream));
+    h->acc.launches += 1;
+    return MUSE_OK;
+}
+
+int muse_corr_set_data(muse_handle* h, const double* x) {
+    CORR_TRY(h, cudaMemcpyAsync(h->corr->xdat, x, (size_t)h->cfg.d * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CORR_TRY(h, cudaStreamSynchronize(h->stream));
+    return MUSE_OK;
+}
+
+int muse_corr_set_z0(muse_handle* h, const double* z0) {
+    CORR_TRY(h, cudaMemcpyAsync(h->corr->z0user, z0, (size_t)h->cfg.d * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CORR_TRY(h, cudaStreamSynchronize(h->stream));
+    return MUSE_OK;
+}
+
+int muse_corr_set_draws(muse_handle* h, const double* xi, const double* nu, const double* xi_m, const double* nu_m, bool hshard) {
+    muse_corr_ctx* c = h->corr;
+    const size_t w = (size_t)h->cfg.d * sizeof(double), pitch = (size_t)c->ld * sizeof(double);
+    const int n = hshard ? h->cfg.nsims_h : h->cfg.nsims;
+    const int pad = hshard ? c->h_pad : c->draw_pad;
+    double* nud = hshard ? c->nu_h : c->nu;
+    CORR_TRY(h, cudaMemsetAsync(c->tmp, 0, (size_t)pad * pitch, h->stream));
+    if (n) {
+        CORR_TRY(h, cudaMemcpy2DAsync(c->tmp, pitch, xi, w, w, n, cudaMemcpyHostToDevice, h->stream));
+        CORR_TRY(h, cudaMemcpy2DAsync(nud, pitch, nu, w, w, n, cudaMemcpyHostToDevice, h->stream));
+    }
+    if (!hshard) {
+        CORR_TRY(h, cudaMemcpyAsync(c->tmp + (size_t)n * c->ld, xi_m, w, cudaMemcpyHostToDevice, h->stream));
+        CORR_TRY(h, cudaMemcpyAsync(nud + (size_t)n * c->ld, nu_m, w, cudaMemcpyHostToDevice, h->stream));
+    }
+    const int rc = corr_make_W(h, hshard ? c->W_h : c->W, pad);
+    if (rc != MUSE_OK) return rc;
+    CORR_TRY(h, cudaStreamSynchronize(h->stream));
+    (hshard ? c->have_W_h : c->have_W) = true;
+    return MUSE_OK;
+}
+
+int muse_corr_seed_draws(muse_handle* h, uint64_t seed) {
+    muse_corr_ctx* c = h->corr;
+    const size_t pitch = (size_t)c->ld * sizeof(double);
+    CORR_TRY(h, cudaMemsetAsync(c->tmp, 0, (size_t)c->draw_pad * pitch, h->stream));
+    CORR_TRY(h, launch_philox_draws(c->tmp, c->nu, h->cfg.nsims + 1, h->cfg.d, c->ld, seed, h->cfg.sim_offset, h->cfg.nsims, h->stream));
+    int rc = corr_make_W(h, c->W, c->draw_pad);
+    if (rc != MUSE_OK) return rc;
+    c->have_W = true;
+    if (h->cfg.nsims_h > 0) {
+        CORR_TRY(h, cudaMemsetAsync(c->tmp, 0, (size_t)c->h_pad * pitch, h->stream));
+        CORR_TRY(h, launch_philox_draws(c->tmp, c->nu_h, h->cfg.nsims_h, h->cfg.d, c->ld, seed, h->cfg.h_sim_offset, -1, h->stream));
+        rc = corr_make_W(h, c->W_h, c->h_pad);
+        if (rc != MUSE_OK) return rc;
+        c->have_W_h = true;
+    }
+    h->acc.launches += 1;
+    h->acc.draw_launches += 1;
+    CORR_TRY(h, cudaStreamSynchronize(h->stream));
+    return MUSE_OK;
+}
+
+int muse_corr_map_score(muse_handle* h, const double* theta_sim, const double* theta_eval, double atol, int include_data,
+                        int warm_start, int first_sim, int count) {
+    muse_corr_ctx* c = h->corr;
+    if (include_data && first_sim != 0) { h->err = "corrgauss: include_data needs first_sim = 0"; return MUSE_EINVAL; }
+    CorrLaunch L{};
+    L.a = std::exp(-theta_eval[0]);
+    L.half_cst = 0.5 * h->cfg.d * theta_eval[0];
+    L.atol = atol;
+    L.sig[0] = L.sig[1] = std::exp(0.5 * theta_sim[0]);
+    L.mode = 0;
+    L.data_row = include_data ? 0 : -1;
+    L.row0 = include_data ? 0 : 1 + first_sim;
+    L.nrows = count + (include_data ? 1 : 0);
+    L.W = c->W; L.nu = c->nu; L.xdat = c->xdat;
+    switch (warm_start) {
+        case MUSE_START_ZEROS: L.start_kind = kStartZero; break;
+        case MUSE_START_PREV: L.start_kind = kStartOwn; break;
+        case MUSE_START_TRUTH: L.start_kind = kStartTruth; break;
+        default: L.start_kind = kStartShared; L.zshared = c->z0user; break;
+    }
+    return corr_solve(h, c->main, L);
+}
+
+// fiducial solve + the 2·n_H virtual sims of get_H! (src/muse.jl:417-442); scores land in items 2k + sgn
+int muse_corr_fd_launch(muse_handle* h, const double* theta0, const double* step, int nsims_H, double atol) {
+    muse_corr_ctx* c = h->corr;
+    const bool hshard = h->cfg.nsims_h > 0;
+    CorrLaunch F{};
+    F.a = std::exp(-theta0[0]);
+    F.half_cst = 0.5 * h->cfg.d * theta0[0];
+    F.atol = atol;
+    F.sig[0] = F.sig[1] = std::exp(0.5 * theta0[0]);
+    F.mode = 0;
+    F.data_row = -1;
+    F.row0 = 0;
+    F.nrows = 1;
+    F.draw_shift = h->cfg.nsims + 1;      // row 0 of the fiducial batch ↔ the master stream's own draw (row nsims)
+    F.W = c->W;
+    F.nu = c->nu;
+    F.start_kind = kStartZero;
+    int rc = corr_solve(h, c->fid, F);
+    if (rc != MUSE_OK) return rc;
+    rc = alloc_batch(h, c->fd, 2 * nsims_H);
+    if (rc != MUSE_OK) return rc;
+    CorrLaunch L{};
+    L.a = F.a; L.half_cst = F.half_cst; L.atol = atol;
+    L.sig[0] = std::exp(0.5 * (theta0[0] + (0.0 + step[0] * -1.0)));
+    L.sig[1] = std::exp(0.5 * (theta0[0] + (0.0 + step[0] * 1.0)));
+    L.mode = 1;
+    L.data_row = -1;
+    L.row0 = 0;
+    L.nrows = 2 * nsims_H;
+    L.W = hshard ? c->W_h : c->W;
+    L.nu = hshard ? c->nu_h : c->nu;
+    L.start_kind = kStartShared;
+    L.zshared = c->fid.z;
+    return corr_solve(h, c->fd, L);
+}
+
+int muse_corr_get_maps(muse_handle* h, int first_unit, int count, double* z_out) {
+    muse_corr_ctx* c = h->corr;
+    const size_t w = (size_t)h->cfg.d * sizeof(double), pitch = (size_t)c->ld * sizeof(double);
+    if (count) CORR_TRY(h, cudaMemcpy2DAsync(z_out, w, c->main.z + (size_t)first_unit * c->ld, pitch, w, count, cudaMemcpyDeviceToHost, h->stream));
+    CORR_TRY(h, cudaStreamSynchronize(h->stream));
+    return MUSE_OK;
+}
+
+bool muse_corr_have_draws(muse_handle* h, bool hshard) { return hshard ? h->corr->have_W_h : h->corr->have_W; }

@@ -7,6 +7,8 @@
 
 using muse::Geometry;
 
+struct muse_corr_ctx;   // correlated-Gaussian family (muse_corr.cu)
+
 struct muse_handle {
     muse_cfg cfg{};
     int ld = 0;
@@ -45,6 +47,8 @@ struct muse_handle {
     int *redo_count = nullptr, *redo_items = nullptr;
     unsigned long long* redo_total = nullptr;
 
+    muse_corr_ctx* corr = nullptr;
+
     // exchange step (muse_comm.cu): NCCL communicator and staging buffers
     void* comm = nullptr;
     int comm_nranks = 0, comm_rank = 0, comm_cap = 0;
@@ -61,3 +65,16 @@ struct muse_handle {
 };
 
 void muse_comm_release(muse_handle* h);
+
+// correlated-Gaussian family (muse_corr.cu)
+int  muse_corr_create(muse_handle* h);
+void muse_corr_destroy(muse_handle* h);
+int  muse_corr_set_data(muse_handle* h, const double* x);
+int  muse_corr_set_z0(muse_handle* h, const double* z0);
+int  muse_corr_set_draws(muse_handle* h, const double* xi, const double* nu, const double* xi_m, const double* nu_m, bool hshard);
+int  muse_corr_seed_draws(muse_handle* h, uint64_t seed);
+int  muse_corr_map_score(muse_handle* h, const double* theta_sim, const double* theta_eval, double atol, int include_data,
+                         int warm_start, int first_sim, int count);
+int  muse_corr_fd_launch(muse_handle* h, const double* theta0, const double* step, int nsims_H, double atol);
+int  muse_corr_get_maps(muse_handle* h, int first_unit, int count, double* z_out);
+bool muse_corr_have_draws(muse_handle* h, bool hshard);

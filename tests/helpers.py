@@ -4,16 +4,27 @@ import numpy as np
 import oracle as O
 
 
+def corr_consts(d, seed=5):
+    """Σ₀ = A·Aᵀ/d + 0.1·I with A ~ N(0,1) from a stated seed; returns P = Σ₀⁻¹, L = chol Σ₀."""
+    rng = np.random.Generator(np.random.Philox(seed))
+    A = rng.standard_normal((d, d))
+    S0 = A @ A.T / d + 0.1 * np.eye(d)
+    return np.linalg.inv(S0), np.linalg.cholesky(S0)
+
+
 def make_family(name, d):
+    if name == "corrgauss":
+        P, L = corr_consts(d)
+        return O.make_family(name, d, P=P, L=L)
     return O.make_family(name, d)
 
 
 def theta_true(name):
-    return np.array([0.0]) if name == "funnel" else np.array([0.0, 0.0])
+    return np.array([0.0, 0.0]) if name == "hiergauss" else np.array([0.0])
 
 
 def theta_start(name):
-    return np.array([1.0]) if name == "funnel" else np.array([0.5, 0.3])
+    return np.array([0.5, 0.3]) if name == "hiergauss" else np.array([1.0])
 
 
 def make_inputs(name, d, nsims, seed=1234, data_seed=99):

@@ -253,3 +253,70 @@ def test_dgemm_dmma_matches_numpy():
     ref = A @ B
     np.testing.assert_allclose(Cm, ref, rtol=0, atol=1e-13 * np.abs(A).max() * np.abs(B).max() * K)
     assert lib.muse_b200_dgemm_host(dp(A), dp(B), dp(Cm), 100, N, K) != 0      # extents must be tile multiples
+
+
+# ------------------------------------------------------------------------------- F3: dense correlated Gaussian
+def _corr_backend(d, nsims, draws, xd, fam, **kw):
+    import museinference_jl_b200 as m
+    be = m.B200Backend("corrgauss", d, nsims, P=fam.P, L=fam.L, **kw)
+    be.set_data(xd)
+    be.set_draws(draws.xi, draws.nu, draws.xi_master, draws.nu_master)
+    return be
+
+
+@pytest.mark.parametrize("d", [200, 384])
+def test_corrgauss_map_score_matches_oracle(d):
+    """Lock-step L-BFGS with one DMMA GEMM per iteration (csrc/muse_corr.cu) against the oracle's honest L-BFGS
+    (P·z evaluated at every trial point): same iteration and evaluation counts, ẑ and g within rtol 1e-8."""
+    name, nsims, atol = "corrgauss", 10, 1e-2
+    fam, draws, xd = make_inputs(name, d, nsims)
+    prob = O.OracleProblem(fam, xd, draws)
+    be = _corr_backend(d, nsims, draws, xd, fam)
+    th0 = np.array([0.6])
+    out = be.map_score(th0, th0, atol, include_data=True, warm_start=0)
+    zs = be.get_maps(0, nsims + 1)
+    ref_z = []
+    for u in range(nsims + 1):
+        x = xd if u == 0 else prob.sample_x_z(u - 1, th0)[0]
+        zh, g, soln = O.map_score_unit(prob, x, np.zeros(d), th0, atol)
+        ref_z.append(zh)
+        assert out["iters"][u] == soln.iterations and out["fg_evals"][u] == soln.f_calls, (u, out["iters"][u], soln.iterations)
+        np.testing.assert_allclose(zs[u], zh, rtol=RTOL_SIM, atol=1e-11)
+        np.testing.assert_allclose(out["g"][u], g, rtol=RTOL_SIM)
+        assert out["status"][u] == 0 and out["gnorm"][u] <= atol
+    assert out["iters"].min() >= 4          # anisotropic Hessian: a real multi-iteration solve
+    # warm pass at a moved θ, then truth start on a sub-range
+    th1 = th0 - 0.4
+    out = be.map_score(th1, th1, atol, include_data=True, warm_start=1)
+    zs = be.get_maps(0, nsims + 1)
+    for u in range(nsims + 1):
+        x = xd if u == 0 else prob.sample_x_z(u - 1, th1)[0]
+        zh, g, soln = O.map_score_unit(prob, x, ref_z[u], th1, atol)
+        assert out["iters"][u] == soln.iterations and out["fg_evals"][u] == soln.f_calls
+        np.testing.assert_allclose(zs[u], zh, rtol=RTOL_SIM, atol=1e-11)
+        np.testing.assert_allclose(out["g"][u], g, rtol=RTOL_SIM)
+    out = be.map_score(th1, th1, atol, include_data=False, warm_start=2, first_sim=3, count=5)
+    for i in range(5):
+        x, z = prob.sample_x_z(3 + i, th1)
+        zh, g, soln = O.map_score_unit(prob, x, z, th1, atol)
+        assert out["iters"][i] == soln.iterations and out["fg_evals"][i] == soln.f_calls
+        np.testing.assert_allclose(out["g"][i], g, rtol=RTOL_SIM)
+    be.close()
+
+
+def test_corrgauss_full_muse_matches_oracle():
+    import museinference_jl_b200 as m
+    name, d, nsims = "corrgauss", 256, 40
+    oprob, fam, draws, xd = oracle_problem(name, d, nsims, prior=O.NormalPrior(0, 3))
+    ref = O.muse(oprob, [1.0], nsims=nsims, get_covariance=True)
+    rng = m.BaseDraws(draws.xi, draws.nu, draws.xi_master, draws.nu_master)
+    for fused in (True, False):
+        prob = m.SimpleMuseProblem(xd, name, m.NormalPrior(0, 3), P=fam.P, L=fam.L)
+        res = m.muse(prob, [1.0], rng=rng, nsims=nsims, get_covariance=True, fused_driver=fused)
+        assert len(res.history) == len(ref.history)
+        np.testing.assert_allclose(res.theta, ref.theta, rtol=RTOL_EST)
+        np.testing.assert_allclose(res.J, ref.J, rtol=RTOL_EST)
+        np.testing.assert_allclose(res.H, ref.H, rtol=RTOL_EST)
+        np.testing.assert_allclose(res.Sigma, ref.Sigma, rtol=10 * RTOL_EST)
+        np.testing.assert_allclose(np.array(res.gs), np.array(ref.gs), rtol=RTOL_SIM)
+        prob.close()
