@@ -51,7 +51,7 @@ def parse():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--d", type=int, default=D)
     ap.add_argument("--nsims", type=int, default=NSIMS_PER_GPU, help="sims per GPU (weak) or in total (strong)")
-    ap.add_argument("--family", default="funnel", choices=["funnel", "hiergauss"])
+    ap.add_argument("--family", default="funnel", choices=["funnel", "hiergauss", "corrgauss"])
     ap.add_argument("--group", type=int, default=0)
     ap.add_argument("--cluster", type=int, default=0)
     ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 generic solver only, 2 streaming kernel first")
@@ -60,15 +60,23 @@ def parse():
     return ap.parse_args()
 
 
-def observed_data(family, d):
-    """Synthetic observation at θ_true (0 for the funnel, (0,0) for hiergauss); host NumPy, seeded."""
+def corr_consts(d, seed=5):
+    """F3 constants: Σ₀ = A·Aᵀ/d + 0.1·I, A ~ N(0,1) from a stated seed; P = Σ₀⁻¹, L = chol Σ₀."""
+    rng = np.random.Generator(np.random.Philox(seed))
+    A = rng.standard_normal((d, d))
+    S0 = A @ A.T / d + 0.1 * np.eye(d)
+    return np.linalg.inv(S0), np.linalg.cholesky(S0)
+
+
+def observed_data(family, d, L=None):
+    """Synthetic observation at θ_true (0 for the funnel and corrgauss, (0,0) for hiergauss); host NumPy, seeded."""
     rng = np.random.Generator(np.random.Philox(DATA_SEED))
     xi, nu = rng.standard_normal(d), rng.standard_normal(d)
-    return xi + nu      # sig = 1, mu = 0 at θ_true for both families
+    return (L @ xi if L is not None else xi) + nu      # sig = 1, mu = 0 at θ_true
 
 
 def theta_start(family):
-    return np.array([THETA0]) if family == "funnel" else np.array([0.5, 0.3])
+    return np.array([0.5, 0.3]) if family == "hiergauss" else np.array([THETA0])
 
 
 # ----------------------------------------------------------------------------- clocks sampler
@@ -115,18 +123,30 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- CPU arm
+_CPU_PROBLEMS = {}
+
+
+def cpu_problem(family, d, nsims):
+    """Oracle problem of the bench shape on seeded host draws (built once per shape: 2·nsims·d normals)."""
+    import oracle as O
+
+    key = (family, d, nsims)
+    if key not in _CPU_PROBLEMS:
+        fam = O.make_family(family, d)
+        rng = np.random.Generator(np.random.Philox(SIM_SEED))
+        draws = O.Draws(rng.standard_normal((nsims, d)), rng.standard_normal((nsims, d)),
+                        rng.standard_normal(d), rng.standard_normal(d))
+        prior = O.NormalPrior(0, 3) if family == "funnel" else O.FlatPrior()
+        _CPU_PROBLEMS[key] = O.OracleProblem(fam, observed_data(family, d), draws, prior)
+    return _CPU_PROBLEMS[key]
+
+
 def cpu_solve_rate(family, d, nsims, nthreads, reps=1):
     """Full solve with the oracle's C port on the host cores; returns (units/s, units, seconds, threads)."""
-    import oracle as O
     from oracle import cmuse, cport
 
     cport.build()
-    fam = O.make_family(family, d)
-    rng = np.random.Generator(np.random.Philox(SIM_SEED))
-    draws = O.Draws(rng.standard_normal((nsims, d)), rng.standard_normal((nsims, d)),
-                    rng.standard_normal(d), rng.standard_normal(d))
-    prior = O.NormalPrior(0, 3) if family == "funnel" else O.FlatPrior()
-    prob = O.OracleProblem(fam, observed_data(family, d), draws, prior)
+    prob = cpu_problem(family, d, nsims)
     threads = nthreads or cport.max_threads()
     best = None
     for _ in range(reps):
@@ -137,15 +157,23 @@ def cpu_solve_rate(family, d, nsims, nthreads, reps=1):
     return units / best, units, best, threads
 
 
+def cpu_sample_nsims(args):
+    """Bounded sample of the workload for the CPU arm: the full per-GPU batch when its two base-normal arrays fit
+    ~4.5 GB of host memory (C3: 2048 × 65536 → 2.1 GB), otherwise as many sims as do."""
+    if args.cpu_sims:
+        return args.cpu_sims
+    return int(max(16, min(args.nsims, 4.5e9 / (16.0 * args.d))))
+
+
 def run_reference(args):
     """--impl reference: the CPU implementation of the path (oracle C port; the Julia reference cannot
     run in this image) on all host threads, each step a bounded sample of the workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    nsims = args.cpu_sims or 256
-    for _ in range(args.warmup):
-        cpu_solve_rate(args.family, args.d, min(nsims, 32), 0)
+    nsims = cpu_sample_nsims(args)
+    for _ in range(min(args.warmup, 1)):
+        cpu_solve_rate(args.family, args.d, nsims, 0)
     rates, secs, units, threads = [], 0.0, 0, 0
     for _ in range(args.steps):
         r, u, dt, threads = cpu_solve_rate(args.family, args.d, nsims, 0)
@@ -153,7 +181,8 @@ def run_reference(args):
         secs += dt
         units += u
     value = units / secs
-    sample = f"full solve (θ̂,J,H) of {args.family} d={args.d} on nsims={nsims} (subset of {args.nsims}); C port, analytic gradients"
+    sample = (f"full solve (θ̂,J,H) of {args.family} d={args.d} on nsims={nsims} of {args.nsims} per step; oracle C port (pthreads), "
+              "analytic gradients — the Julia reference cannot run here and would be slower (serial pool, AD gradients)")
     line = {
         "impl": "reference", "metric": "MUSE sims/sec (MAP+score)", "value": value, "unit": "sims/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
@@ -192,10 +221,13 @@ def run_b200(args):
     family, d = args.family, args.d
     stream = torch.cuda.Stream()          # the library launches on this stream; events are recorded on it
     torch.cuda.set_stream(stream)
-    x_host = torch.from_numpy(observed_data(family, d)).pin_memory()
-    prior = m.NormalPrior(0, 3) if family == "funnel" else m.FlatPrior()
-    prob = m.SimpleMuseProblem(x_host.numpy(), family, prior, group=args.group, cluster=args.cluster, kernel=args.kernel,
-                               stream=stream.cuda_stream)
+    P = Lc = None
+    if family == "corrgauss":
+        P, Lc = corr_consts(d)
+    x_host = torch.from_numpy(observed_data(family, d, Lc)).pin_memory()
+    prior = m.FlatPrior() if family == "hiergauss" else m.NormalPrior(0, 3)
+    prob = m.SimpleMuseProblem(x_host.numpy(), family, prior, P=P, L=Lc, group=args.group, cluster=args.cluster,
+                               kernel=args.kernel, stream=stream.cuda_stream)
     th0 = theta_start(family)
 
     exch = {"s": 0.0, "n": 0}
@@ -294,13 +326,38 @@ def run_b200(args):
             pass
         geo = be.geometry()
         value = units_all / (ms / 1e3)
+        cfg_name = {"funnel": "BASELINE configs[2]" if d == 65536 else ("BASELINE configs[1]" if d == 512 else "funnel, custom shape"),
+                    "hiergauss": "BASELINE configs[3]", "corrgauss": "BASELINE configs[4]"}[family]
+        tensor_roof = None
+        if family == "corrgauss":
+            # FP64 tensor roofline: denominator = cuBLAS DGEMM of the same shape measured here (MEASURED_PEAKS.json
+            # carries only bf16), numerator = 2·rows·d² per P-product ÷ CUDA-event time of the whole solver chains
+            rows = (args.nsims + 1 + 127) // 128 * 128
+            a = torch.full((rows, d), 4.7e-4, dtype=torch.float64, device="cuda")
+            b = torch.full((d, d), 4.7e-4, dtype=torch.float64, device="cuda")
+            for _ in range(2):
+                torch.matmul(a, b)
+            t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0e.record()
+            for _ in range(5):
+                torch.matmul(a, b)
+            t1e.record()
+            torch.cuda.synchronize()
+            cublas_tf = 2.0 * rows * d * d / (t0e.elapsed_time(t1e) / 5 * 1e-3) / 1e12
+            ach = prof["solve_flops"] / (prof["solve_ms"] * 1e-3) / 1e12 if prof["solve_ms"] > 0 else 0.0
+            tensor_roof = {"bound": "tensor", "achieved": ach, "peak": cublas_tf, "unit": "TFLOP/s", "frac": ach / cublas_tf,
+                           "traffic": None, "peak_source": "cuBLAS DGEMM (torch.float64 matmul) of the same shape, measured in this run",
+                           "kernel": "dgemm_dmma_kernel (mma.sync m8n8k4 f64 → DMMA.8x8x4) inside the lock-step solver chains",
+                           "flops_per_solver_pass": prof["solve_flops"] / max(1, prof["solve_launches"]),
+                           "avg_pass_ms": prof["solve_ms"] / max(1, prof["solve_launches"]),
+                           "kernel_share_of_step": prof["solve_ms"] / ms}
         line = {
             "metric": "MUSE sims/sec (MAP+score)", "value": value, "unit": "sims/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {
                 "workload": f"{family} d={d} nsims={args.nsims}{'/GPU' if args.scaling == 'weak' else ' total'} "
-                            f"full solve θ̂/J/H, θ₀={th0.tolist()}, atol={ATOL} (BASELINE configs[2])",
+                            f"full solve θ̂/J/H, θ₀={th0.tolist()}, atol={ATOL} ({cfg_name})",
                 "nsims_total": nsims_total, "outer_iterations": len(res.history),
                 "units_per_step": units_all / args.steps, "l2": "inputs_larger_than_l2 (ξ,ν: %.2f GB per GPU)" % (2 * args.nsims * d * 8 / 1e9 if args.scaling == "weak" else 2 * nsims_total / world * d * 8 / 1e9),
                 "exchange": {"allgathers_per_step": exch_per_step, "wall_ms_per_step_rank0": exch_ms_per_step,
@@ -321,9 +378,13 @@ def run_b200(args):
                          "avg_launch_ms": solve_ms_sum / max(1, prof["solve_launches"] * world),
                          "kernel_share_of_step": solve_ms_sum / world / ms},
         }
-        if world == 1 and not args.no_cpu_baseline:
-            nsims_cpu = args.cpu_sims or 256
-            rate, units, secs, threads = cpu_solve_rate(family, d, nsims_cpu, 0)
+        if tensor_roof is not None:
+            line["roofline"] = tensor_roof
+            line["config"]["l2"] = "inputs_larger_than_l2 (Σ₀⁻¹ 134 MB + batch arrays ≥ 268 MB each at d=4096, nsims=8192)"
+        if world == 1 and not args.no_cpu_baseline and family != "corrgauss":
+            nsims_cpu = cpu_sample_nsims(args)
+            cpu_solve_rate(family, d, nsims_cpu, 0)                       # warm-up (page-in of the host draws)
+            rate, units, secs, threads = cpu_solve_rate(family, d, nsims_cpu, 0, reps=3)
             line["cpu_baseline"] = {
                 "value": rate, "unit": "sims/s", "cores": threads, "kind": "port",
                 "sample": f"full solve (θ̂,J,H) on nsims={nsims_cpu} of the same shape, {units} units in {secs:.2f}s; "

@@ -1,11 +1,17 @@
-"""Model of the device algorithm for F3 (lock-step L-BFGS with ONE P·s product per iteration; line-search trials in
-closed form along the line, quadratic objective) against the oracle's honest L-BFGS."""
-import math, sys, os
+"""Model of the device algorithm for the correlated-Gaussian family (TEST INFRASTRUCTURE ONLY).
+
+csrc/muse_corr.cu advances all units of a pass in lock-step and, because the objective is quadratic, evaluates
+every Hager–Zhang trial of an iteration in closed form from ONE product P·s:
+    φ(α) = f + α g·s + ½α² sᵀ(I + aP)s,   φ′(α) = g·s + α sᵀ(I + aP)s,   ∇f(z + αs) = g + α(s + a P s).
+This module restates that scheme in NumPy so that a CPU test can hold it against the oracle's honest L-BFGS
+(oracle/lbfgs.py: P·z evaluated at every trial point, as the reference's AD-based ``logLike_and_∇z_logLike`` would,
+/root/reference/src/simple.jl:85): same iteration and evaluation counts, same ẑ to round-off."""
+from __future__ import annotations
+
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import oracle as O
-from oracle.lbfgs import _twoloop
-from oracle.hagerzhang import HagerZhang, LineSearchException
+
+from .hagerzhang import HagerZhang, LineSearchException
+from .lbfgs import _twoloop
 
 
 def lockstep(P, a, dth, x, z0, g_tol, m=10, iterations=1000):
@@ -58,23 +64,3 @@ def lockstep(P, a, dth, x, z0, g_tol, m=10, iterations=1000):
     return z, it, fcalls, float(np.max(np.abs(g)))
 
 
-def main():
-    rng = np.random.default_rng(1)
-    for d in (64, 256, 1024):
-        A = rng.standard_normal((d, d)); S0 = A @ A.T / d + 0.1 * np.eye(d)
-        P = np.linalg.inv(S0); L = np.linalg.cholesky(S0)
-        fam = O.CorrGauss(d, P, L)
-        for th in (1.0, 0.0, -1.0):
-            a = math.exp(-th)
-            worst = 0; its = []
-            for k in range(6):
-                x, ztrue = fam.sample([th], rng.standard_normal(d), rng.standard_normal(d))
-                for z0 in (np.zeros(d), ztrue):
-                    ref = O.lbfgs_minimize(lambda z: fam.neg_loglike_and_grad(x, z, [th]), z0, g_tol=1e-2)
-                    z, it, fc, gres = lockstep(P, a, d * th, x, z0, 1e-2)
-                    rel = np.max(np.abs(z - ref.minimizer)) / np.max(np.abs(ref.minimizer))
-                    worst = max(worst, rel)
-                    its.append((ref.iterations, it, ref.f_calls, fc))
-            print(d, th, "worst rel diff %.2e" % worst, "iters/fcalls (ref, model):", its[:4])
-
-main()

@@ -275,3 +275,21 @@ def test_c_port_matches_numpy_oracle():
     np.testing.assert_allclose(res.J, ref.J, rtol=1e-9)
     np.testing.assert_allclose(res.H, ref.H, rtol=1e-7)
     assert units == 2 * 51 + 1 + 2 * 5
+
+
+def test_f3_lockstep_model():
+    """The lock-step, one-product-per-iteration scheme of csrc/muse_corr.cu (oracle/corr_lockstep.py) reproduces
+    the oracle's honest L-BFGS on F3: identical iteration / evaluation counts, ẑ to 1e-12 relative."""
+    from oracle.corr_lockstep import lockstep
+    rng = np.random.default_rng(1)
+    for d in (48, 160):
+        fam = _family("corrgauss", d)
+        for th in (1.0, 0.0, -1.0):
+            for k in range(3):
+                x, ztrue = fam.sample([th], rng.standard_normal(d), rng.standard_normal(d))
+                for z0 in (np.zeros(d), ztrue):
+                    ref = O.lbfgs_minimize(lambda z: fam.neg_loglike_and_grad(x, z, [th]), z0, g_tol=1e-2)
+                    z, it, fc, gres = lockstep(fam.P, math.exp(-th), d * th, x, z0, 1e-2)
+                    assert (it, fc) == (ref.iterations, ref.f_calls)
+                    assert ref.iterations >= 3
+                    np.testing.assert_allclose(z, ref.minimizer, rtol=1e-12, atol=1e-13)
