@@ -98,6 +98,19 @@ int muse_b200_comm_destroy(muse_handle* h) {
     return MUSE_OK;
 }
 
+// after the stream has been synchronised: copy the gathered rows (rank order) out of the pinned receive area
+void muse_comm_unpack(muse_handle* h, int ncol, const int32_t* counts, double* out_host) {
+    const int R = h->comm_nranks;
+    int maxc = 1;
+    for (int r = 0; r < R; ++r) maxc = counts[r] > maxc ? counts[r] : maxc;
+    const size_t need = (size_t)maxc * ncol;
+    size_t off = 0;
+    for (int q = 0; q < R; ++q) {
+        std::memcpy(out_host + off, h->comm_host + (size_t)q * need, (size_t)counts[q] * ncol * sizeof(double));
+        off += (size_t)counts[q] * ncol;
+    }
+}
+
 // gather `counts[q]` rows of `ncol` doubles from every rank q; this rank's rows come from device memory (`src_dev`)
 // or from the host (`src_host`)
 static int allgather_impl(muse_handle* h, const double* src_dev, const double* src_host, int ncol, const int32_t* counts,
@@ -138,14 +151,20 @@ static int allgather_impl(muse_handle* h, const double* src_dev, const double* s
     const ncclResult_t r = a->AllGather(h->comm_send, h->comm_recv, need, ncclDouble, (ncclComm_t)h->comm, h->stream);
     if (r != ncclSuccess) { h->err = std::string("ncclAllGather: ") + a->GetErrorString(r); return MUSE_ECUDA; }
     h->acc.launches += 1;
-    if (cudaMemcpyAsync(h->comm_host, h->comm_recv, need * R * sizeof(double), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
-        cudaStreamSynchronize(h->stream) != cudaSuccess) { h->err = "exchange copy/sync failed"; return MUSE_ECUDA; }
-    size_t off = 0;
-    for (int q = 0; q < R; ++q) {
-        std::memcpy(out_host + off, h->comm_host + (size_t)q * need, (size_t)counts[q] * ncol * sizeof(double));
-        off += (size_t)counts[q] * ncol;
+    if (cudaMemcpyAsync(h->comm_host, h->comm_recv, need * R * sizeof(double), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess) {
+        h->err = "exchange copy failed";
+        return MUSE_ECUDA;
     }
+    if (!out_host) return MUSE_OK;             // enqueue only: the caller synchronises the stream, then unpacks
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess) { h->err = "exchange sync failed"; return MUSE_ECUDA; }
+    muse_comm_unpack(h, ncol, counts, out_host);
     return MUSE_OK;
+}
+
+// enqueue-only variant for the in-library driver: gather on the stream, no synchronisation
+int muse_comm_allgather_scores_enqueue(muse_handle* h, int first_row, const int32_t* counts) {
+    if (h->comm && first_row + counts[h->comm_rank] > h->out_cap) { h->err = "score rows outside the device output buffer"; return MUSE_EINVAL; }
+    return allgather_impl(h, h->g_d + (size_t)first_row * h->cfg.ntheta, nullptr, h->cfg.ntheta, counts, nullptr);
 }
 
 int muse_b200_allgather_scores(muse_handle* h, int32_t first_row, const int32_t* counts, double* out_host) {

@@ -153,7 +153,7 @@ extern "C" int muse_b200_muse_iterate(muse_handle* h, const double* theta0, int3
         if (rc != MUSE_OK) return rc;
         double* gs = out->g_sims_hist + (size_t)row * nsims_total * nt;
         if (multi) {
-            rc = muse_b200_allgather_scores(h, 1, counts, gs);               // the one exchange step
+            rc = muse_comm_allgather_scores_enqueue(h, 1, counts);           // the one exchange step (NCCL on the stream)
             if (rc != MUSE_OK) return rc;
         }
         rc = muse_b200_fetch(h, units, g_local.data(), out->iters_hist + (size_t)row * units, out->fg_hist + (size_t)row * units,
@@ -164,7 +164,8 @@ extern "C" int muse_b200_muse_iterate(muse_handle* h, const double* theta0, int3
                 h->err = "muse!: MAP solution failed with a non-finite objective";
                 return MUSE_ESTATE;
             }
-        if (!multi) std::memcpy(gs, g_local.data() + nt, (size_t)nloc * nt * sizeof(double));
+        if (multi) muse_comm_unpack(h, nt, counts, gs);                       // fetch() has synchronised the stream
+        else std::memcpy(gs, g_local.data() + nt, (size_t)nloc * nt * sizeof(double));
         double* th_row = out->theta_hist + (size_t)row * nt;
         for (int c = 0; c < nt; ++c) {
             double m, v;

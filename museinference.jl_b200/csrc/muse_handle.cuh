@@ -65,6 +65,8 @@ struct muse_handle {
 };
 
 void muse_comm_release(muse_handle* h);
+extern "C" void muse_comm_unpack(muse_handle* h, int ncol, const int32_t* counts, double* out_host);
+extern "C" int  muse_comm_allgather_scores_enqueue(muse_handle* h, int first_row, const int32_t* counts);
 
 // correlated-Gaussian family (muse_corr.cu)
 int  muse_corr_create(muse_handle* h);

@@ -320,3 +320,38 @@ def test_corrgauss_full_muse_matches_oracle():
         np.testing.assert_allclose(res.Sigma, ref.Sigma, rtol=10 * RTOL_EST)
         np.testing.assert_allclose(np.array(res.gs), np.array(ref.gs), rtol=RTOL_SIM)
         prob.close()
+
+
+def test_full_size_c3_closed_form_and_partition_invariance():
+    """BASELINE configs[2] at full size (funnel, d = 65 536, nsims = 2 048, device Philox draws): every per-sim score
+    against the closed form g = ½ e^{-θ} s² ‖x‖² − d/2 with x = e^{θ/2} ξ + ν, iteration counts,
+    and — the size-independent property that makes sharding safe — a handle owning only sims [1000, 1100) of the same
+    seed reproduces those rows bit for bit."""
+    import math
+    import museinference_jl_b200 as m
+    d, n, seed = 65536, 2048, 20261017
+    be = m.B200Backend("funnel", d, n)
+    be.set_data(np.zeros(d))
+    be.seed_draws(seed)
+    th = np.array([0.35])
+    out = be.map_score(th, th, 1e-2, include_data=False, warm_start=0)
+    assert (out["iters"] == 1).all() and (out["fg_evals"] == 3).all() and (out["status"] == 0).all()
+    assert be.profile()["redo_units"] == 0
+    s = 1.0 / (1.0 + math.exp(-th[0]))
+    for lo in range(0, n, 256):                       # closed form from the draws themselves, 256 rows at a time
+        xi, nu = be.get_draws(lo, 256)
+        x = math.exp(0.5 * th[0]) * xi + nu
+        g_ref = 0.5 * math.exp(-th[0]) * s * s * np.einsum("ij,ij->i", x, x) - d / 2
+        np.testing.assert_allclose(out["g"][lo:lo + 256, 0], g_ref, rtol=1e-9)
+    z = be.get_maps(1 + 1234, 1)[0]
+    xi, nu = be.get_draws(1234, 1)
+    np.testing.assert_allclose(z, s * (math.exp(0.5 * th[0]) * xi[0] + nu[0]), rtol=1e-12, atol=1e-15)
+    # J of these scores against the closed form d s²/2 (Monte-Carlo error √(2/N))
+    assert np.var(out["g"][:, 0], ddof=1) == pytest.approx(d * s * s / 2, rel=5 * math.sqrt(2.0 / n))
+    be.close()
+    part = m.B200Backend("funnel", d, 100, sim_offset=1000)
+    part.set_data(np.zeros(d))
+    part.seed_draws(seed)
+    o2 = part.map_score(th, th, 1e-2, include_data=False, warm_start=0)
+    np.testing.assert_array_equal(o2["g"][:, 0], out["g"][1000:1100, 0])
+    part.close()
