@@ -494,22 +494,21 @@ cudaError_t iso_stream_geometry(int d, int ld, int device, Geometry* geo) {
     const int nchunks = (ld + kChunk - 1) / kChunk;
     geo->stream = 1;
     geo->stream_grid = sms;
-    geo->seg_chunks = nchunks >= 4 ? 2 : 1;                   // finest split: 2 chunks (32 KB per row) per segment
+    // A unit is always cut into the same segments (≤ 8 chunks = 128 KB per row each), whatever else is in the
+    // launch: the segment is a node of the fixed reduction tree, so a unit's sums — and with them ẑ and g — do not
+    // depend on how many units a launch holds or on how sims are sharded over GPUs.
+    geo->nseg = (nchunks + 7) / 8;
+    geo->seg_chunks = (nchunks + geo->nseg - 1) / geo->nseg;
     geo->nseg = (nchunks + geo->seg_chunks - 1) / geo->seg_chunks;
     geo->smem_bytes = 4 * 3 * kChunk * 8;                     // ring: 4 stages × 3 rows or 6 stages × 2 rows (192 KB)
     e = cudaFuncSetAttribute(iso_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, geo->smem_bytes);
     return e;
 }
 
-// pass 1 (streaming) + its scalar replay.  A unit is split into segments only as far as needed to give every
-// CTA ≥ ~32 work items to balance dynamically (few units: fiducial solve, finite-difference pass ⇒ fine split).
+// pass 1 (streaming) + its scalar replay
 cudaError_t launch_iso_stream(SolveLaunch& L, const Geometry& geo, cudaStream_t st) {
-    const int nchunks = (L.ld + kChunk - 1) / kChunk;
-    int want = (int)((32LL * geo.stream_grid + L.nitems - 1) / L.nitems);    // segments per unit wanted
-    if (want > geo.nseg) want = geo.nseg;
-    if (want < 1) want = 1;
-    L.seg_chunks = (nchunks + want - 1) / want;
-    L.nseg = (nchunks + L.seg_chunks - 1) / L.seg_chunks;
+    L.seg_chunks = geo.seg_chunks;
+    L.nseg = geo.nseg;
     L.zrows = (L.start_kind == kStartOwn || L.start_kind == kStartShared || L.start_kind == kStartSharedKeep) ? 1 : 0;
     L.stream_stages = L.zrows ? 4 : 6;
     const long long total = (long long)L.nitems * L.nseg;
