@@ -355,3 +355,120 @@ def test_full_size_c3_closed_form_and_partition_invariance():
     o2 = part.map_score(th, th, 1e-2, include_data=False, warm_start=0)
     np.testing.assert_array_equal(o2["g"][:, 0], out["g"][1000:1100, 0])
     part.close()
+
+
+# ------------------------------------------------------------------------------- edge cases and error behaviour
+def test_call_order_and_argument_errors():
+    import museinference_jl_b200 as m
+    be = m.B200Backend("funnel", 100, 4)
+    th = np.array([0.1])
+    with pytest.raises(m.MuseBackendError) as ei:          # no data yet
+        be.map_score(th, th, 1e-2, include_data=True, warm_start=0)
+    assert ei.value.code == -6
+    be.set_data(np.zeros(100))
+    with pytest.raises(m.MuseBackendError) as ei:          # no draws yet
+        be.map_score(th, th, 1e-2, include_data=True, warm_start=0)
+    assert ei.value.code == -6
+    be.seed_draws(1)
+    with pytest.raises(m.MuseBackendError) as ei:          # user start without z₀
+        be.map_score(th, th, 1e-2, include_data=True, warm_start=3)
+    assert ei.value.code == -6
+    with pytest.raises(m.MuseBackendError) as ei:          # range outside the shard
+        be.map_score(th, th, 1e-2, include_data=False, warm_start=0, first_sim=3, count=2)
+    assert ei.value.code == -1
+    with pytest.raises(m.MuseBackendError):                # zero FD step
+        be.fd_jacobian(th, np.array([0.0]), 2, 1e-2)
+    out = be.map_score(th, th, 1e-2, include_data=False, warm_start=0, first_sim=2, count=0)   # empty range is fine
+    assert out["g"].shape == (0, 1)
+    be.close()
+    with pytest.raises(m.MuseBackendError) as ei:          # ntheta / family mismatch is caught at create
+        m.B200Backend("corrgauss", 64, 4)                  # no P, L
+    assert ei.value.code == -1
+
+
+@pytest.mark.parametrize("d,kernel", [(1, 0), (3, 0), (33, 1), (4100, 2)])
+def test_tiny_and_ragged_dimensions(d, kernel):
+    name, nsims = "hiergauss", 5
+    fam, draws, xd = make_inputs(name, d, nsims)
+    prob = O.OracleProblem(fam, xd, draws)
+    be = _backend(name, d, nsims, draws, xd, kernel=kernel)
+    th = theta_start(name)
+    out = be.map_score(th, th, 1e-2, include_data=True, warm_start=0)
+    zs = be.get_maps(0, nsims + 1)
+    for u in range(nsims + 1):
+        x = xd if u == 0 else prob.sample_x_z(u - 1, th)[0]
+        zh, g, soln = O.map_score_unit(prob, x, np.zeros(d), th, 1e-2)
+        np.testing.assert_allclose(out["g"][u], g, rtol=RTOL_SIM, atol=1e-12)
+        np.testing.assert_allclose(zs[u], zh, rtol=RTOL_SIM, atol=1e-12)
+        assert out["iters"][u] == soln.iterations
+    be.close()
+
+
+@pytest.mark.parametrize("d", [512, 6000])
+def test_user_start_vector_and_save_maps(d):
+    import museinference_jl_b200 as m
+    name, nsims = "funnel", 12
+    oprob, fam, draws, xd = oracle_problem(name, d, nsims, prior=O.NormalPrior(0, 3))
+    z0 = np.linspace(-1, 1, d)
+    ref = O.muse(oprob, [1.0], nsims=nsims, z0=z0, save_MAPs=True, maxsteps=3)
+    prob = m.SimpleMuseProblem(xd, name, m.NormalPrior(0, 3))
+    rng = m.BaseDraws(draws.xi, draws.nu, draws.xi_master, draws.nu_master)
+    res = m.muse(prob, [1.0], rng=rng, nsims=nsims, z0=z0, save_MAPs=True, maxsteps=3)
+    assert len(res.history) == len(ref.history)
+    np.testing.assert_allclose(res.theta, ref.theta, rtol=RTOL_EST)
+    for a, b in zip(res.history, ref.history):
+        np.testing.assert_allclose(a["z_dat"], b["z_dat"], rtol=RTOL_SIM, atol=1e-12)
+        np.testing.assert_allclose(a["z_sims"], np.array(b["z_sims"]), rtol=RTOL_SIM, atol=1e-12)
+    prob.close()
+
+
+def test_non_finite_data_is_reported_not_hidden():
+    """A NaN in the data gives a non-finite objective: status NONFINITE for that unit; muse! raises (src/interface.jl:170),
+    get_J!(skip_errors=true) would drop such sims (src/muse.jl:515-521)."""
+    import museinference_jl_b200 as m
+    for d in (512, 6000):
+        fam, draws, xd = make_inputs("funnel", d, 6)
+        xbad = xd.copy()
+        xbad[d // 2] = np.nan
+        be = _backend("funnel", d, 6, draws, xbad)
+        out = be.map_score(np.array([0.3]), np.array([0.3]), 1e-2, include_data=True, warm_start=0)
+        assert out["status"][0] == 4 and (out["status"][1:] == 0).all()
+        be.close()
+        prob = m.SimpleMuseProblem(xbad, "funnel", m.NormalPrior(0, 3))
+        rng = m.BaseDraws(draws.xi, draws.nu, draws.xi_master, draws.nu_master)
+        with pytest.raises((FloatingPointError, m.MuseBackendError)):
+            m.muse(prob, [1.0], rng=rng, nsims=6)
+        prob.close()
+
+
+def test_get_J_top_up_and_resume_on_gpu():
+    import museinference_jl_b200 as m
+    name, d, nsims = "hiergauss", 5000, 30
+    oprob, fam, draws, xd = oracle_problem(name, d, nsims)
+    rng = m.BaseDraws(draws.xi, draws.nu, draws.xi_master, draws.nu_master)
+    prob = m.SimpleMuseProblem(xd, name)
+    th = np.array([0.2, 0.1])
+    res, ref = m.MuseResult(theta=th.copy()), O.MuseResult(theta=th.copy())
+    getJ, getH = getattr(m, "get_J!"), getattr(m, "get_H!")
+    getJ(res, prob, rng=rng, nsims=10)
+    getJ(res, prob, rng=rng, nsims=30)                   # top-up: sims 10..29 only, truth start (src/muse.jl:499-511)
+    O.get_J_bang(ref, oprob, nsims=30)
+    np.testing.assert_allclose(res.J, ref.J, rtol=RTOL_EST)
+    np.testing.assert_allclose(np.array(res.gs), np.array(ref.gs), rtol=RTOL_SIM)
+    getH(res, prob, rng=rng, nsims=5)
+    O.get_H_bang(ref, oprob, nsims=5)
+    np.testing.assert_allclose(res.H, ref.H, rtol=RTOL_EST, atol=RTOL_EST * np.abs(ref.H).max())
+    np.testing.assert_allclose(res.Sigma, ref.Sigma, rtol=10 * RTOL_EST, atol=1e-12)
+    prob.close()
+
+
+def test_corrgauss_iteration_cap_and_status():
+    name, d, nsims = "corrgauss", 128, 4
+    fam, draws, xd = make_inputs(name, d, nsims)
+    import museinference_jl_b200 as m
+    be = m.B200Backend(name, d, nsims, P=fam.P, L=fam.L, max_iters=2)
+    be.set_data(xd)
+    be.set_draws(draws.xi, draws.nu, draws.xi_master, draws.nu_master)
+    out = be.map_score(np.array([-1.0]), np.array([-1.0]), 1e-2, include_data=True, warm_start=0)
+    assert (out["iters"] == 2).all() and (out["status"] == 2).all()      # MAXITER: Optim.converged == false
+    be.close()
