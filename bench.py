@@ -209,6 +209,15 @@ def run_b200(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 backend has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    if world > 1 and os.environ.get("MUSE_BENCH_PIN", "1") == "1":
+        # one slice of the host cores per rank: the rank's thread spins in stream synchronisations between passes and
+        # must not be migrated or share a core with another rank's (16 cores for 8 ranks on the bench box)
+        try:
+            cores = sorted(os.sched_getaffinity(0))
+            per = max(1, len(cores) // world)
+            os.sched_setaffinity(0, set(cores[local_rank * per:(local_rank + 1) * per] or cores))
+        except (AttributeError, OSError):
+            pass
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         pool = m.ShardPool(device=local_rank)

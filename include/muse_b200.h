@@ -151,7 +151,8 @@ int  muse_b200_map_score(muse_handle* h, const double* theta_sim, const double* 
                          double* gnorm_out  /* units: final ‖∇z‖_∞           */,
                          int32_t* status_out/* units: MUSE_STATUS_*          */);
 /* same work enqueued on the stream without a host sync; results stay in device buffers until
- * muse_b200_fetch() copies them out (bench: device-resident timing). */
+ * muse_b200_fetch() copies them out (bench: device-resident timing).  For corrgauss the call returns once the
+ * lock-step rounds have finished (the host counts the active units between rounds); results still wait for fetch. */
 int  muse_b200_map_score_async(muse_handle* h, const double* theta_sim, const double* theta_eval,
                                double atol, int32_t include_data, int32_t warm_start,
                                int32_t first_sim, int32_t count);

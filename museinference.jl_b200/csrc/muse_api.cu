@@ -383,8 +383,7 @@ int muse_b200_seed_draws(muse_handle* h, uint64_t seed) {
         r.cls = 1;
         h->recs.push_back(r);
     }
-    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-    h->have_draws = true;
+    h->have_draws = true;       // no synchronisation: later launches on the stream are ordered behind the generator
     return MUSE_OK;
 }
 

@@ -432,11 +432,7 @@ int corr_solve(muse_handle* h, CorrBatch& b, CorrLaunch& L) {
     SolveLaunch Lq;
     std::memset(&Lq, 0, sizeof(Lq));                  // ev.half_cst = 0: the closed-form issuer returns 2φ
     const int smem = c->ld * (int)sizeof(double);
-    static int smem_set = 0;
-    if (smem > 48 * 1024 && smem > smem_set) {
-        CORR_TRY(h, cudaFuncSetAttribute(corr_iter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        smem_set = smem;
-    }
+    if (smem > 48 * 1024) CORR_TRY(h, cudaFuncSetAttribute(corr_iter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     muse_handle::Rec rec{};
     if (h->prof) {
         CORR_TRY(h, cudaEventCreate(&rec.a));

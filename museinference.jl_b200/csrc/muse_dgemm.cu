@@ -121,12 +121,9 @@ dgemm_dmma_kernel(const double* __restrict__ A, const double* __restrict__ B, do
 cudaError_t launch_dgemm(const double* A, const double* B, double* C, int M, int N, int K, int lda, int ldb, int ldc,
                          cudaStream_t st) {
     if (M % BM || N % BN || K % BK) return cudaErrorInvalidValue;
-    static bool prepared = false;
-    if (!prepared) {
-        cudaError_t e = cudaFuncSetAttribute(dgemm_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
-        if (e != cudaSuccess) return e;
-        prepared = true;
-    }
+    // per launch, not cached: the attribute belongs to the current device's context
+    cudaError_t e = cudaFuncSetAttribute(dgemm_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
+    if (e != cudaSuccess) return e;
     dim3 grid(N / BN, M / BM);
     dgemm_dmma_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(A, B, C, K, lda, ldb, ldc);
     return cudaGetLastError();

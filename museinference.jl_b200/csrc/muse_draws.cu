@@ -37,17 +37,17 @@ __device__ __forceinline__ double u53(uint32_t lo, uint32_t hi) {
     return ((double)v + 0.5) * (1.0 / 9007199254740992.0);
 }
 
+// Grid: x over pairs of a row, y over (row, stream) — no 64-bit index arithmetic in the loop (the first version
+// spent more issue slots on `t / npairs`, `t % npairs` than on the Box–Muller transform: ncu, profiles/README.md).
 __global__ void __launch_bounds__(256)
 philox_draws_kernel(double* __restrict__ xi, double* __restrict__ nu, int rows, int d, int ld,
                     uint32_t k0, uint32_t k1, int64_t sim_offset, int master_row) {
     const int npairs = (d + 1) >> 1;
-    const long long total = (long long)rows * npairs * 2;   // ×2 streams
-    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
-         t += (long long)gridDim.x * blockDim.x) {
-        const int p = (int)(t % npairs);
-        const long long rs = t / npairs;
-        const int stream = (int)(rs & 1);
-        const int row = (int)(rs >> 1);
+    const int p = blockIdx.x * 256 + threadIdx.x;
+    if (p >= npairs) return;
+    for (int rs = blockIdx.y; rs < 2 * rows; rs += gridDim.y) {
+        const int stream = rs & 1;
+        const int row = rs >> 1;
         const uint32_t G = (row == master_row) ? 0xFFFFFFFFu : (uint32_t)(sim_offset + row);
         uint32_t r[4];
         philox4x32_10((uint32_t)p, G, (uint32_t)stream, 0u, k0, k1, r);
@@ -69,12 +69,11 @@ cudaError_t launch_philox_draws(double* xi, double* nu, int rows, int d, int ld,
                                 int64_t sim_offset, int master_row, cudaStream_t st) {
     if (rows <= 0) return cudaSuccess;
     const int npairs = (d + 1) >> 1;
-    const long long total = (long long)rows * npairs * 2;
-    long long blocks = (total + 255) / 256;
-    const long long cap = 148LL * 8 * 16;
-    if (blocks > cap) blocks = cap;
-    philox_draws_kernel<<<(unsigned)blocks, 256, 0, st>>>(xi, nu, rows, d, ld, (uint32_t)(seed & 0xFFFFFFFFu),
-                                                          (uint32_t)(seed >> 32), sim_offset, master_row);
+    // a thread walks several (row, stream) slots of its pair column: set-up (constants, addressing) is paid once
+    const int ny = 2 * rows < 96 ? 2 * rows : 96;
+    dim3 grid((unsigned)((npairs + 255) / 256), (unsigned)ny);
+    philox_draws_kernel<<<grid, 256, 0, st>>>(xi, nu, rows, d, ld, (uint32_t)(seed & 0xFFFFFFFFu),
+                                             (uint32_t)(seed >> 32), sim_offset, master_row);
     return cudaGetLastError();
 }
 

@@ -515,8 +515,10 @@ cudaError_t launch_iso_stream(SolveLaunch& L, const Geometry& geo, cudaStream_t 
     int grid = geo.stream_grid;
     if (grid > total) grid = (int)total;
     if (grid < 1) grid = 1;
+    cudaError_t e = cudaFuncSetAttribute(iso_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, geo.smem_bytes);
+    if (e != cudaSuccess) return e;
     iso_stream_kernel<<<grid, kThreads, geo.smem_bytes, st>>>(L);
-    cudaError_t e = cudaGetLastError();
+    e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     SolveLaunch R = L;
     R.dbg = nullptr;      // the per-CTA rows of the streaming kernel own the diagnostics buffer

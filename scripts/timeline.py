@@ -1,11 +1,12 @@
-"""Controller timeline of one cold + one warm pass (diagnostics; SM clock cycles)."""
+"""Controller timeline of one cold + one warm pass of the GENERIC two-sweep kernel (diagnostics; SM clock cycles).
+The streaming kernel has its own per-CTA timeline: scripts/stream_timeline.py."""
 import os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import museinference_jl_b200 as m
 d = int(os.environ.get("MUSE_D", 65536)); n = int(os.environ.get("MUSE_N", 2048))
 be = m.B200Backend("funnel", d, n, group=int(os.environ.get("MUSE_GROUP", 0)), cluster=int(os.environ.get("MUSE_CLUSTER", 0)),
-                   kernel=int(os.environ.get("MUSE_KERNEL", 0)))
+                   kernel=int(os.environ.get("MUSE_KERNEL", 1)))
 print("geometry", be.geometry())
 be.set_data(np.random.default_rng(0).standard_normal(d)); be.seed_draws(42)
 th0, th1 = np.array([1.0]), np.array([0.45])
