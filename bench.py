@@ -331,11 +331,12 @@ def run_b200(args):
         achieved = (solve_bytes_sum / 1e9) / (solve_ms_sum / 1e3) if solve_ms_sum > 0 else 0.0
         # traffic: dram bytes per solver launch from the committed ncu capture, if present
         traffic = None
-        try:
-            with open(os.path.join(ROOT, "profiles", "r01_solver_traffic.json")) as fh:
-                traffic = json.load(fh).get("dram_bytes_per_launch_avg")
-        except Exception:
-            pass
+        if family == "funnel" and d == D and args.nsims == NSIMS_PER_GPU:     # the capture is of this exact workload
+            try:
+                with open(os.path.join(ROOT, "profiles", "r01_solver_traffic.json")) as fh:
+                    traffic = json.load(fh).get("dram_bytes_per_launch_avg")
+            except Exception:
+                pass
         geo = be.geometry()
         value = units_all / (ms / 1e3)
         cfg_name = {"funnel": "BASELINE configs[2]" if d == 65536 else ("BASELINE configs[1]" if d == 512 else "funnel, custom shape"),
