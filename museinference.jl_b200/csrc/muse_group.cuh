@@ -26,7 +26,11 @@ struct Group {
 
     // controller → workers hand-off: named barrier 1 over the whole CTA (the controller warp and
     // the worker warps arrive from different program locations, which bar.sync permits)
+    // (`bar.sync` is the .aligned form: every lane of a warp must execute it together.  The controller reaches it
+    // right after single-lane code — `if (lane == 0) *scmd = cur;` — so the warp is reconverged first; synccheck
+    // flagged the version without __syncwarp as divergent.)
     static __device__ __forceinline__ void cmd_barrier() {
+        __syncwarp();
         asm volatile("bar.sync 1, %0;" ::"n"(CTA_THREADS) : "memory");
     }
     // end of a sweep that has no reduction: every thread is done with the command slot
