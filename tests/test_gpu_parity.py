@@ -472,3 +472,66 @@ def test_corrgauss_iteration_cap_and_status():
     out = be.map_score(np.array([-1.0]), np.array([-1.0]), 1e-2, include_data=True, warm_start=0)
     assert (out["iters"] == 2).all() and (out["status"] == 2).all()      # MAXITER: Optim.converged == false
     be.close()
+
+
+def test_full_size_c4_hiergauss_closed_form():
+    """BASELINE configs[3] at full size (hierarchical Gaussian, d = 10⁵, nsims = 4 096, θ = (μ, ℓ)): iteration counts of every
+    unit, and both score components of sampled sims against the closed form at the exact MAP
+    ẑ = (x + μ a)/(1 + a), a = e^{−2ℓ}:  g = (a Σ(ẑ−μ), a Σ(ẑ−μ)² − d)."""
+    import math
+    import museinference_jl_b200 as m
+    d, n, seed = 100000, 4096, 7
+    be = m.B200Backend("hiergauss", d, n)
+    be.set_data(np.zeros(d))
+    be.seed_draws(seed)
+    th = np.array([0.5, 0.3])
+    out = be.map_score(th, th, 1e-2, include_data=False, warm_start=0)
+    assert (out["iters"] == 1).all() and (out["fg_evals"] == 3).all() and (out["status"] == 0).all()
+    assert be.profile()["redo_units"] == 0
+    a = math.exp(-2 * th[1])
+    for lo in (0, 1777, 4096 - 64):
+        xi, nu = be.get_draws(lo, 64)
+        x = th[0] + math.exp(th[1]) * xi + nu
+        w = (x + th[0] * a) / (1 + a) - th[0]
+        np.testing.assert_allclose(out["g"][lo:lo + 64, 0], a * w.sum(1), rtol=1e-9, atol=1e-7)
+        np.testing.assert_allclose(out["g"][lo:lo + 64, 1], a * (w * w).sum(1) - d, rtol=1e-9)
+    # warm pass at a moved θ: again one iteration per unit (isotropic Hessian), scores move as the closed form says
+    th2 = np.array([0.45, 0.28])
+    out2 = be.map_score(th2, th2, 1e-2, include_data=False, warm_start=1)
+    assert (out2["iters"] == 1).all() and be.profile()["redo_units"] == 0
+    a2 = math.exp(-2 * th2[1])
+    xi, nu = be.get_draws(100, 8)
+    x = th2[0] + math.exp(th2[1]) * xi + nu
+    w = (x + th2[0] * a2) / (1 + a2) - th2[0]
+    np.testing.assert_allclose(out2["g"][100:108, 1], a2 * (w * w).sum(1) - d, rtol=1e-9)
+    be.close()
+
+
+def test_full_size_c5_corrgauss_properties():
+    """BASELINE configs[4] at full size (dense correlated Gaussian, d = 4 096, nsims = 8 192): every unit stops with
+    ‖∇z‖∞ ≤ atol in a narrow band of iteration counts; for sampled units the returned ẑ satisfies the stationarity
+    residual computed on the host with the full P, and the score equals ½ a ẑᵀPẑ − d/2."""
+    import math
+    import museinference_jl_b200 as m
+    from bench import corr_consts
+    d, n, atol = 4096, 8192, 1e-2
+    P, L = corr_consts(d)
+    be = m.B200Backend("corrgauss", d, n, P=P, L=L)
+    rng = np.random.default_rng(3)
+    xd = L @ rng.standard_normal(d) + rng.standard_normal(d)
+    be.set_data(xd)
+    be.seed_draws(11)
+    th = np.array([0.8])
+    out = be.map_score(th, th, atol, include_data=True, warm_start=0)
+    assert (out["status"] == 0).all() and (out["gnorm"] <= atol).all()
+    assert out["iters"].min() >= 4 and out["iters"].max() - out["iters"].min() <= 3
+    a = math.exp(-th[0])
+    z0 = be.get_maps(0, 1)[0]                                  # the data unit: x is known on the host
+    resid = (z0 - xd) + a * (P @ z0)
+    assert np.abs(resid).max() <= atol * (1 + 1e-6)
+    assert np.abs(resid).max() == pytest.approx(out["gnorm"][0], rel=1e-6)
+    assert out["g"][0, 0] == pytest.approx(0.5 * a * z0 @ (P @ z0) - d / 2, rel=1e-10)
+    zs = be.get_maps(4000, 3)                                  # sims: score from the returned ẑ
+    for k in range(3):
+        assert out["g"][4000 + k, 0] == pytest.approx(0.5 * a * zs[k] @ (P @ zs[k]) - d / 2, rel=1e-10)
+    be.close()
