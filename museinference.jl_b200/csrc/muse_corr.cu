@@ -98,6 +98,52 @@ __device__ __forceinline__ double block_max(double v, double* red) {
     return t;
 }
 
+// y = P·v for ONE vector (P symmetric, row-major, ld × ld): the data unit's product.  Keeping that single row out of
+// the batched GEMM keeps the GEMM at exactly nsims rows (C5: 64 row tiles = 13.8 waves instead of 65 = 14.05 → 15).
+__global__ void __launch_bounds__(256) corr_symv_kernel(const double* __restrict__ P, const double* __restrict__ v,
+                                                        double* __restrict__ y, int ld) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int j = blockIdx.x * 8 + warp;
+    if (j >= ld) return;
+    const double* row = P + (size_t)j * ld;
+    double acc = 0.0;
+    for (int k = 2 * lane; k < ld; k += 64) {
+        const double2 p = *reinterpret_cast<const double2*>(row + k);
+        const double2 x = *reinterpret_cast<const double2*>(v + k);
+        acc = fma(p.x, x.x, acc);
+        acc = fma(p.y, x.y, acc);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) y[j] = acc;
+}
+
+// K values at once: slot k is a max if bit k of MAXMASK is set, else a sum (fixed tree: lane butterfly, warps in order)
+template <int K, unsigned MAXMASK>
+__device__ __forceinline__ void block_reduce(double (&v)[K], double (*red)[4]) {
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const double o = __shfl_xor_sync(0xffffffffu, v[k], off);
+            v[k] = ((MAXMASK >> k) & 1u) ? fmax(v[k], o) : v[k] + o;
+        }
+    const int w = threadIdx.x >> 5;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) red[w][k] = v[k];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        double t = red[0][k];
+#pragma unroll
+        for (int i = 1; i < kCT / 32; ++i) t = ((MAXMASK >> k) & 1u) ? fmax(t, red[i][k]) : t + red[i][k];
+        v[k] = t;
+    }
+}
+
 // ---- pass set-up: x, start vector -------------------------------------------------------------------------
 __global__ void __launch_bounds__(kCT) corr_init_kernel(const CorrLaunch L) {
     const int r = L.row0 + blockIdx.x;
@@ -194,16 +240,16 @@ __global__ void __launch_bounds__(kCT) corr_iter_kernel(const CorrLaunch L, cons
     const double* q = L.b.q + off;
     const int m = L.m;
 
-    double gs = 0, ss = 0, sq = 0;
+    __shared__ double red4[kCT / 32][4];
+    double r3[3] = {0.0, 0.0, 0.0};           // g·s, s·s, s·Q
     for (int j = threadIdx.x; j < L.d; j += kCT) {
-        gs = fma(g[j], s[j], gs);
-        ss = fma(s[j], s[j], ss);
-        sq = fma(s[j], q[j], sq);
+        r3[0] = fma(g[j], s[j], r3[0]);
+        r3[1] = fma(s[j], s[j], r3[1]);
+        r3[2] = fma(s[j], q[j], r3[2]);
     }
-    gs = block_sum(gs, red);
-    ss = block_sum(ss, red);
-    sq = block_sum(sq, red);
-    const double sAs = fma(L.a, sq, ss);
+    block_reduce<3, 0u>(r3, red4);
+    const double gs = r3[0];
+    const double sAs = fma(L.a, r3[2], r3[1]);
 
     // thread 0: reset test, Hager–Zhang on the closed-form line function
     if (threadIdx.x == 0) {
@@ -241,25 +287,23 @@ __global__ void __launch_bounds__(kCT) corr_iter_kernel(const CorrLaunch L, cons
     const int idx = (st.pseudo - 1) % m;
     double* dx = L.b.dxh + idx * hstride + off;
     double* dg = L.b.dgh + idx * hstride + off;
-    double gm = 0, xc = 0, dxdg = 0, dgdg = 0;
+    double r4[4] = {0.0, 0.0, 0.0, 0.0};      // ‖∇f‖∞, max|Δz|, dx·dg, dg·dg
     for (int j = threadIdx.x; j < L.d; j += kCT) {
         const double dxj = alpha * s[j];
         const double dgj = alpha * fma(L.a, q[j], s[j]);
         const double zn = z[j] + dxj;
         const double gn = g[j] + dgj;
-        xc = fmax(xc, fabs(zn - z[j]));
+        r4[1] = fmax(r4[1], fabs(zn - z[j]));
         z[j] = zn;
         g[j] = gn;
         dx[j] = dxj;
         dg[j] = dgj;
-        gm = fmax(gm, fabs(gn));
-        dxdg = fma(dxj, dgj, dxdg);
-        dgdg = fma(dgj, dgj, dgdg);
+        r4[0] = fmax(r4[0], fabs(gn));
+        r4[2] = fma(dxj, dgj, r4[2]);
+        r4[3] = fma(dgj, dgj, r4[3]);
     }
-    gm = block_max(gm, red);
-    xc = block_max(xc, red);
-    dxdg = block_sum(dxdg, red);
-    dgdg = block_sum(dgdg, red);
+    block_reduce<4, 0x3u>(r4, red4);
+    const double gm = r4[0], xc = r4[1], dxdg = r4[2], dgdg = r4[3];
     if (threadIdx.x == 0) {
         const double f_prev = st.f;
         if (flag == 2) {                               // linesearch exception: x moved, optimisation stops
@@ -389,7 +433,7 @@ int alloc_batch(muse_handle* h, CorrBatch& b, int rows) {
     muse_corr_ctx* c = h->corr;
     if (b.rows >= rows) return MUSE_OK;
     free_batch(b);
-    const int mpad = round_up_i(rows, 128);
+    const int mpad = round_up_i(rows, 128) + 128;       // + one tile of slack: GEMM ranges start at any row
     const size_t n = (size_t)mpad * c->ld * sizeof(double), m = (size_t)h->cfg.lbfgs_m;
     CORR_TRY(h, cudaMalloc(&b.x, n));
     CORR_TRY(h, cudaMalloc(&b.z, n));
@@ -406,14 +450,24 @@ int alloc_batch(muse_handle* h, CorrBatch& b, int rows) {
     return MUSE_OK;
 }
 
-// Q[rows] = V[rows]·P over the tile-aligned superset of [row0, row0 + nrows)
-int gemm_rows(muse_handle* h, const CorrBatch& b, const double* V, int row0, int nrows) {
+// Q[rows] = V[rows]·P for rows [row0, row0 + nrows): a DGEMM over that range rounded up to whole row tiles (the
+// rows past the range are scratch: the arrays carry 128 rows of slack), except that a range starting with the data
+// unit (row 0 of the main batch) has that one row done by the symmetric matrix-vector kernel.
+int gemm_rows(muse_handle* h, const CorrBatch& b, const double* V, int row0, int nrows, bool split_first_row) {
     muse_corr_ctx* c = h->corr;
-    const int lo = row0 / 128 * 128, hi = round_up_i(row0 + nrows, 128);
-    const size_t off = (size_t)lo * c->ld;
-    CORR_TRY(h, launch_dgemm(V + off, c->P, b.q + off, hi - lo, c->ld, c->ld, c->ld, c->ld, c->ld, h->stream));
+    if (split_first_row && nrows > 1) {
+        corr_symv_kernel<<<(c->ld + 7) / 8, 256, 0, h->stream>>>(c->P, V + (size_t)row0 * c->ld, b.q + (size_t)row0 * c->ld, c->ld);
+        CORR_TRY(h, cudaGetLastError());
+        h->acc.launches += 1;
+        h->acc.solve_flops += 2.0 * (double)c->ld * c->ld;
+        row0 += 1;
+        nrows -= 1;
+    }
+    const int m = round_up_i(nrows, 128);
+    const size_t off = (size_t)row0 * c->ld;
+    CORR_TRY(h, launch_dgemm(V + off, c->P, b.q + off, m, c->ld, c->ld, c->ld, c->ld, c->ld, h->stream));
     h->acc.launches += 1;
-    h->acc.solve_flops += 2.0 * (hi - lo) * (double)c->ld * c->ld;
+    h->acc.solve_flops += 2.0 * m * (double)c->ld * c->ld;
     return MUSE_OK;
 }
 
@@ -445,7 +499,7 @@ int corr_solve(muse_handle* h, CorrBatch& b, CorrLaunch& L) {
     if (L.start_kind == kStartZero) {
         CORR_TRY(h, cudaMemsetAsync(b.q + (size_t)L.row0 * c->ld, 0, (size_t)L.nrows * c->ld * sizeof(double), h->stream));
     } else {
-        const int rc = gemm_rows(h, b, b.z, L.row0, L.nrows);
+        const int rc = gemm_rows(h, b, b.z, L.row0, L.nrows, L.data_row == L.row0);
         if (rc != MUSE_OK) return rc;
     }
     corr_start_kernel<<<L.nrows, kCT, 0, h->stream>>>(L);
@@ -457,13 +511,13 @@ int corr_solve(muse_handle* h, CorrBatch& b, CorrLaunch& L) {
         CORR_TRY(h, cudaMemcpyAsync(&active, c->active, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         CORR_TRY(h, cudaStreamSynchronize(h->stream));
         if (active <= 0) break;
-        const int rc = gemm_rows(h, b, b.s, L.row0, L.nrows);
+        const int rc = gemm_rows(h, b, b.s, L.row0, L.nrows, L.data_row == L.row0);
         if (rc != MUSE_OK) return rc;
         corr_iter_kernel<<<L.nrows, kCT, smem, h->stream>>>(L, Lq);
         CORR_TRY(h, cudaGetLastError());
         h->acc.launches += 1;
     }
-    const int rc = gemm_rows(h, b, b.z, L.row0, L.nrows);
+    const int rc = gemm_rows(h, b, b.z, L.row0, L.nrows, L.data_row == L.row0);
     if (rc != MUSE_OK) return rc;
     corr_score_kernel<<<L.nrows, kCT, 0, h->stream>>>(L);
     CORR_TRY(h, cudaGetLastError());

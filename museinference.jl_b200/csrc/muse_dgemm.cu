@@ -7,9 +7,9 @@
 // sample_x_z (z = e^{θ/2} L ξ, src/simple.jl:61-65 pattern).
 //
 // How.  tcgen05/TMEM has no f64 kind, so the FP64 tensor path on Blackwell is the warp-level
-// `mma.sync.aligned.m8n8k4.row.col.f64` (SASS: DMMA.8x8x4).  CTA tile 128 × 128 × 16, 8 warps as 2 (M) × 4 (N),
+// `mma.sync.aligned.m8n8k4.row.col.f64` (SASS: DMMA.8x8x4).  CTA tile 128 × 128 × 32, 8 warps as 2 (M) × 4 (N),
 // warp tile 64 × 32 = 8 × 4 MMA tiles (64 accumulator doubles per lane); operands staged in shared memory by a
-// 4-stage `cp.async` (LDGSTS) pipeline; rows padded (A: 20, B: 132 doubles) so that every fragment load is
+// 3-stage `cp.async` (LDGSTS) pipeline; rows padded (A: BK + 4, B: 132 doubles) so that every fragment load is
 // bank-conflict free per half-warp.  All extents are multiples of the tile (the callers allocate padded, zero
 // filled operands), so there is no edge handling.  *Bound: FP64 tensor pipe* — 2·M·N·K flop against
 // 24·(M·K + K·N + M·N)… bytes, ≈ 400 flop/B at the C5 shape.
@@ -19,8 +19,12 @@ namespace muse {
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 16, STAGES = 4;
-constexpr int APAD = BK + 4;      // 20 doubles per A row in shared memory
+#ifndef MUSE_GEMM_BK
+#define MUSE_GEMM_BK 32       // measured (scripts/gemm_variants.sh): BK 32 × 3 stages 32.1 TFLOP/s, 16 × 4: 31.6, 8 × 6: 30.2
+#define MUSE_GEMM_STAGES 3
+#endif
+constexpr int BM = 128, BN = 128, BK = MUSE_GEMM_BK, STAGES = MUSE_GEMM_STAGES;
+constexpr int APAD = BK + 4;      // doubles per A row in shared memory: (BK + 4)·2 ≡ 8 (mod 32) banks
 constexpr int BPAD = BN + 4;      // 132 doubles per B row
 constexpr int A_STAGE = BM * APAD, B_STAGE = BK * BPAD;
 constexpr int GEMM_THREADS = 256;
@@ -57,14 +61,15 @@ dgemm_dmma_kernel(const double* __restrict__ A, const double* __restrict__ B, do
         double* as = As + stage * A_STAGE;
         double* bs = Bs + stage * B_STAGE;
         const int k0 = kt * BK;
+        constexpr int ACH = BK / 2;                    // 16-byte chunks per A row
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {                  // A: 128 rows × 8 chunks of 2 doubles
+        for (int i = 0; i < BM * ACH / GEMM_THREADS; ++i) {        // A: 128 rows × BK/2 chunks of 2 doubles
             const int c = tid + i * GEMM_THREADS;
-            const int r = c >> 3, kc = (c & 7) * 2;
+            const int r = c / ACH, kc = (c % ACH) * 2;
             cp_async16(as + r * APAD + kc, Ag + (size_t)r * lda + k0 + kc);
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {                  // B: 16 rows × 64 chunks
+        for (int i = 0; i < BK * (BN / 2) / GEMM_THREADS; ++i) {   // B: BK rows × 64 chunks
             const int c = tid + i * GEMM_THREADS;
             const int r = c >> 6, nc = (c & 63) * 2;
             cp_async16(bs + r * BPAD + nc, Bg + (size_t)(k0 + r) * ldb + nc);
