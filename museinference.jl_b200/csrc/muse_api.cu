@@ -55,14 +55,16 @@ static int theta_consts(const muse_cfg& c, const double* th_sim, const double* t
 static int ensure_outputs(muse_handle* h, int items) {
     if (items <= h->out_cap) return 0;
     cudaFree(h->out_d); cudaFreeHost(h->out_h);
-    cudaFree(h->gpart); cudaFree(h->redo_items);
+    cudaFree(h->gpart); cudaFree(h->gcount); cudaFree(h->redo_items);
     h->out_d = h->out_h = nullptr;
-    h->gpart = nullptr; h->redo_items = nullptr;
+    h->gpart = nullptr; h->gcount = h->redo_items = nullptr;
     h->out_cap = 0;
     const size_t n = (size_t)items, nt = (size_t)h->cfg.ntheta;
     if (h->geo.stream) {
         CUDA_TRY(h, cudaMalloc(&h->gpart, n * (size_t)h->geo.nseg * 16 * sizeof(double)));
         CUDA_TRY(h, cudaMalloc(&h->redo_items, n * sizeof(int)));
+        CUDA_TRY(h, cudaMalloc(&h->gcount, n * sizeof(int)));
+        CUDA_TRY(h, cudaMemsetAsync(h->gcount, 0, n * sizeof(int), h->stream));
     }
     const size_t n_i = (n + 1) & ~(size_t)1;                       // keep every section 8-byte aligned
     h->out_bytes = n * (nt + 2) * sizeof(double) + 3 * n_i * sizeof(int);
@@ -98,6 +100,7 @@ static void fill_common(muse_handle* h, SolveLaunch& L) {
     L.sbuf = h->sbuf;
     L.xslot = h->xslot;
     L.gpart = h->gpart;
+    L.gcount = h->gcount;
     L.redo_count = h->redo_count;
     L.work_next = h->redo_count + 1;
     L.redo_items = h->redo_items;
@@ -121,8 +124,9 @@ static int launch_solver(muse_handle* h, const SolveLaunch& L, double bytes) {
         CUDA_TRY(h, cudaEventRecord(r.a, h->stream));
     }
     if (h->geo.stream) {
-        // pass 1: single-pass speculative streaming kernel + its scalar replay; pass 2: the generic kernel re-solves
-        // the units pass 1 handed back (device-side list; normally empty, then its CTAs exit at once)
+        // pass 1: single-pass speculative streaming kernel (its finisher warps replay the scalar optimiser on the
+        // sums); pass 2: the generic kernel re-solves the units pass 1 handed back (device-side list; normally empty,
+        // then its CTAs exit at once)
         SolveLaunch S = L;
         if (h->dbg_cap < h->geo.stream_grid) S.dbg = nullptr;   // the streaming kernel stamps per CTA
         CUDA_TRY(h, cudaMemsetAsync(h->redo_count, 0, 2 * sizeof(int), h->stream));
@@ -131,7 +135,7 @@ static int launch_solver(muse_handle* h, const SolveLaunch& L, double bytes) {
         R.item_list = h->redo_items;
         R.item_count = h->redo_count;
         CUDA_TRY(h, launch_iso_solver(R, h->geo, h->stream));
-        h->acc.launches += 3;
+        h->acc.launches += 2;
     } else {
         CUDA_TRY(h, launch_iso_solver(L, h->geo, h->stream));
         h->acc.launches += 1;
@@ -281,7 +285,7 @@ int muse_b200_destroy(muse_handle* h) {
     cudaFree(h->out_d); cudaFreeHost(h->out_h);
     cudaFree(h->zHA); cudaFree(h->zHB);
     cudaFree(h->dbg);
-    cudaFree(h->gpart); cudaFree(h->redo_count); cudaFree(h->redo_items); cudaFree(h->redo_total);
+    cudaFree(h->gpart); cudaFree(h->gcount); cudaFree(h->redo_count); cudaFree(h->redo_items); cudaFree(h->redo_total);
     cudaFree(h->zfidA); cudaFree(h->zfidB); cudaFree(h->zfid_state);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     cudaGetLastError();

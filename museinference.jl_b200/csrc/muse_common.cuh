@@ -93,7 +93,8 @@ struct SolveLaunch {
     int nseg;            // segments per unit
     int zrows;           // 1: a z₀ row is streamed (ring stages hold 3 rows), 0: stages hold 2 rows
     int stream_stages;
-    double* gpart;       // nitems × nseg × 16 partial sums (streaming kernel → replay kernel)
+    double* gpart;       // nitems × nseg × 16 partial sums of the streaming kernel's segments
+    int* gcount;         // nitems arrival counters (zero between launches: the last arrival resets its counter)
     int* redo_count;     // number of units handed to the generic kernel by this launch
     int* work_next;      // dynamic work counter of the streaming kernel (zeroed before every launch)
     unsigned long long* redo_total;   // … since handle creation (diagnostics)

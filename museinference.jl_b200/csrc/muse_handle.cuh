@@ -44,7 +44,7 @@ struct muse_handle {
 
     // streaming kernel: per-(unit, segment) partial sums, arrival counters, hand-back list
     double* gpart = nullptr;
-    int *redo_count = nullptr, *redo_items = nullptr;
+    int *gcount = nullptr, *redo_count = nullptr, *redo_items = nullptr;
     unsigned long long* redo_total = nullptr;
 
     muse_corr_ctx* corr = nullptr;

@@ -216,11 +216,6 @@ struct Controller {
     double com_alpha;      // last committed trial (NaN ⇒ none)
     Red7 com;
     double last_eval_alpha, last_phi, last_dphi;
-    // Streaming kernel (muse_iso_stream.cu): the issuer can only answer the sweeps of the fast path.
-    // Anything else sets `abort`; the unit is then left untouched and re-solved by the generic kernel.
-    bool abort = false;
-    bool spec_mode = false;
-
     __device__ Controller(G& g, const SolveLaunch& l, Issuer& is) : grp(g), L(l), issuer(is) {}
 
     __device__ __forceinline__ void issue(double (&red)[7]) { issuer(cur, red); }
@@ -228,7 +223,6 @@ struct Controller {
     // φ, φ' at step c (Hager–Zhang's ϕdϕ).  Counts one value+gradient evaluation unless the
     // point equals the last one evaluated (NLSolversBase caching semantics).
     __device__ __noinline__ void phidphi(double c, bool commit, double& phi, double& dphi) {
-        if (abort) { phi = dphi = NAN; return; }
         if (pre_valid && c == 1.0) {           // prefetched by the INIT sweep
             pre_valid = false;
             phi = pre_phi;
@@ -526,7 +520,6 @@ struct Controller {
             pseudo_iter += 1;
             double dphi_0;
             if (pseudo_iter > 1) {
-                if (spec_mode) { abort = true; break; }
                 cur.lazy = 0;
                 dphi_0 = twoloop(pseudo_iter, rho, dxdg_h, dgdg_h, alpha_tl);
                 pre_valid = false;
@@ -548,7 +541,6 @@ struct Controller {
             const int ls = hager_zhang(1.0, phi_0, dphi_0, alpha, phi_alpha);   // InitialStatic(alpha = 1)
             stamp(item, 3);
             pre_valid = false;
-            if (abort) break;
 
             const double* zprev = cur.zcur;
             if (alpha == 0.0) {
@@ -593,7 +585,6 @@ struct Controller {
             if (!fin(f) || !fin(gg)) { status = MUSE_STATUS_NONFINITE; break; }
             // update_h! (no observable effect once the loop is about to end)
             if (!converged && iter < L.max_iters) {
-                if (spec_mode) { abort = true; break; }
                 if (alpha == 0.0) {
                     pseudo_iter = 0;                     // dx·dg = 0 ⇒ rho = Inf
                 } else {
@@ -614,10 +605,6 @@ struct Controller {
         }
         if (!converged && !stopped && status == MUSE_STATUS_G_CONVERGED && iter >= L.max_iters)
             status = MUSE_STATUS_MAXITER;
-
-        // a start vector the streaming kernel did not materialise must survive a 0-iteration solve
-        if (spec_mode && iter == 0 && (cur.start_kind == kStartTruth || cur.start_kind == kStartSharedKeep)) abort = true;
-        if (abort) return;
 
         // outputs
         stamp(item, 4);

@@ -13,14 +13,15 @@
 // the secant point z₀ + c·s with c = φ'(0)/(φ'(0) − φ'(1)) = c* up to round-off.  All three are
 // elementwise in (x_j, z₀_j) plus global sums, and only c depends on those sums.  So one sweep
 // evaluates the first two honestly and the third *speculatively* at c_spec = 1/(1+a), committing
-// ẑ = z₀ + c_spec·s as it goes.  The scalar optimiser (the same Controller code as the generic
-// kernel, muse_iso_ctl.cuh) then replays L-BFGS/Hager–Zhang on the reduced sums; when it asks for
-// the committed trial at a step c with |c − c_spec| ≤ 1e-11·c_spec the speculative sums answer it.
-// Any other request (another trial, a second iteration, a start vector that had to be kept …)
-// aborts the unit: nothing of it is published and its index goes to a device-side list that the
-// generic two-sweep kernel re-solves from scratch.  Parity is unaffected: ẑ differs from the
-// non-speculative result by ≤ 1e-11 relative (tests: rtol 1e-8), iteration and evaluation
-// counts are those of the replayed algorithm.
+// ẑ = z₀ + c_spec·s as it goes.  The unit's 15 sums are then run through the scalar optimiser's decisions
+// (fast_replay below: the same tests, in the same order, as Controller::solve / hager_zhang in muse_iso_ctl.cuh,
+// the code the generic kernel executes): initial convergence, φ(1) and the bracket [0, 1], the secant step c, and —
+// iff |c − c_spec| ≤ 1e-11·c_spec — the Wolfe and convergence tests on the speculative sums.  Anything else (another
+// bracket, a rejected trial, a second iteration, a non-finite value after the step, a start vector that had to be
+// kept for a 0-iteration solve …) hands the unit back: nothing of it is published and its index goes to a
+// device-side list that the generic two-sweep kernel, launched right behind, re-solves from the untouched start.
+// Parity is unaffected: ẑ differs from the non-speculative result by ≤ 1e-11 relative (tests: rtol 1e-8), iteration
+// and evaluation counts are those of the algorithm.
 //
 // HBM traffic per unit = the fused floor: read ξ, ν [, z₀], write ẑ (nothing for finite-difference
 // virtual sims, whose ẑ the reference discards too).  x is never materialised.
@@ -32,7 +33,8 @@
 //                      boundaries (bytes in flight per SM = the ring, ~190 KB, independent of registers)
 //   warp 1             finisher: sums the consumer warps' partials in index order, publishes the
 //                      segment's partial to global memory; the CTA that publishes a unit's last
-//                      segment sums the segments in index order and runs the scalar optimiser
+//                      segment sums the segments in index order and replays the optimiser's
+//                      decisions on them (one lane, ≈ 100 FP64 instructions), then writes the outputs
 //   warps 2..17        consumers: wait full[stage], fused elementwise work out of shared memory,
 //                      128-bit coalesced stores of ẑ, arrive empty[stage]; at the end of an item a
 //                      shuffle tree reduces the 15 running sums, which go to the finisher through a
@@ -108,6 +110,9 @@ struct ItemDesc {
     int chunk0, nch;
     int sim;             // rows 0,1 = ξ,ν (else row 0 = x)
     int zk;              // 0: z₀ ≡ 0, 1: z₀ streamed in row 2, 2: z₀ = simulated latent (truth)
+    int start_kind;      // StartKind of the unit
+    int zst_accept;      // ZState of the unit once the committed step is accepted (buffer that holds ẑ)
+    int* zstate_row;     // the unit's zstate cell (null: none)
 };
 
 struct Shared {
@@ -208,40 +213,85 @@ __device__ __forceinline__ void consume_chunk(const double* buf, int base, int l
     }
 }
 
-// issuer of the streaming kernel: answers the fast path's two sweeps from the reduced sums
-struct SpecIssuer {
-    const SolveLaunch& L;
-    double t[kNRed];
-    bool* abort_flag;
-    __device__ SpecIssuer(const SolveLaunch& l) : L(l), abort_flag(nullptr) {}
-    __device__ __noinline__ void operator()(Cmd& cur, double (&red)[7]) {
-        const IsoEval& ev = L.ev;
-        if (cur.op == kOpInit) {
-            red[0] = fma(ev.a, t[rS2_0], t[rR0]);       // e₀ = Σ(x−z)² + a Σ(z−μ)²
-            red[1] = t[rGG0];
-            red[2] = t[rGM0];
-            red[3] = t[rS1_0];
-            red[4] = t[rS2_0];
-            red[5] = fma(ev.a, t[rS2_1], t[rR1]);       // e(z₀+s)
-            red[6] = t[rDP1];
-            return;
-        }
-        if (cur.op == kOpTrial && cur.lazy && cur.commit && fabs(cur.c - ev.cspec) <= kSpecTol * ev.cspec) {
-            red[0] = fma(ev.a, t[rS2T], t[rRT]);
-            red[1] = t[rDPT];
-            red[2] = t[rGGT];
-            red[3] = t[rGMT];
-            red[4] = t[rS1T];
-            red[5] = t[rS2T];
-            red[6] = t[rXC];
-            return;
-        }
-        *abort_flag = true;
-#pragma unroll
-        for (int k = 0; k < 7; ++k) red[k] = NAN;
-    }
+// ---- the scalar optimiser on the fast path, replayed on a unit's 15 sums (one thread) ------------------------------
+// Follows, decision by decision, what Controller::solve / hager_zhang (muse_iso_ctl.cuh — the code the generic kernel
+// runs) do when the first L-BFGS iteration ends the solve:
+//   initial_convergence           non-finite f → stop; ‖∇f(z₀)‖∞ ≤ atol → 0 iterations
+//   HagerZhang, c = 1             φ(1), φ′(1) finite;  φ′(1) ≥ 0 ⇒ bracket [0, 1]                       (B0)
+//   secant²                       c = (a·φ′_b − b·φ′_a)/(φ′_b − φ′_a) with (a, b) = (0, 1); the committed trial at c is the
+//                                 speculated one iff |c − c_spec| ≤ kSpecTol·c_spec; it must satisfy the (approximate) Wolfe conditions
+//   assess_convergence            x unchanged or ‖∇f‖∞ ≤ atol ⇒ done: 1 iteration, 3 evaluations
+// Anything else — another bracket, a rejected secant point, a second iteration, an iteration cap of 0, a non-finite
+// value after the step, a 0-iteration solve whose start vector was not materialised — returns false: the unit is
+// left untouched and the generic kernel solves it from scratch.
+struct FastResult {
+    double f, gmax, s1, s2;
+    int iters, fg, status;
+    bool flip;
 };
 
+__device__ __noinline__ bool fast_replay(const SolveLaunch& L, int start_kind, const double (&t)[kNRed], FastResult& r) {
+    const IsoEval& ev = L.ev;
+    constexpr double delta = 0.1, sigma = 0.9, epsilon = 1e-6;
+    const double f0 = fma(0.5, fma(ev.a, t[rS2_0], t[rR0]), ev.half_cst);
+    const double gg0 = t[rGG0], gmax0 = t[rGM0];
+    r.f = f0; r.gmax = gmax0; r.s1 = t[rS1_0]; r.s2 = t[rS2_0];
+    r.iters = 0; r.fg = 1; r.flip = false;
+    const bool keep_start = (start_kind == kStartTruth || start_kind == kStartSharedKeep);
+    if (!fin(f0) || !fin(gg0)) { r.status = MUSE_STATUS_NONFINITE; return !keep_start; }
+    if (gmax0 <= L.atol) { r.status = MUSE_STATUS_G_CONVERGED; return !keep_start; }
+    if (L.max_iters < 1) return false;
+    // hager_zhang(c = 1, φ₀ = f, φ′₀ = −‖∇f‖²)
+    const double phi_0 = f0, dphi_0 = -gg0;
+    if (dphi_0 >= 0.0 || dphi_0 >= kEpsD * fabs(phi_0)) return false;
+    const double phi_lim = phi_0 + epsilon * fabs(phi_0);
+    const double phi1 = fma(0.5, fma(ev.a, t[rS2_1], t[rR1]), ev.half_cst), dphi1 = t[rDP1];
+    if (!(fin(phi1) && fin(dphi1))) return false;
+    if (!(dphi1 >= 0.0)) return false;                               // B0: bracket (a, b) = (0, 1)
+    const double c = (0.0 * dphi1 - 1.0 * dphi_0) / (dphi1 - dphi_0);    // secant(a, b)
+    if (!(fabs(c - ev.cspec) <= kSpecTol * ev.cspec)) return false;  // the speculated trial is the one asked for
+    const double phic = fma(0.5, fma(ev.a, t[rS2T], t[rRT]), ev.half_cst), dphic = t[rDPT];
+    const bool w1 = (delta * dphi_0 >= (phic - phi_0) / c) && (dphic >= sigma * dphi_0);
+    const bool w2 = ((2 * delta - 1) * dphi_0 >= dphic) && (dphic >= sigma * dphi_0) && (phic <= phi_lim);
+    if (!(w1 || w2)) return false;
+    // the step is taken; assess_convergence
+    const double gg = t[rGGT], gmax = t[rGMT];
+    if (!fin(phic) || !fin(gg)) return false;
+    const bool x_conv = t[rXC] <= 0.0, g_conv = gmax <= L.atol;
+    if (!(x_conv || g_conv)) return false;                           // a second iteration would follow
+    r.f = phic; r.gmax = gmax; r.s1 = t[rS1T]; r.s2 = t[rS2T];
+    r.iters = 1; r.fg = 3; r.flip = true;
+    r.status = g_conv ? MUSE_STATUS_G_CONVERGED : MUSE_STATUS_XF_CONVERGED;
+    return true;
+}
+
+__device__ __forceinline__ void publish_unit(const SolveLaunch& L, const ItemDesc& it, const double (&t)[kNRed]) {
+    FastResult r;
+    if (!fast_replay(L, it.start_kind, t, r)) {
+        L.redo_items[atomicAdd(L.redo_count, 1)] = it.unit;          // hand back to the generic kernel
+        atomicAdd(L.redo_total, 1ULL);
+        return;
+    }
+    const IsoEval& ev = L.ev;
+    double* g = L.g_out + (size_t)it.unit * L.ntheta;
+    if (L.family == MUSE_FAMILY_FUNNEL) {
+        g[0] = 0.5 * ev.a * r.s2 - 0.5 * (double)L.d;                // ∇θ logLike = ½ e^{−θ} Σz² − d/2   (src/simple.jl:66-68)
+    } else {
+        g[0] = ev.a * r.s1;                                          // (e^{−2ℓ} Σ(z−μ), e^{−2ℓ} Σ(z−μ)² − d)
+        g[1] = ev.a * r.s2 - (double)L.d;
+    }
+    L.iters_out[it.unit] = r.iters;
+    L.fg_out[it.unit] = r.fg;
+    L.gnorm_out[it.unit] = r.gmax;
+    L.f_out[it.unit] = r.f;
+    L.status_out[it.unit] = r.status;
+    if (r.flip && it.zstate_row) *it.zstate_row = it.zst_accept;
+}
+
+// unit → pointers (the Controller's own set-up code, muse_iso_ctl.cuh); no sweeps are ever issued through it here
+struct NoIssuer {
+    __device__ void operator()(Cmd&, double (&)[7]) {}
+};
 struct WarpCtx {
     int tid;
 };
@@ -291,8 +341,8 @@ iso_stream_kernel(const __grid_constant__ SolveLaunch L) {
         if (lane == 0) {
             const L2Policy pol = make_policies();
             WarpCtx ctx{0};
-            SpecIssuer dummy(L);
-            Controller<WarpCtx, SpecIssuer> u(ctx, L, dummy);     // only for setup_unit (pointer logic)
+            NoIssuer none;
+            Controller<WarpCtx, NoIssuer> u(ctx, L, none);        // only for setup_unit (pointer logic)
             const double* zshared = u.resolve_zshared();
             const uint64_t zpol = (L.start_kind == kStartShared || L.start_kind == kStartSharedKeep) ? pol.last : pol.first;
             int stage = 0;
@@ -309,9 +359,13 @@ iso_stream_kernel(const __grid_constant__ SolveLaunch L) {
                 }
                 const int wnext = atomicAdd(L.work_next, 1);      // fetched early: its latency hides behind this item
                 const int unit = w / nseg, seg = w % nseg;
-                u.setup_unit(unit, zshared, nullptr);
+                int* zs = u.setup_unit(unit, zshared, nullptr);
                 const Cmd& c = u.cur;
                 it.unit = unit;
+                it.start_kind = c.start_kind;
+                it.zstate_row = zs;
+                it.zst_accept = (c.start_kind == kStartTruth || c.start_kind == kStartSharedKeep) ? kZB
+                                                                                                  : (c.zalt == c.zA ? kZA : kZB);
                 it.seg = seg;
                 it.chunk0 = seg * L.seg_chunks;
                 it.nch = min(L.seg_chunks, nchunks - it.chunk0);
@@ -345,12 +399,13 @@ iso_stream_kernel(const __grid_constant__ SolveLaunch L) {
         for (int i = 0;; ++i) {
             const int slot = i & 1;
             mbar_wait(&sh.part_full[slot], (uint32_t)(i >> 1) & 1u);
-            const int unit = sh.desc[i % kDescRing].unit, seg = sh.desc[i % kDescRing].seg;
+            const ItemDesc& it = sh.desc[i % kDescRing];
+            const int unit = it.unit, seg = it.seg;
             if (unit < 0) break;
             double acc = 0.0;
+            const bool mx = (kMaxMask >> lane) & 1u;
             if (lane < kNRed) {
                 acc = sh.part[slot][0][lane];
-                const bool mx = (kMaxMask >> lane) & 1u;
                 for (int wv = 1; wv < kNCW; ++wv) {
                     const double o = sh.part[slot][wv][lane];
                     acc = mx ? fmax(acc, o) : acc + o;
@@ -358,7 +413,31 @@ iso_stream_kernel(const __grid_constant__ SolveLaunch L) {
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&sh.part_empty[slot]);
-            if (lane < kNRed) L.gpart[((size_t)unit * nseg + seg) * kRedPad + lane] = acc;   // read by iso_replay_kernel
+            if (nseg > 1) {
+                // publish the segment; the CTA that publishes a unit's last segment sums them in index order
+                if (lane < kNRed) __stcg(L.gpart + ((size_t)unit * nseg + seg) * kRedPad + lane, acc);
+                __threadfence();
+                __syncwarp();
+                int last = 0;
+                if (lane == 0) last = atomicAdd(L.gcount + unit, 1) == nseg - 1;
+                last = __shfl_sync(0xffffffffu, last, 0);
+                if (!last) continue;
+                __threadfence();
+                __syncwarp();
+                if (lane < kNRed) {
+                    acc = __ldcg(L.gpart + (size_t)unit * nseg * kRedPad + lane);
+                    for (int sg = 1; sg < nseg; ++sg) {
+                        const double o = __ldcg(L.gpart + ((size_t)unit * nseg + sg) * kRedPad + lane);
+                        acc = mx ? fmax(acc, o) : acc + o;
+                    }
+                }
+                if (lane == 0) L.gcount[unit] = 0;      // ready for the next launch
+            }
+            double t[kNRed];
+#pragma unroll
+            for (int k = 0; k < kNRed; ++k) t[k] = __shfl_sync(0xffffffffu, acc, k);
+            if (lane == 0) publish_unit(L, it, t);
+            __syncwarp();
         }
         if (dbg && lane == 0) dbg[4] = now_ns();
     } else {
@@ -443,46 +522,6 @@ iso_stream_kernel(const __grid_constant__ SolveLaunch L) {
     }
 }
 
-// Scalar replay: one warp per unit sums the unit's segment partials in index order and runs the
-// L-BFGS / Hager–Zhang controller on them (see the file comment).  Accepted units get their outputs
-// and their ẑ buffer flip; the others go to the hand-back list of the generic kernel.
-constexpr int kReplayWarps = 4;
-
-__global__ void __launch_bounds__(kReplayWarps * 32)
-iso_replay_kernel(const __grid_constant__ SolveLaunch L) {
-    const int lane = threadIdx.x & 31;
-    const int unit = blockIdx.x * kReplayWarps + (threadIdx.x >> 5);
-    if (unit >= L.nitems) return;
-    const int nseg = L.nseg;
-    double acc = 0.0;
-    if (lane < kNRed) {
-        const bool mx = (kMaxMask >> lane) & 1u;
-        acc = L.gpart[(size_t)unit * nseg * kRedPad + lane];
-        for (int s = 1; s < nseg; ++s) {
-            const double o = L.gpart[((size_t)unit * nseg + s) * kRedPad + lane];
-            acc = mx ? fmax(acc, o) : acc + o;
-        }
-    }
-    WarpCtx ctx{lane};
-    SpecIssuer issuer(L);
-    Controller<WarpCtx, SpecIssuer> ctl(ctx, L, issuer);
-    issuer.abort_flag = &ctl.abort;
-    ctl.spec_mode = true;
-    ctl.dxh = ctl.dgh = nullptr;
-#pragma unroll
-    for (int k = 0; k < kNRed; ++k) issuer.t[k] = __shfl_sync(0xffffffffu, acc, k);
-    ctl.cur.sbuf = nullptr;
-    ctl.cur.v1 = ctl.cur.v2 = nullptr;
-    ctl.cur.w1 = ctl.cur.w2 = nullptr;
-    ctl.cur.c = 0.0;
-    int* zs = ctl.setup_unit(unit, ctl.resolve_zshared(), nullptr);
-    ctl.solve(unit, zs);
-    if (ctl.abort && lane == 0) {
-        L.redo_items[atomicAdd(L.redo_count, 1)] = unit;
-        atomicAdd(L.redo_total, 1ULL);
-    }
-}
-
 }  // namespace
 
 // Geometry: chunks, segments, ring depth.  One CTA per SM.
@@ -505,7 +544,7 @@ cudaError_t iso_stream_geometry(int d, int ld, int device, Geometry* geo) {
     return e;
 }
 
-// pass 1 (streaming) + its scalar replay
+// pass 1: the streaming kernel
 cudaError_t launch_iso_stream(SolveLaunch& L, const Geometry& geo, cudaStream_t st) {
     L.seg_chunks = geo.seg_chunks;
     L.nseg = geo.nseg;
@@ -518,11 +557,6 @@ cudaError_t launch_iso_stream(SolveLaunch& L, const Geometry& geo, cudaStream_t 
     cudaError_t e = cudaFuncSetAttribute(iso_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, geo.smem_bytes);
     if (e != cudaSuccess) return e;
     iso_stream_kernel<<<grid, kThreads, geo.smem_bytes, st>>>(L);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    SolveLaunch R = L;
-    R.dbg = nullptr;      // the per-CTA rows of the streaming kernel own the diagnostics buffer
-    iso_replay_kernel<<<(L.nitems + kReplayWarps - 1) / kReplayWarps, kReplayWarps * 32, 0, st>>>(R);
     return cudaGetLastError();
 }
 
