@@ -81,29 +81,68 @@ def theta_start(family):
 
 # ----------------------------------------------------------------------------- clocks sampler
 class ClockSampler:
+    """SM clock, power and throttle reasons of one GPU DURING the timed region.  In-process NVML (pynvml) from a
+    sampling thread: an external `nvidia-smi -lms 100` loop cost ≈ 5 % of an 8-rank step on the bench box (it takes
+    driver locks that every rank's launches contend on); `nvidia-smi` remains the fallback when pynvml is missing."""
+
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index=0):
-        self.rows, self.proc, self.index = [], None, index
+    def __init__(self, index=0, period=0.02):
+        self.index, self.period = index, period
+        self.sm, self.mx, self.reasons = [], [], set()
+        self.rows, self.proc, self.thread, self.stop_flag, self.nvml = [], None, None, False, None
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
             self.proc = None
+
+    def _poll(self):
+        nv = self.nvml
+        bits = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
+                self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(self.handle, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                for name, bit in bits.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
 
     def _pump(self):
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=1.0)
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                    "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.25)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
         for r in self.rows:
@@ -119,7 +158,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 # ----------------------------------------------------------------------------- CPU arm
@@ -268,6 +307,11 @@ def run_b200(args):
         res = solve(SIM_SEED)
     be = prob._backend
     sampler = ClockSampler(local_rank)
+    # like timeit: no cyclic-GC pauses inside the timed regions (a 1–2 ms pause in one rank stalls all ranks at the
+    # next exchange; seen as outliers in the per-pass timing of the 8-rank runs)
+    import gc
+    gc.collect()
+    gc.disable()
     sync_all()
     be.profile_reset(True)
     if rank == 0:
@@ -305,6 +349,7 @@ def run_b200(args):
     prof_e = be.profile()
     be.profile_reset(False)
     units_e2e = prof_e["solve_units"]
+    gc.enable()
 
     # ---- reduce over ranks -----------------------------------------------------------------
     if world > 1:
