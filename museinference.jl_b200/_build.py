@@ -12,7 +12,7 @@ SOURCES = ["muse_api.cu", "muse_iso_solver.cu", "muse_iso_stream.cu", "muse_draw
 HEADERS = ["muse_common.cuh", "muse_handle.cuh", "muse_group.cuh", "muse_iso_ctl.cuh", os.path.join("..", "..", "include", "muse_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
-    "-O3", "-lineinfo", "-std=c++17",
+    "-O3", "-lineinfo", "-std=c++17", "--threads", "0",
     "-Xcompiler", "-fPIC", "-shared",
 ]
 
