@@ -248,8 +248,9 @@ int  muse_b200_dgemm_host(const double* A, const double* B, double* C, int32_t M
 int  muse_b200_dgemm_time(int32_t M, int32_t N, int32_t K, int32_t reps, double* ms_per_gemm);
 int  muse_b200_profile_reset(muse_handle* h, int32_t enable);
 int  muse_b200_profile_get(muse_handle* h, muse_profile* out);
-/* diagnostics: per-unit timeline of the solver's controller (16 SM-clock stamps per unit of the last
- * launch).  out == NULL arms the facility for up to `items` units (0 disarms); otherwise copies. */
+/* diagnostics: 16 int64 stamps per row of the last solver launch.  Generic kernel: one row per unit, SM-clock stamps
+ * of its controller.  Streaming kernel: one row per CTA — [start ns, end ns, SM id, producer / finisher / consumers
+ * done ns] (globaltimer).  out == NULL arms the facility for up to `items` rows (0 disarms); otherwise copies. */
 int  muse_b200_debug_timeline(muse_handle* h, int32_t items, int64_t* out);
 /* geometry chosen for the solver: threads per solve group, CTAs per cluster, resident groups */
 int  muse_b200_geometry(muse_handle* h, int32_t* group_threads, int32_t* cluster, int32_t* groups);

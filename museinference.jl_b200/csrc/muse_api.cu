@@ -132,6 +132,7 @@ static int launch_solver(muse_handle* h, const SolveLaunch& L, double bytes) {
         CUDA_TRY(h, cudaMemsetAsync(h->redo_count, 0, 2 * sizeof(int), h->stream));
         CUDA_TRY(h, launch_iso_stream(S, h->geo, h->stream));
         SolveLaunch R = L;
+        R.dbg = nullptr;                  // the diagnostics buffer belongs to the streaming kernel's per-CTA rows
         R.item_list = h->redo_items;
         R.item_count = h->redo_count;
         CUDA_TRY(h, launch_iso_solver(R, h->geo, h->stream));
