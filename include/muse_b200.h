@@ -79,8 +79,9 @@ typedef struct muse_cfg {
     int64_t sim_offset;      /* global index of local simulation 0 */
     int32_t nsims_h;         /* sims of the get_H! shard held as extra draw rows; 0 → the H shard is the
                                 first sims of the local shard (single-GPU default) */
-    int32_t kernel;          /* solver kernels: 0 auto (streaming first when d ≥ 4096), 1 generic two-sweep solver only,
-                                2 single-pass streaming kernel first, generic kernel for what it hands back */
+    int32_t kernel;          /* solver kernels: 0 auto (single-pass kernel first: TMA-ring streaming for d ≥ 4096, warp per
+                                unit below), 1 generic two-sweep solver only, 2 TMA-ring streaming first, 3 warp-per-unit
+                                streaming first; the generic kernel re-solves what the first pass hands back */
     int64_t h_sim_offset;    /* global index of H-shard simulation 0 (used when nsims_h > 0) */
     int32_t lbfgs_m;         /* L-BFGS memory; 0 → 10 (Optim.LBFGS default) */
     int32_t max_iters;       /* 0 → 1000 (Optim.Options default) */

@@ -128,7 +128,7 @@ static int launch_solver(muse_handle* h, const SolveLaunch& L, double bytes) {
         // sums); pass 2: the generic kernel re-solves the units pass 1 handed back (device-side list; normally empty,
         // then its CTAs exit at once)
         SolveLaunch S = L;
-        if (h->dbg_cap < h->geo.stream_grid) S.dbg = nullptr;   // the streaming kernel stamps per CTA
+        if (h->geo.stream != 1 || h->dbg_cap < h->geo.stream_grid) S.dbg = nullptr;   // the TMA-ring kernel stamps per CTA
         CUDA_TRY(h, cudaMemsetAsync(h->redo_count, 0, 2 * sizeof(int), h->stream));
         CUDA_TRY(h, launch_iso_stream(S, h->geo, h->stream));
         SolveLaunch R = L;
@@ -225,13 +225,15 @@ int muse_b200_create(const muse_cfg* cfg, muse_handle** out) {
         return MUSE_OK;
     }
     {
-        // kernel choice: the generic solver's group shape follows d (one warp per unit for
-        // small d, one CTA otherwise); for d ≥ 4096 the streaming kernel runs first and the generic kernel
-        // only re-solves what it hands back.  cfg.kernel: 0 auto, 1 generic only, 2 streaming first (any d).
-        if (cfg->kernel < 0 || cfg->kernel > 2) { h->err = "cfg.kernel must be 0, 1 or 2"; return fail(MUSE_EINVAL); }
+        // kernel choice: a single-pass speculative kernel runs first — the TMA-ring streaming kernel
+        // for d ≥ 4096, its warp-per-unit form below that — and the generic solver (group shape by d: one warp per
+        // unit for small d, one CTA otherwise) only re-solves what the first pass hands back.
+        // cfg.kernel: 0 auto, 1 generic only, 2 TMA-ring streaming first (any d), 3 warp-per-unit streaming first (any d).
+        if (cfg->kernel < 0 || cfg->kernel > 3) { h->err = "cfg.kernel must be 0..3"; return fail(MUSE_EINVAL); }
         CREATE_TRY(iso_solver_geometry(cfg->d, cfg->group, cfg->cluster, cfg->device, &h->geo));
         h->geo.stream = 0;
         if (cfg->kernel == 2 || (cfg->kernel == 0 && cfg->d >= 4096)) CREATE_TRY(iso_stream_geometry(cfg->d, h->ld, cfg->device, &h->geo));
+        else if (cfg->kernel == 3 || cfg->kernel == 0) CREATE_TRY(iso_warp_stream_geometry(cfg->device, &h->geo));
     }
 
     const size_t ld = (size_t)h->ld, rows = (size_t)h->rows, B = sizeof(double);

@@ -108,7 +108,8 @@ struct Geometry {
     int groups;          // resident solve groups (= scratch slots)
     int grid;            // CTAs launched
     // streaming kernel (muse_iso_stream.cu)
-    int stream;          // 1: the single-pass speculative streaming kernel is the first pass of every launch
+    int stream;          // first pass of every launch: 0 none (generic kernel only), 1 streaming kernel (TMA ring),
+                         // 2 warp-per-unit streaming kernel (small d)
     int stream_grid;     // CTAs (one per SM)
     int seg_chunks;      // chunks per segment
     int nseg;            // segments per unit
@@ -118,6 +119,7 @@ struct Geometry {
 cudaError_t launch_iso_solver(const SolveLaunch& L, const Geometry& geo, cudaStream_t st);
 cudaError_t iso_solver_geometry(int d, int want_group, int want_cluster, int device, Geometry* geo);
 cudaError_t iso_stream_geometry(int d, int ld, int device, Geometry* geo);
+cudaError_t iso_warp_stream_geometry(int device, Geometry* geo);
 cudaError_t launch_iso_stream(SolveLaunch& L, const Geometry& geo, cudaStream_t st);
 cudaError_t launch_dgemm(const double* A, const double* B, double* C, int M, int N, int K, int lda, int ldb, int ldc,
                          cudaStream_t st);

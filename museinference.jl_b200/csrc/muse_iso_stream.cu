@@ -213,6 +213,34 @@ __device__ __forceinline__ void consume_chunk(const double* buf, int base, int l
     }
 }
 
+// Warp reduction of the 15 running sums.  Sums: the xor butterfly (16, 8, 4, 2, 1) done "transposed" — at every level
+// a lane keeps half of its slots and ships the other half — 16 shuffles instead of 60, same association tree; slot k
+// ends in lane 2k (`sum_k` of lane 2k).  Maxima (non-negative values): two integer REDUX over the high and low words,
+// result in every lane.
+__device__ __forceinline__ void warp_reduce(const Acc& A, int lane, double& sum_k, double (&mv)[kNRed - kNSum]) {
+    double sv[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) sv[k] = k < kNSum ? A.v[k] : 0.0;
+#pragma unroll
+    for (int half = 8, off = 16; half >= 1; half >>= 1, off >>= 1) {
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int k = 0; k < half; ++k) {
+            const double send = up ? sv[k] : sv[k + half];
+            const double keep = up ? sv[k + half] : sv[k];
+            sv[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    sum_k = sv[0] + __shfl_xor_sync(0xffffffffu, sv[0], 1);
+#pragma unroll
+    for (int k = 0; k < kNRed - kNSum; ++k) {
+        const unsigned hi = (unsigned)__double2hiint(A.v[kNSum + k]), lo = (unsigned)__double2loint(A.v[kNSum + k]);
+        const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+        const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+        mv[k] = __hiloint2double((int)mh, (int)ml);
+    }
+}
+
 // ---- the scalar optimiser on the fast path, replayed on a unit's 15 sums (one thread) ------------------------------
 // Follows, decision by decision, what Controller::solve / hager_zhang (muse_iso_ctl.cuh — the code the generic kernel
 // runs) do when the first L-BFGS iteration ends the solve:
@@ -478,35 +506,12 @@ iso_stream_kernel(const __grid_constant__ SolveLaunch L) {
                 if (lane == 0) mbar_arrive(&sh.empty[stage]);
                 if (++stage == stages) { stage = 0; phase ^= 1u; }
             }
-            // Warp reduction, then the warp's partial goes to the finisher's mailbox.
-            // Sums: the xor butterfly (16, 8, 4, 2, 1) done "transposed" — at every level a lane keeps half of its
-            // slots and ships the other half — 16 shuffles instead of 60, same association tree, slot k ends in
-            // lane 2k.  Maxima (non-negative): two integer REDUX over the high and low words.
-            double sv[16];
-#pragma unroll
-            for (int k = 0; k < 16; ++k) sv[k] = k < kNSum ? A.v[k] : 0.0;
-#pragma unroll
-            for (int half = 8, off = 16; half >= 1; half >>= 1, off >>= 1) {
-                const bool up = (lane & off) != 0;
-#pragma unroll
-                for (int k = 0; k < half; ++k) {
-                    const double send = up ? sv[k] : sv[k + half];
-                    const double keep = up ? sv[k + half] : sv[k];
-                    sv[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-                }
-            }
-            sv[0] += __shfl_xor_sync(0xffffffffu, sv[0], 1);
-            double mv[kNRed - kNSum];
-#pragma unroll
-            for (int k = 0; k < kNRed - kNSum; ++k) {
-                const unsigned hi = (unsigned)__double2hiint(A.v[kNSum + k]), lo = (unsigned)__double2loint(A.v[kNSum + k]);
-                const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
-                const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
-                mv[k] = __hiloint2double((int)mh, (int)ml);
-            }
+            // warp reduction, then the warp's partial goes to the finisher's mailbox
+            double sum_k, mv[kNRed - kNSum];
+            warp_reduce(A, lane, sum_k, mv);
             if (lane == 0) mbar_wait(&sh.part_empty[slot], ((uint32_t)(i >> 1) & 1u) ^ 1u);
             __syncwarp();
-            if (!(lane & 1) && (lane >> 1) < kNSum) sh.part[slot][cw][lane >> 1] = sv[0];
+            if (!(lane & 1) && (lane >> 1) < kNSum) sh.part[slot][cw][lane >> 1] = sum_k;
             if (lane == 0) {
 #pragma unroll
                 for (int k = 0; k < kNRed - kNSum; ++k) sh.part[slot][cw][kNSum + k] = mv[k];
@@ -519,6 +524,93 @@ iso_stream_kernel(const __grid_constant__ SolveLaunch L) {
     if (dbg) {
         __syncthreads();
         if (threadIdx.x == 0) dbg[1] = now_ns();
+    }
+}
+
+// ---- small latent dimension: one warp per unit, same single pass, straight from global memory ---------------------
+// For d below a few thousand a unit is a few KB: no ring, no roles — a warp streams its unit's rows with 128-bit loads
+// (4 pairs per lane in flight), keeps the same 15 sums, reduces them with the same warp tree and lane 0 replays the
+// optimiser's decisions (fast_replay).  Units are dealt round-robin to the grid's warps; a launch of 10⁴ units is one wave.
+constexpr int kWarpCta = 256;
+
+// one unit's sweep by one warp
+template <bool SIM, int ZK>
+__device__ __forceinline__ void warp_unit(const ItemDesc& it, const double* ra, const double* rb, const double* rz, int d,
+                                          const IsoEval& ev, int lane, uint64_t pol, Acc& A) {
+    const int npairs = d >> 1;
+    constexpr int U = 4;
+    for (int p0 = lane; p0 < npairs; p0 += U * 32) {
+        double2 a[U], b[U], z[U];
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            const int p = p0 + k * 32;
+            const bool ok = p < npairs;
+            a[k] = ok ? ld2(ra, p) : make_double2(0.0, 0.0);
+            b[k] = (SIM && ok) ? ld2(rb, p) : make_double2(0.0, 0.0);
+            z[k] = (ZK == 1 && ok) ? ld2(rz, p) : make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            const int p = p0 + k * 32;
+            if (p < npairs) {
+                double2 zt;
+                zt.x = elem3<SIM, ZK>(a[k].x, b[k].x, z[k].x, ev, it.sig, it.mus, A);
+                zt.y = elem3<SIM, ZK>(a[k].y, b[k].y, z[k].y, ev, it.sig, it.mus, A);
+                if (it.zout) st2_stream(it.zout + 2 * (size_t)p, zt, pol);
+            }
+        }
+    }
+    if ((d & 1) && lane == 0) {                               // odd d: the last element
+        const int j = d - 1;
+        const double zt = elem3<SIM, ZK>(ra[j], SIM ? rb[j] : 0.0, ZK == 1 ? rz[j] : 0.0, ev, it.sig, it.mus, A);
+        if (it.zout) it.zout[j] = zt;
+    }
+}
+
+__global__ void __launch_bounds__(kWarpCta, 2)
+iso_warp_stream_kernel(const __grid_constant__ SolveLaunch L) {
+    const int lane = threadIdx.x & 31;
+    const int gw = (blockIdx.x * kWarpCta + threadIdx.x) >> 5, nw = (gridDim.x * kWarpCta) >> 5;
+    const IsoEval ev = L.ev;
+    const L2Policy pol = make_policies();
+    WarpCtx ctx{lane};
+    NoIssuer none;
+    Controller<WarpCtx, NoIssuer> u(ctx, L, none);            // only for setup_unit (pointer logic)
+    const double* zshared = u.resolve_zshared();
+    for (int unit = gw; unit < L.nitems; unit += nw) {
+        int* zs = u.setup_unit(unit, zshared, nullptr);
+        const Cmd& c = u.cur;
+        ItemDesc it;
+        it.unit = unit;
+        it.start_kind = c.start_kind;
+        it.zstate_row = zs;
+        it.zst_accept = (c.start_kind == kStartTruth || c.start_kind == kStartSharedKeep) ? kZB : (c.zalt == c.zA ? kZA : kZB);
+        it.sim = c.xi != nullptr;
+        it.sig = c.smp.sig;
+        it.mus = c.smp.mu;
+        it.zk = (c.start_kind == kStartTruth) ? 2 : (c.zcur ? 1 : 0);
+        it.zout = L.discard_z ? nullptr : c.zalt;
+        const double* ra = it.sim ? c.xi : L.xdat;
+        Acc A;
+#pragma unroll
+        for (int k = 0; k < kNRed; ++k) A.v[k] = 0.0;
+        if (it.sim) {
+            if (it.zk == 0) warp_unit<true, 0>(it, ra, c.nu, c.zcur, L.d, ev, lane, pol.first, A);
+            else if (it.zk == 1) warp_unit<true, 1>(it, ra, c.nu, c.zcur, L.d, ev, lane, pol.first, A);
+            else warp_unit<true, 2>(it, ra, c.nu, c.zcur, L.d, ev, lane, pol.first, A);
+        } else {
+            if (it.zk == 1) warp_unit<false, 1>(it, ra, c.nu, c.zcur, L.d, ev, lane, pol.first, A);
+            else warp_unit<false, 0>(it, ra, c.nu, c.zcur, L.d, ev, lane, pol.first, A);
+        }
+        double sum_k, mv[kNRed - kNSum];
+        warp_reduce(A, lane, sum_k, mv);
+        double t[kNRed];
+#pragma unroll
+        for (int k = 0; k < kNSum; ++k) t[k] = __shfl_sync(0xffffffffu, sum_k, 2 * k);
+#pragma unroll
+        for (int k = 0; k < kNRed - kNSum; ++k) t[kNSum + k] = mv[k];
+        if (lane == 0) publish_unit(L, it, t);
+        __syncwarp();
     }
 }
 
@@ -544,8 +636,17 @@ cudaError_t iso_stream_geometry(int d, int ld, int device, Geometry* geo) {
     return e;
 }
 
-// pass 1: the streaming kernel
+// pass 1: the streaming kernel (geo.stream == 1: TMA ring, one CTA per SM; == 2: one warp per unit, small d)
 cudaError_t launch_iso_stream(SolveLaunch& L, const Geometry& geo, cudaStream_t st) {
+    if (geo.stream == 2) {
+        L.nseg = 1;
+        const int warps_per_cta = kWarpCta / 32;
+        int grid = (L.nitems + warps_per_cta - 1) / warps_per_cta;   // one unit per warp (the loop only runs again beyond 2²⁰ CTAs)
+        if (grid > (1 << 20)) grid = 1 << 20;
+        if (grid < 1) grid = 1;
+        iso_warp_stream_kernel<<<grid, kWarpCta, 0, st>>>(L);
+        return cudaGetLastError();
+    }
     L.seg_chunks = geo.seg_chunks;
     L.nseg = geo.nseg;
     L.zrows = (L.start_kind == kStartOwn || L.start_kind == kStartShared || L.start_kind == kStartSharedKeep) ? 1 : 0;
@@ -558,6 +659,19 @@ cudaError_t launch_iso_stream(SolveLaunch& L, const Geometry& geo, cudaStream_t 
     if (e != cudaSuccess) return e;
     iso_stream_kernel<<<grid, kThreads, geo.smem_bytes, st>>>(L);
     return cudaGetLastError();
+}
+
+// warp-per-unit geometry (small d)
+cudaError_t iso_warp_stream_geometry(int device, Geometry* geo) {
+    int sms = 0;
+    cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (e != cudaSuccess) return e;
+    geo->stream = 2;
+    geo->stream_grid = sms;
+    geo->seg_chunks = 0;
+    geo->nseg = 1;
+    geo->smem_bytes = 0;
+    return cudaSuccess;
 }
 
 }  // namespace muse

@@ -37,14 +37,14 @@ def test_device_philox_matches_oracle():
     be.close()
 
 
-# (family, d, group threads, cluster, kernel): kernel 1 = generic two-sweep solver only, 2 = single-pass streaming
-# kernel first (the default for d ≥ 4096), 0 = auto
+# (family, d, group threads, cluster, kernel): kernel 1 = generic two-sweep solver only, 2 = single-pass TMA-ring streaming
+# kernel first (the default for d ≥ 4096), 3 = its warp-per-unit form first (the default below), 0 = auto
 GEOMS = [
     ("funnel", 512, 0, 0, 0), ("funnel", 513, 0, 0, 0), ("funnel", 512, 256, 1, 1), ("hiergauss", 700, 0, 0, 0),
     ("funnel", 5000, 0, 0, 0), ("hiergauss", 4096, 512, 1, 1), ("funnel", 4098, 512, 2, 1),
     ("funnel", 5000, 256, 1, 2), ("funnel", 5001, 512, 2, 2), ("hiergauss", 9000, 512, 1, 2),
     ("hiergauss", 4097, 0, 0, 0), ("funnel", 20001, 0, 0, 0), ("funnel", 300, 0, 0, 2), ("hiergauss", 70001, 0, 0, 0),
-    ("funnel", 65536, 0, 0, 0),
+    ("funnel", 65536, 0, 0, 0), ("funnel", 600, 32, 0, 1), ("hiergauss", 5001, 0, 0, 3), ("funnel", 2, 0, 0, 3),
 ]
 
 
@@ -93,7 +93,7 @@ def test_map_score_cold_warm_truth(name, d, group, cluster, kernel):
     be.close()
 
 
-@pytest.mark.parametrize("d,kernel", [(512, 0), (6000, 1), (6000, 2)])
+@pytest.mark.parametrize("d,kernel", [(512, 0), (512, 1), (6000, 1), (6000, 2)])
 def test_zero_iteration_warm_start_keeps_previous_map(d, kernel):
     """A start point that already satisfies ‖∇z‖_∞ ≤ atol is returned unchanged (0 iterations)."""
     name, nsims = "funnel", 8
@@ -135,8 +135,8 @@ def test_fd_jacobian_matches_oracle(name, d, kw):
     be.close()
 
 
-@pytest.mark.parametrize("kw", [{}, dict(group=32), dict(group=256, cluster=1, kernel=1), dict(group=256, cluster=2, kernel=1),
-                                dict(kernel=2), dict(group=512, cluster=1, kernel=2)])
+@pytest.mark.parametrize("kw", [{}, dict(group=32), dict(group=32, kernel=1), dict(group=256, cluster=1, kernel=1),
+                                dict(group=256, cluster=2, kernel=1), dict(kernel=2), dict(group=512, cluster=1, kernel=2), dict(kernel=3)])
 def test_history_path_runs_and_stays_at_the_map(kw):
     """atol far below round-off forces iterations ≥ 2: two-loop recursion over the (dx, dg) history,
     direction resets, x/f stagnation exits.  With kernel 2 the streaming kernel cannot finish such a unit:
@@ -151,7 +151,7 @@ def test_history_path_runs_and_stays_at_the_map(kw):
     zs = be.get_maps(0, nsims + 1)
     assert (out["iters"] >= 2).all()
     assert np.isin(out["status"], [0, 1, 3]).all()
-    assert be.profile()["redo_units"] == (nsims + 1 if kw.get("kernel") == 2 else 0)
+    assert be.profile()["redo_units"] == (0 if kw.get("kernel") == 1 else nsims + 1)
     for u in range(nsims + 1):
         x = xd if u == 0 else prob.sample_x_z(u - 1, th)[0]
         np.testing.assert_allclose(zs[u], fam.exact_map(x, th), rtol=1e-12, atol=1e-13)
