@@ -1,5 +1,5 @@
 #!/bin/bash
-# One GPU evidence session: parity tests, bench (both arms), ncu launch list, ncu full captures, timelines.
+# One GPU evidence session: parity tests, bench (both arms, all configs), ncu launch list, ncu full captures, timelines.
 # Usage (from the repo root, under gpurun): bash scripts/gpu_round.sh <tag>
 tag=${1:-rX}
 out=gpurun_out
@@ -8,12 +8,16 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $o
 nproc >> $out/${tag}_gpu.txt
 timeout 900 python -m pytest tests -m gpu -x -q > $out/${tag}_pytest.log 2>&1
 echo "pytest rc=$?" >> $out/${tag}_pytest.log
-timeout 600 python bench.py --steps 40 --warmup 5 > $out/${tag}_bench.json 2> $out/${tag}_bench.err
+timeout 600 python bench.py > $out/${tag}_bench.json 2> $out/${tag}_bench.err
 timeout 600 python bench.py --impl reference --steps 5 --warmup 1 > $out/${tag}_bench_ref.json 2> $out/${tag}_bench_ref.err
+timeout 300 python bench.py --d 512 --nsims 100 --no-cpu-baseline > $out/${tag}_c1.json 2> $out/${tag}_c1.err
+timeout 300 python bench.py --d 512 --nsims 10000 --no-cpu-baseline > $out/${tag}_c2.json 2> $out/${tag}_c2.err
+timeout 300 python bench.py --family hiergauss --d 100000 --nsims 4096 --steps 10 --warmup 3 --no-cpu-baseline > $out/${tag}_c4.json 2> $out/${tag}_c4.err
+timeout 300 python bench.py --family corrgauss --d 4096 --nsims 8192 --steps 3 --warmup 1 > $out/${tag}_c5.json 2> $out/${tag}_c5.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $out/${tag}_launches.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $out/${tag}_bench_under_ncu.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:iso_stream -s 0 -c 4 -o $out/${tag}_stream_full \
-    python scripts/profile_solver.py > $out/${tag}_prof_stream.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:iso_stream -s 4 -c 4 -o $out/${tag}_stream_step_full \
+    python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $out/${tag}_prof_stream.log 2>&1
 MUSE_N=2048 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"dgemm|corr_iter" -s 2 -c 2 -o $out/${tag}_corr_full \
     python scripts/profile_corr.py > $out/${tag}_prof_corr.log 2>&1
 timeout 300 python scripts/stream_timeline.py > $out/${tag}_stream_timeline.log 2>&1
