@@ -171,12 +171,16 @@ def cpu_problem(family, d, nsims):
 
     key = (family, d, nsims)
     if key not in _CPU_PROBLEMS:
-        fam = O.make_family(family, d)
+        if family == "corrgauss":
+            P, L = corr_consts(d)
+            fam = O.make_family(family, d, P=P, L=L)
+        else:
+            fam = O.make_family(family, d)
         rng = np.random.Generator(np.random.Philox(SIM_SEED))
         draws = O.Draws(rng.standard_normal((nsims, d)), rng.standard_normal((nsims, d)),
                         rng.standard_normal(d), rng.standard_normal(d))
-        prior = O.NormalPrior(0, 3) if family == "funnel" else O.FlatPrior()
-        _CPU_PROBLEMS[key] = O.OracleProblem(fam, observed_data(family, d), draws, prior)
+        prior = O.FlatPrior() if family == "hiergauss" else O.NormalPrior(0, 3)
+        _CPU_PROBLEMS[key] = O.OracleProblem(fam, observed_data(family, d, fam.L if family == "corrgauss" else None), draws, prior)
     return _CPU_PROBLEMS[key]
 
 
@@ -201,6 +205,8 @@ def cpu_sample_nsims(args):
     ~4.5 GB of host memory (C3: 2048 × 65536 → 2.1 GB), otherwise as many sims as do."""
     if args.cpu_sims:
         return args.cpu_sims
+    if args.family == "corrgauss":      # 2·d² flop per evaluation, ≈ 20 evaluations per unit: keep the sample to ≈ 10–30 s of CPU work
+        return int(max(8, min(args.nsims, 2.0e11 / (40.0 * args.d * args.d * 2.5))))
     return int(max(16, min(args.nsims, 4.5e9 / (16.0 * args.d))))
 
 
@@ -439,7 +445,7 @@ def run_b200(args):
         if tensor_roof is not None:
             line["roofline"] = tensor_roof
             line["config"]["l2"] = "inputs_larger_than_l2 (Σ₀⁻¹ 134 MB + batch arrays ≥ 268 MB each at d=4096, nsims=8192)"
-        if world == 1 and not args.no_cpu_baseline and family != "corrgauss":
+        if world == 1 and not args.no_cpu_baseline:
             nsims_cpu = cpu_sample_nsims(args)
             cpu_solve_rate(family, d, nsims_cpu, 0)                       # warm-up (page-in of the host draws)
             rate, units, secs, threads = cpu_solve_rate(family, d, nsims_cpu, 0, reps=3)

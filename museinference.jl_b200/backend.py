@@ -198,22 +198,29 @@ class B200Backend:
         """The outer θ loop of muse! inside the library (include/muse_b200.h: muse_b200_muse_iterate)."""
         nt, units, N, K = self.ntheta, self.nsims + 1, int(nsims_total), int(maxsteps)
         t0 = self._theta(theta0)
-        f = lambda *shape: np.zeros(shape)
-        e32 = lambda: np.empty((K, units), dtype=np.int32)          # only rows < n_iter are written and read
-        res = dict(theta_final=f(nt), theta_hist=f(K, nt), g_dat_hist=f(K, nt), g_sims_hist=np.empty((K, N, nt)),
-                   g_like_hist=f(K, nt), g_prior_hist=f(K, nt), h_inv_like_hist=f(K, nt), h_prior_hist=f(K, nt),
-                   h_inv_post_hist=f(K, nt), seconds_hist=f(K), iters_hist=e32(), fg_hist=e32(),
-                   gnorm_hist=np.empty((K, units)), status_hist=e32())
-        o = _capi.muse_iterate_out()
-        for name, arr in res.items():
-            setattr(o, name, _ip(arr) if arr.dtype == np.int32 else _dp(arr))
+        # history buffers are allocated once per (maxsteps, nsims) and reused: the caller copies what it keeps
+        cache = self.__dict__.setdefault("_iterate_bufs", {})
+        if (K, N) not in cache:
+            f = lambda *shape: np.zeros(shape)
+            e32 = lambda: np.empty((K, units), dtype=np.int32)          # only rows < n_iter are written and read
+            res = dict(theta_final=f(nt), theta_hist=f(K, nt), g_dat_hist=f(K, nt), g_sims_hist=np.empty((K, N, nt)),
+                       g_like_hist=f(K, nt), g_prior_hist=f(K, nt), h_inv_like_hist=f(K, nt), h_prior_hist=f(K, nt),
+                       h_inv_post_hist=f(K, nt), seconds_hist=f(K), iters_hist=e32(), fg_hist=e32(),
+                       gnorm_hist=np.empty((K, units)), status_hist=e32())
+            o = _capi.muse_iterate_out()
+            for name, arr in res.items():
+                setattr(o, name, _ip(arr) if arr.dtype == np.int32 else _dp(arr))
+            cache.clear()
+            cache[(K, N)] = (res, o)
+        res, o = cache[(K, N)]
         cnt = np.ascontiguousarray(counts, dtype=np.int32) if counts is not None else None
         pm = self._theta(prior_mean) if prior_mean is not None else None
         ps = self._theta(prior_sigma) if prior_sigma is not None else None
         self._check(self._lib.muse_b200_muse_iterate(self._h, _dp(t0), N, _ip(cnt), K, float(theta_rtol), float(atol),
                                                      float(alpha), int(first_start), _dp(pm), _dp(ps), C.byref(o)))
-        res["n_iter"] = int(o.n_iter)
-        return res
+        out = dict(res)
+        out["n_iter"] = int(o.n_iter)
+        return out
 
     def muse_covariance(self, theta, gs, nsims_h_total: int, counts_h, atol, prior_sigma=None):
         """J, FD Jacobians, H and Σ after the loop (include/muse_b200.h: muse_b200_muse_covariance)."""

@@ -22,6 +22,7 @@ def muse_cpu(prob, theta0, *, nsims, gradz_logLike_atol=1e-2, maxsteps=50, theta
     """Returns (MuseResult, units) where units = MAP+score bodies executed."""
     fam, dr = prob.family, prob.draws
     fid = fam.family_id
+    kw = dict(P=fam.P, L=fam.L) if fid == 3 else {}
     res = MuseResult()
     theta = np.atleast_1d(np.asarray(theta0, dtype=np.float64)).copy()
     hist = res.history
@@ -34,7 +35,7 @@ def muse_cpu(prob, theta0, *, nsims, gradz_logLike_atol=1e-2, maxsteps=50, theta
             if math.sqrt(-(dth @ hist[-1]["H_inv_post"] @ dth)) < theta_rtol:
                 break
         out = cport.map_score(fid, xi, nu, prob.x, theta, theta, gradz_logLike_atol, True, 0 if z is None else 1,
-                              z_start=z, want_z=True, nthreads=nthreads)
+                              z_start=z, want_z=True, nthreads=nthreads, **kw)
         z = out["z"]
         units += nsims + 1
         g_dat, g_sims = out["g"][0], out["g"][1:]
@@ -54,7 +55,7 @@ def muse_cpu(prob, theta0, *, nsims, gradz_logLike_atol=1e-2, maxsteps=50, theta
         nH = max(1, nsims // 10)
         step = 0.1 / np.std(gs, axis=0, ddof=1)
         fo = cport.map_score(fid, dr.xi_master[None], dr.nu_master[None], None, th0, th0, gradz_logLike_atol, False, 0,
-                             want_z=True, nthreads=nthreads)
+                             want_z=True, nthreads=nthreads, **kw)
         units += 1
         zfid = np.repeat(fo["z"], nH, axis=0)
         nt = th0.size
@@ -65,7 +66,7 @@ def muse_cpu(prob, theta0, *, nsims, gradz_logLike_atol=1e-2, maxsteps=50, theta
                 th = th0.copy()
                 th[n] = th0[n] + (0.0 + step[n] * sgn)
                 o = cport.map_score(fid, dr.xi[:nH], dr.nu[:nH], None, th, th0, gradz_logLike_atol, False, 1,
-                                    z_start=zfid, nthreads=nthreads)
+                                    z_start=zfid, nthreads=nthreads, **kw)
                 units += nH
                 gpm.append(o["g"])
             Hs[:, :, n] = ((gpm[0] * -0.5 + 0.0) + gpm[1] * 0.5) / step[n]

@@ -31,6 +31,8 @@ def load():
         lib.muse_oracle_map_score.restype = C.c_int
         lib.muse_oracle_map_score.argtypes = [C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, C.c_double, C.c_int,
                                               C.c_int, _dp, _dp, _ip, _ip, _dp, _ip, C.c_int]
+        lib.muse_oracle_map_score_consts.restype = C.c_int
+        lib.muse_oracle_map_score_consts.argtypes = lib.muse_oracle_map_score.argtypes + [_dp, _dp]
         lib.muse_oracle_max_threads.restype = C.c_int
         _lib = lib
     return _lib
@@ -41,13 +43,13 @@ def max_threads() -> int:
 
 
 def map_score(family_id: int, xi, nu, xdat, theta_sim, theta_eval, atol, include_data, start_mode,
-              z_start=None, want_z=False, nthreads=0):
+              z_start=None, want_z=False, nthreads=0, P=None, L=None):
     """Body of the mapped block (src/muse.jl:169-176 / 508-514) for a batch, on the CPU."""
     lib = load()
     xi = np.ascontiguousarray(xi, dtype=np.float64)
     nu = np.ascontiguousarray(nu, dtype=np.float64)
     nsims, d = xi.shape
-    ntheta = 1 if family_id == 1 else 2
+    ntheta = 2 if family_id == 2 else 1
     units = nsims + (1 if include_data else 0)
     xdat = np.ascontiguousarray(xdat if xdat is not None else np.zeros(d), dtype=np.float64)
     ts = np.ascontiguousarray(np.atleast_1d(theta_sim), dtype=np.float64)
@@ -62,12 +64,16 @@ def map_score(family_id: int, xi, nu, xdat, theta_sim, theta_eval, atol, include
     fg = np.empty(units, dtype=np.int32)
     gnorm = np.empty(units)
     status = np.empty(units, dtype=np.int32)
-    rc = lib.muse_oracle_map_score(family_id, d, nsims, xi.ctypes.data_as(_dp), nu.ctypes.data_as(_dp),
+    Pc = np.ascontiguousarray(P, dtype=np.float64) if P is not None else None
+    Lc = np.ascontiguousarray(L, dtype=np.float64) if L is not None else None
+    rc = lib.muse_oracle_map_score_consts(family_id, d, nsims, xi.ctypes.data_as(_dp), nu.ctypes.data_as(_dp),
                                    xdat.ctypes.data_as(_dp), ts.ctypes.data_as(_dp), te.ctypes.data_as(_dp),
                                    float(atol), int(bool(include_data)), int(start_mode),
                                    z.ctypes.data_as(_dp) if z is not None else None, g.ctypes.data_as(_dp),
                                    iters.ctypes.data_as(_ip), fg.ctypes.data_as(_ip), gnorm.ctypes.data_as(_dp),
-                                   status.ctypes.data_as(_ip), int(nthreads))
+                                   status.ctypes.data_as(_ip), int(nthreads),
+                                   Pc.ctypes.data_as(_dp) if Pc is not None else None,
+                                   Lc.ctypes.data_as(_dp) if Lc is not None else None)
     if rc != 0:
         raise RuntimeError(f"muse_oracle_map_score failed: {rc}")
     return dict(g=g, iters=iters, fg_evals=fg, gnorm=gnorm, status=status, z=z)

@@ -31,16 +31,19 @@
 
 #define FAM_FUNNEL 1
 #define FAM_HIER 2
+#define FAM_CORR 3   /* dense correlated Gaussian: -logLike = ½[Σ(x-z)² + a zᵀPz] + half_cst, P = Σ₀⁻¹ */
 
 typedef struct {
     int family, d;
     double a, mu, half_cst; /* -logLike = ½[Σ(x-z)² + aΣ(z-μ)²] + half_cst */
+    const double* P;        /* FAM_CORR: Σ₀⁻¹, d × d row-major */
+    const double* L;        /* FAM_CORR: chol(Σ₀), lower, d × d row-major */
 } model_t;
 
 static void model_at(model_t* m, int family, int d, const double* th) {
     m->family = family;
     m->d = d;
-    if (family == FAM_FUNNEL) {
+    if (family == FAM_FUNNEL || family == FAM_CORR) {
         m->a = exp(-th[0]);
         m->mu = 0.0;
         m->half_cst = 0.5 * d * th[0];
@@ -51,9 +54,33 @@ static void model_at(model_t* m, int family, int d, const double* th) {
     }
 }
 
+/* g ← P z (dense symmetric mat-vec), returns zᵀPz */
+static double apply_P(const model_t* m, const double* z, double* g) {
+    const int d = m->d;
+    double zPz = 0.0;
+    for (int i = 0; i < d; ++i) {
+        const double* row = m->P + (size_t)i * d;
+        double acc = 0.0;
+        for (int j = 0; j < d; ++j) acc += row[j] * z[j];
+        g[i] = acc;
+        zPz += z[i] * acc;
+    }
+    return zPz;
+}
+
 static double fg(const model_t* m, const double* x, const double* z, double* g) {
     double e = 0.0;
     const double a = m->a, mu = m->mu;
+    if (m->family == FAM_CORR) {
+        const double zPz = apply_P(m, z, g);
+        double rr = 0.0;
+        for (int j = 0; j < m->d; ++j) {
+            const double r = x[j] - z[j];
+            rr += r * r;
+            g[j] = a * g[j] - r;
+        }
+        return 0.5 * (rr + a * zPz) + m->half_cst;
+    }
     for (int j = 0; j < m->d; ++j) {
         const double r = x[j] - z[j], w = z[j] - mu;
         e += r * r + a * w * w;
@@ -62,8 +89,12 @@ static double fg(const model_t* m, const double* x, const double* z, double* g) 
     return 0.5 * e + m->half_cst;
 }
 
-static void score(const model_t* m, const double* z, double* out) {
+static void score(const model_t* m, const double* z, double* out, double* scratch) {
     double s1 = 0.0, s2 = 0.0;
+    if (m->family == FAM_CORR) {                      /* ∇θ logLike = ½ e^{-θ} zᵀPz − d/2 */
+        out[0] = 0.5 * m->a * apply_P(m, z, scratch) - 0.5 * m->d;
+        return;
+    }
     for (int j = 0; j < m->d; ++j) {
         const double w = z[j] - m->mu;
         s1 += w;
@@ -386,7 +417,13 @@ static void* worker(void* arg) {
         } else {
             const double *xk = J->xi + (size_t)k * d, *nk = J->nu + (size_t)k * d;
             for (int j = 0; j < d; ++j) {
-                const double zt = J->smu + J->sig * xk[j];
+                double base = xk[j];
+                if (J->family == FAM_CORR) {          /* z = e^{θ/2} L ξ */
+                    const double* row = J->mdl.L + (size_t)j * d;
+                    base = 0.0;
+                    for (int c = 0; c <= j; ++c) base += row[c] * xk[c];
+                }
+                const double zt = J->smu + J->sig * base;
                 x[j] = zt + nk[j];
                 if (J->start_mode == 2) w->x[j] = zt;
             }
@@ -397,7 +434,7 @@ static void* worker(void* arg) {
         int fc = 0, st = 0;
         double gres = 0.0;
         const int it = lbfgs(w, &J->mdl, xs, J->atol, 1000, &fc, &gres, &st);
-        score(&J->mdl, w->x, J->g_out + (size_t)u * J->ntheta);
+        score(&J->mdl, w->x, J->g_out + (size_t)u * J->ntheta, x);
         if (J->z_inout) memcpy(J->z_inout + (size_t)u * d, w->x, sizeof(double) * d);
         if (J->iters_out) J->iters_out[u] = it;
         if (J->fg_out) J->fg_out[u] = fc;
@@ -414,22 +451,39 @@ int muse_oracle_max_threads(void) {
     return n > 0 ? (int)n : 1;
 }
 
+int muse_oracle_map_score_consts(int family, int d, int nsims, const double* xi, const double* nu, const double* xdat,
+                                 const double* theta_sim, const double* theta_eval, double atol, int include_data,
+                                 int start_mode, double* z_inout, double* g_out, int* iters_out, int* fg_out,
+                                 double* gnorm_out, int* status_out, int nthreads, const double* P, const double* L);
+
 int muse_oracle_map_score(int family, int d, int nsims, const double* xi, const double* nu, const double* xdat,
                           const double* theta_sim, const double* theta_eval, double atol, int include_data,
                           int start_mode, double* z_inout, double* g_out, int* iters_out, int* fg_out,
                           double* gnorm_out, int* status_out, int nthreads) {
-    if (family != FAM_FUNNEL && family != FAM_HIER) return -5;
+    return muse_oracle_map_score_consts(family, d, nsims, xi, nu, xdat, theta_sim, theta_eval, atol, include_data, start_mode,
+                                        z_inout, g_out, iters_out, fg_out, gnorm_out, status_out, nthreads, NULL, NULL);
+}
+
+/* same, with the constants of the correlated-Gaussian family (P = Σ₀⁻¹, L = chol Σ₀; NULL for the other families) */
+int muse_oracle_map_score_consts(int family, int d, int nsims, const double* xi, const double* nu, const double* xdat,
+                                 const double* theta_sim, const double* theta_eval, double atol, int include_data,
+                                 int start_mode, double* z_inout, double* g_out, int* iters_out, int* fg_out,
+                                 double* gnorm_out, int* status_out, int nthreads, const double* P, const double* L) {
+    if (family != FAM_FUNNEL && family != FAM_HIER && family != FAM_CORR) return -5;
+    if (family == FAM_CORR && (!P || !L)) return -1;
     job_t J;
     memset(&J, 0, sizeof(J));
     J.family = family; J.d = d; J.nsims = nsims;
-    J.ntheta = family == FAM_FUNNEL ? 1 : 2;
+    J.ntheta = family == FAM_HIER ? 2 : 1;
     J.include_data = include_data ? 1 : 0;
     J.units = nsims + J.include_data;
     J.start_mode = start_mode;
     J.xi = xi; J.nu = nu; J.xdat = xdat; J.atol = atol;
     model_at(&J.mdl, family, d, theta_eval);
-    J.sig = family == FAM_FUNNEL ? exp(0.5 * theta_sim[0]) : exp(theta_sim[1]);
-    J.smu = family == FAM_FUNNEL ? 0.0 : theta_sim[0];
+    J.mdl.P = P;
+    J.mdl.L = L;
+    J.sig = family == FAM_HIER ? exp(theta_sim[1]) : exp(0.5 * theta_sim[0]);
+    J.smu = family == FAM_HIER ? theta_sim[0] : 0.0;
     J.z_inout = z_inout; J.g_out = g_out; J.gnorm_out = gnorm_out;
     J.iters_out = iters_out; J.fg_out = fg_out; J.status_out = status_out;
     atomic_init(&J.next, 0);

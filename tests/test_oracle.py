@@ -293,3 +293,24 @@ def test_f3_lockstep_model():
                     assert (it, fc) == (ref.iterations, ref.f_calls)
                     assert ref.iterations >= 3
                     np.testing.assert_allclose(z, ref.minimizer, rtol=1e-12, atol=1e-13)
+
+
+def test_c_port_correlated_gaussian():
+    """The C port's F3 (dense P·z mat-vec per evaluation, L·ξ sampling) against the NumPy oracle."""
+    from oracle import cport, cmuse
+    cport.build()
+    fam, draws, xd = make_inputs("corrgauss", 96, 9)
+    prob = O.OracleProblem(fam, xd, draws)
+    th = np.array([0.6])
+    out = cport.map_score(3, draws.xi, draws.nu, xd, th, th, 1e-2, True, 0, want_z=True, nthreads=2, P=fam.P, L=fam.L)
+    for u in range(10):
+        x = xd if u == 0 else prob.sample_x_z(u - 1, th)[0]
+        zh, g, soln = O.map_score_unit(prob, x, np.zeros(96), th, 1e-2)
+        assert out["iters"][u] == soln.iterations and out["fg_evals"][u] == soln.f_calls
+        np.testing.assert_allclose(out["g"][u], g, rtol=1e-9)
+        np.testing.assert_allclose(out["z"][u], zh, rtol=1e-9, atol=1e-12)
+    oprob, *_ = oracle_problem("corrgauss", 64, 30, prior=O.NormalPrior(0, 3))
+    ref = O.muse(oprob, [1.0], nsims=30, get_covariance=True)
+    res, units = cmuse.muse_cpu(oprob, [1.0], nsims=30)
+    np.testing.assert_allclose(res.theta, ref.theta, rtol=1e-8)
+    np.testing.assert_allclose(res.H, ref.H, rtol=1e-6)
