@@ -535,3 +535,35 @@ def test_full_size_c5_corrgauss_properties():
     for k in range(3):
         assert out["g"][4000 + k, 0] == pytest.approx(0.5 * a * zs[k] @ (P @ zs[k]) - d / 2, rel=1e-10)
     be.close()
+
+
+@pytest.mark.parametrize("name,d,kernel", [("funnel", 4500, 2), ("hiergauss", 4500, 2), ("funnel", 700, 3), ("hiergauss", 701, 3)])
+def test_single_pass_kernels_agree_with_generic_solver_over_random_regimes(name, d, kernel):
+    """The straight-line replay of the optimiser's decisions (fast_replay) against the generic kernel, which runs the
+    full Controller: random θ (a = e^{−θ} from 3·10⁻⁴ to 3·10³), tolerances from 10⁻¹ down to 10⁻¹⁸ (below round-off), cold /
+    warm / truth starts.  Whatever path a unit takes (accepted by the single pass or handed back), scores and ẑ must agree to
+    1e-9 and — for tolerances above round-off — iteration and evaluation counts and statuses must be identical."""
+    nsims = 6
+    fam, draws, xd = make_inputs(name, d, nsims)
+    rng = np.random.default_rng(d + kernel)
+    a = _backend(name, d, nsims, draws, xd, kernel=kernel)
+    b = _backend(name, d, nsims, draws, xd, kernel=1)
+    handed_back = 0
+    for trial in range(24):
+        th = rng.uniform(-8, 8, size=fam.ntheta) if name == "funnel" else np.array([rng.uniform(-2, 2), rng.uniform(-4, 4)])
+        atol = 10.0 ** rng.uniform(-18, -1)
+        ws = int(rng.integers(0, 3)) if trial else 0
+        kw = dict(include_data=(ws != 2), warm_start=ws)
+        oa, ob = a.map_score(th, th, atol, **kw), b.map_score(th, th, atol, **kw)
+        if atol >= 1e-12:       # below round-off the counts depend on the last bits of the (warm) start: only values are compared
+            np.testing.assert_array_equal(oa["iters"], ob["iters"], err_msg=f"trial {trial} θ={th} atol={atol} ws={ws}")
+            np.testing.assert_array_equal(oa["fg_evals"], ob["fg_evals"])
+            np.testing.assert_array_equal(oa["status"], ob["status"])
+        np.testing.assert_allclose(oa["g"], ob["g"], rtol=1e-9, atol=1e-9 * d)
+        za, zb = a.get_maps(0, nsims + 1), b.get_maps(0, nsims + 1)
+        np.testing.assert_allclose(za, zb, rtol=1e-9, atol=1e-12)
+        handed_back = a.profile()["redo_units"]
+    assert handed_back > 0          # some regimes (tolerances below round-off) must have gone through the hand-back
+    assert b.profile()["redo_units"] == 0
+    a.close()
+    b.close()
