@@ -49,7 +49,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
-    ap.add_argument("--d", type=int, default=D)
+    ap.add_argument("--d", "--dim", dest="d", type=int, default=D, help="latent dimension (use --dim under torchrun: its parser finds --d ambiguous)")
     ap.add_argument("--nsims", type=int, default=NSIMS_PER_GPU, help="sims per GPU (weak) or in total (strong)")
     ap.add_argument("--family", default="funnel", choices=["funnel", "hiergauss", "corrgauss"])
     ap.add_argument("--group", type=int, default=0)
