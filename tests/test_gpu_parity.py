@@ -567,3 +567,26 @@ def test_single_pass_kernels_agree_with_generic_solver_over_random_regimes(name,
     assert b.profile()["redo_units"] == 0
     a.close()
     b.close()
+
+
+def test_corrgauss_unit_results_do_not_depend_on_the_shard():
+    """A handle owning sims [200, 400) reproduces, bit for bit, those units of a 400-sim handle with the same seed
+    (Philox keyed by the global sim index; per-row GEMM and reduction orders do not depend on the batch)."""
+    import museinference_jl_b200 as m
+    name, d, n = "corrgauss", 256, 400
+    fam = make_inputs(name, d, 1)[0]
+    x = np.random.default_rng(0).standard_normal(d)
+    th = np.array([1.0])
+    outs, zs = [], []
+    for kw, rows in ((dict(nsims=n), (201, 200)), (dict(nsims=200, sim_offset=200), (1, 200))):
+        be = m.B200Backend(name, d, kw.pop("nsims"), P=fam.P, L=fam.L, **kw)
+        be.set_data(x)
+        be.seed_draws(7)
+        o = be.map_score(th, th, 1e-2, include_data=True, warm_start=0)
+        o2 = be.map_score(th - 0.2, th - 0.2, 1e-2, include_data=True, warm_start=1)
+        outs.append((o["g"][0], o["g"][rows[0]:rows[0] + rows[1]], o2["g"][rows[0]:rows[0] + rows[1]], o2["iters"][rows[0]:rows[0] + rows[1]]))
+        zs.append(be.get_maps(*rows))
+        be.close()
+    for a, b in zip(outs[0], outs[1]):
+        np.testing.assert_array_equal(a, b)
+    np.testing.assert_array_equal(zs[0], zs[1])
