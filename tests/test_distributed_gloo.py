@@ -82,6 +82,59 @@ def test_two_rank_gloo_matches_single_process(name, d, nsims):
     np.testing.assert_array_equal(outs[0][3], outs[1][3])
 
 
+def _worker_topup(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    import museinference_jl_b200 as m
+    from fake_backend import FakeBackend
+    from helpers import oracle_problem
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        oprob, fam, draws, xd = oracle_problem("hiergauss", 48, 21)
+        prob = m.SimpleMuseProblem(xd, "hiergauss", backend_factory=FakeBackend)
+        pool = m.ShardPool()
+        rng = m.BaseDraws(draws.xi, draws.nu, draws.xi_master, draws.nu_master)
+        res = m.MuseResult(theta=np.array([0.2, 0.1]))
+        getJ, getH = getattr(m, "get_J!"), getattr(m, "get_H!")
+        getJ(res, prob, rng=rng, nsims=8, pool=pool)
+        getJ(res, prob, rng=rng, nsims=21, pool=pool)           # top-up across the shard boundary (src/muse.jl:499-506)
+        getH(res, prob, rng=rng, nsims=5, pool=pool)
+        q.put((rank, np.array(res.gs), res.J, res.H, res.Sigma))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_get_J_top_up_and_get_H():
+    """get_J! called twice (8, then 21 sims) and get_H! on two gloo ranks against the single-process oracle: the top-up
+    only simulates the missing sims, whichever rank owns them, and every rank ends with the same gs, J, H, Σ."""
+    import torch.multiprocessing as mp
+    import oracle as O
+    from helpers import oracle_problem
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_topup, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    outs = sorted([q.get(timeout=240) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    oprob, *_ = oracle_problem("hiergauss", 48, 21)
+    ref = O.MuseResult(theta=np.array([0.2, 0.1]))
+    O.get_J_bang(ref, oprob, nsims=21)
+    O.get_H_bang(ref, oprob, nsims=5)
+    for rank, gs, J, H, Sigma in outs:
+        assert gs.shape == (21, 2)
+        np.testing.assert_allclose(gs, np.array(ref.gs), rtol=1e-12)
+        np.testing.assert_allclose(J, ref.J, rtol=1e-12)
+        np.testing.assert_allclose(H, ref.H, rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(Sigma, ref.Sigma, rtol=1e-9)
+    np.testing.assert_array_equal(outs[0][1], outs[1][1])
+
+
 def test_block_partition():
     import museinference_jl_b200 as m
     assert m.block_partition(10, 4) == ([0, 3, 6, 8], [3, 3, 2, 2])
