@@ -107,6 +107,20 @@ typedef struct muse_profile {
     double  solve_flops;     /* FP64 tensor-core flops of the solver launches (corrgauss: 2·rows·d² per product) */
 } muse_profile;
 
+/* the same solver figures split by the kind of pass (cold pass, warm pass, …) */
+#define MUSE_PASS_COLD      0   /* start = zero(z): muse! iteration 1                      src/muse.jl:151, 169-176 */
+#define MUSE_PASS_WARM      1   /* start = previous ẑ or user z₀: muse! iterations ≥ 2     src/muse.jl:169, 181     */
+#define MUSE_PASS_TRUTH     2   /* start = simulated z: get_J!                             src/muse.jl:508-514      */
+#define MUSE_PASS_FIDUCIAL  3   /* get_H! fiducial solve of the master draw                src/muse.jl:417-423      */
+#define MUSE_PASS_FD        4   /* get_H! finite-difference virtual sims                   src/muse.jl:426-433      */
+#define MUSE_PASS_KINDS     5
+typedef struct muse_pass_profile {
+    int64_t launches[MUSE_PASS_KINDS];
+    double  ms[MUSE_PASS_KINDS];      /* summed device time (CUDA events on the launch stream) */
+    double  units[MUSE_PASS_KINDS];   /* MAP+score units */
+    double  bytes[MUSE_PASS_KINDS];   /* algorithmic bytes */
+} muse_pass_profile;
+
 int  muse_b200_abi_version(void);
 
 /* lifetime ------------------------------------------------------------------------------- */
@@ -190,6 +204,17 @@ int  muse_b200_fd_jacobian(muse_handle* h, const double* theta0, const double* s
                            double* Hs_out /* nsims_H × ntheta × ntheta */,
                            int32_t* status_out /* nsims_H × ntheta × 2, may be NULL */);
 
+/* The same launch sequence with the raw scores returned and arbitrary sample points: row 2n / 2n+1 of theta_sims is the
+ * "−" / "+" point at which the sims of Jacobian column n are generated (src/muse.jl:430); MAP and score are taken at
+ * theta_eval (:431-432).  g_out[k][2n+s][i] = g_i of sim k at point (n, s).  This is what a host needs when θ lives in a
+ * bounded domain (transform_θ / inv_transform_θ, src/interface.jl:14-28): the reference perturbs the UNtransformed θ₀
+ * (src/muse.jl:428-432, src/util.jl:15), so the points are not symmetric in the kernels' unconstrained parameters and
+ * the host forms sum(fs .* [-1/2, 0, 1/2]) / step and the change of variables itself. */
+int  muse_b200_fd_scores(muse_handle* h, const double* theta_eval, const double* theta_sims /* 2·ntheta × ntheta */,
+                         int32_t nsims_H, double atol,
+                         double* g_out /* nsims_H × 2·ntheta × ntheta */,
+                         int32_t* status_out /* nsims_H × 2·ntheta, may be NULL */);
+
 /* The outer loop of muse! (src/muse.jl:159-236) for the common configuration — constant α, regularize = identity,
  * H⁻¹_update = :sims, prior flat or independent Normal(mean, sigma) per component — run inside the library so that
  * no interpreter sits between two passes: per iteration one map_score pass (data + local sims, start zeros / user z₀
@@ -249,6 +274,7 @@ int  muse_b200_dgemm_host(const double* A, const double* B, double* C, int32_t M
 int  muse_b200_dgemm_time(int32_t M, int32_t N, int32_t K, int32_t reps, double* ms_per_gemm);
 int  muse_b200_profile_reset(muse_handle* h, int32_t enable);
 int  muse_b200_profile_get(muse_handle* h, muse_profile* out);
+int  muse_b200_profile_passes(muse_handle* h, muse_pass_profile* out);
 /* diagnostics: 16 int64 stamps per row of the last solver launch.  Generic kernel: one row per unit, SM-clock stamps
  * of its controller.  Streaming kernel: one row per CTA — [start ns, end ns, SM id, producer / finisher / consumers
  * done ns] (globaltimer).  out == NULL arms the facility for up to `items` rows (0 disarms); otherwise copies. */

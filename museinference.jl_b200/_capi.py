@@ -46,6 +46,13 @@ class muse_profile(C.Structure):
     ]
 
 
+PASS_KINDS = ("cold", "warm", "truth", "fiducial", "fd")      # MUSE_PASS_* of include/muse_b200.h
+
+
+class muse_pass_profile(C.Structure):
+    _fields_ = [("launches", C.c_int64 * 5), ("ms", C.c_double * 5), ("units", C.c_double * 5), ("bytes", C.c_double * 5)]
+
+
 class muse_iterate_out(C.Structure):
     _fields_ = [
         ("n_iter", C.c_int32), ("theta_final", c_double_p), ("theta_hist", c_double_p), ("g_dat_hist", c_double_p),
@@ -90,11 +97,13 @@ SIGNATURES = {
     "muse_b200_muse_covariance": (C.c_int, [C.c_void_p, c_double_p, c_double_p, C.c_int32, C.c_int32, c_int32_p, C.c_double,
                                             c_double_p, C.POINTER(muse_cov_out)]),
     "muse_b200_fd_jacobian": (C.c_int, [C.c_void_p, c_double_p, c_double_p, C.c_int32, C.c_double, c_double_p, c_int32_p]),
+    "muse_b200_fd_scores": (C.c_int, [C.c_void_p, c_double_p, c_double_p, C.c_int32, C.c_double, c_double_p, c_int32_p]),
     "muse_b200_get_maps": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, c_double_p]),
     "muse_b200_dgemm_host": (C.c_int, [c_double_p, c_double_p, c_double_p, C.c_int32, C.c_int32, C.c_int32]),
     "muse_b200_dgemm_time": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_double_p]),
     "muse_b200_profile_reset": (C.c_int, [C.c_void_p, C.c_int32]),
     "muse_b200_profile_get": (C.c_int, [C.c_void_p, C.POINTER(muse_profile)]),
+    "muse_b200_profile_passes": (C.c_int, [C.c_void_p, C.POINTER(muse_pass_profile)]),
     "muse_b200_debug_timeline": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int64)]),
     "muse_b200_geometry": (C.c_int, [C.c_void_p, c_int32_p, c_int32_p, c_int32_p]),
 }

@@ -245,6 +245,17 @@ class B200Backend:
                                                     _ip(status)))
         return Hs, status
 
+    def fd_scores(self, theta_eval, theta_sims, nsims_H: int, atol):
+        """Raw scores of the get_H! virtual sims at arbitrary sample points (include/muse_b200.h: muse_b200_fd_scores):
+        ``theta_sims[2n + s]`` is the −/+ point of Jacobian column n; returns g[k, 2n + s, :] and the statuses."""
+        nt = self.ntheta
+        te = self._theta(theta_eval)
+        ts = _f64(theta_sims, (2 * nt, nt))
+        g = np.empty((nsims_H, 2 * nt, nt))
+        status = np.empty((nsims_H, 2 * nt), dtype=np.int32)
+        self._check(self._lib.muse_b200_fd_scores(self._h, _dp(te), _dp(ts), int(nsims_H), float(atol), _dp(g), _ip(status)))
+        return g, status
+
     def get_maps(self, first_unit: int, count: int):
         z = np.empty((count, self.d))
         self._check(self._lib.muse_b200_get_maps(self._h, int(first_unit), int(count), _dp(z)))
@@ -258,6 +269,13 @@ class B200Backend:
         p = _capi.muse_profile()
         self._check(self._lib.muse_b200_profile_get(self._h, C.byref(p)))
         return {name: getattr(p, name) for name, _ in _capi.muse_profile._fields_}
+
+    def profile_passes(self) -> dict:
+        """Solver time, units and algorithmic bytes split by pass kind (cold / warm / truth / fiducial / fd)."""
+        p = _capi.muse_pass_profile()
+        self._check(self._lib.muse_b200_profile_passes(self._h, C.byref(p)))
+        return {name: dict(launches=int(p.launches[i]), ms=float(p.ms[i]), units=float(p.units[i]), bytes=float(p.bytes[i]))
+                for i, name in enumerate(_capi.PASS_KINDS)}
 
     def debug_timeline(self, items: int, fetch: bool = False):
         """Arm (fetch=False) or read (fetch=True) the controller timeline: items × 16 SM-clock stamps."""

@@ -147,6 +147,7 @@ static int launch_solver(muse_handle* h, const SolveLaunch& L, double bytes) {
         r.cls = 0;
         r.units = L.nitems;
         r.bytes = bytes;
+        r.kind = h->pass_kind;
         h->recs.push_back(r);
     }
     return 0;
@@ -436,6 +437,7 @@ int muse_b200_map_score_async(muse_handle* h, const double* theta_sim, const dou
     const int items = count + (include_data ? 1 : 0);
     if (items == 0) return MUSE_OK;
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    h->pass_kind = warm_start == MUSE_START_ZEROS ? MUSE_PASS_COLD : (warm_start == MUSE_START_TRUTH ? MUSE_PASS_TRUTH : MUSE_PASS_WARM);
     if (h->corr) return muse_corr_map_score(h, theta_sim, theta_eval, atol, include_data, warm_start, first_sim, count);
     SolveLaunch L;
     fill_common(h, L);
@@ -513,24 +515,17 @@ static int fd_combine(muse_handle* h, const double* step, int nsims_H, double* H
     return MUSE_OK;
 }
 
-int muse_b200_fd_jacobian(muse_handle* h, const double* theta0, const double* step, int32_t nsims_H, double atol,
-                          double* Hs_out, int32_t* status_out) {
-    if (!h || !theta0 || !step || !Hs_out) return MUSE_EINVAL;
+// Shared launch sequence of muse_b200_fd_jacobian / muse_b200_fd_scores: the fiducial solve and the 2·nθ virtual sims per
+// H sim, sampled at the rows of th_pts (row 2n = the "−" point of column n, row 2n+1 its "+" point), MAP + score at theta0.
+static int fd_launch(muse_handle* h, const double* theta0, const double* th_pts, int nsims_H, double atol) {
     const bool hshard = h->cfg.nsims_h > 0;
-    if (nsims_H < 0 || nsims_H > (hshard ? h->cfg.nsims_h : h->cfg.nsims)) MUSE_FAIL(h, MUSE_EINVAL, "nsims_H outside the handle's H shard");
-    if (!h->have_draws || (hshard && !h->have_draws_h)) MUSE_FAIL(h, MUSE_ESTATE, "no draws installed (set_draws[_h] / seed_draws)");
     const int nt = h->cfg.ntheta;
-    for (int n = 0; n < nt; ++n)
-        if (!(step[n] != 0.0) || !std::isfinite(step[n])) MUSE_FAIL(h, MUSE_EINVAL, "finite-difference step must be finite and non-zero");
-    if (nsims_H == 0) return MUSE_OK;
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
     const int items = nsims_H * nt * 2;
     const size_t ld = (size_t)h->ld, B = sizeof(double);
     if (h->corr) {
         if (ensure_outputs(h, items) != 0) return MUSE_ECUDA;
-        const int rc = muse_corr_fd_launch(h, theta0, step, nsims_H, atol);
-        if (rc != MUSE_OK) return rc;
-        return fd_combine(h, step, nsims_H, Hs_out, status_out);
+        return muse_corr_fd_launch(h, theta0, th_pts, nsims_H, atol);
     }
     if (items > h->h_cap) {
         cudaFree(h->zHA); cudaFree(h->zHB);
@@ -555,9 +550,10 @@ int muse_b200_fd_jacobian(muse_handle* h, const double* theta0, const double* st
     F.zB = h->zfidB;
     F.zstate = h->zfid_state;
     CUDA_TRY(h, cudaMemsetAsync(h->zfid_state, 0, sizeof(int), h->stream));
+    h->pass_kind = MUSE_PASS_FIDUCIAL;
     int rc = launch_solver(h, F, 3 * d8);
     if (rc != 0) return rc;
-    // (2) virtual sims at θ₀ ± h_n e_n, MAP + score at θ₀ from the fiducial start — src/muse.jl:426-433
+    // (2) virtual sims at the 2·nθ sample points, MAP + score at θ₀ from the fiducial start — src/muse.jl:426-433
     SolveLaunch L;
     fill_common(h, L);
     L.nitems = items;
@@ -570,23 +566,57 @@ int muse_b200_fd_jacobian(muse_handle* h, const double* theta0, const double* st
     L.zsharedB = h->zfidB;
     if (hshard) { L.xi = h->xi_h; L.nu = h->nu_h; }
     if (theta_consts(h->cfg, theta0, theta0, nullptr, &L.ev) != 0) MUSE_FAIL(h, MUSE_EUNSUPPORTED, "family");
-    for (int n = 0; n < nt; ++n) {
-        for (int s = 0; s < 2; ++s) {
-            double th[kMaxTheta];
-            for (int i = 0; i < nt; ++i) th[i] = theta0[i];
-            const double eps = 0.0 + step[n] * (s ? 1.0 : -1.0);     // x .+ step .* grid  [EXT FiniteDifferences]
-            th[n] = theta0[n] + eps;                                 // src/util.jl:15
-            theta_consts(h->cfg, th, theta0, &L.smp[2 * n + s], nullptr);
-        }
-    }
+    for (int p = 0; p < 2 * nt; ++p) theta_consts(h->cfg, th_pts + (size_t)p * nt, theta0, &L.smp[p], nullptr);
     L.zA = h->zHA;
     L.zB = h->zHB;
     L.zstate = nullptr;
     L.discard_z = 1;     // `ẑ, = ẑ_at_θ(...)` is only an intermediate of the score (src/muse.jl:431-432)
     // algorithmic bytes: read ξ, ν per virtual sim; the shared start ẑ_fid is read once (L2)
-    rc = launch_solver(h, L, items * 2 * d8 + d8);
-    if (rc != 0) return rc;
+    h->pass_kind = MUSE_PASS_FD;
+    return launch_solver(h, L, items * 2 * d8 + d8);
+}
+
+static int fd_check(muse_handle* h, int nsims_H) {
+    const bool hshard = h->cfg.nsims_h > 0;
+    if (nsims_H < 0 || nsims_H > (hshard ? h->cfg.nsims_h : h->cfg.nsims)) MUSE_FAIL(h, MUSE_EINVAL, "nsims_H outside the handle's H shard");
+    if (!h->have_draws || (hshard && !h->have_draws_h)) MUSE_FAIL(h, MUSE_ESTATE, "no draws installed (set_draws[_h] / seed_draws)");
+    return MUSE_OK;
+}
+
+int muse_b200_fd_jacobian(muse_handle* h, const double* theta0, const double* step, int32_t nsims_H, double atol,
+                          double* Hs_out, int32_t* status_out) {
+    if (!h || !theta0 || !step || !Hs_out) return MUSE_EINVAL;
+    int rc = fd_check(h, nsims_H);
+    if (rc != MUSE_OK) return rc;
+    const int nt = h->cfg.ntheta;
+    for (int n = 0; n < nt; ++n)
+        if (!(step[n] != 0.0) || !std::isfinite(step[n])) MUSE_FAIL(h, MUSE_EINVAL, "finite-difference step must be finite and non-zero");
+    if (nsims_H == 0) return MUSE_OK;
+    double pts[2 * kMaxTheta * kMaxTheta];
+    for (int n = 0; n < nt; ++n)
+        for (int s = 0; s < 2; ++s) {
+            double* th = pts + (size_t)(2 * n + s) * nt;
+            for (int i = 0; i < nt; ++i) th[i] = theta0[i];
+            const double eps = 0.0 + step[n] * (s ? 1.0 : -1.0);     // x .+ step .* grid  [EXT FiniteDifferences]
+            th[n] = theta0[n] + eps;                                 // src/util.jl:15
+        }
+    rc = fd_launch(h, theta0, pts, nsims_H, atol);
+    if (rc != MUSE_OK) return rc;
     return fd_combine(h, step, nsims_H, Hs_out, status_out);
+}
+
+int muse_b200_fd_scores(muse_handle* h, const double* theta_eval, const double* theta_sims, int32_t nsims_H, double atol,
+                        double* g_out, int32_t* status_out) {
+    if (!h || !theta_eval || !theta_sims || !g_out) return MUSE_EINVAL;
+    int rc = fd_check(h, nsims_H);
+    if (rc != MUSE_OK) return rc;
+    const int nt = h->cfg.ntheta;
+    for (int i = 0; i < 2 * nt * nt; ++i)
+        if (!std::isfinite(theta_sims[i])) MUSE_FAIL(h, MUSE_EINVAL, "finite-difference sample points must be finite");
+    if (nsims_H == 0) return MUSE_OK;
+    rc = fd_launch(h, theta_eval, theta_sims, nsims_H, atol);
+    if (rc != MUSE_OK) return rc;
+    return muse_b200_fetch(h, nsims_H * nt * 2, g_out, nullptr, nullptr, nullptr, status_out);
 }
 
 int muse_b200_get_maps(muse_handle* h, int32_t first_unit, int32_t count, double* z_out) {
@@ -615,7 +645,27 @@ int muse_b200_profile_reset(muse_handle* h, int32_t enable) {
     for (auto& r : h->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     h->recs.clear();
     h->acc = muse_profile{};
+    h->acc_pass = muse_pass_profile{};
     h->prof = enable != 0;
+    return MUSE_OK;
+}
+
+// fold the finished event pairs into the accumulators (stream must be idle)
+static int profile_drain(muse_handle* h) {
+    for (auto& r : h->recs) {
+        float ms = 0.f;
+        CUDA_TRY(h, cudaEventElapsedTime(&ms, r.a, r.b));
+        if (r.cls == 0) {
+            h->acc.solve_ms += ms; h->acc.solve_units += r.units; h->acc.solve_bytes += r.bytes;
+            const int k = r.kind >= 0 && r.kind < MUSE_PASS_KINDS ? r.kind : MUSE_PASS_COLD;
+            h->acc_pass.launches[k] += 1; h->acc_pass.ms[k] += ms; h->acc_pass.units[k] += r.units; h->acc_pass.bytes[k] += r.bytes;
+        }
+        else if (r.cls == 1) h->acc.draw_ms += ms;
+        else { h->acc.other_ms += ms; }
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    h->recs.clear();
     return MUSE_OK;
 }
 
@@ -623,20 +673,22 @@ int muse_b200_profile_get(muse_handle* h, muse_profile* out) {
     if (!h || !out) return MUSE_EINVAL;
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-    for (auto& r : h->recs) {
-        float ms = 0.f;
-        CUDA_TRY(h, cudaEventElapsedTime(&ms, r.a, r.b));
-        if (r.cls == 0) { h->acc.solve_ms += ms; h->acc.solve_units += r.units; h->acc.solve_bytes += r.bytes; }
-        else if (r.cls == 1) h->acc.draw_ms += ms;
-        else { h->acc.other_ms += ms; }
-        cudaEventDestroy(r.a);
-        cudaEventDestroy(r.b);
-    }
-    h->recs.clear();
+    const int rc = profile_drain(h);
+    if (rc != MUSE_OK) return rc;
     unsigned long long redo = 0;
     CUDA_TRY(h, cudaMemcpy(&redo, h->redo_total, sizeof(redo), cudaMemcpyDeviceToHost));
     h->acc.redo_units = (int64_t)redo;
     *out = h->acc;
+    return MUSE_OK;
+}
+
+int muse_b200_profile_passes(muse_handle* h, muse_pass_profile* out) {
+    if (!h || !out) return MUSE_EINVAL;
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    const int rc = profile_drain(h);
+    if (rc != MUSE_OK) return rc;
+    *out = h->acc_pass;
     return MUSE_OK;
 }
 

@@ -528,6 +528,7 @@ int corr_solve(muse_handle* h, CorrBatch& b, CorrLaunch& L) {
         rec.cls = 0;
         rec.units = L.nrows;
         rec.bytes = 0.0;
+        rec.kind = h->pass_kind;
         h->recs.push_back(rec);
     }
     return MUSE_OK;
@@ -680,7 +681,7 @@ int muse_corr_map_score(muse_handle* h, const double* theta_sim, const double* t
 }
 
 // fiducial solve + the 2·n_H virtual sims of get_H! (src/muse.jl:417-442); scores land in items 2k + sgn
-int muse_corr_fd_launch(muse_handle* h, const double* theta0, const double* step, int nsims_H, double atol) {
+int muse_corr_fd_launch(muse_handle* h, const double* theta0, const double* th_pts, int nsims_H, double atol) {
     muse_corr_ctx* c = h->corr;
     const bool hshard = h->cfg.nsims_h > 0;
     CorrLaunch F{};
@@ -696,14 +697,15 @@ int muse_corr_fd_launch(muse_handle* h, const double* theta0, const double* step
     F.W = c->W;
     F.nu = c->nu;
     F.start_kind = kStartZero;
+    h->pass_kind = MUSE_PASS_FIDUCIAL;
     int rc = corr_solve(h, c->fid, F);
     if (rc != MUSE_OK) return rc;
     rc = alloc_batch(h, c->fd, 2 * nsims_H);
     if (rc != MUSE_OK) return rc;
     CorrLaunch L{};
     L.a = F.a; L.half_cst = F.half_cst; L.atol = atol;
-    L.sig[0] = std::exp(0.5 * (theta0[0] + (0.0 + step[0] * -1.0)));
-    L.sig[1] = std::exp(0.5 * (theta0[0] + (0.0 + step[0] * 1.0)));
+    L.sig[0] = std::exp(0.5 * th_pts[0]);      // the "−" and "+" sample points of the single column
+    L.sig[1] = std::exp(0.5 * th_pts[1]);
     L.mode = 1;
     L.data_row = -1;
     L.row0 = 0;
@@ -712,6 +714,7 @@ int muse_corr_fd_launch(muse_handle* h, const double* theta0, const double* step
     L.nu = hshard ? c->nu_h : c->nu;
     L.start_kind = kStartShared;
     L.zshared = c->fid.z;
+    h->pass_kind = MUSE_PASS_FD;
     return corr_solve(h, c->fd, L);
 }
 

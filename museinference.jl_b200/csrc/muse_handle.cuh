@@ -59,9 +59,11 @@ struct muse_handle {
 
     // profiling
     bool prof = false;
-    struct Rec { cudaEvent_t a, b; int cls; double units, bytes; };
+    struct Rec { cudaEvent_t a, b; int cls; double units, bytes; int kind; };
     std::vector<Rec> recs;
     muse_profile acc{};
+    int pass_kind = MUSE_PASS_COLD;      // kind of the solver pass being enqueued (set by the entry point)
+    muse_pass_profile acc_pass{};        // per-kind split of acc.solve_* (muse_b200_profile_passes)
 };
 
 void muse_comm_release(muse_handle* h);
@@ -77,6 +79,6 @@ int  muse_corr_set_draws(muse_handle* h, const double* xi, const double* nu, con
 int  muse_corr_seed_draws(muse_handle* h, uint64_t seed);
 int  muse_corr_map_score(muse_handle* h, const double* theta_sim, const double* theta_eval, double atol, int include_data,
                          int warm_start, int first_sim, int count);
-int  muse_corr_fd_launch(muse_handle* h, const double* theta0, const double* step, int nsims_H, double atol);
+int  muse_corr_fd_launch(muse_handle* h, const double* theta0, const double* th_pts /* 2 sample points */, int nsims_H, double atol);
 int  muse_corr_get_maps(muse_handle* h, int first_unit, int count, double* z_out);
 bool muse_corr_have_draws(muse_handle* h, bool hshard);

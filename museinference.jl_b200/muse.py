@@ -124,9 +124,12 @@ def muse_(result: MuseResult, prob: AbstractMuseProblem, theta0=None, **kwargs):
     if rng is None:
         rng = result.rng if result.rng is not None else 0
     result.rng = rng
-    # :135-136 (identity transform)
+    # :135-136
     theta = prob.standardize_theta(result.theta if result.theta is not None else theta0)
     theta_unreg = theta.copy()
+    theta_t = prob.transform_theta(theta)                                          # θ′ — also what the kernels take
+    theta_unreg_t = theta_t.copy()
+    transformed = prob.has_transform
     history = result.history
     alpha_fn = alpha if callable(alpha) else (lambda i: alpha)                     # :145-149
 
@@ -142,7 +145,7 @@ def muse_(result: MuseResult, prob: AbstractMuseProblem, theta0=None, **kwargs):
     prior_ms = _prior_mean_sigma(prob.prior, prob.ntheta)
     fused = (fused_driver and not history and not callable(alpha) and regularize_is_identity and H_inv_like is None
              and H_inv_update == "sims" and not save_MAPs and checkpoint_filename is None and prior_ms is not False
-             and hasattr(be, "muse_iterate") and maxsteps >= 1 and nsims >= 2)
+             and hasattr(be, "muse_iterate") and maxsteps >= 1 and nsims >= 2 and not transformed)
     if fused:
         counts = None
         if pool.world > 1:
@@ -156,7 +159,8 @@ def muse_(result: MuseResult, prob: AbstractMuseProblem, theta0=None, **kwargs):
             hl, hp, hq = r["h_inv_like_hist"][k], r["h_prior_hist"][k], r["h_inv_post_hist"][k]
             history.append(dict(
                 theta=r["theta_hist"][k].copy(), theta_unreg=th_unreg_prev,
-                g_like_sims=r["g_sims_hist"][k].copy(), g_like_dat=r["g_dat_hist"][k].copy(), g_like=r["g_like_hist"][k].copy(),
+                theta_t=r["theta_hist"][k].copy(), theta_unreg_t=th_unreg_prev,
+                g_like_sims=r["g_sims_hist"][k].copy(), g_like_sims_t=r["g_sims_hist"][k].copy(), g_like_dat=r["g_dat_hist"][k].copy(), g_like=r["g_like_hist"][k].copy(),
                 g_prior=r["g_prior_hist"][k].copy(), g_post=r["g_like_hist"][k] + r["g_prior_hist"][k],
                 H_inv_post=np.diag(hq), H_prior=np.diag(hp), H_inv_like=np.diag(hl), H_inv_like_sims=np.diag(hl),
                 z_history_dat=dict(iters=int(r["iters_hist"][k, 0]), fg_evals=int(r["fg_hist"][k, 0]),
@@ -183,33 +187,35 @@ def muse_(result: MuseResult, prob: AbstractMuseProblem, theta0=None, **kwargs):
 
     for i in range(len(history) + 1, maxsteps + 1):                                # :159
         t0 = time.perf_counter()
-        if i > 2:                                                                  # :163-166
-            dth = history[-1]["theta"] - history[-2]["theta"]
+        if i > 2:                                                                  # :163-166 (Δθ′)
+            dth = history[-1]["theta_t"] - history[-2]["theta_t"]
             q = -(dth @ history[-1]["H_inv_post"] @ dth)
             if q < 0:
                 raise ValueError("DomainError: sqrt of a negative number in the θ convergence test (src/muse.jl:165)")
             if math.sqrt(q) < theta_rtol:
                 break
 
-        # MUSE gradient: the mapped block :169-176 is one backend call on this rank's shard
+        # MUSE gradient: the mapped block :169-176 is one backend call on this rank's shard.  The kernels take θ′ and
+        # return g′ = ∇θ′ logLike (:173); g = ∇θ logLike (:172) is g′ ⊘ ∂θ/∂θ′ (identical arrays without a transform).
         warm = (_capi.START_USER if z0 is not None else _capi.START_ZEROS) if first_pass else _capi.START_PREV
         if getattr(pool, "uses_device_gather", lambda: False)():
             # multi-GPU: the scores are all-gathered with NCCL from device memory on the launch stream
-            units = be.map_score_async(theta, theta, atol, include_data=True, warm_start=warm)
-            g_like_sims = pool.allgather_device_scores(be, 1, nsims)               # the one exchange step
+            units = be.map_score_async(theta_t, theta_t, atol, include_data=True, warm_start=warm)
+            g_like_sims_t = pool.allgather_device_scores(be, 1, nsims)             # the one exchange step
             out = be.fetch(units)
         else:
-            out = be.map_score(theta, theta, atol, include_data=True, warm_start=warm)
-            g_like_sims = pool.allgather_rows(out["g"][1:], nsims)                 # the one exchange step
+            out = be.map_score(theta_t, theta_t, atol, include_data=True, warm_start=warm)
+            g_like_sims_t = pool.allgather_rows(out["g"][1:], nsims)               # the one exchange step
         first_pass = False
         _check_status(out, "muse!")
-        g_like_dat = out["g"][0].copy()                                            # :177
+        g_like_dat = out["g"][0].copy()                                            # :177-178 (g_like_dat′)
+        g_like_sims = g_like_sims_t / prob.dinv_transform(theta_t) if transformed else g_like_sims_t   # :177 (g)
 
-        g_like = g_like_dat - np.mean(g_like_sims, axis=0)                         # :183
-        g_prior = np.asarray(prob.prior.grad(theta), dtype=np.float64)             # :184
+        g_like = g_like_dat - np.mean(g_like_sims_t, axis=0)                       # :183
+        g_prior = prob.prior_grad_t(theta_t) if transformed else np.asarray(prob.prior.grad(theta), dtype=np.float64)   # :184
         g_post = g_like + g_prior                                                  # :185
 
-        h_inv_like_sims = -1.0 / np.var(g_like_sims, axis=0, ddof=1)               # :188
+        h_inv_like_sims = -1.0 / np.var(g_like_sims_t, axis=0, ddof=1)             # :188
         H_inv_like_sims = np.diag(h_inv_like_sims)                                 # :189
         if H_inv_like is None or H_inv_update == "sims":                           # :190-191
             H_inv_like = H_inv_like_sims
@@ -217,19 +223,19 @@ def muse_(result: MuseResult, prob: AbstractMuseProblem, theta0=None, **kwargs):
             j0 = int(max(2, i - broyden_memory))
             H_inv_like = history[j0 - 2]["H_inv_like_sims"]
             for j in range(j0, i):
-                d_th = history[j - 1]["theta"] - history[j - 2]["theta"]
+                d_th = history[j - 1]["theta_t"] - history[j - 2]["theta_t"]
                 d_g = history[j - 1]["g_like"] - history[j - 2]["g_like"]
                 H_inv_like = H_inv_like + np.outer((d_th - H_inv_like @ d_g) / (d_th @ H_inv_like @ d_g), d_th) @ H_inv_like
                 if H_inv_update == "diagonal_broyden":
                     H_inv_like = np.diag(np.diag(H_inv_like))
 
-        H_prior = np.asarray(prob.prior.hess(theta), dtype=np.float64)             # :207
+        H_prior = prob.prior_hess_t(theta_t) if transformed else np.asarray(prob.prior.hess(theta), dtype=np.float64)   # :207
         H_inv_post = np.linalg.inv(np.linalg.inv(H_inv_like) + H_prior)            # :208
 
         t = time.perf_counter() - t0
         entry = dict(                                                              # :211-221
-            theta=theta.copy(), theta_unreg=theta_unreg.copy(),
-            g_like_sims=g_like_sims.copy(), g_like_dat=g_like_dat, g_like=g_like, g_prior=g_prior, g_post=g_post,
+            theta=theta.copy(), theta_unreg=theta_unreg.copy(), theta_t=theta_t.copy(), theta_unreg_t=theta_unreg_t.copy(),
+            g_like_sims=g_like_sims.copy(), g_like_sims_t=g_like_sims_t.copy(), g_like_dat=g_like_dat, g_like=g_like, g_prior=g_prior, g_post=g_post,
             H_inv_post=H_inv_post, H_prior=H_prior, H_inv_like=np.array(H_inv_like, copy=True),
             H_inv_like_sims=H_inv_like_sims,
             z_history_dat=dict(iters=int(out["iters"][0]), fg_evals=int(out["fg_evals"][0]),
@@ -244,8 +250,10 @@ def muse_(result: MuseResult, prob: AbstractMuseProblem, theta0=None, **kwargs):
             entry["z_sims"] = keep(be.get_maps(1, be.nsims))
         history.append(entry)
 
-        theta_unreg = theta - alpha_fn(i) * (H_inv_post @ g_post)                  # :224
-        theta = prob.standardize_theta(regularize(theta_unreg))                    # :226-227
+        theta_unreg_t = theta_t - alpha_fn(i) * (H_inv_post @ g_post)              # :224
+        theta_unreg = prob.inv_transform_theta(theta_unreg_t)                      # :225
+        theta_t = prob.standardize_theta(regularize(theta_unreg_t))                # :226
+        theta = prob.inv_transform_theta(theta_t)                                  # :227
 
         result.theta = theta_unreg.copy()                                          # :230
         result.gs = g_like_sims.copy()                                             # :231 (N×nθ array, one row per sim)
@@ -290,9 +298,10 @@ def get_J_(result: MuseResult, prob: AbstractMuseProblem, theta0=None, **kwargs)
         if z0 is not None:
             be.set_z0(z0)
         warm = _capi.START_USER if z0 is not None else _capi.START_TRUTH           # :511
-        out = be.map_score(theta0, theta0, atol, include_data=False, warm_start=warm, first_sim=lo, count=n_local)
+        theta0_t = prob.transform_theta(theta0)
+        out = be.map_score(theta0_t, theta0_t, atol, include_data=False, warm_start=warm, first_sim=lo, count=n_local)
         bad = _check_status(out, "get_J!", skip_errors)
-        g_local = out["g"]
+        g_local = out["g"] / prob.dinv_transform(theta0_t) if prob.has_transform else out["g"]   # :513 UnTransformedθ()
         if pool.world == 1:
             g_new = np.delete(g_local, bad, axis=0) if bad.size else g_local       # skipmissing (:508)
         else:
@@ -357,7 +366,29 @@ def get_H_(result: MuseResult, prob: AbstractMuseProblem, theta0=None, **kwargs)
     n_total = max(nsims_total, nsims_remaining)
     be = prob.backend_for(n_total, rng, pool, nsims_remaining)
     _, hcnt = pool.shard(nsims_remaining)
-    Hs_local, status = be.fd_jacobian(theta0, step, hcnt, atol)                    # :417-442 + src/util.jl:9-26
+    if not prob.has_transform:
+        Hs_local, status = be.fd_jacobian(theta0, step, hcnt, atol)                # :417-442 + src/util.jl:9-26
+    else:
+        # pjacobian perturbs the UNtransformed θ₀ (src/util.jl:15; sims at θ, MAP and score at θ₀, :430-432); the
+        # kernels take θ′, so the 2·nθ sample points are mapped one by one and the central difference
+        # sum(fs .* [-1/2, 0, 1/2]) / step and the change of variables g = g′ ⊘ ∂θ/∂θ′ are formed here
+        nt = prob.ntheta
+        theta0_t = prob.transform_theta(theta0)
+        pts = np.empty((2 * nt, nt))
+        for n in range(nt):
+            for sgn in (0, 1):
+                th = theta0.copy()
+                th[n] = theta0[n] + (0.0 + step[n] * (1.0 if sgn else -1.0))
+                pts[2 * n + sgn] = prob.transform_theta(th)
+        g_t, st = be.fd_scores(theta0_t, pts, hcnt, atol)
+        g_u = g_t / prob.dinv_transform(theta0_t)
+        Hs_local = np.empty((hcnt, nt, nt))
+        for n in range(nt):
+            acc = g_u[:, 2 * n, :] * -0.5
+            acc = acc + 0.0
+            acc = acc + g_u[:, 2 * n + 1, :] * 0.5
+            Hs_local[:, :, n] = acc / step[n]
+        status = st.reshape(hcnt, nt, 2)
     bad_local = np.flatnonzero((status.reshape(hcnt, -1) == _capi.STATUS_NONFINITE).any(axis=1))
     if bad_local.size and not skip_errors:
         raise FloatingPointError("get_H!: MAP solution failed with a non-finite objective")

@@ -9,7 +9,12 @@ whose sampling rule, log-density and analytic ∇z / ∇θ are compiled into the
 (src/turing.jl, src/soss.jl) — raises ``MuseBackendError`` (EUNSUPPORTED); there is no generic /
 CPU path.
 
-θ-transforms are the identity for ``SimpleMuseProblem`` (src/interface.jl:20, 28, 134).
+θ-transforms (``transform_θ`` / ``inv_transform_θ``, src/interface.jl:14-28) default to the identity, as for the
+reference's ``SimpleMuseProblem``.  A problem whose θ has positive components (a standard deviation, a variance)
+declares ``theta_transform=("identity", "log")``: the registered kernels are parameterised in the unconstrained
+space, so the kernels' parameters ARE the transformed θ′ of src/muse.jl:136, their score is ∇θ′ logLike
+(``Transformedθ()``, src/muse.jl:173) and the untransformed score (src/muse.jl:172, 432, 513) follows by the chain
+rule, exactly as the reference's Soss adapter defines the pair (src/soss.jl:96-117).
 """
 from __future__ import annotations
 
@@ -92,7 +97,7 @@ class SimpleMuseProblem(AbstractMuseProblem):
     stream   raw cudaStream_t to launch on (e.g. ``torch.cuda.current_stream().cuda_stream``)
     """
 
-    def __init__(self, x, family: str = "funnel", prior=None, *, P=None, L=None, group: int = 0,
+    def __init__(self, x, family: str = "funnel", prior=None, *, theta_transform=None, P=None, L=None, group: int = 0,
                  cluster: int = 0, kernel: int = 0, stream=None, backend_factory=None):
         if family not in FAMILY_NTHETA:
             raise MuseBackendError(-5, f"model family {family!r} is not registered with the B200 backend; "
@@ -104,6 +109,12 @@ class SimpleMuseProblem(AbstractMuseProblem):
         self.d = self.x.size
         self.ntheta = FAMILY_NTHETA[family]
         self.prior = prior or FlatPrior()
+        kinds = tuple(theta_transform) if theta_transform is not None else ("identity",) * self.ntheta
+        if len(kinds) != self.ntheta or any(k not in ("identity", "log") for k in kinds):
+            raise ValueError(f"theta_transform must name {self.ntheta} component transform(s) out of 'identity' | 'log'")
+        self.theta_transform = kinds
+        self._log = np.array([k == "log" for k in kinds])
+        self.has_transform = bool(self._log.any())
         self.P, self.L = P, L
         self.group, self.cluster, self.kernel = group, cluster, kernel
         self._backend_factory = backend_factory or B200Backend
@@ -122,6 +133,45 @@ class SimpleMuseProblem(AbstractMuseProblem):
 
     def logPrior(self, theta):
         return self.prior.logp(theta)
+
+    # ------------------------------------------------------------------ θ-transforms (src/interface.jl:14-28)
+    def transform_theta(self, theta):
+        """θ → θ′ ∈ (−∞, ∞)ⁿ: ``log`` on the components declared positive.  θ′ is what the kernels take."""
+        t = np.array(theta, dtype=np.float64, copy=True)
+        if self.has_transform:
+            if np.any(t[self._log] <= 0):
+                raise ValueError("DomainError: a log-transformed θ component must be positive")
+            t[self._log] = np.log(t[self._log])
+        return t
+
+    def inv_transform_theta(self, theta_t):
+        t = np.array(theta_t, dtype=np.float64, copy=True)
+        if self.has_transform:
+            t[self._log] = np.exp(t[self._log])
+        return t
+
+    def dinv_transform(self, theta_t):
+        """Diagonal of ∂θ/∂θ′ at θ′ (1, or θ for a log component): ∇θ′ = ∂θ/∂θ′ ⊙ ∇θ."""
+        j = np.ones(self.ntheta)
+        if self.has_transform:
+            j[self._log] = np.exp(np.asarray(theta_t, dtype=np.float64)[self._log])
+        return j
+
+    def prior_grad_t(self, theta_t):
+        """∇θ′ logPriorθ(θ′, Transformedθ()), with logPriorθ(θ′, Transformedθ()) = logPriorθ(inv_transform_θ(θ′))
+        (src/soss.jl:107-108; used at src/muse.jl:184)."""
+        th = self.inv_transform_theta(theta_t)
+        return self.dinv_transform(theta_t) * np.asarray(self.prior.grad(th), dtype=np.float64)
+
+    def prior_hess_t(self, theta_t):
+        """∇²θ′ of the same function (src/muse.jl:207): D·∇²logπ·D + diag(∇logπ ⊙ ∂²θ/∂θ′²), D = diag(∂θ/∂θ′)."""
+        th = self.inv_transform_theta(theta_t)
+        D = self.dinv_transform(theta_t)
+        H = np.asarray(self.prior.hess(th), dtype=np.float64) * np.outer(D, D)
+        if self.has_transform:
+            g = np.asarray(self.prior.grad(th), dtype=np.float64)
+            H = H + np.diag(np.where(self._log, g * D, 0.0))      # ∂²e^{θ′}/∂θ′² = e^{θ′} = D
+        return H
 
     # ------------------------------------------------------------------ backend management
     def set_data(self, x):

@@ -145,6 +145,63 @@ class CorrGauss:
         return np.linalg.solve(A, x)
 
 
+class TransformedFamily:
+    """A registered family whose user-facing θ has positive components: θ_user[i] = exp(θ_base[i]) where
+    ``kinds[i] == "log"``.  Supplies the pair the reference's interface asks of a problem with a bounded θ
+    (/root/reference/src/interface.jl:14-28, 36-58): ``transform_theta`` / ``inv_transform_theta`` and the score in both
+    spaces, defined as the reference's Soss adapter defines them (src/soss.jl:96-117): the transformed-space gradient
+    is the gradient of θ′ ↦ logLike(inv_transform_θ(θ′)), i.e. the base family's own score."""
+
+    def __init__(self, base, kinds):
+        self.base = base
+        self.kinds = tuple(kinds)
+        assert len(self.kinds) == base.ntheta and all(k in ("identity", "log") for k in self.kinds)
+        self._log = np.array([k == "log" for k in self.kinds])
+        self.name = base.name + "[" + ",".join(self.kinds) + "]"
+        self.family_id = base.family_id
+        self.ntheta = base.ntheta
+        self.d = base.d
+
+    def transform_theta(self, theta):
+        t = np.array(theta, dtype=np.float64, copy=True).reshape(-1)
+        if np.any(t[self._log] <= 0):
+            raise ValueError("DomainError: a log-transformed θ component must be positive")
+        t[self._log] = np.log(t[self._log])
+        return t
+
+    def inv_transform_theta(self, theta_t):
+        t = np.array(theta_t, dtype=np.float64, copy=True).reshape(-1)
+        t[self._log] = np.exp(t[self._log])
+        return t
+
+    def dinv_transform(self, theta_t):
+        j = np.ones(self.ntheta)
+        j[self._log] = np.exp(np.asarray(theta_t, dtype=np.float64).reshape(-1)[self._log])
+        return j
+
+    # everything below takes the UNtransformed θ, like sample_x_z / logLike of the reference (src/interface.jl:62-99)
+    def sample(self, theta, xi, nu):
+        return self.base.sample(self.transform_theta(theta), xi, nu)
+
+    def neg_loglike(self, x, z, theta):
+        return self.base.neg_loglike(x, z, self.transform_theta(theta))
+
+    def neg_loglike_and_grad(self, x, z, theta):
+        return self.base.neg_loglike_and_grad(x, z, self.transform_theta(theta))
+
+    def score(self, x, z, theta):
+        """∇θ logLike(x, z, θ, UnTransformedθ())  (src/muse.jl:172, 432, 513)."""
+        tt = self.transform_theta(theta)
+        return self.base.score(x, z, tt) / self.dinv_transform(tt)
+
+    def score_t(self, x, z, theta_t):
+        """∇θ′ logLike(x, z, θ′, Transformedθ())  (src/muse.jl:173)."""
+        return self.base.score(x, z, np.asarray(theta_t, dtype=np.float64).reshape(-1))
+
+    def exact_map(self, x, theta):
+        return self.base.exact_map(x, self.transform_theta(theta))
+
+
 def make_family(name: str, d: int, **consts):
     if name == "funnel":
         return Funnel(d)

@@ -16,8 +16,13 @@ Differences from the reference that are *representation only*:
     stream's own draw), see oracle/__init__.py.
   * Prior gradient / Hessian come from a prior object with analytic derivatives instead of
     ForwardDiff (src/muse.jl:184, 207, 539).
-  * θ-transforms are the identity (true of SimpleMuseProblem, src/interface.jl:20, 28), so the
-    primed and unprimed quantities coincide; both names are kept in the history for clarity.
+  * θ-transforms are the identity for the plain families (true of SimpleMuseProblem,
+    src/interface.jl:20, 28), so primed and unprimed quantities coincide; a ``TransformedFamily``
+    (oracle/families.py) supplies ``transform_θ`` / ``inv_transform_θ`` and the score in both spaces,
+    and the primed (transformed-space) quantities of src/muse.jl:136, 164, 173, 183-227 become distinct:
+    history keys ``theta_t``, ``theta_unreg_t``, ``g_like_sims_t`` hold θ′, θunreg′, g_like_sims′; the
+    keys g_like_dat, g_like, g_prior, g_post, H_* hold the primed quantities (the reference stores only
+    those), ``theta``, ``theta_unreg``, ``g_like_sims`` the unprimed ones.
 
 Quirks reproduced on purpose:
   * convergence test ``sqrt(-(Δθ' H⁻¹_post Δθ)) < θ_rtol`` uses the *inverse* Hessian (:165);
@@ -128,9 +133,45 @@ class OracleProblem:
         soln = lbfgs_minimize(lambda z: self.family.neg_loglike_and_grad(x, z, theta), z0, g_tol=atol)
         return soln.minimizer, soln
 
-    # ∇θ_logLike  — src/simple.jl:92
+    # ∇θ_logLike(prob, x, z, θ, UnTransformedθ())  — src/simple.jl:92, src/interface.jl:57-58
     def grad_theta(self, x, z, theta):
         return self.family.score(x, z, theta)
+
+    # ∇θ_logLike(prob, x, z, θ′, Transformedθ())  — src/interface.jl:57-58 (identity transform: the same function)
+    def grad_theta_t(self, x, z, theta_t):
+        f = getattr(self.family, "score_t", None)
+        return f(x, z, theta_t) if f else self.family.score(x, z, theta_t)
+
+    # transform_θ / inv_transform_θ  — src/interface.jl:20, 28
+    def transform_theta(self, theta):
+        f = getattr(self.family, "transform_theta", None)
+        return f(theta) if f else np.array(theta, dtype=np.float64, copy=True)
+
+    def inv_transform_theta(self, theta_t):
+        f = getattr(self.family, "inv_transform_theta", None)
+        return f(theta_t) if f else np.array(theta_t, dtype=np.float64, copy=True)
+
+    # logPriorθ(prob, θ′, Transformedθ()) = logPriorθ(prob, inv_transform_θ(θ′), UnTransformedθ())  — src/soss.jl:107-108;
+    # its gradient and Hessian in θ′ (the reference: ForwardDiff, src/muse.jl:184, 207) by central differences of the
+    # analytic untransformed gradient composed with the transform (identity transform: the analytic ones directly)
+    def prior_grad_t(self, theta_t):
+        if not hasattr(self.family, "transform_theta"):
+            return self.prior.grad(theta_t)
+        D = self.family.dinv_transform(theta_t)
+        return D * self.prior.grad(self.inv_transform_theta(theta_t))
+
+    def prior_hess_t(self, theta_t):
+        if not hasattr(self.family, "transform_theta"):
+            return self.prior.hess(theta_t)
+        tt = np.asarray(theta_t, dtype=np.float64)
+        n = tt.size
+        H = np.empty((n, n))
+        for j in range(n):                      # column j of the Hessian = ∂(∇logπ′)/∂θ′_j, Richardson-extrapolated
+            def gcol(h):
+                e = np.zeros(n); e[j] = h
+                return (self.prior_grad_t(tt + e) - self.prior_grad_t(tt - e)) / (2 * h)
+            H[:, j] = (4.0 * gcol(5e-4) - gcol(1e-3)) / 3.0
+        return 0.5 * (H + H.T)
 
     # ẑ_guess_from_truth — src/interface.jl:184-186
     def z_guess_from_truth(self, x, z, theta):
@@ -180,6 +221,8 @@ def muse_bang(result: MuseResult, prob: OracleProblem, theta0=None, *, z0=None, 
     # :135-136
     theta = np.atleast_1d(np.asarray(result.theta if result.theta is not None else theta0, dtype=np.float64)).copy()
     theta_unreg = theta.copy()
+    theta_t = prob.transform_theta(theta)
+    theta_unreg_t = theta_t.copy()
     history = result.history
     ntheta = theta.size
     alpha_fn = alpha if callable(alpha) else (lambda i, _a=alpha: _a)   # :145-149
@@ -192,7 +235,7 @@ def muse_bang(result: MuseResult, prob: OracleProblem, theta0=None, *, z0=None, 
     for i in range(len(history) + 1, maxsteps + 1):                       # :159
         t0 = time.perf_counter()
         if i > 2:                                                         # :163-166
-            dth = history[-1]["theta"] - history[-2]["theta"]
+            dth = history[-1]["theta_t"] - history[-2]["theta_t"]
             q = -(dth @ history[-1]["H_inv_post"] @ dth)
             if q < 0:
                 raise ValueError("sqrt of a negative number in the θ convergence test (DomainError in the reference)")
@@ -200,22 +243,24 @@ def muse_bang(result: MuseResult, prob: OracleProblem, theta0=None, *, z0=None, 
                 break
 
         # MUSE gradient  :169-176  (unit 0 = data, units 1..nsims = sims)
-        gs_all, zs_new, hists = [], [], []
+        gs_all, gts_all, zs_new, hists = [], [], [], []
         for u in range(nsims + 1):
             x = prob.x if u == 0 else prob.sample_x_z(u - 1, theta)[0]
-            zhat, g, soln = map_score_unit(prob, x, zs[u], theta, gradz_logLike_atol)
+            zhat, g, soln = map_score_unit(prob, x, zs[u], theta, gradz_logLike_atol)      # :171-172
             gs_all.append(g)
+            gts_all.append(prob.grad_theta_t(x, zhat, theta_t))           # :173
             zs_new.append(zhat)
             hists.append(soln)
-        g_like_dat = gs_all[0]
-        g_like_sims = np.array(gs_all[1:])                                # :177-180
+        g_like_sims = np.array(gs_all[1:])                                # :177
+        g_like_dat = gts_all[0]                                           # :178 (primed from here on)
+        g_like_sims_t = np.array(gts_all[1:])
         zs = zs_new                                                       # :181
 
-        g_like = g_like_dat - np.mean(g_like_sims, axis=0)                # :183
-        g_prior = prob.prior.grad(theta)                                  # :184
+        g_like = g_like_dat - np.mean(g_like_sims_t, axis=0)              # :183
+        g_prior = prob.prior_grad_t(theta_t)                              # :184
         g_post = g_like + g_prior                                         # :185
 
-        h_inv_like_sims = -1.0 / _var_corrected(g_like_sims)              # :188
+        h_inv_like_sims = -1.0 / _var_corrected(g_like_sims_t)            # :188
         H_inv_like_sims = np.diag(h_inv_like_sims)                        # :189
         if H_inv_like is None or H_inv_update == "sims":                  # :190-191
             H_inv_like = H_inv_like_sims
@@ -223,19 +268,20 @@ def muse_bang(result: MuseResult, prob: OracleProblem, theta0=None, *, z0=None, 
             j0 = int(max(2, i - broyden_memory))
             H_inv_like = history[j0 - 2]["H_inv_like_sims"]
             for j in range(j0, i):
-                dth = history[j - 1]["theta"] - history[j - 2]["theta"]
+                dth = history[j - 1]["theta_t"] - history[j - 2]["theta_t"]
                 dgl = history[j - 1]["g_like"] - history[j - 2]["g_like"]
                 H_inv_like = H_inv_like + np.outer((dth - H_inv_like @ dgl) / (dth @ H_inv_like @ dgl), dth) @ H_inv_like
                 if H_inv_update == "diagonal_broyden":
                     H_inv_like = np.diag(np.diag(H_inv_like))
 
-        H_prior = prob.prior.hess(theta)                                  # :207
+        H_prior = prob.prior_hess_t(theta_t)                              # :207
         H_inv_post = np.linalg.inv(np.linalg.inv(H_inv_like) + H_prior)   # :208
 
         t = time.perf_counter() - t0
         history.append(dict(                                              # :211-221
-            theta=theta.copy(), theta_unreg=theta_unreg.copy(),
-            g_like_sims=g_like_sims.copy(), g_like_dat=g_like_dat.copy(), g_like=g_like.copy(),
+            theta=theta.copy(), theta_unreg=theta_unreg.copy(), theta_t=theta_t.copy(), theta_unreg_t=theta_unreg_t.copy(),
+            g_like_sims=g_like_sims.copy(), g_like_sims_t=g_like_sims_t.copy(),
+            g_like_dat=g_like_dat.copy(), g_like=g_like.copy(),
             g_prior=g_prior.copy(), g_post=g_post.copy(),
             H_inv_post=H_inv_post.copy(), H_prior=H_prior.copy(), H_inv_like=H_inv_like.copy(),
             H_inv_like_sims=H_inv_like_sims.copy(),
@@ -244,8 +290,10 @@ def muse_bang(result: MuseResult, prob: OracleProblem, theta0=None, *, z0=None, 
             z_sims=[z.copy() for z in zs[1:]] if save_MAPs else None,
         ))
 
-        theta_unreg = theta - alpha_fn(i) * (H_inv_post @ g_post)         # :224
-        theta = np.atleast_1d(np.asarray(regularize(theta_unreg), dtype=np.float64))   # :226-227
+        theta_unreg_t = theta_t - alpha_fn(i) * (H_inv_post @ g_post)     # :224
+        theta_unreg = prob.inv_transform_theta(theta_unreg_t)             # :225
+        theta_t = np.atleast_1d(np.asarray(regularize(theta_unreg_t), dtype=np.float64))   # :226
+        theta = prob.inv_transform_theta(theta_t)                         # :227
 
         result.theta = theta_unreg.copy()                                 # :230
         result.gs = [g.copy() for g in g_like_sims]                       # :231

@@ -83,5 +83,24 @@ class FakeBackend:
         Hs = np.array(res.Hs).reshape(nsims_H, self.ntheta, self.ntheta)
         return Hs, np.zeros((nsims_H, self.ntheta, 2), dtype=np.int32)
 
+    def fd_scores(self, theta_eval, theta_sims, nsims_H, atol):
+        if self.nsims_h:
+            dr = O.Draws(self.draws_h[0], self.draws_h[1], self.draws.xi_master, self.draws.nu_master)
+        else:
+            dr = self.draws
+        prob = O.OracleProblem(self.fam, self.x, dr)
+        theta_eval = np.atleast_1d(np.asarray(theta_eval, dtype=np.float64))
+        theta_sims = np.asarray(theta_sims, dtype=np.float64).reshape(2 * self.ntheta, self.ntheta)
+        self.calls.append(("fd_scores", tuple(theta_eval), nsims_H))
+        xm, zm = prob.sample_x_z("master", theta_eval)
+        zfid, _ = prob.z_at_theta(xm, np.zeros(self.d), theta_eval, atol)
+        g = np.empty((nsims_H, 2 * self.ntheta, self.ntheta))
+        for k in range(nsims_H):
+            for p in range(2 * self.ntheta):
+                x, _ = prob.sample_x_z(k, theta_sims[p])
+                zh, _ = prob.z_at_theta(x, zfid, theta_eval, atol)
+                g[k, p] = prob.grad_theta(x, zh, theta_eval)
+        return g, np.zeros((nsims_H, 2 * self.ntheta), dtype=np.int32)
+
     def get_maps(self, first_unit, count):
         return np.array(self.z[first_unit:first_unit + count])

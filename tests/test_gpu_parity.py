@@ -590,3 +590,97 @@ def test_corrgauss_unit_results_do_not_depend_on_the_shard():
     for a, b in zip(outs[0], outs[1]):
         np.testing.assert_array_equal(a, b)
     np.testing.assert_array_equal(zs[0], zs[1])
+
+
+# ----------------------------------------------------------------------------- fd_scores, θ-transforms, per-pass profile
+@pytest.mark.parametrize("name,d,kw", [("funnel", 512, {}), ("hiergauss", 5000, {}), ("hiergauss", 700, dict(kernel=1)),
+                                       ("corrgauss", 256, {})])
+def test_fd_scores_reproduces_fd_jacobian_and_takes_asymmetric_points(name, d, kw):
+    """muse_b200_fd_scores is the launch sequence of fd_jacobian with the sample points supplied by the host: at the
+    symmetric points θ₀ ∓ h e_n it must reproduce fd_jacobian's columns to the last bit or two, and at arbitrary points each
+    virtual sim must match the oracle's (sample at θ_sim, MAP + score at θ_eval from the fiducial ẑ)."""
+    nsims, nH = 12, 5
+    fam, draws, xd = make_inputs(name, d, nsims)
+    prob = O.OracleProblem(fam, xd, draws)
+    if name == "corrgauss":
+        kw = dict(kw, P=fam.P, L=fam.L)
+    be = _backend(name, d, nsims, draws, xd, **kw)
+    th0 = theta_start(name)
+    nt = th0.size
+    step = np.full(nt, 0.02) * (1 + np.arange(nt))
+    Hs, _ = be.fd_jacobian(th0, step, nH, 1e-2)
+    pts = np.empty((2 * nt, nt))
+    for n in range(nt):
+        for s in (0, 1):
+            pts[2 * n + s] = th0
+            pts[2 * n + s, n] = th0[n] + (0.0 + step[n] * (1.0 if s else -1.0))
+    g, status = be.fd_scores(th0, pts, nH, 1e-2)
+    assert g.shape == (nH, 2 * nt, nt) and (status == 0).all()
+    for n in range(nt):
+        col = ((g[:, 2 * n, :] * -0.5 + 0.0) + g[:, 2 * n + 1, :] * 0.5) / step[n]
+        np.testing.assert_allclose(col, Hs[:, :, n], rtol=0, atol=4e-16 * np.abs(g).max() / step[n])   # same launch, same combine
+    # asymmetric points (what a bounded θ produces): every virtual sim against the oracle
+    pts2 = pts + 0.013 * np.arange(1, 2 * nt + 1)[:, None]
+    g2, status2 = be.fd_scores(th0, pts2, nH, 1e-2)
+    assert (status2 == 0).all()
+    xm, _ = prob.sample_x_z("master", th0)
+    zfid, _ = prob.z_at_theta(xm, np.zeros(d), th0, 1e-2)
+    for k in range(nH):
+        for p in range(2 * nt):
+            x, _ = prob.sample_x_z(k, pts2[p])
+            zh, _ = prob.z_at_theta(x, zfid, th0, 1e-2)
+            np.testing.assert_allclose(g2[k, p], prob.grad_theta(x, zh, th0), rtol=RTOL_SIM, atol=1e-7)
+    with pytest.raises(Exception):
+        be.fd_scores(th0, np.full((2 * nt, nt), np.nan), nH, 1e-2)
+    be.close()
+
+
+@pytest.mark.parametrize("d,nsims,prior", [(2048, 60, False), (6000, 40, True)])
+def test_transformed_theta_full_muse_matches_oracle(d, nsims, prior):
+    """θ = (μ, σ) with σ > 0 (transform_θ = (μ, log σ), src/interface.jl:14-28): the outer iteration runs in θ′, scores,
+    J and H are reported in θ (src/muse.jl:172-173, 432, 513, 225-227)."""
+    import museinference_jl_b200 as m
+    fam = O.TransformedFamily(O.HierGauss(d), ("identity", "log"))
+    draws = O.Draws.from_philox(4321, nsims, d)
+    xd, _ = fam.sample([0.0, 1.0], O.philox_normals(99, 0, 0, d), O.philox_normals(99, 0, 1, d))
+    oprob = O.OracleProblem(fam, xd, draws, O.NormalPrior([0.0, 1.0], [2.0, 0.7]) if prior else None)
+    th0 = np.array([0.5, np.exp(0.3)])
+    ref = O.muse(oprob, th0, nsims=nsims, get_covariance=True)
+    prob = m.SimpleMuseProblem(xd, "hiergauss", m.NormalPrior([0.0, 1.0], [2.0, 0.7]) if prior else None,
+                               theta_transform=("identity", "log"))
+    rng = m.BaseDraws(draws.xi, draws.nu, draws.xi_master, draws.nu_master)
+    res = m.muse(prob, th0, rng=rng, nsims=nsims, get_covariance=True)
+    assert len(res.history) == len(ref.history)
+    np.testing.assert_allclose(res.theta, ref.theta, rtol=RTOL_EST)
+    np.testing.assert_allclose(np.array(res.gs), np.array(ref.gs), rtol=RTOL_SIM, atol=1e-7)
+    np.testing.assert_allclose(res.J, ref.J, rtol=RTOL_EST)
+    np.testing.assert_allclose(res.H, ref.H, rtol=RTOL_EST, atol=RTOL_EST * np.abs(ref.H).max())
+    np.testing.assert_allclose(res.Sigma, ref.Sigma, rtol=10 * RTOL_EST, atol=RTOL_EST * np.abs(ref.Sigma).max())
+    for a, b in zip(res.history, ref.history):
+        np.testing.assert_allclose(a["theta_t"], b["theta_t"], rtol=RTOL_EST)
+        np.testing.assert_allclose(a["g_like_sims_t"], b["g_like_sims_t"], rtol=RTOL_SIM, atol=1e-7)
+    prob.close()
+
+
+def test_profile_splits_solver_time_by_pass_kind():
+    """cold pass, warm pass, get_J! (truth start) and get_H! (fiducial + FD) are reported separately."""
+    name, d, nsims = "funnel", 8192, 64
+    fam, draws, xd = make_inputs(name, d, nsims)
+    be = _backend(name, d, nsims, draws, xd)
+    th = np.array([0.7])
+    be.profile_reset(True)
+    be.map_score(th, th, 1e-2, include_data=True, warm_start=0)
+    be.map_score(th, th, 1e-2, include_data=True, warm_start=1)
+    be.map_score(th, th, 1e-2, include_data=True, warm_start=1)
+    be.map_score(th, th, 1e-2, include_data=False, warm_start=2)
+    be.fd_jacobian(th, np.array([0.01]), 6, 1e-2)
+    p = be.profile_passes()
+    tot = be.profile()
+    assert [p[k]["launches"] for k in ("cold", "warm", "truth", "fiducial", "fd")] == [1, 2, 1, 1, 1]
+    assert p["cold"]["units"] == nsims + 1 and p["warm"]["units"] == 2 * (nsims + 1) and p["truth"]["units"] == nsims
+    assert p["fiducial"]["units"] == 1 and p["fd"]["units"] == 12
+    assert p["cold"]["bytes"] == nsims * 24 * d + 16 * d and p["warm"]["bytes"] == 2 * (nsims * 32 * d + 24 * d)
+    assert abs(sum(v["ms"] for v in p.values()) - tot["solve_ms"]) < 1e-6 * max(1.0, tot["solve_ms"])
+    assert all(v["ms"] > 0 for v in p.values())
+    be.profile_reset(False)
+    be.close()

@@ -102,3 +102,82 @@ def test_unsupported_options_raise():
         getH(res, prob, rng=rng, nsims=2)            # no step and no scores yet
     with pytest.raises(ValueError):
         m.muse(prob, [0.1, 0.2], rng=rng, nsims=10)  # wrong θ length
+
+
+# ----------------------------------------------------------------------------- θ-transforms (src/interface.jl:14-28)
+def _pair_t(d, nsims, prior=None, seed=77):
+    """hiergauss with θ = (μ, σ), σ > 0: host problem with theta_transform=("identity","log") against the oracle's
+    TransformedFamily on identical base normals."""
+    import museinference_jl_b200 as m
+    base = O.HierGauss(d)
+    fam = O.TransformedFamily(base, ("identity", "log"))
+    draws = O.Draws.from_philox(seed, nsims, d)
+    xd, _ = fam.sample([0.0, 1.0], O.philox_normals(99, 0, 0, d), O.philox_normals(99, 0, 1, d))
+    oprob = O.OracleProblem(fam, xd, draws, O.NormalPrior([0.0, 1.0], [2.0, 0.7]) if prior else None)
+    prob = m.SimpleMuseProblem(xd, "hiergauss", m.NormalPrior([0.0, 1.0], [2.0, 0.7]) if prior else None,
+                               theta_transform=("identity", "log"), backend_factory=FakeBackend)
+    rng = m.BaseDraws(draws.xi, draws.nu, draws.xi_master, draws.nu_master)
+    return m, oprob, prob, rng, base, draws, xd
+
+
+@pytest.mark.parametrize("prior", [False, True])
+def test_transformed_theta_driver_matches_oracle(prior):
+    m, oprob, prob, rng, base, draws, xd = _pair_t(150, 30, prior)
+    th0 = np.array([0.5, np.exp(0.3)])
+    ref = O.muse(oprob, th0, nsims=30, get_covariance=True)
+    res = m.muse(prob, th0, rng=rng, nsims=30, get_covariance=True)
+    assert len(res.history) == len(ref.history) >= 2
+    np.testing.assert_allclose(res.theta, ref.theta, rtol=1e-9)
+    np.testing.assert_allclose(np.array(res.gs), np.array(ref.gs), rtol=1e-9)
+    np.testing.assert_allclose(res.J, ref.J, rtol=1e-9)
+    np.testing.assert_allclose(res.H, ref.H, rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(res.Sigma, ref.Sigma, rtol=1e-7)
+    for a, b in zip(res.history, ref.history):
+        for key in ("theta", "theta_t", "theta_unreg", "g_like_sims", "g_like_sims_t", "g_like", "g_prior", "g_post", "H_prior", "H_inv_post"):
+            np.testing.assert_allclose(a[key], b[key], rtol=1e-8, atol=1e-12, err_msg=key)
+    assert res.theta[1] > 0
+
+
+def test_transformed_theta_is_the_base_family_in_unconstrained_space():
+    """Known-answer property: with a flat prior the θ′ iteration of the (μ, σ) problem IS the (μ, ℓ) iteration of the
+    plain family; J and the scores change variables with D = diag(1, 1/σ); the FD H perturbs σ, not ℓ."""
+    m, oprob, prob, rng, base, draws, xd = _pair_t(150, 30, False)
+    th0_t = np.array([0.5, 0.3])
+    plain = O.muse(O.OracleProblem(base, xd, draws), th0_t, nsims=30, get_covariance=True)
+    res = m.muse(prob, [0.5, np.exp(0.3)], rng=rng, nsims=30, get_covariance=True)
+    assert len(res.history) == len(plain.history)
+    for a, b in zip(res.history, plain.history):
+        np.testing.assert_allclose(a["theta_t"], b["theta"], rtol=1e-12)
+        np.testing.assert_allclose(a["g_like_sims_t"], b["g_like_sims"], rtol=1e-10)
+    np.testing.assert_allclose(prob.transform_theta(res.theta), plain.theta, rtol=1e-12)
+    sig = res.history[-1]["theta"][1]
+    D = np.diag([1.0, 1.0 / sig])
+    np.testing.assert_allclose(res.J, D @ plain.J @ D, rtol=1e-9)
+    # H: same quantity up to the O(h²) difference between perturbing σ and perturbing ℓ, and the change of variables at θ̂
+    sig_hat = res.theta[1]
+    Dh = np.diag([1.0, 1.0 / sig_hat])
+    np.testing.assert_allclose(res.H, Dh @ plain.H @ Dh, rtol=0.05, atol=0.05 * np.abs(res.H).max())
+
+
+def test_transform_validation():
+    import museinference_jl_b200 as m
+    x = np.zeros(8)
+    with pytest.raises(ValueError):
+        m.SimpleMuseProblem(x, "hiergauss", theta_transform=("log",), backend_factory=FakeBackend)
+    with pytest.raises(ValueError):
+        m.SimpleMuseProblem(x, "hiergauss", theta_transform=("identity", "sqrt"), backend_factory=FakeBackend)
+    prob = m.SimpleMuseProblem(x, "hiergauss", theta_transform=("identity", "log"), backend_factory=FakeBackend)
+    with pytest.raises(ValueError):
+        prob.transform_theta([0.0, -1.0])
+    t = prob.transform_theta([0.3, 2.0])
+    np.testing.assert_allclose(prob.inv_transform_theta(t), [0.3, 2.0], rtol=1e-15)
+    # analytic transformed-space prior derivatives against central differences of logπ(inv(θ′))
+    pr = m.NormalPrior([0.0, 1.0], [2.0, 0.7])
+    prob = m.SimpleMuseProblem(x, "hiergauss", pr, theta_transform=("identity", "log"), backend_factory=FakeBackend)
+    f = lambda tt: pr.logp(prob.inv_transform_theta(tt))
+    tt = np.array([0.4, -0.2])
+    h = 1e-5
+    gnum = np.array([(f(tt + h * e) - f(tt - h * e)) / (2 * h) for e in np.eye(2)])
+    np.testing.assert_allclose(prob.prior_grad_t(tt), gnum, rtol=1e-7)
+    Hnum = np.array([(prob.prior_grad_t(tt + h * e) - prob.prior_grad_t(tt - h * e)) / (2 * h) for e in np.eye(2)])
+    np.testing.assert_allclose(prob.prior_hess_t(tt), Hnum, rtol=1e-7, atol=1e-9)
