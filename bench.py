@@ -333,6 +333,7 @@ def run_b200(args):
     clocks = sampler.stop() if rank == 0 else None
     ms = e0.elapsed_time(e1)
     prof = be.profile()
+    passes = be.profile_passes()       # the same solver figures split by pass kind (cold, warm, …)
     be.profile_reset(False)
     units_local = prof["solve_units"]
 
@@ -442,7 +443,20 @@ def run_b200(args):
                          "avg_launch_ms": solve_ms_sum / max(1, prof["solve_launches"] * world),
                          "kernel_share_of_step": solve_ms_sum / world / ms},
         }
+        # per pass kind on rank 0 (CUDA events over each launch chain): average launch time, units and, for the HBM-bound
+        # families, algorithmic GB/s — "grad-eval HBM GB/s vs peak" for the cold and the warm pass separately
+        by_pass = {}
+        for kind, v in passes.items():
+            if v["launches"]:
+                e = {"launches_per_step": v["launches"] / args.steps, "units_per_launch": v["units"] / v["launches"],
+                     "avg_launch_ms": v["ms"] / v["launches"], "sims_per_s": v["units"] / (v["ms"] * 1e-3) if v["ms"] > 0 else None}
+                if v["bytes"] > 0 and v["ms"] > 0:
+                    e["algorithmic_gbs"] = v["bytes"] / 1e9 / (v["ms"] * 1e-3)
+                    e["frac_of_hbm_peak"] = e["algorithmic_gbs"] / hbm_peak
+                by_pass[kind] = e
+        line["roofline"]["passes"] = by_pass
         if tensor_roof is not None:
+            tensor_roof["passes"] = by_pass
             line["roofline"] = tensor_roof
             line["config"]["l2"] = "inputs_larger_than_l2 (Σ₀⁻¹ 134 MB + batch arrays ≥ 268 MB each at d=4096, nsims=8192)"
         if world == 1 and not args.no_cpu_baseline:

@@ -101,7 +101,11 @@ def _worker_topup(rank, world, port, q):
         getJ(res, prob, rng=rng, nsims=8, pool=pool)
         getJ(res, prob, rng=rng, nsims=21, pool=pool)           # top-up across the shard boundary (src/muse.jl:499-506)
         getH(res, prob, rng=rng, nsims=5, pool=pool)
-        q.put((rank, np.array(res.gs), res.J, res.H, res.Sigma))
+        # the same problem with θ = (μ, σ), σ > 0 (transform_θ = (μ, log σ)): full solve sharded over the two ranks
+        import oracle as O
+        tprob = m.SimpleMuseProblem(xd, "hiergauss", theta_transform=("identity", "log"), backend_factory=FakeBackend)
+        tres = m.muse(tprob, [0.5, np.exp(0.3)], rng=rng, nsims=21, get_covariance=True, pool=pool)
+        q.put((rank, np.array(res.gs), res.J, res.H, res.Sigma, tres.theta, tres.J, tres.H))
     finally:
         dist.destroy_process_group()
 
@@ -126,13 +130,19 @@ def test_two_rank_get_J_top_up_and_get_H():
     ref = O.MuseResult(theta=np.array([0.2, 0.1]))
     O.get_J_bang(ref, oprob, nsims=21)
     O.get_H_bang(ref, oprob, nsims=5)
-    for rank, gs, J, H, Sigma in outs:
+    tfam = O.TransformedFamily(oprob.family, ("identity", "log"))
+    tref = O.muse(O.OracleProblem(tfam, oprob.x, oprob.draws), [0.5, np.exp(0.3)], nsims=21, get_covariance=True)
+    for rank, gs, J, H, Sigma, t_theta, t_J, t_H in outs:
+        np.testing.assert_allclose(t_theta, tref.theta, rtol=1e-9)
+        np.testing.assert_allclose(t_J, tref.J, rtol=1e-9)
+        np.testing.assert_allclose(t_H, tref.H, rtol=1e-7, atol=1e-9)
         assert gs.shape == (21, 2)
         np.testing.assert_allclose(gs, np.array(ref.gs), rtol=1e-12)
         np.testing.assert_allclose(J, ref.J, rtol=1e-12)
         np.testing.assert_allclose(H, ref.H, rtol=1e-9, atol=1e-12)
         np.testing.assert_allclose(Sigma, ref.Sigma, rtol=1e-9)
     np.testing.assert_array_equal(outs[0][1], outs[1][1])
+    np.testing.assert_array_equal(outs[0][5], outs[1][5])
 
 
 def test_block_partition():
