@@ -13,7 +13,15 @@
 // FP64 log/sincospi are ~150 FP64 instructions per pair, so this kernel is compute-bound; it
 // runs once per seed (draws are stored and re-read, 16·d B per sim per pass, which is cheaper
 // than regenerating them).
+#include <cstdlib>
+
 #include "muse_common.cuh"
+#include "muse_draw_tables.cuh"
+#include "muse_normal_math.cuh"
+
+#ifndef MUSE_DRAWS_IMPL_DEFAULT
+#define MUSE_DRAWS_IMPL_DEFAULT 1
+#endif
 
 namespace muse {
 
@@ -65,6 +73,42 @@ philox_draws_kernel(double* __restrict__ xi, double* __restrict__ nu, int rows, 
     }
 }
 
+// The same generator with the table-driven transform of muse_normal_math.cuh (tables staged in shared memory once per
+// CTA): ≈ 55 issue slots for Philox + ≈ 75 for the transform and the store, against ≈ 250 per pair above.
+__global__ void __launch_bounds__(256)
+philox_draws_tab_kernel(double* __restrict__ xi, double* __restrict__ nu, int rows, int d, int ld,
+                        uint32_t k0, uint32_t k1, int64_t sim_offset, int master_row) {
+    __shared__ __align__(16) double s_log[91][2];
+    __shared__ __align__(16) double s_trig[256][2];
+    for (int i = threadIdx.x; i < 91 * 2; i += 256) (&s_log[0][0])[i] = (&kLogTab[0][0])[i];
+    for (int i = threadIdx.x; i < 256 * 2; i += 256) (&s_trig[0][0])[i] = (&kTrigTab[0][0])[i];
+    __syncthreads();
+    const int npairs = (d + 1) >> 1;
+    const int p = blockIdx.x * 256 + threadIdx.x;
+    if (p >= npairs) return;
+    for (int rs = blockIdx.y; rs < 2 * rows; rs += gridDim.y) {
+        const int stream = rs & 1;
+        const int row = rs >> 1;
+        const uint32_t G = (row == master_row) ? 0xFFFFFFFFu : (uint32_t)(sim_offset + row);
+        uint32_t r[4];
+        philox4x32_10((uint32_t)p, G, (uint32_t)stream, 0u, k0, k1, r);
+        double n0, n1;
+        box_muller_tab(r[0], r[1], r[2], r[3], s_log, s_trig, &n0, &n1);
+        double* dst = (stream ? nu : xi) + (size_t)row * ld + 2 * (size_t)p;
+        if (2 * p + 1 < d) {
+            *reinterpret_cast<double2*>(dst) = make_double2(n0, n1);
+        } else {
+            dst[0] = n0;
+        }
+    }
+}
+
+// MUSE_DRAWS_IMPL: 1 = table-driven transform (default), 0 = libm log / sincospi (the first implementation, kept for A/B)
+static int draws_impl() {
+    static const int impl = [] { const char* e = std::getenv("MUSE_DRAWS_IMPL"); return e ? std::atoi(e) : MUSE_DRAWS_IMPL_DEFAULT; }();
+    return impl;
+}
+
 cudaError_t launch_philox_draws(double* xi, double* nu, int rows, int d, int ld, uint64_t seed,
                                 int64_t sim_offset, int master_row, cudaStream_t st) {
     if (rows <= 0) return cudaSuccess;
@@ -72,8 +116,12 @@ cudaError_t launch_philox_draws(double* xi, double* nu, int rows, int d, int ld,
     // a thread walks several (row, stream) slots of its pair column: set-up (constants, addressing) is paid once
     const int ny = 2 * rows < 96 ? 2 * rows : 96;
     dim3 grid((unsigned)((npairs + 255) / 256), (unsigned)ny);
-    philox_draws_kernel<<<grid, 256, 0, st>>>(xi, nu, rows, d, ld, (uint32_t)(seed & 0xFFFFFFFFu),
-                                             (uint32_t)(seed >> 32), sim_offset, master_row);
+    if (draws_impl() == 1)
+        philox_draws_tab_kernel<<<grid, 256, 0, st>>>(xi, nu, rows, d, ld, (uint32_t)(seed & 0xFFFFFFFFu),
+                                                     (uint32_t)(seed >> 32), sim_offset, master_row);
+    else
+        philox_draws_kernel<<<grid, 256, 0, st>>>(xi, nu, rows, d, ld, (uint32_t)(seed & 0xFFFFFFFFu),
+                                                 (uint32_t)(seed >> 32), sim_offset, master_row);
     return cudaGetLastError();
 }
 
