@@ -175,4 +175,20 @@ function MuseInference.get_H!(result::MuseResult, prob::B200MuseProblem, θ₀ =
     finalize_result!(result, prob)
 end
 
+# Bounded θ (transform_θ / inv_transform_θ, src/interface.jl:14-28).  The kernels take the unconstrained θ′ and return
+# ∇θ′ logLike, so a problem with positive components passes θ′ = transform_θ(prob, θ) to `map_score`, divides the scores by
+# ∂θ/∂θ′ where the reference asks for UnTransformedθ() (src/muse.jl:172, 432, 513), and — because pjacobian perturbs the
+# UNtransformed θ₀ (src/util.jl:15) — gets the raw ± scores of get_H!'s virtual sims at the mapped points from this call,
+# forming sum(fs .* [-1/2, 0, 1/2]) / step itself (museinference.jl_b200/muse.py does exactly this; DESIGN.md §8.1).
+function fd_scores(p::B200MuseProblem, h, θeval′, θsims′::Matrix{Float64}, nsims_H, atol)
+    nθ = ntheta(p)
+    size(θsims′) == (nθ, 2nθ) || error("θsims′ must be nθ × 2nθ (column 2n-1 / 2n = the − / + point of Jacobian column n)")
+    g = Array{Float64}(undef, nθ, 2nθ, nsims_H)       # column-major (i, point, k) == C row-major [k][point][i]
+    te = collect(Float64, θeval′)
+    GC.@preserve te θsims′ g check(h, ccall((:muse_b200_fd_scores, libmuse), Cint,
+        (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Cint, Cdouble, Ptr{Cdouble}, Ptr{Cint}),
+        h, te, θsims′, nsims_H, atol, g, C_NULL))
+    g
+end
+
 end # module
