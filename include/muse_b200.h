@@ -264,6 +264,20 @@ int  muse_b200_muse_covariance(muse_handle* h, const double* theta, const double
                                int32_t nsims_total, int32_t nsims_h_total, const int32_t* counts_h, double atol,
                                const double* prior_sigma /* NULL: flat prior */, muse_cov_out* out);
 
+/* muse_iterate + muse_covariance in ONE call with the θ update on the DEVICE (csrc/muse_outer.cu): a single-CTA kernel per
+ * pass does the arithmetic of src/muse.jl:183-224 and the convergence test of :163-166 and writes the θ-dependent constants
+ * of the next pass into device memory, so consecutive passes — and get_H!'s fiducial solve and virtual sims, whose step
+ * 0.1 ./ std(gs) (:411-413) is derived on the device too — follow each other on the stream without a host round trip; the host
+ * synchronises once per chunk of three passes (the typical solve: once).  Isotropic families only (corrgauss: use
+ * muse_iterate), maxsteps ≤ 64.  Same outputs as the two calls it replaces; θ agrees with them to round-off (parallel
+ * reductions, device libm), not bit for bit; seconds_hist holds the chunk's wall time divided by its iterations.
+ * get_covariance = 0: the loop only (cov may be NULL). */
+int  muse_b200_muse_solve(muse_handle* h, const double* theta0, int32_t nsims_total, const int32_t* counts,
+                          int32_t maxsteps, double theta_rtol, double atol, double alpha, int32_t first_start,
+                          const double* prior_mean, const double* prior_sigma /* NULL: flat prior */,
+                          int32_t get_covariance, int32_t nsims_h_total, const int32_t* counts_h,
+                          muse_iterate_out* out, muse_cov_out* cov);
+
 /* MAPs of units [first_unit, first_unit+count) (unit 0 = data) — `save_MAPs`, src/muse.jl:139-143,219 */
 int  muse_b200_get_maps(muse_handle* h, int32_t first_unit, int32_t count, double* z_out /* count × d */);
 

@@ -193,12 +193,10 @@ class B200Backend:
         self._check(self._lib.muse_b200_allgather_rows(self._h, _dp(local), int(ncol), _ip(counts), _dp(out)))
         return out
 
-    def muse_iterate(self, theta0, nsims_total: int, counts, maxsteps: int, theta_rtol, atol, alpha, first_start: int,
-                     prior_mean=None, prior_sigma=None):
-        """The outer θ loop of muse! inside the library (include/muse_b200.h: muse_b200_muse_iterate)."""
-        nt, units, N, K = self.ntheta, self.nsims + 1, int(nsims_total), int(maxsteps)
-        t0 = self._theta(theta0)
-        # history buffers are allocated once per (maxsteps, nsims) and reused: the caller copies what it keeps
+    def _iterate_buffers(self, K: int, N: int):
+        """History buffers of the in-library loops, allocated once per (maxsteps, nsims) and reused: the caller copies
+        what it keeps."""
+        nt, units = self.ntheta, self.nsims + 1
         cache = self.__dict__.setdefault("_iterate_bufs", {})
         if (K, N) not in cache:
             f = lambda *shape: np.zeros(shape)
@@ -212,7 +210,14 @@ class B200Backend:
                 setattr(o, name, _ip(arr) if arr.dtype == np.int32 else _dp(arr))
             cache.clear()
             cache[(K, N)] = (res, o)
-        res, o = cache[(K, N)]
+        return cache[(K, N)]
+
+    def muse_iterate(self, theta0, nsims_total: int, counts, maxsteps: int, theta_rtol, atol, alpha, first_start: int,
+                     prior_mean=None, prior_sigma=None):
+        """The outer θ loop of muse! inside the library (include/muse_b200.h: muse_b200_muse_iterate)."""
+        N, K = int(nsims_total), int(maxsteps)
+        t0 = self._theta(theta0)
+        res, o = self._iterate_buffers(K, N)
         cnt = np.ascontiguousarray(counts, dtype=np.int32) if counts is not None else None
         pm = self._theta(prior_mean) if prior_mean is not None else None
         ps = self._theta(prior_sigma) if prior_sigma is not None else None
@@ -221,6 +226,29 @@ class B200Backend:
         out = dict(res)
         out["n_iter"] = int(o.n_iter)
         return out
+
+    def muse_solve(self, theta0, nsims_total: int, counts, maxsteps: int, theta_rtol, atol, alpha, first_start: int,
+                   prior_mean=None, prior_sigma=None, get_covariance: bool = False, nsims_h_total: int = 0, counts_h=None):
+        """Loop + covariance stage with the θ update on the device (include/muse_b200.h: muse_b200_muse_solve).
+        Returns (iterate dict as muse_iterate, covariance dict as muse_covariance or None)."""
+        nt, N, K = self.ntheta, int(nsims_total), int(maxsteps)
+        t0 = self._theta(theta0)
+        res, o = self._iterate_buffers(K, N)
+        cnt = np.ascontiguousarray(counts, dtype=np.int32) if counts is not None else None
+        cnth = np.ascontiguousarray(counts_h, dtype=np.int32) if counts_h is not None else None
+        pm = self._theta(prior_mean) if prior_mean is not None else None
+        ps = self._theta(prior_sigma) if prior_sigma is not None else None
+        cres, co = None, None
+        if get_covariance:
+            cres = dict(J=np.zeros((nt, nt)), step=np.zeros(nt), Hs=np.zeros((int(nsims_h_total), nt, nt)), H=np.zeros((nt, nt)),
+                        Sigma_inv=np.zeros((nt, nt)), Sigma=np.zeros((nt, nt)))
+            co = _capi.muse_cov_out(**{k: _dp(v) for k, v in cres.items()})
+        self._check(self._lib.muse_b200_muse_solve(self._h, _dp(t0), N, _ip(cnt), K, float(theta_rtol), float(atol), float(alpha),
+                                                   int(first_start), _dp(pm), _dp(ps), int(bool(get_covariance)), int(nsims_h_total),
+                                                   _ip(cnth), C.byref(o), C.byref(co) if co is not None else None))
+        out = dict(res)
+        out["n_iter"] = int(o.n_iter)
+        return out, cres
 
     def muse_covariance(self, theta, gs, nsims_h_total: int, counts_h, atol, prior_sigma=None):
         """J, FD Jacobians, H and Σ after the loop (include/muse_b200.h: muse_b200_muse_covariance)."""

@@ -85,6 +85,29 @@ static int ensure_outputs(muse_handle* h, int items) {
     return 0;
 }
 
+// a stand-alone output block of the same layout (device-resident outer loop: one per pass of a chunk)
+int muse_outblock_ensure(muse_handle* h, OutBlock& ob, int items) {
+    if (items <= ob.cap) return 0;
+    muse_outblock_free(ob);
+    const size_t n = (size_t)items, nt = (size_t)h->cfg.ntheta;
+    const size_t n_i = (n + 1) & ~(size_t)1;
+    ob.bytes = n * (nt + 2) * sizeof(double) + 3 * n_i * sizeof(int);
+    CUDA_TRY(h, cudaMalloc(&ob.d, ob.bytes));
+    CUDA_TRY(h, cudaMallocHost(&ob.hst, ob.bytes));
+    ob.g_d = reinterpret_cast<double*>(ob.d); ob.gnorm_d = ob.g_d + n * nt; ob.f_d = ob.gnorm_d + n;
+    ob.iters_d = reinterpret_cast<int*>(ob.f_d + n); ob.fg_d = ob.iters_d + n_i; ob.status_d = ob.fg_d + n_i;
+    ob.g_h = reinterpret_cast<double*>(ob.hst); ob.gnorm_h = ob.g_h + n * nt;
+    ob.iters_h = reinterpret_cast<int*>(ob.gnorm_h + 2 * n); ob.fg_h = ob.iters_h + n_i; ob.status_h = ob.fg_h + n_i;
+    ob.cap = items;
+    return 0;
+}
+
+void muse_outblock_free(OutBlock& ob) {
+    cudaFree(ob.d);
+    cudaFreeHost(ob.hst);
+    ob = OutBlock{};
+}
+
 static void fill_common(muse_handle* h, SolveLaunch& L) {
     std::memset(&L, 0, sizeof(L));
     L.d = h->cfg.d;
@@ -148,9 +171,46 @@ static int launch_solver(muse_handle* h, const SolveLaunch& L, double bytes) {
         r.units = L.nitems;
         r.bytes = bytes;
         r.kind = h->pass_kind;
+        r.tag = h->rec_tag;
         h->recs.push_back(r);
     }
     return 0;
+}
+
+// One solver pass over (data?) + sims [first_sim, first_sim + count) enqueued on the stream.  ob: where the per-unit outputs
+// go (null: the handle's main block); dyn: θ-dependent constants in device memory (null: computed here from theta_*).
+int muse_pass_enqueue(muse_handle* h, const double* theta_sim, const double* theta_eval, double atol, int include_data,
+                      int warm_start, int first_sim, int count, const OutBlock* ob, const DynConsts* dyn) {
+    const int items = count + (include_data ? 1 : 0);
+    h->pass_kind = warm_start == MUSE_START_ZEROS ? MUSE_PASS_COLD : (warm_start == MUSE_START_TRUTH ? MUSE_PASS_TRUTH : MUSE_PASS_WARM);
+    if (h->corr) return muse_corr_map_score(h, theta_sim, theta_eval, atol, include_data, warm_start, first_sim, count);
+    SolveLaunch L;
+    fill_common(h, L);
+    L.nitems = items;
+    L.mode = 0;
+    L.include_data = include_data ? 1 : 0;
+    L.first_sim = first_sim;
+    L.atol = atol;
+    if (dyn) L.dyn = dyn;
+    else if (theta_consts(h->cfg, theta_sim, theta_eval, &L.smp[0], &L.ev) != 0) MUSE_FAIL(h, MUSE_EUNSUPPORTED, "family");
+    switch (warm_start) {
+        case MUSE_START_ZEROS: L.start_kind = kStartZero; break;
+        case MUSE_START_PREV: L.start_kind = kStartOwn; break;
+        case MUSE_START_TRUTH: L.start_kind = kStartTruth; break;
+        default: L.start_kind = kStartSharedKeep; L.zshared = h->z0user; break;
+    }
+    L.zA = h->zA;
+    L.zB = h->zB;
+    L.zstate = h->zstate;
+    if (ob) {
+        L.g_out = ob->g_d; L.iters_out = ob->iters_d; L.fg_out = ob->fg_d;
+        L.gnorm_out = ob->gnorm_d; L.f_out = ob->f_d; L.status_out = ob->status_d;
+    }
+    // algorithmic bytes (DESIGN.md §4): per sim read ξ, ν (16d) [+ z₀ 8d], write ẑ (8d); data unit reads x (8d)
+    const double d8 = 8.0 * h->cfg.d;
+    const double z0b = (warm_start == MUSE_START_PREV || warm_start == MUSE_START_USER) ? d8 : 0.0;
+    const double bytes = count * (3 * d8 + z0b) + (include_data ? (2 * d8 + z0b) : 0.0);
+    return launch_solver(h, L, bytes);
 }
 
 extern "C" {
@@ -282,6 +342,7 @@ int muse_b200_destroy(muse_handle* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (auto& r : h->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     muse_comm_release(h);
+    muse_outer_release(h);
     muse_corr_destroy(h);
     cudaFree(h->xi); cudaFree(h->nu); cudaFree(h->xi_h); cudaFree(h->nu_h); cudaFree(h->xdat); cudaFree(h->z0user);
     cudaFree(h->xslot); cudaFree(h->zA); cudaFree(h->zB); cudaFree(h->zstate);
@@ -437,30 +498,7 @@ int muse_b200_map_score_async(muse_handle* h, const double* theta_sim, const dou
     const int items = count + (include_data ? 1 : 0);
     if (items == 0) return MUSE_OK;
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
-    h->pass_kind = warm_start == MUSE_START_ZEROS ? MUSE_PASS_COLD : (warm_start == MUSE_START_TRUTH ? MUSE_PASS_TRUTH : MUSE_PASS_WARM);
-    if (h->corr) return muse_corr_map_score(h, theta_sim, theta_eval, atol, include_data, warm_start, first_sim, count);
-    SolveLaunch L;
-    fill_common(h, L);
-    L.nitems = items;
-    L.mode = 0;
-    L.include_data = include_data ? 1 : 0;
-    L.first_sim = first_sim;
-    L.atol = atol;
-    if (theta_consts(h->cfg, theta_sim, theta_eval, &L.smp[0], &L.ev) != 0) MUSE_FAIL(h, MUSE_EUNSUPPORTED, "family");
-    switch (warm_start) {
-        case MUSE_START_ZEROS: L.start_kind = kStartZero; break;
-        case MUSE_START_PREV: L.start_kind = kStartOwn; break;
-        case MUSE_START_TRUTH: L.start_kind = kStartTruth; break;
-        default: L.start_kind = kStartSharedKeep; L.zshared = h->z0user; break;
-    }
-    L.zA = h->zA;
-    L.zB = h->zB;
-    L.zstate = h->zstate;
-    // algorithmic bytes (DESIGN.md §4): per sim read ξ, ν (16d) [+ z₀ 8d], write ẑ (8d); data unit reads x (8d)
-    const double d8 = 8.0 * h->cfg.d;
-    const double z0b = (warm_start == MUSE_START_PREV || warm_start == MUSE_START_USER) ? d8 : 0.0;
-    const double bytes = count * (3 * d8 + z0b) + (include_data ? (2 * d8 + z0b) : 0.0);
-    return launch_solver(h, L, bytes);
+    return muse_pass_enqueue(h, theta_sim, theta_eval, atol, include_data, warm_start, first_sim, count, nullptr, nullptr);
 }
 
 int muse_b200_fetch(muse_handle* h, int32_t units, double* g_out, int32_t* iters_out, int32_t* fg_out,
@@ -496,10 +534,8 @@ int muse_b200_device_scores(muse_handle* h, double** g_dev, int32_t* capacity_un
 }
 
 // fetch the ± scores and form central_fdm(3,1): sum(fs .* [-1/2, 0, 1/2]) / step   — src/util.jl:13-19
-static int fd_combine(muse_handle* h, const double* step, int nsims_H, double* Hs_out, int32_t* status_out) {
+void muse_fd_combine_host(muse_handle* h, const double* step, int nsims_H, double* Hs_out, int32_t* status_out) {
     const int nt = h->cfg.ntheta, items = nsims_H * nt * 2;
-    int rc = muse_b200_fetch(h, items, h->g_h, nullptr, nullptr, nullptr, status_out ? h->status_h : nullptr);
-    if (rc != 0) return rc;
     if (status_out) std::memcpy(status_out, h->status_h, (size_t)items * sizeof(int));
     for (int k = 0; k < nsims_H; ++k)
         for (int n = 0; n < nt; ++n) {
@@ -512,12 +548,21 @@ static int fd_combine(muse_handle* h, const double* step, int nsims_H, double* H
                 Hs_out[((size_t)k * nt + i) * nt + n] = acc / step[n];
             }
         }
+}
+
+static int fd_combine(muse_handle* h, const double* step, int nsims_H, double* Hs_out, int32_t* status_out) {
+    const int nt = h->cfg.ntheta, items = nsims_H * nt * 2;
+    int rc = muse_b200_fetch(h, items, h->g_h, nullptr, nullptr, nullptr, status_out ? h->status_h : nullptr);
+    if (rc != 0) return rc;
+    muse_fd_combine_host(h, step, nsims_H, Hs_out, status_out);
     return MUSE_OK;
 }
 
+
 // Shared launch sequence of muse_b200_fd_jacobian / muse_b200_fd_scores: the fiducial solve and the 2·nθ virtual sims per
 // H sim, sampled at the rows of th_pts (row 2n = the "−" point of column n, row 2n+1 its "+" point), MAP + score at theta0.
-static int fd_launch(muse_handle* h, const double* theta0, const double* th_pts, int nsims_H, double atol) {
+static int fd_launch(muse_handle* h, const double* theta0, const double* th_pts, int nsims_H, double atol,
+                     const DynConsts* dyn_fid = nullptr, const DynConsts* dyn_fd = nullptr) {
     const bool hshard = h->cfg.nsims_h > 0;
     const int nt = h->cfg.ntheta;
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
@@ -545,7 +590,8 @@ static int fd_launch(muse_handle* h, const double* theta0, const double* th_pts,
     F.mode = 2;
     F.atol = atol;
     F.start_kind = kStartZero;
-    if (theta_consts(h->cfg, theta0, theta0, &F.smp[0], &F.ev) != 0) MUSE_FAIL(h, MUSE_EUNSUPPORTED, "family");
+    if (dyn_fid) F.dyn = dyn_fid;
+    else if (theta_consts(h->cfg, theta0, theta0, &F.smp[0], &F.ev) != 0) MUSE_FAIL(h, MUSE_EUNSUPPORTED, "family");
     F.zA = h->zfidA;
     F.zB = h->zfidB;
     F.zstate = h->zfid_state;
@@ -565,8 +611,11 @@ static int fd_launch(muse_handle* h, const double* theta0, const double* th_pts,
     L.zsharedA = h->zfidA;
     L.zsharedB = h->zfidB;
     if (hshard) { L.xi = h->xi_h; L.nu = h->nu_h; }
-    if (theta_consts(h->cfg, theta0, theta0, nullptr, &L.ev) != 0) MUSE_FAIL(h, MUSE_EUNSUPPORTED, "family");
-    for (int p = 0; p < 2 * nt; ++p) theta_consts(h->cfg, th_pts + (size_t)p * nt, theta0, &L.smp[p], nullptr);
+    if (dyn_fd) L.dyn = dyn_fd;
+    else {
+        if (theta_consts(h->cfg, theta0, theta0, nullptr, &L.ev) != 0) MUSE_FAIL(h, MUSE_EUNSUPPORTED, "family");
+        for (int p = 0; p < 2 * nt; ++p) theta_consts(h->cfg, th_pts + (size_t)p * nt, theta0, &L.smp[p], nullptr);
+    }
     L.zA = h->zHA;
     L.zB = h->zHB;
     L.zstate = nullptr;
@@ -574,6 +623,11 @@ static int fd_launch(muse_handle* h, const double* theta0, const double* th_pts,
     // algorithmic bytes: read ξ, ν per virtual sim; the shared start ẑ_fid is read once (L2)
     h->pass_kind = MUSE_PASS_FD;
     return launch_solver(h, L, items * 2 * d8 + d8);
+}
+
+int muse_fd_enqueue(muse_handle* h, const double* theta0, const double* th_pts, int nsims_H, double atol,
+                    const DynConsts* dyn_fid, const DynConsts* dyn_fd) {
+    return fd_launch(h, theta0, th_pts, nsims_H, atol, dyn_fid, dyn_fd);
 }
 
 static int fd_check(muse_handle* h, int nsims_H) {

@@ -167,6 +167,15 @@ int muse_comm_allgather_scores_enqueue(muse_handle* h, int first_row, const int3
     return allgather_impl(h, h->g_d + (size_t)first_row * h->cfg.ntheta, nullptr, h->cfg.ntheta, counts, nullptr);
 }
 
+// the same from an arbitrary device source (the device-resident outer loop gathers from a per-pass output block);
+// *need_out = doubles per rank slot of the receive area h->comm_recv
+int muse_comm_allgather_dev_enqueue(muse_handle* h, const double* src_dev, int ncol, const int32_t* counts, size_t* need_out) {
+    int maxc = 1;
+    for (int r = 0; r < h->comm_nranks; ++r) maxc = counts[r] > maxc ? counts[r] : maxc;
+    if (need_out) *need_out = (size_t)maxc * ncol;
+    return allgather_impl(h, src_dev, nullptr, ncol, counts, nullptr);
+}
+
 int muse_b200_allgather_scores(muse_handle* h, int32_t first_row, const int32_t* counts, double* out_host) {
     if (!h || !counts || !out_host || first_row < 0) return MUSE_EINVAL;
     if (h->comm && first_row + counts[h->comm_rank] > h->out_cap) { h->err = "score rows outside the device output buffer"; return MUSE_EINVAL; }

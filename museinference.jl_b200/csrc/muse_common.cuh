@@ -28,6 +28,16 @@ struct IsoSample {
     double mu;
 };
 
+// θ-dependent constants of a launch held in DEVICE memory: written by the θ-update kernel of the device-resident outer loop
+// (muse_outer.cu) and read by the solver kernels of the next pass, so that no host round trip sits between two passes.
+// skip != 0: the pass is not needed (the loop has converged or failed) — every kernel of the launch returns at once.
+struct DynConsts {
+    IsoEval ev;
+    IsoSample smp[kMaxThetaSim];
+    int skip;
+    int pad;
+};
+
 // where the start vector z₀ of a unit comes from
 enum StartKind : int {
     kStartZero = 0,        // z₀ ≡ 0, never read from memory
@@ -56,6 +66,7 @@ struct SolveLaunch {
     double atol;
     IsoEval ev;                      // at θ_eval
     IsoSample smp[kMaxThetaSim];     // mode 0: [0]; mode 1: index 2n+s ↔ θ₀ ∓/± h_n e_n
+    const DynConsts* dyn;            // non-null: ev / smp come from device memory instead (launch_ev / launch_smp below)
     // inputs
     const double* xi;    // nsims+1 rows (row nsims = master draw)
     const double* nu;
@@ -100,6 +111,12 @@ struct SolveLaunch {
     unsigned long long* redo_total;   // … since handle creation (diagnostics)
     int* redo_items;
 };
+
+#if defined(__CUDACC__)
+__device__ __forceinline__ IsoEval launch_ev(const SolveLaunch& L) { return L.dyn ? L.dyn->ev : L.ev; }
+__device__ __forceinline__ IsoSample launch_smp(const SolveLaunch& L, int t) { return L.dyn ? L.dyn->smp[t] : L.smp[t]; }
+__device__ __forceinline__ bool launch_skipped(const SolveLaunch& L) { return L.dyn != nullptr && L.dyn->skip != 0; }
+#endif
 
 struct Geometry {
     int group_threads;   // threads per CTA taking part in a solve (32 → one warp per solve)

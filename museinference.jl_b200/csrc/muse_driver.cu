@@ -68,13 +68,13 @@ bool invert_small(double* a, int n) {
 
 }  // namespace
 
-extern "C" int muse_b200_muse_covariance(muse_handle* h, const double* theta, const double* gs, int32_t nsims_total,
-                                         int32_t nsims_h_total, const int32_t* counts_h, double atol,
-                                         const double* prior_sigma, muse_cov_out* out) {
-    if (!h || !theta || !gs || !out || nsims_total < 2 || nsims_h_total < 1) return MUSE_EINVAL;
+// J from the scores, exchange of the per-sim Jacobians, H and Σ — the host arithmetic of the covariance stage, shared by
+// muse_b200_muse_covariance (below) and the device-resident loop (muse_outer.cu).  out->step is left to the caller.
+int muse_cov_finish(muse_handle* h, const double* theta, const double* gs, int nsims_total, int nsims_h_total, const int32_t* counts_h,
+                    const double* Hs_local, int mine, const double* prior_sigma, muse_cov_out* out) {
+    (void)theta;
     const int nt = h->cfg.ntheta;
     const bool multi = h->comm != nullptr && h->comm_nranks > 1;
-    if (multi && !counts_h) { h->err = "counts_h (H sims per rank) required with a communicator"; return MUSE_EINVAL; }
     // J = var(gs) | cov(SimpleCovariance(corrected = true), gs)                       src/muse.jl:529
     std::vector<double> mean(nt);
     for (int c = 0; c < nt; ++c) mean[c] = sum8(nsims_total, [&](int k) { return gs[(size_t)k * nt + c]; }) / nsims_total;
@@ -83,21 +83,11 @@ extern "C" int muse_b200_muse_covariance(muse_handle* h, const double* theta, co
             const double q = sum8(nsims_total, [&](int k) { return (gs[(size_t)k * nt + a] - mean[a]) * (gs[(size_t)k * nt + b] - mean[b]); });
             out->J[a * nt + b] = out->J[b * nt + a] = q / (nsims_total - 1);
         }
-    // step = 0.1 ./ std(gs)                                                           src/muse.jl:411-413
-    for (int c = 0; c < nt; ++c) out->step[c] = 0.1 / std::sqrt(out->J[c * nt + c]);
-    // per-sim finite-difference Jacobians of this rank's H shard, then their exchange  src/muse.jl:417-442
-    const int mine = multi ? counts_h[h->comm_rank] : nsims_h_total;
-    std::vector<double> local((size_t)(mine > 0 ? mine : 1) * nt * nt);
-    std::vector<int32_t> status((size_t)(mine > 0 ? mine : 1) * nt * 2, 0);
-    int rc = muse_b200_fd_jacobian(h, theta, out->step, mine, atol, local.data(), status.data());
-    if (rc != MUSE_OK) return rc;
-    for (size_t i = 0; i < (size_t)mine * nt * 2; ++i)
-        if (status[i] == MUSE_STATUS_NONFINITE) { h->err = "get_H!: MAP solution failed with a non-finite objective"; return MUSE_ESTATE; }
     if (multi) {
-        rc = muse_b200_allgather_rows(h, local.data(), nt * nt, counts_h, out->Hs);
+        const int rc = muse_b200_allgather_rows(h, Hs_local, nt * nt, counts_h, out->Hs);
         if (rc != MUSE_OK) return rc;
     } else {
-        std::memcpy(out->Hs, local.data(), (size_t)mine * nt * nt * sizeof(double));
+        std::memcpy(out->Hs, Hs_local, (size_t)mine * nt * nt * sizeof(double));
     }
     // H = mean(Hs)                                                                    src/muse.jl:446
     for (int e = 0; e < nt * nt; ++e)
@@ -122,6 +112,30 @@ extern "C" int muse_b200_muse_covariance(muse_handle* h, const double* theta, co
     std::memcpy(out->Sigma, out->Sigma_inv, sizeof(double) * nt * nt);
     if (!invert_small(out->Sigma, nt)) { h->err = "finalize_result!: Σ⁻¹ is singular"; return MUSE_ESTATE; }
     return MUSE_OK;
+}
+
+extern "C" int muse_b200_muse_covariance(muse_handle* h, const double* theta, const double* gs, int32_t nsims_total,
+                                         int32_t nsims_h_total, const int32_t* counts_h, double atol,
+                                         const double* prior_sigma, muse_cov_out* out) {
+    if (!h || !theta || !gs || !out || nsims_total < 2 || nsims_h_total < 1) return MUSE_EINVAL;
+    const int nt = h->cfg.ntheta;
+    const bool multi = h->comm != nullptr && h->comm_nranks > 1;
+    if (multi && !counts_h) { h->err = "counts_h (H sims per rank) required with a communicator"; return MUSE_EINVAL; }
+    // step = 0.1 ./ std(gs)                                                           src/muse.jl:411-413
+    for (int c = 0; c < nt; ++c) {
+        double m, v;
+        mean_var(gs, nsims_total, nt, c, &m, &v);
+        out->step[c] = 0.1 / std::sqrt(v);
+    }
+    // per-sim finite-difference Jacobians of this rank's H shard                      src/muse.jl:417-442
+    const int mine = multi ? counts_h[h->comm_rank] : nsims_h_total;
+    std::vector<double> local((size_t)(mine > 0 ? mine : 1) * nt * nt);
+    std::vector<int32_t> status((size_t)(mine > 0 ? mine : 1) * nt * 2, 0);
+    int rc = muse_b200_fd_jacobian(h, theta, out->step, mine, atol, local.data(), status.data());
+    if (rc != MUSE_OK) return rc;
+    for (size_t i = 0; i < (size_t)mine * nt * 2; ++i)
+        if (status[i] == MUSE_STATUS_NONFINITE) { h->err = "get_H!: MAP solution failed with a non-finite objective"; return MUSE_ESTATE; }
+    return muse_cov_finish(h, theta, gs, nsims_total, nsims_h_total, counts_h, local.data(), mine, prior_sigma, out);
 }
 
 extern "C" int muse_b200_muse_iterate(muse_handle* h, const double* theta0, int32_t nsims_total, const int32_t* counts,

@@ -9,6 +9,33 @@ using muse::Geometry;
 
 struct muse_corr_ctx;   // correlated-Gaussian family (muse_corr.cu)
 
+// One block of per-unit solver outputs (device + pinned host mirror), laid out as muse_api.cu describes.
+struct OutBlock {
+    unsigned char *d = nullptr, *hst = nullptr;
+    size_t bytes = 0;
+    int cap = 0;
+    double *g_d = nullptr, *gnorm_d = nullptr, *f_d = nullptr;
+    int *iters_d = nullptr, *fg_d = nullptr, *status_d = nullptr;
+    double *g_h = nullptr, *gnorm_h = nullptr;
+    int *iters_h = nullptr, *fg_h = nullptr, *status_h = nullptr;
+};
+
+// Device-resident outer loop (muse_outer.cu): state of the θ iteration kept on the device between passes.
+constexpr int kOuterSlots = 3;      // passes enqueued per host synchronisation (2 iterations + the convergence test is typical)
+constexpr int kOuterMaxIter = 64;   // history rows held on the device
+struct OuterState {
+    int n_iter, done, error, pad;
+    double theta[MUSE_MAX_NTHETA];                       // θ after the last update (= θ of the next pass)
+    double step[MUSE_MAX_NTHETA];                        // 0.1 ./ std(gs) of the covariance stage
+    double theta_hist[kOuterMaxIter][MUSE_MAX_NTHETA];   // θ at which iteration i evaluated
+    double g_dat[kOuterMaxIter][MUSE_MAX_NTHETA];
+    double g_like[kOuterMaxIter][MUSE_MAX_NTHETA];
+    double g_prior[kOuterMaxIter][MUSE_MAX_NTHETA];
+    double h_inv_like[kOuterMaxIter][MUSE_MAX_NTHETA];
+    double h_prior[kOuterMaxIter][MUSE_MAX_NTHETA];
+    double h_inv_post[kOuterMaxIter][MUSE_MAX_NTHETA];
+};
+
 struct muse_handle {
     muse_cfg cfg{};
     int ld = 0;
@@ -49,6 +76,14 @@ struct muse_handle {
 
     muse_corr_ctx* corr = nullptr;
 
+    // device-resident outer loop (muse_outer.cu)
+    OutBlock outer_slot[kOuterSlots];                    // per-pass outputs of the iterations of one chunk
+    double* outer_gall[kOuterSlots] = {nullptr, nullptr, nullptr};   // multi-GPU: gathered score rows per pass (device)
+    double* outer_gall_h = nullptr;                      // pinned mirror of the three gathered blocks
+    size_t outer_gall_doubles = 0;
+    OuterState *outer_st_d = nullptr, *outer_st_h = nullptr;
+    muse::DynConsts* outer_dyn = nullptr;                // [0], [1]: passes (alternating); [2]: fiducial; [3]: FD sims
+
     // exchange step (muse_comm.cu): NCCL communicator and staging buffers
     void* comm = nullptr;
     int comm_nranks = 0, comm_rank = 0, comm_cap = 0;
@@ -59,12 +94,25 @@ struct muse_handle {
 
     // profiling
     bool prof = false;
-    struct Rec { cudaEvent_t a, b; int cls; double units, bytes; int kind; };
+    struct Rec { cudaEvent_t a, b; int cls; double units, bytes; int kind; int tag; };
     std::vector<Rec> recs;
     muse_profile acc{};
     int pass_kind = MUSE_PASS_COLD;      // kind of the solver pass being enqueued (set by the entry point)
+    int rec_tag = 0;                     // device-resident loop: iteration (> 0) or covariance stage (−1) a launch belongs to,
+                                         // so that launches the device skipped can be dropped from the statistics afterwards
     muse_pass_profile acc_pass{};        // per-kind split of acc.solve_* (muse_b200_profile_passes)
 };
+
+// internal entry points of muse_api.cu used by the device-resident outer loop (muse_outer.cu)
+int  muse_outblock_ensure(muse_handle* h, OutBlock& ob, int items);
+void muse_outblock_free(OutBlock& ob);
+int  muse_pass_enqueue(muse_handle* h, const double* theta_sim, const double* theta_eval, double atol, int include_data,
+                       int warm_start, int first_sim, int count, const OutBlock* ob, const muse::DynConsts* dyn);
+extern "C" int  muse_fd_enqueue(muse_handle* h, const double* theta0, const double* th_pts, int nsims_H, double atol,
+                                const muse::DynConsts* dyn_fid, const muse::DynConsts* dyn_fd);
+extern "C" void muse_fd_combine_host(muse_handle* h, const double* step, int nsims_H, double* Hs_out, int32_t* status_out);
+void muse_outer_release(muse_handle* h);
+extern "C" int  muse_comm_allgather_dev_enqueue(muse_handle* h, const double* src_dev, int ncol, const int32_t* counts, size_t* need_out);
 
 void muse_comm_release(muse_handle* h);
 extern "C" void muse_comm_unpack(muse_handle* h, int ncol, const int32_t* counts, double* out_host);

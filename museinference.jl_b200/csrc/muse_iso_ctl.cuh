@@ -117,7 +117,7 @@ __device__ __forceinline__ void st2_hint(double* p, int i, double2 v, uint64_t p
 // slow-path vector operations (only reached when a unit needs more than one L-BFGS iteration)
 template <class G, class Iter>
 __device__ __noinline__ void sweep_misc(G& grp, const SolveLaunch& L, const Cmd& c, double (&red)[7], Iter iter) {
-    const IsoEval ev = L.ev;
+    const IsoEval ev = launch_ev(L);
     const double* x = c.xsrc;
     double* sb = c.sbuf;
     auto grad = [&](const double* z, int j) { return elem(x[j], z ? z[j] : 0.0, ev).g; };
@@ -244,7 +244,7 @@ struct Controller {
         cur.c = c;
         cur.commit = commit ? 1 : 0;
         issue(red);
-        phi = fma(0.5, red[0], L.ev.half_cst);
+        phi = fma(0.5, red[0], launch_ev(L).half_cst);
         dphi = red[1];
         if (c != last_eval_alpha) fg_evals += 1;
         last_eval_alpha = c;
@@ -474,7 +474,7 @@ struct Controller {
     }
 
     __device__ __noinline__ void solve(int item, int* zstate_row) {
-        const IsoEval ev = L.ev;
+        const IsoEval ev = launch_ev(L);
         double red[7];
         stamp(item, 0);
         com_alpha = NAN;
@@ -651,7 +651,7 @@ struct Controller {
             draw = L.master_row;
         }
         cur.item = item;
-        cur.smp = L.smp[tsel];
+        cur.smp = launch_smp(L, tsel);
         cur.start_kind = (draw < 0 && L.start_kind == kStartTruth) ? kStartZero : L.start_kind;
         cur.xi = draw >= 0 ? L.xi + (size_t)draw * ld : nullptr;
         cur.nu = draw >= 0 ? L.nu + (size_t)draw * ld : nullptr;

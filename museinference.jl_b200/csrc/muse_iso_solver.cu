@@ -44,7 +44,7 @@ namespace {
 // red: [e0, gg0, gmax0, s1, s2, e1, dphi1]
 template <class G>
 __device__ __forceinline__ void sweep_init(G& grp, const SolveLaunch& L, const Cmd& c, double (&red)[7]) {
-    const IsoEval ev = L.ev;
+    const IsoEval ev = launch_ev(L);
     const IsoSample sp = c.smp;
     const double *xi = c.xi, *nu = c.nu, *xsrc = c.xsrc, *zcur = c.zcur;
     double *xw = c.xw, *zA = c.zA;
@@ -127,7 +127,7 @@ __device__ __forceinline__ void sweep_init(G& grp, const SolveLaunch& L, const C
 // zt = zcur + c·s with s = −∇f(zcur) (lazy) or sbuf.  red: [e, dphi, gg, gmax, s1, s2, xchg]
 template <class G, bool LAZY, bool ZNULL>
 __device__ __forceinline__ void sweep_trial(G& grp, const SolveLaunch& L, const Cmd& cm, double (&red)[7]) {
-    const IsoEval ev = L.ev;
+    const IsoEval ev = launch_ev(L);
     const double c = cm.c;
     const bool commit = cm.commit != 0;
     const double *xsrc = cm.xsrc, *zcur = cm.zcur, *sb = cm.sbuf;
@@ -228,6 +228,7 @@ struct RegIssuer {
 template <int CTA_THREADS, bool WARP_GROUP, int CLUSTER>
 __global__ void __launch_bounds__(CTA_THREADS, (CTA_THREADS >= 512 ? 1 : (CTA_THREADS == 256 ? 2 : 4)))
 iso_solver_kernel(const __grid_constant__ SolveLaunch L) {
+    if (launch_skipped(L)) return;      // uniform over the grid (and over a cluster): nobody reaches a barrier
     using G = Group<CTA_THREADS, WARP_GROUP, CLUSTER>;
     __shared__ typename G::Smem smem;
     __shared__ Cmd scmd;

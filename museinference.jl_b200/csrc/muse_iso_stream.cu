@@ -259,7 +259,7 @@ struct FastResult {
 };
 
 __device__ __noinline__ bool fast_replay(const SolveLaunch& L, int start_kind, const double (&t)[kNRed], FastResult& r) {
-    const IsoEval& ev = L.ev;
+    const IsoEval ev = launch_ev(L);
     constexpr double delta = 0.1, sigma = 0.9, epsilon = 1e-6;
     const double f0 = fma(0.5, fma(ev.a, t[rS2_0], t[rR0]), ev.half_cst);
     const double gg0 = t[rGG0], gmax0 = t[rGM0];
@@ -300,7 +300,7 @@ __device__ __forceinline__ void publish_unit(const SolveLaunch& L, const ItemDes
         atomicAdd(L.redo_total, 1ULL);
         return;
     }
-    const IsoEval& ev = L.ev;
+    const IsoEval ev = launch_ev(L);
     double* g = L.g_out + (size_t)it.unit * L.ntheta;
     if (L.family == MUSE_FAMILY_FUNNEL) {
         g[0] = 0.5 * ev.a * r.s2 - 0.5 * (double)L.d;                // ∇θ logLike = ½ e^{−θ} Σz² − d/2   (src/simple.jl:66-68)
@@ -326,6 +326,7 @@ struct WarpCtx {
 
 __global__ void __launch_bounds__(kThreads, 1)
 iso_stream_kernel(const __grid_constant__ SolveLaunch L) {
+    if (launch_skipped(L)) return;      // device-resident outer loop: this pass is not needed (uniform over the grid)
     extern __shared__ __align__(128) unsigned char dyn[];
     __shared__ Shared sh;
     double* const ring = reinterpret_cast<double*>(dyn);
@@ -471,7 +472,7 @@ iso_stream_kernel(const __grid_constant__ SolveLaunch L) {
     } else {
         // ------------------------------------------------------------------ consumers
         const int ct = (int)threadIdx.x - 64, cw = warp - 2;
-        const IsoEval ev = L.ev;
+        const IsoEval ev = launch_ev(L);
         const L2Policy pol = make_policies();
         int stage = 0;
         uint32_t phase = 0;
@@ -569,9 +570,10 @@ __device__ __forceinline__ void warp_unit(const ItemDesc& it, const double* ra, 
 
 __global__ void __launch_bounds__(kWarpCta, 2)
 iso_warp_stream_kernel(const __grid_constant__ SolveLaunch L) {
+    if (launch_skipped(L)) return;
     const int lane = threadIdx.x & 31;
     const int gw = (blockIdx.x * kWarpCta + threadIdx.x) >> 5, nw = (gridDim.x * kWarpCta) >> 5;
-    const IsoEval ev = L.ev;
+    const IsoEval ev = launch_ev(L);
     const L2Policy pol = make_policies();
     WarpCtx ctx{lane};
     NoIssuer none;

@@ -1,0 +1,427 @@
+// muse_outer.cu — the outer θ loop of muse! (/root/reference/src/muse.jl:159-236) and its covariance stage (:244-247) with
+// the θ update ON THE DEVICE, so that consecutive solver passes follow each other on the stream without a host round trip.
+//
+// muse_driver.cu runs the same loop with the O(N·nθ) arithmetic on the host: every pass ends in a device→host copy, a stream
+// synchronisation and a fresh launch — ≈ 50 µs during which the GPU idles, three times per full solve.  That is 10 % of a C3
+// solve (d = 65 536) and most of a C1/C2 solve (d = 512), whose passes take 20–50 µs.  Here one single-CTA kernel per pass
+// (theta_step_kernel) does what the host did between two passes — status check, mean and variance of the scores
+// (:183, :188), prior terms (:184, :207), H⁻¹_post (:208), the Newton step (:224), the convergence test of the NEXT
+// iteration (:163-166) — and writes the θ-dependent constants of the next pass into device memory (DynConsts), which the
+// solver kernels read instead of launch parameters.  The host enqueues a chunk of kOuterSlots passes speculatively; once the
+// loop has converged the remaining passes see skip = 1 and return at once.  cov_prep_kernel then derives the finite-difference
+// step 0.1 ./ std(gs) (:411-413) and the constants of the fiducial solve and of the 2·nθ sample points θ̂ ± h·eₙ (:417-433), so
+// that get_H!'s launches ride the same stream.  One synchronisation per chunk; the typical solve (2 iterations + the
+// convergence test + covariance) needs exactly one.
+//
+// Differences from the host loop: the reductions are parallel trees (deterministic, but not the host's summation order) and
+// e^{·} comes from the device's libm, so θ agrees with muse_driver.cu to round-off (≈ 1e-16 relative), not bit for bit.
+// Every rank of a multi-GPU job runs the identical kernel on the identical gathered scores, so θ stays bit-identical ACROSS
+// ranks, as before.  history[i].t is the chunk's wall time divided by its iterations (no per-iteration host clock exists).
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "muse_handle.cuh"
+
+using namespace muse;
+
+extern "C" int muse_b200_allgather_rows(muse_handle* h, const double* local_host, int32_t ncol, const int32_t* counts, double* out_host);
+int muse_cov_finish(muse_handle* h, const double* theta, const double* gs, int nsims_total, int nsims_h_total, const int32_t* counts_h,
+                    const double* Hs_local, int mine, const double* prior_sigma, muse_cov_out* out);
+
+namespace {
+
+constexpr int kStepThreads = 256;
+constexpr int kMaxRanks = 16;
+
+struct OuterParams {
+    int nt, family, d;
+    int iter;                 // 1-based index of the pass just executed
+    int maxsteps;
+    int units_local;          // units of the pass on this rank (data + local sims)
+    int nranks, n_total;
+    int counts[kMaxRanks];    // sims per rank
+    long long need;           // doubles per rank slot of g_all
+    double alpha, theta_rtol;
+    int have_prior;
+    double prior_mean[kMaxTheta], prior_sigma[kMaxTheta];
+    const double* g_local;    // this pass: local score rows, row 0 = data
+    const int* status_local;
+    const double* g_all;      // this pass: sim scores of all ranks (rank q's rows at g_all + q·need)
+    OuterState* st;
+    DynConsts* dyn_next;      // constants of the next pass
+};
+
+struct CovParams {
+    int nt, family, d;
+    int nranks, n_total;
+    int counts[kMaxRanks];
+    long long need;
+    const double* g_all_slot[kOuterSlots];   // gathered sim scores of iteration i live in slot (i − 1) % kOuterSlots
+    OuterState* st;
+    DynConsts* dyn_fid;
+    DynConsts* dyn_fd;
+};
+
+// θ → constants, as theta_consts() of muse_api.cu (device libm)
+__device__ void consts_of(int family, int d, const double* th_sim, const double* th_eval, IsoSample* smp, IsoEval* ev) {
+    const double dd = (double)d;
+    if (family == MUSE_FAMILY_FUNNEL) {
+        if (smp) { smp->sig = exp(0.5 * th_sim[0]); smp->mu = 0.0; }
+        if (ev) { ev->a = exp(-th_eval[0]); ev->mu = 0.0; ev->half_cst = 0.5 * dd * th_eval[0]; ev->cspec = 1.0 / (1.0 + ev->a); }
+    } else {
+        if (smp) { smp->sig = exp(th_sim[1]); smp->mu = th_sim[0]; }
+        if (ev) { ev->a = exp(-2.0 * th_eval[1]); ev->mu = th_eval[0]; ev->half_cst = dd * th_eval[1]; ev->cspec = 1.0 / (1.0 + ev->a); }
+    }
+}
+
+// Σ_k f(k) over the sims of all ranks in a fixed order: thread t takes sims t, t + 256, … of every rank slot in turn, then a
+// shared-memory tree.  Deterministic for a given (nranks, counts).
+template <class F>
+__device__ double block_sum(const int* counts, int nranks, long long need, int nt, F&& f, double* sh) {
+    double acc = 0.0;
+    for (int q = 0; q < nranks; ++q)
+        for (int r = threadIdx.x; r < counts[q]; r += kStepThreads) acc += f((size_t)q * need + (size_t)r * nt);
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = kStepThreads / 2; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+        __syncthreads();
+    }
+    const double r = sh[0];
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(kStepThreads) theta_step_kernel(const OuterParams P) {
+    __shared__ double sh[kStepThreads];
+    __shared__ int bad;
+    OuterState* st = P.st;
+    if (st->done) {                                            // the pass before this step was skipped: keep skipping
+        if (threadIdx.x == 0 && P.dyn_next) P.dyn_next->skip = 1;
+        return;
+    }
+    if (threadIdx.x == 0) bad = 0;
+    __syncthreads();
+    for (int u = threadIdx.x; u < P.units_local; u += kStepThreads)
+        if (P.status_local[u] == MUSE_STATUS_NONFINITE) bad = 1;   // src/interface.jl:170
+    __syncthreads();
+    if (bad) {
+        if (threadIdx.x == 0) { st->error = 1; st->done = 1; if (P.dyn_next) P.dyn_next->skip = 1; }
+        return;
+    }
+    const int row = P.iter - 1;
+    double mean[kMaxTheta], var[kMaxTheta];
+    for (int c = 0; c < P.nt; ++c) {
+        const double* g = P.g_all + c;
+        const double m = block_sum(P.counts, P.nranks, P.need, P.nt, [&](size_t o) { return g[o]; }, sh) / P.n_total;
+        const double q = block_sum(P.counts, P.nranks, P.need, P.nt, [&](size_t o) { const double dlt = g[o] - m; return dlt * dlt; }, sh);
+        mean[c] = m;
+        var[c] = q / (P.n_total - 1);
+    }
+    if (threadIdx.x != 0) return;
+    double th_new[kMaxTheta];
+    for (int c = 0; c < P.nt; ++c) {
+        const double th = st->theta[c];
+        const double g_dat = P.g_local[c];
+        const double g_like = g_dat - mean[c];                                                     // :183
+        const double g_prior = P.have_prior ? -(th - P.prior_mean[c]) / (P.prior_sigma[c] * P.prior_sigma[c]) : 0.0;   // :184
+        const double g_post = g_like + g_prior;                                                    // :185
+        const double h_inv_like = -1.0 / var[c];                                                   // :188
+        const double h_prior = P.have_prior ? -1.0 / (P.prior_sigma[c] * P.prior_sigma[c]) : 0.0;  // :207
+        const double h_inv_post = 1.0 / (1.0 / h_inv_like + h_prior);                              // :208 (diagonal)
+        if (row < kOuterMaxIter) {
+            st->theta_hist[row][c] = th;
+            st->g_dat[row][c] = g_dat;
+            st->g_like[row][c] = g_like;
+            st->g_prior[row][c] = g_prior;
+            st->h_inv_like[row][c] = h_inv_like;
+            st->h_prior[row][c] = h_prior;
+            st->h_inv_post[row][c] = h_inv_post;
+        }
+        th_new[c] = th - P.alpha * (h_inv_post * g_post);                                          // :224
+    }
+    for (int c = 0; c < P.nt; ++c) st->theta[c] = th_new[c];                                       // :230
+    st->n_iter = P.iter;
+    int done = 0;
+    if (P.iter >= 2) {                                   // the test at the top of iteration iter + 1 > 2   (:163-166)
+        double q = 0.0;
+        for (int c = 0; c < P.nt; ++c) {
+            const double dlt = st->theta_hist[row][c] - st->theta_hist[row - 1][c];
+            q += dlt * st->h_inv_post[row][c] * dlt;
+        }
+        q = -q;
+        if (q < 0.0) { st->error = 2; done = 1; }        // DomainError of sqrt in the reference
+        else if (sqrt(q) < P.theta_rtol) done = 1;
+    }
+    if (P.iter >= P.maxsteps) done = 1;
+    st->done = done;
+    if (P.dyn_next) {
+        consts_of(P.family, P.d, th_new, th_new, &P.dyn_next->smp[0], &P.dyn_next->ev);
+        P.dyn_next->skip = done;
+    }
+}
+
+// after the last θ-step of a chunk: if the loop has ended, the constants of get_H!'s launches; otherwise they are skipped
+__global__ void __launch_bounds__(kStepThreads) cov_prep_kernel(const CovParams P) {
+    __shared__ double sh[kStepThreads];
+    OuterState* st = P.st;
+    if (!st->done || st->error || st->n_iter < 1) {
+        if (threadIdx.x == 0) { P.dyn_fid->skip = 1; P.dyn_fd->skip = 1; }
+        return;
+    }
+    const double* gall = P.g_all_slot[(st->n_iter - 1) % kOuterSlots];
+    double step[kMaxTheta];
+    for (int c = 0; c < P.nt; ++c) {                     // step = 0.1 ./ std(gs)   (:411-413), gs = the last scores (:231)
+        const double* g = gall + c;
+        const double m = block_sum(P.counts, P.nranks, P.need, P.nt, [&](size_t o) { return g[o]; }, sh) / P.n_total;
+        const double q = block_sum(P.counts, P.nranks, P.need, P.nt, [&](size_t o) { const double dlt = g[o] - m; return dlt * dlt; }, sh);
+        step[c] = 0.1 / sqrt(q / (P.n_total - 1));
+    }
+    if (threadIdx.x != 0) return;
+    double th0[kMaxTheta];
+    for (int c = 0; c < P.nt; ++c) { th0[c] = st->theta[c]; st->step[c] = step[c]; }
+    consts_of(P.family, P.d, th0, th0, &P.dyn_fid->smp[0], &P.dyn_fid->ev);
+    P.dyn_fid->skip = 0;
+    consts_of(P.family, P.d, th0, th0, nullptr, &P.dyn_fd->ev);
+    for (int n = 0; n < P.nt; ++n)
+        for (int s = 0; s < 2; ++s) {
+            double th[kMaxTheta];
+            for (int c = 0; c < P.nt; ++c) th[c] = th0[c];
+            const double eps = 0.0 + step[n] * (s ? 1.0 : -1.0);     // x .+ step .* grid   (src/util.jl:15)
+            th[n] = th0[n] + eps;
+            consts_of(P.family, P.d, th, th0, &P.dyn_fd->smp[2 * n + s], nullptr);
+        }
+    P.dyn_fd->skip = 0;
+}
+
+#define OUTER_TRY(h, expr)                                                                    \
+    do {                                                                                      \
+        cudaError_t e__ = (expr);                                                             \
+        if (e__ != cudaSuccess) {                                                             \
+            (h)->err = std::string(#expr) + ": " + cudaGetErrorString(e__);                   \
+            return e__ == cudaErrorMemoryAllocation ? MUSE_ENOMEM : MUSE_ECUDA;               \
+        }                                                                                     \
+    } while (0)
+
+int outer_ensure(muse_handle* h, int units, size_t gall_doubles) {
+    for (int s = 0; s < kOuterSlots; ++s) {
+        const int rc = muse_outblock_ensure(h, h->outer_slot[s], units);
+        if (rc != 0) return rc;
+    }
+    if (!h->outer_st_d) {
+        OUTER_TRY(h, cudaMalloc(&h->outer_st_d, sizeof(OuterState)));
+        OUTER_TRY(h, cudaMallocHost(&h->outer_st_h, sizeof(OuterState)));
+        OUTER_TRY(h, cudaMalloc(&h->outer_dyn, 4 * sizeof(DynConsts)));
+    }
+    if (gall_doubles > h->outer_gall_doubles) {
+        for (int s = 0; s < kOuterSlots; ++s) { cudaFree(h->outer_gall[s]); h->outer_gall[s] = nullptr; }
+        cudaFreeHost(h->outer_gall_h);
+        h->outer_gall_h = nullptr;
+        h->outer_gall_doubles = 0;
+        for (int s = 0; s < kOuterSlots; ++s) OUTER_TRY(h, cudaMalloc(&h->outer_gall[s], gall_doubles * sizeof(double)));
+        OUTER_TRY(h, cudaMallocHost(&h->outer_gall_h, kOuterSlots * gall_doubles * sizeof(double)));
+        h->outer_gall_doubles = gall_doubles;
+    }
+    return MUSE_OK;
+}
+
+}  // namespace
+
+void muse_outer_release(muse_handle* h) {
+    for (int s = 0; s < kOuterSlots; ++s) { muse_outblock_free(h->outer_slot[s]); cudaFree(h->outer_gall[s]); h->outer_gall[s] = nullptr; }
+    cudaFreeHost(h->outer_gall_h);
+    cudaFree(h->outer_st_d);
+    cudaFreeHost(h->outer_st_h);
+    cudaFree(h->outer_dyn);
+    h->outer_gall_h = nullptr; h->outer_st_d = h->outer_st_h = nullptr; h->outer_dyn = nullptr; h->outer_gall_doubles = 0;
+}
+
+extern "C" int muse_b200_muse_solve(muse_handle* h, const double* theta0, int32_t nsims_total, const int32_t* counts,
+                                    int32_t maxsteps, double theta_rtol, double atol, double alpha, int32_t first_start,
+                                    const double* prior_mean, const double* prior_sigma, int32_t get_covariance,
+                                    int32_t nsims_h_total, const int32_t* counts_h, muse_iterate_out* out, muse_cov_out* cov) {
+    if (!h || !theta0 || !out || maxsteps < 1 || nsims_total < 2) return MUSE_EINVAL;
+    if (h->corr) { h->err = "muse_solve: the device-resident loop serves the isotropic families; corrgauss uses muse_iterate"; return MUSE_EUNSUPPORTED; }
+    if (maxsteps > kOuterMaxIter) { h->err = "muse_solve: maxsteps exceeds the device history (64 rows); use muse_iterate"; return MUSE_EUNSUPPORTED; }
+    if (first_start != MUSE_START_ZEROS && first_start != MUSE_START_USER) { h->err = "first_start must be ZEROS or USER"; return MUSE_EINVAL; }
+    if ((prior_mean == nullptr) != (prior_sigma == nullptr)) return MUSE_EINVAL;
+    if (get_covariance && (!cov || nsims_h_total < 1)) return MUSE_EINVAL;
+    const int nt = h->cfg.ntheta, nloc = h->cfg.nsims, units = nloc + 1;
+    const bool multi = h->comm != nullptr && h->comm_nranks > 1;
+    if (multi && (!counts || (get_covariance && !counts_h))) { h->err = "counts (and counts_h) required with a communicator"; return MUSE_EINVAL; }
+    if (multi && h->comm_nranks > kMaxRanks) { h->err = "muse_solve: more ranks than the θ-step kernel's table"; return MUSE_EUNSUPPORTED; }
+    if (!multi && nsims_total != nloc) { h->err = "nsims_total must equal the handle's nsims without a communicator"; return MUSE_EINVAL; }
+    if (!h->have_data) { h->err = "observed data not set (muse_b200_set_data)"; return MUSE_ESTATE; }
+    if (!h->have_draws) { h->err = "no draws installed (set_draws / seed_draws)"; return MUSE_ESTATE; }
+    if (first_start == MUSE_START_USER && !h->have_z0) { h->err = "user z0 not set (muse_b200_set_z0)"; return MUSE_ESTATE; }
+    OUTER_TRY(h, cudaSetDevice(h->cfg.device));
+
+    // layout of the gathered scores the θ-step reads
+    OuterParams P{};
+    P.nt = nt; P.family = h->cfg.family; P.d = h->cfg.d;
+    P.maxsteps = maxsteps; P.units_local = units; P.n_total = nsims_total;
+    P.alpha = alpha; P.theta_rtol = theta_rtol;
+    P.have_prior = prior_sigma ? 1 : 0;
+    for (int c = 0; c < nt; ++c) { P.prior_mean[c] = prior_mean ? prior_mean[c] : 0.0; P.prior_sigma[c] = prior_sigma ? prior_sigma[c] : 1.0; }
+    int maxc = 1;
+    if (multi) {
+        P.nranks = h->comm_nranks;
+        for (int q = 0; q < P.nranks; ++q) { P.counts[q] = counts[q]; maxc = counts[q] > maxc ? counts[q] : maxc; }
+        P.need = (long long)maxc * nt;
+    } else {
+        P.nranks = 1; P.counts[0] = nloc; P.need = (long long)nloc * nt;
+    }
+    const size_t gall_doubles = multi ? (size_t)P.need * P.nranks : 0;
+    int rc = outer_ensure(h, units, gall_doubles);
+    if (rc != MUSE_OK) return rc;
+    const int nh_mine = get_covariance ? (multi ? counts_h[h->comm_rank] : nsims_h_total) : 0;
+    if (get_covariance) {
+        const bool hshard = h->cfg.nsims_h > 0;
+        if (nh_mine < 0 || nh_mine > (hshard ? h->cfg.nsims_h : h->cfg.nsims)) { h->err = "nsims_H outside the handle's H shard"; return MUSE_EINVAL; }
+        if (hshard && !h->have_draws_h) { h->err = "no H-shard draws installed (set_draws_h / seed_draws)"; return MUSE_ESTATE; }
+    }
+
+    OuterState* sd = h->outer_st_d;
+    OuterState* sh_ = h->outer_st_h;
+    std::memset(sh_, 0, sizeof(OuterState));
+    for (int c = 0; c < nt; ++c) sh_->theta[c] = theta0[c];
+    OUTER_TRY(h, cudaMemcpyAsync(sd, sh_, sizeof(OuterState), cudaMemcpyHostToDevice, h->stream));
+    P.st = sd;
+    DynConsts* dyn = h->outer_dyn;
+
+    out->n_iter = 0;
+    int it_done = 0;                        // iterations whose history has been copied out
+    bool finished = false;
+    while (!finished) {
+        const auto t0 = std::chrono::steady_clock::now();
+        const int first = it_done + 1;
+        const int last = std::min(maxsteps, it_done + kOuterSlots);
+        for (int i = first; i <= last; ++i) {
+            const int slot = (i - 1) % kOuterSlots;
+            const OutBlock& ob = h->outer_slot[slot];
+            // pass i: data + local sims, start zeros / user z₀ on the first, previous ẑ afterwards (:169-176)
+            h->rec_tag = i;
+            rc = muse_pass_enqueue(h, theta0, theta0, atol, 1, i == 1 ? first_start : MUSE_START_PREV, 0, nloc, &ob,
+                                   i == 1 ? nullptr : &dyn[i & 1]);
+            h->rec_tag = 0;
+            if (rc != MUSE_OK) return rc;
+            P.iter = i;
+            P.g_local = ob.g_d;
+            P.status_local = ob.status_d;
+            if (multi) {                    // the one exchange step, on the stream
+                size_t need = 0;
+                rc = muse_comm_allgather_dev_enqueue(h, ob.g_d + nt, nt, counts, &need);
+                if (rc != MUSE_OK) return rc;
+                OUTER_TRY(h, cudaMemcpyAsync(h->outer_gall[slot], h->comm_recv, gall_doubles * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+                P.g_all = h->outer_gall[slot];
+            } else {
+                P.g_all = ob.g_d + nt;
+            }
+            P.dyn_next = &dyn[(i + 1) & 1];
+            theta_step_kernel<<<1, kStepThreads, 0, h->stream>>>(P);
+            OUTER_TRY(h, cudaGetLastError());
+            h->acc.launches += 1;
+        }
+        if (get_covariance) {
+            CovParams C{};
+            C.nt = nt; C.family = P.family; C.d = P.d; C.nranks = P.nranks; C.n_total = nsims_total; C.need = P.need;
+            for (int q = 0; q < P.nranks; ++q) C.counts[q] = P.counts[q];
+            for (int s = 0; s < kOuterSlots; ++s) C.g_all_slot[s] = multi ? h->outer_gall[s] : h->outer_slot[s].g_d + nt;
+            C.st = sd; C.dyn_fid = &dyn[2]; C.dyn_fd = &dyn[3];
+            cov_prep_kernel<<<1, kStepThreads, 0, h->stream>>>(C);
+            OUTER_TRY(h, cudaGetLastError());
+            h->acc.launches += 1;
+            if (nh_mine > 0) {
+                h->rec_tag = -1;
+                rc = muse_fd_enqueue(h, nullptr, nullptr, nh_mine, atol, &dyn[2], &dyn[3]);
+                h->rec_tag = 0;
+                if (rc != MUSE_OK) return rc;
+            }
+        }
+        // results of the chunk: state, per-pass outputs, gathered scores, FD outputs — then the one synchronisation
+        OUTER_TRY(h, cudaMemcpyAsync(sh_, sd, sizeof(OuterState), cudaMemcpyDeviceToHost, h->stream));
+        for (int i = first; i <= last; ++i) {
+            const OutBlock& ob = h->outer_slot[(i - 1) % kOuterSlots];
+            OUTER_TRY(h, cudaMemcpyAsync(ob.hst, ob.d, ob.bytes, cudaMemcpyDeviceToHost, h->stream));
+            if (multi)
+                OUTER_TRY(h, cudaMemcpyAsync(h->outer_gall_h + (size_t)((i - 1) % kOuterSlots) * gall_doubles, h->outer_gall[(i - 1) % kOuterSlots],
+                                             gall_doubles * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        }
+        if (get_covariance && nh_mine > 0) OUTER_TRY(h, cudaMemcpyAsync(h->out_h, h->out_d, h->out_bytes, cudaMemcpyDeviceToHost, h->stream));
+        OUTER_TRY(h, cudaStreamSynchronize(h->stream));
+        const double chunk_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+
+        if (sh_->error == 1) { h->err = "muse!: MAP solution failed with a non-finite objective"; return MUSE_ESTATE; }
+        const int n_now = sh_->n_iter;
+        {   // statistics: passes the device skipped (speculative launches after the loop ended, a covariance stage that was
+            // not due yet) returned at once — they are neither solver passes nor algorithmic bytes
+            const bool cov_ran = sh_->done != 0 && sh_->error == 0;
+            int skipped = std::max(0, last - std::max(n_now, first - 1));
+            if (get_covariance && nh_mine > 0 && !cov_ran) skipped += 2;
+            h->acc.solve_launches -= skipped;
+            for (size_t k = 0; k < h->recs.size();) {
+                const muse_handle::Rec& r = h->recs[k];
+                if (r.tag > n_now || (r.tag == -1 && !cov_ran)) {
+                    cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+                    h->recs.erase(h->recs.begin() + k);
+                } else {
+                    if (h->recs[k].tag != 0) h->recs[k].tag = 0;      // settled
+                    ++k;
+                }
+            }
+        }
+        for (int i = first; i <= n_now && i <= last; ++i) {
+            const int row = i - 1, slot = row % kOuterSlots;
+            const OutBlock& ob = h->outer_slot[slot];
+            for (int c = 0; c < nt; ++c) {
+                out->theta_hist[(size_t)row * nt + c] = sh_->theta_hist[row][c];
+                out->g_dat_hist[(size_t)row * nt + c] = sh_->g_dat[row][c];
+                out->g_like_hist[(size_t)row * nt + c] = sh_->g_like[row][c];
+                out->g_prior_hist[(size_t)row * nt + c] = sh_->g_prior[row][c];
+                out->h_inv_like_hist[(size_t)row * nt + c] = sh_->h_inv_like[row][c];
+                out->h_prior_hist[(size_t)row * nt + c] = sh_->h_prior[row][c];
+                out->h_inv_post_hist[(size_t)row * nt + c] = sh_->h_inv_post[row][c];
+            }
+            double* gs = out->g_sims_hist + (size_t)row * nsims_total * nt;
+            if (multi) {
+                const double* src = h->outer_gall_h + (size_t)slot * gall_doubles;
+                size_t off = 0;
+                for (int q = 0; q < P.nranks; ++q) {
+                    std::memcpy(gs + off, src + (size_t)q * P.need, (size_t)counts[q] * nt * sizeof(double));
+                    off += (size_t)counts[q] * nt;
+                }
+            } else {
+                std::memcpy(gs, ob.g_h + nt, (size_t)nloc * nt * sizeof(double));
+            }
+            std::memcpy(out->iters_hist + (size_t)row * units, ob.iters_h, (size_t)units * sizeof(int));
+            std::memcpy(out->fg_hist + (size_t)row * units, ob.fg_h, (size_t)units * sizeof(int));
+            std::memcpy(out->gnorm_hist + (size_t)row * units, ob.gnorm_h, (size_t)units * sizeof(double));
+            std::memcpy(out->status_hist + (size_t)row * units, ob.status_h, (size_t)units * sizeof(int));
+            out->seconds_hist[row] = chunk_s / std::max(1, n_now - first + 1);
+        }
+        out->n_iter = n_now;
+        for (int c = 0; c < nt; ++c) out->theta_final[c] = sh_->theta[c];
+        if (sh_->error == 2) { h->err = "DomainError: sqrt of a negative number in the θ convergence test (src/muse.jl:165)"; return MUSE_ESTATE; }
+        it_done = n_now;
+        finished = sh_->done != 0 || it_done >= maxsteps;
+        if (!finished && n_now < last) { h->err = "muse_solve: internal error (loop stalled)"; return MUSE_ESTATE; }
+    }
+
+    if (get_covariance) {
+        // the FD scores of this rank's H shard are in the main output block; combine with the device's step (:411-413)
+        std::vector<double> Hs_local((size_t)std::max(1, nh_mine) * nt * nt);
+        std::vector<int32_t> status((size_t)std::max(1, nh_mine) * nt * 2, 0);
+        for (int c = 0; c < nt; ++c) cov->step[c] = sh_->step[c];
+        if (nh_mine > 0) {
+            muse_fd_combine_host(h, sh_->step, nh_mine, Hs_local.data(), status.data());
+            for (size_t i = 0; i < (size_t)nh_mine * nt * 2; ++i)
+                if (status[i] == MUSE_STATUS_NONFINITE) { h->err = "get_H!: MAP solution failed with a non-finite objective"; return MUSE_ESTATE; }
+        }
+        const double* gs_last = out->g_sims_hist + (size_t)(out->n_iter - 1) * nsims_total * nt;
+        return muse_cov_finish(h, out->theta_final, gs_last, nsims_total, nsims_h_total, counts_h, Hs_local.data(), nh_mine, prior_sigma, cov);
+    }
+    return MUSE_OK;
+}

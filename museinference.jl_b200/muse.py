@@ -14,6 +14,7 @@ Keyword names: ASCII spellings are canonical, the reference's Unicode spellings 
 from __future__ import annotations
 
 import math
+import os
 import pickle
 import time
 from dataclasses import dataclass, field
@@ -25,6 +26,11 @@ from . import _capi
 from .parallel import LocalPool, block_partition
 from .problem import AbstractMuseProblem, BaseDraws, FlatPrior, NormalPrior, SimpleMuseProblem
 from ._capi import MuseBackendError
+
+# Which in-library outer loop the common configuration takes when the caller does not say (fused_driver=True):
+# "device" — θ update on the device, one host synchronisation per solve (csrc/muse_outer.cu; isotropic families);
+# "host"   — host arithmetic between two passes (csrc/muse_driver.cu).  fused_driver=False: the line-by-line loop below.
+DEFAULT_FUSED_DRIVER = os.environ.get("MUSE_FUSED_DRIVER", "host")
 
 _KW_ALIASES = {
     "θ_rtol": "theta_rtol", "∇z_logLike_atol": "gradz_logLike_atol", "α": "alpha", "z₀": "z0",
@@ -151,9 +157,21 @@ def muse_(result: MuseResult, prob: AbstractMuseProblem, theta0=None, **kwargs):
         if pool.world > 1:
             pool.bind(be)
             counts = block_partition(nsims, pool.world)[1]
-        r = be.muse_iterate(theta, nsims, counts, maxsteps, theta_rtol, atol, alpha,
-                            _capi.START_USER if z0 is not None else _capi.START_ZEROS,
-                            *(prior_ms if prior_ms else (None, None)))
+        mode = DEFAULT_FUSED_DRIVER if fused_driver is True else fused_driver
+        device_loop = (mode == "device" and hasattr(be, "muse_solve") and prob.family != "corrgauss" and maxsteps <= 64)
+        cdev = None
+        if device_loop:
+            counts_h = block_partition(nh_total, pool.world)[1] if (pool.world > 1 and get_covariance) else None
+            tc0 = time.perf_counter()
+            r, cdev = be.muse_solve(theta, nsims, counts, maxsteps, theta_rtol, atol, alpha,
+                                    _capi.START_USER if z0 is not None else _capi.START_ZEROS,
+                                    *(prior_ms if prior_ms else (None, None)), get_covariance=bool(get_covariance),
+                                    nsims_h_total=nh_total, counts_h=counts_h)
+            t_solve = time.perf_counter() - tc0
+        else:
+            r = be.muse_iterate(theta, nsims, counts, maxsteps, theta_rtol, atol, alpha,
+                                _capi.START_USER if z0 is not None else _capi.START_ZEROS,
+                                *(prior_ms if prior_ms else (None, None)))
         th_unreg_prev = theta.copy()
         for k in range(r["n_iter"]):
             hl, hp, hq = r["h_inv_like_hist"][k], r["h_prior_hist"][k], r["h_inv_post_hist"][k]
@@ -174,6 +192,13 @@ def muse_(result: MuseResult, prob: AbstractMuseProblem, theta0=None, **kwargs):
             result.theta = r["theta_final"].copy()                                 # :230
             result.gs = r["g_sims_hist"][r["n_iter"] - 1].copy()                   # :231
         maxsteps = 0                                                               # the loop below has nothing left to do
+        if cdev is not None and r["n_iter"]:                                       # :244-247, already done on the stream
+            result.J, result.H, result.Hs = cdev["J"], cdev["H"], cdev["Hs"]
+            result.Sigma_inv, result.Sigma = cdev["Sigma_inv"], cdev["Sigma"]
+            result.dist = (result.theta.copy(), result.Sigma.copy())               # :542-546
+            result.metadata["fd_step"] = cdev["step"]
+            result.time = t_solve
+            return result
         if get_covariance and r["n_iter"]:                                         # :244-247, same stage in the library
             tc = time.perf_counter()
             counts_h = block_partition(nh_total, pool.world)[1] if pool.world > 1 else None

@@ -684,3 +684,90 @@ def test_profile_splits_solver_time_by_pass_kind():
     assert all(v["ms"] > 0 for v in p.values())
     be.profile_reset(False)
     be.close()
+
+
+# ----------------------------------------------------------------------------- device-resident outer loop (csrc/muse_outer.cu)
+def _solve_modes(m, xd, name, pr, rng, nsims, modes, **kw):
+    res = {}
+    for mode in modes:
+        prob = m.SimpleMuseProblem(xd, name, pr())
+        res[mode] = m.muse(prob, theta_start(name), rng=rng, nsims=nsims, fused_driver=mode, **kw)
+        prob.close()
+    return res
+
+
+def _assert_same_solve(a, b, cov=True):
+    assert len(a.history) == len(b.history)
+    np.testing.assert_allclose(a.theta, b.theta, rtol=1e-11)
+    np.testing.assert_allclose(np.array(a.gs), np.array(b.gs), rtol=1e-9, atol=1e-9)
+    if cov:
+        np.testing.assert_allclose(a.J, b.J, rtol=1e-10)
+        np.testing.assert_allclose(a.H, b.H, rtol=1e-8, atol=1e-9 * np.abs(b.H).max())
+        np.testing.assert_allclose(a.Sigma, b.Sigma, rtol=1e-7)
+        np.testing.assert_allclose(np.array(a.Hs), np.array(b.Hs), rtol=1e-7, atol=1e-8 * np.abs(np.array(b.Hs)).max())
+        np.testing.assert_allclose(a.metadata["fd_step"], b.metadata["fd_step"], rtol=1e-12)
+    for ha, hb in zip(a.history, b.history):
+        for key in ("theta", "theta_unreg", "g_like_sims", "g_like_dat", "g_like", "g_prior", "g_post", "H_inv_post",
+                    "H_prior", "H_inv_like"):
+            np.testing.assert_allclose(ha[key], hb[key], rtol=1e-9, atol=1e-9, err_msg=key)
+        assert {k: v for k, v in ha["z_history_dat"].items() if k != "gnorm"} == {k: v for k, v in hb["z_history_dat"].items() if k != "gnorm"}
+        np.testing.assert_array_equal(ha["z_history_sims"]["fg_evals"], hb["z_history_sims"]["fg_evals"])
+        np.testing.assert_array_equal(ha["z_history_sims"]["status"], hb["z_history_sims"]["status"])
+
+
+@pytest.mark.parametrize("name,d,nsims,prior,kw", [
+    ("funnel", 512, 100, True, {}),                                     # the reference's example: 2 iterations + convergence test
+    ("hiergauss", 5000, 50, False, dict(theta_rtol=1e-3, maxsteps=6)),   # several chunks of three passes
+    ("hiergauss", 300, 30, True, dict(theta_rtol=0.0, maxsteps=7)),      # runs into maxsteps: 3 + 3 + 1 passes
+    ("funnel", 6000, 40, True, dict(maxsteps=1)),                        # one pass, then the covariance stage
+    ("funnel", 70000, 24, True, dict(theta_rtol=1e-2, maxsteps=3)),      # loop ends exactly at the end of a chunk
+])
+def test_device_resident_outer_loop_matches_host_loop(name, d, nsims, prior, kw):
+    """muse_b200_muse_solve (θ update on the device, one synchronisation per chunk of passes) against muse_b200_muse_iterate +
+    muse_b200_muse_covariance (host arithmetic between passes): same iteration count, histories, θ̂, J, H, Σ to round-off."""
+    import museinference_jl_b200 as m
+    oprob, fam, draws, xd = oracle_problem(name, d, nsims)
+    rng = m.BaseDraws(draws.xi, draws.nu, draws.xi_master, draws.nu_master)
+    pr = (lambda: m.NormalPrior([0.0, 0.1][:fam.ntheta], [3.0, 2.0][:fam.ntheta])) if prior else (lambda: None)
+    res = _solve_modes(m, xd, name, pr, rng, nsims, ("device", "host"), get_covariance=True, **kw)
+    _assert_same_solve(res["device"], res["host"])
+    res = _solve_modes(m, xd, name, pr, rng, nsims, ("device", "host"), get_covariance=False, **kw)
+    _assert_same_solve(res["device"], res["host"], cov=False)
+    assert res["device"].J is None
+
+
+def test_device_resident_outer_loop_against_oracle_and_errors():
+    import museinference_jl_b200 as m
+    name, d, nsims = "hiergauss", 2048, 60
+    oprob, fam, draws, xd = oracle_problem(name, d, nsims)
+    ref = O.muse(oprob, theta_start(name), nsims=nsims, get_covariance=True)
+    prob = m.SimpleMuseProblem(xd, name)
+    rng = m.BaseDraws(draws.xi, draws.nu, draws.xi_master, draws.nu_master)
+    res = m.muse(prob, theta_start(name), rng=rng, nsims=nsims, get_covariance=True, fused_driver="device")
+    assert len(res.history) == len(ref.history)
+    np.testing.assert_allclose(res.theta, ref.theta, rtol=RTOL_EST)
+    np.testing.assert_allclose(res.J, ref.J, rtol=RTOL_EST)
+    np.testing.assert_allclose(res.H, ref.H, rtol=RTOL_EST, atol=RTOL_EST * np.abs(ref.H).max())
+    np.testing.assert_allclose(res.Sigma, ref.Sigma, rtol=10 * RTOL_EST, atol=RTOL_EST * np.abs(ref.Sigma).max())
+    np.testing.assert_allclose(np.array(res.gs), np.array(ref.gs), rtol=RTOL_SIM)
+    # a second solve on the same handle (state is re-initialised), seeded draws this time
+    a = m.muse(prob, theta_start(name), rng=5, nsims=nsims, get_covariance=True, fused_driver="device")
+    b = m.muse(prob, theta_start(name), rng=5, nsims=nsims, get_covariance=True, fused_driver="host")
+    _assert_same_solve(a, b)
+    prob.close()
+    # a NaN in the data: the θ-step kernel sees the NONFINITE status and the call fails loudly (src/interface.jl:170)
+    xbad = xd.copy()
+    xbad[7] = np.nan
+    prob = m.SimpleMuseProblem(xbad, name)
+    with pytest.raises(m.MuseBackendError):
+        m.muse(prob, theta_start(name), rng=rng, nsims=nsims, get_covariance=True, fused_driver="device")
+    prob.close()
+    # corrgauss keeps the host loop even when asked for the device one
+    from helpers import make_family
+    famc = make_family("corrgauss", 128)
+    oprobc, _, drawsc, xdc = oracle_problem("corrgauss", 128, 20, prior=O.NormalPrior(0, 3))
+    probc = m.SimpleMuseProblem(xdc, "corrgauss", m.NormalPrior(0, 3), P=famc.P, L=famc.L)
+    rc = m.muse(probc, [1.0], rng=m.BaseDraws(drawsc.xi, drawsc.nu, drawsc.xi_master, drawsc.nu_master), nsims=20,
+                get_covariance=True, fused_driver="device")
+    assert rc.Sigma is not None
+    probc.close()
