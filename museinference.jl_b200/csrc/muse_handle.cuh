@@ -23,17 +23,16 @@ struct OutBlock {
 // Device-resident outer loop (muse_outer.cu): state of the θ iteration kept on the device between passes.
 constexpr int kOuterSlots = 3;      // passes enqueued per host synchronisation (2 iterations + the convergence test is typical)
 constexpr int kOuterMaxIter = 64;   // history rows held on the device
+struct OuterRow {                                        // history row of one iteration (what muse_iterate_out holds per row)
+    double theta[MUSE_MAX_NTHETA];                       // θ at which the iteration evaluated
+    double g_dat[MUSE_MAX_NTHETA], g_like[MUSE_MAX_NTHETA], g_prior[MUSE_MAX_NTHETA];
+    double h_inv_like[MUSE_MAX_NTHETA], h_prior[MUSE_MAX_NTHETA], h_inv_post[MUSE_MAX_NTHETA];
+};
 struct OuterState {
     int n_iter, done, error, pad;
     double theta[MUSE_MAX_NTHETA];                       // θ after the last update (= θ of the next pass)
     double step[MUSE_MAX_NTHETA];                        // 0.1 ./ std(gs) of the covariance stage
-    double theta_hist[kOuterMaxIter][MUSE_MAX_NTHETA];   // θ at which iteration i evaluated
-    double g_dat[kOuterMaxIter][MUSE_MAX_NTHETA];
-    double g_like[kOuterMaxIter][MUSE_MAX_NTHETA];
-    double g_prior[kOuterMaxIter][MUSE_MAX_NTHETA];
-    double h_inv_like[kOuterMaxIter][MUSE_MAX_NTHETA];
-    double h_prior[kOuterMaxIter][MUSE_MAX_NTHETA];
-    double h_inv_post[kOuterMaxIter][MUSE_MAX_NTHETA];
+    OuterRow row[kOuterMaxIter];
 };
 
 struct muse_handle {

@@ -7,8 +7,9 @@
 // (theta_step_kernel) does what the host did between two passes — status check, mean and variance of the scores
 // (:183, :188), prior terms (:184, :207), H⁻¹_post (:208), the Newton step (:224), the convergence test of the NEXT
 // iteration (:163-166) — and writes the θ-dependent constants of the next pass into device memory (DynConsts), which the
-// solver kernels read instead of launch parameters.  The host enqueues a chunk of kOuterSlots passes speculatively; once the
-// loop has converged the remaining passes see skip = 1 and return at once.  cov_prep_kernel then derives the finite-difference
+// solver kernels read instead of launch parameters.  The host enqueues a chunk of passes (two first — the fewest the
+// convergence test needs — then three at a time) speculatively; once the loop has ended the remaining passes see skip = 1
+// and return at once.  cov_prep_kernel then derives the finite-difference
 // step 0.1 ./ std(gs) (:411-413) and the constants of the fiducial solve and of the 2·nθ sample points θ̂ ± h·eₙ (:417-433), so
 // that get_H!'s launches ride the same stream.  One synchronisation per chunk; the typical solve (2 iterations + the
 // convergence test + covariance) needs exactly one.
@@ -20,6 +21,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstddef>
 #include <cstring>
 #include <vector>
 
@@ -33,7 +35,7 @@ int muse_cov_finish(muse_handle* h, const double* theta, const double* gs, int n
 
 namespace {
 
-constexpr int kStepThreads = 256;
+constexpr int kStepThreads = 1024;
 constexpr int kMaxRanks = 16;
 
 struct OuterParams {
@@ -77,26 +79,67 @@ __device__ void consts_of(int family, int d, const double* th_sim, const double*
     }
 }
 
-// Σ_k f(k) over the sims of all ranks in a fixed order: thread t takes sims t, t + 256, … of every rank slot in turn, then a
-// shared-memory tree.  Deterministic for a given (nranks, counts).
+// Σ_k f_c(k) for every θ-component c over the sims of all ranks, in a fixed order: thread t takes sims t, t + T, … of every
+// rank slot in turn (loads issued four at a time — a lone CTA is latency-bound, not bandwidth-bound), then a shuffle tree
+// per warp and a second one over the warp results.  Deterministic for a given (nranks, counts).  f(o, c) reads element c of
+// the score row at offset o.  Results land in out[0..nt).
 template <class F>
-__device__ double block_sum(const int* counts, int nranks, long long need, int nt, F&& f, double* sh) {
-    double acc = 0.0;
-    for (int q = 0; q < nranks; ++q)
-        for (int r = threadIdx.x; r < counts[q]; r += kStepThreads) acc += f((size_t)q * need + (size_t)r * nt);
-    sh[threadIdx.x] = acc;
-    __syncthreads();
-    for (int s = kStepThreads / 2; s > 0; s >>= 1) {
-        if ((int)threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
-        __syncthreads();
+__device__ void block_sums(const int* counts, int nranks, long long need, int nt, F&& f, double (*sh)[32], double* out) {
+    double acc[kMaxTheta];
+#pragma unroll
+    for (int c = 0; c < kMaxTheta; ++c) acc[c] = 0.0;
+    constexpr int T = kStepThreads;
+    for (int q = 0; q < nranks; ++q) {
+        const int cnt = counts[q];
+        const size_t base = (size_t)q * need;
+        int r = threadIdx.x;
+        for (; r + 3 * T < cnt; r += 4 * T) {
+#pragma unroll
+            for (int c = 0; c < kMaxTheta; ++c) {
+                if (c < nt) {
+                    const double v0 = f(base + (size_t)r * nt, c), v1 = f(base + (size_t)(r + T) * nt, c);
+                    const double v2 = f(base + (size_t)(r + 2 * T) * nt, c), v3 = f(base + (size_t)(r + 3 * T) * nt, c);
+                    acc[c] += v0; acc[c] += v1; acc[c] += v2; acc[c] += v3;
+                }
+            }
+        }
+        for (; r < cnt; r += T) {
+#pragma unroll
+            for (int c = 0; c < kMaxTheta; ++c)
+                if (c < nt) acc[c] += f(base + (size_t)r * nt, c);
+        }
     }
-    const double r = sh[0];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int c = 0; c < kMaxTheta; ++c) {
+        if (c < nt) {
+            double v = acc[c];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) sh[c][warp] = v;
+        }
+    }
     __syncthreads();
-    return r;
+    for (int c = 0; c < nt; ++c) {
+        double v = (lane < T / 32) ? sh[c][lane] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        out[c] = v;                                      // every warp computes the same value
+    }
+    __syncthreads();
+}
+
+// mean and corrected variance of every component (two passes, like Statistics.mean / var)
+__device__ void block_mean_var(const double* g, const int* counts, int nranks, long long need, int nt, int n_total,
+                               double (*sh)[32], double* mean, double* var) {
+    block_sums(counts, nranks, need, nt, [&](size_t o, int c) { return g[o + c]; }, sh, mean);
+    for (int c = 0; c < nt; ++c) mean[c] /= n_total;
+    block_sums(counts, nranks, need, nt, [&](size_t o, int c) { const double dlt = g[o + c] - mean[c]; return dlt * dlt; }, sh, var);
+    for (int c = 0; c < nt; ++c) var[c] /= (n_total - 1);
 }
 
 __global__ void __launch_bounds__(kStepThreads) theta_step_kernel(const OuterParams P) {
-    __shared__ double sh[kStepThreads];
+    __shared__ double sh[kMaxTheta][32];
     __shared__ int bad;
     OuterState* st = P.st;
     if (st->done) {                                            // the pass before this step was skipped: keep skipping
@@ -106,7 +149,7 @@ __global__ void __launch_bounds__(kStepThreads) theta_step_kernel(const OuterPar
     if (threadIdx.x == 0) bad = 0;
     __syncthreads();
     for (int u = threadIdx.x; u < P.units_local; u += kStepThreads)
-        if (P.status_local[u] == MUSE_STATUS_NONFINITE) bad = 1;   // src/interface.jl:170
+        if (__ldcg(P.status_local + u) == MUSE_STATUS_NONFINITE) bad = 1;   // src/interface.jl:170
     __syncthreads();
     if (bad) {
         if (threadIdx.x == 0) { st->error = 1; st->done = 1; if (P.dyn_next) P.dyn_next->skip = 1; }
@@ -114,13 +157,7 @@ __global__ void __launch_bounds__(kStepThreads) theta_step_kernel(const OuterPar
     }
     const int row = P.iter - 1;
     double mean[kMaxTheta], var[kMaxTheta];
-    for (int c = 0; c < P.nt; ++c) {
-        const double* g = P.g_all + c;
-        const double m = block_sum(P.counts, P.nranks, P.need, P.nt, [&](size_t o) { return g[o]; }, sh) / P.n_total;
-        const double q = block_sum(P.counts, P.nranks, P.need, P.nt, [&](size_t o) { const double dlt = g[o] - m; return dlt * dlt; }, sh);
-        mean[c] = m;
-        var[c] = q / (P.n_total - 1);
-    }
+    block_mean_var(P.g_all, P.counts, P.nranks, P.need, P.nt, P.n_total, sh, mean, var);
     if (threadIdx.x != 0) return;
     double th_new[kMaxTheta];
     for (int c = 0; c < P.nt; ++c) {
@@ -133,13 +170,9 @@ __global__ void __launch_bounds__(kStepThreads) theta_step_kernel(const OuterPar
         const double h_prior = P.have_prior ? -1.0 / (P.prior_sigma[c] * P.prior_sigma[c]) : 0.0;  // :207
         const double h_inv_post = 1.0 / (1.0 / h_inv_like + h_prior);                              // :208 (diagonal)
         if (row < kOuterMaxIter) {
-            st->theta_hist[row][c] = th;
-            st->g_dat[row][c] = g_dat;
-            st->g_like[row][c] = g_like;
-            st->g_prior[row][c] = g_prior;
-            st->h_inv_like[row][c] = h_inv_like;
-            st->h_prior[row][c] = h_prior;
-            st->h_inv_post[row][c] = h_inv_post;
+            OuterRow& R = st->row[row];
+            R.theta[c] = th; R.g_dat[c] = g_dat; R.g_like[c] = g_like; R.g_prior[c] = g_prior;
+            R.h_inv_like[c] = h_inv_like; R.h_prior[c] = h_prior; R.h_inv_post[c] = h_inv_post;
         }
         th_new[c] = th - P.alpha * (h_inv_post * g_post);                                          // :224
     }
@@ -149,8 +182,8 @@ __global__ void __launch_bounds__(kStepThreads) theta_step_kernel(const OuterPar
     if (P.iter >= 2) {                                   // the test at the top of iteration iter + 1 > 2   (:163-166)
         double q = 0.0;
         for (int c = 0; c < P.nt; ++c) {
-            const double dlt = st->theta_hist[row][c] - st->theta_hist[row - 1][c];
-            q += dlt * st->h_inv_post[row][c] * dlt;
+            const double dlt = st->row[row].theta[c] - st->row[row - 1].theta[c];
+            q += dlt * st->row[row].h_inv_post[c] * dlt;
         }
         q = -q;
         if (q < 0.0) { st->error = 2; done = 1; }        // DomainError of sqrt in the reference
@@ -166,20 +199,16 @@ __global__ void __launch_bounds__(kStepThreads) theta_step_kernel(const OuterPar
 
 // after the last θ-step of a chunk: if the loop has ended, the constants of get_H!'s launches; otherwise they are skipped
 __global__ void __launch_bounds__(kStepThreads) cov_prep_kernel(const CovParams P) {
-    __shared__ double sh[kStepThreads];
+    __shared__ double sh[kMaxTheta][32];
     OuterState* st = P.st;
     if (!st->done || st->error || st->n_iter < 1) {
         if (threadIdx.x == 0) { P.dyn_fid->skip = 1; P.dyn_fd->skip = 1; }
         return;
     }
     const double* gall = P.g_all_slot[(st->n_iter - 1) % kOuterSlots];
-    double step[kMaxTheta];
-    for (int c = 0; c < P.nt; ++c) {                     // step = 0.1 ./ std(gs)   (:411-413), gs = the last scores (:231)
-        const double* g = gall + c;
-        const double m = block_sum(P.counts, P.nranks, P.need, P.nt, [&](size_t o) { return g[o]; }, sh) / P.n_total;
-        const double q = block_sum(P.counts, P.nranks, P.need, P.nt, [&](size_t o) { const double dlt = g[o] - m; return dlt * dlt; }, sh);
-        step[c] = 0.1 / sqrt(q / (P.n_total - 1));
-    }
+    double step[kMaxTheta], mean[kMaxTheta], var[kMaxTheta];
+    block_mean_var(gall, P.counts, P.nranks, P.need, P.nt, P.n_total, sh, mean, var);
+    for (int c = 0; c < P.nt; ++c) step[c] = 0.1 / sqrt(var[c]);       // step = 0.1 ./ std(gs)   (:411-413), gs = the last scores (:231)
     if (threadIdx.x != 0) return;
     double th0[kMaxTheta];
     for (int c = 0; c < P.nt; ++c) { th0[c] = st->theta[c]; st->step[c] = step[c]; }
@@ -295,10 +324,13 @@ extern "C" int muse_b200_muse_solve(muse_handle* h, const double* theta0, int32_
     out->n_iter = 0;
     int it_done = 0;                        // iterations whose history has been copied out
     bool finished = false;
+    const int items_fd = nh_mine * nt * 2;
     while (!finished) {
         const auto t0 = std::chrono::steady_clock::now();
         const int first = it_done + 1;
-        const int last = std::min(maxsteps, it_done + kOuterSlots);
+        // the first chunk holds the two passes the convergence test needs before it can stop the loop (the reference's
+        // typical solve: two iterations, then `break` at the top of the third, :163-166); later chunks hold three
+        const int last = std::min(maxsteps, it_done + (it_done == 0 ? 2 : kOuterSlots));
         for (int i = first; i <= last; ++i) {
             const int slot = (i - 1) % kOuterSlots;
             const OutBlock& ob = h->outer_slot[slot];
@@ -341,8 +373,12 @@ extern "C" int muse_b200_muse_solve(muse_handle* h, const double* theta0, int32_
                 if (rc != MUSE_OK) return rc;
             }
         }
-        // results of the chunk: state, per-pass outputs, gathered scores, FD outputs — then the one synchronisation
-        OUTER_TRY(h, cudaMemcpyAsync(sh_, sd, sizeof(OuterState), cudaMemcpyDeviceToHost, h->stream));
+        // results of the chunk — the state header with the chunk's history rows, the per-pass outputs, the gathered scores,
+        // the scores and statuses of the FD sims — then the one synchronisation
+        const size_t head = offsetof(OuterState, row);
+        OUTER_TRY(h, cudaMemcpyAsync(sh_, sd, head, cudaMemcpyDeviceToHost, h->stream));
+        OUTER_TRY(h, cudaMemcpyAsync(&sh_->row[first - 1], &sd->row[first - 1], (size_t)(last - first + 1) * sizeof(OuterRow),
+                                     cudaMemcpyDeviceToHost, h->stream));
         for (int i = first; i <= last; ++i) {
             const OutBlock& ob = h->outer_slot[(i - 1) % kOuterSlots];
             OUTER_TRY(h, cudaMemcpyAsync(ob.hst, ob.d, ob.bytes, cudaMemcpyDeviceToHost, h->stream));
@@ -350,7 +386,10 @@ extern "C" int muse_b200_muse_solve(muse_handle* h, const double* theta0, int32_
                 OUTER_TRY(h, cudaMemcpyAsync(h->outer_gall_h + (size_t)((i - 1) % kOuterSlots) * gall_doubles, h->outer_gall[(i - 1) % kOuterSlots],
                                              gall_doubles * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         }
-        if (get_covariance && nh_mine > 0) OUTER_TRY(h, cudaMemcpyAsync(h->out_h, h->out_d, h->out_bytes, cudaMemcpyDeviceToHost, h->stream));
+        if (get_covariance && nh_mine > 0) {
+            OUTER_TRY(h, cudaMemcpyAsync(h->g_h, h->g_d, (size_t)items_fd * nt * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            OUTER_TRY(h, cudaMemcpyAsync(h->status_h, h->status_d, (size_t)items_fd * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        }
         OUTER_TRY(h, cudaStreamSynchronize(h->stream));
         const double chunk_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 
@@ -376,14 +415,15 @@ extern "C" int muse_b200_muse_solve(muse_handle* h, const double* theta0, int32_
         for (int i = first; i <= n_now && i <= last; ++i) {
             const int row = i - 1, slot = row % kOuterSlots;
             const OutBlock& ob = h->outer_slot[slot];
+            const OuterRow& R = sh_->row[row];
             for (int c = 0; c < nt; ++c) {
-                out->theta_hist[(size_t)row * nt + c] = sh_->theta_hist[row][c];
-                out->g_dat_hist[(size_t)row * nt + c] = sh_->g_dat[row][c];
-                out->g_like_hist[(size_t)row * nt + c] = sh_->g_like[row][c];
-                out->g_prior_hist[(size_t)row * nt + c] = sh_->g_prior[row][c];
-                out->h_inv_like_hist[(size_t)row * nt + c] = sh_->h_inv_like[row][c];
-                out->h_prior_hist[(size_t)row * nt + c] = sh_->h_prior[row][c];
-                out->h_inv_post_hist[(size_t)row * nt + c] = sh_->h_inv_post[row][c];
+                out->theta_hist[(size_t)row * nt + c] = R.theta[c];
+                out->g_dat_hist[(size_t)row * nt + c] = R.g_dat[c];
+                out->g_like_hist[(size_t)row * nt + c] = R.g_like[c];
+                out->g_prior_hist[(size_t)row * nt + c] = R.g_prior[c];
+                out->h_inv_like_hist[(size_t)row * nt + c] = R.h_inv_like[c];
+                out->h_prior_hist[(size_t)row * nt + c] = R.h_prior[c];
+                out->h_inv_post_hist[(size_t)row * nt + c] = R.h_inv_post[c];
             }
             double* gs = out->g_sims_hist + (size_t)row * nsims_total * nt;
             if (multi) {

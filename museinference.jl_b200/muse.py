@@ -175,10 +175,11 @@ def muse_(result: MuseResult, prob: AbstractMuseProblem, theta0=None, **kwargs):
         th_unreg_prev = theta.copy()
         for k in range(r["n_iter"]):
             hl, hp, hq = r["h_inv_like_hist"][k], r["h_prior_hist"][k], r["h_inv_post_hist"][k]
+            gsk = r["g_sims_hist"][k].copy()              # identity transform: g and g′ are the same array
             history.append(dict(
                 theta=r["theta_hist"][k].copy(), theta_unreg=th_unreg_prev,
                 theta_t=r["theta_hist"][k].copy(), theta_unreg_t=th_unreg_prev,
-                g_like_sims=r["g_sims_hist"][k].copy(), g_like_sims_t=r["g_sims_hist"][k].copy(), g_like_dat=r["g_dat_hist"][k].copy(), g_like=r["g_like_hist"][k].copy(),
+                g_like_sims=gsk, g_like_sims_t=gsk, g_like_dat=r["g_dat_hist"][k].copy(), g_like=r["g_like_hist"][k].copy(),
                 g_prior=r["g_prior_hist"][k].copy(), g_post=r["g_like_hist"][k] + r["g_prior_hist"][k],
                 H_inv_post=np.diag(hq), H_prior=np.diag(hp), H_inv_like=np.diag(hl), H_inv_like_sims=np.diag(hl),
                 z_history_dat=dict(iters=int(r["iters_hist"][k, 0]), fg_evals=int(r["fg_hist"][k, 0]),

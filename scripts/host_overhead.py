@@ -15,7 +15,7 @@ def wrap(name):
     def g(*a, **k):
         t = time.perf_counter(); r = f(*a, **k); acc[name] = acc.get(name, 0.0) + time.perf_counter() - t; return r
     setattr(be, name, g)
-for nm in ("map_score", "fd_jacobian", "muse_iterate", "muse_covariance"):
+for nm in ("map_score", "fd_jacobian", "muse_iterate", "muse_covariance", "muse_solve"):
     wrap(nm)
 K = 50
 be.profile_reset(True)
