@@ -49,6 +49,10 @@ static int theta_consts(const muse_cfg& c, const double* th_sim, const double* t
     return -1;
 }
 
+int muse_theta_consts(const muse_cfg& c, const double* th_sim, const double* th_eval, IsoSample* smp, IsoEval* ev) {
+    return theta_consts(c, th_sim, th_eval, smp, ev);
+}
+
 // Outputs live in ONE device block with a pinned host mirror of the same layout
 //   [ g: cap×nθ f64 | ‖∇z‖∞: cap f64 | f: cap f64 | iterations: cap i32 | f/g evaluations: cap i32 | status: cap i32 ]
 // so that a fetch is a single device→host copy (five small copies cost ~8 µs each on the copy engine).
@@ -141,10 +145,15 @@ static void fill_common(muse_handle* h, SolveLaunch& L) {
 
 static int launch_solver(muse_handle* h, const SolveLaunch& L, double bytes) {
     muse_handle::Rec r{};
+    // inside a stream capture (device-resident loop, muse_outer.cu) the event records become external event-record nodes of
+    // the graph, and the launch counters go to the graph's own tallies (added at every graph launch)
+    const unsigned evflag = h->capturing ? cudaEventRecordExternal : cudaEventRecordDefault;
+    int64_t& n_launch = h->capturing ? h->cap_launches : h->acc.launches;
+    int64_t& n_solve = h->capturing ? h->cap_solve_launches : h->acc.solve_launches;
     if (h->prof) {
         CUDA_TRY(h, cudaEventCreate(&r.a));
         CUDA_TRY(h, cudaEventCreate(&r.b));
-        CUDA_TRY(h, cudaEventRecord(r.a, h->stream));
+        CUDA_TRY(h, cudaEventRecordWithFlags(r.a, h->stream, evflag));
     }
     if (h->geo.stream) {
         // pass 1: single-pass speculative streaming kernel (its finisher warps replay the scalar optimiser on the
@@ -159,20 +168,20 @@ static int launch_solver(muse_handle* h, const SolveLaunch& L, double bytes) {
         R.item_list = h->redo_items;
         R.item_count = h->redo_count;
         CUDA_TRY(h, launch_iso_solver(R, h->geo, h->stream));
-        h->acc.launches += 2;
+        n_launch += 2;
     } else {
         CUDA_TRY(h, launch_iso_solver(L, h->geo, h->stream));
-        h->acc.launches += 1;
+        n_launch += 1;
     }
-    h->acc.solve_launches += 1;
+    n_solve += 1;
     if (h->prof) {
-        CUDA_TRY(h, cudaEventRecord(r.b, h->stream));
+        CUDA_TRY(h, cudaEventRecordWithFlags(r.b, h->stream, evflag));
         r.cls = 0;
         r.units = L.nitems;
         r.bytes = bytes;
         r.kind = h->pass_kind;
         r.tag = h->rec_tag;
-        h->recs.push_back(r);
+        (h->capturing ? h->outer_recs : h->recs).push_back(r);
     }
     return 0;
 }

@@ -82,6 +82,14 @@ struct muse_handle {
     size_t outer_gall_doubles = 0;
     OuterState *outer_st_d = nullptr, *outer_st_h = nullptr;
     muse::DynConsts* outer_dyn = nullptr;                // [0], [1]: passes (alternating); [2]: fiducial; [3]: FD sims
+    muse::DynConsts* outer_dyn_stage = nullptr;          // pinned: constants of pass 1 at θ₀ (uploaded by a node of the graph)
+    // CUDA graph of the first chunk of the device-resident loop — the whole of a typical solve: one cudaGraphLaunch replaces
+    // ≈ 25 stream operations (launches, memsets, copies, event records) whose CPU-side issue cost, not the GPU, bounded the
+    // small configurations.  Captured from the very enqueue code the eager path runs, on the second solve with a given key.
+    bool capturing = false;                              // launch_solver: record events as external nodes, count into cap_*
+    void* outer_exec = nullptr;                          // cudaGraphExec_t
+    std::vector<unsigned char> outer_key, outer_warm_key;   // parameters baked into the graph / of the last eager solve
+    int64_t cap_launches = 0, cap_solve_launches = 0;    // kernel launches / solver passes inside the graph
 
     // exchange step (muse_comm.cu): NCCL communicator and staging buffers
     void* comm = nullptr;
@@ -95,6 +103,7 @@ struct muse_handle {
     bool prof = false;
     struct Rec { cudaEvent_t a, b; int cls; double units, bytes; int kind; int tag; };
     std::vector<Rec> recs;
+    std::vector<Rec> outer_recs;         // event pairs recorded by nodes of the graph (re-recorded at every graph launch)
     muse_profile acc{};
     int pass_kind = MUSE_PASS_COLD;      // kind of the solver pass being enqueued (set by the entry point)
     int rec_tag = 0;                     // device-resident loop: iteration (> 0) or covariance stage (−1) a launch belongs to,
@@ -103,6 +112,7 @@ struct muse_handle {
 };
 
 // internal entry points of muse_api.cu used by the device-resident outer loop (muse_outer.cu)
+int  muse_theta_consts(const muse_cfg& c, const double* th_sim, const double* th_eval, muse::IsoSample* smp, muse::IsoEval* ev);
 int  muse_outblock_ensure(muse_handle* h, OutBlock& ob, int items);
 void muse_outblock_free(OutBlock& ob);
 int  muse_pass_enqueue(muse_handle* h, const double* theta_sim, const double* theta_eval, double atol, int include_data,

@@ -22,6 +22,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstddef>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -235,6 +236,14 @@ __global__ void __launch_bounds__(kStepThreads) cov_prep_kernel(const CovParams 
         }                                                                                     \
     } while (0)
 
+void outer_graph_release(muse_handle* h) {
+    if (h->outer_exec) cudaGraphExecDestroy((cudaGraphExec_t)h->outer_exec);
+    h->outer_exec = nullptr;
+    for (auto& r : h->outer_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    h->outer_recs.clear();
+    h->outer_key.clear();
+}
+
 int outer_ensure(muse_handle* h, int units, size_t gall_doubles) {
     for (int s = 0; s < kOuterSlots; ++s) {
         const int rc = muse_outblock_ensure(h, h->outer_slot[s], units);
@@ -244,6 +253,7 @@ int outer_ensure(muse_handle* h, int units, size_t gall_doubles) {
         OUTER_TRY(h, cudaMalloc(&h->outer_st_d, sizeof(OuterState)));
         OUTER_TRY(h, cudaMallocHost(&h->outer_st_h, sizeof(OuterState)));
         OUTER_TRY(h, cudaMalloc(&h->outer_dyn, 4 * sizeof(DynConsts)));
+        OUTER_TRY(h, cudaMallocHost(&h->outer_dyn_stage, sizeof(DynConsts)));
     }
     if (gall_doubles > h->outer_gall_doubles) {
         for (int s = 0; s < kOuterSlots; ++s) { cudaFree(h->outer_gall[s]); h->outer_gall[s] = nullptr; }
@@ -260,6 +270,9 @@ int outer_ensure(muse_handle* h, int units, size_t gall_doubles) {
 }  // namespace
 
 void muse_outer_release(muse_handle* h) {
+    outer_graph_release(h);
+    cudaFreeHost(h->outer_dyn_stage);
+    h->outer_dyn_stage = nullptr;
     for (int s = 0; s < kOuterSlots; ++s) { muse_outblock_free(h->outer_slot[s]); cudaFree(h->outer_gall[s]); h->outer_gall[s] = nullptr; }
     cudaFreeHost(h->outer_gall_h);
     cudaFree(h->outer_st_d);
@@ -315,38 +328,34 @@ extern "C" int muse_b200_muse_solve(muse_handle* h, const double* theta0, int32_
 
     OuterState* sd = h->outer_st_d;
     OuterState* sh_ = h->outer_st_h;
-    std::memset(sh_, 0, sizeof(OuterState));
-    for (int c = 0; c < nt; ++c) sh_->theta[c] = theta0[c];
-    OUTER_TRY(h, cudaMemcpyAsync(sd, sh_, sizeof(OuterState), cudaMemcpyHostToDevice, h->stream));
     P.st = sd;
     DynConsts* dyn = h->outer_dyn;
-
-    out->n_iter = 0;
-    int it_done = 0;                        // iterations whose history has been copied out
-    bool finished = false;
     const int items_fd = nh_mine * nt * 2;
-    while (!finished) {
-        const auto t0 = std::chrono::steady_clock::now();
-        const int first = it_done + 1;
-        // the first chunk holds the two passes the convergence test needs before it can stop the loop (the reference's
-        // typical solve: two iterations, then `break` at the top of the third, :163-166); later chunks hold three
-        const int last = std::min(maxsteps, it_done + (it_done == 0 ? 2 : kOuterSlots));
+
+    // Everything one chunk puts on the stream: (first chunk) the initial state and the constants of pass 1 from pinned
+    // staging, the passes with their exchange and θ-step, the conditional covariance stage, the copies of the results.
+    // The same code runs eagerly or under stream capture.
+    auto enqueue_chunk = [&](int first, int last) -> int {
+        int rc2;
+        if (first == 1) {
+            OUTER_TRY(h, cudaMemcpyAsync(sd, sh_, offsetof(OuterState, row), cudaMemcpyHostToDevice, h->stream));
+            OUTER_TRY(h, cudaMemcpyAsync(&dyn[1], h->outer_dyn_stage, sizeof(DynConsts), cudaMemcpyHostToDevice, h->stream));
+        }
         for (int i = first; i <= last; ++i) {
             const int slot = (i - 1) % kOuterSlots;
             const OutBlock& ob = h->outer_slot[slot];
             // pass i: data + local sims, start zeros / user z₀ on the first, previous ẑ afterwards (:169-176)
             h->rec_tag = i;
-            rc = muse_pass_enqueue(h, theta0, theta0, atol, 1, i == 1 ? first_start : MUSE_START_PREV, 0, nloc, &ob,
-                                   i == 1 ? nullptr : &dyn[i & 1]);
+            rc2 = muse_pass_enqueue(h, nullptr, nullptr, atol, 1, i == 1 ? first_start : MUSE_START_PREV, 0, nloc, &ob, &dyn[i & 1]);
             h->rec_tag = 0;
-            if (rc != MUSE_OK) return rc;
+            if (rc2 != MUSE_OK) return rc2;
             P.iter = i;
             P.g_local = ob.g_d;
             P.status_local = ob.status_d;
             if (multi) {                    // the one exchange step, on the stream
                 size_t need = 0;
-                rc = muse_comm_allgather_dev_enqueue(h, ob.g_d + nt, nt, counts, &need);
-                if (rc != MUSE_OK) return rc;
+                rc2 = muse_comm_allgather_dev_enqueue(h, ob.g_d + nt, nt, counts, &need);
+                if (rc2 != MUSE_OK) return rc2;
                 OUTER_TRY(h, cudaMemcpyAsync(h->outer_gall[slot], h->comm_recv, gall_doubles * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
                 P.g_all = h->outer_gall[slot];
             } else {
@@ -355,7 +364,7 @@ extern "C" int muse_b200_muse_solve(muse_handle* h, const double* theta0, int32_
             P.dyn_next = &dyn[(i + 1) & 1];
             theta_step_kernel<<<1, kStepThreads, 0, h->stream>>>(P);
             OUTER_TRY(h, cudaGetLastError());
-            h->acc.launches += 1;
+            (h->capturing ? h->cap_launches : h->acc.launches) += 1;
         }
         if (get_covariance) {
             CovParams C{};
@@ -365,18 +374,17 @@ extern "C" int muse_b200_muse_solve(muse_handle* h, const double* theta0, int32_
             C.st = sd; C.dyn_fid = &dyn[2]; C.dyn_fd = &dyn[3];
             cov_prep_kernel<<<1, kStepThreads, 0, h->stream>>>(C);
             OUTER_TRY(h, cudaGetLastError());
-            h->acc.launches += 1;
+            (h->capturing ? h->cap_launches : h->acc.launches) += 1;
             if (nh_mine > 0) {
                 h->rec_tag = -1;
-                rc = muse_fd_enqueue(h, nullptr, nullptr, nh_mine, atol, &dyn[2], &dyn[3]);
+                rc2 = muse_fd_enqueue(h, nullptr, nullptr, nh_mine, atol, &dyn[2], &dyn[3]);
                 h->rec_tag = 0;
-                if (rc != MUSE_OK) return rc;
+                if (rc2 != MUSE_OK) return rc2;
             }
         }
         // results of the chunk — the state header with the chunk's history rows, the per-pass outputs, the gathered scores,
-        // the scores and statuses of the FD sims — then the one synchronisation
-        const size_t head = offsetof(OuterState, row);
-        OUTER_TRY(h, cudaMemcpyAsync(sh_, sd, head, cudaMemcpyDeviceToHost, h->stream));
+        // the scores and statuses of the FD sims
+        OUTER_TRY(h, cudaMemcpyAsync(sh_, sd, offsetof(OuterState, row), cudaMemcpyDeviceToHost, h->stream));
         OUTER_TRY(h, cudaMemcpyAsync(&sh_->row[first - 1], &sd->row[first - 1], (size_t)(last - first + 1) * sizeof(OuterRow),
                                      cudaMemcpyDeviceToHost, h->stream));
         for (int i = first; i <= last; ++i) {
@@ -390,6 +398,71 @@ extern "C" int muse_b200_muse_solve(muse_handle* h, const double* theta0, int32_
             OUTER_TRY(h, cudaMemcpyAsync(h->g_h, h->g_d, (size_t)items_fd * nt * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
             OUTER_TRY(h, cudaMemcpyAsync(h->status_h, h->status_d, (size_t)items_fd * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         }
+        return MUSE_OK;
+    };
+
+    // what a captured graph bakes in: every by-value launch parameter and every pointer the chunk touches
+    std::vector<unsigned char> key;
+    {
+        auto put = [&](const void* p, size_t n) { const unsigned char* b = static_cast<const unsigned char*>(p); key.insert(key.end(), b, b + n); };
+        const int ints[] = {maxsteps, first_start, get_covariance, nh_mine, nsims_total, nloc, h->prof ? 1 : 0, P.have_prior, h->out_cap, h->h_cap};
+        const double dbl[] = {theta_rtol, atol, alpha};
+        put(ints, sizeof(ints)); put(dbl, sizeof(dbl)); put(P.prior_mean, sizeof(P.prior_mean)); put(P.prior_sigma, sizeof(P.prior_sigma));
+        const void* ptrs[] = {h->stream, h->out_d, h->out_h, h->zHA, sd, sh_, dyn, h->outer_slot[0].d, h->outer_slot[1].d, h->outer_slot[2].d,
+                              h->gpart, h->dbg, h->xi, h->xi_h};
+        put(ptrs, sizeof(ptrs));
+    }
+    static const bool graphs_on = [] { const char* e = std::getenv("MUSE_OUTER_GRAPH"); return !e || std::atoi(e) != 0; }();
+    const bool use_graph = graphs_on && !multi;
+
+    out->n_iter = 0;
+    int it_done = 0;                        // iterations whose history has been copied out
+    bool finished = false;
+    while (!finished) {
+        const auto t0 = std::chrono::steady_clock::now();
+        const int first = it_done + 1;
+        // the first chunk holds the two passes the convergence test needs before it can stop the loop (the reference's
+        // typical solve: two iterations, then `break` at the top of the third, :163-166); later chunks hold three
+        const int last = std::min(maxsteps, it_done + (it_done == 0 ? 2 : kOuterSlots));
+        bool via_graph = false;
+        if (first == 1) {
+            std::memset(sh_, 0, offsetof(OuterState, row));
+            for (int c = 0; c < nt; ++c) sh_->theta[c] = theta0[c];
+            std::memset(h->outer_dyn_stage, 0, sizeof(DynConsts));
+            if (muse_theta_consts(h->cfg, theta0, theta0, &h->outer_dyn_stage->smp[0], &h->outer_dyn_stage->ev) != 0) { h->err = "family"; return MUSE_EUNSUPPORTED; }
+            if (use_graph && h->outer_exec && key == h->outer_key) {
+                via_graph = true;
+            } else if (use_graph && key == h->outer_warm_key) {
+                // second solve with these parameters: every buffer exists, capture the chunk the eager path would enqueue
+                outer_graph_release(h);
+                cudaGraph_t graph = nullptr;
+                h->capturing = true;
+                h->cap_launches = h->cap_solve_launches = 0;
+                cudaError_t e = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed);
+                rc = e == cudaSuccess ? enqueue_chunk(first, last) : MUSE_ECUDA;
+                const cudaError_t e2 = e == cudaSuccess ? cudaStreamEndCapture(h->stream, &graph) : e;
+                h->capturing = false;
+                cudaGraphExec_t exec = nullptr;
+                if (rc == MUSE_OK && e2 == cudaSuccess && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
+                    h->outer_exec = exec;
+                    h->outer_key = key;
+                    via_graph = true;
+                } else {
+                    cudaGetLastError();
+                    outer_graph_release(h);             // fall back to the eager path below
+                }
+                if (graph) cudaGraphDestroy(graph);
+            }
+        }
+        if (via_graph) {
+            OUTER_TRY(h, cudaGraphLaunch((cudaGraphExec_t)h->outer_exec, h->stream));
+            h->acc.launches += h->cap_launches;
+            h->acc.solve_launches += h->cap_solve_launches;
+        } else {
+            rc = enqueue_chunk(first, last);
+            if (rc != MUSE_OK) return rc;
+            if (first == 1) h->outer_warm_key = key;
+        }
         OUTER_TRY(h, cudaStreamSynchronize(h->stream));
         const double chunk_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 
@@ -401,7 +474,17 @@ extern "C" int muse_b200_muse_solve(muse_handle* h, const double* theta0, int32_
             int skipped = std::max(0, last - std::max(n_now, first - 1));
             if (get_covariance && nh_mine > 0 && !cov_ran) skipped += 2;
             h->acc.solve_launches -= skipped;
-            for (size_t k = 0; k < h->recs.size();) {
+            if (via_graph) {                 // the graph's own event pairs: fold the passes that ran into the accumulators now
+                for (const muse_handle::Rec& r : h->outer_recs) {
+                    if (r.tag > n_now || (r.tag == -1 && !cov_ran)) continue;
+                    float ms = 0.f;
+                    if (cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) { cudaGetLastError(); continue; }
+                    h->acc.solve_ms += ms; h->acc.solve_units += r.units; h->acc.solve_bytes += r.bytes;
+                    const int kd = r.kind >= 0 && r.kind < MUSE_PASS_KINDS ? r.kind : MUSE_PASS_COLD;
+                    h->acc_pass.launches[kd] += 1; h->acc_pass.ms[kd] += ms; h->acc_pass.units[kd] += r.units; h->acc_pass.bytes[kd] += r.bytes;
+                }
+            }
+            for (size_t k = 0; !via_graph && k < h->recs.size();) {
                 const muse_handle::Rec& r = h->recs[k];
                 if (r.tag > n_now || (r.tag == -1 && !cov_ran)) {
                     cudaEventDestroy(r.a); cudaEventDestroy(r.b);
