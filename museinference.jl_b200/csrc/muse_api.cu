@@ -89,26 +89,36 @@ static int ensure_outputs(muse_handle* h, int items) {
     return 0;
 }
 
-// a stand-alone output block of the same layout (device-resident outer loop: one per pass of a chunk)
-int muse_outblock_ensure(muse_handle* h, OutBlock& ob, int items) {
-    if (items <= ob.cap) return 0;
-    muse_outblock_free(ob);
+// output blocks of the same layout outside the handle's main block (device-resident outer loop)
+size_t muse_outblock_bytes(const muse_handle* h, int items) {
     const size_t n = (size_t)items, nt = (size_t)h->cfg.ntheta;
     const size_t n_i = (n + 1) & ~(size_t)1;
-    ob.bytes = n * (nt + 2) * sizeof(double) + 3 * n_i * sizeof(int);
-    CUDA_TRY(h, cudaMalloc(&ob.d, ob.bytes));
-    CUDA_TRY(h, cudaMallocHost(&ob.hst, ob.bytes));
+    return n * (nt + 2) * sizeof(double) + 3 * n_i * sizeof(int);
+}
+
+void muse_outblock_carve(const muse_handle* h, OutBlock& ob, unsigned char* dev, unsigned char* host, int items) {
+    const size_t n = (size_t)items, nt = (size_t)h->cfg.ntheta;
+    const size_t n_i = (n + 1) & ~(size_t)1;
+    ob.d = dev; ob.hst = host; ob.bytes = muse_outblock_bytes(h, items); ob.cap = items; ob.owned = false;
     ob.g_d = reinterpret_cast<double*>(ob.d); ob.gnorm_d = ob.g_d + n * nt; ob.f_d = ob.gnorm_d + n;
     ob.iters_d = reinterpret_cast<int*>(ob.f_d + n); ob.fg_d = ob.iters_d + n_i; ob.status_d = ob.fg_d + n_i;
     ob.g_h = reinterpret_cast<double*>(ob.hst); ob.gnorm_h = ob.g_h + n * nt;
     ob.iters_h = reinterpret_cast<int*>(ob.gnorm_h + 2 * n); ob.fg_h = ob.iters_h + n_i; ob.status_h = ob.fg_h + n_i;
-    ob.cap = items;
+}
+
+int muse_outblock_ensure(muse_handle* h, OutBlock& ob, int items) {
+    if (items <= ob.cap) return 0;
+    muse_outblock_free(ob);
+    unsigned char *dev = nullptr, *host = nullptr;
+    CUDA_TRY(h, cudaMalloc(&dev, muse_outblock_bytes(h, items)));
+    CUDA_TRY(h, cudaMallocHost(&host, muse_outblock_bytes(h, items)));
+    muse_outblock_carve(h, ob, dev, host, items);
+    ob.owned = true;
     return 0;
 }
 
 void muse_outblock_free(OutBlock& ob) {
-    cudaFree(ob.d);
-    cudaFreeHost(ob.hst);
+    if (ob.owned) { cudaFree(ob.d); cudaFreeHost(ob.hst); }
     ob = OutBlock{};
 }
 
@@ -161,12 +171,21 @@ static int launch_solver(muse_handle* h, const SolveLaunch& L, double bytes) {
         // then its CTAs exit at once)
         SolveLaunch S = L;
         if (h->geo.stream != 1 || h->dbg_cap < h->geo.stream_grid) S.dbg = nullptr;   // the TMA-ring kernel stamps per CTA
-        CUDA_TRY(h, cudaMemsetAsync(h->redo_count, 0, 2 * sizeof(int), h->stream));
+        int* ctr = h->redo_count;
+        if (h->ctr_override) {            // device-resident loop: a counter pair of its own per chain, zeroed with the state
+            ctr = h->ctr_override;
+            S.redo_count = ctr;
+            S.work_next = ctr + 1;
+        } else {
+            CUDA_TRY(h, cudaMemsetAsync(h->redo_count, 0, 2 * sizeof(int), h->stream));
+        }
         CUDA_TRY(h, launch_iso_stream(S, h->geo, h->stream));
         SolveLaunch R = L;
         R.dbg = nullptr;                  // the diagnostics buffer belongs to the streaming kernel's per-CTA rows
         R.item_list = h->redo_items;
-        R.item_count = h->redo_count;
+        R.item_count = ctr;
+        R.redo_count = ctr;
+        R.work_next = ctr + 1;
         CUDA_TRY(h, launch_iso_solver(R, h->geo, h->stream));
         n_launch += 2;
     } else {
@@ -543,13 +562,14 @@ int muse_b200_device_scores(muse_handle* h, double** g_dev, int32_t* capacity_un
 }
 
 // fetch the ± scores and form central_fdm(3,1): sum(fs .* [-1/2, 0, 1/2]) / step   — src/util.jl:13-19
-void muse_fd_combine_host(muse_handle* h, const double* step, int nsims_H, double* Hs_out, int32_t* status_out) {
+void muse_fd_combine_host(muse_handle* h, const double* g_h, const int* status_h, const double* step, int nsims_H,
+                          double* Hs_out, int32_t* status_out) {
     const int nt = h->cfg.ntheta, items = nsims_H * nt * 2;
-    if (status_out) std::memcpy(status_out, h->status_h, (size_t)items * sizeof(int));
+    if (status_out) std::memcpy(status_out, status_h, (size_t)items * sizeof(int));
     for (int k = 0; k < nsims_H; ++k)
         for (int n = 0; n < nt; ++n) {
-            const double* gm = h->g_h + ((size_t)(k * nt + n) * 2 + 0) * nt;
-            const double* gp = h->g_h + ((size_t)(k * nt + n) * 2 + 1) * nt;
+            const double* gm = g_h + ((size_t)(k * nt + n) * 2 + 0) * nt;
+            const double* gp = g_h + ((size_t)(k * nt + n) * 2 + 1) * nt;
             for (int i = 0; i < nt; ++i) {
                 double acc = gm[i] * -0.5;
                 acc = acc + 0.0;
@@ -563,7 +583,7 @@ static int fd_combine(muse_handle* h, const double* step, int nsims_H, double* H
     const int nt = h->cfg.ntheta, items = nsims_H * nt * 2;
     int rc = muse_b200_fetch(h, items, h->g_h, nullptr, nullptr, nullptr, status_out ? h->status_h : nullptr);
     if (rc != 0) return rc;
-    muse_fd_combine_host(h, step, nsims_H, Hs_out, status_out);
+    muse_fd_combine_host(h, h->g_h, h->status_h, step, nsims_H, Hs_out, status_out);
     return MUSE_OK;
 }
 
@@ -571,7 +591,7 @@ static int fd_combine(muse_handle* h, const double* step, int nsims_H, double* H
 // Shared launch sequence of muse_b200_fd_jacobian / muse_b200_fd_scores: the fiducial solve and the 2·nθ virtual sims per
 // H sim, sampled at the rows of th_pts (row 2n = the "−" point of column n, row 2n+1 its "+" point), MAP + score at theta0.
 static int fd_launch(muse_handle* h, const double* theta0, const double* th_pts, int nsims_H, double atol,
-                     const DynConsts* dyn_fid = nullptr, const DynConsts* dyn_fd = nullptr) {
+                     const DynConsts* dyn_fid = nullptr, const DynConsts* dyn_fd = nullptr, const OutBlock* ob = nullptr) {
     const bool hshard = h->cfg.nsims_h > 0;
     const int nt = h->cfg.ntheta;
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
@@ -603,11 +623,20 @@ static int fd_launch(muse_handle* h, const double* theta0, const double* th_pts,
     else if (theta_consts(h->cfg, theta0, theta0, &F.smp[0], &F.ev) != 0) MUSE_FAIL(h, MUSE_EUNSUPPORTED, "family");
     F.zA = h->zfidA;
     F.zB = h->zfidB;
-    F.zstate = h->zfid_state;
-    CUDA_TRY(h, cudaMemsetAsync(h->zfid_state, 0, sizeof(int), h->stream));
+    int* zst = h->zfid_override ? h->zfid_override : h->zfid_state;     // override: already zero (uploaded with the loop's state)
+    F.zstate = zst;
+    if (!h->zfid_override) CUDA_TRY(h, cudaMemsetAsync(h->zfid_state, 0, sizeof(int), h->stream));
+    auto outputs_to = [&](SolveLaunch& X) {
+        if (!ob) return;
+        X.g_out = ob->g_d; X.iters_out = ob->iters_d; X.fg_out = ob->fg_d;
+        X.gnorm_out = ob->gnorm_d; X.f_out = ob->f_d; X.status_out = ob->status_d;
+    };
+    outputs_to(F);
     h->pass_kind = MUSE_PASS_FIDUCIAL;
+    int* const ctr0 = h->ctr_override;
     int rc = launch_solver(h, F, 3 * d8);
     if (rc != 0) return rc;
+    if (ctr0) h->ctr_override = ctr0 + 2;          // the virtual sims' chain takes the next counter pair
     // (2) virtual sims at the 2·nθ sample points, MAP + score at θ₀ from the fiducial start — src/muse.jl:426-433
     SolveLaunch L;
     fill_common(h, L);
@@ -616,7 +645,8 @@ static int fd_launch(muse_handle* h, const double* theta0, const double* th_pts,
     L.atol = atol;
     L.start_kind = kStartShared;
     L.zshared = nullptr;
-    L.zshared_state = h->zfid_state;     // picked on the device: no host sync between the two launches
+    L.zshared_state = zst;               // picked on the device: no host sync between the two launches
+    outputs_to(L);
     L.zsharedA = h->zfidA;
     L.zsharedB = h->zfidB;
     if (hshard) { L.xi = h->xi_h; L.nu = h->nu_h; }
@@ -631,12 +661,14 @@ static int fd_launch(muse_handle* h, const double* theta0, const double* th_pts,
     L.discard_z = 1;     // `ẑ, = ẑ_at_θ(...)` is only an intermediate of the score (src/muse.jl:431-432)
     // algorithmic bytes: read ξ, ν per virtual sim; the shared start ẑ_fid is read once (L2)
     h->pass_kind = MUSE_PASS_FD;
-    return launch_solver(h, L, items * 2 * d8 + d8);
+    rc = launch_solver(h, L, items * 2 * d8 + d8);
+    h->ctr_override = ctr0;
+    return rc;
 }
 
 int muse_fd_enqueue(muse_handle* h, const double* theta0, const double* th_pts, int nsims_H, double atol,
-                    const DynConsts* dyn_fid, const DynConsts* dyn_fd) {
-    return fd_launch(h, theta0, th_pts, nsims_H, atol, dyn_fid, dyn_fd);
+                    const DynConsts* dyn_fid, const DynConsts* dyn_fd, const OutBlock* ob) {
+    return fd_launch(h, theta0, th_pts, nsims_H, atol, dyn_fid, dyn_fd, ob);
 }
 
 static int fd_check(muse_handle* h, int nsims_H) {

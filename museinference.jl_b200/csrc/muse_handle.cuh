@@ -14,6 +14,7 @@ struct OutBlock {
     unsigned char *d = nullptr, *hst = nullptr;
     size_t bytes = 0;
     int cap = 0;
+    bool owned = false;         // false: carved out of a larger allocation (the device-resident loop's arena)
     double *g_d = nullptr, *gnorm_d = nullptr, *f_d = nullptr;
     int *iters_d = nullptr, *fg_d = nullptr, *status_d = nullptr;
     double *g_h = nullptr, *gnorm_h = nullptr;
@@ -29,9 +30,14 @@ struct OuterRow {                                        // history row of one i
     double h_inv_like[MUSE_MAX_NTHETA], h_prior[MUSE_MAX_NTHETA], h_inv_post[MUSE_MAX_NTHETA];
 };
 struct OuterState {
+    // header: uploaded from pinned staging at the start of a solve (one copy initialises everything below)
     int n_iter, done, error, pad;
     double theta[MUSE_MAX_NTHETA];                       // θ after the last update (= θ of the next pass)
     double step[MUSE_MAX_NTHETA];                        // 0.1 ./ std(gs) of the covariance stage
+    int ctr[16];                                         // per launch chain of a chunk: [2k] hand-back count, [2k+1] streaming work
+                                                         // counter (k = 0..4); [12] state of the fiducial ẑ — zero at chunk start
+    muse::DynConsts dyn_first;                           // constants of pass 1 at θ₀ (host libm, like the other drivers)
+    // history
     OuterRow row[kOuterMaxIter];
 };
 
@@ -76,13 +82,21 @@ struct muse_handle {
     muse_corr_ctx* corr = nullptr;
 
     // device-resident outer loop (muse_outer.cu)
+    // one device allocation with a pinned host mirror of the same layout — [state | slot 0 | slot 1 | FD block | slot 2] — so
+    // that the results of a typical solve come back in ONE copy (every DMA node costs ≈ 8 µs of latency)
+    unsigned char *outer_arena_d = nullptr, *outer_arena_h = nullptr;
+    size_t outer_arena_bytes = 0, outer_arena_head = 0;  // head: bytes up to the end of the FD block
+    int outer_units_cap = 0, outer_fd_cap = 0;
+    OutBlock outer_fd;                                   // outputs of get_H!'s launches
+    int* ctr_override = nullptr;                         // launch_solver: this chain's counter pair instead of redo_count + memset
+    int* zfid_override = nullptr;                        // fd_launch: the fiducial ẑ's state cell instead of zfid_state + memset
     OutBlock outer_slot[kOuterSlots];                    // per-pass outputs of the iterations of one chunk
     double* outer_gall[kOuterSlots] = {nullptr, nullptr, nullptr};   // multi-GPU: gathered score rows per pass (device)
     double* outer_gall_h = nullptr;                      // pinned mirror of the three gathered blocks
     size_t outer_gall_doubles = 0;
     OuterState *outer_st_d = nullptr, *outer_st_h = nullptr;
     muse::DynConsts* outer_dyn = nullptr;                // [0], [1]: passes (alternating); [2]: fiducial; [3]: FD sims
-    muse::DynConsts* outer_dyn_stage = nullptr;          // pinned: constants of pass 1 at θ₀ (uploaded by a node of the graph)
+    OuterState* outer_st_stage = nullptr;                // pinned: the state header a solve starts from (uploaded by the first node)
     // CUDA graph of the first chunk of the device-resident loop — the whole of a typical solve: one cudaGraphLaunch replaces
     // ≈ 25 stream operations (launches, memsets, copies, event records) whose CPU-side issue cost, not the GPU, bounded the
     // small configurations.  Captured from the very enqueue code the eager path runs, on the second solve with a given key.
@@ -118,8 +132,11 @@ void muse_outblock_free(OutBlock& ob);
 int  muse_pass_enqueue(muse_handle* h, const double* theta_sim, const double* theta_eval, double atol, int include_data,
                        int warm_start, int first_sim, int count, const OutBlock* ob, const muse::DynConsts* dyn);
 extern "C" int  muse_fd_enqueue(muse_handle* h, const double* theta0, const double* th_pts, int nsims_H, double atol,
-                                const muse::DynConsts* dyn_fid, const muse::DynConsts* dyn_fd);
-extern "C" void muse_fd_combine_host(muse_handle* h, const double* step, int nsims_H, double* Hs_out, int32_t* status_out);
+                                const muse::DynConsts* dyn_fid, const muse::DynConsts* dyn_fd, const OutBlock* ob);
+extern "C" void muse_fd_combine_host(muse_handle* h, const double* g_h, const int* status_h, const double* step, int nsims_H,
+                                     double* Hs_out, int32_t* status_out);
+size_t muse_outblock_bytes(const muse_handle* h, int items);
+void muse_outblock_carve(const muse_handle* h, OutBlock& ob, unsigned char* dev, unsigned char* host, int items);
 void muse_outer_release(muse_handle* h);
 extern "C" int  muse_comm_allgather_dev_enqueue(muse_handle* h, const double* src_dev, int ncol, const int32_t* counts, size_t* need_out);
 

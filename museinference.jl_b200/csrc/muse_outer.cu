@@ -22,6 +22,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstddef>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -244,18 +245,40 @@ void outer_graph_release(muse_handle* h) {
     h->outer_key.clear();
 }
 
-int outer_ensure(muse_handle* h, int units, size_t gall_doubles) {
-    for (int s = 0; s < kOuterSlots; ++s) {
-        const int rc = muse_outblock_ensure(h, h->outer_slot[s], units);
-        if (rc != 0) return rc;
+size_t up256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+// the arena [state | slot 0 | slot 1 | FD block | slot 2] (device + pinned mirror) and the exchange mirrors
+int outer_ensure(muse_handle* h, int units, int fd_items, size_t gall_doubles) {
+    if (units > h->outer_units_cap || fd_items > h->outer_fd_cap || !h->outer_arena_d) {
+        outer_graph_release(h);
+        cudaFree(h->outer_arena_d); cudaFreeHost(h->outer_arena_h);
+        h->outer_arena_d = h->outer_arena_h = nullptr;
+        const int ucap = std::max(units, h->outer_units_cap), fcap = std::max(std::max(fd_items, 1), h->outer_fd_cap);
+        const size_t sz_state = up256(sizeof(OuterState)), sz_slot = up256(muse_outblock_bytes(h, ucap)), sz_fd = up256(muse_outblock_bytes(h, fcap));
+        const size_t total = sz_state + 3 * sz_slot + sz_fd;
+        OUTER_TRY(h, cudaMalloc(&h->outer_arena_d, total));
+        OUTER_TRY(h, cudaMallocHost(&h->outer_arena_h, total));
+        OUTER_TRY(h, cudaMemsetAsync(h->outer_arena_d, 0, total, h->stream));
+        std::memset(h->outer_arena_h, 0, total);
+        size_t off = 0;
+        h->outer_st_d = reinterpret_cast<OuterState*>(h->outer_arena_d);
+        h->outer_st_h = reinterpret_cast<OuterState*>(h->outer_arena_h);
+        off += sz_state;
+        muse_outblock_carve(h, h->outer_slot[0], h->outer_arena_d + off, h->outer_arena_h + off, ucap); off += sz_slot;
+        muse_outblock_carve(h, h->outer_slot[1], h->outer_arena_d + off, h->outer_arena_h + off, ucap); off += sz_slot;
+        muse_outblock_carve(h, h->outer_fd, h->outer_arena_d + off, h->outer_arena_h + off, fcap); off += sz_fd;
+        h->outer_arena_head = off;
+        muse_outblock_carve(h, h->outer_slot[2], h->outer_arena_d + off, h->outer_arena_h + off, ucap); off += sz_slot;
+        h->outer_arena_bytes = off;
+        h->outer_units_cap = ucap;
+        h->outer_fd_cap = fcap;
     }
-    if (!h->outer_st_d) {
-        OUTER_TRY(h, cudaMalloc(&h->outer_st_d, sizeof(OuterState)));
-        OUTER_TRY(h, cudaMallocHost(&h->outer_st_h, sizeof(OuterState)));
+    if (!h->outer_dyn) {
         OUTER_TRY(h, cudaMalloc(&h->outer_dyn, 4 * sizeof(DynConsts)));
-        OUTER_TRY(h, cudaMallocHost(&h->outer_dyn_stage, sizeof(DynConsts)));
+        OUTER_TRY(h, cudaMallocHost(&h->outer_st_stage, sizeof(OuterState)));
     }
     if (gall_doubles > h->outer_gall_doubles) {
+        outer_graph_release(h);
         for (int s = 0; s < kOuterSlots; ++s) { cudaFree(h->outer_gall[s]); h->outer_gall[s] = nullptr; }
         cudaFreeHost(h->outer_gall_h);
         h->outer_gall_h = nullptr;
@@ -271,14 +294,19 @@ int outer_ensure(muse_handle* h, int units, size_t gall_doubles) {
 
 void muse_outer_release(muse_handle* h) {
     outer_graph_release(h);
-    cudaFreeHost(h->outer_dyn_stage);
-    h->outer_dyn_stage = nullptr;
-    for (int s = 0; s < kOuterSlots; ++s) { muse_outblock_free(h->outer_slot[s]); cudaFree(h->outer_gall[s]); h->outer_gall[s] = nullptr; }
-    cudaFreeHost(h->outer_gall_h);
-    cudaFree(h->outer_st_d);
-    cudaFreeHost(h->outer_st_h);
+    cudaFree(h->outer_arena_d);
+    cudaFreeHost(h->outer_arena_h);
+    cudaFreeHost(h->outer_st_stage);
     cudaFree(h->outer_dyn);
-    h->outer_gall_h = nullptr; h->outer_st_d = h->outer_st_h = nullptr; h->outer_dyn = nullptr; h->outer_gall_doubles = 0;
+    for (int s = 0; s < kOuterSlots; ++s) { cudaFree(h->outer_gall[s]); h->outer_gall[s] = nullptr; h->outer_slot[s] = OutBlock{}; }
+    cudaFreeHost(h->outer_gall_h);
+    h->outer_fd = OutBlock{};
+    h->outer_arena_d = h->outer_arena_h = nullptr;
+    h->outer_st_d = h->outer_st_h = h->outer_st_stage = nullptr;
+    h->outer_dyn = nullptr;
+    h->outer_gall_h = nullptr;
+    h->outer_gall_doubles = 0;
+    h->outer_units_cap = h->outer_fd_cap = 0;
 }
 
 extern "C" int muse_b200_muse_solve(muse_handle* h, const double* theta0, int32_t nsims_total, const int32_t* counts,
@@ -317,9 +345,9 @@ extern "C" int muse_b200_muse_solve(muse_handle* h, const double* theta0, int32_
         P.nranks = 1; P.counts[0] = nloc; P.need = (long long)nloc * nt;
     }
     const size_t gall_doubles = multi ? (size_t)P.need * P.nranks : 0;
-    int rc = outer_ensure(h, units, gall_doubles);
-    if (rc != MUSE_OK) return rc;
     const int nh_mine = get_covariance ? (multi ? counts_h[h->comm_rank] : nsims_h_total) : 0;
+    int rc = outer_ensure(h, units, std::max(0, nh_mine) * nt * 2, gall_doubles);
+    if (rc != MUSE_OK) return rc;
     if (get_covariance) {
         const bool hshard = h->cfg.nsims_h > 0;
         if (nh_mine < 0 || nh_mine > (hshard ? h->cfg.nsims_h : h->cfg.nsims)) { h->err = "nsims_H outside the handle's H shard"; return MUSE_EINVAL; }
@@ -337,16 +365,20 @@ extern "C" int muse_b200_muse_solve(muse_handle* h, const double* theta0, int32_
     // The same code runs eagerly or under stream capture.
     auto enqueue_chunk = [&](int first, int last) -> int {
         int rc2;
-        if (first == 1) {
-            OUTER_TRY(h, cudaMemcpyAsync(sd, sh_, offsetof(OuterState, row), cudaMemcpyHostToDevice, h->stream));
-            OUTER_TRY(h, cudaMemcpyAsync(&dyn[1], h->outer_dyn_stage, sizeof(DynConsts), cudaMemcpyHostToDevice, h->stream));
-        }
+        // ONE upload initialises the state, zeroes the chains' counters and carries the constants of pass 1; later chunks
+        // only need fresh counters
+        if (first == 1) OUTER_TRY(h, cudaMemcpyAsync(sd, h->outer_st_stage, offsetof(OuterState, row), cudaMemcpyHostToDevice, h->stream));
+        else OUTER_TRY(h, cudaMemsetAsync(sd->ctr, 0, sizeof(sd->ctr), h->stream));
+        int chain = 0;
         for (int i = first; i <= last; ++i) {
             const int slot = (i - 1) % kOuterSlots;
             const OutBlock& ob = h->outer_slot[slot];
             // pass i: data + local sims, start zeros / user z₀ on the first, previous ẑ afterwards (:169-176)
             h->rec_tag = i;
-            rc2 = muse_pass_enqueue(h, nullptr, nullptr, atol, 1, i == 1 ? first_start : MUSE_START_PREV, 0, nloc, &ob, &dyn[i & 1]);
+            h->ctr_override = &sd->ctr[2 * chain++];
+            rc2 = muse_pass_enqueue(h, nullptr, nullptr, atol, 1, i == 1 ? first_start : MUSE_START_PREV, 0, nloc, &ob,
+                                    i == 1 ? &sd->dyn_first : &dyn[i & 1]);
+            h->ctr_override = nullptr;
             h->rec_tag = 0;
             if (rc2 != MUSE_OK) return rc2;
             P.iter = i;
@@ -377,27 +409,26 @@ extern "C" int muse_b200_muse_solve(muse_handle* h, const double* theta0, int32_
             (h->capturing ? h->cap_launches : h->acc.launches) += 1;
             if (nh_mine > 0) {
                 h->rec_tag = -1;
-                rc2 = muse_fd_enqueue(h, nullptr, nullptr, nh_mine, atol, &dyn[2], &dyn[3]);
+                h->ctr_override = &sd->ctr[2 * chain];          // fiducial: this pair, virtual sims: the next one
+                h->zfid_override = &sd->ctr[12];
+                rc2 = muse_fd_enqueue(h, nullptr, nullptr, nh_mine, atol, &dyn[2], &dyn[3], &h->outer_fd);
+                h->ctr_override = nullptr;
+                h->zfid_override = nullptr;
                 h->rec_tag = 0;
                 if (rc2 != MUSE_OK) return rc2;
             }
         }
-        // results of the chunk — the state header with the chunk's history rows, the per-pass outputs, the gathered scores,
-        // the scores and statuses of the FD sims
-        OUTER_TRY(h, cudaMemcpyAsync(sh_, sd, offsetof(OuterState, row), cudaMemcpyDeviceToHost, h->stream));
-        OUTER_TRY(h, cudaMemcpyAsync(&sh_->row[first - 1], &sd->row[first - 1], (size_t)(last - first + 1) * sizeof(OuterRow),
-                                     cudaMemcpyDeviceToHost, h->stream));
-        for (int i = first; i <= last; ++i) {
-            const OutBlock& ob = h->outer_slot[(i - 1) % kOuterSlots];
-            OUTER_TRY(h, cudaMemcpyAsync(ob.hst, ob.d, ob.bytes, cudaMemcpyDeviceToHost, h->stream));
-            if (multi)
+        // results of the chunk in ONE copy: the arena's head [state | slot 0 | slot 1 | FD block] holds everything a first chunk
+        // produces; later chunks (which also use slot 2) copy the whole arena
+        const bool head_only = first == 1 && last <= 2;
+        const size_t nbytes = head_only ? (get_covariance && nh_mine > 0 ? h->outer_arena_head
+                                                                          : (size_t)(h->outer_slot[1].d - h->outer_arena_d) + h->outer_slot[1].bytes)
+                                        : h->outer_arena_bytes;
+        OUTER_TRY(h, cudaMemcpyAsync(h->outer_arena_h, h->outer_arena_d, nbytes, cudaMemcpyDeviceToHost, h->stream));
+        if (multi)
+            for (int i = first; i <= last; ++i)
                 OUTER_TRY(h, cudaMemcpyAsync(h->outer_gall_h + (size_t)((i - 1) % kOuterSlots) * gall_doubles, h->outer_gall[(i - 1) % kOuterSlots],
                                              gall_doubles * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-        }
-        if (get_covariance && nh_mine > 0) {
-            OUTER_TRY(h, cudaMemcpyAsync(h->g_h, h->g_d, (size_t)items_fd * nt * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-            OUTER_TRY(h, cudaMemcpyAsync(h->status_h, h->status_d, (size_t)items_fd * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-        }
         return MUSE_OK;
     };
 
@@ -408,8 +439,7 @@ extern "C" int muse_b200_muse_solve(muse_handle* h, const double* theta0, int32_
         const int ints[] = {maxsteps, first_start, get_covariance, nh_mine, nsims_total, nloc, h->prof ? 1 : 0, P.have_prior, h->out_cap, h->h_cap};
         const double dbl[] = {theta_rtol, atol, alpha};
         put(ints, sizeof(ints)); put(dbl, sizeof(dbl)); put(P.prior_mean, sizeof(P.prior_mean)); put(P.prior_sigma, sizeof(P.prior_sigma));
-        const void* ptrs[] = {h->stream, h->out_d, h->out_h, h->zHA, sd, sh_, dyn, h->outer_slot[0].d, h->outer_slot[1].d, h->outer_slot[2].d,
-                              h->gpart, h->dbg, h->xi, h->xi_h};
+        const void* ptrs[] = {h->stream, h->out_d, h->zHA, h->outer_arena_d, h->outer_arena_h, h->outer_st_stage, dyn, h->gpart, h->dbg, h->xi, h->xi_h};
         put(ptrs, sizeof(ptrs));
     }
     static const bool graphs_on = [] { const char* e = std::getenv("MUSE_OUTER_GRAPH"); return !e || std::atoi(e) != 0; }();
@@ -426,10 +456,10 @@ extern "C" int muse_b200_muse_solve(muse_handle* h, const double* theta0, int32_
         const int last = std::min(maxsteps, it_done + (it_done == 0 ? 2 : kOuterSlots));
         bool via_graph = false;
         if (first == 1) {
-            std::memset(sh_, 0, offsetof(OuterState, row));
-            for (int c = 0; c < nt; ++c) sh_->theta[c] = theta0[c];
-            std::memset(h->outer_dyn_stage, 0, sizeof(DynConsts));
-            if (muse_theta_consts(h->cfg, theta0, theta0, &h->outer_dyn_stage->smp[0], &h->outer_dyn_stage->ev) != 0) { h->err = "family"; return MUSE_EUNSUPPORTED; }
+            OuterState* stg = h->outer_st_stage;
+            std::memset(stg, 0, offsetof(OuterState, row));
+            for (int c = 0; c < nt; ++c) stg->theta[c] = theta0[c];
+            if (muse_theta_consts(h->cfg, theta0, theta0, &stg->dyn_first.smp[0], &stg->dyn_first.ev) != 0) { h->err = "family"; return MUSE_EUNSUPPORTED; }
             if (use_graph && h->outer_exec && key == h->outer_key) {
                 via_graph = true;
             } else if (use_graph && key == h->outer_warm_key) {
@@ -443,13 +473,20 @@ extern "C" int muse_b200_muse_solve(muse_handle* h, const double* theta0, int32_
                 const cudaError_t e2 = e == cudaSuccess ? cudaStreamEndCapture(h->stream, &graph) : e;
                 h->capturing = false;
                 cudaGraphExec_t exec = nullptr;
-                if (rc == MUSE_OK && e2 == cudaSuccess && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
+                cudaError_t e3 = cudaSuccess;
+                if (rc == MUSE_OK && e2 == cudaSuccess && (e3 = cudaGraphInstantiate(&exec, graph, 0)) == cudaSuccess) {
                     h->outer_exec = exec;
                     h->outer_key = key;
                     via_graph = true;
                 } else {
                     cudaGetLastError();
                     outer_graph_release(h);             // fall back to the eager path below
+                }
+                if (std::getenv("MUSE_DEBUG_TIMING")) {
+                    size_t nodes = 0;
+                    if (graph) cudaGraphGetNodes(graph, nullptr, &nodes);
+                    std::fprintf(stderr, "[muse_solve] graph capture: begin=%s enqueue rc=%d end=%s instantiate=%s nodes=%zu -> %s\n",
+                                 cudaGetErrorName(e), rc, cudaGetErrorName(e2), cudaGetErrorName(e3), nodes, via_graph ? "graph" : "eager");
                 }
                 if (graph) cudaGraphDestroy(graph);
             }
@@ -539,7 +576,7 @@ extern "C" int muse_b200_muse_solve(muse_handle* h, const double* theta0, int32_
         std::vector<int32_t> status((size_t)std::max(1, nh_mine) * nt * 2, 0);
         for (int c = 0; c < nt; ++c) cov->step[c] = sh_->step[c];
         if (nh_mine > 0) {
-            muse_fd_combine_host(h, sh_->step, nh_mine, Hs_local.data(), status.data());
+            muse_fd_combine_host(h, h->outer_fd.g_h, h->outer_fd.status_h, sh_->step, nh_mine, Hs_local.data(), status.data());
             for (size_t i = 0; i < (size_t)nh_mine * nt * 2; ++i)
                 if (status[i] == MUSE_STATUS_NONFINITE) { h->err = "get_H!: MAP solution failed with a non-finite objective"; return MUSE_ESTATE; }
         }
