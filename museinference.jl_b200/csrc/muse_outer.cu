@@ -16,8 +16,8 @@
 //
 // Differences from the host loop: the reductions are parallel trees (deterministic, but not the host's summation order) and
 // e^{·} comes from the device's libm, so θ agrees with muse_driver.cu to round-off (≈ 1e-16 relative), not bit for bit.
-// Every rank of a multi-GPU job runs the identical kernel on the identical gathered scores, so θ stays bit-identical ACROSS
-// ranks, as before.  history[i].t is the chunk's wall time divided by its iterations (no per-iteration host clock exists).
+// The trees are ordered by the GLOBAL sim index, and every rank of a multi-GPU job runs the identical kernel on the
+// identical gathered scores: θ stays bit-identical across ranks and for any sharding, as before.  history[i].t is the chunk's wall time divided by its iterations (no per-iteration host clock exists).
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -81,35 +81,38 @@ __device__ void consts_of(int family, int d, const double* th_sim, const double*
     }
 }
 
-// Σ_k f_c(k) for every θ-component c over the sims of all ranks, in a fixed order: thread t takes sims t, t + T, … of every
-// rank slot in turn (loads issued four at a time — a lone CTA is latency-bound, not bandwidth-bound), then a shuffle tree
-// per warp and a second one over the warp results.  Deterministic for a given (nranks, counts).  f(o, c) reads element c of
-// the score row at offset o.  Results land in out[0..nt).
+// Σ_k f_c(k) for every θ-component c over all sims, in an order fixed by the GLOBAL sim index: thread t takes sims t, t + T,
+// t + 2T, … (loads issued four at a time — a lone CTA is latency-bound, not bandwidth-bound), then a shuffle tree per warp
+// and a second one over the warp results.  The order does not depend on how the sims are sharded over ranks, so θ — like
+// every per-sim result — is bit-identical for any number of GPUs.  f(o, c) reads element c of the score row at offset o of
+// the gathered layout (rank q's rows start at q·need).  Results land in out[0..nt).
 template <class F>
-__device__ void block_sums(const int* counts, int nranks, long long need, int nt, F&& f, double (*sh)[32], double* out) {
+__device__ void block_sums(const int* counts, int nranks, long long need, int nt, int n_total, F&& f, double (*sh)[32], double* out) {
     double acc[kMaxTheta];
 #pragma unroll
     for (int c = 0; c < kMaxTheta; ++c) acc[c] = 0.0;
     constexpr int T = kStepThreads;
-    for (int q = 0; q < nranks; ++q) {
-        const int cnt = counts[q];
-        const size_t base = (size_t)q * need;
-        int r = threadIdx.x;
-        for (; r + 3 * T < cnt; r += 4 * T) {
+    auto row_off = [&](int k) -> size_t {                 // global sim k → offset of its row
+        int q = 0, base = 0;
+        while (q + 1 < nranks && k >= base + counts[q]) { base += counts[q]; ++q; }
+        return (size_t)q * (size_t)need + (size_t)(k - base) * nt;
+    };
+    int k = threadIdx.x;
+    for (; k + 3 * T < n_total; k += 4 * T) {
+        const size_t o0 = row_off(k), o1 = row_off(k + T), o2 = row_off(k + 2 * T), o3 = row_off(k + 3 * T);
 #pragma unroll
-            for (int c = 0; c < kMaxTheta; ++c) {
-                if (c < nt) {
-                    const double v0 = f(base + (size_t)r * nt, c), v1 = f(base + (size_t)(r + T) * nt, c);
-                    const double v2 = f(base + (size_t)(r + 2 * T) * nt, c), v3 = f(base + (size_t)(r + 3 * T) * nt, c);
-                    acc[c] += v0; acc[c] += v1; acc[c] += v2; acc[c] += v3;
-                }
+        for (int c = 0; c < kMaxTheta; ++c) {
+            if (c < nt) {
+                const double v0 = f(o0, c), v1 = f(o1, c), v2 = f(o2, c), v3 = f(o3, c);
+                acc[c] += v0; acc[c] += v1; acc[c] += v2; acc[c] += v3;
             }
         }
-        for (; r < cnt; r += T) {
+    }
+    for (; k < n_total; k += T) {
+        const size_t o = row_off(k);
 #pragma unroll
-            for (int c = 0; c < kMaxTheta; ++c)
-                if (c < nt) acc[c] += f(base + (size_t)r * nt, c);
-        }
+        for (int c = 0; c < kMaxTheta; ++c)
+            if (c < nt) acc[c] += f(o, c);
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -134,9 +137,9 @@ __device__ void block_sums(const int* counts, int nranks, long long need, int nt
 // mean and corrected variance of every component (two passes, like Statistics.mean / var)
 __device__ void block_mean_var(const double* g, const int* counts, int nranks, long long need, int nt, int n_total,
                                double (*sh)[32], double* mean, double* var) {
-    block_sums(counts, nranks, need, nt, [&](size_t o, int c) { return g[o + c]; }, sh, mean);
+    block_sums(counts, nranks, need, nt, n_total, [&](size_t o, int c) { return g[o + c]; }, sh, mean);
     for (int c = 0; c < nt; ++c) mean[c] /= n_total;
-    block_sums(counts, nranks, need, nt, [&](size_t o, int c) { const double dlt = g[o + c] - mean[c]; return dlt * dlt; }, sh, var);
+    block_sums(counts, nranks, need, nt, n_total, [&](size_t o, int c) { const double dlt = g[o + c] - mean[c]; return dlt * dlt; }, sh, var);
     for (int c = 0; c < nt; ++c) var[c] /= (n_total - 1);
 }
 

@@ -30,7 +30,7 @@ from ._capi import MuseBackendError
 # Which in-library outer loop the common configuration takes when the caller does not say (fused_driver=True):
 # "device" — θ update on the device, one host synchronisation per solve (csrc/muse_outer.cu; isotropic families);
 # "host"   — host arithmetic between two passes (csrc/muse_driver.cu).  fused_driver=False: the line-by-line loop below.
-DEFAULT_FUSED_DRIVER = os.environ.get("MUSE_FUSED_DRIVER", "host")
+DEFAULT_FUSED_DRIVER = os.environ.get("MUSE_FUSED_DRIVER", "device")
 
 _KW_ALIASES = {
     "θ_rtol": "theta_rtol", "∇z_logLike_atol": "gradz_logLike_atol", "α": "alpha", "z₀": "z0",

@@ -218,12 +218,12 @@ def test_in_library_outer_loop_matches_line_by_line_driver(name, d, nsims, prior
     rng = m.BaseDraws(draws.xi, draws.nu, draws.xi_master, draws.nu_master)
     pr = (lambda: m.NormalPrior([0.0, 0.1][:fam.ntheta], [3.0, 2.0][:fam.ntheta])) if prior else (lambda: None)
     res = {}
-    for fused in (True, False):
+    for fused in ("host", False):
         prob = m.SimpleMuseProblem(xd, name, pr())
         res[fused] = m.muse(prob, theta_start(name), rng=rng, nsims=nsims, get_covariance=True, fused_driver=fused,
                             theta_rtol=1e-3, maxsteps=6)
         prob.close()
-    a, b = res[True], res[False]
+    a, b = res["host"], res[False]
     assert len(a.history) == len(b.history) >= 3
     np.testing.assert_allclose(a.theta, b.theta, rtol=1e-12)
     np.testing.assert_allclose(a.J, b.J, rtol=1e-12)
