@@ -361,7 +361,6 @@ extern "C" int muse_b200_muse_solve(muse_handle* h, const double* theta0, int32_
     OuterState* sh_ = h->outer_st_h;
     P.st = sd;
     DynConsts* dyn = h->outer_dyn;
-    const int items_fd = nh_mine * nt * 2;
 
     // Everything one chunk puts on the stream: (first chunk) the initial state and the constants of pass 1 from pinned
     // staging, the passes with their exchange and θ-step, the conditional covariance stage, the copies of the results.
