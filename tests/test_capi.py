@@ -98,3 +98,49 @@ def test_bench_reference_arm_contract():
     assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and d["vs_baseline"] is None
+
+
+def test_struct_layouts_and_constants_match_a_c_compilation_of_the_header(tmp_path):
+    """Compile include/muse_b200.h with gcc (as C, so the header must be plain C) and compare sizeof / offsetof of every
+    struct that crosses the boundary, and the numeric constants, with the ctypes binding."""
+    import subprocess
+    import museinference_jl_b200 as m
+    from importlib import import_module
+    capi = import_module(m.__name__ + "._capi")
+    structs = {"muse_cfg": capi.muse_cfg, "muse_profile": capi.muse_profile, "muse_pass_profile": capi.muse_pass_profile,
+               "muse_iterate_out": capi.muse_iterate_out, "muse_cov_out": capi.muse_cov_out}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "muse_b200.h"', 'int main(void) {']
+    for name, st in structs.items():
+        lines.append(f'  printf("sizeof {name} %zu\\n", sizeof({name}));')
+        for fname, _ in st._fields_:
+            lines.append(f'  printf("offsetof {name}.{fname} %zu\\n", offsetof({name}, {fname}));')
+    consts = ["MUSE_B200_ABI_VERSION", "MUSE_FAMILY_FUNNEL", "MUSE_FAMILY_HIERGAUSS", "MUSE_FAMILY_CORRGAUSS", "MUSE_START_ZEROS",
+              "MUSE_START_PREV", "MUSE_START_TRUTH", "MUSE_START_USER", "MUSE_STATUS_G_CONVERGED", "MUSE_STATUS_XF_CONVERGED",
+              "MUSE_STATUS_MAXITER", "MUSE_STATUS_LS_FAILED", "MUSE_STATUS_NONFINITE", "MUSE_PASS_KINDS", "MUSE_EUNSUPPORTED",
+              "MUSE_ENODEVICE", "MUSE_ESTATE"]
+    for c in consts:
+        lines.append(f'  printf("const {c} %d\\n", (int)({c}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "abi.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "abi"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout
+    got = {}
+    for line in out.splitlines():
+        kind, key, val = line.split()
+        got[(kind, key)] = int(val)
+    for name, st in structs.items():
+        assert got[("sizeof", name)] == C.sizeof(st), name
+        for fname, _ in st._fields_:
+            assert got[("offsetof", f"{name}.{fname}")] == getattr(st, fname).offset, f"{name}.{fname}"
+    assert got[("const", "MUSE_B200_ABI_VERSION")] == capi.ABI_VERSION
+    assert (got[("const", "MUSE_FAMILY_FUNNEL")], got[("const", "MUSE_FAMILY_HIERGAUSS")], got[("const", "MUSE_FAMILY_CORRGAUSS")]) == \
+        (capi.FAMILY_FUNNEL, capi.FAMILY_HIERGAUSS, capi.FAMILY_CORRGAUSS)
+    assert [got[("const", f"MUSE_START_{k}")] for k in ("ZEROS", "PREV", "TRUTH", "USER")] == \
+        [capi.START_ZEROS, capi.START_PREV, capi.START_TRUTH, capi.START_USER]
+    assert [got[("const", f"MUSE_STATUS_{k}")] for k in ("G_CONVERGED", "XF_CONVERGED", "MAXITER", "LS_FAILED", "NONFINITE")] == \
+        [capi.STATUS_G_CONVERGED, capi.STATUS_XF_CONVERGED, capi.STATUS_MAXITER, capi.STATUS_LS_FAILED, capi.STATUS_NONFINITE]
+    assert got[("const", "MUSE_PASS_KINDS")] == len(capi.PASS_KINDS)
+    assert {v: k for k, v in capi.E_NAMES.items()}["EUNSUPPORTED"] == got[("const", "MUSE_EUNSUPPORTED")]
+    assert {v: k for k, v in capi.E_NAMES.items()}["ENODEVICE"] == got[("const", "MUSE_ENODEVICE")]
