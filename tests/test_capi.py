@@ -144,3 +144,21 @@ def test_struct_layouts_and_constants_match_a_c_compilation_of_the_header(tmp_pa
     assert got[("const", "MUSE_PASS_KINDS")] == len(capi.PASS_KINDS)
     assert {v: k for k, v in capi.E_NAMES.items()}["EUNSUPPORTED"] == got[("const", "MUSE_EUNSUPPORTED")]
     assert {v: k for k, v in capi.E_NAMES.items()}["ENODEVICE"] == got[("const", "MUSE_ENODEVICE")]
+
+
+def test_plain_c_example_links_against_the_library_and_fails_loudly_without_a_gpu(lib_built, tmp_path):
+    """examples/solve_funnel.c: the ABI used from C99 with nothing but the header and the .so.  Here (no GPU) it must
+    report ENODEVICE — exit status 3 — instead of computing anything on the CPU; on a B200 it prints OK."""
+    import subprocess
+    import torch
+    import museinference_jl_b200 as m
+    libdir = os.path.dirname(m.library_path())
+    exe = tmp_path / "solve_funnel"
+    subprocess.run(["gcc", "-std=c99", "-O2", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "solve_funnel.c"), "-o", str(exe), "-L", libdir, "-lmuse_b200", "-lm",
+                    f"-Wl,-rpath,{libdir}"], check=True)
+    out = subprocess.run([str(exe), "1024", "64"], capture_output=True, text=True, timeout=120)
+    if torch.cuda.is_available():
+        assert out.returncode == 0 and "OK" in out.stdout, out.stdout + out.stderr
+    else:
+        assert out.returncode == 3 and "no CPU fallback" in out.stderr, out.stdout + out.stderr
