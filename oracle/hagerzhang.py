@@ -176,14 +176,23 @@ class HagerZhang:
             f"Linesearch failed to converge, reached maximum iterations {linesearchmax}.", alphas[ia])
 
 
+def _div(x: float, y: float) -> float:
+    """IEEE-754 division (Julia and CUDA semantics): x/0 is ±Inf or NaN, never an exception."""
+    if y == 0.0:
+        if x == 0.0 or x != x:
+            return math.nan
+        return math.copysign(math.inf, x) * math.copysign(1.0, y)
+    return x / y
+
+
 def _satisfies_wolfe(c, phi_c, dphi_c, phi_0, dphi_0, phi_lim, delta, sigma) -> bool:
-    wolfe1 = (delta * dphi_0 >= (phi_c - phi_0) / c) and (dphi_c >= sigma * dphi_0)
+    wolfe1 = (delta * dphi_0 >= _div(phi_c - phi_0, c)) and (dphi_c >= sigma * dphi_0)
     wolfe2 = ((2 * delta - 1) * dphi_0 >= dphi_c >= sigma * dphi_0) and (phi_c <= phi_lim)
     return wolfe1 or wolfe2
 
 
 def _secant(a, b, dphi_a, dphi_b):
-    return (a * dphi_b - b * dphi_a) / (dphi_b - dphi_a)
+    return _div(a * dphi_b - b * dphi_a, dphi_b - dphi_a)
 
 
 def _secant2(phidphi, alphas, values, slopes, ia, ib, phi_lim, delta, sigma):
