@@ -444,8 +444,11 @@ extern "C" int muse_b200_muse_solve(muse_handle* h, const double* theta0, int32_
         const void* ptrs[] = {h->stream, h->out_d, h->zHA, h->outer_arena_d, h->outer_arena_h, h->outer_st_stage, dyn, h->gpart, h->dbg, h->xi, h->xi_h};
         put(ptrs, sizeof(ptrs));
     }
+    // MUSE_OUTER_GRAPH=0: eager enqueue only.  MUSE_OUTER_GRAPH_MULTI=1: also capture the chunk when a communicator is bound
+    // (NCCL's all-gather inside the capture) — off by default: validated eagerly at N = 2, the captured form is unmeasured.
     static const bool graphs_on = [] { const char* e = std::getenv("MUSE_OUTER_GRAPH"); return !e || std::atoi(e) != 0; }();
-    const bool use_graph = graphs_on && !multi;
+    static const bool graphs_multi = [] { const char* e = std::getenv("MUSE_OUTER_GRAPH_MULTI"); return e && std::atoi(e) != 0; }();
+    const bool use_graph = graphs_on && (!multi || graphs_multi);
 
     out->n_iter = 0;
     int it_done = 0;                        // iterations whose history has been copied out
