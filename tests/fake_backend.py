@@ -104,3 +104,65 @@ class FakeBackend:
 
     def get_maps(self, first_unit, count):
         return np.array(self.z[first_unit:first_unit + count])
+
+
+class FusedFakeBackend(FakeBackend):
+    """FakeBackend plus the in-library outer loops (``muse_iterate`` / ``muse_covariance`` / ``muse_solve`` of
+    include/muse_b200.h) restated on the host from the same per-sim pieces, single rank: lets the glue that turns the
+    library's history arrays back into ``MuseResult.history`` (museinference.jl_b200/muse.py, fused path) run on the CPU."""
+
+    def muse_iterate(self, theta0, nsims_total, counts, maxsteps, theta_rtol, atol, alpha, first_start, prior_mean=None, prior_sigma=None):
+        assert counts is None and nsims_total == self.nsims
+        nt, N, K, units = self.ntheta, self.nsims, int(maxsteps), self.nsims + 1
+        f = lambda *s: np.zeros(s)
+        cache = self.__dict__.setdefault("_bufs", {})      # like the real wrapper: buffers are reused, the caller copies
+        if (K, N) not in cache:
+            cache[(K, N)] = dict(theta_final=f(nt), theta_hist=f(K, nt), g_dat_hist=f(K, nt), g_sims_hist=f(K, N, nt), g_like_hist=f(K, nt),
+                                 g_prior_hist=f(K, nt), h_inv_like_hist=f(K, nt), h_prior_hist=f(K, nt), h_inv_post_hist=f(K, nt),
+                                 seconds_hist=f(K), iters_hist=np.zeros((K, units), dtype=np.int32),
+                                 fg_hist=np.zeros((K, units), dtype=np.int32), gnorm_hist=f(K, units),
+                                 status_hist=np.zeros((K, units), dtype=np.int32))
+        r = dict(cache[(K, N)], n_iter=0)
+        theta = np.array(theta0, dtype=np.float64)
+        pm = np.asarray(prior_mean, dtype=np.float64) if prior_mean is not None else None
+        ps = np.asarray(prior_sigma, dtype=np.float64) if prior_sigma is not None else None
+        for i in range(1, K + 1):
+            if i > 2:
+                dth = r["theta_hist"][i - 2] - r["theta_hist"][i - 3]
+                if np.sqrt(-(dth * r["h_inv_post_hist"][i - 2] * dth).sum()) < theta_rtol:
+                    break
+            out = self.map_score(theta, theta, atol, include_data=True, warm_start=first_start if i == 1 else 1)
+            k = i - 1
+            gs = out["g"][1:]
+            g_like = out["g"][0] - gs.mean(axis=0)
+            g_prior = -(theta - pm) / ps ** 2 if ps is not None else np.zeros(nt)
+            h_like = -1.0 / gs.var(axis=0, ddof=1)
+            h_prior = -1.0 / ps ** 2 if ps is not None else np.zeros(nt)
+            h_post = 1.0 / (1.0 / h_like + h_prior)
+            r["theta_hist"][k], r["g_dat_hist"][k], r["g_sims_hist"][k], r["g_like_hist"][k] = theta, out["g"][0], gs, g_like
+            r["g_prior_hist"][k], r["h_inv_like_hist"][k], r["h_prior_hist"][k], r["h_inv_post_hist"][k] = g_prior, h_like, h_prior, h_post
+            r["iters_hist"][k], r["fg_hist"][k], r["gnorm_hist"][k], r["status_hist"][k] = out["iters"], out["fg_evals"], out["gnorm"], out["status"]
+            r["seconds_hist"][k] = 1e-3
+            theta = theta - alpha * (h_post * (g_like + g_prior))
+            r["n_iter"] = i
+            r["theta_final"][:] = theta
+        return r
+
+    def muse_covariance(self, theta, gs, nsims_h_total, counts_h, atol, prior_sigma=None):
+        nt = self.ntheta
+        gs = np.asarray(gs, dtype=np.float64).reshape(-1, nt)
+        J = np.atleast_2d(np.cov(gs, rowvar=False, ddof=1)) if nt > 1 else np.array([[gs[:, 0].var(ddof=1)]])
+        step = 0.1 / gs.std(axis=0, ddof=1)
+        Hs, _ = self.fd_jacobian(theta, step, nsims_h_total, atol)
+        H = Hs.mean(axis=0)
+        Hp = np.diag(1.0 / np.asarray(prior_sigma, dtype=np.float64) ** 2) if prior_sigma is not None else np.zeros((nt, nt))
+        Sinv = H.T @ np.linalg.inv(J) @ H + Hp
+        return dict(J=J, step=step, Hs=Hs, H=H, Sigma_inv=Sinv, Sigma=np.linalg.inv(Sinv))
+
+    def muse_solve(self, theta0, nsims_total, counts, maxsteps, theta_rtol, atol, alpha, first_start, prior_mean=None, prior_sigma=None,
+                   get_covariance=False, nsims_h_total=0, counts_h=None):
+        r = self.muse_iterate(theta0, nsims_total, counts, maxsteps, theta_rtol, atol, alpha, first_start, prior_mean, prior_sigma)
+        c = None
+        if get_covariance:
+            c = self.muse_covariance(r["theta_final"], r["g_sims_hist"][r["n_iter"] - 1], nsims_h_total, counts_h, atol, prior_sigma)
+        return r, c

