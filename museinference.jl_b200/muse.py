@@ -74,9 +74,19 @@ def _prior_mean_sigma(prior, ntheta):
     if type(prior) is FlatPrior:
         return None
     if type(prior) is NormalPrior:
-        return (np.broadcast_to(np.asarray(prior.mean, dtype=np.float64), (ntheta,)).copy(),
-                np.broadcast_to(np.asarray(prior.sigma, dtype=np.float64), (ntheta,)).copy())
+        mean, sigma = np.empty(ntheta), np.empty(ntheta)
+        mean[:] = prior.mean
+        sigma[:] = prior.sigma
+        return mean, sigma
     return False
+
+
+def _diagm(v):
+    """np.diag(v) for a short 1-D v without its generic-path overhead (called 3× per iteration of every solve)."""
+    n = v.size
+    a = np.zeros((n, n))
+    a.flat[::n + 1] = v
+    return a
 
 
 def _check_problem(prob):
@@ -172,26 +182,34 @@ def muse_(result: MuseResult, prob: AbstractMuseProblem, theta0=None, **kwargs):
             r = be.muse_iterate(theta, nsims, counts, maxsteps, theta_rtol, atol, alpha,
                                 _capi.START_USER if z0 is not None else _capi.START_ZEROS,
                                 *(prior_ms if prior_ms else (None, None)))
+        # the library's history buffers are reused by the next call: take ONE private copy of the executed rows of each
+        # array and hand out views of those copies (a solve of 10⁴ sims spent more time in 16 small copies per iteration
+        # than in the interpreter proper)
+        n = r["n_iter"]
+        H = {key: r[key][:n].copy() for key in ("theta_hist", "g_dat_hist", "g_sims_hist", "g_like_hist", "g_prior_hist", "h_inv_like_hist",
+                                              "h_prior_hist", "h_inv_post_hist", "iters_hist", "fg_hist", "gnorm_hist", "status_hist")}
+        secs = r["seconds_hist"][:n].tolist()
+        theta_final = r["theta_final"].copy()
         th_unreg_prev = theta.copy()
-        for k in range(r["n_iter"]):
-            hl, hp, hq = r["h_inv_like_hist"][k], r["h_prior_hist"][k], r["h_inv_post_hist"][k]
-            gsk = r["g_sims_hist"][k].copy()              # identity transform: g and g′ are the same array
+        for k in range(n):
+            gsk = H["g_sims_hist"][k]                     # identity transform: g and g′ are the same array
+            g_like, g_prior = H["g_like_hist"][k], H["g_prior_hist"][k]
+            H_inv_like = _diagm(H["h_inv_like_hist"][k])
+            it_k, fg_k, gn_k, st_k = H["iters_hist"][k], H["fg_hist"][k], H["gnorm_hist"][k], H["status_hist"][k]
             history.append(dict(
-                theta=r["theta_hist"][k].copy(), theta_unreg=th_unreg_prev,
-                theta_t=r["theta_hist"][k].copy(), theta_unreg_t=th_unreg_prev,
-                g_like_sims=gsk, g_like_sims_t=gsk, g_like_dat=r["g_dat_hist"][k].copy(), g_like=r["g_like_hist"][k].copy(),
-                g_prior=r["g_prior_hist"][k].copy(), g_post=r["g_like_hist"][k] + r["g_prior_hist"][k],
-                H_inv_post=np.diag(hq), H_prior=np.diag(hp), H_inv_like=np.diag(hl), H_inv_like_sims=np.diag(hl),
-                z_history_dat=dict(iters=int(r["iters_hist"][k, 0]), fg_evals=int(r["fg_hist"][k, 0]),
-                                   gnorm=float(r["gnorm_hist"][k, 0]), status=int(r["status_hist"][k, 0])),
-                z_history_sims=dict(iters=r["iters_hist"][k, 1:].copy(), fg_evals=r["fg_hist"][k, 1:].copy(),
-                                    gnorm=r["gnorm_hist"][k, 1:].copy(), status=r["status_hist"][k, 1:].copy()),
-                t=float(r["seconds_hist"][k]), z_dat=None, z_sims=None))
-            th_unreg_prev = r["theta_hist"][k + 1].copy() if k + 1 < r["n_iter"] else r["theta_final"].copy()
-            result.time += float(r["seconds_hist"][k])
-        if r["n_iter"]:
-            result.theta = r["theta_final"].copy()                                 # :230
-            result.gs = r["g_sims_hist"][r["n_iter"] - 1].copy()                   # :231
+                theta=H["theta_hist"][k], theta_unreg=th_unreg_prev, theta_t=H["theta_hist"][k], theta_unreg_t=th_unreg_prev,
+                g_like_sims=gsk, g_like_sims_t=gsk, g_like_dat=H["g_dat_hist"][k], g_like=g_like,
+                g_prior=g_prior, g_post=g_like + g_prior,
+                H_inv_post=_diagm(H["h_inv_post_hist"][k]), H_prior=_diagm(H["h_prior_hist"][k]), H_inv_like=H_inv_like,
+                H_inv_like_sims=H_inv_like,
+                z_history_dat=dict(iters=int(it_k[0]), fg_evals=int(fg_k[0]), gnorm=float(gn_k[0]), status=int(st_k[0])),
+                z_history_sims=dict(iters=it_k[1:], fg_evals=fg_k[1:], gnorm=gn_k[1:], status=st_k[1:]),
+                t=secs[k], z_dat=None, z_sims=None))
+            th_unreg_prev = H["theta_hist"][k + 1] if k + 1 < n else theta_final
+            result.time += secs[k]
+        if n:
+            result.theta = theta_final.copy()                                      # :230
+            result.gs = H["g_sims_hist"][n - 1].copy()                             # :231
         maxsteps = 0                                                               # the loop below has nothing left to do
         if cdev is not None and r["n_iter"]:                                       # :244-247, already done on the stream
             result.J, result.H, result.Hs = cdev["J"], cdev["H"], cdev["Hs"]
