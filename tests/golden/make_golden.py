@@ -20,6 +20,9 @@ CASES = [
     dict(name="funnel_d512_n100", family="funnel", d=512, nsims=100, seed=1234, prior=True, atol=1e-2),
     dict(name="funnel_d64_n16_tight", family="funnel", d=64, nsims=16, seed=77, prior=True, atol=1e-10),
     dict(name="hiergauss_d300_n40", family="hiergauss", d=300, nsims=40, seed=4321, prior=False, atol=1e-2),
+    # θ = (μ, σ) with σ > 0: transform_θ = (μ, log σ) (oracle/families.py TransformedFamily), θ₀ = (0.5, e^0.3)
+    dict(name="hiergauss_sigma_d200_n30", family="hiergauss", d=200, nsims=30, seed=2468, prior=False, atol=1e-2,
+         transform=["identity", "log"]),
 ]
 
 
@@ -29,6 +32,9 @@ def main():
         prior = O.NormalPrior(0, 3) if c["prior"] else None
         prob, fam, draws, xd = oracle_problem(c["family"], c["d"], c["nsims"], seed=c["seed"], prior=prior)
         th0 = theta_start(c["family"])
+        if c.get("transform"):
+            prob = O.OracleProblem(O.TransformedFamily(fam, c["transform"]), xd, draws, prior)
+            th0 = prob.inv_transform_theta(th0)
         res = O.muse(prob, th0, nsims=c["nsims"], gradz_logLike_atol=c["atol"], get_covariance=True, save_MAPs=True)
         h0 = res.history[0]
         fix = dict(

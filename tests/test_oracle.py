@@ -229,13 +229,15 @@ def test_broyden_updates_run_and_agree_on_first_iterations():
     np.testing.assert_allclose(a.history[0]["g_like"], b.history[0]["g_like"])
 
 
-@pytest.mark.parametrize("name", ["funnel_d512_n100", "funnel_d64_n16_tight", "hiergauss_d300_n40"])
+@pytest.mark.parametrize("name", ["funnel_d512_n100", "funnel_d64_n16_tight", "hiergauss_d300_n40", "hiergauss_sigma_d200_n30"])
 def test_golden_fixtures(name):
     with open(os.path.join(GOLDEN, name + ".json")) as fh:
         fix = json.load(fh)
     c = fix["case"]
     prior = O.NormalPrior(0, 3) if c["prior"] else None
     prob, fam, draws, xd = oracle_problem(c["family"], c["d"], c["nsims"], seed=c["seed"], prior=prior)
+    if c.get("transform"):
+        prob = O.OracleProblem(O.TransformedFamily(fam, c["transform"]), xd, draws, prior)
     np.testing.assert_allclose(xd[:4], fix["xdat_head"], rtol=1e-14)          # philox inputs are platform independent
     np.testing.assert_allclose(draws.xi[0, :4], fix["xi0_head"], rtol=1e-14)
     res = O.muse(prob, np.array(fix["theta0"]), nsims=c["nsims"], gradz_logLike_atol=c["atol"],
