@@ -162,3 +162,27 @@ def test_plain_c_example_links_against_the_library_and_fails_loudly_without_a_gp
         assert out.returncode == 0 and "OK" in out.stdout, out.stdout + out.stderr
     else:
         assert out.returncode == 3 and "no CPU fallback" in out.stderr, out.stdout + out.stderr
+
+
+def test_committed_bench_line_satisfies_the_contract():
+    """The bench line of the round (profiles/r01_v5_bench.json, produced by `python bench.py` on a B200) carries every key the
+    measurement contract names, with consistent values."""
+    import json
+    with open(os.path.join(ROOT, "profiles", "r01_v5_bench.json")) as fh:
+        d = json.loads(fh.read())
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
+        assert key in d, key
+    assert d["unit"] == "sims/s" and d["dtype"] == "f64" and d["data"] == "synthetic" and d["scaling"] == "weak"
+    assert d["higher_is_better"] is True and d["vs_baseline"] is None and d["n_gpus"] == 1 and d["warmup"] >= 3
+    assert "workload" in d["config"] and "model" not in d["config"] and "inputs_larger_than_l2" in d["config"]["l2"]
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12 and r["traffic"] > 0
+    assert 0.5 < r["frac"] < 1.2 and set(r["passes"]) >= {"cold", "warm", "fiducial", "fd"}
+    e = d["e2e"]
+    assert e["unit"] == "sims/s" and 0 < e["value"] < d["value"] and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0
+    c = d["cpu_baseline"]
+    assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] > 0 and c["unit"] == "sims/s" and c["sample"]
+    assert d["gpu_launches"] > 0 and d["clocks"]["sm_mhz"] and not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    units = d["config"]["units_per_step"]
+    assert abs(d["value"] - units / (d["ms_per_step"] * 1e-3)) / d["value"] < 1e-9
