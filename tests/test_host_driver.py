@@ -221,3 +221,70 @@ def test_fused_path_glue_rebuilds_the_same_result_as_the_line_by_line_loop(name,
     m.muse(pa, theta_start(name) + 0.2, fused_driver=mode, **kw)
     for s0, h in zip(snap, a.history):
         np.testing.assert_array_equal(s0, h["g_like_sims"])
+
+
+# ----------------------------------------------------------------------------- error policy, user start, saved MAPs
+class _FlakyBackend(FakeBackend):
+    """Reports a non-finite objective (status 4) for chosen sims, as the kernels do for NaN inputs."""
+    bad_sims = (2, 5)
+
+    def map_score(self, theta_sim, theta_eval, atol, *, include_data, warm_start, first_sim=0, count=None):
+        out = super().map_score(theta_sim, theta_eval, atol, include_data=include_data, warm_start=warm_start, first_sim=first_sim, count=count)
+        off = 1 if include_data else 0
+        for k in self.bad_sims:
+            if first_sim <= k < first_sim + (self.nsims - first_sim if count is None else count):
+                out["status"][off + k - first_sim] = 4
+                out["g"][off + k - first_sim] = np.nan
+        return out
+
+    def fd_jacobian(self, theta0, step, nsims_H, atol):
+        Hs, st = super().fd_jacobian(theta0, step, nsims_H, atol)
+        st[1, 0, 1] = 4
+        Hs[1] = np.nan
+        return Hs, st
+
+
+def test_skip_errors_drops_failed_sims_and_the_default_raises():
+    """src/muse.jl:515-521 / 434-441: with skip_errors a failed sim becomes `missing` and is skipped; without it the error
+    propagates (src/interface.jl:170)."""
+    import museinference_jl_b200 as m
+    oprob, fam, draws, xd = oracle_problem("hiergauss", 60, 12)
+    rng = m.BaseDraws(draws.xi, draws.nu, draws.xi_master, draws.nu_master)
+    prob = m.SimpleMuseProblem(xd, "hiergauss", backend_factory=_FlakyBackend)
+    getJ, getH = getattr(m, "get_J!"), getattr(m, "get_H!")
+    th = np.array([0.2, 0.1])
+    with pytest.raises(FloatingPointError):
+        getJ(m.MuseResult(theta=th.copy()), prob, rng=rng, nsims=12)
+    res = m.MuseResult(theta=th.copy())
+    getJ(res, prob, rng=rng, nsims=12, skip_errors=True)
+    ref = O.MuseResult(theta=th.copy())
+    O.get_J_bang(ref, oprob, nsims=12)
+    keep = [k for k in range(12) if k not in _FlakyBackend.bad_sims]
+    assert len(res.gs) == 10
+    np.testing.assert_allclose(np.array(res.gs), np.array(ref.gs)[keep], rtol=1e-12)
+    np.testing.assert_allclose(res.J, np.cov(np.array(ref.gs)[keep], rowvar=False, ddof=1), rtol=1e-12)
+    with pytest.raises(FloatingPointError):
+        getH(res, prob, rng=rng, nsims=4)
+    getH(res, prob, rng=rng, nsims=4, skip_errors=True)
+    assert len(res.Hs) == 3 and np.isfinite(res.H).all() and res.Sigma is not None
+    with pytest.raises(FloatingPointError):
+        m.muse(prob, [0.5, 0.3], rng=rng, nsims=12)            # muse! has no skip_errors: a failed MAP is an error
+
+
+def test_user_start_vector_and_saved_maps_on_the_host_path():
+    """`z₀` (src/muse.jl:117, 151) and `save_MAPs` (callable or true, src/muse.jl:139-143, 219)."""
+    import museinference_jl_b200 as m
+    d, nsims = 80, 10
+    m_, oprob, prob, rng = _pair("funnel", d, nsims, True)
+    z0 = np.linspace(-0.5, 0.5, d)
+    ref = O.muse(oprob, [1.0], nsims=nsims, z0=z0, save_MAPs=True, maxsteps=3, theta_rtol=0.0)
+    res = m.muse(prob, [1.0], rng=rng, nsims=nsims, z0=z0, save_MAPs=True, maxsteps=3, theta_rtol=0.0)
+    assert len(res.history) == 3
+    for a, b in zip(res.history, ref.history):
+        np.testing.assert_allclose(a["z_dat"], b["z_dat"], rtol=1e-10, atol=1e-12)
+        np.testing.assert_allclose(a["z_sims"], np.array(b["z_sims"]), rtol=1e-10, atol=1e-12)
+    first = prob._backend.calls[0]
+    assert first[0] == "map_score" and first[3] == 3                  # START_USER on the first pass only
+    assert [c[3] for c in prob._backend.calls if c[0] == "map_score"][1:] == [1, 1]
+    res2 = m.muse(prob, [1.0], rng=rng, nsims=nsims, save_MAPs=lambda z: float(np.sum(z)), maxsteps=2, theta_rtol=0.0)
+    assert isinstance(res2.history[0]["z_dat"], float)
