@@ -168,7 +168,8 @@ def muse_(result: MuseResult, prob: AbstractMuseProblem, theta0=None, **kwargs):
             pool.bind(be)
             counts = block_partition(nsims, pool.world)[1]
         mode = DEFAULT_FUSED_DRIVER if fused_driver is True else fused_driver
-        device_loop = (mode == "device" and hasattr(be, "muse_solve") and prob.family != "corrgauss" and maxsteps <= 64)
+        device_loop = (mode == "device" and hasattr(be, "muse_solve") and prob.family != "corrgauss" and maxsteps <= 64
+                       and pool.world <= 16)      # the limits of csrc/muse_outer.cu (history rows, rank table); else the host loop
         cdev = None
         if device_loop:
             counts_h = block_partition(nh_total, pool.world)[1] if (pool.world > 1 and get_covariance) else None
