@@ -316,3 +316,44 @@ def test_c_port_correlated_gaussian():
     res, units = cmuse.muse_cpu(oprob, [1.0], nsims=30)
     np.testing.assert_allclose(res.theta, ref.theta, rtol=1e-8)
     np.testing.assert_allclose(res.H, ref.H, rtol=1e-6)
+
+
+@pytest.mark.parametrize("name,d,nsims,kw,expect", [
+    ("funnel", 512, 100, dict(), dict(syncs=1, skipped=0, n_iter=2)),                   # the docs example: 2 iterations, break, 1 sync
+    ("funnel", 128, 40, dict(), dict(syncs=2, skipped=1, n_iter=4)),                    # 4 iterations: 2 passes + 3, of which 1 skipped
+    ("hiergauss", 200, 30, dict(theta_rtol=1e-3, maxsteps=6), None),
+    ("funnel", 64, 20, dict(theta_rtol=0.0, maxsteps=7), dict(syncs=3, skipped=0, n_iter=7)),   # chunks of 2 + 3 + 2 passes
+    ("funnel", 64, 20, dict(maxsteps=1), dict(syncs=1, skipped=0, n_iter=1)),
+])
+def test_device_resident_outer_loop_model(name, d, nsims, kw, expect):
+    """oracle/outer_device_model.py — the chunked, speculative control flow and the reduction order of csrc/muse_outer.cu —
+    against the line-by-line restatement of muse! (oracle/muse.py): same iterations, θ to round-off."""
+    from oracle import outer_device_model as M
+    prior = O.NormalPrior(0, 3) if name == "funnel" else None
+    oprob, fam, draws, xd = oracle_problem(name, d, nsims, prior=prior)
+    ref = O.muse(oprob, theta_start(name), nsims=nsims, **kw)
+    zs = [np.zeros(d) for _ in range(nsims + 1)]
+
+    def pass_fn(i, theta):
+        g = []
+        for u in range(nsims + 1):
+            x = oprob.x if u == 0 else oprob.sample_x_z(u - 1, theta)[0]
+            zs[u], gu, _ = O.map_score_unit(oprob, x, zs[u], theta, 1e-2)
+            g.append(gu)
+        return g[0], np.array(g[1:])
+
+    nt = fam.ntheta
+    pm = np.zeros(nt) if prior else None
+    ps = np.full(nt, 3.0) if prior else None
+    out = M.run(pass_fn, theta_start(name), maxsteps=kw.get("maxsteps", 50), theta_rtol=kw.get("theta_rtol", 1e-1), alpha=0.7,
+                prior_mean=pm, prior_sigma=ps)
+    assert out["n_iter"] == len(ref.history)
+    np.testing.assert_allclose(out["theta"], ref.theta, rtol=1e-12)
+    np.testing.assert_allclose(out["theta_hist"], np.array([h["theta"] for h in ref.history]), rtol=1e-12, atol=1e-300)
+    assert out["launched"] - out["skipped"] == out["n_iter"]
+    if expect:
+        for k, v in expect.items():
+            assert out[k] == v, (k, out[k], v)
+    # the tree sum is a re-ordering of the plain sum: equal to round-off on data like the scores
+    v = np.random.default_rng(0).standard_normal(5000) * 30 + 250
+    assert abs(M.tree_sum(v) - math.fsum(v)) <= 1e-12 * abs(math.fsum(v))
