@@ -53,6 +53,7 @@ constexpr int kThreads = kNC + 64;     // + producer warp + finisher warp
 constexpr int kChunk = 2048;           // elements per row per stage (16 KB)
 constexpr int kMaxStages = 8;
 constexpr int kDescRing = 16;
+// [host-test:begin red-slots]  (tests/test_fast_replay.py compiles the marked blocks for the host)
 constexpr int kNRed = 15;              // running sums per unit
 constexpr int kRedPad = 16;
 constexpr double kSpecTol = 1e-11;
@@ -67,6 +68,7 @@ enum Red : int {
 constexpr int kNSum = 12;                       // slots [0, kNSum) are sums, [kNSum, kNRed) maxima of non-negative values
 constexpr unsigned kMaxMask = (1u << rGM0) | (1u << rGMT) | (1u << rXC);
 static_assert(rGM0 == kNSum && rXC == kNRed - 1, "reduction slot layout");
+// [host-test:end red-slots]
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -252,6 +254,7 @@ __device__ __forceinline__ void warp_reduce(const Acc& A, int lane, double& sum_
 // Anything else — another bracket, a rejected secant point, a second iteration, an iteration cap of 0, a non-finite
 // value after the step, a 0-iteration solve whose start vector was not materialised — returns false: the unit is
 // left untouched and the generic kernel solves it from scratch.
+// [host-test:begin fast-replay]
 struct FastResult {
     double f, gmax, s1, s2;
     int iters, fg, status;
@@ -292,6 +295,7 @@ __device__ __noinline__ bool fast_replay(const SolveLaunch& L, int start_kind, c
     r.status = g_conv ? MUSE_STATUS_G_CONVERGED : MUSE_STATUS_XF_CONVERGED;
     return true;
 }
+// [host-test:end fast-replay]
 
 __device__ __forceinline__ void publish_unit(const SolveLaunch& L, const ItemDesc& it, const double (&t)[kNRed]) {
     FastResult r;
