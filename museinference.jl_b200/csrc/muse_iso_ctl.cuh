@@ -9,6 +9,7 @@
 namespace muse {
 namespace {
 
+// [host-test:begin ctl-a]  (tests/test_generic_solver_host.py compiles the marked blocks for the host)
 constexpr double kEpsD = 2.220446049250313e-16;
 #ifndef MUSE_BATCH
 #define MUSE_BATCH 4
@@ -81,6 +82,7 @@ __device__ __forceinline__ void st2(double* p, int i, double2 v) {
     *reinterpret_cast<double2*>(p + 2 * (size_t)i) = v;
 }
 
+// [host-test:end ctl-a]
 // L2 residency control.  The base normals are streamed once per launch
 // (evict_first); the unit's materialised x lives in a per-slot scratch row that is rewritten by
 // the next unit of the same group, so with evict_last it stays in the 126 MB L2 between the INIT
@@ -114,6 +116,7 @@ __device__ __forceinline__ void st2_hint(double* p, int i, double2 v, uint64_t p
                  : "l"(p + 2 * (size_t)i), "d"(v.x), "d"(v.y), "l"(pol));
 }
 
+// [host-test:begin ctl-b]
 // slow-path vector operations (only reached when a unit needs more than one L-BFGS iteration)
 template <class G, class Iter>
 __device__ __noinline__ void sweep_misc(G& grp, const SolveLaunch& L, const Cmd& c, double (&red)[7], Iter iter) {
@@ -710,6 +713,7 @@ struct Controller {
         }
     }
 };
+// [host-test:end ctl-b]
 
 
 }  // namespace

@@ -40,6 +40,7 @@ namespace muse {
 
 namespace {
 
+// [host-test:begin sweeps]
 // ---- the sweeps (executed by every thread of the group) -----------------------------------
 // red: [e0, gg0, gmax0, s1, s2, e1, dphi1]
 template <class G>
@@ -206,6 +207,7 @@ __device__ __noinline__ void run_op(G& grp, const SolveLaunch& L, const Cmd& c, 
     } else sweep_misc(grp, L, c, red, StridedIter<G>{grp, L});
 }
 
+// [host-test:end sweeps]
 
 // issuer of the register-loop kernel: broadcast the command, run it with every thread of the group
 template <class G>
