@@ -165,3 +165,61 @@ def test_generic_solver_history_path_iteration_cap_and_non_finite_data_on_the_ho
     hs3 = HostSolver(gs, family, d, draws, xbad)
     out = hs3.map_score(th, th, 1e-2, True, ZERO)
     assert out["status"][0] == 4 and (out["status"][1:] == 0).all()
+
+
+@pytest.mark.parametrize("family,d", [("funnel", 40), ("hiergauss", 27)])
+def test_generic_solver_fd_launches_on_the_host_match_the_oracle(gs, family, d):
+    """get_H!'s two launches (src/muse.jl:417-433): mode 2 — the fiducial MAP of the master stream's draw from zero(z) — then
+    mode 1 — 2·nθ virtual sims per H sim at θ₀ ∓ h·eₙ, MAP and score at θ₀ from the shared fiducial start."""
+    rng = np.random.default_rng(3 * d)
+    nsims, nH, atol = 9, 4, 1e-2
+    fam = O.make_family(family, d)
+    nt = fam.ntheta
+    draws = O.Draws.from_numpy(5, nsims, d)
+    xd, _ = fam.sample(np.zeros(nt), rng.standard_normal(d), rng.standard_normal(d))
+    prob = O.OracleProblem(fam, xd, draws)
+    th0 = np.array([0.6]) if family == "funnel" else np.array([0.2, 0.15])
+    step = 0.03 * (1 + np.arange(nt))
+    hs = HostSolver(gs, family, d, draws, xd)
+    p = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
+    ev, smp0 = hs.consts(th0, th0)
+    # fiducial: one item, mode 2, start zeros, own buffers (row 0 of a 1-row pair)
+    zfA, zfB, zfs = np.zeros((1, hs.ld)), np.zeros((1, hs.ld)), np.zeros(1, dtype=np.int32)
+    g1, it1, fg1, gn1, f1, st1 = np.zeros((1, nt)), np.zeros(1, np.int32), np.zeros(1, np.int32), np.zeros(1), np.zeros(1), np.zeros(1, np.int32)
+    gs.muse_host_generic_run(FAMILY_ID[family], d, hs.ld, 1, 2, 0, 0, ZERO, 10, 1000, C.c_double(atol), p(ev), p(smp0), 1, p(hs.xi), p(hs.nu),
+                             p(hs.xdat), None, nsims, p(hs.xslot), p(zfA), p(zfB), p(zfs), p(hs.sbuf), p(hs.dxh), p(hs.dgh),
+                             p(g1), p(it1), p(fg1), p(gn1), p(f1), p(st1))
+    xm, _ = prob.sample_x_z("master", th0)
+    zfid_ref, soln = prob.z_at_theta(xm, np.zeros(d), th0, atol)
+    zfid = (zfA if zfs[0] == 1 else zfB)[0, :d].copy()
+    np.testing.assert_allclose(zfid, zfid_ref, rtol=1e-11, atol=1e-12)
+    assert (it1[0], fg1[0]) == (soln.iterations, soln.f_calls)
+    # virtual sims: items (k·nθ + n)·2 + s, constants of the sample points in smp[2n + s], shared start = the fiducial ẑ
+    items = nH * nt * 2
+    smp = np.zeros((2 * nt, 2))
+    pts = []
+    for n in range(nt):
+        for s in (0, 1):
+            th = th0.copy(); th[n] += step[n] * (1.0 if s else -1.0)
+            smp[2 * n + s] = hs.consts(th, th0)[1]
+            pts.append(th)
+    zHA, zHB = np.zeros((items, hs.ld)), np.zeros((items, hs.ld))
+    g, it, fg, gn, f, st = np.zeros((items, nt)), np.zeros(items, np.int32), np.zeros(items, np.int32), np.zeros(items), np.zeros(items), np.zeros(items, np.int32)
+    zsh = np.ascontiguousarray(np.pad(zfid, (0, hs.ld - d)))
+    gs.muse_host_generic_run(FAMILY_ID[family], d, hs.ld, items, 1, 0, 0, SHARED, 10, 1000, C.c_double(atol), p(ev), p(np.ascontiguousarray(smp)), 2 * nt,
+                             p(hs.xi), p(hs.nu), p(hs.xdat), p(zsh), nsims, p(hs.xslot), p(zHA), p(zHB), None, p(hs.sbuf), p(hs.dxh), p(hs.dgh),
+                             p(g), p(it), p(fg), p(gn), p(f), p(st))
+    for k in range(nH):
+        for n in range(nt):
+            for s in (0, 1):
+                item = (k * nt + n) * 2 + s
+                x, _ = prob.sample_x_z(k, pts[2 * n + s])
+                zh, sol = prob.z_at_theta(x, zfid_ref, th0, atol)
+                assert (it[item], fg[item], st[item]) == (sol.iterations, sol.f_calls, _status(sol))
+                np.testing.assert_allclose(g[item], prob.grad_theta(x, zh, th0), rtol=1e-10, atol=1e-9)
+    # the Jacobian the host forms from them (central_fdm(3,1), src/util.jl:13-19) against the oracle's get_H!
+    res = O.MuseResult(theta=th0.copy())
+    O.get_H_bang(res, prob, th0, nsims=nH, step=step, gradz_logLike_atol=atol)
+    for k in range(nH):
+        Hk = np.stack([(g[(k * nt + n) * 2 + 1] * 0.5 + g[(k * nt + n) * 2] * -0.5) / step[n] for n in range(nt)], axis=1)
+        np.testing.assert_allclose(Hk, res.Hs[k], rtol=1e-7, atol=1e-7 * np.abs(res.Hs[k]).max())
