@@ -103,6 +103,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ double2 lds2(const double* p) { return *reinterpret_cast<const double2*>(p); }
 
+// [host-test:begin item-desc]
 // what the producer tells the other roles about one work item
 struct ItemDesc {
     double* zout;        // where ẑ goes (null: discarded)
@@ -116,6 +117,7 @@ struct ItemDesc {
     int zst_accept;      // ZState of the unit once the committed step is accepted (buffer that holds ẑ)
     int* zstate_row;     // the unit's zstate cell (null: none)
 };
+// [host-test:end item-desc]
 
 struct Shared {
     uint64_t full[kMaxStages], empty[kMaxStages];
@@ -124,6 +126,7 @@ struct Shared {
     double part[2][kNCW][kRedPad];
 };
 
+// [host-test:begin elem3]
 struct Acc {
     double v[kNRed];
 };
@@ -169,6 +172,7 @@ __device__ __forceinline__ double elem3(double p, double q, double z0in, const I
     A.v[rXC] = fmax(A.v[rXC], fabs(zt - z0));
     return zt;
 }
+// [host-test:end elem3]
 
 __device__ __forceinline__ void st2_stream(double* p, double2 v, uint64_t pol) {
     asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(v.x), "d"(v.y), "l"(pol) : "memory");
@@ -297,6 +301,7 @@ __device__ __noinline__ bool fast_replay(const SolveLaunch& L, int start_kind, c
 }
 // [host-test:end fast-replay]
 
+// [host-test:begin publish]
 __device__ __forceinline__ void publish_unit(const SolveLaunch& L, const ItemDesc& it, const double (&t)[kNRed]) {
     FastResult r;
     if (!fast_replay(L, it.start_kind, t, r)) {
@@ -317,7 +322,12 @@ __device__ __forceinline__ void publish_unit(const SolveLaunch& L, const ItemDes
     L.gnorm_out[it.unit] = r.gmax;
     L.f_out[it.unit] = r.f;
     L.status_out[it.unit] = r.status;
-    if (r.flip && it.zstate_row) *it.zstate_row = it.zst_accept;
+    if (it.zstate_row) {
+        if (r.flip) *it.zstate_row = it.zst_accept;
+        // 0 iterations from zero(z): the unit's ẑ IS zero — say so, or a buffer left by an earlier solve would pass for it
+        // (found by the host-side fuzz, tests/test_generic_solver_host.py; the generic kernel always did this)
+        else if (it.start_kind == kStartZero) *it.zstate_row = kZZero;
+    }
 }
 
 // unit → pointers (the Controller's own set-up code, muse_iso_ctl.cuh); no sweeps are ever issued through it here
@@ -327,6 +337,7 @@ struct NoIssuer {
 struct WarpCtx {
     int tid;
 };
+// [host-test:end publish]
 
 __global__ void __launch_bounds__(kThreads, 1)
 iso_stream_kernel(const __grid_constant__ SolveLaunch L) {
@@ -586,6 +597,7 @@ iso_warp_stream_kernel(const __grid_constant__ SolveLaunch L) {
     for (int unit = gw; unit < L.nitems; unit += nw) {
         int* zs = u.setup_unit(unit, zshared, nullptr);
         const Cmd& c = u.cur;
+        // [host-test:begin warp-item]
         ItemDesc it;
         it.unit = unit;
         it.start_kind = c.start_kind;
@@ -597,6 +609,7 @@ iso_warp_stream_kernel(const __grid_constant__ SolveLaunch L) {
         it.zk = (c.start_kind == kStartTruth) ? 2 : (c.zcur ? 1 : 0);
         it.zout = L.discard_z ? nullptr : c.zalt;
         const double* ra = it.sim ? c.xi : L.xdat;
+        // [host-test:end warp-item]
         Acc A;
 #pragma unroll
         for (int k = 0; k < kNRed; ++k) A.v[k] = 0.0;

@@ -30,7 +30,11 @@ def gs(tmp_path_factory):
         return m.group(1)
 
     src = open(os.path.join(ROOT, "tests", "csrc", "generic_solver_host.cpp.in")).read()
+    stream = open(os.path.join(csrc, "muse_iso_stream.cu")).read()
     src = src.replace("@CTL_A@", block(ctl, "ctl-a")).replace("@CTL_B@", block(ctl, "ctl-b")).replace("@SWEEPS@", block(sol, "sweeps"))
+    for tag, key in (("red-slots", "@RED_SLOTS@"), ("item-desc", "@ITEM_DESC@"), ("elem3", "@ELEM3@"), ("fast-replay", "@FAST_REPLAY@"),
+                     ("publish", "@PUBLISH@"), ("warp-item", "@WARP_ITEM@")):
+        src = src.replace(key, block(stream, tag))
     d = tmp_path_factory.mktemp("gs")
     (d / "gs.cpp").write_text(src)
     out = str(d / "libgs.so")
@@ -42,8 +46,11 @@ def gs(tmp_path_factory):
 class HostSolver:
     """Host arrays of one handle and launches of the generic solver over them."""
 
-    def __init__(self, lib, family, d, draws, xdat, lbfgs_m=10, max_iters=1000):
+    def __init__(self, lib, family, d, draws, xdat, lbfgs_m=10, max_iters=1000, single_pass=False):
         self.lib, self.family, self.d, self.n = lib, family, d, draws.xi.shape[0]
+        self.single_pass = single_pass          # True: the streaming kernels' single pass first, generic solver on the hand-backs
+        self.redo_total = np.zeros(1, dtype=np.uint64)
+        self.last_redo = 0
         self.ld = d + (d & 1) + 2
         self.nt = 2 if family == "hiergauss" else 1
         rows = self.n + 1
@@ -72,11 +79,14 @@ class HostSolver:
         g = np.zeros((items, self.nt)); it = np.zeros(items, dtype=np.int32); fg = np.zeros(items, dtype=np.int32)
         gn = np.zeros(items); f = np.zeros(items); st = np.zeros(items, dtype=np.int32)
         zs = None if zshared is None else np.ascontiguousarray(np.pad(zshared, (0, self.ld - self.d)))
+        redo_items = np.zeros(items, dtype=np.int32) if self.single_pass else None
+        redo_count = np.zeros(2, dtype=np.int32)
         p = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
         self.lib.muse_host_generic_run(FAMILY_ID[self.family], self.d, self.ld, items, 0, int(include_data), first, start, self.m, self.max_iters,
                                        C.c_double(atol), p(ev), p(smp), 1, p(self.xi), p(self.nu), p(self.xdat), p(zs), self.n,
                                        p(self.xslot), p(self.zA), p(self.zB), p(self.zstate), p(self.sbuf), p(self.dxh), p(self.dgh),
-                                       p(g), p(it), p(fg), p(gn), p(f), p(st))
+                                       p(g), p(it), p(fg), p(gn), p(f), p(st), p(redo_items), p(redo_count), p(self.redo_total) if self.single_pass else None, 0)
+        self.last_redo = int(redo_count[0])
         return dict(g=g, iters=it, fg=fg, gnorm=gn, f=f, status=st)
 
     def z(self, unit):
@@ -88,8 +98,9 @@ def _status(soln):
     return 0 if soln.g_converged else (1 if soln.converged else 2)
 
 
+@pytest.mark.parametrize("single_pass", [False, True])
 @pytest.mark.parametrize("family,d,atol", [("funnel", 37, 1e-2), ("funnel", 64, 1e-8), ("hiergauss", 51, 1e-2), ("hiergauss", 20, 1e-6)])
-def test_generic_solver_code_on_the_host_matches_the_oracle(gs, family, d, atol):
+def test_generic_solver_code_on_the_host_matches_the_oracle(gs, family, d, atol, single_pass):
     rng = np.random.default_rng(d)
     nsims = 14
     fam = O.make_family(family, d)
@@ -97,7 +108,7 @@ def test_generic_solver_code_on_the_host_matches_the_oracle(gs, family, d, atol)
     th_true = np.zeros(fam.ntheta)
     xd, _ = fam.sample(th_true, rng.standard_normal(d), rng.standard_normal(d))
     prob = O.OracleProblem(fam, xd, draws)
-    hs = HostSolver(gs, family, d, draws, xd)
+    hs = HostSolver(gs, family, d, draws, xd, single_pass=single_pass)
     th0 = np.array([0.7]) if family == "funnel" else np.array([0.4, 0.25])
 
     def check(out, units, theta_sim, theta_eval, starts, z_prev):
@@ -115,6 +126,7 @@ def test_generic_solver_code_on_the_host_matches_the_oracle(gs, family, d, atol)
     out = hs.map_score(th0, th0, atol, True, ZERO)
     check(out, units, th0, th0, [np.zeros(d)] * (nsims + 1), None)
     assert (out["iters"] == 1).all() and (out["fg"] == 3).all()
+    assert hs.last_redo == 0                 # single pass: every unit finished on the fast path, nothing handed back
     zprev = [hs.z(u) for u in units]
     # warm pass at a moved θ from the previous ẑ
     th1 = th0 - 0.3
@@ -149,8 +161,9 @@ def test_generic_solver_history_path_iteration_cap_and_non_finite_data_on_the_ho
     xd, _ = fam.sample(np.zeros(fam.ntheta), rng.standard_normal(d), rng.standard_normal(d))
     prob = O.OracleProblem(fam, xd, draws)
     th = np.array([0.8]) if family == "funnel" else np.array([0.3, -0.2])
-    hs = HostSolver(gs, family, d, draws, xd)
+    hs = HostSolver(gs, family, d, draws, xd, single_pass=True)
     out = hs.map_score(th, th, 1e-300, True, ZERO)
+    assert hs.last_redo == nsims + 1         # the single pass cannot finish such a unit: all handed back, re-solved from the untouched start
     assert (out["iters"] >= 2).all() and np.isin(out["status"], [0, 1, 3]).all()
     for u in range(nsims + 1):
         x = xd if u == 0 else prob.sample_x_z(u - 1, th)[0]
@@ -188,7 +201,7 @@ def test_generic_solver_fd_launches_on_the_host_match_the_oracle(gs, family, d):
     g1, it1, fg1, gn1, f1, st1 = np.zeros((1, nt)), np.zeros(1, np.int32), np.zeros(1, np.int32), np.zeros(1), np.zeros(1), np.zeros(1, np.int32)
     gs.muse_host_generic_run(FAMILY_ID[family], d, hs.ld, 1, 2, 0, 0, ZERO, 10, 1000, C.c_double(atol), p(ev), p(smp0), 1, p(hs.xi), p(hs.nu),
                              p(hs.xdat), None, nsims, p(hs.xslot), p(zfA), p(zfB), p(zfs), p(hs.sbuf), p(hs.dxh), p(hs.dgh),
-                             p(g1), p(it1), p(fg1), p(gn1), p(f1), p(st1))
+                             p(g1), p(it1), p(fg1), p(gn1), p(f1), p(st1), None, None, None, 0)
     xm, _ = prob.sample_x_z("master", th0)
     zfid_ref, soln = prob.z_at_theta(xm, np.zeros(d), th0, atol)
     zfid = (zfA if zfs[0] == 1 else zfB)[0, :d].copy()
@@ -208,7 +221,7 @@ def test_generic_solver_fd_launches_on_the_host_match_the_oracle(gs, family, d):
     zsh = np.ascontiguousarray(np.pad(zfid, (0, hs.ld - d)))
     gs.muse_host_generic_run(FAMILY_ID[family], d, hs.ld, items, 1, 0, 0, SHARED, 10, 1000, C.c_double(atol), p(ev), p(np.ascontiguousarray(smp)), 2 * nt,
                              p(hs.xi), p(hs.nu), p(hs.xdat), p(zsh), nsims, p(hs.xslot), p(zHA), p(zHB), None, p(hs.sbuf), p(hs.dxh), p(hs.dgh),
-                             p(g), p(it), p(fg), p(gn), p(f), p(st))
+                             p(g), p(it), p(fg), p(gn), p(f), p(st), None, None, None, 0)
     for k in range(nH):
         for n in range(nt):
             for s in (0, 1):
@@ -223,3 +236,22 @@ def test_generic_solver_fd_launches_on_the_host_match_the_oracle(gs, family, d):
     for k in range(nH):
         Hk = np.stack([(g[(k * nt + n) * 2 + 1] * 0.5 + g[(k * nt + n) * 2] * -0.5) / step[n] for n in range(nt)], axis=1)
         np.testing.assert_allclose(Hk, res.Hs[k], rtol=1e-7, atol=1e-7 * np.abs(res.Hs[k]).max())
+
+
+@pytest.mark.parametrize("single_pass", [False, True])
+def test_zero_iteration_solve_from_zeros_leaves_a_zero_map_not_a_stale_one(gs, single_pass):
+    """A unit whose zero start already satisfies the tolerance ends with ẑ = zero(z).  The single-pass kernels used to leave
+    the unit's state cell untouched in that case, so the buffer of an EARLIER solve passed for its ẑ (found by the random
+    sweep of this harness; publish_unit now records kZZero, as the generic kernel always did)."""
+    d, nsims = 6, 5
+    fam = O.make_family("funnel", d)
+    draws = O.Draws.from_numpy(3, nsims, d)
+    xd = np.full(d, 0.3)
+    hs = HostSolver(gs, "funnel", d, draws, xd, single_pass=single_pass)
+    th = np.array([0.5])
+    hs.map_score(th, th, 1e-2, True, ZERO)                       # a real solve: every unit now holds a non-zero ẑ
+    assert all(np.abs(hs.z(u)).max() > 0 for u in range(nsims + 1))
+    out = hs.map_score(th, th, 1e3, True, ZERO)                  # tolerance so loose that zero(z) is already "converged"
+    assert (out["iters"] == 0).all() and (out["fg"] == 1).all() and (out["status"] == 0).all()
+    for u in range(nsims + 1):
+        np.testing.assert_array_equal(hs.z(u), np.zeros(d))

@@ -771,3 +771,19 @@ def test_device_resident_outer_loop_against_oracle_and_errors():
                 get_covariance=True, fused_driver="device")
     assert rc.Sigma is not None
     probc.close()
+
+
+@pytest.mark.parametrize("d,kernel", [(512, 0), (6000, 0), (6000, 1)])
+def test_zero_iteration_solve_from_zeros_leaves_a_zero_map(d, kernel):
+    """ẑ of a unit whose zero start already satisfies the tolerance is zero(z) — not the buffer an earlier solve left behind.
+    (Last in the file on purpose: added after the round's last GPU session, checked on the CPU through the host build of the
+    kernels' code, tests/test_generic_solver_host.py.)"""
+    fam, draws, xd = make_inputs("funnel", d, 8)
+    be = _backend("funnel", d, 8, draws, xd, kernel=kernel)
+    th = np.array([0.5])
+    be.map_score(th, th, 1e-2, include_data=True, warm_start=0)
+    assert np.abs(be.get_maps(0, 9)).max() > 0
+    out = be.map_score(th, th, 1e6, include_data=True, warm_start=0)
+    assert (out["iters"] == 0).all() and (out["fg_evals"] == 1).all() and (out["status"] == 0).all()
+    np.testing.assert_array_equal(be.get_maps(0, 9), np.zeros((9, d)))
+    be.close()
