@@ -47,6 +47,17 @@ NcclApi* nccl_api() {
     return &api;
 }
 
+// this rank's score rows → the send buffer; the rows of units whose solve ended with a non-finite objective go out as NaN,
+// so that EVERY rank sees the failure in the gathered matrix and takes the same error decision (src/interface.jl:170) —
+// a rank that failed alone would leave the others waiting in the next exchange
+__global__ void pack_rows_kernel(const double* __restrict__ src, const int* __restrict__ status, double* __restrict__ dst, int n, int ncol) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * ncol) return;
+    const int row = i / ncol;
+    const bool bad = status != nullptr && status[row] == MUSE_STATUS_NONFINITE;
+    dst[i] = bad ? __longlong_as_double(0x7ff8000000000000LL) : src[i];
+}
+
 }  // namespace
 
 void muse_comm_release(muse_handle* h) {
@@ -114,7 +125,7 @@ void muse_comm_unpack(muse_handle* h, int ncol, const int32_t* counts, double* o
 // gather `counts[q]` rows of `ncol` doubles from every rank q; this rank's rows come from device memory (`src_dev`)
 // or from the host (`src_host`)
 static int allgather_impl(muse_handle* h, const double* src_dev, const double* src_host, int ncol, const int32_t* counts,
-                          double* out_host) {
+                          double* out_host, const int* status_dev = nullptr) {
     if (!h->comm) { h->err = "no communicator (muse_b200_comm_init)"; return MUSE_ESTATE; }
     NcclApi* a = nccl_api();
     const int R = h->comm_nranks;
@@ -141,7 +152,10 @@ static int allgather_impl(muse_handle* h, const double* src_dev, const double* s
     }
     const size_t bytes_mine = (size_t)mine * ncol * sizeof(double);
     if (mine && src_dev) {
-        if (cudaMemcpyAsync(h->comm_send, src_dev, bytes_mine, cudaMemcpyDeviceToDevice, h->stream) != cudaSuccess) { h->err = "cudaMemcpyAsync"; return MUSE_ECUDA; }
+        const int n = mine * ncol;
+        pack_rows_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(src_dev, status_dev, h->comm_send, mine, ncol);
+        if (cudaGetLastError() != cudaSuccess) { h->err = "pack_rows_kernel launch failed"; return MUSE_ECUDA; }
+        h->acc.launches += 1;
     } else if (mine) {
         double* stage = h->comm_host + need * R;            // pinned staging slot behind the receive area
         std::memcpy(stage, src_host, bytes_mine);
@@ -164,22 +178,22 @@ static int allgather_impl(muse_handle* h, const double* src_dev, const double* s
 // enqueue-only variant for the in-library driver: gather on the stream, no synchronisation
 int muse_comm_allgather_scores_enqueue(muse_handle* h, int first_row, const int32_t* counts) {
     if (h->comm && first_row + counts[h->comm_rank] > h->out_cap) { h->err = "score rows outside the device output buffer"; return MUSE_EINVAL; }
-    return allgather_impl(h, h->g_d + (size_t)first_row * h->cfg.ntheta, nullptr, h->cfg.ntheta, counts, nullptr);
+    return allgather_impl(h, h->g_d + (size_t)first_row * h->cfg.ntheta, nullptr, h->cfg.ntheta, counts, nullptr, h->status_d + first_row);
 }
 
 // the same from an arbitrary device source (the device-resident outer loop gathers from a per-pass output block);
 // *need_out = doubles per rank slot of the receive area h->comm_recv
-int muse_comm_allgather_dev_enqueue(muse_handle* h, const double* src_dev, int ncol, const int32_t* counts, size_t* need_out) {
+int muse_comm_allgather_dev_enqueue(muse_handle* h, const double* src_dev, const int* status_dev, int ncol, const int32_t* counts, size_t* need_out) {
     int maxc = 1;
     for (int r = 0; r < h->comm_nranks; ++r) maxc = counts[r] > maxc ? counts[r] : maxc;
     if (need_out) *need_out = (size_t)maxc * ncol;
-    return allgather_impl(h, src_dev, nullptr, ncol, counts, nullptr);
+    return allgather_impl(h, src_dev, nullptr, ncol, counts, nullptr, status_dev);
 }
 
 int muse_b200_allgather_scores(muse_handle* h, int32_t first_row, const int32_t* counts, double* out_host) {
     if (!h || !counts || !out_host || first_row < 0) return MUSE_EINVAL;
     if (h->comm && first_row + counts[h->comm_rank] > h->out_cap) { h->err = "score rows outside the device output buffer"; return MUSE_EINVAL; }
-    return allgather_impl(h, h->g_d + (size_t)first_row * h->cfg.ntheta, nullptr, h->cfg.ntheta, counts, out_host);
+    return allgather_impl(h, h->g_d + (size_t)first_row * h->cfg.ntheta, nullptr, h->cfg.ntheta, counts, out_host, h->status_d + first_row);
 }
 
 int muse_b200_allgather_rows(muse_handle* h, const double* local_host, int32_t ncol, const int32_t* counts, double* out_host) {

@@ -176,19 +176,25 @@ extern "C" int muse_b200_muse_iterate(muse_handle* h, const double* theta0, int3
         rc = muse_b200_fetch(h, units, g_local.data(), out->iters_hist + (size_t)row * units, out->fg_hist + (size_t)row * units,
                              out->gnorm_hist + (size_t)row * units, out->status_hist + (size_t)row * units);
         if (rc != MUSE_OK) return rc;
-        for (int u = 0; u < units; ++u)
-            if (out->status_hist[(size_t)row * units + u] == MUSE_STATUS_NONFINITE) {
-                h->err = "muse!: MAP solution failed with a non-finite objective";
-                return MUSE_ESTATE;
-            }
+        // the error decision must be the same on every rank (a rank that returned alone would leave the others waiting in the
+        // next exchange): the data unit is replicated, and the gathered rows of failed sims arrive as NaN (muse_comm.cu)
+        bool failed = out->status_hist[(size_t)row * units] == MUSE_STATUS_NONFINITE;
+        if (!multi) {
+            for (int u = 1; u < units; ++u) failed = failed || out->status_hist[(size_t)row * units + u] == MUSE_STATUS_NONFINITE;
+        }
         if (g_debug_timing) {
             const auto t_b = std::chrono::steady_clock::now();
             std::fprintf(stderr, "[muse_iterate rank %d] iter %d: enqueue+wait %.1f us (since loop top %.1f us)\n", h->comm_rank, i,
                          std::chrono::duration<double, std::micro>(t_b - t_a).count(),
                          std::chrono::duration<double, std::micro>(t_b - t0).count());
         }
-        if (multi) muse_comm_unpack(h, nt, counts, gs);                       // fetch() has synchronised the stream
-        else std::memcpy(gs, g_local.data() + nt, (size_t)nloc * nt * sizeof(double));
+        if (multi) {
+            muse_comm_unpack(h, nt, counts, gs);                              // fetch() has synchronised the stream
+            for (size_t e = 0; e < (size_t)nsims_total * nt; ++e) failed = failed || std::isnan(gs[e]);
+        } else {
+            std::memcpy(gs, g_local.data() + nt, (size_t)nloc * nt * sizeof(double));
+        }
+        if (failed) { h->err = "muse!: MAP solution failed with a non-finite objective"; return MUSE_ESTATE; }
         double* th_row = out->theta_hist + (size_t)row * nt;
         for (int c = 0; c < nt; ++c) {
             double m, v;

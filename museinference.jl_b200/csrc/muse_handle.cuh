@@ -138,7 +138,7 @@ extern "C" void muse_fd_combine_host(muse_handle* h, const double* g_h, const in
 size_t muse_outblock_bytes(const muse_handle* h, int items);
 void muse_outblock_carve(const muse_handle* h, OutBlock& ob, unsigned char* dev, unsigned char* host, int items);
 void muse_outer_release(muse_handle* h);
-extern "C" int  muse_comm_allgather_dev_enqueue(muse_handle* h, const double* src_dev, int ncol, const int32_t* counts, size_t* need_out);
+extern "C" int  muse_comm_allgather_dev_enqueue(muse_handle* h, const double* src_dev, const int* status_dev, int ncol, const int32_t* counts, size_t* need_out);
 
 void muse_comm_release(muse_handle* h);
 extern "C" void muse_comm_unpack(muse_handle* h, int ncol, const int32_t* counts, double* out_host);

@@ -153,8 +153,17 @@ __global__ void __launch_bounds__(kStepThreads) theta_step_kernel(const OuterPar
     }
     if (threadIdx.x == 0) bad = 0;
     __syncthreads();
-    for (int u = threadIdx.x; u < P.units_local; u += kStepThreads)
-        if (__ldcg(P.status_local + u) == MUSE_STATUS_NONFINITE) bad = 1;   // src/interface.jl:170
+    // src/interface.jl:170.  The decision must be the same on every rank: with several ranks it is taken from what all of them
+    // see — the replicated data unit and the gathered rows, in which a failed sim arrives as NaN (muse_comm.cu / publish_peer)
+    if (P.nranks > 1) {
+        if (threadIdx.x == 0 && __ldcg(P.status_local) == MUSE_STATUS_NONFINITE) bad = 1;
+        for (int q = 0; q < P.nranks; ++q)
+            for (int e = threadIdx.x; e < P.counts[q] * P.nt; e += kStepThreads)
+                if (isnan(__ldcg(P.g_all + (size_t)q * P.need + e))) bad = 1;
+    } else {
+        for (int u = threadIdx.x; u < P.units_local; u += kStepThreads)
+            if (__ldcg(P.status_local + u) == MUSE_STATUS_NONFINITE) bad = 1;
+    }
     __syncthreads();
     if (bad) {
         if (threadIdx.x == 0) { st->error = 1; st->done = 1; if (P.dyn_next) P.dyn_next->skip = 1; }
@@ -388,7 +397,7 @@ extern "C" int muse_b200_muse_solve(muse_handle* h, const double* theta0, int32_
             P.status_local = ob.status_d;
             if (multi) {                    // the one exchange step, on the stream
                 size_t need = 0;
-                rc2 = muse_comm_allgather_dev_enqueue(h, ob.g_d + nt, nt, counts, &need);
+                rc2 = muse_comm_allgather_dev_enqueue(h, ob.g_d + nt, ob.status_d + 1, nt, counts, &need);
                 if (rc2 != MUSE_OK) return rc2;
                 OUTER_TRY(h, cudaMemcpyAsync(h->outer_gall[slot], h->comm_recv, gall_doubles * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
                 P.g_all = h->outer_gall[slot];
@@ -441,7 +450,8 @@ extern "C" int muse_b200_muse_solve(muse_handle* h, const double* theta0, int32_
         const int ints[] = {maxsteps, first_start, get_covariance, nh_mine, nsims_total, nloc, h->prof ? 1 : 0, P.have_prior, h->out_cap, h->h_cap};
         const double dbl[] = {theta_rtol, atol, alpha};
         put(ints, sizeof(ints)); put(dbl, sizeof(dbl)); put(P.prior_mean, sizeof(P.prior_mean)); put(P.prior_sigma, sizeof(P.prior_sigma));
-        const void* ptrs[] = {h->stream, h->out_d, h->zHA, h->outer_arena_d, h->outer_arena_h, h->outer_st_stage, dyn, h->gpart, h->dbg, h->xi, h->xi_h};
+        const void* ptrs[] = {h->stream, h->out_d, h->zHA, h->outer_arena_d, h->outer_arena_h, h->outer_st_stage, dyn, h->gpart, h->dbg, h->xi, h->xi_h,
+                              h->comm_send, h->comm_recv, h->comm_host, h->outer_gall[0], h->outer_gall[1], h->outer_gall[2], h->outer_gall_h};
         put(ptrs, sizeof(ptrs));
     }
     // MUSE_OUTER_GRAPH=0: eager enqueue only.  MUSE_OUTER_GRAPH_MULTI=1: also capture the chunk when a communicator is bound

@@ -96,11 +96,17 @@ def _check_problem(prob):
                                    "Turing/Soss-defined models raise, there is no CPU fallback")
 
 
-def _check_status(out, what, skip_errors=False):
-    """src/interface.jl:168-171: non-convergence warns, a non-finite objective is an error."""
+def _check_status(out, what, skip_errors=False, pool=None):
+    """src/interface.jl:168-171: non-convergence warns, a non-finite objective is an error.  With several ranks the
+    decision is collective: every rank learns whether ANY rank saw a failure and raises (or not) together — a rank that
+    raised alone would leave the others waiting in the next exchange step."""
     bad = np.flatnonzero(out["status"] == _capi.STATUS_NONFINITE)
-    if bad.size and not skip_errors:
-        raise FloatingPointError(f"{what}: MAP solution failed with a non-finite objective for unit(s) {bad[:8].tolist()}")
+    any_bad = bool(bad.size)
+    if pool is not None and pool.world > 1 and not skip_errors:
+        any_bad = bool(pool.any_flag(any_bad))
+    if any_bad and not skip_errors:
+        where = f"unit(s) {bad[:8].tolist()}" if bad.size else "a unit of another rank"
+        raise FloatingPointError(f"{what}: MAP solution failed with a non-finite objective for {where}")
     return bad
 
 
@@ -136,7 +142,9 @@ def muse_(result: MuseResult, prob: AbstractMuseProblem, theta0=None, **kwargs):
         raise TypeError(f"muse!: unknown keyword argument(s) {sorted(kw)}")
     _check_problem(prob)
 
-    # :134  rng: given, else the result's, else a fresh default seed
+    # :134  rng: given, else the result's, else seed 0.  The reference falls back to copy(Random.default_rng()), which does
+    # not advance the global stream either: repeated calls without an rng reuse the same sims there too, unless the
+    # caller consumed the global RNG in between.  Pass distinct seeds for independent solves.
     if rng is None:
         rng = result.rng if result.rng is not None else 0
     result.rng = rng
@@ -252,7 +260,7 @@ def muse_(result: MuseResult, prob: AbstractMuseProblem, theta0=None, **kwargs):
             out = be.map_score(theta_t, theta_t, atol, include_data=True, warm_start=warm)
             g_like_sims_t = pool.allgather_rows(out["g"][1:], nsims)               # the one exchange step
         first_pass = False
-        _check_status(out, "muse!")
+        _check_status(out, "muse!", pool=pool)
         g_like_dat = out["g"][0].copy()                                            # :177-178 (g_like_dat′)
         g_like_sims = g_like_sims_t / prob.dinv_transform(theta_t) if transformed else g_like_sims_t   # :177 (g)
 
@@ -337,15 +345,17 @@ def get_J_(result: MuseResult, prob: AbstractMuseProblem, theta0=None, **kwargs)
         # rngs = split_rng(rng, nsims)[nsims_existing+1:end]  (:506) → global sims [existing, nsims)
         be = prob.backend_for(nsims, rng, pool, nh_total)
         off, cnt = pool.shard(nsims)
-        lo = max(nsims_existing, off) - off
-        hi = cnt
-        n_local = max(0, hi - lo)
+        lo = min(max(nsims_existing, off) - off, cnt)      # a shard that lies wholly below nsims_existing has nothing to do
+        n_local = cnt - lo
         if z0 is not None:
             be.set_z0(z0)
         warm = _capi.START_USER if z0 is not None else _capi.START_TRUTH           # :511
         theta0_t = prob.transform_theta(theta0)
-        out = be.map_score(theta0_t, theta0_t, atol, include_data=False, warm_start=warm, first_sim=lo, count=n_local)
-        bad = _check_status(out, "get_J!", skip_errors)
+        if n_local > 0:
+            out = be.map_score(theta0_t, theta0_t, atol, include_data=False, warm_start=warm, first_sim=lo, count=n_local)
+        else:
+            out = dict(g=np.zeros((0, prob.ntheta)), status=np.zeros(0, dtype=np.int32))
+        bad = _check_status(out, "get_J!", skip_errors, pool)
         g_local = out["g"] / prob.dinv_transform(theta0_t) if prob.has_transform else out["g"]   # :513 UnTransformedθ()
         if pool.world == 1:
             g_new = np.delete(g_local, bad, axis=0) if bad.size else g_local       # skipmissing (:508)
@@ -435,7 +445,10 @@ def get_H_(result: MuseResult, prob: AbstractMuseProblem, theta0=None, **kwargs)
             Hs_local[:, :, n] = acc / step[n]
         status = st.reshape(hcnt, nt, 2)
     bad_local = np.flatnonzero((status.reshape(hcnt, -1) == _capi.STATUS_NONFINITE).any(axis=1))
-    if bad_local.size and not skip_errors:
+    any_bad = bool(bad_local.size)
+    if pool.world > 1 and not skip_errors:
+        any_bad = bool(pool.any_flag(any_bad))           # collective decision: all ranks raise together
+    if any_bad and not skip_errors:
         raise FloatingPointError("get_H!: MAP solution failed with a non-finite objective")
     nt = prob.ntheta
     flat = Hs_local.reshape(hcnt, nt * nt).copy()

@@ -38,6 +38,9 @@ class LocalPool:
     def allgather_rows(self, local: np.ndarray, n_total: int) -> np.ndarray:
         return np.asarray(local)
 
+    def any_flag(self, flag: bool) -> bool:
+        return bool(flag)
+
     def barrier(self):
         pass
 
@@ -60,7 +63,17 @@ class ShardPool:
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
         self.backend = dist.get_backend(group)
-        self.device = device if device is not None else 0
+        if device is None:
+            # one rank per GPU: torchrun's LOCAL_RANK, else the rank modulo the visible devices (never "everyone on GPU 0")
+            import os
+            device = int(os.environ.get("LOCAL_RANK", -1))
+            if device < 0:
+                try:
+                    import torch
+                    device = self.rank % max(1, torch.cuda.device_count())
+                except Exception:
+                    device = 0
+        self.device = device
         self._bufs = {}
 
     def shard(self, n):
@@ -142,6 +155,11 @@ class ShardPool:
             raise ValueError("local block does not match the partition")
         self.bind(be)
         return be.allgather_rows(local, cnts)
+
+    def any_flag(self, flag: bool) -> bool:
+        """True on every rank iff any rank passed True (the collective form of a per-rank error test)."""
+        rows = self.allgather_rows(np.array([[1.0 if flag else 0.0]]), self.world)
+        return bool(rows.any())
 
     def barrier(self):
         self._dist.barrier(group=self.group)

@@ -189,7 +189,10 @@ class SimpleMuseProblem(AbstractMuseProblem):
         off, cnt = pool.shard(nsims_total)
         hoff, hcnt = pool.shard(nsims_h_total) if (pool.world > 1 and nsims_h_total > 0) else (0, 0)
         gkey = (nsims_total, off, cnt, hoff, hcnt, pool.device)
-        rkey = ("seed", int(rng)) if isinstance(rng, (int, np.integer)) else ("draws", id(rng))
+        # installed draws are recognised by identity: the BaseDraws object itself is held (a bare id() could be reused by a
+        # new object once the old one is collected, and stale draws would pass for the new ones).  Arrays mutated in place
+        # are NOT detected — pass a new BaseDraws for new normals.
+        rkey = ("seed", int(rng)) if isinstance(rng, (int, np.integer)) else ("draws", rng)
         if self._backend is None or self._backend_key != gkey:
             if self._backend is not None:
                 self._backend.close()
@@ -201,7 +204,9 @@ class SimpleMuseProblem(AbstractMuseProblem):
         if self._data_dirty:
             be.set_data(self.x)
             self._data_dirty = False
-        if self._rng_key != rkey:
+        same = (self._rng_key is not None and self._rng_key[0] == rkey[0]
+                and (self._rng_key[1] is rkey[1] if rkey[0] == "draws" else self._rng_key[1] == rkey[1]))
+        if not same:
             if isinstance(rng, (int, np.integer)):
                 be.seed_draws(int(rng))
             elif isinstance(rng, BaseDraws):

@@ -48,6 +48,9 @@ class FakeBackend:
 
     def map_score(self, theta_sim, theta_eval, atol, *, include_data, warm_start, first_sim=0, count=None):
         count = self.nsims - first_sim if count is None else count
+        # the real backend rejects ranges outside the handle's shard (muse_b200_map_score_async) and empty launches
+        assert first_sim >= 0 and count >= 0 and first_sim + count <= self.nsims, "sim range outside the handle's shard"
+        assert count + (1 if include_data else 0) > 0, "empty launch"
         prob = self._prob()
         units = ([0] if include_data else []) + [1 + first_sim + i for i in range(count)]
         self.calls.append(("map_score", tuple(np.atleast_1d(theta_eval)), include_data, warm_start, first_sim, count))

@@ -101,6 +101,11 @@ def _worker_topup(rank, world, port, q):
         getJ(res, prob, rng=rng, nsims=8, pool=pool)
         getJ(res, prob, rng=rng, nsims=21, pool=pool)           # top-up across the shard boundary (src/muse.jl:499-506)
         getH(res, prob, rng=rng, nsims=5, pool=pool)
+        # top-up whose existing rows already cover the whole of rank 0's shard (11 sims): rank 0 has nothing to simulate
+        res3 = m.MuseResult(theta=np.array([0.2, 0.1]))
+        getJ(res3, prob, rng=rng, nsims=14, pool=pool)
+        getJ(res3, prob, rng=rng, nsims=21, pool=pool)
+        assert np.array_equal(np.array(res3.gs), np.array(res.gs)) and np.array_equal(res3.J, res.J)
         # the same problem with θ = (μ, σ), σ > 0 (transform_θ = (μ, log σ)): full solve sharded over the two ranks
         import oracle as O
         tprob = m.SimpleMuseProblem(xd, "hiergauss", theta_transform=("identity", "log"), backend_factory=FakeBackend)
