@@ -4,7 +4,12 @@
 default line search of ``Optim.LBFGS()``), which the reference reaches through
 ``Optim.optimize(..., Optim.LBFGS(), ...)`` at /root/reference/src/interface.jl:163.
 LineSearches.jl is not vendored under /root/reference (transitive dependency of
-Optim "1.5", unpinned); this is the published algorithm of
+Optim "1.5", unpinned).  Target of this restatement: **LineSearches.jl v7.2.0** (what Optim v1.7–v1.9 —
+the releases the compat range "1.5" resolved to while MuseInference v0.2.4 was current, Julia 1.7–1.10 — depend on
+through `LineSearches = "7.0.1"`); ``hagerzhang.jl`` has not changed its arithmetic since v7.0 (the B0–B3 /
+``secant2!`` / ``update!`` / ``bisect!`` structure, the ``nextfloat(values[ia]) >= values[ib]`` stagnation exit,
+``psi3``, ``iterfinitemax = -log2(eps)``).  PARITY UNPINNED: restated from the published source as recalled, no
+reference-held vector exists to check it against.  This is the published algorithm of
 
     W. W. Hager and H. Zhang, "Algorithm 851: CG_DESCENT", ACM TOMS 32 (2006),
     stages B0-B3 (bracket), S1-S4 (secant²), U0-U3 (update / bisect)

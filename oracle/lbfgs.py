@@ -7,7 +7,12 @@
                    Optim.LBFGS(), Optim.Options(g_tol = ∇z_logLike_atol))
 
 Optim.jl is a dependency with compat "1.5" (Project.toml:45), not vendored under
-/root/reference.  Restated from Optim.jl 1.x:
+/root/reference.  Target of this restatement: **Optim.jl v1.7.8** (with NLSolversBase v7.8.3 and
+LineSearches v7.2.0) — any release from v1.5.0 to v1.9.x satisfies the compat range, and the L-BFGS path restated
+here (``twoloop!`` with ``pseudo_iteration``, ``scaleinvH0``, ``reset_search_direction!`` when dφ₀ ≥ 0,
+``update_h!`` skipping the pair when 1/(dx·dg) is infinite, ``assess_convergence`` with ``successive_f_tol = 1``,
+``g_abstol`` tested at the initial point) is the same in all of them.  PARITY UNPINNED: restated from the published
+source as recalled; the reference ships no vector that would pin it.  Restated from:
 
   * ``optimize`` main loop           src/multivariate/optimize/optimize.jl
   * ``LBFGS`` state / twoloop! / update_state! / update_h! / reset_search_direction!

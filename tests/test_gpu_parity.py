@@ -787,3 +787,147 @@ def test_zero_iteration_solve_from_zeros_leaves_a_zero_map(d, kernel):
     assert (out["iters"] == 0).all() and (out["fg_evals"] == 1).all() and (out["status"] == 0).all()
     np.testing.assert_array_equal(be.get_maps(0, 9), np.zeros((9, d)))
     be.close()
+
+
+# ----------------------------------------------------------------------------- round 2: configs at size, multi-rank NCCL
+def test_full_size_c2_funnel_against_closed_form_and_oracle():
+    """BASELINE configs[1] at full size (funnel, d = 512, nsims = 10⁴, device Philox draws): 10 001 units = 1 251 CTAs of the
+    warp-per-unit kernel in one launch.  Every unit: 1 iteration / 3 evaluations, score against the closed form
+    g = ½ e^{-θ} s² ‖x‖² − d/2; 64 sampled units (and the data unit) against the oracle's L-BFGS on the device's own draws,
+    for the cold pass and for the warm pass that follows (src/muse.jl:169-176, 181)."""
+    import math
+    import museinference_jl_b200 as m
+    d, n, seed, atol = 512, 10000, 424242, 1e-2
+    fam = O.make_family("funnel", d)
+    xd, _ = fam.sample(np.array([0.0]), O.philox_normals(5, 0, 0, d), O.philox_normals(5, 0, 1, d))
+    be = m.B200Backend("funnel", d, n)
+    be.set_data(xd)
+    be.seed_draws(seed)
+    xi, nu = be.get_draws(0, n + 1)
+    draws = O.Draws(xi[:n], nu[:n], xi[n], nu[n])
+    prob = O.OracleProblem(fam, xd, draws)
+    th0, th1 = np.array([1.0]), np.array([0.55])
+    out0 = be.map_score(th0, th0, atol, include_data=True, warm_start=0)
+    z0 = be.get_maps(0, n + 1)
+    out1 = be.map_score(th1, th1, atol, include_data=True, warm_start=1)
+    z1 = be.get_maps(0, n + 1)
+    assert be.profile()["redo_units"] == 0
+    for out, th in ((out0, th0), (out1, th1)):
+        assert (out["iters"] == 1).all() and (out["fg_evals"] == 3).all() and (out["status"] == 0).all()
+        s, a = 1.0 / (1.0 + math.exp(-th[0])), math.exp(-th[0])
+        x = np.vstack([xd[None], math.exp(0.5 * th[0]) * xi[:n] + nu[:n]])
+        np.testing.assert_allclose(out["g"][:, 0], 0.5 * a * s * s * np.einsum("ij,ij->i", x, x) - d / 2, rtol=1e-9)
+    sample = [0] + sorted(np.random.default_rng(0).choice(np.arange(1, n + 1), size=64, replace=False).tolist())
+    for u in sample:
+        x = xd if u == 0 else prob.sample_x_z(u - 1, th0)[0]
+        zh, g, soln = O.map_score_unit(prob, x, np.zeros(d), th0, atol)
+        assert (out0["iters"][u], out0["fg_evals"][u]) == (soln.iterations, soln.f_calls)
+        np.testing.assert_allclose(out0["g"][u], g, rtol=RTOL_SIM)
+        np.testing.assert_allclose(z0[u], zh, rtol=RTOL_SIM, atol=1e-12)
+        x = xd if u == 0 else prob.sample_x_z(u - 1, th1)[0]
+        zh1, g1, soln1 = O.map_score_unit(prob, x, zh, th1, atol)
+        assert (out1["iters"][u], out1["fg_evals"][u]) == (soln1.iterations, soln1.f_calls)
+        np.testing.assert_allclose(out1["g"][u], g1, rtol=RTOL_SIM)
+        np.testing.assert_allclose(z1[u], zh1, rtol=RTOL_SIM, atol=1e-12)
+    be.close()
+
+
+def test_full_size_c5_corrgauss_sampled_units_match_oracle_lbfgs():
+    """BASELINE configs[4] at full size (d = 4 096, nsims = 8 192, host Philox draws uploaded): the data unit and 8 sampled
+    sims against the oracle's honest L-BFGS + Hager–Zhang (C port, P·z evaluated at every trial point) at d = 4 096 —
+    identical iteration and evaluation counts, ẑ and g within rtol 1e-8 — for the cold pass and the warm pass after it."""
+    import museinference_jl_b200 as m
+    from bench import corr_consts
+    from oracle import cport
+    d, n, atol = 4096, 8192, 1e-2
+    P, L = corr_consts(d)
+    rng = np.random.Generator(np.random.Philox(77))
+    xi, nu = rng.standard_normal((n, d)), rng.standard_normal((n, d))
+    xim, num = rng.standard_normal(d), rng.standard_normal(d)
+    xd = L @ rng.standard_normal(d) + rng.standard_normal(d)
+    be = m.B200Backend("corrgauss", d, n, P=P, L=L)
+    be.set_data(xd)
+    be.set_draws(xi, nu, xim, num)
+    th0, th1 = np.array([1.0]), np.array([0.6])
+    sims = sorted(np.random.default_rng(1).choice(n, size=8, replace=False).tolist())
+    out0 = be.map_score(th0, th0, atol, include_data=True, warm_start=0)
+    z0 = np.vstack([be.get_maps(0, 1)] + [be.get_maps(1 + k, 1) for k in sims])
+    out1 = be.map_score(th1, th1, atol, include_data=True, warm_start=1)
+    z1 = np.vstack([be.get_maps(0, 1)] + [be.get_maps(1 + k, 1) for k in sims])
+    be.close()
+    units = [0] + [1 + k for k in sims]
+    ref0 = cport.map_score(3, xi[sims], nu[sims], xd, th0, th0, atol, True, 0, want_z=True, P=P, L=L)
+    ref1 = cport.map_score(3, xi[sims], nu[sims], xd, th1, th1, atol, True, 1, z_start=ref0["z"], want_z=True, P=P, L=L)
+    for out, z, ref in ((out0, z0, ref0), (out1, z1, ref1)):
+        np.testing.assert_array_equal(out["iters"][units], ref["iters"])
+        np.testing.assert_array_equal(out["fg_evals"][units], ref["fg_evals"])
+        np.testing.assert_array_equal(out["status"][units], ref["status"])
+        np.testing.assert_allclose(out["g"][units], ref["g"], rtol=RTOL_SIM)
+        np.testing.assert_allclose(z, ref["z"], rtol=RTOL_SIM, atol=1e-11)
+    assert out0["iters"][units].min() >= 4
+
+
+def _nccl_worker(rank, world, port, cases, q):
+    import os
+    import sys
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import torch
+    import torch.distributed as dist
+    import museinference_jl_b200 as m
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        pool = m.ShardPool(device=rank)
+        outs = []
+        for name, d, nsims, th0, xd, P, L, prior, fused in cases:
+            prob = m.SimpleMuseProblem(xd, name, m.NormalPrior(0, 3) if prior else None, P=P, L=L)
+            for seed in (11, 12):          # twice: the second solve of a shape goes through the library's captured graph
+                res = m.muse(prob, th0, rng=seed, nsims=nsims, get_covariance=True, pool=pool, fused_driver=fused)
+            outs.append((res.theta, np.array(res.gs), res.H, res.J, res.Sigma, len(res.history)))
+            prob.close()
+        q.put((rank, outs))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_nccl_solve_is_bit_identical_to_one_gpu():
+    """Two ranks, one GPU each (skipped on a one-GPU box): contiguous sim shards, the score exchange between the passes, θ
+    updated identically on both ranks.  θ̂, gs, H, J, Σ of every rank must equal the single-GPU solve BIT FOR BIT for F1, F2
+    (device-resident loop) and F3 (host loop), and through the line-by-line driver — per-sim results do not depend on the
+    shard and every reduction is ordered by the global sim index (src/muse.jl:169, 177-183)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import socket
+    import torch.multiprocessing as mp
+    import museinference_jl_b200 as m
+    cases = []
+    for name, d, nsims, prior, fused in (("funnel", 6000, 203, True, True), ("hiergauss", 5001, 120, False, True),
+                                         ("funnel", 512, 301, True, True), ("corrgauss", 256, 100, True, True),
+                                         ("hiergauss", 700, 64, True, False)):
+        fam, _, xd = make_inputs(name, d, 1)
+        cases.append((name, d, nsims, theta_start(name), xd, getattr(fam, "P", None), getattr(fam, "L", None), prior, fused))
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, cases, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=600) for _ in procs)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for i, (name, d, nsims, th0, xd, P, L, prior, fused) in enumerate(cases):
+        prob = m.SimpleMuseProblem(xd, name, m.NormalPrior(0, 3) if prior else None, P=P, L=L)
+        ref = m.muse(prob, th0, rng=12, nsims=nsims, get_covariance=True, fused_driver=fused)
+        prob.close()
+        for rank in (0, 1):
+            theta, gs, H, J, Sigma, nhist = got[rank][i]
+            assert nhist == len(ref.history)
+            np.testing.assert_array_equal(gs, np.array(ref.gs), err_msg=f"{name} rank {rank}: gs")
+            np.testing.assert_array_equal(theta, ref.theta, err_msg=f"{name} rank {rank}: θ")
+            np.testing.assert_array_equal(H, ref.H, err_msg=f"{name} rank {rank}: H")
+            np.testing.assert_array_equal(J, ref.J)
+            np.testing.assert_array_equal(Sigma, ref.Sigma)
