@@ -5,12 +5,16 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 Workload (BASELINE.json configs[2], the config the metric is quoted on at 1/2/4/8 B200; it fits one
-GPU): Neal's funnel, 2^16 latent dims, nsims = 2048 per GPU, full solve θ̂ / J / H
+GPU): Neal's funnel, 2^16 latent dims, nsims = 2048, full solve θ̂ / J / H
 (``muse(prob, 1.0; nsims, get_covariance=true)``, prior N(0,3), ∇z_logLike_atol = 1e-2, data at
 θ_true = 0).  One *step* = one such full solve.  The metric counts the MAP+score units actually
 executed (outer iterations × (nsims+1) + 1 fiducial + 2·nθ·(nsims÷10) finite-difference solves; the
 reference's redundant centre evaluations and duplicate fiducial solves are neither executed nor
-counted) divided by the device time of the step.
+counted) divided by the device time of the step.  With N GPUs the default is the north star's split
+(``--scaling strong``: the 2048 sims are sharded, N/8 per rank at 8); the weak-scaling figure (2048 sims
+per GPU) rides along as ``other_scaling``.  A block of K steps is repeated until ≈ 0.6 s have been timed
+(so that the clock record holds > 20 samples); the reported time is the median block.  The default
+single-GPU run also measures the other BASELINE configs (C1, C2, C4, C5) into ``configs``.
 
 value   device-resident: base normals and data already in HBM, K steps bracketed by CUDA events on
         the launch stream (barrier + synchronize on both sides), max over ranks.
@@ -35,7 +39,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 D = 65536
-NSIMS_PER_GPU = 2048
+NSIMS = 2048
 THETA0 = 1.0
 ATOL = 1e-2
 DATA_SEED = 20261017
@@ -45,18 +49,21 @@ SIM_SEED = 314159
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
+                    help="strong (default, the north-star split): --nsims sims in total, N/world per rank; weak: --nsims per rank")
     ap.add_argument("--d", "--dim", dest="d", type=int, default=D, help="latent dimension (use --dim under torchrun: its parser finds --d ambiguous)")
-    ap.add_argument("--nsims", type=int, default=NSIMS_PER_GPU, help="sims per GPU (weak) or in total (strong)")
+    ap.add_argument("--nsims", type=int, default=NSIMS, help="sims in total (strong) or per GPU (weak)")
     ap.add_argument("--family", default="funnel", choices=["funnel", "hiergauss", "corrgauss"])
     ap.add_argument("--group", type=int, default=0)
     ap.add_argument("--cluster", type=int, default=0)
     ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 generic solver only, 2 streaming kernel first")
     ap.add_argument("--cpu-sims", type=int, default=0, help="sims in the bounded CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-configs", action="store_true", help="skip the C1/C2/C4/C5 records of the default single-GPU run")
+    ap.add_argument("--no-other-scaling", action="store_true", help="N > 1: skip the sub-record of the other scaling mode")
     return ap.parse_args()
 
 
@@ -210,10 +217,32 @@ def cpu_sample_nsims(args):
     return int(max(16, min(args.nsims, 4.5e9 / (16.0 * args.d))))
 
 
+def workload_name(family, d, nsims, scaling, world):
+    cfg_name = {"funnel": "BASELINE configs[2]" if d == 65536 else ("BASELINE configs[1]" if (d == 512 and nsims == 10000) else
+                          ("BASELINE configs[0]" if (d == 512 and nsims == 100) else "funnel, custom shape")),
+                "hiergauss": "BASELINE configs[3]", "corrgauss": "BASELINE configs[4]"}[family]
+    per = "" if world == 1 else (" per GPU" if scaling == "weak" else " in total, sharded over the GPUs")
+    return (f"{family} d={d} nsims={nsims}{per}: full solve θ̂/J/H = muse(prob, θ₀={theta_start(family).tolist()}; nsims, "
+            f"get_covariance=true), ∇z_logLike_atol={ATOL} ({cfg_name})")
+
+
+def bench_config(args, world):
+    """The `config` object — the SAME in the GPU arm and in the reference arm (the driver compares them): only what
+    names the workload, nothing measured."""
+    nsims_total = args.nsims * world if args.scaling == "weak" else args.nsims
+    per_gpu = nsims_total / world
+    return {"workload": workload_name(args.family, args.d, args.nsims, args.scaling, world),
+            "family": args.family, "d": args.d, "nsims_total": nsims_total, "theta0": theta_start(args.family).tolist(),
+            "atol": ATOL, "scaling": args.scaling,
+            "l2": "inputs_larger_than_l2" if 2 * per_gpu * args.d * 8 > 126e6 else
+                  "inputs fit the 126 MB L2 (%.1f MB of base normals per GPU): a latency-bound configuration, L2 is not flushed" % (2 * per_gpu * args.d * 8 / 1e6)}
+
+
 def run_reference(args):
     """--impl reference: the CPU implementation of the path (oracle C port; the Julia reference cannot
     run in this image) on all host threads, each step a bounded sample of the workload."""
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
     nsims = cpu_sample_nsims(args)
@@ -232,8 +261,7 @@ def run_reference(args):
         "impl": "reference", "metric": "MUSE sims/sec (MAP+score)", "value": value, "unit": "sims/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
         "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.family} d={args.d} nsims={args.nsims}/GPU full solve θ̂/J/H (BASELINE configs[2])",
-                   "cpu_sample_nsims": nsims},
+        "config": bench_config(args, world),
         "cpu_baseline": {"value": value, "unit": "sims/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -242,7 +270,187 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------- GPU arm
+MIN_TIMED_SECONDS = 0.6       # blocks of K steps are repeated until the timed regions add up to this (clock record > 20 samples)
+
+
+def src_sha256():
+    """sha256 of the library's CUDA sources (what scripts/ncu_traffic.py stamps a capture with)."""
+    import hashlib
+    h = hashlib.sha256()
+    cs = os.path.join(ROOT, "museinference.jl_b200", "csrc")
+    for f in sorted(os.listdir(cs)) + [os.path.join("..", "..", "include", "muse_b200.h")]:
+        with open(os.path.join(cs, f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
+def measured_traffic(family, d, nsims):
+    """DRAM bytes per solver launch from an `ncu --set full` capture of THIS build of the library (scripts/ncu_traffic.py
+    writes profiles/r02_solver_traffic.json with the sha256 of the library's sources); null when the capture is of another build or shape."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_solver_traffic.json")) as fh:
+            t = json.load(fh)
+        if t.get("src_sha256") == src_sha256() and (t.get("family"), t.get("d"), t.get("nsims")) == (family, d, nsims):
+            return t.get("dram_bytes_per_launch_avg")
+    except Exception:
+        pass
+    return None
+
+
+class Workload:
+    """One problem of the bench on this rank's GPU: the solve closure and its timing helpers."""
+
+    def __init__(self, m, torch, dist, family, d, nsims_total, pool, stream, args, world):
+        self.m, self.torch, self.dist, self.world, self.stream = m, torch, dist, world, stream
+        self.family, self.d, self.nsims_total, self.pool = family, d, nsims_total, pool
+        P = Lc = None
+        if family == "corrgauss":
+            P, Lc = corr_consts(d)
+        self.x_host = torch.from_numpy(observed_data(family, d, Lc)).pin_memory()
+        prior = m.FlatPrior() if family == "hiergauss" else m.NormalPrior(0, 3)
+        self.prob = m.SimpleMuseProblem(self.x_host.numpy(), family, prior, P=P, L=Lc, group=args.group, cluster=args.cluster,
+                                        kernel=args.kernel, stream=stream.cuda_stream)
+        self.th0 = theta_start(family)
+        self.res = None
+
+    def solve(self, seed):
+        self.res = self.m.muse(self.prob, self.th0, rng=seed, nsims=self.nsims_total, gradz_logLike_atol=ATOL, get_covariance=True,
+                               pool=self.pool)
+        return self.res
+
+    def sync_all(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
+
+    def warm(self, n):
+        for w in range(n):
+            self.solve(SIM_SEED)
+            if w == 0:
+                # per-launch event timing on from the second warm-up solve on: the library's graph of a solve bakes the
+                # event-record nodes in, so the timed steps must see the configuration they were warmed with
+                self.prob._backend.profile_reset(True)
+
+    def timed_blocks(self, steps, body, min_seconds=MIN_TIMED_SECONDS, max_blocks=200):
+        """Blocks of exactly `steps` steps, each bracketed by barrier + synchronize and CUDA events on the launch stream;
+        returns the per-block times (ms, this rank)."""
+        torch = self.torch
+        out, total = [], 0.0
+        while (total < min_seconds * 1e3 and len(out) < max_blocks) or not out:
+            self.sync_all()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            e0.record(self.stream)
+            for s in range(steps):
+                body(s)
+            e1.record(self.stream)
+            self.sync_all()
+            wall = 1e3 * (time.perf_counter() - t0)
+            out.append((e0.elapsed_time(e1), wall))
+            total += wall
+            if self.world > 1:      # every rank must take the same number of blocks
+                t = torch.tensor([total], dtype=torch.float64, device="cuda")
+                self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+                total = float(t.item())
+        return out
+
+    def reduce_max(self, vals):
+        if self.world == 1:
+            return list(vals)
+        t = self.torch.tensor(list(vals), dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return t.tolist()
+
+    def reduce_sum(self, vals):
+        if self.world == 1:
+            return list(vals)
+        t = self.torch.tensor(list(vals), dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return t.tolist()
+
+    def close(self):
+        self.prob.close()
+
+
+def measure_value(wl, steps, warmup, min_seconds=MIN_TIMED_SECONDS):
+    """Device-resident arm: base normals and data in HBM, blocks of `steps` full solves.  Returns a dict with the median
+    block (max over ranks per block), the profile of the timed blocks and the units executed."""
+    wl.warm(warmup)
+    be = wl.prob._backend
+    wl.sync_all()
+    be.profile_reset(True)
+    blocks = wl.timed_blocks(steps, lambda s: wl.solve(SIM_SEED), min_seconds)
+    prof = be.profile()
+    passes = be.profile_passes()
+    be.profile_reset(False)
+    ev = wl.reduce_max([b[0] for b in blocks])            # per block: max over ranks of the device time
+    nb = len(ev)
+    ms_block = float(np.median(ev))
+    units_all, solve_ms_sum, solve_bytes_sum, launches_sum, flops_sum = wl.reduce_sum(
+        [prof["solve_units"], prof["solve_ms"], prof["solve_bytes"], float(prof["launches"]), prof["solve_flops"]])
+    return dict(ms_block=ms_block, blocks=nb, block_ms_all=ev, units_per_block=units_all / nb, prof=prof, passes=passes,
+                solve_ms_sum=solve_ms_sum, solve_bytes_sum=solve_bytes_sum, launches_per_block=launches_sum / nb, flops_sum=flops_sum)
+
+
+def roofline_of(wl, mv, hbm_peak, peak_src, steps, kernel_flag):
+    """`roofline` object of one measured workload (HBM-bound isotropic families; FP64 tensor pipe for corrgauss)."""
+    torch = wl.torch
+    prof, world = mv["prof"], wl.world
+    n_launch = max(1, prof["solve_launches"] * world)
+    by_pass = {}
+    for kind, v in mv["passes"].items():
+        if v["launches"]:
+            e = {"launches_per_step": v["launches"] / (steps * mv["blocks"]), "units_per_launch": v["units"] / v["launches"],
+                 "avg_launch_ms": v["ms"] / v["launches"], "sims_per_s": v["units"] / (v["ms"] * 1e-3) if v["ms"] > 0 else None}
+            if v["bytes"] > 0 and v["ms"] > 0:
+                e["algorithmic_gbs"] = v["bytes"] / 1e9 / (v["ms"] * 1e-3)
+                e["frac_of_hbm_peak"] = e["algorithmic_gbs"] / hbm_peak
+            by_pass[kind] = e
+    share = mv["solve_ms_sum"] / world / (mv["ms_block"] * mv["blocks"])
+    if wl.family == "corrgauss":
+        # FP64 tensor roofline: denominator = cuBLAS DGEMM of the same shape measured here (MEASURED_PEAKS.json carries only
+        # bf16), numerator = 2·rows·d² per P-product ÷ CUDA-event time of the whole solver chains
+        d = wl.d
+        rows = (wl.nsims_total // world + 1 + 127) // 128 * 128
+        a = torch.full((rows, d), 4.7e-4, dtype=torch.float64, device="cuda")
+        b = torch.full((d, d), 4.7e-4, dtype=torch.float64, device="cuda")
+        for _ in range(2):
+            torch.matmul(a, b)
+        t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0e.record()
+        for _ in range(5):
+            torch.matmul(a, b)
+        t1e.record()
+        torch.cuda.synchronize()
+        cublas_tf = 2.0 * rows * d * d / (t0e.elapsed_time(t1e) / 5 * 1e-3) / 1e12
+        del a, b
+        ach = prof["solve_flops"] / (prof["solve_ms"] * 1e-3) / 1e12 if prof["solve_ms"] > 0 else 0.0
+        return {"bound": "tensor", "achieved": ach, "peak": cublas_tf, "unit": "TFLOP/s", "frac": ach / cublas_tf, "traffic": None,
+                "peak_source": "cuBLAS DGEMM (torch.float64 matmul) of the same shape, measured in this run",
+                "kernel": "dgemm_dmma_kernel (mma.sync m8n8k4 f64 → DMMA.8x8x4) inside the lock-step solver chains",
+                "flops_per_solver_pass": prof["solve_flops"] / max(1, prof["solve_launches"]),
+                "avg_pass_ms": prof["solve_ms"] / max(1, prof["solve_launches"]), "kernel_share_of_step": share, "passes": by_pass}
+    achieved = (mv["solve_bytes_sum"] / 1e9) / (mv["solve_ms_sum"] / 1e3) if mv["solve_ms_sum"] > 0 else 0.0
+    redo = prof.get("redo_units", 0)
+    if kernel_flag == 1:
+        kname = "iso_solver_kernel (generic two-sweep MAP+score solver)"
+    elif wl.d >= 4096 or kernel_flag == 2:
+        kname = "iso_stream_kernel (single-pass MAP+score, TMA ring)"
+    else:
+        kname = "iso_warp_stream_kernel (single-pass MAP+score, one warp per unit)"
+    if redo:
+        kname += f" + iso_solver_kernel re-solve of {redo} handed-back units"
+    return {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+            "traffic": measured_traffic(wl.family, wl.d, wl.nsims_total) if world == 1 else None,
+            "peak_source": peak_src, "kernel": kname, "redo_units": redo,
+            "algorithmic_bytes_per_launch": mv["solve_bytes_sum"] / n_launch, "avg_launch_ms": mv["solve_ms_sum"] / n_launch,
+            "kernel_share_of_step": share, "passes": by_pass}
+
+
 def run_b200(args):
+    import gc
+
     import torch
     import torch.distributed as dist
 
@@ -271,111 +479,61 @@ def run_b200(args):
         pool.device = local_rank
     m.build_library()
 
-    nsims_total = args.nsims * world if args.scaling == "weak" else args.nsims
     family, d = args.family, args.d
+    nsims_total = args.nsims * world if args.scaling == "weak" else args.nsims
     stream = torch.cuda.Stream()          # the library launches on this stream; events are recorded on it
     torch.cuda.set_stream(stream)
-    P = Lc = None
-    if family == "corrgauss":
-        P, Lc = corr_consts(d)
-    x_host = torch.from_numpy(observed_data(family, d, Lc)).pin_memory()
-    prior = m.FlatPrior() if family == "hiergauss" else m.NormalPrior(0, 3)
-    prob = m.SimpleMuseProblem(x_host.numpy(), family, prior, P=P, L=Lc, group=args.group, cluster=args.cluster,
-                               kernel=args.kernel, stream=stream.cuda_stream)
-    th0 = theta_start(family)
-
-    exch = {"s": 0.0, "n": 0}
-    if world > 1:       # wall time spent in the exchange step (all-gather of the score rows), for the record
-        for name in ("allgather_device_scores", "allgather_host_rows", "allgather_rows"):
-            def timed(*a, _f=getattr(pool, name), **k):
-                t = time.perf_counter()
-                r = _f(*a, **k)
-                exch["s"] += time.perf_counter() - t
-                exch["n"] += 1
-                return r
-            setattr(pool, name, timed)
-
-    def solve(seed):
-        return m.muse(prob, th0, rng=seed, nsims=nsims_total, gradz_logLike_atol=ATOL, get_covariance=True, pool=pool)
-
-    def sync_all():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    # ---- device-resident arm ("value") ---------------------------------------------------
-    # multi-rank runs get at least 5 warm-up solves: the first collectives of a fresh communicator set up their
-    # channels lazily, and one 2-GPU run timed right after 3 warm-ups was 1.8× slower than its repeats
-    # single rank: at least 3 (the measurement rules ask for W ≥ 3; the library also needs one solve to allocate, one with the
-    # profiling configuration of the timed steps and one to capture its CUDA graph of a solve)
+    # multi-rank runs get at least 5 warm-up solves (the first exchanges of a fresh communicator / peer mapping set up
+    # lazily); single rank at least 3 (the measurement rules ask for W ≥ 3; the library also needs one solve to allocate, one
+    # with the profiling configuration of the timed steps and one to capture its CUDA graph of a solve)
     warmup = max(args.warmup, 5) if world > 1 else max(args.warmup, 3)
-    res = None
-    for w in range(warmup):
-        res = solve(SIM_SEED)
-        if w == 0:
-            # per-launch event timing on from the second warm-up solve on: the library's graph of a solve (device-resident
-            # outer loop) bakes the event-record nodes in, so the timed steps must see the configuration they were warmed with
-            prob._backend.profile_reset(True)
-    be = prob._backend
+
+    wl = Workload(m, torch, dist, family, d, nsims_total, pool, stream, args, world)
     sampler = ClockSampler(local_rank)
-    # like timeit: no cyclic-GC pauses inside the timed regions (a 1–2 ms pause in one rank stalls all ranks at the
-    # next exchange; seen as outliers in the per-pass timing of the 8-rank runs)
-    import gc
+    # like timeit: no cyclic-GC pauses inside the timed regions (a 1–2 ms pause in one rank stalls all ranks at the next exchange)
     gc.collect()
     gc.disable()
-    sync_all()
-    be.profile_reset(True)
+    wl.warm(warmup)
     if rank == 0:
         sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    exch["s"], exch["n"] = 0.0, 0
-    e0.record(stream)
-    for _ in range(args.steps):
-        res = solve(SIM_SEED)
-    e1.record(stream)
-    sync_all()
-    exch_ms_per_step, exch_per_step = 1e3 * exch["s"] / args.steps, exch["n"] / args.steps
-    clocks = sampler.stop() if rank == 0 else None
-    ms = e0.elapsed_time(e1)
-    prof = be.profile()
-    passes = be.profile_passes()       # the same solver figures split by pass kind (cold, warm, …)
-    be.profile_reset(False)
-    units_local = prof["solve_units"]
+    mv = measure_value(wl, args.steps, 0)
+    be = wl.prob._backend
+    res = wl.res
+    geo = be.geometry()
 
     # ---- end-to-end arm ("e2e"): host data in, results out, draws regenerated from the seed ----
+    th0 = wl.th0
     h2d = d * 8 + th0.size * 8
-    d2h = 0
-    sync_all()
-    t0 = time.perf_counter()
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2.record(stream)
-    units_e2e = 0.0
+    d2h_box = [0]
     be.profile_reset(True)
-    for s in range(args.steps):
-        prob.set_data(x_host.numpy())            # H2D of the step's input from pinned host memory
-        r = solve(SIM_SEED + 1 + (s % 2))        # new seed ⇒ base normals regenerated on the device
-        d2h = (len(r.gs) * th0.size + len(r.Hs) * th0.size ** 2) * 8 + (len(r.history) * (nsims_total // world + 1) * 20)
-    e3.record(stream)
-    sync_all()
-    ms_e2e = max(e2.elapsed_time(e3), 1e3 * (time.perf_counter() - t0))
+
+    def e2e_step(s):
+        wl.prob.set_data(wl.x_host.numpy())         # H2D of the step's input from pinned host memory
+        r = wl.solve(SIM_SEED + 1 + (s % 2))        # new seed ⇒ base normals regenerated on the device
+        d2h_box[0] = (len(r.gs) * th0.size + len(r.Hs) * th0.size ** 2) * 8 + (len(r.history) * (nsims_total // world + 1) * 20)
+
+    blocks_e = wl.timed_blocks(args.steps, e2e_step)
     prof_e = be.profile()
     be.profile_reset(False)
-    units_e2e = prof_e["solve_units"]
-    gc.enable()
+    clocks = sampler.stop() if rank == 0 else None
+    ev_e = wl.reduce_max([max(b) for b in blocks_e])                 # per block: device events or wall clock, whichever is longer
+    ms_e2e = float(np.median(ev_e))
+    (units_e2e_all,) = wl.reduce_sum([prof_e["solve_units"]])
+    units_e2e_block = units_e2e_all / len(ev_e)
 
-    # ---- reduce over ranks -----------------------------------------------------------------
-    if world > 1:
-        t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e = t.tolist()
-        u = torch.tensor([units_local, units_e2e, prof["solve_ms"], prof["solve_bytes"], float(prof["launches"])],
-                         dtype=torch.float64, device="cuda")
-        dist.all_reduce(u, op=dist.ReduceOp.SUM)
-        units_all, units_e2e_all, solve_ms_sum, solve_bytes_sum, launches_sum = u.tolist()
-    else:
-        units_all, units_e2e_all = units_local, units_e2e
-        solve_ms_sum, solve_bytes_sum, launches_sum = prof["solve_ms"], prof["solve_bytes"], float(prof["launches"])
+    # ---- the other scaling mode as a sub-record (N > 1) ------------------------------------------------------------
+    other = None
+    if world > 1 and not args.no_other_scaling:
+        o_mode = "weak" if args.scaling == "strong" else "strong"
+        o_total = args.nsims * world if o_mode == "weak" else args.nsims
+        wl.close()
+        wl2 = Workload(m, torch, dist, family, d, o_total, pool, stream, args, world)
+        mv2 = measure_value(wl2, args.steps, warmup, min_seconds=0.3)
+        other = {"scaling": o_mode, "nsims_total": o_total, "value": mv2["units_per_block"] / (mv2["ms_block"] / 1e3), "unit": "sims/s",
+                 "ms_per_step": mv2["ms_block"] / args.steps, "blocks": mv2["blocks"],
+                 "kernel_share_of_step": mv2["solve_ms_sum"] / world / (mv2["ms_block"] * mv2["blocks"])}
+        wl2.close()
+    gc.enable()
 
     if rank == 0:
         peaks, peak_src = {}, "fallback"
@@ -386,97 +544,75 @@ def run_b200(args):
         except Exception:
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        achieved = (solve_bytes_sum / 1e9) / (solve_ms_sum / 1e3) if solve_ms_sum > 0 else 0.0
-        # traffic: dram bytes per solver launch from the committed ncu capture, if present
-        traffic = None
-        if family == "funnel" and d == D and args.nsims == NSIMS_PER_GPU:     # the capture is of this exact workload
-            try:
-                with open(os.path.join(ROOT, "profiles", "r01_solver_traffic.json")) as fh:
-                    traffic = json.load(fh).get("dram_bytes_per_launch_avg")
-            except Exception:
-                pass
-        geo = be.geometry()
-        value = units_all / (ms / 1e3)
-        cfg_name = {"funnel": "BASELINE configs[2]" if d == 65536 else ("BASELINE configs[1]" if d == 512 else "funnel, custom shape"),
-                    "hiergauss": "BASELINE configs[3]", "corrgauss": "BASELINE configs[4]"}[family]
-        tensor_roof = None
-        if family == "corrgauss":
-            # FP64 tensor roofline: denominator = cuBLAS DGEMM of the same shape measured here (MEASURED_PEAKS.json
-            # carries only bf16), numerator = 2·rows·d² per P-product ÷ CUDA-event time of the whole solver chains
-            rows = (args.nsims + 1 + 127) // 128 * 128
-            a = torch.full((rows, d), 4.7e-4, dtype=torch.float64, device="cuda")
-            b = torch.full((d, d), 4.7e-4, dtype=torch.float64, device="cuda")
-            for _ in range(2):
-                torch.matmul(a, b)
-            t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            t0e.record()
-            for _ in range(5):
-                torch.matmul(a, b)
-            t1e.record()
-            torch.cuda.synchronize()
-            cublas_tf = 2.0 * rows * d * d / (t0e.elapsed_time(t1e) / 5 * 1e-3) / 1e12
-            ach = prof["solve_flops"] / (prof["solve_ms"] * 1e-3) / 1e12 if prof["solve_ms"] > 0 else 0.0
-            tensor_roof = {"bound": "tensor", "achieved": ach, "peak": cublas_tf, "unit": "TFLOP/s", "frac": ach / cublas_tf,
-                           "traffic": None, "peak_source": "cuBLAS DGEMM (torch.float64 matmul) of the same shape, measured in this run",
-                           "kernel": "dgemm_dmma_kernel (mma.sync m8n8k4 f64 → DMMA.8x8x4) inside the lock-step solver chains",
-                           "flops_per_solver_pass": prof["solve_flops"] / max(1, prof["solve_launches"]),
-                           "avg_pass_ms": prof["solve_ms"] / max(1, prof["solve_launches"]),
-                           "kernel_share_of_step": prof["solve_ms"] / ms}
+        value = mv["units_per_block"] / (mv["ms_block"] / 1e3)
         line = {
             "metric": "MUSE sims/sec (MAP+score)", "value": value, "unit": "sims/s", "n_gpus": world,
-            "steps": args.steps, "warmup": warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "steps": args.steps, "warmup": warmup, "ms_per_step": mv["ms_block"] / args.steps, "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {
-                "workload": f"{family} d={d} nsims={args.nsims}{'/GPU' if args.scaling == 'weak' else ' total'} "
-                            f"full solve θ̂/J/H, θ₀={th0.tolist()}, atol={ATOL} ({cfg_name})",
-                "nsims_total": nsims_total, "outer_iterations": len(res.history),
-                "units_per_step": units_all / args.steps, "l2": "inputs_larger_than_l2 (ξ,ν: %.2f GB per GPU)" % (2 * args.nsims * d * 8 / 1e9 if args.scaling == "weak" else 2 * nsims_total / world * d * 8 / 1e9),
-                "exchange": {"allgathers_per_step": exch_per_step, "wall_ms_per_step_rank0": exch_ms_per_step,
-                             "bytes_per_allgather": nsims_total * th0.size * 8},
-                "solver_geometry": geo, "theta_hat": [float(t) for t in res.theta],
-                "sigma": [float(s) for s in np.sqrt(np.diag(res.Sigma))],
-            },
+            "config": bench_config(args, world),
+            "timing": {"blocks": mv["blocks"], "steps_per_block": args.steps, "block_ms": [round(b, 4) for b in mv["block_ms_all"]],
+                       "statistic": "median block, max over ranks per block; every block is bracketed by barrier + synchronize and "
+                                    "timed with CUDA events on the launch stream"},
+            "detail": {"outer_iterations": len(res.history), "units_per_step": mv["units_per_block"] / args.steps,
+                       "solver_geometry": geo,
+                       "theta_hat": [float(t) for t in res.theta], "sigma": [float(s) for s in np.sqrt(np.diag(res.Sigma))],
+                       "exchange": None if world == 1 else os.environ.get("MUSE_EXCHANGE", "auto")},
             "clocks": clocks,
-            "e2e": {"value": units_e2e_all / (ms_e2e / 1e3), "unit": "sims/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
+            "e2e": {"value": units_e2e_block / (ms_e2e / 1e3), "unit": "sims/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h_box[0], "ms_per_step": ms_e2e / args.steps, "blocks": len(ev_e),
                     "note": "draws regenerated on device from the seed each step (reference draws inside sample_x_z)"},
-            "gpu_launches": int(launches_sum),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
-                         "kernel": ("iso_stream_kernel (single-pass MAP+score; + empty re-solve launch)" if prof.get("redo_units", 0) == 0 and d >= 4096 and args.kernel != 1 else "iso_solver_kernel (generic two-sweep MAP+score solver)"),
-                         "redo_units": prof.get("redo_units", 0),
-                         "algorithmic_bytes_per_launch": solve_bytes_sum / max(1, prof["solve_launches"] * world),
-                         "avg_launch_ms": solve_ms_sum / max(1, prof["solve_launches"] * world),
-                         "kernel_share_of_step": solve_ms_sum / world / ms},
+            "gpu_launches": int(round(mv["launches_per_block"])),
+            "roofline": roofline_of(wl, mv, hbm_peak, peak_src, args.steps, args.kernel) if other is None else None,
         }
-        # per pass kind on rank 0 (CUDA events over each launch chain): average launch time, units and, for the HBM-bound
-        # families, algorithmic GB/s — "grad-eval HBM GB/s vs peak" for the cold and the warm pass separately
-        by_pass = {}
-        for kind, v in passes.items():
-            if v["launches"]:
-                e = {"launches_per_step": v["launches"] / args.steps, "units_per_launch": v["units"] / v["launches"],
-                     "avg_launch_ms": v["ms"] / v["launches"], "sims_per_s": v["units"] / (v["ms"] * 1e-3) if v["ms"] > 0 else None}
-                if v["bytes"] > 0 and v["ms"] > 0:
-                    e["algorithmic_gbs"] = v["bytes"] / 1e9 / (v["ms"] * 1e-3)
-                    e["frac_of_hbm_peak"] = e["algorithmic_gbs"] / hbm_peak
-                by_pass[kind] = e
-        line["roofline"]["passes"] = by_pass
-        if tensor_roof is not None:
-            tensor_roof["passes"] = by_pass
-            line["roofline"] = tensor_roof
-            line["config"]["l2"] = "inputs_larger_than_l2 (Σ₀⁻¹ 134 MB + batch arrays ≥ 268 MB each at d=4096, nsims=8192)"
+        if other is not None:
+            line["other_scaling"] = other
+            # the primary workload's handle was closed for the sub-record: its roofline comes from the saved profile
+            line["roofline"] = roofline_of(wl, mv, hbm_peak, peak_src, args.steps, args.kernel)
         if world == 1 and not args.no_cpu_baseline:
             nsims_cpu = cpu_sample_nsims(args)
             cpu_solve_rate(family, d, nsims_cpu, 0)                       # warm-up (page-in of the host draws)
             rate, units, secs, threads = cpu_solve_rate(family, d, nsims_cpu, 0, reps=3)
+            n1 = max(16, min(nsims_cpu, 128))
+            rate1, units1, secs1, _ = cpu_solve_rate(family, d, n1, 1)
             line["cpu_baseline"] = {
                 "value": rate, "unit": "sims/s", "cores": threads, "kind": "port",
                 "sample": f"full solve (θ̂,J,H) on nsims={nsims_cpu} of the same shape, {units} units in {secs:.2f}s; "
-                          "oracle C port with analytic gradients (faster than the Julia reference's AD path)"}
+                          "oracle C port with analytic gradients (faster than the Julia reference's AD path)",
+                "value_1thread": rate1, "sample_1thread": f"the same on 1 thread (the reference's default pool is a serial map), nsims={n1}: {units1} units in {secs1:.2f}s"}
+        if world == 1 and not args.no_extra_configs and (family, d, args.nsims) == ("funnel", D, NSIMS):
+            if other is None:
+                wl.close()
+            line["configs"] = extra_configs(m, torch, dist, pool, stream, args, hbm_peak, peak_src)
         _emit(line)
-    prob.close()
+    try:
+        wl.close()
+    except Exception:
+        pass
     if world > 1:
         dist.destroy_process_group()
+
+
+def extra_configs(m, torch, dist, pool, stream, args, hbm_peak, peak_src):
+    """The other BASELINE configs through the same code, one record each (single GPU): C1, C2 (latency path), C4, C5."""
+    import copy
+    out = []
+    for name, family, d, nsims, steps, secs in (("C1", "funnel", 512, 100, 100, 0.3), ("C2", "funnel", 512, 10000, 50, 0.3),
+                                                ("C4", "hiergauss", 100000, 4096, 5, 0.2), ("C5", "corrgauss", 4096, 8192, 2, 0.0)):
+        rec = {"name": name, "workload": workload_name(family, d, nsims, "weak", 1), "steps": steps}
+        try:
+            a = copy.copy(args)
+            a.family, a.d, a.nsims, a.kernel, a.group, a.cluster = family, d, nsims, 0, 0, 0
+            wl = Workload(m, torch, dist, family, d, nsims, pool, stream, a, 1)
+            mv = measure_value(wl, steps, 3, min_seconds=secs)
+            rec.update(value=mv["units_per_block"] / (mv["ms_block"] / 1e3), unit="sims/s", ms_per_step=mv["ms_block"] / steps,
+                       blocks=mv["blocks"], outer_iterations=len(wl.res.history), units_per_step=mv["units_per_block"] / steps,
+                       gpu_launches=int(round(mv["launches_per_block"])),
+                       roofline=roofline_of(wl, mv, hbm_peak, peak_src, steps, 0))
+            wl.close()
+        except Exception as e:      # an extra config must never take the headline line down with it
+            rec["error"] = f"{type(e).__name__}: {e}"
+        out.append(rec)
+    return out
 
 
 def main():
