@@ -192,6 +192,17 @@ int  muse_b200_comm_destroy(muse_handle* h);
 int  muse_b200_allgather_scores(muse_handle* h, int32_t first_row, const int32_t* counts /* nranks */, double* out_host);
 int  muse_b200_allgather_rows(muse_handle* h, const double* local_host, int32_t ncol, const int32_t* counts, double* out_host);
 
+/* The same exchange step WITHOUT a collective launch: with these buffers in place muse_b200_muse_solve runs the whole solve in
+ * one cooperative kernel per rank, whose CTA 0 stores this rank's score rows (and get_H!'s finite-difference scores) straight
+ * into every peer's gathered buffer over NVLink (peer-mapped device memory, CUDA IPC) and raises a flag there; the θ update
+ * then reads the gathered rows locally.  p2p_alloc creates this rank's region — 2 parities × 4 blocks of block_doubles doubles,
+ * block_doubles ≥ nranks × max(sims per rank × ntheta, H sims per rank × 2·ntheta²) — and returns its 64-byte IPC handle; the host
+ * distributes the handles (like the NCCL id) and every rank calls p2p_connect with all of them in rank order.  Collective:
+ * every rank of the communicator must make the same calls.  Results are bit-identical to the NCCL path and to one GPU. */
+int  muse_b200_p2p_alloc(muse_handle* h, int32_t nranks, int32_t rank, int64_t block_doubles, uint8_t* handle_out /* 64 bytes */);
+int  muse_b200_p2p_connect(muse_handle* h, const uint8_t* handles /* nranks × 64 bytes */);
+int  muse_b200_p2p_info(muse_handle* h, int64_t* block_doubles, int32_t* ready);
+
 /* Finite-difference branch of get_H! (src/muse.jl:417-442 + pjacobian src/util.jl:9-26 with
  * fdm = central_fdm(3,1) and an explicit step): one fiducial MAP of the master-stream draw from
  * zero(z) (the reference computes nsims_H identical copies, :417-423), then for the first

@@ -92,6 +92,9 @@ SIGNATURES = {
     "muse_b200_comm_destroy": (C.c_int, [C.c_void_p]),
     "muse_b200_allgather_scores": (C.c_int, [C.c_void_p, C.c_int32, c_int32_p, c_double_p]),
     "muse_b200_allgather_rows": (C.c_int, [C.c_void_p, c_double_p, C.c_int32, c_int32_p, c_double_p]),
+    "muse_b200_p2p_alloc": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.POINTER(C.c_uint8)]),
+    "muse_b200_p2p_connect": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint8)]),
+    "muse_b200_p2p_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), c_int32_p]),
     "muse_b200_muse_iterate": (C.c_int, [C.c_void_p, c_double_p, C.c_int32, c_int32_p, C.c_int32, C.c_double, C.c_double,
                                          C.c_double, C.c_int32, c_double_p, c_double_p, C.POINTER(muse_iterate_out)]),
     "muse_b200_muse_covariance": (C.c_int, [C.c_void_p, c_double_p, c_double_p, C.c_int32, C.c_int32, c_int32_p, C.c_double,

@@ -179,6 +179,23 @@ class B200Backend:
         self._check(self._lib.muse_b200_comm_init(self._h, int(nranks), int(rank), buf))
         self.comm = (int(nranks), int(rank))
 
+    def p2p_alloc(self, nranks: int, rank: int, block_doubles: int) -> bytes:
+        """This rank's peer-exchange region (include/muse_b200.h: muse_b200_p2p_alloc); returns its 64-byte IPC handle."""
+        buf = (C.c_uint8 * 64)()
+        self._check(self._lib.muse_b200_p2p_alloc(self._h, int(nranks), int(rank), int(block_doubles), buf))
+        return bytes(buf)
+
+    def p2p_connect(self, handles):
+        """Map the peers' regions: ``handles`` = the 64-byte handles of all ranks in rank order."""
+        blob = b"".join(handles)
+        buf = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+        self._check(self._lib.muse_b200_p2p_connect(self._h, buf))
+
+    def p2p_info(self):
+        blk, ready = C.c_int64(), C.c_int32()
+        self._check(self._lib.muse_b200_p2p_info(self._h, C.byref(blk), C.byref(ready)))
+        return int(blk.value), bool(ready.value)
+
     def allgather_scores(self, first_row: int, counts):
         counts = np.ascontiguousarray(counts, dtype=np.int32)
         out = np.empty((int(counts.sum()), self.ntheta))

@@ -153,6 +153,9 @@ static void fill_common(muse_handle* h, SolveLaunch& L) {
     L.dbg = h->dbg;
 }
 
+int muse_ensure_outputs(muse_handle* h, int items) { return ensure_outputs(h, items); }
+void muse_fill_common(muse_handle* h, SolveLaunch& L) { fill_common(h, L); }
+
 static int launch_solver(muse_handle* h, const SolveLaunch& L, double bytes) {
     muse_handle::Rec r{};
     // inside a stream capture (device-resident loop, muse_outer.cu) the event records become external event-record nodes of
@@ -369,6 +372,7 @@ int muse_b200_destroy(muse_handle* h) {
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (auto& r : h->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    muse_p2p_release(h);
     muse_comm_release(h);
     muse_outer_release(h);
     muse_corr_destroy(h);
@@ -755,6 +759,7 @@ static int profile_drain(muse_handle* h) {
             const int k = r.kind >= 0 && r.kind < MUSE_PASS_KINDS ? r.kind : MUSE_PASS_COLD;
             h->acc_pass.launches[k] += 1; h->acc_pass.ms[k] += ms; h->acc_pass.units[k] += r.units; h->acc_pass.bytes[k] += r.bytes;
         }
+        else if (r.cls == 3) { h->acc.solve_ms += ms; h->acc.solve_units += r.units; h->acc.solve_bytes += r.bytes; }   // a whole solve in one launch
         else if (r.cls == 1) h->acc.draw_ms += ms;
         else { h->acc.other_ms += ms; }
         cudaEventDestroy(r.a);

@@ -71,7 +71,89 @@ void muse_comm_release(muse_handle* h) {
     h->comm_cap = 0;
 }
 
+// ---- exchange through peer-mapped memory -----------------------------------------------------------------------------
+// solve_persist_kernel (muse_iso_stream.cu) performs the exchange step itself: CTA 0 of every rank stores its score rows into
+// every peer's gathered-score buffer over NVLink and raises a flag there.  Here: the buffers.  Every rank allocates one region
+//   [ flags: 16 × 2 u64 | 2 parities × (kOuterSlots + 1) blocks of `block_doubles` doubles ]
+// exports it as a CUDA IPC handle (64 bytes, distributed by the host like the NCCL id), and maps the regions of its peers.
+// Parity = solve number mod 2: a rank that is already in the next solve never overwrites rows a slower peer has not read yet
+// (it cannot get two solves ahead — every pass needs every rank).  Flags only grow (epoch = 8 × solve number + phase).
+constexpr size_t kP2pFlagBytes = 256;
+
+void muse_p2p_release(muse_handle* h) {
+    for (int q = 0; q < 16; ++q) {
+        if (h->p2p_peer[q] && h->p2p_peer[q] != h->p2p_region) cudaIpcCloseMemHandle(h->p2p_peer[q]);
+        h->p2p_peer[q] = nullptr;
+    }
+    cudaFree(h->p2p_region);
+    cudaFreeHost(h->p2p_host);
+    h->p2p_region = nullptr;
+    h->p2p_host = nullptr;
+    h->p2p_block = 0;
+    h->p2p_ready = false;
+    cudaGetLastError();
+}
+
 extern "C" {
+
+int muse_b200_p2p_alloc(muse_handle* h, int32_t nranks, int32_t rank, int64_t block_doubles, uint8_t* handle_out /* 64 bytes */) {
+    if (!h || !handle_out || nranks < 2 || nranks > 16 || rank < 0 || rank >= nranks || block_doubles < 1) return MUSE_EINVAL;
+    if (cudaSetDevice(h->cfg.device) != cudaSuccess) { h->err = "cudaSetDevice"; return MUSE_ECUDA; }
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    muse_p2p_release(h);
+    const size_t blocks = 2 * (size_t)(kOuterSlots + 1);
+    const size_t bytes = kP2pFlagBytes + blocks * (size_t)block_doubles * sizeof(double);
+    if (cudaMalloc(&h->p2p_region, bytes) != cudaSuccess || cudaMemset(h->p2p_region, 0, bytes) != cudaSuccess ||
+        cudaMallocHost(&h->p2p_host, (size_t)(kOuterSlots + 1) * (size_t)block_doubles * sizeof(double)) != cudaSuccess) {
+        cudaGetLastError();
+        muse_p2p_release(h);
+        h->err = "allocation of the peer exchange region failed";
+        return MUSE_ENOMEM;
+    }
+    cudaIpcMemHandle_t mh;
+    static_assert(sizeof(mh) == 64, "cudaIpcMemHandle_t size");
+    const cudaError_t e = cudaIpcGetMemHandle(&mh, h->p2p_region);
+    if (e != cudaSuccess) {
+        h->err = std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e);
+        cudaGetLastError();
+        muse_p2p_release(h);
+        return MUSE_ECUDA;
+    }
+    std::memcpy(handle_out, &mh, sizeof(mh));
+    h->p2p_block = block_doubles;
+    h->p2p_nranks = nranks;
+    h->p2p_rank = rank;
+    return MUSE_OK;
+}
+
+int muse_b200_p2p_connect(muse_handle* h, const uint8_t* handles /* nranks × 64 bytes, rank order */) {
+    if (!h || !handles) return MUSE_EINVAL;
+    if (!h->p2p_region) { h->err = "p2p_connect before p2p_alloc"; return MUSE_ESTATE; }
+    if (cudaSetDevice(h->cfg.device) != cudaSuccess) { h->err = "cudaSetDevice"; return MUSE_ECUDA; }
+    for (int q = 0; q < h->p2p_nranks; ++q) {
+        if (q == h->p2p_rank) { h->p2p_peer[q] = h->p2p_region; continue; }
+        cudaIpcMemHandle_t mh;
+        std::memcpy(&mh, handles + (size_t)q * 64, sizeof(mh));
+        void* ptr = nullptr;
+        const cudaError_t e = cudaIpcOpenMemHandle(&ptr, mh, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            h->err = std::string("cudaIpcOpenMemHandle (rank ") + std::to_string(q) + "): " + cudaGetErrorString(e);
+            cudaGetLastError();
+            muse_p2p_release(h);
+            return MUSE_ECUDA;
+        }
+        h->p2p_peer[q] = static_cast<unsigned char*>(ptr);
+    }
+    h->p2p_ready = true;
+    return MUSE_OK;
+}
+
+int muse_b200_p2p_info(muse_handle* h, int64_t* block_doubles, int32_t* ready) {
+    if (!h) return MUSE_EINVAL;
+    if (block_doubles) *block_doubles = h->p2p_block;
+    if (ready) *ready = h->p2p_ready ? 1 : 0;
+    return MUSE_OK;
+}
 
 int muse_b200_comm_unique_id(uint8_t* out /* 128 bytes */) {
     if (!out) return MUSE_EINVAL;

@@ -71,7 +71,7 @@ bool invert_small(double* a, int n) {
 // J from the scores, exchange of the per-sim Jacobians, H and Σ — the host arithmetic of the covariance stage, shared by
 // muse_b200_muse_covariance (below) and the device-resident loop (muse_outer.cu).  out->step is left to the caller.
 int muse_cov_finish(muse_handle* h, const double* theta, const double* gs, int nsims_total, int nsims_h_total, const int32_t* counts_h,
-                    const double* Hs_local, int mine, const double* prior_sigma, muse_cov_out* out) {
+                    const double* Hs_local, int mine, const double* prior_sigma, muse_cov_out* out, const double* Hs_all) {
     (void)theta;
     const int nt = h->cfg.ntheta;
     const bool multi = h->comm != nullptr && h->comm_nranks > 1;
@@ -83,7 +83,9 @@ int muse_cov_finish(muse_handle* h, const double* theta, const double* gs, int n
             const double q = sum8(nsims_total, [&](int k) { return (gs[(size_t)k * nt + a] - mean[a]) * (gs[(size_t)k * nt + b] - mean[b]); });
             out->J[a * nt + b] = out->J[b * nt + a] = q / (nsims_total - 1);
         }
-    if (multi) {
+    if (Hs_all) {            // already gathered (peer exchange of solve_persist_kernel)
+        std::memcpy(out->Hs, Hs_all, (size_t)nsims_h_total * nt * nt * sizeof(double));
+    } else if (multi) {
         const int rc = muse_b200_allgather_rows(h, Hs_local, nt * nt, counts_h, out->Hs);
         if (rc != MUSE_OK) return rc;
     } else {
@@ -135,7 +137,7 @@ extern "C" int muse_b200_muse_covariance(muse_handle* h, const double* theta, co
     if (rc != MUSE_OK) return rc;
     for (size_t i = 0; i < (size_t)mine * nt * 2; ++i)
         if (status[i] == MUSE_STATUS_NONFINITE) { h->err = "get_H!: MAP solution failed with a non-finite objective"; return MUSE_ESTATE; }
-    return muse_cov_finish(h, theta, gs, nsims_total, nsims_h_total, counts_h, local.data(), mine, prior_sigma, out);
+    return muse_cov_finish(h, theta, gs, nsims_total, nsims_h_total, counts_h, local.data(), mine, prior_sigma, out, nullptr);
 }
 
 extern "C" int muse_b200_muse_iterate(muse_handle* h, const double* theta0, int32_t nsims_total, const int32_t* counts,

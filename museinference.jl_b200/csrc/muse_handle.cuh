@@ -31,11 +31,13 @@ struct OuterRow {                                        // history row of one i
 };
 struct OuterState {
     // header: uploaded from pinned staging at the start of a solve (one copy initialises everything below)
-    int n_iter, done, error, pad;
+    int n_iter, done, error;
+    int abort;                                           // solve_persist_kernel gave up (a unit left the fast path): re-run on the chain of launches
     double theta[MUSE_MAX_NTHETA];                       // θ after the last update (= θ of the next pass)
     double step[MUSE_MAX_NTHETA];                        // 0.1 ./ std(gs) of the covariance stage
     int ctr[16];                                         // per launch chain of a chunk: [2k] hand-back count, [2k+1] streaming work
                                                          // counter (k = 0..4); [12] state of the fiducial ẑ — zero at chunk start
+    long long stamp[16];                                 // solve_persist_kernel: globaltimer stamps of CTA 0 (muse_outer_dev.cuh)
     muse::DynConsts dyn_first;                           // constants of pass 1 at θ₀ (host libm, like the other drivers)
     // history
     OuterRow row[kOuterMaxIter];
@@ -105,6 +107,20 @@ struct muse_handle {
     std::vector<unsigned char> outer_key, outer_warm_key;   // parameters baked into the graph / of the last eager solve
     int64_t cap_launches = 0, cap_solve_launches = 0;    // kernel launches / solver passes inside the graph
 
+    // the whole solve in one cooperative launch (solve_persist_kernel, muse_iso_stream.cu)
+    void* persist_ctl = nullptr;                         // muse::PersistCtl, device, zero between launches
+    int persist_grid = -1, persist_threads = 0;          // −1: not queried yet; 0: unavailable
+    std::vector<unsigned char> persist_off_key;          // parameters with which the launch gave up (hand-backs): straight to the chain
+
+    // exchange through peer-mapped memory (muse_comm.cu: muse_b200_p2p_*): this rank's region and the peers' mappings of theirs
+    unsigned char* p2p_region = nullptr;                 // [flags 256 B | 2 parities × (kOuterSlots + 1) blocks of p2p_block doubles]
+    unsigned char* p2p_peer[16] = {};                    // region of rank q as mapped here ([rank] = p2p_region)
+    double* p2p_host = nullptr;                          // pinned mirror of one parity's blocks
+    long long p2p_block = 0;
+    int p2p_nranks = 0, p2p_rank = 0;
+    bool p2p_ready = false;
+    unsigned long long p2p_seq = 0;                      // persistent multi-GPU solves so far (flag epochs, buffer parity)
+
     // exchange step (muse_comm.cu): NCCL communicator and staging buffers
     void* comm = nullptr;
     int comm_nranks = 0, comm_rank = 0, comm_cap = 0;
@@ -141,6 +157,9 @@ void muse_outer_release(muse_handle* h);
 extern "C" int  muse_comm_allgather_dev_enqueue(muse_handle* h, const double* src_dev, const int* status_dev, int ncol, const int32_t* counts, size_t* need_out);
 
 void muse_comm_release(muse_handle* h);
+void muse_p2p_release(muse_handle* h);
+int  muse_ensure_outputs(muse_handle* h, int items);
+void muse_fill_common(muse_handle* h, muse::SolveLaunch& L);
 extern "C" void muse_comm_unpack(muse_handle* h, int ncol, const int32_t* counts, double* out_host);
 extern "C" int  muse_comm_allgather_scores_enqueue(muse_handle* h, int first_row, const int32_t* counts);
 

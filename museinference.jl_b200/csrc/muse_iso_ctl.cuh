@@ -116,6 +116,10 @@ __device__ __forceinline__ void st2_hint(double* p, int i, double2 v, uint64_t p
                  : "l"(p + 2 * (size_t)i), "d"(v.x), "d"(v.y), "l"(pol));
 }
 
+// a unit's ẑ-state cell (or the fiducial ẑ's): written by an earlier phase of the SAME launch in solve_persist_kernel, so it
+// is read at the L2, never from a stale L1 line
+__device__ __forceinline__ int ld_state(const int* p) { return __ldcg(p); }
+
 // [host-test:begin ctl-b]
 // slow-path vector operations (only reached when a unit needs more than one L-BFGS iteration)
 template <class G, class Iter>
@@ -666,7 +670,7 @@ struct Controller {
         int* zs = L.zstate ? L.zstate + row : nullptr;
         switch (cur.start_kind) {
             case kStartOwn: {
-                const int st = *zs;
+                const int st = ld_state(zs);
                 cur.zcur = st == kZZero ? nullptr : (st == kZA ? zA : zB);
                 cur.zalt = st == kZA ? zB : zA;
                 zother = st == kZA ? zA : zB;
@@ -686,7 +690,7 @@ struct Controller {
 
     __device__ __forceinline__ const double* resolve_zshared() const {
         if (L.zshared_state) {       // shared start = result of an earlier launch (fiducial ẑ)
-            const int st = *L.zshared_state;
+            const int st = ld_state(L.zshared_state);
             return st == kZA ? L.zsharedA : (st == kZB ? L.zsharedB : nullptr);
         }
         return L.zshared;

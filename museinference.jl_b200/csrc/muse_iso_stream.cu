@@ -42,6 +42,7 @@
 // Every reduction is a fixed tree (thread → warp butterfly → warps in order → segments in order),
 // so results do not depend on scheduling, grid size or how sims are sharded over GPUs.
 #include "muse_iso_ctl.cuh"
+#include "muse_outer_dev.cuh"
 
 namespace muse {
 
@@ -100,6 +101,10 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
         ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
         : "memory");
 }
+__device__ __forceinline__ void mbar_inval(uint64_t* bar) {
+    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ double2 lds2(const double* p) { return *reinterpret_cast<const double2*>(p); }
 
@@ -339,18 +344,22 @@ struct WarpCtx {
 };
 // [host-test:end publish]
 
-__global__ void __launch_bounds__(kThreads, 1)
-iso_stream_kernel(const __grid_constant__ SolveLaunch L) {
-    if (launch_skipped(L)) return;      // device-resident outer loop: this pass is not needed (uniform over the grid)
-    extern __shared__ __align__(128) unsigned char dyn[];
-    __shared__ Shared sh;
-    double* const ring = reinterpret_cast<double*>(dyn);
+// One streaming pass over the launch's units by the three roles of one CTA (file comment).  The body of iso_stream_kernel, and
+// of every phase of solve_persist_kernel (PERSIST: the barriers of the previous phase are invalidated and set up again, the
+// proxies are fenced around the phase — ẑ written with ordinary stores by one phase is read by bulk copies in the next —
+// and the CTA ends the phase together).
+template <bool PERSIST>
+__device__ __forceinline__ void stream_pass(const SolveLaunch& L, Shared& sh, double* const ring, bool reinit) {
     const int rows = L.zrows ? 3 : 2;
     const int stages = L.stream_stages;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < stages; ++s) {
+        if (PERSIST && reinit) {
+            for (int s = 0; s < kMaxStages; ++s) { mbar_inval(&sh.full[s]); mbar_inval(&sh.empty[s]); }
+            for (int s = 0; s < 2; ++s) { mbar_inval(&sh.part_full[s]); mbar_inval(&sh.part_empty[s]); }
+        }
+        for (int s = 0; s < (PERSIST ? kMaxStages : stages); ++s) {
             mbar_init(&sh.full[s], 1);
             mbar_init(&sh.empty[s], kNCW);
         }
@@ -360,6 +369,7 @@ iso_stream_kernel(const __grid_constant__ SolveLaunch L) {
         }
         fence_mbar_init();
     }
+    if (PERSIST) fence_proxy_async();       // what earlier phases stored (any CTA, ordered by the phase barrier) → this phase's bulk copies
     __syncthreads();
 
     // diagnostics (muse_b200_debug_timeline): per CTA [start ns, end ns, smid, producer done ns, finisher done ns, consumers done ns]
@@ -537,10 +547,22 @@ iso_stream_kernel(const __grid_constant__ SolveLaunch L) {
         }
         if (dbg && ct == 0) dbg[5] = now_ns();
     }
+    if (PERSIST) {
+        fence_proxy_async();
+        __syncthreads();
+    }
     if (dbg) {
         __syncthreads();
         if (threadIdx.x == 0) dbg[1] = now_ns();
     }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+iso_stream_kernel(const __grid_constant__ SolveLaunch L) {
+    if (launch_skipped(L)) return;      // device-resident outer loop: this pass is not needed (uniform over the grid)
+    extern __shared__ __align__(128) unsigned char dyn[];
+    __shared__ Shared sh;
+    stream_pass<false>(L, sh, reinterpret_cast<double*>(dyn), false);
 }
 
 // ---- small latent dimension: one warp per unit, same single pass, straight from global memory ---------------------
@@ -583,9 +605,9 @@ __device__ __forceinline__ void warp_unit(const ItemDesc& it, const double* ra, 
     }
 }
 
-__global__ void __launch_bounds__(kWarpCta, 2)
-iso_warp_stream_kernel(const __grid_constant__ SolveLaunch L) {
-    if (launch_skipped(L)) return;
+// the launch's units dealt round-robin to the grid's warps (body of iso_warp_stream_kernel and of every phase of
+// solve_persist_kernel's small-d form)
+__device__ __forceinline__ void warp_pass(const SolveLaunch& L) {
     const int lane = threadIdx.x & 31;
     const int gw = (blockIdx.x * kWarpCta + threadIdx.x) >> 5, nw = (gridDim.x * kWarpCta) >> 5;
     const IsoEval ev = launch_ev(L);
@@ -633,6 +655,319 @@ iso_warp_stream_kernel(const __grid_constant__ SolveLaunch L) {
     }
 }
 
+__global__ void __launch_bounds__(kWarpCta, 2)
+iso_warp_stream_kernel(const __grid_constant__ SolveLaunch L) {
+    if (launch_skipped(L)) return;
+    warp_pass(L);
+}
+
+// ---- the whole solve in ONE launch ------------------------------------------------------------------------------------
+// solve_persist_kernel runs what muse_b200_muse_solve otherwise enqueues as a chain of ≈ 13 kernels and 2 copies (muse_outer.cu):
+// the passes of muse!'s first iterations (/root/reference/src/muse.jl:159-236), the θ update between them, and — once the
+// loop has ended — get_H!'s fiducial solve and finite-difference sims (:411-433).  A cooperative launch (every CTA resident);
+// a phase = one streaming pass by all CTAs (stream_pass / warp_pass above, unchanged per-unit arithmetic); at its end every CTA
+// arrives on a counter, CTA 0 waits for all of them, runs the arithmetic the host loop does between two passes
+// (theta_step_body / cov_prep_body of muse_outer_dev.cuh — the code and reduction tree of theta_step_kernel, hence the same θ
+// bit for bit), publishes the constants of the next phase and releases a flag the other CTAs spin on.  With several GPUs CTA 0
+// also performs the exchange step: it stores this rank's score rows straight into every peer's gathered-score buffer over
+// NVLink (peer-mapped memory, muse_comm.cu) and raises a flag there; no collective launch, no staging copy.
+// A unit that leaves the fast path (hand-back) makes the launch give up: state `abort`, the host re-runs the solve on the chain
+// of launches, whose generic kernel handles such units.  Every spin is bounded (kSpinTimeoutNs): a rank that never shows up
+// ends in an error, not in a hung GPU.
+constexpr long long kSpinTimeoutNs = 4000000000LL;
+
+__device__ __forceinline__ long long gtime_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return (long long)t; }
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned* p, unsigned v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+struct PersistShared {
+    SolveLaunch L;                    // the phase in flight
+    DynConsts dyn[2];                 // its θ-dependent constants ([1]: FD sims)
+    double red[kMaxTheta][32];        // CTA 0: scratch of the reduction tree
+    int bad;
+    int done, error, abort, timeout;  // CTA 0's message after the phase, as every CTA has read it
+    int l_abort;                      // CTA 0: this phase handed units back (here or on a peer)
+};
+static_assert(sizeof(DynConsts) % 8 == 0, "DynConsts is copied in 8-byte words");
+
+// ps.L ← the launch description of phase ph: what muse_pass_enqueue / fd_launch (muse_api.cu) fill in on the host
+__device__ void phase_launch(const PersistParams& P, int ph, PersistShared& ps) {
+    SolveLaunch& L = ps.L;
+    L = P.base;
+    PersistCtl* const ctl = P.ctl;
+    L.redo_count = &ctl->redo[ph];
+    L.work_next = &ctl->work[ph];
+    L.redo_total = &ctl->redo_sink;
+    const OutPtrs* ob;
+    if (ph < kOuterSlots) {              // pass ph + 1 of muse!: data + local sims, start zeros / user z₀ on the first, previous ẑ afterwards
+        L.nitems = P.step.units_local;
+        L.mode = 0;
+        L.include_data = 1;
+        L.first_sim = 0;
+        L.start_kind = ph == 0 ? P.first_kind : (int)kStartOwn;
+        L.zshared = P.z0user;
+        L.dyn = &ps.dyn[0];
+        ob = &P.slot[ph];
+    } else if (ph == kPhaseFid) {        // fiducial MAP of the master stream's draw from zero(z)   — src/muse.jl:417-423
+        L.nitems = 1;
+        L.mode = 2;
+        L.start_kind = kStartZero;
+        L.zA = P.zfidA;
+        L.zB = P.zfidB;
+        L.zstate = &ctl->zfid_state;
+        L.dyn = &ps.dyn[0];
+        ob = &P.fd;
+    } else {                             // virtual sims at the 2·nθ sample points, MAP + score at θ̂ from the fiducial start — :426-433
+        L.nitems = P.nh_mine * P.step.nt * 2;
+        L.mode = 1;
+        L.start_kind = kStartShared;
+        L.zshared = nullptr;
+        L.zshared_state = &ctl->zfid_state;
+        L.zsharedA = P.zfidA;
+        L.zsharedB = P.zfidB;
+        L.xi = P.xi_fd;
+        L.nu = P.nu_fd;
+        L.zA = L.zB = nullptr;
+        L.zstate = nullptr;
+        L.discard_z = 1;
+        L.dyn = &ps.dyn[1];
+        ob = &P.fd;
+    }
+    L.g_out = ob->g; L.iters_out = ob->iters; L.fg_out = ob->fg;
+    L.gnorm_out = ob->gnorm; L.f_out = ob->f; L.status_out = ob->status;
+    L.zrows = (L.start_kind == kStartOwn || L.start_kind == kStartShared || L.start_kind == kStartSharedKeep) ? 1 : 0;
+    L.stream_stages = L.zrows ? 4 : 6;
+}
+
+template <int STREAM>
+__device__ __forceinline__ void run_phase(const SolveLaunch& L, bool reinit) {
+    if constexpr (STREAM == 1) {
+        extern __shared__ __align__(128) unsigned char dynsm[];
+        __shared__ Shared sh;
+        stream_pass<true>(L, sh, reinterpret_cast<double*>(dynsm), reinit);
+    } else {
+        warp_pass(L);
+        __syncthreads();
+    }
+}
+
+// thread 0 of CTA 0: until every CTA has arrived at the end of phase ph
+__device__ void wait_arrivals(const PersistParams& P, int ph, PersistShared& ps) {
+    const long long t0 = gtime_ns();
+    while (ld_acquire_gpu(&P.ctl->arrive[ph]) < (int)gridDim.x)
+        if (gtime_ns() - t0 > kSpinTimeoutNs) { ps.timeout = 1; break; }
+    if (__ldcg(&P.ctl->redo[ph]) > 0) ps.l_abort = 1;
+}
+
+// The exchange step by CTA 0 (all its threads): `n` doubles of this rank (rows src, one status per `per_row` doubles; failed units
+// go out as NaN so that every rank takes the same error decision) → slot `rank` of dst[q] on EVERY rank q, then flag `ep`
+// there; then wait for the flags of all peers.  An abort bit rides on the flag.
+__device__ void exchange_rows(const PersistParams& P, PersistShared& ps, const double* src, const int* status, int n, int per_row,
+                              double* const* dst, long long need, unsigned long long ep) {
+    const XchgParams& X = P.x;
+    const int tid = threadIdx.x;
+    for (int e = tid; e < n; e += blockDim.x) {
+        const bool bad = __ldcg(status + e / per_row) == MUSE_STATUS_NONFINITE;
+        const double v = bad ? __longlong_as_double(0x7ff8000000000000LL) : __ldcg(src + e);
+        for (int q = 0; q < X.nranks; ++q) dst[q][(size_t)X.rank * need + e] = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < X.nranks && tid != X.rank) {
+        st_release_sys(X.flags[tid] + 2 * X.rank, ep * 2 + (ps.l_abort ? 1ULL : 0ULL));
+        const long long t0 = gtime_ns();
+        unsigned long long v;
+        while (((v = ld_acquire_sys(X.flags[X.rank] + 2 * tid)) >> 1) < ep)
+            if (gtime_ns() - t0 > kSpinTimeoutNs) { ps.timeout = 1; break; }
+        if ((v >> 1) == ep && (v & 1ULL)) ps.l_abort = 1;
+    }
+    __syncthreads();
+}
+
+// CTA 0 after pass i: wait for the grid, exchange, θ-step (and, if the loop has ended, the covariance stage's constants), release
+template <int V>
+__device__ void leader_step(const PersistParams& P, PersistShared& ps, int i, unsigned seq) {
+    PersistCtl* const ctl = P.ctl;
+    volatile OuterState* const st = P.step.st;
+    const int tid = threadIdx.x, nt = P.step.nt, ph = i - 1;
+    const OutPtrs& ob = P.slot[ph];
+    if (tid == 0) {
+        ps.l_abort = 0;
+        wait_arrivals(P, ph, ps);
+        P.stamps[1 + 2 * ph] = gtime_ns();
+    }
+    __syncthreads();
+    const double* g_all = ob.g + nt;
+    if (P.x.nranks > 1 && !ps.timeout) {
+        double* dst[kMaxRanks];
+        for (int q = 0; q < P.x.nranks; ++q) dst[q] = P.x.gall[q][ph];
+        exchange_rows(P, ps, ob.g + nt, ob.status + 1, P.step.counts[P.x.rank] * nt, nt, dst, P.step.need, P.x.epoch0 + i);
+        g_all = P.x.gall[P.x.rank][ph];
+    }
+    if (!ps.l_abort && !ps.timeout) {
+        OuterParams S = P.step;
+        S.iter = i;
+        S.g_local = ob.g;
+        S.status_local = ob.status;
+        S.g_all = g_all;
+        S.dyn_next = &ctl->dyn[0];
+        theta_step_body<V>(S, ps.red, &ps.bad);
+        __syncthreads();
+        if (P.get_cov && st->done && !st->error) {
+            CovParams C = P.cov;
+            C.dyn_fid = &ctl->dyn[0];
+            C.dyn_fd = &ctl->dyn[1];
+            cov_prep_body<V>(C, ps.red);
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        if (ps.timeout) { st->error = 3; st->done = 1; }
+        if (ps.l_abort) st->abort = 1;
+        ctl->msg_done = st->done;
+        ctl->msg_error = st->error;
+        ctl->msg_abort = ps.l_abort;
+        P.stamps[2 + 2 * ph] = gtime_ns();
+        __threadfence();
+        st_release_gpu(&ctl->step_flag, seq);
+    }
+}
+
+// every CTA: until CTA 0 has released `seq`; then its message and the constants it published are in ps
+__device__ bool wait_step(const PersistParams& P, PersistShared& ps, unsigned seq) {
+    PersistCtl* const ctl = P.ctl;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        const long long t0 = gtime_ns();
+        while (ld_acquire_gpu(&ctl->step_flag) < seq)
+            if (gtime_ns() - t0 > kSpinTimeoutNs + 1000000000LL) { ps.timeout = 1; break; }
+        ps.done = __ldcg(&ctl->msg_done);
+        ps.error = __ldcg(&ctl->msg_error);
+        ps.abort = __ldcg(&ctl->msg_abort);
+    }
+    __syncthreads();
+    if (ps.timeout) return false;
+    constexpr int kWords = 2 * (int)sizeof(DynConsts) / 8;
+    for (int w = tid; w < kWords; w += blockDim.x)
+        reinterpret_cast<double*>(ps.dyn)[w] = __ldcg(reinterpret_cast<const double*>(ctl->dyn) + w);
+    __syncthreads();
+    return true;
+}
+
+template <int STREAM>
+__global__ void __launch_bounds__(STREAM == 1 ? kThreads : kWarpCta, STREAM == 1 ? 1 : 2)
+solve_persist_kernel(const __grid_constant__ PersistParams P) {
+    constexpr int V = STREAM == 1 ? 2 : 4;            // lanes of the θ-step's reduction tree per thread (512 / 256 threads carry them)
+    __shared__ PersistShared ps;
+    PersistCtl* const ctl = P.ctl;
+    const int tid = threadIdx.x;
+    const bool lead = blockIdx.x == 0;
+    if (tid == 0) {
+        ps.done = ps.error = ps.abort = ps.timeout = ps.l_abort = 0;
+        ps.dyn[0] = P.first;
+        if (lead) {
+            OuterState* st = P.step.st;
+            st->n_iter = 0; st->done = 0; st->error = 0; st->abort = 0;
+            for (int c = 0; c < kMaxTheta; ++c) { st->theta[c] = P.theta0[c]; st->step[c] = 0.0; }
+            for (int k = 0; k < 16; ++k) P.stamps[k] = 0;
+            P.stamps[0] = gtime_ns();
+        }
+    }
+    unsigned seq = 0;
+    bool reinit = false, finished = false;
+    for (int i = 1; i <= P.max_pass; ++i) {
+        if (tid == 0) phase_launch(P, i - 1, ps);
+        __syncthreads();
+        run_phase<STREAM>(ps.L, reinit);
+        reinit = true;
+        if (tid == 0) { __threadfence(); atomicAdd(&ctl->arrive[i - 1], 1); }
+        ++seq;
+        if (lead) leader_step<V>(P, ps, i, seq);
+        if (!wait_step(P, ps, seq)) break;
+        if (ps.abort || ps.error) break;
+        if (ps.done) { finished = true; break; }
+    }
+    if (finished && P.get_cov) {
+        bool ran_fd = false;
+        if (P.nh_mine > 0) {
+            if (tid == 0) phase_launch(P, kPhaseFid, ps);
+            __syncthreads();
+            run_phase<STREAM>(ps.L, reinit);
+            reinit = true;
+            if (tid == 0) { __threadfence(); atomicAdd(&ctl->arrive[kPhaseFid], 1); }
+            ++seq;
+            if (lead) {
+                if (tid == 0) {
+                    ps.l_abort = 0;
+                    wait_arrivals(P, kPhaseFid, ps);
+                    P.stamps[1 + 2 * kPhaseFid] = gtime_ns();
+                    ctl->msg_abort = ps.l_abort;
+                    if (ps.timeout) ctl->msg_error = 3;
+                    __threadfence();
+                    st_release_gpu(&ctl->step_flag, seq);
+                }
+            }
+            if (wait_step(P, ps, seq) && !ps.abort && !ps.error) {
+                if (tid == 0) phase_launch(P, kPhaseFd, ps);
+                __syncthreads();
+                run_phase<STREAM>(ps.L, reinit);
+                if (tid == 0) { __threadfence(); atomicAdd(&ctl->arrive[kPhaseFd], 1); }
+                ran_fd = true;
+            }
+        }
+        if (lead) {                       // the end of the covariance stage: hand-backs, and the exchange of the FD scores
+            __syncthreads();
+            if (tid == 0) {
+                if (ran_fd) wait_arrivals(P, kPhaseFd, ps);
+                else if (ps.abort) ps.l_abort = 1;
+                P.stamps[1 + 2 * kPhaseFd] = gtime_ns();
+            }
+            __syncthreads();
+            if (P.x.nranks > 1 && !ps.timeout) {
+                double* dst[kMaxRanks];
+                for (int q = 0; q < P.x.nranks; ++q) dst[q] = P.x.fdall[q];
+                const int nt = P.step.nt;
+                exchange_rows(P, ps, P.fd.g, P.fd.status, P.nh_mine * nt * 2 * nt, nt, dst, P.x.need_fd, P.x.epoch0 + kOuterSlots + 1);
+            }
+            if (tid == 0) {
+                volatile OuterState* st = P.step.st;
+                if (ps.l_abort) st->abort = 1;
+                if (ps.timeout) st->error = 3;
+                P.stamps[2 + 2 * kPhaseFd] = gtime_ns();
+            }
+        }
+    }
+    // the last CTA to leave clears the control block for the next launch
+    __syncthreads();
+    if (tid == 0) {
+        if (ps.timeout && lead) { volatile OuterState* st = P.step.st; st->error = 3; }
+        __threadfence();
+        if (atomicAdd(&ctl->exit_count, 1) == (int)gridDim.x - 1) {
+            volatile int* w = reinterpret_cast<volatile int*>(ctl);
+            for (int k = 0; k < (int)(offsetof(PersistCtl, dyn) / sizeof(int)); ++k) w[k] = 0;
+            __threadfence();
+        }
+    }
+}
 }  // namespace
 
 // Geometry: chunks, segments, ring depth.  One CTA per SM.
@@ -678,6 +1013,37 @@ cudaError_t launch_iso_stream(SolveLaunch& L, const Geometry& geo, cudaStream_t 
     if (e != cudaSuccess) return e;
     iso_stream_kernel<<<grid, kThreads, geo.smem_bytes, st>>>(L);
     return cudaGetLastError();
+}
+
+// solve_persist_kernel: a cooperative grid — one CTA per SM with the ring (d ≥ 4096), as many 256-thread CTAs as are resident
+// otherwise
+cudaError_t iso_persist_geometry(const Geometry& geo, int device, int* grid, int* threads) {
+    int sms = 0, coop = 0, per_sm = 0;
+    cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (e != cudaSuccess) return e;
+    e = cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+    if (e != cudaSuccess) return e;
+    if (!coop || (geo.stream != 1 && geo.stream != 2)) { *grid = 0; *threads = 0; return cudaSuccess; }
+    if (geo.stream == 1) {
+        e = cudaFuncSetAttribute(solve_persist_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, geo.smem_bytes);
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, solve_persist_kernel<1>, kThreads, geo.smem_bytes);
+        *threads = kThreads;
+    } else {
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, solve_persist_kernel<2>, kWarpCta, 0);
+        *threads = kWarpCta;
+    }
+    if (e != cudaSuccess) return e;
+    *grid = sms * per_sm;
+    return cudaSuccess;
+}
+
+cudaError_t launch_iso_persist(const PersistParams& P, const Geometry& geo, int grid, cudaStream_t st) {
+    void* args[] = {const_cast<PersistParams*>(&P)};
+    if (geo.stream == 1)
+        return cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(&solve_persist_kernel<1>), dim3(grid), dim3(kThreads), args,
+                                           (size_t)geo.smem_bytes, st);
+    return cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(&solve_persist_kernel<2>), dim3(grid), dim3(kWarpCta), args, 0, st);
 }
 
 // warp-per-unit geometry (small d)

@@ -27,217 +27,32 @@
 #include <cstring>
 #include <vector>
 
-#include "muse_handle.cuh"
+#include "muse_outer_dev.cuh"
 
 using namespace muse;
 
 extern "C" int muse_b200_allgather_rows(muse_handle* h, const double* local_host, int32_t ncol, const int32_t* counts, double* out_host);
 int muse_cov_finish(muse_handle* h, const double* theta, const double* gs, int nsims_total, int nsims_h_total, const int32_t* counts_h,
-                    const double* Hs_local, int mine, const double* prior_sigma, muse_cov_out* out);
+                    const double* Hs_local, int mine, const double* prior_sigma, muse_cov_out* out, const double* Hs_all);
 
 namespace {
 
-constexpr int kStepThreads = 1024;
-constexpr int kMaxRanks = 16;
-
-struct OuterParams {
-    int nt, family, d;
-    int iter;                 // 1-based index of the pass just executed
-    int maxsteps;
-    int units_local;          // units of the pass on this rank (data + local sims)
-    int nranks, n_total;
-    int counts[kMaxRanks];    // sims per rank
-    long long need;           // doubles per rank slot of g_all
-    double alpha, theta_rtol;
-    int have_prior;
-    double prior_mean[kMaxTheta], prior_sigma[kMaxTheta];
-    const double* g_local;    // this pass: local score rows, row 0 = data
-    const int* status_local;
-    const double* g_all;      // this pass: sim scores of all ranks (rank q's rows at g_all + q·need)
-    OuterState* st;
-    DynConsts* dyn_next;      // constants of the next pass
-};
-
-struct CovParams {
-    int nt, family, d;
-    int nranks, n_total;
-    int counts[kMaxRanks];
-    long long need;
-    const double* g_all_slot[kOuterSlots];   // gathered sim scores of iteration i live in slot (i − 1) % kOuterSlots
-    OuterState* st;
-    DynConsts* dyn_fid;
-    DynConsts* dyn_fd;
-};
-
-// θ → constants, as theta_consts() of muse_api.cu (device libm)
-__device__ void consts_of(int family, int d, const double* th_sim, const double* th_eval, IsoSample* smp, IsoEval* ev) {
-    const double dd = (double)d;
-    if (family == MUSE_FAMILY_FUNNEL) {
-        if (smp) { smp->sig = exp(0.5 * th_sim[0]); smp->mu = 0.0; }
-        if (ev) { ev->a = exp(-th_eval[0]); ev->mu = 0.0; ev->half_cst = 0.5 * dd * th_eval[0]; ev->cspec = 1.0 / (1.0 + ev->a); }
-    } else {
-        if (smp) { smp->sig = exp(th_sim[1]); smp->mu = th_sim[0]; }
-        if (ev) { ev->a = exp(-2.0 * th_eval[1]); ev->mu = th_eval[0]; ev->half_cst = dd * th_eval[1]; ev->cspec = 1.0 / (1.0 + ev->a); }
-    }
-}
-
-// Σ_k f_c(k) for every θ-component c over all sims, in an order fixed by the GLOBAL sim index: thread t takes sims t, t + T,
-// t + 2T, … (loads issued four at a time — a lone CTA is latency-bound, not bandwidth-bound), then a shuffle tree per warp
-// and a second one over the warp results.  The order does not depend on how the sims are sharded over ranks, so θ — like
-// every per-sim result — is bit-identical for any number of GPUs.  f(o, c) reads element c of the score row at offset o of
-// the gathered layout (rank q's rows start at q·need).  Results land in out[0..nt).
-template <class F>
-__device__ void block_sums(const int* counts, int nranks, long long need, int nt, int n_total, F&& f, double (*sh)[32], double* out) {
-    double acc[kMaxTheta];
-#pragma unroll
-    for (int c = 0; c < kMaxTheta; ++c) acc[c] = 0.0;
-    constexpr int T = kStepThreads;
-    auto row_off = [&](int k) -> size_t {                 // global sim k → offset of its row
-        int q = 0, base = 0;
-        while (q + 1 < nranks && k >= base + counts[q]) { base += counts[q]; ++q; }
-        return (size_t)q * (size_t)need + (size_t)(k - base) * nt;
-    };
-    int k = threadIdx.x;
-    for (; k + 3 * T < n_total; k += 4 * T) {
-        const size_t o0 = row_off(k), o1 = row_off(k + T), o2 = row_off(k + 2 * T), o3 = row_off(k + 3 * T);
-#pragma unroll
-        for (int c = 0; c < kMaxTheta; ++c) {
-            if (c < nt) {
-                const double v0 = f(o0, c), v1 = f(o1, c), v2 = f(o2, c), v3 = f(o3, c);
-                acc[c] += v0; acc[c] += v1; acc[c] += v2; acc[c] += v3;
-            }
-        }
-    }
-    for (; k < n_total; k += T) {
-        const size_t o = row_off(k);
-#pragma unroll
-        for (int c = 0; c < kMaxTheta; ++c)
-            if (c < nt) acc[c] += f(o, c);
-    }
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int c = 0; c < kMaxTheta; ++c) {
-        if (c < nt) {
-            double v = acc[c];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0) sh[c][warp] = v;
-        }
-    }
-    __syncthreads();
-    for (int c = 0; c < nt; ++c) {
-        double v = (lane < T / 32) ? sh[c][lane] : 0.0;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        out[c] = v;                                      // every warp computes the same value
-    }
-    __syncthreads();
-}
-
-// mean and corrected variance of every component (two passes, like Statistics.mean / var)
-__device__ void block_mean_var(const double* g, const int* counts, int nranks, long long need, int nt, int n_total,
-                               double (*sh)[32], double* mean, double* var) {
-    block_sums(counts, nranks, need, nt, n_total, [&](size_t o, int c) { return g[o + c]; }, sh, mean);
-    for (int c = 0; c < nt; ++c) mean[c] /= n_total;
-    block_sums(counts, nranks, need, nt, n_total, [&](size_t o, int c) { const double dlt = g[o + c] - mean[c]; return dlt * dlt; }, sh, var);
-    for (int c = 0; c < nt; ++c) var[c] /= (n_total - 1);
-}
+constexpr int kStepThreads = kStepLanes;
 
 __global__ void __launch_bounds__(kStepThreads) theta_step_kernel(const OuterParams P) {
     __shared__ double sh[kMaxTheta][32];
     __shared__ int bad;
-    OuterState* st = P.st;
-    if (st->done) {                                            // the pass before this step was skipped: keep skipping
+    if (P.st->done) {                                          // the pass before this step was skipped: keep skipping
         if (threadIdx.x == 0 && P.dyn_next) P.dyn_next->skip = 1;
         return;
     }
-    if (threadIdx.x == 0) bad = 0;
-    __syncthreads();
-    // src/interface.jl:170.  The decision must be the same on every rank: with several ranks it is taken from what all of them
-    // see — the replicated data unit and the gathered rows, in which a failed sim arrives as NaN (muse_comm.cu / publish_peer)
-    if (P.nranks > 1) {
-        if (threadIdx.x == 0 && __ldcg(P.status_local) == MUSE_STATUS_NONFINITE) bad = 1;
-        for (int q = 0; q < P.nranks; ++q)
-            for (int e = threadIdx.x; e < P.counts[q] * P.nt; e += kStepThreads)
-                if (isnan(__ldcg(P.g_all + (size_t)q * P.need + e))) bad = 1;
-    } else {
-        for (int u = threadIdx.x; u < P.units_local; u += kStepThreads)
-            if (__ldcg(P.status_local + u) == MUSE_STATUS_NONFINITE) bad = 1;
-    }
-    __syncthreads();
-    if (bad) {
-        if (threadIdx.x == 0) { st->error = 1; st->done = 1; if (P.dyn_next) P.dyn_next->skip = 1; }
-        return;
-    }
-    const int row = P.iter - 1;
-    double mean[kMaxTheta], var[kMaxTheta];
-    block_mean_var(P.g_all, P.counts, P.nranks, P.need, P.nt, P.n_total, sh, mean, var);
-    if (threadIdx.x != 0) return;
-    double th_new[kMaxTheta];
-    for (int c = 0; c < P.nt; ++c) {
-        const double th = st->theta[c];
-        const double g_dat = P.g_local[c];
-        const double g_like = g_dat - mean[c];                                                     // :183
-        const double g_prior = P.have_prior ? -(th - P.prior_mean[c]) / (P.prior_sigma[c] * P.prior_sigma[c]) : 0.0;   // :184
-        const double g_post = g_like + g_prior;                                                    // :185
-        const double h_inv_like = -1.0 / var[c];                                                   // :188
-        const double h_prior = P.have_prior ? -1.0 / (P.prior_sigma[c] * P.prior_sigma[c]) : 0.0;  // :207
-        const double h_inv_post = 1.0 / (1.0 / h_inv_like + h_prior);                              // :208 (diagonal)
-        if (row < kOuterMaxIter) {
-            OuterRow& R = st->row[row];
-            R.theta[c] = th; R.g_dat[c] = g_dat; R.g_like[c] = g_like; R.g_prior[c] = g_prior;
-            R.h_inv_like[c] = h_inv_like; R.h_prior[c] = h_prior; R.h_inv_post[c] = h_inv_post;
-        }
-        th_new[c] = th - P.alpha * (h_inv_post * g_post);                                          // :224
-    }
-    for (int c = 0; c < P.nt; ++c) st->theta[c] = th_new[c];                                       // :230
-    st->n_iter = P.iter;
-    int done = 0;
-    if (P.iter >= 2) {                                   // the test at the top of iteration iter + 1 > 2   (:163-166)
-        double q = 0.0;
-        for (int c = 0; c < P.nt; ++c) {
-            const double dlt = st->row[row].theta[c] - st->row[row - 1].theta[c];
-            q += dlt * st->row[row].h_inv_post[c] * dlt;
-        }
-        q = -q;
-        if (q < 0.0) { st->error = 2; done = 1; }        // DomainError of sqrt in the reference
-        else if (sqrt(q) < P.theta_rtol) done = 1;
-    }
-    if (P.iter >= P.maxsteps) done = 1;
-    st->done = done;
-    if (P.dyn_next) {
-        consts_of(P.family, P.d, th_new, th_new, &P.dyn_next->smp[0], &P.dyn_next->ev);
-        P.dyn_next->skip = done;
-    }
+    theta_step_body<1>(P, sh, &bad);
 }
 
 // after the last θ-step of a chunk: if the loop has ended, the constants of get_H!'s launches; otherwise they are skipped
 __global__ void __launch_bounds__(kStepThreads) cov_prep_kernel(const CovParams P) {
     __shared__ double sh[kMaxTheta][32];
-    OuterState* st = P.st;
-    if (!st->done || st->error || st->n_iter < 1) {
-        if (threadIdx.x == 0) { P.dyn_fid->skip = 1; P.dyn_fd->skip = 1; }
-        return;
-    }
-    const double* gall = P.g_all_slot[(st->n_iter - 1) % kOuterSlots];
-    double step[kMaxTheta], mean[kMaxTheta], var[kMaxTheta];
-    block_mean_var(gall, P.counts, P.nranks, P.need, P.nt, P.n_total, sh, mean, var);
-    for (int c = 0; c < P.nt; ++c) step[c] = 0.1 / sqrt(var[c]);       // step = 0.1 ./ std(gs)   (:411-413), gs = the last scores (:231)
-    if (threadIdx.x != 0) return;
-    double th0[kMaxTheta];
-    for (int c = 0; c < P.nt; ++c) { th0[c] = st->theta[c]; st->step[c] = step[c]; }
-    consts_of(P.family, P.d, th0, th0, &P.dyn_fid->smp[0], &P.dyn_fid->ev);
-    P.dyn_fid->skip = 0;
-    consts_of(P.family, P.d, th0, th0, nullptr, &P.dyn_fd->ev);
-    for (int n = 0; n < P.nt; ++n)
-        for (int s = 0; s < 2; ++s) {
-            double th[kMaxTheta];
-            for (int c = 0; c < P.nt; ++c) th[c] = th0[c];
-            const double eps = 0.0 + step[n] * (s ? 1.0 : -1.0);     // x .+ step .* grid   (src/util.jl:15)
-            th[n] = th0[n] + eps;
-            consts_of(P.family, P.d, th, th0, &P.dyn_fd->smp[2 * n + s], nullptr);
-        }
-    P.dyn_fd->skip = 0;
+    cov_prep_body<1>(P, sh);
 }
 
 #define OUTER_TRY(h, expr)                                                                    \
@@ -310,6 +125,8 @@ void muse_outer_release(muse_handle* h) {
     cudaFreeHost(h->outer_arena_h);
     cudaFreeHost(h->outer_st_stage);
     cudaFree(h->outer_dyn);
+    cudaFree(h->persist_ctl);
+    h->persist_ctl = nullptr;
     for (int s = 0; s < kOuterSlots; ++s) { cudaFree(h->outer_gall[s]); h->outer_gall[s] = nullptr; h->outer_slot[s] = OutBlock{}; }
     cudaFreeHost(h->outer_gall_h);
     h->outer_fd = OutBlock{};
@@ -360,6 +177,7 @@ extern "C" int muse_b200_muse_solve(muse_handle* h, const double* theta0, int32_
     const int nh_mine = get_covariance ? (multi ? counts_h[h->comm_rank] : nsims_h_total) : 0;
     int rc = outer_ensure(h, units, std::max(0, nh_mine) * nt * 2, gall_doubles);
     if (rc != MUSE_OK) return rc;
+    if (muse_ensure_outputs(h, std::max(units, std::max(0, nh_mine) * nt * 2)) != 0) return MUSE_ECUDA;   // segment sums / hand-back list of every unit
     if (get_covariance) {
         const bool hshard = h->cfg.nsims_h > 0;
         if (nh_mine < 0 || nh_mine > (hshard ? h->cfg.nsims_h : h->cfg.nsims)) { h->err = "nsims_H outside the handle's H shard"; return MUSE_EINVAL; }
@@ -460,9 +278,227 @@ extern "C" int muse_b200_muse_solve(muse_handle* h, const double* theta0, int32_
     static const bool graphs_multi = [] { const char* e = std::getenv("MUSE_OUTER_GRAPH_MULTI"); return e && std::atoi(e) != 0; }();
     const bool use_graph = graphs_on && (!multi || graphs_multi);
 
+    // copy the history rows of iterations [first, upto] out of the host mirrors (state, per-pass output blocks, gathered scores)
+    const double* gall_h = h->outer_gall_h;          // host mirror of the gathered score slots (multi-GPU) and its slot stride
+    size_t gall_h_stride = gall_doubles;
+    auto copy_history = [&](int first, int upto, double chunk_s) {
+        for (int i = first; i <= upto; ++i) {
+            const int row = i - 1, slot = row % kOuterSlots;
+            const OutBlock& ob = h->outer_slot[slot];
+            const OuterRow& R = sh_->row[row];
+            for (int c = 0; c < nt; ++c) {
+                out->theta_hist[(size_t)row * nt + c] = R.theta[c];
+                out->g_dat_hist[(size_t)row * nt + c] = R.g_dat[c];
+                out->g_like_hist[(size_t)row * nt + c] = R.g_like[c];
+                out->g_prior_hist[(size_t)row * nt + c] = R.g_prior[c];
+                out->h_inv_like_hist[(size_t)row * nt + c] = R.h_inv_like[c];
+                out->h_prior_hist[(size_t)row * nt + c] = R.h_prior[c];
+                out->h_inv_post_hist[(size_t)row * nt + c] = R.h_inv_post[c];
+            }
+            double* gs = out->g_sims_hist + (size_t)row * nsims_total * nt;
+            if (multi) {
+                const double* src = gall_h + (size_t)slot * gall_h_stride;
+                size_t off = 0;
+                for (int q = 0; q < P.nranks; ++q) {
+                    std::memcpy(gs + off, src + (size_t)q * P.need, (size_t)counts[q] * nt * sizeof(double));
+                    off += (size_t)counts[q] * nt;
+                }
+            } else {
+                std::memcpy(gs, ob.g_h + nt, (size_t)nloc * nt * sizeof(double));
+            }
+            std::memcpy(out->iters_hist + (size_t)row * units, ob.iters_h, (size_t)units * sizeof(int));
+            std::memcpy(out->fg_hist + (size_t)row * units, ob.fg_h, (size_t)units * sizeof(int));
+            std::memcpy(out->gnorm_hist + (size_t)row * units, ob.gnorm_h, (size_t)units * sizeof(double));
+            std::memcpy(out->status_hist + (size_t)row * units, ob.status_h, (size_t)units * sizeof(int));
+            out->seconds_hist[row] = chunk_s / std::max(1, upto - first + 1);
+        }
+    };
+
     out->n_iter = 0;
     int it_done = 0;                        // iterations whose history has been copied out
     bool finished = false;
+    std::vector<double> Hs_all;             // multi-GPU persistent launch: the FD Jacobians of ALL ranks (no second exchange)
+
+    // ---- the first chunk — normally the whole solve — in ONE cooperative launch (solve_persist_kernel, muse_iso_stream.cu) ----
+    // MUSE_PERSIST=0 switches it off (A/B against the chain of launches below).
+    // (read at every call, so that one process can hold the two paths against each other)
+    const bool persist_on = [] { const char* e = std::getenv("MUSE_PERSIST"); return !e || std::atoi(e) != 0; }();
+    const bool p2p_on = [] { const char* e = std::getenv("MUSE_EXCHANGE"); return !e || std::strcmp(e, "nccl") != 0; }();
+    if (h->persist_grid < 0) {
+        int g = 0, t = 0;
+        if (iso_persist_geometry(h->geo, h->cfg.device, &g, &t) != cudaSuccess) { cudaGetLastError(); g = 0; }
+        h->persist_grid = g;
+        h->persist_threads = t;
+    }
+    const int fd_items = std::max(0, nh_mine) * nt * 2;
+    bool p2p_fit = false;
+    if (multi && h->p2p_ready && p2p_on && h->p2p_nranks == P.nranks && h->p2p_rank == h->comm_rank) {
+        int maxh = 1;
+        if (get_covariance) for (int q = 0; q < P.nranks; ++q) maxh = std::max(maxh, (int)counts_h[q]);
+        const long long need_fd = (long long)maxh * 2 * nt * nt;
+        p2p_fit = (long long)P.nranks * std::max(P.need, need_fd) <= h->p2p_block;
+    }
+    // what makes units leave the fast path is the tolerance (below round-off) or the data, not the launch mechanics
+    std::vector<unsigned char> pkey;
+    {
+        const double dbl[] = {atol};
+        const int ints[] = {first_start, nloc, nsims_total};
+        pkey.insert(pkey.end(), reinterpret_cast<const unsigned char*>(dbl), reinterpret_cast<const unsigned char*>(dbl) + sizeof(dbl));
+        pkey.insert(pkey.end(), reinterpret_cast<const unsigned char*>(ints), reinterpret_cast<const unsigned char*>(ints) + sizeof(ints));
+    }
+    if (persist_on && h->persist_grid > 0 && !h->dbg && (!multi || p2p_fit) && pkey != h->persist_off_key) {
+        const auto t0 = std::chrono::steady_clock::now();
+        if (!h->persist_ctl) {
+            OUTER_TRY(h, cudaMalloc(&h->persist_ctl, sizeof(PersistCtl)));
+            OUTER_TRY(h, cudaMemsetAsync(h->persist_ctl, 0, sizeof(PersistCtl), h->stream));
+        }
+        PersistParams Q{};
+        muse_fill_common(h, Q.base);
+        Q.base.atol = atol;
+        Q.base.zA = h->zA; Q.base.zB = h->zB; Q.base.zstate = h->zstate;
+        Q.base.dbg = nullptr;
+        Q.base.seg_chunks = h->geo.seg_chunks;
+        Q.base.nseg = h->geo.stream == 1 ? h->geo.nseg : 1;
+        Q.step = P;
+        Q.cov.nt = nt; Q.cov.family = P.family; Q.cov.d = P.d; Q.cov.nranks = P.nranks; Q.cov.n_total = nsims_total; Q.cov.need = P.need;
+        for (int q = 0; q < P.nranks; ++q) Q.cov.counts[q] = P.counts[q];
+        Q.cov.st = sd;
+        if (muse_theta_consts(h->cfg, theta0, theta0, &Q.first.smp[0], &Q.first.ev) != 0) { h->err = "family"; return MUSE_EUNSUPPORTED; }
+        for (int c = 0; c < nt; ++c) Q.theta0[c] = theta0[c];
+        Q.first_kind = first_start == MUSE_START_USER ? kStartSharedKeep : kStartZero;
+        Q.max_pass = std::min((int)maxsteps, kOuterSlots);
+        Q.get_cov = get_covariance ? 1 : 0;
+        Q.nh_mine = std::max(0, nh_mine);
+        Q.z0user = h->z0user;
+        const bool hshard = h->cfg.nsims_h > 0;
+        Q.xi_fd = hshard ? h->xi_h : h->xi;
+        Q.nu_fd = hshard ? h->nu_h : h->nu;
+        Q.zfidA = h->zfidA; Q.zfidB = h->zfidB;
+        auto optrs = [](const OutBlock& ob) { return OutPtrs{ob.g_d, ob.gnorm_d, ob.f_d, ob.iters_d, ob.fg_d, ob.status_d}; };
+        for (int s2 = 0; s2 < kOuterSlots; ++s2) Q.slot[s2] = optrs(h->outer_slot[s2]);
+        Q.fd = optrs(h->outer_fd);
+        Q.ctl = static_cast<PersistCtl*>(h->persist_ctl);
+        Q.stamps = sd->stamp;
+        Q.x.nranks = 1;
+        size_t x_blk = 0;
+        int parity = 0;
+        if (multi) {
+            const unsigned long long seq = ++h->p2p_seq;
+            parity = (int)(seq & 1ULL);
+            x_blk = (size_t)h->p2p_block;
+            Q.x.nranks = P.nranks;
+            Q.x.rank = h->comm_rank;
+            Q.x.epoch0 = seq * 8ULL;
+            int maxh = 1;
+            for (int q = 0; q < P.nranks; ++q) {
+                Q.x.counts_h[q] = get_covariance ? counts_h[q] : 0;
+                maxh = std::max(maxh, Q.x.counts_h[q]);
+            }
+            Q.x.need_fd = (long long)maxh * 2 * nt * nt;
+            for (int q = 0; q < P.nranks; ++q) {
+                unsigned char* base = h->p2p_peer[q];
+                Q.x.flags[q] = reinterpret_cast<unsigned long long*>(base);
+                double* blocks = reinterpret_cast<double*>(base + 256) + (size_t)parity * (kOuterSlots + 1) * x_blk;
+                for (int s2 = 0; s2 < kOuterSlots; ++s2) Q.x.gall[q][s2] = blocks + (size_t)s2 * x_blk;
+                Q.x.fdall[q] = blocks + (size_t)kOuterSlots * x_blk;
+            }
+            for (int s2 = 0; s2 < kOuterSlots; ++s2) Q.cov.g_all_slot[s2] = Q.x.gall[h->comm_rank][s2];
+        } else {
+            for (int s2 = 0; s2 < kOuterSlots; ++s2) Q.cov.g_all_slot[s2] = h->outer_slot[s2].g_d + nt;
+        }
+        cudaEvent_t ea = nullptr, eb = nullptr;
+        if (h->prof) {
+            OUTER_TRY(h, cudaEventCreate(&ea));
+            OUTER_TRY(h, cudaEventCreate(&eb));
+            OUTER_TRY(h, cudaEventRecord(ea, h->stream));
+        }
+        OUTER_TRY(h, launch_iso_persist(Q, h->geo, h->persist_grid, h->stream));
+        if (h->prof) OUTER_TRY(h, cudaEventRecord(eb, h->stream));
+        h->acc.launches += 1;
+        // results: [state | slot 0 | slot 1 | FD block] in one copy (the typical solve); slot 2 only if a third pass ran
+        OUTER_TRY(h, cudaMemcpyAsync(h->outer_arena_h, h->outer_arena_d, h->outer_arena_head, cudaMemcpyDeviceToHost, h->stream));
+        if (multi)
+            OUTER_TRY(h, cudaMemcpyAsync(h->p2p_host, Q.x.gall[h->comm_rank][0], (size_t)(kOuterSlots + 1) * x_blk * sizeof(double),
+                                         cudaMemcpyDeviceToHost, h->stream));
+        OUTER_TRY(h, cudaStreamSynchronize(h->stream));
+        if (sh_->error == 3) {
+            cudaMemsetAsync(h->persist_ctl, 0, sizeof(PersistCtl), h->stream);
+            if (ea) { cudaEventDestroy(ea); cudaEventDestroy(eb); }
+            h->err = "muse_solve: a rank did not arrive at the exchange step within 4 s (peer-mapped exchange of the persistent launch)";
+            return MUSE_ECUDA;
+        }
+        if (sh_->abort) {
+            // a unit left the fast path somewhere (on any rank: the flag travels with the exchange): this configuration goes
+            // through the chain of launches, whose generic kernel re-solves such units — from scratch, now and from now on
+            h->persist_off_key = pkey;
+            if (ea) { cudaEventDestroy(ea); cudaEventDestroy(eb); }
+        } else {
+            const int n_now = sh_->n_iter;
+            if (n_now > 2) {
+                OUTER_TRY(h, cudaMemcpyAsync(h->outer_slot[2].hst, h->outer_slot[2].d, h->outer_slot[2].bytes, cudaMemcpyDeviceToHost, h->stream));
+                OUTER_TRY(h, cudaStreamSynchronize(h->stream));
+            }
+            const double chunk_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            if (sh_->error == 1) { if (ea) { cudaEventDestroy(ea); cudaEventDestroy(eb); } h->err = "muse!: MAP solution failed with a non-finite objective"; return MUSE_ESTATE; }
+            const bool cov_ran = get_covariance && sh_->done != 0 && sh_->error == 0;
+            {   // statistics: one launch; units and algorithmic bytes of the phases that ran, their times from CTA 0's globaltimer stamps
+                const double d8 = 8.0 * h->cfg.d;
+                const long long* T = sh_->stamp;
+                double units_sum = 0.0, bytes_sum = 0.0;
+                auto add = [&](int kind, double u, double b, long long t_a, long long t_b) {
+                    units_sum += u; bytes_sum += b;
+                    if (!h->prof) return;
+                    h->acc_pass.launches[kind] += 1; h->acc_pass.ms[kind] += (double)(t_b - t_a) * 1e-6;
+                    h->acc_pass.units[kind] += u; h->acc_pass.bytes[kind] += b;
+                };
+                for (int i = 1; i <= n_now; ++i) {
+                    const bool warm = i > 1 || first_start == MUSE_START_USER;
+                    const double z0b = warm ? d8 : 0.0;
+                    add(warm ? MUSE_PASS_WARM : MUSE_PASS_COLD, units, nloc * (3 * d8 + z0b) + (2 * d8 + z0b), i == 1 ? T[0] : T[2 + 2 * (i - 2)], T[1 + 2 * (i - 1)]);
+                }
+                if (cov_ran && nh_mine > 0) {
+                    add(MUSE_PASS_FIDUCIAL, 1, 3 * d8, T[2 + 2 * (n_now - 1)], T[1 + 2 * kPhaseFid]);
+                    add(MUSE_PASS_FD, fd_items, fd_items * 2 * d8 + d8, T[1 + 2 * kPhaseFid], T[1 + 2 * kPhaseFd]);
+                }
+                h->acc.solve_launches += 1;
+                if (h->prof) {
+                    muse_handle::Rec r{};
+                    r.a = ea; r.b = eb; r.cls = 3; r.units = units_sum; r.bytes = bytes_sum; r.kind = MUSE_PASS_COLD; r.tag = 0;
+                    h->recs.push_back(r);
+                }
+            }
+            if (multi) { gall_h = h->p2p_host; gall_h_stride = x_blk; }
+            copy_history(1, n_now, chunk_s);
+            if (multi) { gall_h = h->outer_gall_h; gall_h_stride = gall_doubles; }
+            out->n_iter = n_now;
+            for (int c = 0; c < nt; ++c) out->theta_final[c] = sh_->theta[c];
+            if (sh_->error == 2) { h->err = "DomainError: sqrt of a negative number in the θ convergence test (src/muse.jl:165)"; return MUSE_ESTATE; }
+            it_done = n_now;
+            finished = sh_->done != 0 || it_done >= maxsteps;
+            if (finished && cov_ran) {
+                if (multi) {        // every rank's FD scores are here: combine them all, in rank order
+                    Hs_all.assign((size_t)std::max(1, (int)nsims_h_total) * nt * nt, 0.0);
+                    const double* fd_h = h->p2p_host + (size_t)kOuterSlots * x_blk;
+                    size_t off = 0;
+                    for (int q = 0; q < P.nranks; ++q) {
+                        const double* rows = fd_h + (size_t)q * Q.x.need_fd;
+                        for (size_t e = 0; e < (size_t)counts_h[q] * 2 * nt * nt; ++e)
+                            if (std::isnan(rows[e])) { h->err = "get_H!: MAP solution failed with a non-finite objective"; return MUSE_ESTATE; }
+                        if (counts_h[q] > 0) muse_fd_combine_host(h, rows, nullptr, sh_->step, counts_h[q], Hs_all.data() + off, nullptr);
+                        off += (size_t)counts_h[q] * nt * nt;
+                    }
+                }
+            } else if (!finished) {
+                // the loop goes on in chunks of launches: they take the constants of the next pass from outer_dyn
+                OUTER_TRY(h, cudaMemcpyAsync(&dyn[(n_now + 1) & 1], &static_cast<PersistCtl*>(h->persist_ctl)->dyn[0], sizeof(DynConsts),
+                                             cudaMemcpyDeviceToDevice, h->stream));
+            } else if (get_covariance) {
+                h->err = "muse_solve: internal error (the persistent launch ended the loop without its covariance stage)";
+                return MUSE_ESTATE;
+            }
+        }
+    }
+
     while (!finished) {
         const auto t0 = std::chrono::steady_clock::now();
         const int first = it_done + 1;
@@ -547,36 +583,7 @@ extern "C" int muse_b200_muse_solve(muse_handle* h, const double* theta0, int32_
                 }
             }
         }
-        for (int i = first; i <= n_now && i <= last; ++i) {
-            const int row = i - 1, slot = row % kOuterSlots;
-            const OutBlock& ob = h->outer_slot[slot];
-            const OuterRow& R = sh_->row[row];
-            for (int c = 0; c < nt; ++c) {
-                out->theta_hist[(size_t)row * nt + c] = R.theta[c];
-                out->g_dat_hist[(size_t)row * nt + c] = R.g_dat[c];
-                out->g_like_hist[(size_t)row * nt + c] = R.g_like[c];
-                out->g_prior_hist[(size_t)row * nt + c] = R.g_prior[c];
-                out->h_inv_like_hist[(size_t)row * nt + c] = R.h_inv_like[c];
-                out->h_prior_hist[(size_t)row * nt + c] = R.h_prior[c];
-                out->h_inv_post_hist[(size_t)row * nt + c] = R.h_inv_post[c];
-            }
-            double* gs = out->g_sims_hist + (size_t)row * nsims_total * nt;
-            if (multi) {
-                const double* src = h->outer_gall_h + (size_t)slot * gall_doubles;
-                size_t off = 0;
-                for (int q = 0; q < P.nranks; ++q) {
-                    std::memcpy(gs + off, src + (size_t)q * P.need, (size_t)counts[q] * nt * sizeof(double));
-                    off += (size_t)counts[q] * nt;
-                }
-            } else {
-                std::memcpy(gs, ob.g_h + nt, (size_t)nloc * nt * sizeof(double));
-            }
-            std::memcpy(out->iters_hist + (size_t)row * units, ob.iters_h, (size_t)units * sizeof(int));
-            std::memcpy(out->fg_hist + (size_t)row * units, ob.fg_h, (size_t)units * sizeof(int));
-            std::memcpy(out->gnorm_hist + (size_t)row * units, ob.gnorm_h, (size_t)units * sizeof(double));
-            std::memcpy(out->status_hist + (size_t)row * units, ob.status_h, (size_t)units * sizeof(int));
-            out->seconds_hist[row] = chunk_s / std::max(1, n_now - first + 1);
-        }
+        copy_history(first, std::min(n_now, last), chunk_s);
         out->n_iter = n_now;
         for (int c = 0; c < nt; ++c) out->theta_final[c] = sh_->theta[c];
         if (sh_->error == 2) { h->err = "DomainError: sqrt of a negative number in the θ convergence test (src/muse.jl:165)"; return MUSE_ESTATE; }
@@ -596,7 +603,8 @@ extern "C" int muse_b200_muse_solve(muse_handle* h, const double* theta0, int32_
                 if (status[i] == MUSE_STATUS_NONFINITE) { h->err = "get_H!: MAP solution failed with a non-finite objective"; return MUSE_ESTATE; }
         }
         const double* gs_last = out->g_sims_hist + (size_t)(out->n_iter - 1) * nsims_total * nt;
-        return muse_cov_finish(h, out->theta_final, gs_last, nsims_total, nsims_h_total, counts_h, Hs_local.data(), nh_mine, prior_sigma, cov);
+        return muse_cov_finish(h, out->theta_final, gs_last, nsims_total, nsims_h_total, counts_h, Hs_local.data(), nh_mine, prior_sigma, cov,
+                               Hs_all.empty() ? nullptr : Hs_all.data());
     }
     return MUSE_OK;
 }

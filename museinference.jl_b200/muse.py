@@ -173,7 +173,10 @@ def muse_(result: MuseResult, prob: AbstractMuseProblem, theta0=None, **kwargs):
     if fused:
         counts = None
         if pool.world > 1:
-            pool.bind(be)
+            try:
+                pool.bind(be, nsims, nh_total)
+            except TypeError:                   # a pool without the peer-exchange set-up
+                pool.bind(be)
             counts = block_partition(nsims, pool.world)[1]
         mode = DEFAULT_FUSED_DRIVER if fused_driver is True else fused_driver
         device_loop = (mode == "device" and hasattr(be, "muse_solve") and prob.family != "corrgauss" and maxsteps <= 64

@@ -133,13 +133,52 @@ class ShardPool:
     def uses_device_gather(self) -> bool:
         return self.backend == "nccl"
 
-    def bind(self, be):
-        """Give the handle a communicator over this group's ranks (once per handle)."""
+    def bind(self, be, nsims: int | None = None, nh_total: int = 0):
+        """Give the handle a communicator over this group's ranks (once per handle) and — when the problem size is known
+        — the peer-mapped exchange buffers of the one-launch solve (csrc/muse_comm.cu: muse_b200_p2p_*): every rank allocates
+        its region, the 64-byte IPC handles go round the process group, every rank maps its peers' regions.  Collective: all
+        ranks call it with the same arguments.  MUSE_EXCHANGE=nccl keeps the NCCL all-gather only."""
+        import os
+
         if getattr(be, "comm", None) is None:
             ids = [be.comm_unique_id() if self.rank == 0 else None]
             self._dist.broadcast_object_list(ids, src=self._dist.get_global_rank(self.group, 0) if self.group else 0,
                                              group=self.group)
             be.comm_init(self.world, self.rank, ids[0])
+        if nsims is None or not hasattr(be, "p2p_alloc") or os.environ.get("MUSE_EXCHANGE", "auto") == "nccl" or self.world > 16:
+            return
+        nt = be.ntheta
+        maxc = max(block_partition(nsims, self.world)[1])
+        maxh = max(block_partition(max(nh_total, 0), self.world)[1]) if nh_total else 0
+        need = self.world * max(maxc * nt, maxh * 2 * nt * nt, 1)
+        if getattr(be, "_p2p_block", 0) >= need or getattr(be, "_p2p_failed", False):
+            return
+        # every rank takes the same decisions: the outcome of each step is agreed on before the next
+        handle, ok = None, True
+        try:
+            handle = be.p2p_alloc(self.world, self.rank, need)
+        except Exception:
+            ok = False
+        got = [None] * self.world
+        self._dist.all_gather_object(got, handle if ok else None, group=self.group)
+        if any(g is None for g in got):
+            be._p2p_failed = True
+            return
+        try:
+            be.p2p_connect(got)
+        except Exception:
+            ok = False
+        flags = [None] * self.world
+        self._dist.all_gather_object(flags, ok, group=self.group)
+        if not all(flags):
+            be._p2p_failed = True       # NOTE: ranks that did connect keep p2p_ready; block size 0 on the others stops them using it
+            be._p2p_block = 0
+            try:
+                be.p2p_alloc(self.world, self.rank, 1)      # drop the mapping state: a 1-double region can never fit a solve
+            except Exception:
+                pass
+            return
+        be._p2p_block = need
 
     def allgather_device_scores(self, be, first_row: int, n_total: int) -> np.ndarray:
         """All-gather this rank's sim rows [first_row, first_row + count) of the score matrix the last

@@ -686,6 +686,93 @@ def test_profile_splits_solver_time_by_pass_kind():
     be.close()
 
 
+# ----------------------------------------------------------------------------- the whole solve in one launch (solve_persist_kernel)
+def _solve_persist(m, xd, name, pr, rng, nsims, persist, **kw):
+    """One solve with MUSE_PERSIST = persist; returns (result, kernel launches the solve took, hand-backs it saw)."""
+    import os
+    os.environ["MUSE_PERSIST"] = "1" if persist else "0"
+    try:
+        prob = m.SimpleMuseProblem(xd, name, pr())
+        res = m.muse(prob, theta_start(name), rng=rng, nsims=nsims, **kw)      # first solve: allocations
+        be = prob._backend
+        be.profile_reset(True)
+        res = m.muse(prob, theta_start(name), rng=rng, nsims=nsims, **kw)
+        prof = be.profile()
+        passes = be.profile_passes()
+        be.profile_reset(False)
+        prob.close()
+    finally:
+        os.environ.pop("MUSE_PERSIST", None)
+    return res, prof, passes
+
+
+def _assert_identical_solve(a, b, cov=True):
+    assert len(a.history) == len(b.history)
+    np.testing.assert_array_equal(a.theta, b.theta)
+    np.testing.assert_array_equal(np.array(a.gs), np.array(b.gs))
+    if cov:
+        for key in ("J", "H", "Sigma"):
+            np.testing.assert_array_equal(getattr(a, key), getattr(b, key), err_msg=key)
+        np.testing.assert_array_equal(np.array(a.Hs), np.array(b.Hs))
+        np.testing.assert_array_equal(a.metadata["fd_step"], b.metadata["fd_step"])
+    for ha, hb in zip(a.history, b.history):
+        for key in ("theta", "g_like_sims", "g_like_dat", "g_like", "g_prior", "H_inv_post", "H_inv_like"):
+            np.testing.assert_array_equal(ha[key], hb[key], err_msg=key)
+        assert ha["z_history_dat"] == hb["z_history_dat"]
+        for key in ("iters", "fg_evals", "status", "gnorm"):
+            np.testing.assert_array_equal(ha["z_history_sims"][key], hb["z_history_sims"][key], err_msg=key)
+
+
+@pytest.mark.parametrize("name,d,nsims,prior,kw", [
+    ("funnel", 512, 100, True, {}),                                      # the reference's example (warp-per-unit phases)
+    ("funnel", 512, 2500, True, {}),                                     # more units than resident warps
+    ("hiergauss", 5000, 50, False, {}),                                  # TMA-ring phases, nθ = 2
+    ("funnel", 70000, 24, True, {}),                                     # several segments per unit
+    ("hiergauss", 300, 30, True, dict(theta_rtol=0.0, maxsteps=7)),      # 3 passes in the launch, the rest on the chain of launches
+    ("funnel", 6000, 40, True, dict(theta_rtol=1e-2, maxsteps=3)),       # the loop ends with the launch's last pass
+    ("funnel", 6000, 40, True, dict(maxsteps=1)),                        # one pass, then the covariance stage
+])
+def test_one_launch_solve_is_bit_identical_to_the_chain_of_launches(name, d, nsims, prior, kw):
+    """solve_persist_kernel (one cooperative launch: passes, θ updates, get_H!'s fiducial solve and FD sims) against the chain of
+    launches it replaces (streaming kernel + re-solve + theta_step_kernel per pass, cov_prep_kernel, two more chains): the same
+    per-unit arithmetic and the same reduction tree, hence every number of the result bit for bit — and ONE kernel launch."""
+    import museinference_jl_b200 as m
+    oprob, fam, draws, xd = oracle_problem(name, d, nsims)
+    rng = m.BaseDraws(draws.xi, draws.nu, draws.xi_master, draws.nu_master)
+    pr = (lambda: m.NormalPrior([0.0, 0.1][:fam.ntheta], [3.0, 2.0][:fam.ntheta])) if prior else (lambda: None)
+    for cov in (True, False):
+        a, pa, passes = _solve_persist(m, xd, name, pr, rng, nsims, True, get_covariance=cov, fused_driver="device", **kw)
+        b, pb, _ = _solve_persist(m, xd, name, pr, rng, nsims, False, get_covariance=cov, fused_driver="device", **kw)
+        _assert_identical_solve(a, b, cov=cov)
+        n = len(a.history)
+        if n <= 3:
+            assert pa["launches"] == 1 and pa["solve_launches"] == 1, pa
+            assert pb["launches"] > 4
+            assert passes["cold"]["launches"] == 1 and passes["warm"]["launches"] == n - 1
+            assert passes["fd"]["launches"] == (1 if cov else 0)
+            assert all(v["ms"] > 0 for v in passes.values() if v["launches"])
+            assert pa["solve_units"] == pb["solve_units"] and pa["solve_bytes"] == pb["solve_bytes"]
+        else:
+            assert pa["launches"] < pb["launches"]
+
+
+def test_one_launch_solve_gives_way_to_the_chain_when_units_leave_the_fast_path():
+    """atol below round-off: every unit needs the L-BFGS history path, which only the chain's generic kernel has.  The launch
+    notices (hand-backs), gives up, and the solve is re-run on the chain — same result as with MUSE_PERSIST=0, and the next
+    solve with these parameters goes to the chain directly."""
+    import museinference_jl_b200 as m
+    name, d, nsims = "funnel", 600, 40
+    oprob, fam, draws, xd = oracle_problem(name, d, nsims)
+    rng = m.BaseDraws(draws.xi, draws.nu, draws.xi_master, draws.nu_master)
+    pr = lambda: m.NormalPrior(0, 3)
+    kw = dict(get_covariance=True, fused_driver="device", gradz_logLike_atol=1e-300, maxsteps=2)
+    a, pa, _ = _solve_persist(m, xd, name, pr, rng, nsims, True, **kw)
+    b, pb, _ = _solve_persist(m, xd, name, pr, rng, nsims, False, **kw)
+    _assert_identical_solve(a, b)
+    assert pa["launches"] == pb["launches"]          # the measured (second) solve did not try the one-launch form again
+    assert max(h["z_history_sims"]["iters"].max() for h in a.history) >= 2
+
+
 # ----------------------------------------------------------------------------- device-resident outer loop (csrc/muse_outer.cu)
 def _solve_modes(m, xd, name, pr, rng, nsims, modes, **kw):
     res = {}
@@ -881,11 +968,23 @@ def _nccl_worker(rank, world, port, cases, q):
     try:
         pool = m.ShardPool(device=rank)
         outs = []
-        for name, d, nsims, th0, xd, P, L, prior, fused in cases:
+        for name, d, nsims, th0, xd, P, L, prior, fused, exchange in cases:
+            # exchange "p2p": the one-launch solve, score rows stored into the peer's memory by the kernel; "nccl": the chain
+            # of launches with ncclAllGather between pass and θ-step
+            if exchange == "nccl":
+                os.environ["MUSE_EXCHANGE"] = "nccl"
+            else:
+                os.environ.pop("MUSE_EXCHANGE", None)
             prob = m.SimpleMuseProblem(xd, name, m.NormalPrior(0, 3) if prior else None, P=P, L=L)
+            launches = p2p = None
             for seed in (11, 12):          # twice: the second solve of a shape goes through the library's captured graph
+                if seed == 12 and prob._backend is not None:
+                    prob._backend.profile_reset(True)
                 res = m.muse(prob, th0, rng=seed, nsims=nsims, get_covariance=True, pool=pool, fused_driver=fused)
-            outs.append((res.theta, np.array(res.gs), res.H, res.J, res.Sigma, len(res.history)))
+            if prob._backend is not None:
+                launches = prob._backend.profile()["launches"]
+                p2p = prob._backend.p2p_info()
+            outs.append((res.theta, np.array(res.gs), res.H, res.J, res.Sigma, len(res.history), launches, p2p))
             prob.close()
         q.put((rank, outs))
     finally:
@@ -904,11 +1003,13 @@ def test_two_rank_nccl_solve_is_bit_identical_to_one_gpu():
     import torch.multiprocessing as mp
     import museinference_jl_b200 as m
     cases = []
-    for name, d, nsims, prior, fused in (("funnel", 6000, 203, True, True), ("hiergauss", 5001, 120, False, True),
-                                         ("funnel", 512, 301, True, True), ("corrgauss", 256, 100, True, True),
-                                         ("hiergauss", 700, 64, True, False)):
+    for name, d, nsims, prior, fused, exchange in (("funnel", 6000, 203, True, True, "p2p"), ("funnel", 6000, 203, True, True, "nccl"),
+                                                   ("hiergauss", 5001, 120, False, True, "p2p"), ("hiergauss", 5001, 120, False, True, "nccl"),
+                                                   ("funnel", 512, 301, True, True, "p2p"), ("funnel", 512, 5, True, True, "p2p"),
+                                                   ("corrgauss", 256, 100, True, True, "p2p"),
+                                                   ("hiergauss", 700, 64, True, False, "p2p")):
         fam, _, xd = make_inputs(name, d, 1)
-        cases.append((name, d, nsims, theta_start(name), xd, getattr(fam, "P", None), getattr(fam, "L", None), prior, fused))
+        cases.append((name, d, nsims, theta_start(name), xd, getattr(fam, "P", None), getattr(fam, "L", None), prior, fused, exchange))
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
@@ -919,13 +1020,17 @@ def test_two_rank_nccl_solve_is_bit_identical_to_one_gpu():
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
-    for i, (name, d, nsims, th0, xd, P, L, prior, fused) in enumerate(cases):
+    for i, (name, d, nsims, th0, xd, P, L, prior, fused, exchange) in enumerate(cases):
         prob = m.SimpleMuseProblem(xd, name, m.NormalPrior(0, 3) if prior else None, P=P, L=L)
         ref = m.muse(prob, th0, rng=12, nsims=nsims, get_covariance=True, fused_driver=fused)
         prob.close()
         for rank in (0, 1):
-            theta, gs, H, J, Sigma, nhist = got[rank][i]
+            theta, gs, H, J, Sigma, nhist, launches, p2p = got[rank][i]
             assert nhist == len(ref.history)
+            if name != "corrgauss" and fused is True:
+                # the exchange that ran is the one asked for: one launch per solve with the peer-mapped buffers, a chain otherwise
+                assert p2p[1] == (exchange == "p2p"), (name, exchange, p2p)
+                assert (launches == 1) == (exchange == "p2p" and nhist <= 3), (name, exchange, launches)
             np.testing.assert_array_equal(gs, np.array(ref.gs), err_msg=f"{name} rank {rank}: gs")
             np.testing.assert_array_equal(theta, ref.theta, err_msg=f"{name} rank {rank}: θ")
             np.testing.assert_array_equal(H, ref.H, err_msg=f"{name} rank {rank}: H")
