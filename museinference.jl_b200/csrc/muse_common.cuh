@@ -38,6 +38,19 @@ struct DynConsts {
     int pad;
 };
 
+// Lazy ẑ (solve_persist_kernel): when every earlier solve of a unit within the launch took the fast path, its ẑ is an elementwise
+// function of the unit's base normals — level l: x = mus + sig·ξ + ν, g = a(z − mu) − (x − z), z ← z + cspec·(−g) — so a pass
+// recomputes its start vector in registers instead of reading it, and no pass stores ẑ.
+constexpr int kMaxLazy = 4;
+struct LazyLevel {
+    double sig, mus, a, mu, cspec;
+};
+struct LazyLevels {
+    int nlev;        // earlier passes of this launch
+    int store;       // 1: this pass materialises ẑ (the chain of launches may continue from it)
+    LazyLevel lev[kMaxLazy];
+};
+
 // where the start vector z₀ of a unit comes from
 enum StartKind : int {
     kStartZero = 0,        // z₀ ≡ 0, never read from memory
@@ -110,6 +123,7 @@ struct SolveLaunch {
     int* work_next;      // dynamic work counter of the streaming kernel (zeroed before every launch)
     unsigned long long* redo_total;   // … since handle creation (diagnostics)
     int* redo_items;
+    const LazyLevels* lazy;  // non-null (solve_persist_kernel only): z₀ is recomputed, the zstate cells hold per-unit level masks
 };
 
 #if defined(__CUDACC__)

@@ -121,6 +121,7 @@ struct ItemDesc {
     int start_kind;      // StartKind of the unit
     int zst_accept;      // ZState of the unit once the committed step is accepted (buffer that holds ẑ)
     int* zstate_row;     // the unit's zstate cell (null: none)
+    unsigned levmask;    // lazy ẑ: bit l set ⇔ the unit's solve of level l took its step (a 0-iteration solve keeps z)
 };
 // [host-test:end item-desc]
 
@@ -179,6 +180,29 @@ __device__ __forceinline__ double elem3(double p, double q, double z0in, const I
 }
 // [host-test:end elem3]
 
+// lazy ẑ: the unit's current ẑ from its base normals — the committed points of the earlier passes, replayed with the very
+// operations elem3 used to produce them (bit for bit what the chain of launches would have stored and read back)
+template <bool SIM>
+__device__ __forceinline__ double lazy_z0(double p, double q, double zstart, const LazyLevels& LZ, unsigned mask) {
+    double z = zstart;
+    for (int l = 0; l < LZ.nlev; ++l) {
+        if ((mask >> l) & 1u) {
+            const LazyLevel& v = LZ.lev[l];
+            const double x = SIM ? fma(v.sig, p, v.mus) + q : p;
+            const double r0 = x - z, w0 = z - v.mu;
+            const double g0 = fma(v.a, w0, -r0);
+            z = fma(v.cspec, -g0, z);
+        }
+    }
+    return z;
+}
+// ZK: 0 z₀ ≡ 0 · 1 z₀ streamed · 2 z₀ = simulated latent · 3 lazy from zero · 4 lazy from a streamed start row
+template <bool SIM, int ZK>
+__device__ __forceinline__ double elem_zk(double p, double q, double z0in, const IsoEval& ev, const ItemDesc& it, const LazyLevels* LZ, Acc& A) {
+    if (ZK >= 3) return elem3<SIM, 1>(p, q, lazy_z0<SIM>(p, q, ZK == 4 ? z0in : 0.0, *LZ, it.levmask), ev, it.sig, it.mus, A);
+    return elem3<SIM, (ZK >= 3 ? 1 : ZK)>(p, q, z0in, ev, it.sig, it.mus, A);
+}
+
 __device__ __forceinline__ void st2_stream(double* p, double2 v, uint64_t pol) {
     asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(v.x), "d"(v.y), "l"(pol) : "memory");
 }
@@ -186,7 +210,7 @@ __device__ __forceinline__ void st2_stream(double* p, double2 v, uint64_t pol) {
 // one chunk of one item, executed by the consumer threads
 template <bool SIM, int ZK>
 __device__ __forceinline__ void consume_chunk(const double* buf, int base, int len, int d, const ItemDesc& it,
-                                              const IsoEval& ev, int ct, uint64_t pol, Acc& A) {
+                                              const IsoEval& ev, int ct, uint64_t pol, const LazyLevels* LZ, Acc& A) {
     const double* ra = buf;
     const double* rb = buf + kChunk;
     const double* rz = buf + 2 * kChunk;
@@ -198,10 +222,10 @@ __device__ __forceinline__ void consume_chunk(const double* buf, int base, int l
             if (q2 < len) {
                 const double2 p = lds2(ra + q2);
                 const double2 q = SIM ? lds2(rb + q2) : make_double2(0.0, 0.0);
-                const double2 z = (ZK == 1) ? lds2(rz + q2) : make_double2(0.0, 0.0);
+                const double2 z = (ZK == 1 || ZK == 4) ? lds2(rz + q2) : make_double2(0.0, 0.0);
                 double2 zt;
-                zt.x = elem3<SIM, ZK>(p.x, q.x, z.x, ev, it.sig, it.mus, A);
-                zt.y = elem3<SIM, ZK>(p.y, q.y, z.y, ev, it.sig, it.mus, A);
+                zt.x = elem_zk<SIM, ZK>(p.x, q.x, z.x, ev, it, LZ, A);
+                zt.y = elem_zk<SIM, ZK>(p.y, q.y, z.y, ev, it, LZ, A);
                 if (zout) st2_stream(zout + base + q2, zt, pol);
             }
         }
@@ -211,11 +235,11 @@ __device__ __forceinline__ void consume_chunk(const double* buf, int base, int l
             if (j >= d) break;
             const double2 p = lds2(ra + q2);
             const double2 q = SIM ? lds2(rb + q2) : make_double2(0.0, 0.0);
-            const double2 z = (ZK == 1) ? lds2(rz + q2) : make_double2(0.0, 0.0);
+            const double2 z = (ZK == 1 || ZK == 4) ? lds2(rz + q2) : make_double2(0.0, 0.0);
             double2 zt;
-            zt.x = elem3<SIM, ZK>(p.x, q.x, z.x, ev, it.sig, it.mus, A);
+            zt.x = elem_zk<SIM, ZK>(p.x, q.x, z.x, ev, it, LZ, A);
             zt.y = 0.0;
-            if (j + 1 < d) zt.y = elem3<SIM, ZK>(p.y, q.y, z.y, ev, it.sig, it.mus, A);
+            if (j + 1 < d) zt.y = elem_zk<SIM, ZK>(p.y, q.y, z.y, ev, it, LZ, A);
             if (zout) {
                 if (j + 1 < d) st2_stream(zout + j, zt, pol);
                 else zout[j] = zt.x;
@@ -344,6 +368,28 @@ struct WarpCtx {
 };
 // [host-test:end publish]
 
+// lazy ẑ: what changes in a unit's descriptor — no start row unless the user gave one, no ẑ store unless this pass
+// materialises it, the level mask out of the unit's state cell
+__device__ __forceinline__ void lazy_item(const SolveLaunch& L, const Cmd& c, int* zs, const double* zshared, ItemDesc& it, const double*& rz) {
+    const LazyLevels& LZ = *L.lazy;
+    it.levmask = LZ.nlev ? (unsigned)ld_state(zs) : 0u;
+    it.zk = L.zrows ? 4 : 3;
+    rz = L.zrows ? zshared : nullptr;
+    it.zout = LZ.store ? c.zA : nullptr;
+    it.zst_accept = kZA;
+    it.zstate_row = zs;
+    // a pass that materialises ẑ cannot serve a 0-iteration solve (the committed point is written as it goes): treated like a
+    // start that has to be kept — handed back
+    it.start_kind = LZ.store ? (int)kStartSharedKeep : (LZ.nlev ? (int)kStartOwn : c.start_kind);
+}
+// after publish_unit (same thread): the unit's level mask for the next pass (its iteration count says whether it stepped)
+__device__ __forceinline__ void lazy_after_publish(const SolveLaunch& L, const ItemDesc& it) {
+    const LazyLevels& LZ = *L.lazy;
+    if (LZ.store || !it.zstate_row) return;
+    const unsigned stepped = L.iters_out[it.unit] > 0 ? 1u : 0u;
+    *it.zstate_row = (int)(it.levmask | (stepped << LZ.nlev));
+}
+
 // One streaming pass over the launch's units by the three roles of one CTA (file comment).  The body of iso_stream_kernel, and
 // of every phase of solve_persist_kernel (PERSIST: the barriers of the previous phase are invalidated and set up again, the
 // proxies are fenced around the phase — ẑ written with ordinary stores by one phase is read by bulk copies in the next —
@@ -428,9 +474,11 @@ __device__ __forceinline__ void stream_pass(const SolveLaunch& L, Shared& sh, do
                 it.mus = c.smp.mu;
                 it.zk = (c.start_kind == kStartTruth) ? 2 : (c.zcur ? 1 : 0);
                 it.zout = L.discard_z ? nullptr : c.zalt;
+                it.levmask = 0u;
                 const double* ra = it.sim ? c.xi : L.xdat;
                 const double* rb = it.sim ? c.nu : nullptr;
                 const double* rz = it.zk == 1 ? c.zcur : nullptr;
+                if (L.lazy) lazy_item(L, c, zs, zshared, it, rz);
                 const uint64_t apol = it.sim ? pol.first : pol.last;
                 const int nrows = 1 + (rb != nullptr) + (rz != nullptr);
                 for (int k = 0; k < it.nch; ++k) {
@@ -490,7 +538,10 @@ __device__ __forceinline__ void stream_pass(const SolveLaunch& L, Shared& sh, do
             double t[kNRed];
 #pragma unroll
             for (int k = 0; k < kNRed; ++k) t[k] = __shfl_sync(0xffffffffu, acc, k);
-            if (lane == 0) publish_unit(L, it, t);
+            if (lane == 0) {
+                publish_unit(L, it, t);
+                if (L.lazy) lazy_after_publish(L, it);
+            }
             __syncwarp();
         }
         if (dbg && lane == 0) dbg[4] = now_ns();
@@ -521,12 +572,16 @@ __device__ __forceinline__ void stream_pass(const SolveLaunch& L, Shared& sh, do
                 const int base = (it.chunk0 + k) * kChunk;
                 const int len = min(kChunk, L.ld - base);
                 if (it.sim) {
-                    if (it.zk == 0) consume_chunk<true, 0>(buf, base, len, L.d, it, ev, ct, pol.first, A);
-                    else if (it.zk == 1) consume_chunk<true, 1>(buf, base, len, L.d, it, ev, ct, pol.first, A);
-                    else consume_chunk<true, 2>(buf, base, len, L.d, it, ev, ct, pol.first, A);
+                    if (it.zk == 0) consume_chunk<true, 0>(buf, base, len, L.d, it, ev, ct, pol.first, nullptr, A);
+                    else if (it.zk == 1) consume_chunk<true, 1>(buf, base, len, L.d, it, ev, ct, pol.first, nullptr, A);
+                    else if (it.zk == 2) consume_chunk<true, 2>(buf, base, len, L.d, it, ev, ct, pol.first, nullptr, A);
+                    else if (it.zk == 3) consume_chunk<true, 3>(buf, base, len, L.d, it, ev, ct, pol.first, L.lazy, A);
+                    else consume_chunk<true, 4>(buf, base, len, L.d, it, ev, ct, pol.first, L.lazy, A);
                 } else {
-                    if (it.zk == 1) consume_chunk<false, 1>(buf, base, len, L.d, it, ev, ct, pol.first, A);
-                    else consume_chunk<false, 0>(buf, base, len, L.d, it, ev, ct, pol.first, A);
+                    if (it.zk == 1) consume_chunk<false, 1>(buf, base, len, L.d, it, ev, ct, pol.first, nullptr, A);
+                    else if (it.zk == 3) consume_chunk<false, 3>(buf, base, len, L.d, it, ev, ct, pol.first, L.lazy, A);
+                    else if (it.zk == 4) consume_chunk<false, 4>(buf, base, len, L.d, it, ev, ct, pol.first, L.lazy, A);
+                    else consume_chunk<false, 0>(buf, base, len, L.d, it, ev, ct, pol.first, nullptr, A);
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&sh.empty[stage]);
@@ -574,7 +629,7 @@ constexpr int kWarpCta = 256;
 // one unit's sweep by one warp
 template <bool SIM, int ZK>
 __device__ __forceinline__ void warp_unit(const ItemDesc& it, const double* ra, const double* rb, const double* rz, int d,
-                                          const IsoEval& ev, int lane, uint64_t pol, Acc& A) {
+                                          const IsoEval& ev, int lane, uint64_t pol, const LazyLevels* LZ, Acc& A) {
     const int npairs = d >> 1;
     constexpr int U = 4;
     for (int p0 = lane; p0 < npairs; p0 += U * 32) {
@@ -585,22 +640,22 @@ __device__ __forceinline__ void warp_unit(const ItemDesc& it, const double* ra, 
             const bool ok = p < npairs;
             a[k] = ok ? ld2(ra, p) : make_double2(0.0, 0.0);
             b[k] = (SIM && ok) ? ld2(rb, p) : make_double2(0.0, 0.0);
-            z[k] = (ZK == 1 && ok) ? ld2(rz, p) : make_double2(0.0, 0.0);
+            z[k] = ((ZK == 1 || ZK == 4) && ok) ? ld2(rz, p) : make_double2(0.0, 0.0);
         }
 #pragma unroll
         for (int k = 0; k < U; ++k) {
             const int p = p0 + k * 32;
             if (p < npairs) {
                 double2 zt;
-                zt.x = elem3<SIM, ZK>(a[k].x, b[k].x, z[k].x, ev, it.sig, it.mus, A);
-                zt.y = elem3<SIM, ZK>(a[k].y, b[k].y, z[k].y, ev, it.sig, it.mus, A);
+                zt.x = elem_zk<SIM, ZK>(a[k].x, b[k].x, z[k].x, ev, it, LZ, A);
+                zt.y = elem_zk<SIM, ZK>(a[k].y, b[k].y, z[k].y, ev, it, LZ, A);
                 if (it.zout) st2_stream(it.zout + 2 * (size_t)p, zt, pol);
             }
         }
     }
     if ((d & 1) && lane == 0) {                               // odd d: the last element
         const int j = d - 1;
-        const double zt = elem3<SIM, ZK>(ra[j], SIM ? rb[j] : 0.0, ZK == 1 ? rz[j] : 0.0, ev, it.sig, it.mus, A);
+        const double zt = elem_zk<SIM, ZK>(ra[j], SIM ? rb[j] : 0.0, (ZK == 1 || ZK == 4) ? rz[j] : 0.0, ev, it, LZ, A);
         if (it.zout) it.zout[j] = zt;
     }
 }
@@ -632,16 +687,23 @@ __device__ __forceinline__ void warp_pass(const SolveLaunch& L) {
         it.zout = L.discard_z ? nullptr : c.zalt;
         const double* ra = it.sim ? c.xi : L.xdat;
         // [host-test:end warp-item]
+        it.levmask = 0u;
+        const double* rz = c.zcur;
+        if (L.lazy) lazy_item(L, c, zs, zshared, it, rz);
         Acc A;
 #pragma unroll
         for (int k = 0; k < kNRed; ++k) A.v[k] = 0.0;
         if (it.sim) {
-            if (it.zk == 0) warp_unit<true, 0>(it, ra, c.nu, c.zcur, L.d, ev, lane, pol.first, A);
-            else if (it.zk == 1) warp_unit<true, 1>(it, ra, c.nu, c.zcur, L.d, ev, lane, pol.first, A);
-            else warp_unit<true, 2>(it, ra, c.nu, c.zcur, L.d, ev, lane, pol.first, A);
+            if (it.zk == 0) warp_unit<true, 0>(it, ra, c.nu, rz, L.d, ev, lane, pol.first, nullptr, A);
+            else if (it.zk == 1) warp_unit<true, 1>(it, ra, c.nu, rz, L.d, ev, lane, pol.first, nullptr, A);
+            else if (it.zk == 2) warp_unit<true, 2>(it, ra, c.nu, rz, L.d, ev, lane, pol.first, nullptr, A);
+            else if (it.zk == 3) warp_unit<true, 3>(it, ra, c.nu, rz, L.d, ev, lane, pol.first, L.lazy, A);
+            else warp_unit<true, 4>(it, ra, c.nu, rz, L.d, ev, lane, pol.first, L.lazy, A);
         } else {
-            if (it.zk == 1) warp_unit<false, 1>(it, ra, c.nu, c.zcur, L.d, ev, lane, pol.first, A);
-            else warp_unit<false, 0>(it, ra, c.nu, c.zcur, L.d, ev, lane, pol.first, A);
+            if (it.zk == 1) warp_unit<false, 1>(it, ra, c.nu, rz, L.d, ev, lane, pol.first, nullptr, A);
+            else if (it.zk == 3) warp_unit<false, 3>(it, ra, c.nu, rz, L.d, ev, lane, pol.first, L.lazy, A);
+            else if (it.zk == 4) warp_unit<false, 4>(it, ra, c.nu, rz, L.d, ev, lane, pol.first, L.lazy, A);
+            else warp_unit<false, 0>(it, ra, c.nu, rz, L.d, ev, lane, pol.first, nullptr, A);
         }
         double sum_k, mv[kNRed - kNSum];
         warp_reduce(A, lane, sum_k, mv);
@@ -650,7 +712,10 @@ __device__ __forceinline__ void warp_pass(const SolveLaunch& L) {
         for (int k = 0; k < kNSum; ++k) t[k] = __shfl_sync(0xffffffffu, sum_k, 2 * k);
 #pragma unroll
         for (int k = 0; k < kNRed - kNSum; ++k) t[kNSum + k] = mv[k];
-        if (lane == 0) publish_unit(L, it, t);
+        if (lane == 0) {
+            publish_unit(L, it, t);
+            if (L.lazy) lazy_after_publish(L, it);
+        }
         __syncwarp();
     }
 }
@@ -702,6 +767,7 @@ __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned l
 struct PersistShared {
     SolveLaunch L;                    // the phase in flight
     DynConsts dyn[2];                 // its θ-dependent constants ([1]: FD sims)
+    LazyLevels lazy;                  // constants of the launch's earlier passes (lazy ẑ)
     double red[kMaxTheta][32];        // CTA 0: scratch of the reduction tree
     int bad;
     int done, error, abort, timeout;  // CTA 0's message after the phase, as every CTA has read it
@@ -727,6 +793,14 @@ __device__ void phase_launch(const PersistParams& P, int ph, PersistShared& ps) 
         L.zshared = P.z0user;
         L.dyn = &ps.dyn[0];
         ob = &P.slot[ph];
+        if (P.lazy) {
+            // this pass's constants become level ph of the passes that follow; it materialises ẑ only if it is the launch's last
+            // possible pass and the loop may go on after it (on the chain of launches, which starts from stored vectors)
+            ps.lazy.lev[ph] = LazyLevel{ps.dyn[0].smp[0].sig, ps.dyn[0].smp[0].mu, ps.dyn[0].ev.a, ps.dyn[0].ev.mu, ps.dyn[0].ev.cspec};
+            ps.lazy.nlev = ph;
+            ps.lazy.store = (ph == P.max_pass - 1 && P.max_pass < P.step.maxsteps) ? 1 : 0;
+            L.lazy = &ps.lazy;
+        }
     } else if (ph == kPhaseFid) {        // fiducial MAP of the master stream's draw from zero(z)   — src/muse.jl:417-423
         L.nitems = 1;
         L.mode = 2;
@@ -755,6 +829,7 @@ __device__ void phase_launch(const PersistParams& P, int ph, PersistShared& ps) 
     L.g_out = ob->g; L.iters_out = ob->iters; L.fg_out = ob->fg;
     L.gnorm_out = ob->gnorm; L.f_out = ob->f; L.status_out = ob->status;
     L.zrows = (L.start_kind == kStartOwn || L.start_kind == kStartShared || L.start_kind == kStartSharedKeep) ? 1 : 0;
+    if (L.lazy) L.zrows = P.first_kind == kStartSharedKeep ? 1 : 0;      // only a user start vector is ever streamed
     L.stream_stages = L.zrows ? 4 : 6;
 }
 

@@ -324,6 +324,7 @@ extern "C" int muse_b200_muse_solve(muse_handle* h, const double* theta0, int32_
     // (read at every call, so that one process can hold the two paths against each other)
     const bool persist_on = [] { const char* e = std::getenv("MUSE_PERSIST"); return !e || std::atoi(e) != 0; }();
     const bool p2p_on = [] { const char* e = std::getenv("MUSE_EXCHANGE"); return !e || std::strcmp(e, "nccl") != 0; }();
+    const bool lazy_on = [] { const char* e = std::getenv("MUSE_LAZY"); return !e || std::atoi(e) != 0; }();   // lazy ẑ
     if (h->persist_grid < 0) {
         int g = 0, t = 0;
         if (iso_persist_geometry(h->geo, h->cfg.device, &g, &t) != cudaSuccess) { cudaGetLastError(); g = 0; }
@@ -346,7 +347,7 @@ extern "C" int muse_b200_muse_solve(muse_handle* h, const double* theta0, int32_
         pkey.insert(pkey.end(), reinterpret_cast<const unsigned char*>(dbl), reinterpret_cast<const unsigned char*>(dbl) + sizeof(dbl));
         pkey.insert(pkey.end(), reinterpret_cast<const unsigned char*>(ints), reinterpret_cast<const unsigned char*>(ints) + sizeof(ints));
     }
-    if (persist_on && h->persist_grid > 0 && !h->dbg && (!multi || p2p_fit) && pkey != h->persist_off_key) {
+    if (persist_on && h->persist_grid > 0 && nt <= 2 && !h->dbg && (!multi || p2p_fit) && pkey != h->persist_off_key) {
         const auto t0 = std::chrono::steady_clock::now();
         if (!h->persist_ctl) {
             OUTER_TRY(h, cudaMalloc(&h->persist_ctl, sizeof(PersistCtl)));
@@ -368,6 +369,7 @@ extern "C" int muse_b200_muse_solve(muse_handle* h, const double* theta0, int32_
         Q.first_kind = first_start == MUSE_START_USER ? kStartSharedKeep : kStartZero;
         Q.max_pass = std::min((int)maxsteps, kOuterSlots);
         Q.get_cov = get_covariance ? 1 : 0;
+        Q.lazy = lazy_on ? 1 : 0;
         Q.nh_mine = std::max(0, nh_mine);
         Q.z0user = h->z0user;
         const bool hshard = h->cfg.nsims_h > 0;
@@ -431,6 +433,7 @@ extern "C" int muse_b200_muse_solve(muse_handle* h, const double* theta0, int32_
             // a unit left the fast path somewhere (on any rank: the flag travels with the exchange): this configuration goes
             // through the chain of launches, whose generic kernel re-solves such units — from scratch, now and from now on
             h->persist_off_key = pkey;
+            if (lazy_on) OUTER_TRY(h, cudaMemsetAsync(h->zstate, 0, (size_t)h->rows * sizeof(int), h->stream));
             if (ea) { cudaEventDestroy(ea); cudaEventDestroy(eb); }
         } else {
             const int n_now = sh_->n_iter;
@@ -441,6 +444,12 @@ extern "C" int muse_b200_muse_solve(muse_handle* h, const double* theta0, int32_
             const double chunk_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
             if (sh_->error == 1) { if (ea) { cudaEventDestroy(ea); cudaEventDestroy(eb); } h->err = "muse!: MAP solution failed with a non-finite objective"; return MUSE_ESTATE; }
             const bool cov_ran = get_covariance && sh_->done != 0 && sh_->error == 0;
+            if (std::getenv("MUSE_DEBUG_TIMING")) {
+                const long long* T = sh_->stamp;
+                std::fprintf(stderr, "[muse_solve persist rank %d] n_iter=%d host %.1f us | kernel stamps (us since start):", h->comm_rank, n_now, chunk_s * 1e6);
+                for (int k = 1; k < 12; ++k) std::fprintf(stderr, " %.1f", T[k] ? (double)(T[k] - T[0]) * 1e-3 : -1.0);
+                std::fprintf(stderr, "\n");
+            }
             {   // statistics: one launch; units and algorithmic bytes of the phases that ran, their times from CTA 0's globaltimer stamps
                 const double d8 = 8.0 * h->cfg.d;
                 const long long* T = sh_->stamp;
@@ -454,7 +463,14 @@ extern "C" int muse_b200_muse_solve(muse_handle* h, const double* theta0, int32_
                 for (int i = 1; i <= n_now; ++i) {
                     const bool warm = i > 1 || first_start == MUSE_START_USER;
                     const double z0b = warm ? d8 : 0.0;
-                    add(warm ? MUSE_PASS_WARM : MUSE_PASS_COLD, units, nloc * (3 * d8 + z0b) + (2 * d8 + z0b), i == 1 ? T[0] : T[2 + 2 * (i - 2)], T[1 + 2 * (i - 1)]);
+                    // algorithmic bytes: per sim read ξ, ν [+ z₀], write ẑ; lazy ẑ: read ξ, ν only (a user start row is shared by
+                    // all units: counted once), ẑ written only by a pass that materialises it
+                    double bytes = nloc * (3 * d8 + z0b) + (2 * d8 + z0b);
+                    if (lazy_on) {
+                        const bool stored = i == Q.max_pass && Q.max_pass < maxsteps;
+                        bytes = nloc * 2 * d8 + d8 + (first_start == MUSE_START_USER ? d8 : 0.0) + (stored ? units * d8 : 0.0);
+                    }
+                    add(warm ? MUSE_PASS_WARM : MUSE_PASS_COLD, units, bytes, i == 1 ? T[0] : T[2 + 2 * (i - 2)], T[1 + 2 * (i - 1)]);
                 }
                 if (cov_ran && nh_mine > 0) {
                     add(MUSE_PASS_FIDUCIAL, 1, 3 * d8, T[2 + 2 * (n_now - 1)], T[1 + 2 * kPhaseFid]);
@@ -467,6 +483,9 @@ extern "C" int muse_b200_muse_solve(muse_handle* h, const double* theta0, int32_
                     h->recs.push_back(r);
                 }
             }
+            // lazy ẑ: the state cells hold level masks unless the last pass materialised ẑ — no resident ẑ is left behind
+            if (lazy_on && !(n_now == Q.max_pass && Q.max_pass < maxsteps))
+                OUTER_TRY(h, cudaMemsetAsync(h->zstate, 0, (size_t)h->rows * sizeof(int), h->stream));
             if (multi) { gall_h = h->p2p_host; gall_h_stride = x_blk; }
             copy_history(1, n_now, chunk_s);
             if (multi) { gall_h = h->outer_gall_h; gall_h_stride = gall_doubles; }

@@ -88,6 +88,7 @@ struct PersistParams {
     int first_kind;           // StartKind of pass 1
     int max_pass;             // passes this launch may run (≤ kOuterSlots)
     int get_cov, nh_mine;
+    int lazy;                 // 1: ẑ is recomputed from the base normals instead of stored and re-read (muse_common.cuh: LazyLevels)
     const double *z0user, *xi_fd, *nu_fd;
     double *zfidA, *zfidB;
     OutPtrs slot[kOuterSlots], fd;
@@ -186,7 +187,7 @@ template <int V>
 __device__ inline void block_mean_var(const double* g, const int* counts, int nranks, long long need, int nt, int n_total,
                                       double (*sh)[32], double* mean, double* var) {
     if (nt == 1) block_mean_var_nt<V, 1>(g, counts, nranks, need, nt, n_total, sh, mean, var);
-    else if (nt == 2) block_mean_var_nt<V, 2>(g, counts, nranks, need, nt, n_total, sh, mean, var);
+    else if (nt == 2 || V > 1) block_mean_var_nt<V, 2>(g, counts, nranks, need, nt, n_total, sh, mean, var);   // V > 1 (one-launch solve): nθ ≤ 2 (host check)
     else block_mean_var_nt<V, kMaxTheta>(g, counts, nranks, need, nt, n_total, sh, mean, var);
 }
 
@@ -201,15 +202,32 @@ __device__ inline void theta_step_body(const OuterParams& P, double (*sh)[32], i
     // src/interface.jl:170.  The decision must be the same on every rank: with several ranks it is taken from what all of them
     // see — the replicated data unit and the gathered rows, in which a failed sim arrives as NaN (muse_comm.cu / the exchange
     // of solve_persist_kernel)
+    // (loads issued eight at a time: one CTA scanning 10⁴ units is bound by the latency of dependent round trips to the L2)
+    bool mine = false;
     if (P.nranks > 1) {
-        if (threadIdx.x == 0 && __ldcg(P.status_local) == MUSE_STATUS_NONFINITE) *bad = 1;
-        for (int q = 0; q < P.nranks; ++q)
-            for (int e = threadIdx.x; e < P.counts[q] * P.nt; e += blockDim.x)
-                if (isnan(__ldcg(P.g_all + (size_t)q * P.need + e))) *bad = 1;
+        if (threadIdx.x == 0 && __ldcg(P.status_local) == MUSE_STATUS_NONFINITE) mine = true;
+        for (int q = 0; q < P.nranks; ++q) {
+            const double* g = P.g_all + (size_t)q * P.need;
+            const int n = P.counts[q] * P.nt;
+            for (int e = threadIdx.x; e < n; e += 8 * blockDim.x) {
+                double v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { const int i = e + u * blockDim.x; v[u] = i < n ? __ldcg(g + i) : 0.0; }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) mine = mine || isnan(v[u]);
+            }
+        }
     } else {
-        for (int u = threadIdx.x; u < P.units_local; u += blockDim.x)
-            if (__ldcg(P.status_local + u) == MUSE_STATUS_NONFINITE) *bad = 1;
+        const int n = P.units_local;
+        for (int e = threadIdx.x; e < n; e += 8 * blockDim.x) {
+            int v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { const int i = e + u * blockDim.x; v[u] = i < n ? __ldcg(P.status_local + i) : 0; }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) mine = mine || v[u] == MUSE_STATUS_NONFINITE;
+        }
     }
+    if (mine) *bad = 1;
     __syncthreads();
     if (*bad) {
         if (threadIdx.x == 0) { st->error = 1; st->done = 1; if (P.dyn_next) P.dyn_next->skip = 1; }

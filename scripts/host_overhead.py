@@ -17,7 +17,7 @@ def wrap(name):
     setattr(be, name, g)
 for nm in ("map_score", "fd_jacobian", "muse_iterate", "muse_covariance", "muse_solve"):
     wrap(nm)
-K = 50
+K = int(os.environ.get("MUSE_K", 50))
 be.profile_reset(True)
 t0 = time.perf_counter()
 for _ in range(K):
