@@ -247,25 +247,37 @@ class B200Backend:
     def muse_solve(self, theta0, nsims_total: int, counts, maxsteps: int, theta_rtol, atol, alpha, first_start: int,
                    prior_mean=None, prior_sigma=None, get_covariance: bool = False, nsims_h_total: int = 0, counts_h=None):
         """Loop + covariance stage with the θ update on the device (include/muse_b200.h: muse_b200_muse_solve).
-        Returns (iterate dict as muse_iterate, covariance dict as muse_covariance or None)."""
+        Returns (iterate dict as muse_iterate, covariance dict as muse_covariance or None).  The ctypes argument objects and
+        the small input / output buffers are built once per call shape and reused (they cost more than the call)."""
         nt, N, K = self.ntheta, int(nsims_total), int(maxsteps)
-        t0 = self._theta(theta0)
         res, o = self._iterate_buffers(K, N)
-        cnt = np.ascontiguousarray(counts, dtype=np.int32) if counts is not None else None
-        cnth = np.ascontiguousarray(counts_h, dtype=np.int32) if counts_h is not None else None
-        pm = self._theta(prior_mean) if prior_mean is not None else None
-        ps = self._theta(prior_sigma) if prior_sigma is not None else None
-        cres, co = None, None
-        if get_covariance:
-            cres = dict(J=np.zeros((nt, nt)), step=np.zeros(nt), Hs=np.zeros((int(nsims_h_total), nt, nt)), H=np.zeros((nt, nt)),
-                        Sigma_inv=np.zeros((nt, nt)), Sigma=np.zeros((nt, nt)))
-            co = _capi.muse_cov_out(**{k: _dp(v) for k, v in cres.items()})
-        self._check(self._lib.muse_b200_muse_solve(self._h, _dp(t0), N, _ip(cnt), K, float(theta_rtol), float(atol), float(alpha),
-                                                   int(first_start), _dp(pm), _dp(ps), int(bool(get_covariance)), int(nsims_h_total),
-                                                   _ip(cnth), C.byref(o), C.byref(co) if co is not None else None))
+        key = (K, N, bool(get_covariance), int(nsims_h_total), None if counts is None else tuple(int(c) for c in counts),
+               None if counts_h is None else tuple(int(c) for c in counts_h), prior_mean is None, prior_sigma is None)
+        cache = self.__dict__.setdefault("_solve_args", {})
+        a = cache.get(key)
+        if a is None:
+            cache.clear()
+            a = dict(t0=np.zeros(nt), pm=np.zeros(nt), ps=np.ones(nt),
+                     cnt=np.ascontiguousarray(counts, dtype=np.int32) if counts is not None else None,
+                     cnth=np.ascontiguousarray(counts_h, dtype=np.int32) if counts_h is not None else None)
+            a["cres"] = dict(J=np.zeros((nt, nt)), step=np.zeros(nt), Hs=np.zeros((int(nsims_h_total), nt, nt)), H=np.zeros((nt, nt)),
+                             Sigma_inv=np.zeros((nt, nt)), Sigma=np.zeros((nt, nt))) if get_covariance else None
+            a["co"] = _capi.muse_cov_out(**{k: _dp(v) for k, v in a["cres"].items()}) if get_covariance else None
+            a["ptr"] = (_dp(a["t0"]), _ip(a["cnt"]), _dp(a["pm"]) if prior_mean is not None else None,
+                        _dp(a["ps"]) if prior_sigma is not None else None, _ip(a["cnth"]), C.byref(o),
+                        C.byref(a["co"]) if get_covariance else None)
+            cache[key] = a
+        a["t0"][:] = theta0
+        if prior_mean is not None:
+            a["pm"][:] = prior_mean
+        if prior_sigma is not None:
+            a["ps"][:] = prior_sigma
+        t0p, cntp, pmp, psp, cnthp, op, cop = a["ptr"]
+        self._check(self._lib.muse_b200_muse_solve(self._h, t0p, N, cntp, K, float(theta_rtol), float(atol), float(alpha),
+                                                   int(first_start), pmp, psp, 1 if get_covariance else 0, int(nsims_h_total), cnthp, op, cop))
         out = dict(res)
         out["n_iter"] = int(o.n_iter)
-        return out, cres
+        return out, ({k: v.copy() for k, v in a["cres"].items()} if get_covariance else None)
 
     def muse_covariance(self, theta, gs, nsims_h_total: int, counts_h, atol, prior_sigma=None):
         """J, FD Jacobians, H and Σ after the loop (include/muse_b200.h: muse_b200_muse_covariance)."""

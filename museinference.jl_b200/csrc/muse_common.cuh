@@ -123,6 +123,9 @@ struct SolveLaunch {
     int* work_next;      // dynamic work counter of the streaming kernel (zeroed before every launch)
     unsigned long long* redo_total;   // … since handle creation (diagnostics)
     int* redo_items;
+    int lean;                // 1 (solve_persist_kernel only): the α = 1 trial is not evaluated element by element — for these families
+                             // φ′(1) = a·‖∇f(z₀)‖² and φ(1) = φ(0) − ‖∇f‖² + ½(1 + a)‖∇f‖² exactly, and only their sign / finiteness and the
+                             // secant step (≡ c_spec) enter the decisions (muse_iso_stream.cu: fast_replay)
     const LazyLevels* lazy;  // non-null (solve_persist_kernel only): z₀ is recomputed, the zstate cells hold per-unit level masks
 };
 

@@ -110,6 +110,7 @@ struct muse_handle {
     // the whole solve in one cooperative launch (solve_persist_kernel, muse_iso_stream.cu)
     void* persist_ctl = nullptr;                         // muse::PersistCtl, device, zero between launches
     int persist_grid = -1, persist_threads = 0;          // −1: not queried yet; 0: unavailable
+    cudaEvent_t persist_ev[2] = {nullptr, nullptr};      // profiling: the launch's event pair (read right after the solve's synchronisation)
     std::vector<unsigned char> persist_off_key;          // parameters with which the launch gave up (hand-backs): straight to the chain
 
     // exchange through peer-mapped memory (muse_comm.cu: muse_b200_p2p_*): this rank's region and the peers' mappings of theirs

@@ -138,7 +138,7 @@ struct Acc {
 };
 
 // one element: the three evaluations of the fast path (see the file comment)
-template <bool SIM, int ZK>
+template <bool SIM, int ZK, bool LEAN = false>
 __device__ __forceinline__ double elem3(double p, double q, double z0in, const IsoEval& ev, double sig, double mus,
                                         Acc& A) {
     double x, z0;
@@ -158,13 +158,15 @@ __device__ __forceinline__ double elem3(double p, double q, double z0in, const I
     A.v[rS1_0] += w0;
     A.v[rGG0] = fma(g0, g0, A.v[rGG0]);
     A.v[rGM0] = fmax(A.v[rGM0], fabs(g0));
-    // φ(1), φ'(1) along s = −∇f(z₀)
-    const double z1 = z0 - g0;
-    const double r1 = x - z1, w1 = z1 - ev.mu;
-    const double g1 = fma(ev.a, w1, -r1);
-    A.v[rR1] = fma(r1, r1, A.v[rR1]);
-    A.v[rS2_1] = fma(w1, w1, A.v[rS2_1]);
-    A.v[rDP1] = fma(g1, -g0, A.v[rDP1]);
+    // φ(1), φ'(1) along s = −∇f(z₀)   (LEAN: left to fast_replay's closed forms, see SolveLaunch::lean)
+    if (!LEAN) {
+        const double z1 = z0 - g0;
+        const double r1 = x - z1, w1 = z1 - ev.mu;
+        const double g1 = fma(ev.a, w1, -r1);
+        A.v[rR1] = fma(r1, r1, A.v[rR1]);
+        A.v[rS2_1] = fma(w1, w1, A.v[rS2_1]);
+        A.v[rDP1] = fma(g1, -g0, A.v[rDP1]);
+    }
     // speculated committed trial at c_spec
     const double zt = fma(ev.cspec, -g0, z0);
     const double rt = x - zt, wt = zt - ev.mu;
@@ -175,7 +177,7 @@ __device__ __forceinline__ double elem3(double p, double q, double z0in, const I
     A.v[rDPT] = fma(gt, -g0, A.v[rDPT]);
     A.v[rGGT] = fma(gt, gt, A.v[rGGT]);
     A.v[rGMT] = fmax(A.v[rGMT], fabs(gt));
-    A.v[rXC] = fmax(A.v[rXC], fabs(zt - z0));
+    if (!LEAN) A.v[rXC] = fmax(A.v[rXC], fabs(zt - z0));
     return zt;
 }
 // [host-test:end elem3]
@@ -183,24 +185,40 @@ __device__ __forceinline__ double elem3(double p, double q, double z0in, const I
 // lazy ẑ: the unit's current ẑ from its base normals — the committed points of the earlier passes, replayed with the very
 // operations elem3 used to produce them (bit for bit what the chain of launches would have stored and read back)
 template <bool SIM>
-__device__ __forceinline__ double lazy_z0(double p, double q, double zstart, const LazyLevels& LZ, unsigned mask) {
+__device__ __forceinline__ double lazy_level(double p, double q, double z, const LazyLevel& v) {
+    const double x = SIM ? fma(v.sig, p, v.mus) + q : p;
+    const double r0 = x - z, w0 = z - v.mu;
+    const double g0 = fma(v.a, w0, -r0);
+    return fma(v.cspec, -g0, z);
+}
+// what a consumer needs of the launch's lazy description (the levels stay in shared memory: broadcast reads, no registers held
+// across the element loop)
+struct LazyView {
+    const LazyLevels* all;
+    int nlev;
+};
+template <bool SIM>
+__device__ __forceinline__ double lazy_z0(double p, double q, double zstart, const LazyView& LV, unsigned mask) {
     double z = zstart;
-    for (int l = 0; l < LZ.nlev; ++l) {
-        if ((mask >> l) & 1u) {
-            const LazyLevel& v = LZ.lev[l];
-            const double x = SIM ? fma(v.sig, p, v.mus) + q : p;
-            const double r0 = x - z, w0 = z - v.mu;
-            const double g0 = fma(v.a, w0, -r0);
-            z = fma(v.cspec, -g0, z);
-        }
+    if (LV.nlev == 1) {                      // the hot case: the second pass of a solve
+        if (mask & 1u) z = lazy_level<SIM>(p, q, z, LV.all->lev[0]);
+        return z;
     }
+    for (int l = 0; l < LV.nlev; ++l)
+        if ((mask >> l) & 1u) z = lazy_level<SIM>(p, q, z, LV.all->lev[l]);
     return z;
 }
 // ZK: 0 z₀ ≡ 0 · 1 z₀ streamed · 2 z₀ = simulated latent · 3 lazy from zero · 4 lazy from a streamed start row
-template <bool SIM, int ZK>
-__device__ __forceinline__ double elem_zk(double p, double q, double z0in, const IsoEval& ev, const ItemDesc& it, const LazyLevels* LZ, Acc& A) {
-    if (ZK >= 3) return elem3<SIM, 1>(p, q, lazy_z0<SIM>(p, q, ZK == 4 ? z0in : 0.0, *LZ, it.levmask), ev, it.sig, it.mus, A);
-    return elem3<SIM, (ZK >= 3 ? 1 : ZK)>(p, q, z0in, ev, it.sig, it.mus, A);
+template <bool SIM, int ZK, bool LEAN>
+__device__ __forceinline__ double elem_zk(double p, double q, double z0in, const IsoEval& ev, const ItemDesc& it, const LazyView& LV, Acc& A) {
+    if (ZK >= 3) return elem3<SIM, 1, LEAN>(p, q, lazy_z0<SIM>(p, q, ZK == 4 ? z0in : 0.0, LV, it.levmask), ev, it.sig, it.mus, A);
+    return elem3<SIM, (ZK >= 3 ? 1 : ZK), LEAN>(p, q, z0in, ev, it.sig, it.mus, A);
+}
+__device__ __forceinline__ LazyView lazy_view(const SolveLaunch& L) {
+    LazyView LV;
+    LV.all = L.lazy;
+    LV.nlev = L.lazy ? L.lazy->nlev : 0;
+    return LV;
 }
 
 __device__ __forceinline__ void st2_stream(double* p, double2 v, uint64_t pol) {
@@ -208,9 +226,9 @@ __device__ __forceinline__ void st2_stream(double* p, double2 v, uint64_t pol) {
 }
 
 // one chunk of one item, executed by the consumer threads
-template <bool SIM, int ZK>
+template <bool SIM, int ZK, bool LEAN>
 __device__ __forceinline__ void consume_chunk(const double* buf, int base, int len, int d, const ItemDesc& it,
-                                              const IsoEval& ev, int ct, uint64_t pol, const LazyLevels* LZ, Acc& A) {
+                                              const IsoEval& ev, int ct, uint64_t pol, const LazyView& LV, Acc& A) {
     const double* ra = buf;
     const double* rb = buf + kChunk;
     const double* rz = buf + 2 * kChunk;
@@ -224,8 +242,8 @@ __device__ __forceinline__ void consume_chunk(const double* buf, int base, int l
                 const double2 q = SIM ? lds2(rb + q2) : make_double2(0.0, 0.0);
                 const double2 z = (ZK == 1 || ZK == 4) ? lds2(rz + q2) : make_double2(0.0, 0.0);
                 double2 zt;
-                zt.x = elem_zk<SIM, ZK>(p.x, q.x, z.x, ev, it, LZ, A);
-                zt.y = elem_zk<SIM, ZK>(p.y, q.y, z.y, ev, it, LZ, A);
+                zt.x = elem_zk<SIM, ZK, LEAN>(p.x, q.x, z.x, ev, it, LV, A);
+                zt.y = elem_zk<SIM, ZK, LEAN>(p.y, q.y, z.y, ev, it, LV, A);
                 if (zout) st2_stream(zout + base + q2, zt, pol);
             }
         }
@@ -237,9 +255,9 @@ __device__ __forceinline__ void consume_chunk(const double* buf, int base, int l
             const double2 q = SIM ? lds2(rb + q2) : make_double2(0.0, 0.0);
             const double2 z = (ZK == 1 || ZK == 4) ? lds2(rz + q2) : make_double2(0.0, 0.0);
             double2 zt;
-            zt.x = elem_zk<SIM, ZK>(p.x, q.x, z.x, ev, it, LZ, A);
+            zt.x = elem_zk<SIM, ZK, LEAN>(p.x, q.x, z.x, ev, it, LV, A);
             zt.y = 0.0;
-            if (j + 1 < d) zt.y = elem_zk<SIM, ZK>(p.y, q.y, z.y, ev, it, LZ, A);
+            if (j + 1 < d) zt.y = elem_zk<SIM, ZK, LEAN>(p.y, q.y, z.y, ev, it, LV, A);
             if (zout) {
                 if (j + 1 < d) st2_stream(zout + j, zt, pol);
                 else zout[j] = zt.x;
@@ -309,7 +327,10 @@ __device__ __noinline__ bool fast_replay(const SolveLaunch& L, int start_kind, c
     const double phi_0 = f0, dphi_0 = -gg0;
     if (dphi_0 >= 0.0 || dphi_0 >= kEpsD * fabs(phi_0)) return false;
     const double phi_lim = phi_0 + epsilon * fabs(phi_0);
-    const double phi1 = fma(0.5, fma(ev.a, t[rS2_1], t[rR1]), ev.half_cst), dphi1 = t[rDP1];
+    const bool lean = L.lean != 0;
+    // lean: ∇f(z₀ + s) = −a·∇f(z₀) for these families, hence φ′(1) = a‖∇f(z₀)‖² and φ(1) = φ(0) + φ′(0) + ½(1 + a)‖∇f(z₀)‖²
+    const double phi1 = lean ? phi_0 + dphi_0 + 0.5 * (1.0 + ev.a) * gg0 : fma(0.5, fma(ev.a, t[rS2_1], t[rR1]), ev.half_cst);
+    const double dphi1 = lean ? ev.a * gg0 : t[rDP1];
     if (!(fin(phi1) && fin(dphi1))) return false;
     if (!(dphi1 >= 0.0)) return false;                               // B0: bracket (a, b) = (0, 1)
     const double c = (0.0 * dphi1 - 1.0 * dphi_0) / (dphi1 - dphi_0);    // secant(a, b)
@@ -321,7 +342,7 @@ __device__ __noinline__ bool fast_replay(const SolveLaunch& L, int start_kind, c
     // the step is taken; assess_convergence
     const double gg = t[rGGT], gmax = t[rGMT];
     if (!fin(phic) || !fin(gg)) return false;
-    const bool x_conv = t[rXC] <= 0.0, g_conv = gmax <= L.atol;
+    const bool x_conv = !lean && t[rXC] <= 0.0, g_conv = gmax <= L.atol;     // lean: max|Δz| is not tracked — an exactly unchanged x is handed back
     if (!(x_conv || g_conv)) return false;                           // a second iteration would follow
     r.f = phic; r.gmax = gmax; r.s1 = t[rS1T]; r.s2 = t[rS2T];
     r.iters = 1; r.fg = 3; r.flip = true;
@@ -367,6 +388,41 @@ struct WarpCtx {
     int tid;
 };
 // [host-test:end publish]
+
+template <bool LEAN>
+__device__ __forceinline__ void consume_dispatch_l(const double* buf, int base, int len, const SolveLaunch& L, const ItemDesc& it, const IsoEval& ev,
+                                                   int ct, uint64_t pol, const LazyView& LV, Acc& A) {
+    if (it.sim) {
+        if (it.zk == 0) consume_chunk<true, 0, LEAN>(buf, base, len, L.d, it, ev, ct, pol, LV, A);
+        else if (it.zk == 1) consume_chunk<true, 1, LEAN>(buf, base, len, L.d, it, ev, ct, pol, LV, A);
+        else if (it.zk == 2) consume_chunk<true, 2, LEAN>(buf, base, len, L.d, it, ev, ct, pol, LV, A);
+        else if (it.zk == 3) consume_chunk<true, 3, LEAN>(buf, base, len, L.d, it, ev, ct, pol, LV, A);
+        else consume_chunk<true, 4, LEAN>(buf, base, len, L.d, it, ev, ct, pol, LV, A);
+    } else {
+        if (it.zk == 1) consume_chunk<false, 1, LEAN>(buf, base, len, L.d, it, ev, ct, pol, LV, A);
+        else if (it.zk == 3) consume_chunk<false, 3, LEAN>(buf, base, len, L.d, it, ev, ct, pol, LV, A);
+        else if (it.zk == 4) consume_chunk<false, 4, LEAN>(buf, base, len, L.d, it, ev, ct, pol, LV, A);
+        else consume_chunk<false, 0, LEAN>(buf, base, len, L.d, it, ev, ct, pol, LV, A);
+    }
+}
+// lean evaluation and lazy ẑ exist in solve_persist_kernel only: the single-pass kernels of the chain of launches keep their code
+template <bool PERSIST>
+__device__ __forceinline__ void consume_dispatch(const double* buf, int base, int len, const SolveLaunch& L, const ItemDesc& it, const IsoEval& ev,
+                                                 int ct, uint64_t pol, const LazyView& LV, Acc& A) {
+    if constexpr (PERSIST) {
+        if (L.lean) consume_dispatch_l<true>(buf, base, len, L, it, ev, ct, pol, LV, A);
+        else consume_dispatch_l<false>(buf, base, len, L, it, ev, ct, pol, LV, A);
+    } else {
+        if (it.sim) {
+            if (it.zk == 0) consume_chunk<true, 0, false>(buf, base, len, L.d, it, ev, ct, pol, LV, A);
+            else if (it.zk == 1) consume_chunk<true, 1, false>(buf, base, len, L.d, it, ev, ct, pol, LV, A);
+            else consume_chunk<true, 2, false>(buf, base, len, L.d, it, ev, ct, pol, LV, A);
+        } else {
+            if (it.zk == 1) consume_chunk<false, 1, false>(buf, base, len, L.d, it, ev, ct, pol, LV, A);
+            else consume_chunk<false, 0, false>(buf, base, len, L.d, it, ev, ct, pol, LV, A);
+        }
+    }
+}
 
 // lazy ẑ: what changes in a unit's descriptor — no start row unless the user gave one, no ẑ store unless this pass
 // materialises it, the level mask out of the unit's state cell
@@ -478,7 +534,7 @@ __device__ __forceinline__ void stream_pass(const SolveLaunch& L, Shared& sh, do
                 const double* ra = it.sim ? c.xi : L.xdat;
                 const double* rb = it.sim ? c.nu : nullptr;
                 const double* rz = it.zk == 1 ? c.zcur : nullptr;
-                if (L.lazy) lazy_item(L, c, zs, zshared, it, rz);
+                if (PERSIST && L.lazy) lazy_item(L, c, zs, zshared, it, rz);
                 const uint64_t apol = it.sim ? pol.first : pol.last;
                 const int nrows = 1 + (rb != nullptr) + (rz != nullptr);
                 for (int k = 0; k < it.nch; ++k) {
@@ -540,7 +596,7 @@ __device__ __forceinline__ void stream_pass(const SolveLaunch& L, Shared& sh, do
             for (int k = 0; k < kNRed; ++k) t[k] = __shfl_sync(0xffffffffu, acc, k);
             if (lane == 0) {
                 publish_unit(L, it, t);
-                if (L.lazy) lazy_after_publish(L, it);
+                if (PERSIST && L.lazy) lazy_after_publish(L, it);
             }
             __syncwarp();
         }
@@ -550,6 +606,7 @@ __device__ __forceinline__ void stream_pass(const SolveLaunch& L, Shared& sh, do
         const int ct = (int)threadIdx.x - 64, cw = warp - 2;
         const IsoEval ev = launch_ev(L);
         const L2Policy pol = make_policies();
+        const LazyView LV = PERSIST ? lazy_view(L) : LazyView{nullptr, 0};
         int stage = 0;
         uint32_t phase = 0;
         for (int i = 0;; ++i) {
@@ -571,18 +628,7 @@ __device__ __forceinline__ void stream_pass(const SolveLaunch& L, Shared& sh, do
                 const double* buf = ring + (size_t)stage * rows * kChunk;
                 const int base = (it.chunk0 + k) * kChunk;
                 const int len = min(kChunk, L.ld - base);
-                if (it.sim) {
-                    if (it.zk == 0) consume_chunk<true, 0>(buf, base, len, L.d, it, ev, ct, pol.first, nullptr, A);
-                    else if (it.zk == 1) consume_chunk<true, 1>(buf, base, len, L.d, it, ev, ct, pol.first, nullptr, A);
-                    else if (it.zk == 2) consume_chunk<true, 2>(buf, base, len, L.d, it, ev, ct, pol.first, nullptr, A);
-                    else if (it.zk == 3) consume_chunk<true, 3>(buf, base, len, L.d, it, ev, ct, pol.first, L.lazy, A);
-                    else consume_chunk<true, 4>(buf, base, len, L.d, it, ev, ct, pol.first, L.lazy, A);
-                } else {
-                    if (it.zk == 1) consume_chunk<false, 1>(buf, base, len, L.d, it, ev, ct, pol.first, nullptr, A);
-                    else if (it.zk == 3) consume_chunk<false, 3>(buf, base, len, L.d, it, ev, ct, pol.first, L.lazy, A);
-                    else if (it.zk == 4) consume_chunk<false, 4>(buf, base, len, L.d, it, ev, ct, pol.first, L.lazy, A);
-                    else consume_chunk<false, 0>(buf, base, len, L.d, it, ev, ct, pol.first, nullptr, A);
-                }
+                consume_dispatch<PERSIST>(buf, base, len, L, it, ev, ct, pol.first, LV, A);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&sh.empty[stage]);
                 if (++stage == stages) { stage = 0; phase ^= 1u; }
@@ -627,9 +673,9 @@ iso_stream_kernel(const __grid_constant__ SolveLaunch L) {
 constexpr int kWarpCta = 256;
 
 // one unit's sweep by one warp
-template <bool SIM, int ZK>
+template <bool SIM, int ZK, bool LEAN>
 __device__ __forceinline__ void warp_unit(const ItemDesc& it, const double* ra, const double* rb, const double* rz, int d,
-                                          const IsoEval& ev, int lane, uint64_t pol, const LazyLevels* LZ, Acc& A) {
+                                          const IsoEval& ev, int lane, uint64_t pol, const LazyView& LV, Acc& A) {
     const int npairs = d >> 1;
     constexpr int U = 4;
     for (int p0 = lane; p0 < npairs; p0 += U * 32) {
@@ -647,21 +693,39 @@ __device__ __forceinline__ void warp_unit(const ItemDesc& it, const double* ra, 
             const int p = p0 + k * 32;
             if (p < npairs) {
                 double2 zt;
-                zt.x = elem_zk<SIM, ZK>(a[k].x, b[k].x, z[k].x, ev, it, LZ, A);
-                zt.y = elem_zk<SIM, ZK>(a[k].y, b[k].y, z[k].y, ev, it, LZ, A);
+                zt.x = elem_zk<SIM, ZK, LEAN>(a[k].x, b[k].x, z[k].x, ev, it, LV, A);
+                zt.y = elem_zk<SIM, ZK, LEAN>(a[k].y, b[k].y, z[k].y, ev, it, LV, A);
                 if (it.zout) st2_stream(it.zout + 2 * (size_t)p, zt, pol);
             }
         }
     }
     if ((d & 1) && lane == 0) {                               // odd d: the last element
         const int j = d - 1;
-        const double zt = elem_zk<SIM, ZK>(ra[j], SIM ? rb[j] : 0.0, (ZK == 1 || ZK == 4) ? rz[j] : 0.0, ev, it, LZ, A);
+        const double zt = elem_zk<SIM, ZK, LEAN>(ra[j], SIM ? rb[j] : 0.0, (ZK == 1 || ZK == 4) ? rz[j] : 0.0, ev, it, LV, A);
         if (it.zout) it.zout[j] = zt;
+    }
+}
+
+template <bool LEAN>
+__device__ __forceinline__ void warp_dispatch(const ItemDesc& it, const double* ra, const double* rb, const double* rz, int d,
+                                              const IsoEval& ev, int lane, uint64_t pol, const LazyView& LV, Acc& A) {
+    if (it.sim) {
+        if (it.zk == 0) warp_unit<true, 0, LEAN>(it, ra, rb, rz, d, ev, lane, pol, LV, A);
+        else if (it.zk == 1) warp_unit<true, 1, LEAN>(it, ra, rb, rz, d, ev, lane, pol, LV, A);
+        else if (it.zk == 2) warp_unit<true, 2, LEAN>(it, ra, rb, rz, d, ev, lane, pol, LV, A);
+        else if (it.zk == 3) warp_unit<true, 3, LEAN>(it, ra, rb, rz, d, ev, lane, pol, LV, A);
+        else warp_unit<true, 4, LEAN>(it, ra, rb, rz, d, ev, lane, pol, LV, A);
+    } else {
+        if (it.zk == 1) warp_unit<false, 1, LEAN>(it, ra, rb, rz, d, ev, lane, pol, LV, A);
+        else if (it.zk == 3) warp_unit<false, 3, LEAN>(it, ra, rb, rz, d, ev, lane, pol, LV, A);
+        else if (it.zk == 4) warp_unit<false, 4, LEAN>(it, ra, rb, rz, d, ev, lane, pol, LV, A);
+        else warp_unit<false, 0, LEAN>(it, ra, rb, rz, d, ev, lane, pol, LV, A);
     }
 }
 
 // the launch's units dealt round-robin to the grid's warps (body of iso_warp_stream_kernel and of every phase of
 // solve_persist_kernel's small-d form)
+template <bool PERSIST>
 __device__ __forceinline__ void warp_pass(const SolveLaunch& L) {
     const int lane = threadIdx.x & 31;
     const int gw = (blockIdx.x * kWarpCta + threadIdx.x) >> 5, nw = (gridDim.x * kWarpCta) >> 5;
@@ -671,6 +735,7 @@ __device__ __forceinline__ void warp_pass(const SolveLaunch& L) {
     NoIssuer none;
     Controller<WarpCtx, NoIssuer> u(ctx, L, none);            // only for setup_unit (pointer logic)
     const double* zshared = u.resolve_zshared();
+    const LazyView LV = PERSIST ? lazy_view(L) : LazyView{nullptr, 0};
     for (int unit = gw; unit < L.nitems; unit += nw) {
         int* zs = u.setup_unit(unit, zshared, nullptr);
         const Cmd& c = u.cur;
@@ -689,21 +754,22 @@ __device__ __forceinline__ void warp_pass(const SolveLaunch& L) {
         // [host-test:end warp-item]
         it.levmask = 0u;
         const double* rz = c.zcur;
-        if (L.lazy) lazy_item(L, c, zs, zshared, it, rz);
+        if (PERSIST && L.lazy) lazy_item(L, c, zs, zshared, it, rz);
         Acc A;
 #pragma unroll
         for (int k = 0; k < kNRed; ++k) A.v[k] = 0.0;
-        if (it.sim) {
-            if (it.zk == 0) warp_unit<true, 0>(it, ra, c.nu, rz, L.d, ev, lane, pol.first, nullptr, A);
-            else if (it.zk == 1) warp_unit<true, 1>(it, ra, c.nu, rz, L.d, ev, lane, pol.first, nullptr, A);
-            else if (it.zk == 2) warp_unit<true, 2>(it, ra, c.nu, rz, L.d, ev, lane, pol.first, nullptr, A);
-            else if (it.zk == 3) warp_unit<true, 3>(it, ra, c.nu, rz, L.d, ev, lane, pol.first, L.lazy, A);
-            else warp_unit<true, 4>(it, ra, c.nu, rz, L.d, ev, lane, pol.first, L.lazy, A);
+        if constexpr (PERSIST) {
+            if (L.lean) warp_dispatch<true>(it, ra, c.nu, rz, L.d, ev, lane, pol.first, LV, A);
+            else warp_dispatch<false>(it, ra, c.nu, rz, L.d, ev, lane, pol.first, LV, A);
         } else {
-            if (it.zk == 1) warp_unit<false, 1>(it, ra, c.nu, rz, L.d, ev, lane, pol.first, nullptr, A);
-            else if (it.zk == 3) warp_unit<false, 3>(it, ra, c.nu, rz, L.d, ev, lane, pol.first, L.lazy, A);
-            else if (it.zk == 4) warp_unit<false, 4>(it, ra, c.nu, rz, L.d, ev, lane, pol.first, L.lazy, A);
-            else warp_unit<false, 0>(it, ra, c.nu, rz, L.d, ev, lane, pol.first, nullptr, A);
+            if (it.sim) {
+                if (it.zk == 0) warp_unit<true, 0, false>(it, ra, c.nu, rz, L.d, ev, lane, pol.first, LV, A);
+                else if (it.zk == 1) warp_unit<true, 1, false>(it, ra, c.nu, rz, L.d, ev, lane, pol.first, LV, A);
+                else warp_unit<true, 2, false>(it, ra, c.nu, rz, L.d, ev, lane, pol.first, LV, A);
+            } else {
+                if (it.zk == 1) warp_unit<false, 1, false>(it, ra, c.nu, rz, L.d, ev, lane, pol.first, LV, A);
+                else warp_unit<false, 0, false>(it, ra, c.nu, rz, L.d, ev, lane, pol.first, LV, A);
+            }
         }
         double sum_k, mv[kNRed - kNSum];
         warp_reduce(A, lane, sum_k, mv);
@@ -714,7 +780,7 @@ __device__ __forceinline__ void warp_pass(const SolveLaunch& L) {
         for (int k = 0; k < kNRed - kNSum; ++k) t[kNSum + k] = mv[k];
         if (lane == 0) {
             publish_unit(L, it, t);
-            if (L.lazy) lazy_after_publish(L, it);
+            if (PERSIST && L.lazy) lazy_after_publish(L, it);
         }
         __syncwarp();
     }
@@ -723,7 +789,7 @@ __device__ __forceinline__ void warp_pass(const SolveLaunch& L) {
 __global__ void __launch_bounds__(kWarpCta, 2)
 iso_warp_stream_kernel(const __grid_constant__ SolveLaunch L) {
     if (launch_skipped(L)) return;
-    warp_pass(L);
+    warp_pass<false>(L);
 }
 
 // ---- the whole solve in ONE launch ------------------------------------------------------------------------------------
@@ -783,6 +849,7 @@ __device__ void phase_launch(const PersistParams& P, int ph, PersistShared& ps) 
     L.redo_count = &ctl->redo[ph];
     L.work_next = &ctl->work[ph];
     L.redo_total = &ctl->redo_sink;
+    L.lean = P.lean;
     const OutPtrs* ob;
     if (ph < kOuterSlots) {              // pass ph + 1 of muse!: data + local sims, start zeros / user z₀ on the first, previous ẑ afterwards
         L.nitems = P.step.units_local;
@@ -809,6 +876,12 @@ __device__ void phase_launch(const PersistParams& P, int ph, PersistShared& ps) 
         L.zB = P.zfidB;
         L.zstate = &ctl->zfid_state;
         L.dyn = &ps.dyn[0];
+        // one unit is all this phase has: one chunk per segment spreads it over as many CTAs as it has chunks (its ẑ is elementwise,
+        // so the segmentation does not change it; its sums only feed the accept / hand-back decision)
+        if (P.fid_seg_chunks > 0) {
+            L.seg_chunks = P.fid_seg_chunks;
+            L.nseg = ((L.ld + kChunk - 1) / kChunk + L.seg_chunks - 1) / L.seg_chunks;
+        }
         ob = &P.fd;
     } else {                             // virtual sims at the 2·nθ sample points, MAP + score at θ̂ from the fiducial start — :426-433
         L.nitems = P.nh_mine * P.step.nt * 2;
@@ -840,7 +913,7 @@ __device__ __forceinline__ void run_phase(const SolveLaunch& L, bool reinit) {
         __shared__ Shared sh;
         stream_pass<true>(L, sh, reinterpret_cast<double*>(dynsm), reinit);
     } else {
-        warp_pass(L);
+        warp_pass<true>(L);
         __syncthreads();
     }
 }

@@ -127,6 +127,7 @@ void muse_outer_release(muse_handle* h) {
     cudaFree(h->outer_dyn);
     cudaFree(h->persist_ctl);
     h->persist_ctl = nullptr;
+    for (auto& e : h->persist_ev) { if (e) cudaEventDestroy(e); e = nullptr; }
     for (int s = 0; s < kOuterSlots; ++s) { cudaFree(h->outer_gall[s]); h->outer_gall[s] = nullptr; h->outer_slot[s] = OutBlock{}; }
     cudaFreeHost(h->outer_gall_h);
     h->outer_fd = OutBlock{};
@@ -327,6 +328,7 @@ extern "C" int muse_b200_muse_solve(muse_handle* h, const double* theta0, int32_
     // lazy ẑ: off unless MUSE_LAZY=1 — measured on C3 the passes are co-limited by the FP64 pipe, so moving fewer
     // bytes (16·d instead of 24·d / 32·d per sim) does not shorten them yet: cold pass 0.52 ms either way, warm pass 0.82 vs 0.64 ms
     const bool lazy_on = [] { const char* e = std::getenv("MUSE_LAZY"); return e && std::atoi(e) != 0; }();
+    const bool lean_on = [] { const char* e = std::getenv("MUSE_LEAN"); return e && std::atoi(e) != 0; }();   // SolveLaunch::lean (muse_common.cuh)
     if (h->persist_grid < 0) {
         int g = 0, t = 0;
         if (iso_persist_geometry(h->geo, h->cfg.device, &g, &t) != cudaSuccess) { cudaGetLastError(); g = 0; }
@@ -372,6 +374,11 @@ extern "C" int muse_b200_muse_solve(muse_handle* h, const double* theta0, int32_
         Q.max_pass = std::min((int)maxsteps, kOuterSlots);
         Q.get_cov = get_covariance ? 1 : 0;
         Q.lazy = lazy_on ? 1 : 0;
+        Q.lean = lean_on ? 1 : 0;
+        if (h->geo.stream == 1) {           // room in the segment-sum array for the fiducial unit cut into single chunks?
+            const long long nchunks = (h->ld + 2047) / 2048;
+            Q.fid_seg_chunks = (long long)h->out_cap * h->geo.nseg >= nchunks ? 1 : 0;
+        }
         Q.nh_mine = std::max(0, nh_mine);
         Q.z0user = h->z0user;
         const bool hshard = h->cfg.nsims_h > 0;
@@ -412,13 +419,17 @@ extern "C" int muse_b200_muse_solve(muse_handle* h, const double* theta0, int32_
         }
         cudaEvent_t ea = nullptr, eb = nullptr;
         if (h->prof) {
-            OUTER_TRY(h, cudaEventCreate(&ea));
-            OUTER_TRY(h, cudaEventCreate(&eb));
+            if (!h->persist_ev[0]) {
+                OUTER_TRY(h, cudaEventCreate(&h->persist_ev[0]));
+                OUTER_TRY(h, cudaEventCreate(&h->persist_ev[1]));
+            }
+            ea = h->persist_ev[0]; eb = h->persist_ev[1];
             OUTER_TRY(h, cudaEventRecord(ea, h->stream));
         }
         OUTER_TRY(h, launch_iso_persist(Q, h->geo, h->persist_grid, h->stream));
         if (h->prof) OUTER_TRY(h, cudaEventRecord(eb, h->stream));
         h->acc.launches += 1;
+        const auto t_launched = std::chrono::steady_clock::now();
         // results: [state | slot 0 | slot 1 | FD block] in one copy (the typical solve); slot 2 only if a third pass ran
         OUTER_TRY(h, cudaMemcpyAsync(h->outer_arena_h, h->outer_arena_d, h->outer_arena_head, cudaMemcpyDeviceToHost, h->stream));
         if (multi)
@@ -427,7 +438,6 @@ extern "C" int muse_b200_muse_solve(muse_handle* h, const double* theta0, int32_
         OUTER_TRY(h, cudaStreamSynchronize(h->stream));
         if (sh_->error == 3) {
             cudaMemsetAsync(h->persist_ctl, 0, sizeof(PersistCtl), h->stream);
-            if (ea) { cudaEventDestroy(ea); cudaEventDestroy(eb); }
             h->err = "muse_solve: a rank did not arrive at the exchange step within 4 s (peer-mapped exchange of the persistent launch)";
             return MUSE_ECUDA;
         }
@@ -436,7 +446,6 @@ extern "C" int muse_b200_muse_solve(muse_handle* h, const double* theta0, int32_
             // through the chain of launches, whose generic kernel re-solves such units — from scratch, now and from now on
             h->persist_off_key = pkey;
             if (lazy_on) OUTER_TRY(h, cudaMemsetAsync(h->zstate, 0, (size_t)h->rows * sizeof(int), h->stream));
-            if (ea) { cudaEventDestroy(ea); cudaEventDestroy(eb); }
         } else {
             const int n_now = sh_->n_iter;
             if (n_now > 2) {
@@ -444,11 +453,13 @@ extern "C" int muse_b200_muse_solve(muse_handle* h, const double* theta0, int32_
                 OUTER_TRY(h, cudaStreamSynchronize(h->stream));
             }
             const double chunk_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-            if (sh_->error == 1) { if (ea) { cudaEventDestroy(ea); cudaEventDestroy(eb); } h->err = "muse!: MAP solution failed with a non-finite objective"; return MUSE_ESTATE; }
+            if (sh_->error == 1) { h->err = "muse!: MAP solution failed with a non-finite objective"; return MUSE_ESTATE; }
             const bool cov_ran = get_covariance && sh_->done != 0 && sh_->error == 0;
-            if (std::getenv("MUSE_DEBUG_TIMING")) {
+            static const bool dbg_timing = [] { const char* e = std::getenv("MUSE_DEBUG_TIMING"); return e && *e; }();
+            if (dbg_timing) {
                 const long long* T = sh_->stamp;
-                std::fprintf(stderr, "[muse_solve persist rank %d] n_iter=%d host %.1f us | kernel stamps (us since start):", h->comm_rank, n_now, chunk_s * 1e6);
+                std::fprintf(stderr, "[muse_solve persist rank %d] n_iter=%d host: set-up+launch %.1f us, until synchronised %.1f us | kernel stamps (us since start):",
+                             h->comm_rank, n_now, std::chrono::duration<double>(t_launched - t0).count() * 1e6, chunk_s * 1e6);
                 for (int k = 1; k < 12; ++k) std::fprintf(stderr, " %.1f", T[k] ? (double)(T[k] - T[0]) * 1e-3 : -1.0);
                 std::fprintf(stderr, "\n");
             }
@@ -479,10 +490,10 @@ extern "C" int muse_b200_muse_solve(muse_handle* h, const double* theta0, int32_
                     add(MUSE_PASS_FD, fd_items, fd_items * 2 * d8 + d8, T[1 + 2 * kPhaseFid], T[1 + 2 * kPhaseFd]);
                 }
                 h->acc.solve_launches += 1;
-                if (h->prof) {
-                    muse_handle::Rec r{};
-                    r.a = ea; r.b = eb; r.cls = 3; r.units = units_sum; r.bytes = bytes_sum; r.kind = MUSE_PASS_COLD; r.tag = 0;
-                    h->recs.push_back(r);
+                if (h->prof) {              // the stream has been synchronised: the launch's event pair can be read now
+                    float ms = 0.f;
+                    if (cudaEventElapsedTime(&ms, ea, eb) != cudaSuccess) { cudaGetLastError(); ms = 0.f; }
+                    h->acc.solve_ms += ms; h->acc.solve_units += units_sum; h->acc.solve_bytes += bytes_sum;
                 }
             }
             // lazy ẑ: the state cells hold level masks unless the last pass materialised ẑ — no resident ẑ is left behind

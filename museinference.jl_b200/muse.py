@@ -42,6 +42,63 @@ def _ascii_kwargs(kw: dict) -> dict:
     return {_KW_ALIASES.get(k, k): v for k, v in kw.items()}
 
 
+class FusedHistory:
+    """``result.history`` of a solve that ran inside the library: the rows (one dict per iteration, src/muse.jl:211-221) are
+    built from the library's history arrays on first access — a solve whose caller only wants θ̂ ± σ never pays for them.
+    Behaves like the list it stands for (len, indexing, iteration, append, truth value); pickles as a plain list."""
+
+    __slots__ = ("_H", "_secs", "_theta0", "_theta_final", "_items")
+
+    def __init__(self, H, secs, theta0, theta_final):
+        self._H, self._secs, self._theta0, self._theta_final, self._items = H, secs, theta0, theta_final, None
+
+    def _rows(self):
+        if self._items is None:
+            H, secs, n = self._H, self._secs, len(self._secs)
+            items, th_unreg_prev = [], self._theta0
+            for k in range(n):
+                gsk = H["g_sims_hist"][k]                     # identity transform: g and g′ are the same array
+                g_like, g_prior = H["g_like_hist"][k], H["g_prior_hist"][k]
+                H_inv_like = _diagm(H["h_inv_like_hist"][k])
+                it_k, fg_k, gn_k, st_k = H["iters_hist"][k], H["fg_hist"][k], H["gnorm_hist"][k], H["status_hist"][k]
+                items.append(dict(
+                    theta=H["theta_hist"][k], theta_unreg=th_unreg_prev, theta_t=H["theta_hist"][k], theta_unreg_t=th_unreg_prev,
+                    g_like_sims=gsk, g_like_sims_t=gsk, g_like_dat=H["g_dat_hist"][k], g_like=g_like,
+                    g_prior=g_prior, g_post=g_like + g_prior,
+                    H_inv_post=_diagm(H["h_inv_post_hist"][k]), H_prior=_diagm(H["h_prior_hist"][k]), H_inv_like=H_inv_like,
+                    H_inv_like_sims=H_inv_like,
+                    z_history_dat=dict(iters=int(it_k[0]), fg_evals=int(fg_k[0]), gnorm=float(gn_k[0]), status=int(st_k[0])),
+                    z_history_sims=dict(iters=it_k[1:], fg_evals=fg_k[1:], gnorm=gn_k[1:], status=st_k[1:]),
+                    t=secs[k], z_dat=None, z_sims=None))
+                th_unreg_prev = H["theta_hist"][k + 1] if k + 1 < n else self._theta_final
+            self._items = items
+        return self._items
+
+    def __len__(self):
+        return len(self._secs) if self._items is None else len(self._items)
+
+    def __bool__(self):
+        return len(self) > 0
+
+    def __getitem__(self, i):
+        return self._rows()[i]
+
+    def __iter__(self):
+        return iter(self._rows())
+
+    def append(self, entry):
+        self._rows().append(entry)
+
+    def __eq__(self, other):
+        return list(self) == list(other)
+
+    def __reduce__(self):
+        return (list, (self._rows(),))
+
+    def __repr__(self):
+        return repr(self._rows())
+
+
 @dataclass
 class MuseResult:
     """src/muse.jl:29-42.  ``theta`` ↔ θ, ``Sigma``/``Sigma_inv`` ↔ Σ/Σ⁻¹, ``dist`` is the
@@ -195,33 +252,17 @@ def muse_(result: MuseResult, prob: AbstractMuseProblem, theta0=None, **kwargs):
                                 _capi.START_USER if z0 is not None else _capi.START_ZEROS,
                                 *(prior_ms if prior_ms else (None, None)))
         # the library's history buffers are reused by the next call: take ONE private copy of the executed rows of each
-        # array and hand out views of those copies (a solve of 10⁴ sims spent more time in 16 small copies per iteration
-        # than in the interpreter proper)
+        # array; the per-iteration dicts of result.history are built from those copies when somebody looks at them
         n = r["n_iter"]
         H = {key: r[key][:n].copy() for key in ("theta_hist", "g_dat_hist", "g_sims_hist", "g_like_hist", "g_prior_hist", "h_inv_like_hist",
                                               "h_prior_hist", "h_inv_post_hist", "iters_hist", "fg_hist", "gnorm_hist", "status_hist")}
         secs = r["seconds_hist"][:n].tolist()
         theta_final = r["theta_final"].copy()
-        th_unreg_prev = theta.copy()
-        for k in range(n):
-            gsk = H["g_sims_hist"][k]                     # identity transform: g and g′ are the same array
-            g_like, g_prior = H["g_like_hist"][k], H["g_prior_hist"][k]
-            H_inv_like = _diagm(H["h_inv_like_hist"][k])
-            it_k, fg_k, gn_k, st_k = H["iters_hist"][k], H["fg_hist"][k], H["gnorm_hist"][k], H["status_hist"][k]
-            history.append(dict(
-                theta=H["theta_hist"][k], theta_unreg=th_unreg_prev, theta_t=H["theta_hist"][k], theta_unreg_t=th_unreg_prev,
-                g_like_sims=gsk, g_like_sims_t=gsk, g_like_dat=H["g_dat_hist"][k], g_like=g_like,
-                g_prior=g_prior, g_post=g_like + g_prior,
-                H_inv_post=_diagm(H["h_inv_post_hist"][k]), H_prior=_diagm(H["h_prior_hist"][k]), H_inv_like=H_inv_like,
-                H_inv_like_sims=H_inv_like,
-                z_history_dat=dict(iters=int(it_k[0]), fg_evals=int(fg_k[0]), gnorm=float(gn_k[0]), status=int(st_k[0])),
-                z_history_sims=dict(iters=it_k[1:], fg_evals=fg_k[1:], gnorm=gn_k[1:], status=st_k[1:]),
-                t=secs[k], z_dat=None, z_sims=None))
-            th_unreg_prev = H["theta_hist"][k + 1] if k + 1 < n else theta_final
-            result.time += secs[k]
+        result.history = history = FusedHistory(H, secs, theta.copy(), theta_final)
+        result.time += sum(secs)
         if n:
             result.theta = theta_final.copy()                                      # :230
-            result.gs = H["g_sims_hist"][n - 1].copy()                             # :231
+            result.gs = H["g_sims_hist"][n - 1]                                    # :231 (a view of this solve's private copy)
         maxsteps = 0                                                               # the loop below has nothing left to do
         if cdev is not None and r["n_iter"]:                                       # :244-247, already done on the stream
             result.J, result.H, result.Hs = cdev["J"], cdev["H"], cdev["Hs"]

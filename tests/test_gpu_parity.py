@@ -687,11 +687,12 @@ def test_profile_splits_solver_time_by_pass_kind():
 
 
 # ----------------------------------------------------------------------------- the whole solve in one launch (solve_persist_kernel)
-def _solve_persist(m, xd, name, pr, rng, nsims, persist, lazy=True, **kw):
-    """One solve with MUSE_PERSIST = persist (and MUSE_LAZY = lazy); returns (result, profile, per-pass profile)."""
+def _solve_persist(m, xd, name, pr, rng, nsims, persist, lazy=False, lean=False, **kw):
+    """One solve with MUSE_PERSIST = persist (and MUSE_LAZY = lazy, MUSE_LEAN = lean); returns (result, profile, per-pass profile)."""
     import os
     os.environ["MUSE_PERSIST"] = "1" if persist else "0"
     os.environ["MUSE_LAZY"] = "1" if lazy else "0"
+    os.environ["MUSE_LEAN"] = "1" if lean else "0"
     try:
         prob = m.SimpleMuseProblem(xd, name, pr())
         res = m.muse(prob, theta_start(name), rng=rng, nsims=nsims, **kw)      # first solve: allocations
@@ -703,8 +704,8 @@ def _solve_persist(m, xd, name, pr, rng, nsims, persist, lazy=True, **kw):
         be.profile_reset(False)
         prob.close()
     finally:
-        os.environ.pop("MUSE_PERSIST", None)
-        os.environ.pop("MUSE_LAZY", None)
+        for k in ("MUSE_PERSIST", "MUSE_LAZY", "MUSE_LEAN"):
+            os.environ.pop(k, None)
     return res, prof, passes
 
 
@@ -742,8 +743,10 @@ def test_one_launch_solve_is_bit_identical_to_the_chain_of_launches(name, d, nsi
     oprob, fam, draws, xd = oracle_problem(name, d, nsims)
     rng = m.BaseDraws(draws.xi, draws.nu, draws.xi_master, draws.nu_master)
     pr = (lambda: m.NormalPrior([0.0, 0.1][:fam.ntheta], [3.0, 2.0][:fam.ntheta])) if prior else (lambda: None)
-    for cov, lazy in ((True, True), (False, True), (True, False)):
-        a, pa, passes = _solve_persist(m, xd, name, pr, rng, nsims, True, lazy, get_covariance=cov, fused_driver="device", **kw)
+    # lazy: ẑ recomputed from the base normals instead of stored and re-read; lean: the α = 1 trial from its closed form — neither
+    # may change a single bit of the result
+    for cov, lazy, lean in ((True, False, False), (False, False, False), (True, True, False), (True, False, True), (True, True, True), (False, True, True)):
+        a, pa, passes = _solve_persist(m, xd, name, pr, rng, nsims, True, lazy, lean, get_covariance=cov, fused_driver="device", **kw)
         b, pb, _ = _solve_persist(m, xd, name, pr, rng, nsims, False, get_covariance=cov, fused_driver="device", **kw)
         _assert_identical_solve(a, b, cov=cov)
         n = len(a.history)
@@ -989,7 +992,7 @@ def _nccl_worker(rank, world, port, cases, q):
                     prob._backend.profile_reset(True)
                 res = m.muse(prob, th0, rng=seed, nsims=nsims, get_covariance=True, pool=pool, fused_driver=fused)
             if prob._backend is not None:
-                launches = prob._backend.profile()["launches"]
+                launches = prob._backend.profile()["solve_launches"]
                 p2p = prob._backend.p2p_info()
             outs.append((res.theta, np.array(res.gs), res.H, res.J, res.Sigma, len(res.history), launches, p2p))
             prob.close()
@@ -1037,7 +1040,7 @@ def test_two_rank_nccl_solve_is_bit_identical_to_one_gpu():
             if name != "corrgauss" and fused is True:
                 # the exchange that ran is the one asked for: one launch per solve with the peer-mapped buffers, a chain otherwise
                 assert p2p[1] == (exchange == "p2p"), (name, exchange, p2p)
-                assert (launches == 1) == (exchange == "p2p" and nhist <= 3), (name, exchange, launches)
+                assert (launches == 1) == (exchange == "p2p" and nhist <= 3), (name, exchange, launches)     # solver launches of the solve
             np.testing.assert_array_equal(gs, np.array(ref.gs), err_msg=f"{name} rank {rank}: gs")
             np.testing.assert_array_equal(theta, ref.theta, err_msg=f"{name} rank {rank}: θ")
             np.testing.assert_array_equal(H, ref.H, err_msg=f"{name} rank {rank}: H")
