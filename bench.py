@@ -439,13 +439,22 @@ def roofline_of(wl, mv, hbm_peak, peak_src, steps, kernel_flag):
         kname = "iso_stream_kernel (single-pass MAP+score, TMA ring)"
     else:
         kname = "iso_warp_stream_kernel (single-pass MAP+score, one warp per unit)"
+    one_launch = prof["solve_launches"] > 0 and prof["launches"] == prof["solve_launches"] and "fd" in by_pass
+    if one_launch:
+        # muse_b200_muse_solve ran every solve as ONE cooperative launch (solve_persist_kernel: all passes, the θ updates and the
+        # covariance stage's launches as phases of one kernel); `achieved` = the algorithmic bytes of all its phases ÷ the CUDA-event
+        # time of the launch; the per-pass split below comes from the kernel's own %globaltimer stamps
+        kname = ("solve_persist_kernel (one cooperative launch per solve; phases = the passes of " +
+                 ("iso_stream_kernel's TMA ring" if (wl.d >= 4096 or kernel_flag == 2) else "iso_warp_stream_kernel's warp-per-unit sweep") +
+                 ", θ updates and get_H! stage in between; lazy ẑ + lean α=1 trial unless MUSE_LAZY=0 / MUSE_LEAN=0)")
     if redo:
         kname += f" + iso_solver_kernel re-solve of {redo} handed-back units"
     return {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
             "traffic": measured_traffic(wl.family, wl.d, wl.nsims_total) if world == 1 else None,
             "peak_source": peak_src, "kernel": kname, "redo_units": redo,
             "algorithmic_bytes_per_launch": mv["solve_bytes_sum"] / n_launch, "avg_launch_ms": mv["solve_ms_sum"] / n_launch,
-            "kernel_share_of_step": share, "passes": by_pass}
+            "kernel_share_of_step": share, "passes": by_pass,
+            "passes_timed_by": "globaltimer stamps of the launch's CTA 0" if one_launch else "CUDA events around each launch chain"}
 
 
 def run_b200(args):
@@ -556,7 +565,8 @@ def run_b200(args):
             "detail": {"outer_iterations": len(res.history), "units_per_step": mv["units_per_block"] / args.steps,
                        "solver_geometry": geo,
                        "theta_hat": [float(t) for t in res.theta], "sigma": [float(s) for s in np.sqrt(np.diag(res.Sigma))],
-                       "exchange": None if world == 1 else os.environ.get("MUSE_EXCHANGE", "auto")},
+                       "exchange": None if world == 1 else ("nccl all-gather between launches" if os.environ.get("MUSE_EXCHANGE") == "nccl" or not be.p2p_info()[1]
+                                                            else "peer-mapped stores + flags inside the one-launch solve (NVLink, no collective launch)")},
             "clocks": clocks,
             "e2e": {"value": units_e2e_block / (ms_e2e / 1e3), "unit": "sims/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h_box[0], "ms_per_step": ms_e2e / args.steps, "blocks": len(ev_e),

@@ -325,10 +325,11 @@ extern "C" int muse_b200_muse_solve(muse_handle* h, const double* theta0, int32_
     // (read at every call, so that one process can hold the two paths against each other)
     const bool persist_on = [] { const char* e = std::getenv("MUSE_PERSIST"); return !e || std::atoi(e) != 0; }();
     const bool p2p_on = [] { const char* e = std::getenv("MUSE_EXCHANGE"); return !e || std::strcmp(e, "nccl") != 0; }();
-    // lazy ẑ: off unless MUSE_LAZY=1 — measured on C3 the passes are co-limited by the FP64 pipe, so moving fewer
-    // bytes (16·d instead of 24·d / 32·d per sim) does not shorten them yet: cold pass 0.52 ms either way, warm pass 0.82 vs 0.64 ms
-    const bool lazy_on = [] { const char* e = std::getenv("MUSE_LAZY"); return e && std::atoi(e) != 0; }();
-    const bool lean_on = [] { const char* e = std::getenv("MUSE_LEAN"); return e && std::atoi(e) != 0; }();   // SolveLaunch::lean (muse_common.cuh)
+    // lazy ẑ and lean evaluation (muse_common.cuh: LazyLevels, SolveLaunch::lean): on unless MUSE_LAZY=0 / MUSE_LEAN=0.
+    // Measured on C3 (one B200, profiles/README.md): the passes are co-limited by the FP64 pipe, so lazy ẑ alone (16·d instead of
+    // 24·d / 32·d bytes per sim) gains ≈ 4 % and lean evaluation alone ≈ 5 %; together 1.48 → 1.30 ms per solve, C4 4.56 → 3.94 ms.
+    const bool lazy_on = [] { const char* e = std::getenv("MUSE_LAZY"); return !e || std::atoi(e) != 0; }();
+    const bool lean_on = [] { const char* e = std::getenv("MUSE_LEAN"); return !e || std::atoi(e) != 0; }();
     if (h->persist_grid < 0) {
         int g = 0, t = 0;
         if (iso_persist_geometry(h->geo, h->cfg.device, &g, &t) != cudaSuccess) { cudaGetLastError(); g = 0; }
