@@ -509,6 +509,7 @@ def run_b200(args):
     be = wl.prob._backend
     res = wl.res
     geo = be.geometry()
+    p2p_ready = be.p2p_info()[1] if world > 1 else False
 
     # ---- end-to-end arm ("e2e"): host data in, results out, draws regenerated from the seed ----
     th0 = wl.th0
@@ -565,7 +566,7 @@ def run_b200(args):
             "detail": {"outer_iterations": len(res.history), "units_per_step": mv["units_per_block"] / args.steps,
                        "solver_geometry": geo,
                        "theta_hat": [float(t) for t in res.theta], "sigma": [float(s) for s in np.sqrt(np.diag(res.Sigma))],
-                       "exchange": None if world == 1 else ("nccl all-gather between launches" if os.environ.get("MUSE_EXCHANGE") == "nccl" or not be.p2p_info()[1]
+                       "exchange": None if world == 1 else ("nccl all-gather between launches" if os.environ.get("MUSE_EXCHANGE") == "nccl" or not p2p_ready
                                                             else "peer-mapped stores + flags inside the one-launch solve (NVLink, no collective launch)")},
             "clocks": clocks,
             "e2e": {"value": units_e2e_block / (ms_e2e / 1e3), "unit": "sims/s", "h2d_bytes_per_step": h2d,

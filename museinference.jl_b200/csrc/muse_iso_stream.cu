@@ -199,20 +199,30 @@ struct LazyView {
 };
 template <bool SIM>
 __device__ __forceinline__ double lazy_z0(double p, double q, double zstart, const LazyView& LV, unsigned mask) {
+    // no branches: a level the unit did not step at (a 0-iteration solve — rare) is evaluated and dropped by a select, so that the
+    // elements of a thread stay independent instruction streams
     double z = zstart;
     if (LV.nlev == 1) {                      // the hot case: the second pass of a solve
-        if (mask & 1u) z = lazy_level<SIM>(p, q, z, LV.all->lev[0]);
-        return z;
+        const double zn = lazy_level<SIM>(p, q, z, LV.all->lev[0]);
+        return (mask & 1u) ? zn : z;
     }
-    for (int l = 0; l < LV.nlev; ++l)
-        if ((mask >> l) & 1u) z = lazy_level<SIM>(p, q, z, LV.all->lev[l]);
+    for (int l = 0; l < LV.nlev; ++l) {
+        const double zn = lazy_level<SIM>(p, q, z, LV.all->lev[l]);
+        z = ((mask >> l) & 1u) ? zn : z;
+    }
     return z;
 }
+// what a consumer keeps of an item's descriptor
+struct ItemRegs {
+    double sig, mus;
+    double* zout;
+    unsigned mask;
+};
 // ZK: 0 z₀ ≡ 0 · 1 z₀ streamed · 2 z₀ = simulated latent · 3 lazy from zero · 4 lazy from a streamed start row
 template <bool SIM, int ZK, bool LEAN>
-__device__ __forceinline__ double elem_zk(double p, double q, double z0in, const IsoEval& ev, const ItemDesc& it, const LazyView& LV, Acc& A) {
-    if (ZK >= 3) return elem3<SIM, 1, LEAN>(p, q, lazy_z0<SIM>(p, q, ZK == 4 ? z0in : 0.0, LV, it.levmask), ev, it.sig, it.mus, A);
-    return elem3<SIM, (ZK >= 3 ? 1 : ZK), LEAN>(p, q, z0in, ev, it.sig, it.mus, A);
+__device__ __forceinline__ double elem_zk(double p, double q, double z0in, const IsoEval& ev, const ItemRegs& R, const LazyView& LV, Acc& A) {
+    if (ZK >= 3) return elem3<SIM, 1, LEAN>(p, q, lazy_z0<SIM>(p, q, ZK == 4 ? z0in : 0.0, LV, R.mask), ev, R.sig, R.mus, A);
+    return elem3<SIM, (ZK >= 3 ? 1 : ZK), LEAN>(p, q, z0in, ev, R.sig, R.mus, A);
 }
 __device__ __forceinline__ LazyView lazy_view(const SolveLaunch& L) {
     LazyView LV;
@@ -227,37 +237,44 @@ __device__ __forceinline__ void st2_stream(double* p, double2 v, uint64_t pol) {
 
 // one chunk of one item, executed by the consumer threads
 template <bool SIM, int ZK, bool LEAN>
-__device__ __forceinline__ void consume_chunk(const double* buf, int base, int len, int d, const ItemDesc& it,
+__device__ __forceinline__ void consume_chunk(const double* buf, int base, int len, int d, const ItemRegs& R,
                                               const IsoEval& ev, int ct, uint64_t pol, const LazyView& LV, Acc& A) {
+    constexpr bool ZROW = (ZK == 1 || ZK == 4);
+    constexpr int U = kChunk / (2 * kNC);
     const double* ra = buf;
     const double* rb = buf + kChunk;
     const double* rz = buf + 2 * kChunk;
-    double* zout = it.zout;
-    if (base + len <= d) {
+    double* zout = R.zout;
+    if (len == kChunk && base + kChunk <= d) {
+        // a full chunk (all but a row's last): every load first, then the thread's 2·U elements as independent instruction streams
+        double2 p[U], q[U], z[U], zt[U];
 #pragma unroll
-        for (int u = 0; u < kChunk / (2 * kNC); ++u) {
+        for (int u = 0; u < U; ++u) {
             const int q2 = 2 * (ct + u * kNC);
-            if (q2 < len) {
-                const double2 p = lds2(ra + q2);
-                const double2 q = SIM ? lds2(rb + q2) : make_double2(0.0, 0.0);
-                const double2 z = (ZK == 1 || ZK == 4) ? lds2(rz + q2) : make_double2(0.0, 0.0);
-                double2 zt;
-                zt.x = elem_zk<SIM, ZK, LEAN>(p.x, q.x, z.x, ev, it, LV, A);
-                zt.y = elem_zk<SIM, ZK, LEAN>(p.y, q.y, z.y, ev, it, LV, A);
-                if (zout) st2_stream(zout + base + q2, zt, pol);
-            }
+            p[u] = lds2(ra + q2);
+            q[u] = SIM ? lds2(rb + q2) : make_double2(0.0, 0.0);
+            z[u] = ZROW ? lds2(rz + q2) : make_double2(0.0, 0.0);
         }
-    } else {   // the row's last chunk: elements ≥ d are padding
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            zt[u].x = elem_zk<SIM, ZK, LEAN>(p[u].x, q[u].x, z[u].x, ev, R, LV, A);
+            zt[u].y = elem_zk<SIM, ZK, LEAN>(p[u].y, q[u].y, z[u].y, ev, R, LV, A);
+        }
+        if (zout) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) st2_stream(zout + base + 2 * (ct + u * kNC), zt[u], pol);
+        }
+    } else {   // the row's last chunk: it may be short, and elements ≥ d are padding
         for (int q2 = 2 * ct; q2 < len; q2 += 2 * kNC) {
             const int j = base + q2;
             if (j >= d) break;
             const double2 p = lds2(ra + q2);
             const double2 q = SIM ? lds2(rb + q2) : make_double2(0.0, 0.0);
-            const double2 z = (ZK == 1 || ZK == 4) ? lds2(rz + q2) : make_double2(0.0, 0.0);
+            const double2 z = ZROW ? lds2(rz + q2) : make_double2(0.0, 0.0);
             double2 zt;
-            zt.x = elem_zk<SIM, ZK, LEAN>(p.x, q.x, z.x, ev, it, LV, A);
+            zt.x = elem_zk<SIM, ZK, LEAN>(p.x, q.x, z.x, ev, R, LV, A);
             zt.y = 0.0;
-            if (j + 1 < d) zt.y = elem_zk<SIM, ZK, LEAN>(p.y, q.y, z.y, ev, it, LV, A);
+            if (j + 1 < d) zt.y = elem_zk<SIM, ZK, LEAN>(p.y, q.y, z.y, ev, R, LV, A);
             if (zout) {
                 if (j + 1 < d) st2_stream(zout + j, zt, pol);
                 else zout[j] = zt.x;
@@ -389,38 +406,64 @@ struct WarpCtx {
 };
 // [host-test:end publish]
 
-template <bool LEAN>
-__device__ __forceinline__ void consume_dispatch_l(const double* buf, int base, int len, const SolveLaunch& L, const ItemDesc& it, const IsoEval& ev,
-                                                   int ct, uint64_t pol, const LazyView& LV, Acc& A) {
-    if (it.sim) {
-        if (it.zk == 0) consume_chunk<true, 0, LEAN>(buf, base, len, L.d, it, ev, ct, pol, LV, A);
-        else if (it.zk == 1) consume_chunk<true, 1, LEAN>(buf, base, len, L.d, it, ev, ct, pol, LV, A);
-        else if (it.zk == 2) consume_chunk<true, 2, LEAN>(buf, base, len, L.d, it, ev, ct, pol, LV, A);
-        else if (it.zk == 3) consume_chunk<true, 3, LEAN>(buf, base, len, L.d, it, ev, ct, pol, LV, A);
-        else consume_chunk<true, 4, LEAN>(buf, base, len, L.d, it, ev, ct, pol, LV, A);
-    } else {
-        if (it.zk == 1) consume_chunk<false, 1, LEAN>(buf, base, len, L.d, it, ev, ct, pol, LV, A);
-        else if (it.zk == 3) consume_chunk<false, 3, LEAN>(buf, base, len, L.d, it, ev, ct, pol, LV, A);
-        else if (it.zk == 4) consume_chunk<false, 4, LEAN>(buf, base, len, L.d, it, ev, ct, pol, LV, A);
-        else consume_chunk<false, 0, LEAN>(buf, base, len, L.d, it, ev, ct, pol, LV, A);
+// A consumer's view of the ring: where it stands, and the loop over an item's chunks with ONE variant of the per-element code
+// (the variant is chosen per item, not per chunk: the loop body stays small and resident in the instruction cache).
+struct RingPos {
+    int stage;
+    uint32_t phase;
+};
+template <bool SIM, int ZK, bool LEAN>
+__device__ __forceinline__ void consume_item(const SolveLaunch& L, Shared& sh, const double* ring, int rows, int stages, int chunk0, int nch,
+                                             const ItemRegs& R, const IsoEval& ev, int ct, int lane, uint64_t pol, const LazyView& LV,
+                                             RingPos& rp, Acc& A) {
+    for (int k = 0; k < nch; ++k) {
+        if (k) mbar_wait(&sh.full[rp.stage], rp.phase);         // the first chunk was waited for by the caller (descriptor hand-over)
+        const double* buf = ring + (size_t)rp.stage * rows * kChunk;
+        const int base = (chunk0 + k) * kChunk;
+        consume_chunk<SIM, ZK, LEAN>(buf, base, min(kChunk, L.ld - base), L.d, R, ev, ct, pol, LV, A);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sh.empty[rp.stage]);
+        if (++rp.stage == stages) { rp.stage = 0; rp.phase ^= 1u; }
     }
 }
-// lean evaluation and lazy ẑ exist in solve_persist_kernel only: the single-pass kernels of the chain of launches keep their code
-template <bool PERSIST>
-__device__ __forceinline__ void consume_dispatch(const double* buf, int base, int len, const SolveLaunch& L, const ItemDesc& it, const IsoEval& ev,
-                                                 int ct, uint64_t pol, const LazyView& LV, Acc& A) {
-    if constexpr (PERSIST) {
-        if (L.lean) consume_dispatch_l<true>(buf, base, len, L, it, ev, ct, pol, LV, A);
-        else consume_dispatch_l<false>(buf, base, len, L, it, ev, ct, pol, LV, A);
+template <bool LEAN>
+__device__ __forceinline__ void consume_item_l(const SolveLaunch& L, Shared& sh, const double* ring, int rows, int stages, const ItemDesc& it,
+                                               const ItemRegs& R, const IsoEval& ev, int ct, int lane, uint64_t pol, const LazyView& LV,
+                                               RingPos& rp, Acc& A) {
+#define MUSE_ITEM(SIM_, ZK_) consume_item<SIM_, ZK_, LEAN>(L, sh, ring, rows, stages, it.chunk0, it.nch, R, ev, ct, lane, pol, LV, rp, A)
+    if (it.sim) {
+        if (it.zk == 0) MUSE_ITEM(true, 0);
+        else if (it.zk == 1) MUSE_ITEM(true, 1);
+        else if (it.zk == 2) MUSE_ITEM(true, 2);
+        else if (it.zk == 3) MUSE_ITEM(true, 3);
+        else MUSE_ITEM(true, 4);
     } else {
+        if (it.zk == 1) MUSE_ITEM(false, 1);
+        else if (it.zk == 3) MUSE_ITEM(false, 3);
+        else if (it.zk == 4) MUSE_ITEM(false, 4);
+        else MUSE_ITEM(false, 0);
+    }
+#undef MUSE_ITEM
+}
+// lean evaluation and lazy ẑ exist in solve_persist_kernel only (LEAN is a parameter of that kernel): the single-pass kernels of the
+// chain of launches keep their variants
+template <bool PERSIST, bool LEAN>
+__device__ __forceinline__ void consume_item_any(const SolveLaunch& L, Shared& sh, const double* ring, int rows, int stages, const ItemDesc& it,
+                                                 const ItemRegs& R, const IsoEval& ev, int ct, int lane, uint64_t pol, const LazyView& LV,
+                                                 RingPos& rp, Acc& A) {
+    if constexpr (PERSIST) {
+        consume_item_l<LEAN>(L, sh, ring, rows, stages, it, R, ev, ct, lane, pol, LV, rp, A);
+    } else {
+#define MUSE_ITEM(SIM_, ZK_) consume_item<SIM_, ZK_, false>(L, sh, ring, rows, stages, it.chunk0, it.nch, R, ev, ct, lane, pol, LV, rp, A)
         if (it.sim) {
-            if (it.zk == 0) consume_chunk<true, 0, false>(buf, base, len, L.d, it, ev, ct, pol, LV, A);
-            else if (it.zk == 1) consume_chunk<true, 1, false>(buf, base, len, L.d, it, ev, ct, pol, LV, A);
-            else consume_chunk<true, 2, false>(buf, base, len, L.d, it, ev, ct, pol, LV, A);
+            if (it.zk == 0) MUSE_ITEM(true, 0);
+            else if (it.zk == 1) MUSE_ITEM(true, 1);
+            else MUSE_ITEM(true, 2);
         } else {
-            if (it.zk == 1) consume_chunk<false, 1, false>(buf, base, len, L.d, it, ev, ct, pol, LV, A);
-            else consume_chunk<false, 0, false>(buf, base, len, L.d, it, ev, ct, pol, LV, A);
+            if (it.zk == 1) MUSE_ITEM(false, 1);
+            else MUSE_ITEM(false, 0);
         }
+#undef MUSE_ITEM
     }
 }
 
@@ -450,7 +493,7 @@ __device__ __forceinline__ void lazy_after_publish(const SolveLaunch& L, const I
 // of every phase of solve_persist_kernel (PERSIST: the barriers of the previous phase are invalidated and set up again, the
 // proxies are fenced around the phase — ẑ written with ordinary stores by one phase is read by bulk copies in the next —
 // and the CTA ends the phase together).
-template <bool PERSIST>
+template <bool PERSIST, bool LEAN = false>
 __device__ __forceinline__ void stream_pass(const SolveLaunch& L, Shared& sh, double* const ring, bool reinit) {
     const int rows = L.zrows ? 3 : 2;
     const int stages = L.stream_stages;
@@ -607,14 +650,13 @@ __device__ __forceinline__ void stream_pass(const SolveLaunch& L, Shared& sh, do
         const IsoEval ev = launch_ev(L);
         const L2Policy pol = make_policies();
         const LazyView LV = PERSIST ? lazy_view(L) : LazyView{nullptr, 0};
-        int stage = 0;
-        uint32_t phase = 0;
+        RingPos rp{0, 0u};
         for (int i = 0;; ++i) {
             Acc A;
 #pragma unroll
             for (int k = 0; k < kNRed; ++k) A.v[k] = 0.0;
-            mbar_wait(&sh.full[stage], phase);          // the item's first chunk has landed ⇒ its descriptor is visible
-            const ItemDesc it = sh.desc[i % kDescRing];
+            mbar_wait(&sh.full[rp.stage], rp.phase);    // the item's first chunk has landed ⇒ its descriptor is visible
+            const ItemDesc& it = sh.desc[i % kDescRing];
             const int slot = i & 1;
             if (it.unit < 0) {                          // end of work: wake the finisher (mailbox protocol as for an item)
                 if (lane == 0) {
@@ -623,16 +665,8 @@ __device__ __forceinline__ void stream_pass(const SolveLaunch& L, Shared& sh, do
                 }
                 break;
             }
-            for (int k = 0; k < it.nch; ++k) {
-                if (k) mbar_wait(&sh.full[stage], phase);
-                const double* buf = ring + (size_t)stage * rows * kChunk;
-                const int base = (it.chunk0 + k) * kChunk;
-                const int len = min(kChunk, L.ld - base);
-                consume_dispatch<PERSIST>(buf, base, len, L, it, ev, ct, pol.first, LV, A);
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&sh.empty[stage]);
-                if (++stage == stages) { stage = 0; phase ^= 1u; }
-            }
+            const ItemRegs R{it.sig, it.mus, it.zout, it.levmask};
+            consume_item_any<PERSIST, LEAN>(L, sh, ring, rows, stages, it, R, ev, ct, lane, pol.first, LV, rp, A);
             // warp reduction, then the warp's partial goes to the finisher's mailbox
             double sum_k, mv[kNRed - kNSum];
             warp_reduce(A, lane, sum_k, mv);
@@ -676,6 +710,7 @@ constexpr int kWarpCta = 256;
 template <bool SIM, int ZK, bool LEAN>
 __device__ __forceinline__ void warp_unit(const ItemDesc& it, const double* ra, const double* rb, const double* rz, int d,
                                           const IsoEval& ev, int lane, uint64_t pol, const LazyView& LV, Acc& A) {
+    const ItemRegs R{it.sig, it.mus, it.zout, it.levmask};
     const int npairs = d >> 1;
     constexpr int U = 4;
     for (int p0 = lane; p0 < npairs; p0 += U * 32) {
@@ -693,15 +728,15 @@ __device__ __forceinline__ void warp_unit(const ItemDesc& it, const double* ra, 
             const int p = p0 + k * 32;
             if (p < npairs) {
                 double2 zt;
-                zt.x = elem_zk<SIM, ZK, LEAN>(a[k].x, b[k].x, z[k].x, ev, it, LV, A);
-                zt.y = elem_zk<SIM, ZK, LEAN>(a[k].y, b[k].y, z[k].y, ev, it, LV, A);
+                zt.x = elem_zk<SIM, ZK, LEAN>(a[k].x, b[k].x, z[k].x, ev, R, LV, A);
+                zt.y = elem_zk<SIM, ZK, LEAN>(a[k].y, b[k].y, z[k].y, ev, R, LV, A);
                 if (it.zout) st2_stream(it.zout + 2 * (size_t)p, zt, pol);
             }
         }
     }
     if ((d & 1) && lane == 0) {                               // odd d: the last element
         const int j = d - 1;
-        const double zt = elem_zk<SIM, ZK, LEAN>(ra[j], SIM ? rb[j] : 0.0, (ZK == 1 || ZK == 4) ? rz[j] : 0.0, ev, it, LV, A);
+        const double zt = elem_zk<SIM, ZK, LEAN>(ra[j], SIM ? rb[j] : 0.0, (ZK == 1 || ZK == 4) ? rz[j] : 0.0, ev, R, LV, A);
         if (it.zout) it.zout[j] = zt;
     }
 }
@@ -725,7 +760,7 @@ __device__ __forceinline__ void warp_dispatch(const ItemDesc& it, const double* 
 
 // the launch's units dealt round-robin to the grid's warps (body of iso_warp_stream_kernel and of every phase of
 // solve_persist_kernel's small-d form)
-template <bool PERSIST>
+template <bool PERSIST, bool LEAN = false>
 __device__ __forceinline__ void warp_pass(const SolveLaunch& L) {
     const int lane = threadIdx.x & 31;
     const int gw = (blockIdx.x * kWarpCta + threadIdx.x) >> 5, nw = (gridDim.x * kWarpCta) >> 5;
@@ -759,8 +794,7 @@ __device__ __forceinline__ void warp_pass(const SolveLaunch& L) {
 #pragma unroll
         for (int k = 0; k < kNRed; ++k) A.v[k] = 0.0;
         if constexpr (PERSIST) {
-            if (L.lean) warp_dispatch<true>(it, ra, c.nu, rz, L.d, ev, lane, pol.first, LV, A);
-            else warp_dispatch<false>(it, ra, c.nu, rz, L.d, ev, lane, pol.first, LV, A);
+            warp_dispatch<LEAN>(it, ra, c.nu, rz, L.d, ev, lane, pol.first, LV, A);
         } else {
             if (it.sim) {
                 if (it.zk == 0) warp_unit<true, 0, false>(it, ra, c.nu, rz, L.d, ev, lane, pol.first, LV, A);
@@ -906,14 +940,14 @@ __device__ void phase_launch(const PersistParams& P, int ph, PersistShared& ps) 
     L.stream_stages = L.zrows ? 4 : 6;
 }
 
-template <int STREAM>
+template <int STREAM, bool LEAN>
 __device__ __forceinline__ void run_phase(const SolveLaunch& L, bool reinit) {
     if constexpr (STREAM == 1) {
         extern __shared__ __align__(128) unsigned char dynsm[];
         __shared__ Shared sh;
-        stream_pass<true>(L, sh, reinterpret_cast<double*>(dynsm), reinit);
+        stream_pass<true, LEAN>(L, sh, reinterpret_cast<double*>(dynsm), reinit);
     } else {
-        warp_pass<true>(L);
+        warp_pass<true, LEAN>(L);
         __syncthreads();
     }
 }
@@ -1021,7 +1055,7 @@ __device__ bool wait_step(const PersistParams& P, PersistShared& ps, unsigned se
     return true;
 }
 
-template <int STREAM>
+template <int STREAM, bool LEAN>
 __global__ void __launch_bounds__(STREAM == 1 ? kThreads : kWarpCta, STREAM == 1 ? 1 : 2)
 solve_persist_kernel(const __grid_constant__ PersistParams P) {
     constexpr int V = STREAM == 1 ? 2 : 4;            // lanes of the θ-step's reduction tree per thread (512 / 256 threads carry them)
@@ -1045,7 +1079,7 @@ solve_persist_kernel(const __grid_constant__ PersistParams P) {
     for (int i = 1; i <= P.max_pass; ++i) {
         if (tid == 0) phase_launch(P, i - 1, ps);
         __syncthreads();
-        run_phase<STREAM>(ps.L, reinit);
+        run_phase<STREAM, LEAN>(ps.L, reinit);
         reinit = true;
         if (tid == 0) { __threadfence(); atomicAdd(&ctl->arrive[i - 1], 1); }
         ++seq;
@@ -1059,7 +1093,7 @@ solve_persist_kernel(const __grid_constant__ PersistParams P) {
         if (P.nh_mine > 0) {
             if (tid == 0) phase_launch(P, kPhaseFid, ps);
             __syncthreads();
-            run_phase<STREAM>(ps.L, reinit);
+            run_phase<STREAM, LEAN>(ps.L, reinit);
             reinit = true;
             if (tid == 0) { __threadfence(); atomicAdd(&ctl->arrive[kPhaseFid], 1); }
             ++seq;
@@ -1077,7 +1111,7 @@ solve_persist_kernel(const __grid_constant__ PersistParams P) {
             if (wait_step(P, ps, seq) && !ps.abort && !ps.error) {
                 if (tid == 0) phase_launch(P, kPhaseFd, ps);
                 __syncthreads();
-                run_phase<STREAM>(ps.L, reinit);
+                run_phase<STREAM, LEAN>(ps.L, reinit);
                 if (tid == 0) { __threadfence(); atomicAdd(&ctl->arrive[kPhaseFd], 1); }
                 ran_fd = true;
             }
@@ -1173,12 +1207,19 @@ cudaError_t iso_persist_geometry(const Geometry& geo, int device, int* grid, int
     if (e != cudaSuccess) return e;
     if (!coop || (geo.stream != 1 && geo.stream != 2)) { *grid = 0; *threads = 0; return cudaSuccess; }
     if (geo.stream == 1) {
-        e = cudaFuncSetAttribute(solve_persist_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, geo.smem_bytes);
+        e = cudaFuncSetAttribute(solve_persist_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, geo.smem_bytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_persist_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, geo.smem_bytes);
         if (e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, solve_persist_kernel<1>, kThreads, geo.smem_bytes);
+        int a = 0, b = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, solve_persist_kernel<1, true>, kThreads, geo.smem_bytes);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, solve_persist_kernel<1, false>, kThreads, geo.smem_bytes);
+        per_sm = a < b ? a : b;
         *threads = kThreads;
     } else {
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, solve_persist_kernel<2>, kWarpCta, 0);
+        int a = 0, b = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, solve_persist_kernel<2, true>, kWarpCta, 0);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, solve_persist_kernel<2, false>, kWarpCta, 0);
+        per_sm = a < b ? a : b;
         *threads = kWarpCta;
     }
     if (e != cudaSuccess) return e;
@@ -1188,10 +1229,10 @@ cudaError_t iso_persist_geometry(const Geometry& geo, int device, int* grid, int
 
 cudaError_t launch_iso_persist(const PersistParams& P, const Geometry& geo, int grid, cudaStream_t st) {
     void* args[] = {const_cast<PersistParams*>(&P)};
-    if (geo.stream == 1)
-        return cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(&solve_persist_kernel<1>), dim3(grid), dim3(kThreads), args,
-                                           (size_t)geo.smem_bytes, st);
-    return cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(&solve_persist_kernel<2>), dim3(grid), dim3(kWarpCta), args, 0, st);
+    const void* fn = geo.stream == 1 ? (P.lean ? reinterpret_cast<const void*>(&solve_persist_kernel<1, true>) : reinterpret_cast<const void*>(&solve_persist_kernel<1, false>))
+                                     : (P.lean ? reinterpret_cast<const void*>(&solve_persist_kernel<2, true>) : reinterpret_cast<const void*>(&solve_persist_kernel<2, false>));
+    if (geo.stream == 1) return cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kThreads), args, (size_t)geo.smem_bytes, st);
+    return cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kWarpCta), args, 0, st);
 }
 
 // warp-per-unit geometry (small d)
