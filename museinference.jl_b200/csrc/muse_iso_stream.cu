@@ -183,18 +183,26 @@ __device__ __forceinline__ double elem3(double p, double q, double z0in, const I
 // [host-test:end elem3]
 
 // lazy ẑ: the unit's current ẑ from its base normals — the committed points of the earlier passes, replayed with the very
-// operations elem3 used to produce them (bit for bit what the chain of launches would have stored and read back)
-template <bool SIM>
-__device__ __forceinline__ double lazy_level(double p, double q, double z, const LazyLevel& v) {
-    const double x = SIM ? fma(v.sig, p, v.mus) + q : p;
-    const double r0 = x - z, w0 = z - v.mu;
-    const double g0 = fma(v.a, w0, -r0);
-    return fma(v.cspec, -g0, z);
+// operations elem3 used to produce them (bit for bit what the chain of launches would have stored and read back).
+// The levels' constants sit in shared memory and are read with ld.shared through a pure (non-volatile) asm: the compiler is free to
+// keep them in registers across elements or to reload them — a generic load per element is what it emitted for a plain pointer.
+__device__ __forceinline__ double lds_f64(uint32_t saddr) {
+    double v;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(saddr));
+    return v;
 }
-// what a consumer needs of the launch's lazy description (the levels stay in shared memory: broadcast reads, no registers held
-// across the element loop)
+template <bool SIM>
+__device__ __forceinline__ double lazy_level(double p, double q, double z, uint32_t lev) {     // lev: shared address of a LazyLevel
+    const double sig = lds_f64(lev), mus = lds_f64(lev + 8), a = lds_f64(lev + 16), mu = lds_f64(lev + 24), cspec = lds_f64(lev + 32);
+    const double x = SIM ? fma(sig, p, mus) + q : p;
+    const double r0 = x - z, w0 = z - mu;
+    const double g0 = fma(a, w0, -r0);
+    return fma(cspec, -g0, z);
+}
+static_assert(sizeof(LazyLevel) == 40 && offsetof(LazyLevel, cspec) == 32, "LazyLevel layout (lazy_level reads it field by field)");
+// what a consumer needs of the launch's lazy description
 struct LazyView {
-    const LazyLevels* all;
+    uint32_t lev0;           // shared address of level 0
     int nlev;
 };
 template <bool SIM>
@@ -202,12 +210,12 @@ __device__ __forceinline__ double lazy_z0(double p, double q, double zstart, con
     // no branches: a level the unit did not step at (a 0-iteration solve — rare) is evaluated and dropped by a select, so that the
     // elements of a thread stay independent instruction streams
     double z = zstart;
-    if (LV.nlev == 1) {                      // the hot case: the second pass of a solve
-        const double zn = lazy_level<SIM>(p, q, z, LV.all->lev[0]);
-        return (mask & 1u) ? zn : z;
+    if (LV.nlev >= 1) {                      // the hot case: the second pass of a solve
+        const double zn = lazy_level<SIM>(p, q, z, LV.lev0);
+        z = (mask & 1u) ? zn : z;
     }
-    for (int l = 0; l < LV.nlev; ++l) {
-        const double zn = lazy_level<SIM>(p, q, z, LV.all->lev[l]);
+    for (int l = 1; l < LV.nlev; ++l) {
+        const double zn = lazy_level<SIM>(p, q, z, LV.lev0 + (uint32_t)l * (uint32_t)sizeof(LazyLevel));
         z = ((mask >> l) & 1u) ? zn : z;
     }
     return z;
@@ -226,7 +234,7 @@ __device__ __forceinline__ double elem_zk(double p, double q, double z0in, const
 }
 __device__ __forceinline__ LazyView lazy_view(const SolveLaunch& L) {
     LazyView LV;
-    LV.all = L.lazy;
+    LV.lev0 = L.lazy ? smem_u32(&L.lazy->lev[0]) : 0u;
     LV.nlev = L.lazy ? L.lazy->nlev : 0;
     return LV;
 }
@@ -649,7 +657,7 @@ __device__ __forceinline__ void stream_pass(const SolveLaunch& L, Shared& sh, do
         const int ct = (int)threadIdx.x - 64, cw = warp - 2;
         const IsoEval ev = launch_ev(L);
         const L2Policy pol = make_policies();
-        const LazyView LV = PERSIST ? lazy_view(L) : LazyView{nullptr, 0};
+        const LazyView LV = PERSIST ? lazy_view(L) : LazyView{0u, 0};
         RingPos rp{0, 0u};
         for (int i = 0;; ++i) {
             Acc A;
@@ -770,7 +778,7 @@ __device__ __forceinline__ void warp_pass(const SolveLaunch& L) {
     NoIssuer none;
     Controller<WarpCtx, NoIssuer> u(ctx, L, none);            // only for setup_unit (pointer logic)
     const double* zshared = u.resolve_zshared();
-    const LazyView LV = PERSIST ? lazy_view(L) : LazyView{nullptr, 0};
+    const LazyView LV = PERSIST ? lazy_view(L) : LazyView{0u, 0};
     for (int unit = gw; unit < L.nitems; unit += nw) {
         int* zs = u.setup_unit(unit, zshared, nullptr);
         const Cmd& c = u.cur;
