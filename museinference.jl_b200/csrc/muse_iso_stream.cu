@@ -877,6 +877,7 @@ struct PersistShared {
     DynConsts dyn[2];                 // its θ-dependent constants ([1]: FD sims)
     LazyLevels lazy;                  // constants of the launch's earlier passes (lazy ẑ)
     double red[kMaxTheta][32];        // CTA 0: scratch of the reduction tree
+    StepCache cache;                  // CTA 0: θ, the last history row's θ, the last variance (muse_outer_dev.cuh)
     int bad;
     int done, error, abort, timeout;  // CTA 0's message after the phase, as every CTA has read it
     int l_abort;                      // CTA 0: this phase handed units back (here or on a peer)
@@ -980,7 +981,8 @@ __device__ void exchange_rows(const PersistParams& P, PersistShared& ps, const d
         const double v = bad ? __longlong_as_double(0x7ff8000000000000LL) : __ldcg(src + e);
         for (int q = 0; q < X.nranks; ++q) dst[q][(size_t)X.rank * need + e] = v;
     }
-    __threadfence_system();
+    // the rows of all threads happen-before the barrier, the barrier before the flag threads' release stores: one system-scope
+    // release per peer orders everything (a __threadfence_system() in each of the CTA's 18 warps cost more than the exchange)
     __syncthreads();
     if (tid < X.nranks && tid != X.rank) {
         st_release_sys(X.flags[tid] + 2 * X.rank, ep * 2 + (ps.l_abort ? 1ULL : 0ULL));
@@ -1012,6 +1014,7 @@ __device__ void leader_step(const PersistParams& P, PersistShared& ps, int i, un
         for (int q = 0; q < P.x.nranks; ++q) dst[q] = P.x.gall[q][ph];
         exchange_rows(P, ps, ob.g + nt, ob.status + 1, P.step.counts[P.x.rank] * nt, nt, dst, P.step.need, P.x.epoch0 + i);
         g_all = P.x.gall[P.x.rank][ph];
+        if (tid == 0 && ph < 2) P.stamps[11 + ph] = gtime_ns();          // diagnostics: rows of every peer are here
     }
     if (!ps.l_abort && !ps.timeout) {
         OuterParams S = P.step;
@@ -1020,21 +1023,21 @@ __device__ void leader_step(const PersistParams& P, PersistShared& ps, int i, un
         S.status_local = ob.status;
         S.g_all = g_all;
         S.dyn_next = &ctl->dyn[0];
-        theta_step_body<V>(S, ps.red, &ps.bad);
+        theta_step_body<V>(S, ps.red, &ps.bad, &ps.cache);
         __syncthreads();
-        if (P.get_cov && st->done && !st->error) {
+        if (P.get_cov && ps.cache.done && !ps.cache.error) {
             CovParams C = P.cov;
             C.dyn_fid = &ctl->dyn[0];
             C.dyn_fd = &ctl->dyn[1];
-            cov_prep_body<V>(C, ps.red);
+            cov_prep_body<V>(C, ps.red, &ps.cache);
         }
     }
     __syncthreads();
     if (tid == 0) {
-        if (ps.timeout) { st->error = 3; st->done = 1; }
+        if (ps.timeout) { st->error = 3; st->done = 1; ps.cache.error = 3; ps.cache.done = 1; }
         if (ps.l_abort) st->abort = 1;
-        ctl->msg_done = st->done;
-        ctl->msg_error = st->error;
+        ctl->msg_done = ps.cache.done;
+        ctl->msg_error = ps.cache.error;
         ctl->msg_abort = ps.l_abort;
         P.stamps[2 + 2 * ph] = gtime_ns();
         __threadfence();
@@ -1042,7 +1045,8 @@ __device__ void leader_step(const PersistParams& P, PersistShared& ps, int i, un
     }
 }
 
-// every CTA: until CTA 0 has released `seq`; then its message and the constants it published are in ps
+// every CTA: until CTA 0 has released `seq`; then its message and the constants it published are in ps (one round trip to the L2
+// for both: every thread fetches one word)
 __device__ bool wait_step(const PersistParams& P, PersistShared& ps, unsigned seq) {
     PersistCtl* const ctl = P.ctl;
     const int tid = threadIdx.x;
@@ -1050,18 +1054,18 @@ __device__ bool wait_step(const PersistParams& P, PersistShared& ps, unsigned se
         const long long t0 = gtime_ns();
         while (ld_acquire_gpu(&ctl->step_flag) < seq)
             if (gtime_ns() - t0 > kSpinTimeoutNs + 1000000000LL) { ps.timeout = 1; break; }
-        ps.done = __ldcg(&ctl->msg_done);
-        ps.error = __ldcg(&ctl->msg_error);
-        ps.abort = __ldcg(&ctl->msg_abort);
     }
     __syncthreads();
     if (ps.timeout) return false;
     constexpr int kWords = 2 * (int)sizeof(DynConsts) / 8;
-    for (int w = tid; w < kWords; w += blockDim.x)
-        reinterpret_cast<double*>(ps.dyn)[w] = __ldcg(reinterpret_cast<const double*>(ctl->dyn) + w);
+    if (tid < kWords) reinterpret_cast<double*>(ps.dyn)[tid] = __ldcg(reinterpret_cast<const double*>(ctl->dyn) + tid);
+    else if (tid == kWords) ps.done = __ldcg(&ctl->msg_done);
+    else if (tid == kWords + 1) ps.error = __ldcg(&ctl->msg_error);
+    else if (tid == kWords + 2) ps.abort = __ldcg(&ctl->msg_abort);
     __syncthreads();
     return true;
 }
+static_assert(2 * sizeof(DynConsts) / 8 + 3 <= kWarpCta, "wait_step: one word per thread");
 
 template <int STREAM, bool LEAN>
 __global__ void __launch_bounds__(STREAM == 1 ? kThreads : kWarpCta, STREAM == 1 ? 1 : 2)
@@ -1077,7 +1081,11 @@ solve_persist_kernel(const __grid_constant__ PersistParams P) {
         if (lead) {
             OuterState* st = P.step.st;
             st->n_iter = 0; st->done = 0; st->error = 0; st->abort = 0;
-            for (int c = 0; c < kMaxTheta; ++c) { st->theta[c] = P.theta0[c]; st->step[c] = 0.0; }
+            for (int c = 0; c < kMaxTheta; ++c) {
+                st->theta[c] = P.theta0[c]; st->step[c] = 0.0;
+                ps.cache.theta[c] = P.theta0[c]; ps.cache.row_theta[c] = 0.0; ps.cache.var[c] = 0.0;
+            }
+            ps.cache.n_iter = ps.cache.done = ps.cache.error = 0;
             for (int k = 0; k < 16; ++k) P.stamps[k] = 0;
             P.stamps[0] = gtime_ns();
         }

@@ -459,10 +459,12 @@ extern "C" int muse_b200_muse_solve(muse_handle* h, const double* theta0, int32_
             static const bool dbg_timing = [] { const char* e = std::getenv("MUSE_DEBUG_TIMING"); return e && *e; }();
             if (dbg_timing) {
                 const long long* T = sh_->stamp;
-                std::fprintf(stderr, "[muse_solve persist rank %d] n_iter=%d host: set-up+launch %.1f us, until synchronised %.1f us | kernel stamps (us since start):",
-                             h->comm_rank, n_now, std::chrono::duration<double>(t_launched - t0).count() * 1e6, chunk_s * 1e6);
-                for (int k = 1; k < 12; ++k) std::fprintf(stderr, " %.1f", T[k] ? (double)(T[k] - T[0]) * 1e-3 : -1.0);
-                std::fprintf(stderr, "\n");
+                char line[512];
+                int off = std::snprintf(line, sizeof line, "[muse_solve persist rank %d] n_iter=%d host: set-up+launch %.1f us, until synchronised %.1f us | kernel stamps (us since start):",
+                                        h->comm_rank, n_now, std::chrono::duration<double>(t_launched - t0).count() * 1e6, chunk_s * 1e6);
+                for (int k = 1; k < 13 && off < (int)sizeof line - 16; ++k)
+                    off += std::snprintf(line + off, sizeof line - off, " %.1f", T[k] ? (double)(T[k] - T[0]) * 1e-3 : -1.0);
+                std::fprintf(stderr, "%s\n", line);
             }
             {   // statistics: one launch; units and algorithmic bytes of the phases that ran, their times from CTA 0's globaltimer stamps
                 const double d8 = 8.0 * h->cfg.d;

@@ -130,28 +130,30 @@ __device__ inline void block_sums(const int* counts, int nranks, long long need,
         for (int j = 0; j < V; ++j)
 #pragma unroll
             for (int c = 0; c < NT; ++c) acc[j][c] = 0.0;
-        // every lane walks its sims in increasing order; the loads of a thread's V lanes (and of four steps) are independent and
-        // issued together — a lone CTA is latency-bound, not bandwidth-bound
+        // every lane walks its sims in increasing order (k = t, t + T, t + 2T, …).  The loads of four steps of ALL the thread's V
+        // lanes are issued before the first addition: a lone CTA is bound by the latency of dependent round trips to the L2, not by
+        // bandwidth (with the lanes one after the other a θ-step over 10⁴ sims took 29 µs)
+        constexpr int S = 4;
+        for (int k0 = 0; k0 < n_total; k0 += S * T) {
+            double v[S][V][NT];
+            bool ok[S][V];
 #pragma unroll
-        for (int j = 0; j < V; ++j) {
-            const int t = (pw + j * (PT / 32)) * 32 + lane;
-            int k = t;
-            for (; k + 3 * T < n_total; k += 4 * T) {
-                const size_t o0 = row_off(k), o1 = row_off(k + T), o2 = row_off(k + 2 * T), o3 = row_off(k + 3 * T);
+            for (int st = 0; st < S; ++st)
 #pragma unroll
-                for (int c = 0; c < NT; ++c) {
-                    if (c < nt) {
-                        const double v0 = f(o0, c), v1 = f(o1, c), v2 = f(o2, c), v3 = f(o3, c);
-                        acc[j][c] += v0; acc[j][c] += v1; acc[j][c] += v2; acc[j][c] += v3;
-                    }
+                for (int j = 0; j < V; ++j) {
+                    const int k = k0 + st * T + (pw + j * (PT / 32)) * 32 + lane;
+                    ok[st][j] = k < n_total;
+                    const size_t o = ok[st][j] ? row_off(k) : 0;
+#pragma unroll
+                    for (int c = 0; c < NT; ++c) v[st][j][c] = (ok[st][j] && c < nt) ? f(o, c) : 0.0;
                 }
-            }
-            for (; k < n_total; k += T) {
-                const size_t o = row_off(k);
 #pragma unroll
-                for (int c = 0; c < NT; ++c)
-                    if (c < nt) acc[j][c] += f(o, c);
-            }
+            for (int st = 0; st < S; ++st)
+#pragma unroll
+                for (int j = 0; j < V; ++j)
+#pragma unroll
+                    for (int c = 0; c < NT; ++c)
+                        if (ok[st][j] && c < nt) acc[j][c] += v[st][j][c];
         }
 #pragma unroll
         for (int j = 0; j < V; ++j) {
@@ -193,11 +195,20 @@ __device__ inline void block_mean_var(const double* g, const int* counts, int nr
     else block_mean_var_nt<V, kMaxTheta>(g, counts, nranks, need, nt, n_total, sh, mean, var);
 }
 
+// solve_persist_kernel: CTA 0 lives through the whole solve, so what one θ-step needs of the previous one (θ, the last history
+// row, the variance the covariance stage starts from) stays in its shared memory instead of making dependent round trips to the L2
+struct StepCache {
+    double theta[kMaxTheta];        // θ after the last update
+    double row_theta[kMaxTheta];    // θ at which the last executed iteration evaluated
+    double var[kMaxTheta];          // corrected variance of the last scores
+    int n_iter, done, error;
+};
+
 // What the host loop does between two passes (src/muse.jl:183-224, the test of :163-166 for the NEXT iteration), by all
 // threads of one CTA (≥ kStepLanes / V threads).  Thread 0 writes the history row, θ, the flags and the constants of the next
 // pass (*dyn_next, which may live in global or shared memory).
 template <int V>
-__device__ inline void theta_step_body(const OuterParams& P, double (*sh)[32], int* bad) {
+__device__ inline void theta_step_body(const OuterParams& P, double (*sh)[32], int* bad, StepCache* cache = nullptr) {
     OuterState* st = P.st;
     if (threadIdx.x == 0) *bad = 0;
     __syncthreads();
@@ -232,16 +243,20 @@ __device__ inline void theta_step_body(const OuterParams& P, double (*sh)[32], i
     if (mine) *bad = 1;
     __syncthreads();
     if (*bad) {
-        if (threadIdx.x == 0) { st->error = 1; st->done = 1; if (P.dyn_next) P.dyn_next->skip = 1; }
+        if (threadIdx.x == 0) {
+            st->error = 1; st->done = 1;
+            if (cache) { cache->error = 1; cache->done = 1; }
+            if (P.dyn_next) P.dyn_next->skip = 1;
+        }
         return;
     }
     const int row = P.iter - 1;
     double mean[kMaxTheta], var[kMaxTheta];
     block_mean_var<V>(P.g_all, P.counts, P.nranks, P.need, P.nt, P.n_total, sh, mean, var);
     if (threadIdx.x != 0) return;
-    double th_new[kMaxTheta];
+    double th_new[kMaxTheta], hip[kMaxTheta];
     for (int c = 0; c < P.nt; ++c) {
-        const double th = st->theta[c];
+        const double th = cache ? cache->theta[c] : st->theta[c];
         const double g_dat = __ldcg(P.g_local + c);
         const double g_like = g_dat - mean[c];                                                     // :183
         const double g_prior = P.have_prior ? -(th - P.prior_mean[c]) / (P.prior_sigma[c] * P.prior_sigma[c]) : 0.0;   // :184
@@ -254,23 +269,31 @@ __device__ inline void theta_step_body(const OuterParams& P, double (*sh)[32], i
             R.theta[c] = th; R.g_dat[c] = g_dat; R.g_like[c] = g_like; R.g_prior[c] = g_prior;
             R.h_inv_like[c] = h_inv_like; R.h_prior[c] = h_prior; R.h_inv_post[c] = h_inv_post;
         }
+        hip[c] = h_inv_post;
         th_new[c] = th - P.alpha * (h_inv_post * g_post);                                          // :224
     }
     for (int c = 0; c < P.nt; ++c) st->theta[c] = th_new[c];                                       // :230
     st->n_iter = P.iter;
-    int done = 0;
+    int done = 0, err2 = 0;
     if (P.iter >= 2) {                                   // the test at the top of iteration iter + 1 > 2   (:163-166)
         double q = 0.0;
         for (int c = 0; c < P.nt; ++c) {
-            const double dlt = st->row[row].theta[c] - st->row[row - 1].theta[c];
-            q += dlt * st->row[row].h_inv_post[c] * dlt;
+            // (θ of this row = θ before this update; the row before it comes from the cache when there is one — same values)
+            const double th_row = cache ? cache->theta[c] : st->row[row].theta[c];
+            const double th_prev = cache ? cache->row_theta[c] : st->row[row - 1].theta[c];
+            const double dlt = th_row - th_prev;
+            q += dlt * hip[c] * dlt;
         }
         q = -q;
-        if (q < 0.0) { st->error = 2; done = 1; }        // DomainError of sqrt in the reference
+        if (q < 0.0) { st->error = 2; err2 = 1; done = 1; }        // DomainError of sqrt in the reference
         else if (sqrt(q) < P.theta_rtol) done = 1;
     }
     if (P.iter >= P.maxsteps) done = 1;
     st->done = done;
+    if (cache) {
+        for (int c = 0; c < P.nt; ++c) { cache->row_theta[c] = cache->theta[c]; cache->theta[c] = th_new[c]; cache->var[c] = var[c]; }
+        cache->n_iter = P.iter; cache->done = done; cache->error = err2 ? 2 : 0;
+    }
     if (P.dyn_next) {
         consts_of(P.family, P.d, th_new, th_new, &P.dyn_next->smp[0], &P.dyn_next->ev);
         P.dyn_next->skip = done;
@@ -280,19 +303,25 @@ __device__ inline void theta_step_body(const OuterParams& P, double (*sh)[32], i
 // after the last θ-step: if the loop has ended, step = 0.1 ./ std(gs) (:411-413) and the constants of get_H!'s launches;
 // otherwise they are skipped.  All threads of one CTA.
 template <int V>
-__device__ inline void cov_prep_body(const CovParams& P, double (*sh)[32]) {
+__device__ inline void cov_prep_body(const CovParams& P, double (*sh)[32], const StepCache* cache = nullptr) {
     volatile OuterState* st = P.st;      // written by this CTA's thread 0 a barrier ago when the θ-step ran in the same launch
-    if (!st->done || st->error || st->n_iter < 1) {
+    const int s_done = cache ? cache->done : st->done, s_error = cache ? cache->error : st->error, s_iter = cache ? cache->n_iter : st->n_iter;
+    if (!s_done || s_error || s_iter < 1) {
         if (threadIdx.x == 0) { P.dyn_fid->skip = 1; P.dyn_fd->skip = 1; }
         return;
     }
-    const double* gall = P.g_all_slot[(st->n_iter - 1) % kOuterSlots];
     double step[kMaxTheta], mean[kMaxTheta], var[kMaxTheta];
-    block_mean_var<V>(gall, P.counts, P.nranks, P.need, P.nt, P.n_total, sh, mean, var);
+    if (cache) {
+        // the θ-step of this very launch has just reduced the same scores with the same tree: its variance IS the one below
+        for (int c = 0; c < P.nt; ++c) var[c] = cache->var[c];
+    } else {
+        const double* gall = P.g_all_slot[(s_iter - 1) % kOuterSlots];
+        block_mean_var<V>(gall, P.counts, P.nranks, P.need, P.nt, P.n_total, sh, mean, var);
+    }
     for (int c = 0; c < P.nt; ++c) step[c] = 0.1 / sqrt(var[c]);       // step = 0.1 ./ std(gs)   (:411-413), gs = the last scores (:231)
     if (threadIdx.x != 0) return;
     double th0[kMaxTheta];
-    for (int c = 0; c < P.nt; ++c) { th0[c] = st->theta[c]; st->step[c] = step[c]; }
+    for (int c = 0; c < P.nt; ++c) { th0[c] = cache ? cache->theta[c] : st->theta[c]; st->step[c] = step[c]; }
     consts_of(P.family, P.d, th0, th0, &P.dyn_fid->smp[0], &P.dyn_fid->ev);
     P.dyn_fid->skip = 0;
     consts_of(P.family, P.d, th0, th0, nullptr, &P.dyn_fd->ev);
