@@ -215,6 +215,11 @@ int  muse_b200_fd_jacobian(muse_handle* h, const double* theta0, const double* s
                            double* Hs_out /* nsims_H × ntheta × ntheta */,
                            int32_t* status_out /* nsims_H × ntheta × 2, may be NULL */);
 
+/* Start vector of the fiducial solve of the two entry points around this comment: MUSE_START_ZEROS (default; the reference's
+ * ẑ_guess_from_truth, src/interface.jl:184-186) or MUSE_START_USER (the `z₀` keyword of get_H!, src/muse.jl:309, 419; needs
+ * muse_b200_set_z0).  Stays in force until changed. */
+int  muse_b200_fd_start(muse_handle* h, int32_t start);
+
 /* The same launch sequence with the raw scores returned and arbitrary sample points: row 2n / 2n+1 of theta_sims is the
  * "−" / "+" point at which the sims of Jacobian column n are generated (src/muse.jl:430); MAP and score are taken at
  * theta_eval (:431-432).  g_out[k][2n+s][i] = g_i of sim k at point (n, s).  This is what a host needs when θ lives in a

@@ -302,6 +302,10 @@ class B200Backend:
                                                     _ip(status)))
         return Hs, status
 
+    def fd_start(self, start: int):
+        """Start of get_H!'s fiducial solve: START_ZEROS (default) or START_USER (the vector given to set_z0)."""
+        self._check(self._lib.muse_b200_fd_start(self._h, int(start)))
+
     def fd_scores(self, theta_eval, theta_sims, nsims_H: int, atol):
         """Raw scores of the get_H! virtual sims at arbitrary sample points (include/muse_b200.h: muse_b200_fd_scores):
         ``theta_sims[2n + s]`` is the −/+ point of Jacobian column n; returns g[k, 2n + s, :] and the statuses."""

@@ -622,7 +622,9 @@ static int fd_launch(muse_handle* h, const double* theta0, const double* th_pts,
     F.nitems = 1;
     F.mode = 2;
     F.atol = atol;
-    F.start_kind = kStartZero;
+    // start of the fiducial solve: zero(z) (ẑ_guess_from_truth's default) or the user's z₀ (`z₀` keyword of get_H!, src/muse.jl:309, 419)
+    F.start_kind = h->fd_start_user ? kStartSharedKeep : kStartZero;
+    F.zshared = h->z0user;
     if (dyn_fid) F.dyn = dyn_fid;
     else if (theta_consts(h->cfg, theta0, theta0, &F.smp[0], &F.ev) != 0) MUSE_FAIL(h, MUSE_EUNSUPPORTED, "family");
     F.zA = h->zfidA;
@@ -679,6 +681,14 @@ static int fd_check(muse_handle* h, int nsims_H) {
     const bool hshard = h->cfg.nsims_h > 0;
     if (nsims_H < 0 || nsims_H > (hshard ? h->cfg.nsims_h : h->cfg.nsims)) MUSE_FAIL(h, MUSE_EINVAL, "nsims_H outside the handle's H shard");
     if (!h->have_draws || (hshard && !h->have_draws_h)) MUSE_FAIL(h, MUSE_ESTATE, "no draws installed (set_draws[_h] / seed_draws)");
+    return MUSE_OK;
+}
+
+int muse_b200_fd_start(muse_handle* h, int32_t start) {
+    if (!h || (start != MUSE_START_ZEROS && start != MUSE_START_USER)) return MUSE_EINVAL;
+    if (start == MUSE_START_USER && !h->have_z0) MUSE_FAIL(h, MUSE_ESTATE, "user z0 not set (muse_b200_set_z0)");
+    if (start == MUSE_START_USER && h->corr) MUSE_FAIL(h, MUSE_EUNSUPPORTED, "corrgauss: the fiducial solve of get_H! starts from zero(z)");
+    h->fd_start_user = start == MUSE_START_USER;
     return MUSE_OK;
 }
 

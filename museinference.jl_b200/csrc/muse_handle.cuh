@@ -52,6 +52,7 @@ struct muse_handle {
     std::string err;
     Geometry geo{};
     bool have_data = false, have_draws = false, have_z0 = false;
+    bool fd_start_user = false;     // get_H!'s fiducial solve starts from the user's z₀ (muse_b200_fd_start)
 
     // device arrays
     double *xi = nullptr, *nu = nullptr;          // (nsims+1) × ld, last row = master draw

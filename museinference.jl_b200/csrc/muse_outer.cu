@@ -352,7 +352,7 @@ extern "C" int muse_b200_muse_solve(muse_handle* h, const double* theta0, int32_
         pkey.insert(pkey.end(), reinterpret_cast<const unsigned char*>(dbl), reinterpret_cast<const unsigned char*>(dbl) + sizeof(dbl));
         pkey.insert(pkey.end(), reinterpret_cast<const unsigned char*>(ints), reinterpret_cast<const unsigned char*>(ints) + sizeof(ints));
     }
-    if (persist_on && h->persist_grid > 0 && nt <= 2 && !h->dbg && (!multi || p2p_fit) && pkey != h->persist_off_key) {
+    if (persist_on && h->persist_grid > 0 && nt <= 2 && !h->dbg && !h->fd_start_user && (!multi || p2p_fit) && pkey != h->persist_off_key) {
         const auto t0 = std::chrono::steady_clock::now();
         if (!h->persist_ctl) {
             OUTER_TRY(h, cudaMalloc(&h->persist_ctl, sizeof(PersistCtl)));

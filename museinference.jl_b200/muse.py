@@ -42,6 +42,39 @@ def _ascii_kwargs(kw: dict) -> dict:
     return {_KW_ALIASES.get(k, k): v for k, v in kw.items()}
 
 
+def central_fdm(p: int, q: int = 1):
+    """``FiniteDifferences.central_fdm(p, q)`` as get_H!'s ``fdm`` keyword takes it (src/muse.jl:300): the symmetric integer grid
+    of p points and the coefficients c with Σᵢ cᵢ gᵢᵏ = q!·δ_{kq} (exact rationals, rounded to Float64).  Only first
+    derivatives of odd-point methods (q = 1; p = 3, 5, 7, …) can be served by the backend's ± sample points; the step is always
+    explicit (``step`` or 0.1 ./ std(result.gs), src/muse.jl:411-413) — the package's adaptive step estimation is not provided."""
+    from fractions import Fraction
+    from math import factorial
+    if q != 1 or p < 3 or p % 2 == 0:
+        raise MuseBackendError(-5, "fdm: only central_fdm(p, 1) with an odd number of points p ≥ 3 is provided")
+    grid = list(range(-(p // 2), p // 2 + 1))
+    A = [[Fraction(g) ** k for g in grid] + [Fraction(factorial(q) if k == q else 0)] for k in range(p)]
+    for c in range(p):
+        piv = next(r for r in range(c, p) if A[r][c] != 0)
+        A[c], A[piv] = A[piv], A[c]
+        A[c] = [v / A[c][c] for v in A[c]]
+        for r in range(p):
+            if r != c and A[r][c] != 0:
+                A[r] = [vr - A[r][c] * vc for vr, vc in zip(A[r], A[c])]
+    return tuple(float(g) for g in grid), tuple(float(A[k][p]) for k in range(p))
+
+
+class SimpleCovariance:
+    """``CovarianceEstimation.SimpleCovariance(corrected=…)`` — get_J!'s ``covariance_method`` (src/muse.jl:494, 529): the sample
+    covariance of the scores normalised by n − 1 (corrected, the reference's default) or by n.  Any callable
+    ``gs (N×nθ) → nθ×nθ matrix`` may be passed instead (the package's shrinkage estimators are not provided)."""
+
+    def __init__(self, corrected: bool = False):
+        self.corrected = bool(corrected)
+
+    def __call__(self, gs):
+        return np.atleast_2d(np.cov(np.asarray(gs, dtype=np.float64), rowvar=False, ddof=1 if self.corrected else 0))
+
+
 class FusedHistory:
     """``result.history`` of a solve that ran inside the library: the rows (one dict per iteration, src/muse.jl:211-221) are
     built from the library's history arrays on first access — a solve whose caller only wants θ̂ ± σ never pays for them.
@@ -376,6 +409,9 @@ def get_J_(result: MuseResult, prob: AbstractMuseProblem, theta0=None, **kwargs)
     pool = kw.pop("pool", None) or LocalPool()
     kw.pop("progress", False)
     skip_errors = kw.pop("skip_errors", False)
+    covariance_method = kw.pop("covariance_method", None) or SimpleCovariance(corrected=True)   # :494
+    if not callable(covariance_method):
+        raise TypeError("get_J!: covariance_method must be a SimpleCovariance or a callable gs → matrix")
     nh_total = kw.pop("_nh_total", 0)
     if kw:
         raise TypeError(f"get_J!: unknown keyword argument(s) {sorted(kw)}")
@@ -417,7 +453,7 @@ def get_J_(result: MuseResult, prob: AbstractMuseProblem, theta0=None, **kwargs)
     if theta0.size == 1:
         result.J = np.array([[np.var(gs[:, 0], ddof=1)]])                          # :529 var
     else:
-        result.J = np.cov(gs, rowvar=False, ddof=1)                                # :529 cov(SimpleCovariance(corrected=true))
+        result.J = np.asarray(covariance_method(gs), dtype=np.float64)             # :529 cov(covariance_method, gs)
     finalize_result_(result, prob)
     return result
 
@@ -439,10 +475,17 @@ def get_H_(result: MuseResult, prob: AbstractMuseProblem, theta0=None, **kwargs)
     if kw.pop("implicit_diff", False):
         raise MuseBackendError(-5, "implicit_diff=true (experimental in the reference, src/muse.jl:287, 335-405) "
                                    "is not provided by the B200 backend")
-    if kw.pop("fdm", None) is not None:
-        raise MuseBackendError(-5, "only fdm = central_fdm(3,1) (the reference default, src/muse.jl:300) is provided")
-    if z0 is not None:
-        raise MuseBackendError(-5, "get_H!: a user z₀ is not supported; the fiducial start is zero(z) (src/muse.jl:419)")
+    fdm = kw.pop("fdm", None)                                                      # :300; None = central_fdm(3,1)
+    if fdm is not None:
+        try:
+            grid, coefs = fdm
+            grid, coefs = tuple(float(g) for g in grid), tuple(float(c) for c in coefs)
+            M = len(grid) // 2
+            assert len(grid) == len(coefs) and len(grid) % 2 == 1 and grid == tuple(float(g) for g in range(-M, M + 1))
+        except Exception:
+            raise MuseBackendError(-5, "fdm must come from central_fdm(p, 1) (odd p): a symmetric integer grid and its coefficients")
+        if grid == (-1.0, 0.0, 1.0) and coefs == (-0.5, 0.0, 0.5):
+            fdm = None
     if kw:
         raise TypeError(f"get_H!: unknown keyword argument(s) {sorted(kw)}")
     _check_problem(prob)
@@ -465,29 +508,47 @@ def get_H_(result: MuseResult, prob: AbstractMuseProblem, theta0=None, **kwargs)
     n_total = max(nsims_total, nsims_remaining)
     be = prob.backend_for(n_total, rng, pool, nsims_remaining)
     _, hcnt = pool.shard(nsims_remaining)
-    if not prob.has_transform:
-        Hs_local, status = be.fd_jacobian(theta0, step, hcnt, atol)                # :417-442 + src/util.jl:9-26
-    else:
-        # pjacobian perturbs the UNtransformed θ₀ (src/util.jl:15; sims at θ, MAP and score at θ₀, :430-432); the
-        # kernels take θ′, so the 2·nθ sample points are mapped one by one and the central difference
-        # sum(fs .* [-1/2, 0, 1/2]) / step and the change of variables g = g′ ⊘ ∂θ/∂θ′ are formed here
-        nt = prob.ntheta
-        theta0_t = prob.transform_theta(theta0)
-        pts = np.empty((2 * nt, nt))
-        for n in range(nt):
-            for sgn in (0, 1):
-                th = theta0.copy()
-                th[n] = theta0[n] + (0.0 + step[n] * (1.0 if sgn else -1.0))
-                pts[2 * n + sgn] = prob.transform_theta(th)
-        g_t, st = be.fd_scores(theta0_t, pts, hcnt, atol)
-        g_u = g_t / prob.dinv_transform(theta0_t)
-        Hs_local = np.empty((hcnt, nt, nt))
-        for n in range(nt):
-            acc = g_u[:, 2 * n, :] * -0.5
-            acc = acc + 0.0
-            acc = acc + g_u[:, 2 * n + 1, :] * 0.5
-            Hs_local[:, :, n] = acc / step[n]
-        status = st.reshape(hcnt, nt, 2)
+    if z0 is not None:                                                             # :419  z_start = @something(z₀, …)
+        if not hasattr(be, "fd_start"):
+            raise MuseBackendError(-5, "get_H!: this backend cannot start the fiducial solve from a user z₀")
+        be.set_z0(z0)
+        be.fd_start(_capi.START_USER)
+    try:
+        if not prob.has_transform and fdm is None:
+            Hs_local, status = be.fd_jacobian(theta0, step, hcnt, atol)            # :417-442 + src/util.jl:9-26
+        else:
+            # pjacobian perturbs the UNtransformed θ₀ (src/util.jl:15; sims at θ, MAP and score at θ₀, :430-432); the kernels
+            # take θ′, so the sample points are mapped one by one and sum(fs .* coefs) / step and the change of variables
+            # g = g′ ⊘ ∂θ/∂θ′ are formed here.  One fd_scores call serves the ± pair of one grid distance m (p-point central
+            # methods: m = 1 … (p − 1)/2); the centre point, whose coefficient is 0, is not executed.
+            nt = prob.ntheta
+            grid, coefs = fdm if fdm is not None else ((-1.0, 0.0, 1.0), (-0.5, 0.0, 0.5))
+            M = len(grid) // 2
+            theta0_t = prob.transform_theta(theta0)
+            dinv = prob.dinv_transform(theta0_t) if prob.has_transform else 1.0
+            g_at = {}                                                              # grid value → scores (hcnt × nθ columns × nθ)
+            status = np.zeros((hcnt, nt, 2), dtype=np.int32)
+            for m_ in range(1, M + 1):
+                pts = np.empty((2 * nt, nt))
+                for n in range(nt):
+                    for sgn in (0, 1):
+                        th = theta0.copy()
+                        th[n] = theta0[n] + (0.0 + step[n] * (float(m_) if sgn else -float(m_)))
+                        pts[2 * n + sgn] = prob.transform_theta(th)
+                g_t, st = be.fd_scores(theta0_t, pts, hcnt, atol)
+                g_u = g_t / dinv
+                g_at[-float(m_)] = g_u[:, 0::2, :]
+                g_at[float(m_)] = g_u[:, 1::2, :]
+                status = np.maximum(status, np.where(st.reshape(hcnt, nt, 2) == _capi.STATUS_NONFINITE, _capi.STATUS_NONFINITE, 0))
+            Hs_local = np.empty((hcnt, nt, nt))
+            for n in range(nt):
+                acc = g_at[grid[0]][:, n, :] * coefs[0]
+                for gk, ck in zip(grid[1:], coefs[1:]):
+                    acc = acc + (g_at[gk][:, n, :] * ck if gk != 0.0 else 0.0)
+                Hs_local[:, :, n] = acc / step[n]
+    finally:
+        if z0 is not None:
+            be.fd_start(_capi.START_ZEROS)
     bad_local = np.flatnonzero((status.reshape(hcnt, -1) == _capi.STATUS_NONFINITE).any(axis=1))
     any_bad = bool(bad_local.size)
     if pool.world > 1 and not skip_errors:

@@ -306,8 +306,18 @@ def muse_bang(result: MuseResult, prob: OracleProblem, theta0=None, *, z0=None, 
 
 
 # ----------------------------------------------------------------------------- get_J!
+class SimpleCovariance:
+    """[EXT CovarianceEstimation 0.2] ``SimpleCovariance(corrected=…)``: the sample covariance, normalised by n − 1 (corrected) or n."""
+
+    def __init__(self, corrected=False):
+        self.corrected = bool(corrected)
+
+    def __call__(self, gs):
+        return np.atleast_2d(np.cov(np.asarray(gs, dtype=np.float64), rowvar=False, ddof=1 if self.corrected else 0))
+
+
 def get_J_bang(result: MuseResult, prob: OracleProblem, theta0=None, *, z0=None,
-               gradz_logLike_atol=1e-2, nsims=100):
+               gradz_logLike_atol=1e-2, nsims=100, covariance_method=None):
     theta0 = np.atleast_1d(np.asarray(theta0 if theta0 is not None else result.theta, dtype=np.float64))   # :498
     nsims_existing = len(result.gs)
     nsims_remaining = nsims - nsims_existing
@@ -320,21 +330,41 @@ def get_J_bang(result: MuseResult, prob: OracleProblem, theta0=None, *, z0=None,
     gs = np.array(result.gs)
     if theta0.size == 1:
         result.J = np.array([[np.var(gs[:, 0], ddof=1)]])                 # :529 var
-    else:
-        result.J = np.cov(gs, rowvar=False, ddof=1)                       # :529 cov(SimpleCovariance(corrected=true))
+    else:                                                                 # :529 cov(covariance_method, gs), default SimpleCovariance(corrected=true)
+        result.J = (covariance_method or SimpleCovariance(corrected=True))(gs)
     finalize_result_bang(result, prob)
     return result
 
 
 # ----------------------------------------------------------------------------- get_H!
-def pjacobian(f, theta0, step):
-    """src/util.jl:9-26 with fdm = central_fdm(3,1) and an explicit step per component.
-    [EXT FiniteDifferences 0.12] grid = [-1, 0, 1], coefs = [-1/2, 0, 1/2]; with an explicit
-    step the estimate is ``sum(fs .* coefs) / step`` where fs = f.(0 .+ step .* grid)."""
+def central_fdm(p, q=1):
+    """[EXT FiniteDifferences 0.12] ``central_fdm(p, q)`` without adaptation: the symmetric integer grid of p points (odd p:
+    −(p−1)/2 … (p−1)/2; even p: without 0) and the coefficients c with Σᵢ cᵢ gᵢᵏ = q!·δ_{kq}, k = 0 … p−1 — solved in exact
+    rational arithmetic, as the package does, then rounded to Float64.  central_fdm(3,1) → grid [−1, 0, 1], coefs [−1/2, 0, 1/2];
+    central_fdm(5,1) → [1/12, −2/3, 0, 2/3, −1/12]."""
+    from fractions import Fraction
+    from math import factorial
+    if p < 2 or q != 1 and q >= p:
+        raise ValueError("central_fdm: need p ≥ 2 points and q < p")
+    grid = list(range(-(p // 2), p // 2 + 1)) if p % 2 else [g for g in range(-(p // 2), p // 2 + 1) if g != 0]
+    A = [[Fraction(g) ** k for g in grid] + [Fraction(factorial(q) if k == q else 0)] for k in range(p)]
+    for c in range(p):                                   # Gauss–Jordan over the rationals
+        piv = next(r for r in range(c, p) if A[r][c] != 0)
+        A[c], A[piv] = A[piv], A[c]
+        A[c] = [v / A[c][c] for v in A[c]]
+        for r in range(p):
+            if r != c and A[r][c] != 0:
+                A[r] = [vr - A[r][c] * vc for vr, vc in zip(A[r], A[c])]
+    return tuple(float(g) for g in grid), tuple(float(A[k][p]) for k in range(p))
+
+
+def pjacobian(f, theta0, step, fdm=None):
+    """src/util.jl:9-26 with an explicit step per component; fdm = (grid, coefs), default central_fdm(3,1).
+    [EXT FiniteDifferences 0.12] with an explicit step the estimate is ``sum(fs .* coefs) / step`` where
+    fs = f.(0 .+ step .* grid) — every grid point is evaluated, also the centre one that central methods multiply by 0."""
     x = np.array(theta0, dtype=np.float64, copy=True)
     cols = []
-    grid = (-1.0, 0.0, 1.0)
-    coefs = (-0.5, 0.0, 0.5)
+    grid, coefs = fdm if fdm is not None else ((-1.0, 0.0, 1.0), (-0.5, 0.0, 0.5))
     for n in range(x.size):
         h = float(step[n])
         fs = []
@@ -345,14 +375,14 @@ def pjacobian(f, theta0, step):
             fs.append(np.array(f(x.copy()), dtype=np.float64, copy=True))
             x[n] = xn
         acc = fs[0] * coefs[0]
-        acc = acc + fs[1] * coefs[1]
-        acc = acc + fs[2] * coefs[2]
+        for fk, ck in zip(fs[1:], coefs[1:]):
+            acc = acc + fk * ck
         cols.append(acc / h)
     return np.stack(cols, axis=1)
 
 
 def get_H_bang(result: MuseResult, prob: OracleProblem, theta0=None, *, gradz_logLike_atol=1e-2,
-               nsims=10, step=None, z0=None):
+               nsims=10, step=None, z0=None, fdm=None):
     theta0 = np.atleast_1d(np.asarray(theta0 if theta0 is not None else result.theta, dtype=np.float64))   # :315
     nsims_existing = len(result.Hs)
     nsims_remaining = nsims - nsims_existing
@@ -381,7 +411,7 @@ def get_H_bang(result: MuseResult, prob: OracleProblem, theta0=None, *, gradz_lo
             x, _ = prob.sample_x_z(_k, theta)                             # sim generated at θ
             zhat, _ = prob.z_at_theta(x, _z, theta0, gradz_logLike_atol)  # MAP at fiducial θ₀
             return prob.grad_theta(x, zhat, theta0)                       # score at fiducial θ₀
-        result.Hs.append(pjacobian(f, theta0, step))
+        result.Hs.append(pjacobian(f, theta0, step, fdm))
 
     result.H = np.mean(np.array(result.Hs), axis=0)                       # :446
     result.time += time.perf_counter() - t0

@@ -43,6 +43,9 @@ class FakeBackend:
     def set_z0(self, z0):
         self.z0 = np.array(z0, dtype=np.float64)
 
+    def fd_start(self, start):
+        self.fd_user_start = int(start) == 3        # MUSE_START_USER
+
     def _prob(self):
         return O.OracleProblem(self.fam, self.x if self.x is not None else np.zeros(self.d), self.draws)
 
@@ -82,7 +85,8 @@ class FakeBackend:
             dr = self.draws
         prob = O.OracleProblem(self.fam, self.x, dr)
         res = O.MuseResult(theta=np.array(theta0, dtype=np.float64))
-        O.get_H_bang(res, prob, theta0, nsims=nsims_H, step=np.atleast_1d(step), gradz_logLike_atol=atol)
+        O.get_H_bang(res, prob, theta0, nsims=nsims_H, step=np.atleast_1d(step), gradz_logLike_atol=atol,
+                     z0=self.z0 if getattr(self, "fd_user_start", False) else None)
         Hs = np.array(res.Hs).reshape(nsims_H, self.ntheta, self.ntheta)
         return Hs, np.zeros((nsims_H, self.ntheta, 2), dtype=np.int32)
 
@@ -96,7 +100,7 @@ class FakeBackend:
         theta_sims = np.asarray(theta_sims, dtype=np.float64).reshape(2 * self.ntheta, self.ntheta)
         self.calls.append(("fd_scores", tuple(theta_eval), nsims_H))
         xm, zm = prob.sample_x_z("master", theta_eval)
-        zfid, _ = prob.z_at_theta(xm, np.zeros(self.d), theta_eval, atol)
+        zfid, _ = prob.z_at_theta(xm, self.z0 if getattr(self, "fd_user_start", False) else np.zeros(self.d), theta_eval, atol)
         g = np.empty((nsims_H, 2 * self.ntheta, self.ntheta))
         for k in range(nsims_H):
             for p in range(2 * self.ntheta):

@@ -104,6 +104,46 @@ def test_unsupported_options_raise():
         m.muse(prob, [0.1, 0.2], rng=rng, nsims=10)  # wrong θ length
 
 
+def test_keywords_of_get_J_and_get_H_covariance_method_fdm_and_user_start():
+    """get_J!(covariance_method = SimpleCovariance(corrected = false)) (src/muse.jl:494, 529), get_H!(fdm = central_fdm(5, 1))
+    (src/muse.jl:300, src/util.jl:9-26) and get_H!(z₀ = …) (src/muse.jl:309, 419) against the oracle's restatement."""
+    m, oprob, prob, rng = _pair("hiergauss", 60, 24, False)
+    getJ, getH = getattr(m, "get_J!"), getattr(m, "get_H!")
+    th = np.array([0.2, 0.1])
+    res, ref = m.MuseResult(theta=th.copy()), O.MuseResult(theta=th.copy())
+    getJ(res, prob, rng=rng, nsims=24, covariance_method=m.SimpleCovariance(corrected=False))
+    O.get_J_bang(ref, oprob, nsims=24, covariance_method=O.SimpleCovariance(corrected=False))
+    np.testing.assert_allclose(res.J, ref.J, rtol=1e-12)
+    np.testing.assert_allclose(res.J * 24 / 23, np.cov(np.array(ref.gs), rowvar=False, ddof=1), rtol=1e-12)
+    res2 = m.MuseResult(theta=th.copy())
+    getJ(res2, prob, rng=rng, nsims=24, covariance_method=lambda gs: np.eye(2) * 7.0)       # any callable gs → matrix
+    np.testing.assert_array_equal(res2.J, np.eye(2) * 7.0)
+    with pytest.raises(TypeError):
+        getJ(m.MuseResult(theta=th.copy()), prob, rng=rng, nsims=24, covariance_method="shrinkage")
+    # five-point central differences: grid [-2 … 2], coefficients [1/12, −2/3, 0, 2/3, −1/12]
+    assert m.central_fdm(5, 1) == O.central_fdm(5, 1) == ((-2.0, -1.0, 0.0, 1.0, 2.0), (1 / 12, -2 / 3, 0.0, 2 / 3, -1 / 12))
+    assert m.central_fdm(3, 1) == ((-1.0, 0.0, 1.0), (-0.5, 0.0, 0.5))
+    getH(res, prob, rng=rng, nsims=3, step=np.array([0.02, 0.03]), fdm=m.central_fdm(5, 1))
+    O.get_H_bang(ref, oprob, nsims=3, step=np.array([0.02, 0.03]), fdm=O.central_fdm(5, 1))
+    np.testing.assert_allclose(np.array(res.Hs), np.array(ref.Hs), rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(res.H, ref.H, rtol=1e-9, atol=1e-9)
+    # … and it is a better derivative than the three-point one where the score is curved: both agree to O(step²)
+    res3 = m.MuseResult(theta=th.copy(), gs=res.gs)
+    getH(res3, prob, rng=rng, nsims=3, step=np.array([0.02, 0.03]))
+    np.testing.assert_allclose(res3.H, res.H, rtol=5e-3, atol=5e-3)
+    with pytest.raises(m.MuseBackendError):
+        getH(m.MuseResult(theta=th.copy()), prob, rng=rng, nsims=2, step=np.array([0.02, 0.03]), fdm=((-1.0, 0.5, 1.0), (1.0, 0.0, 1.0)))
+    with pytest.raises(m.MuseBackendError):
+        m.central_fdm(4, 1)
+    # a user start for the fiducial solve
+    z0 = np.linspace(-1.0, 1.0, 60)
+    res4, ref4 = m.MuseResult(theta=th.copy()), O.MuseResult(theta=th.copy())
+    getH(res4, prob, rng=rng, nsims=3, step=np.array([0.02, 0.03]), z0=z0, gradz_logLike_atol=1e-10)
+    O.get_H_bang(ref4, oprob, nsims=3, step=np.array([0.02, 0.03]), z0=z0, gradz_logLike_atol=1e-10)
+    np.testing.assert_allclose(np.array(res4.Hs), np.array(ref4.Hs), rtol=1e-9, atol=1e-9)
+    assert not getattr(prob._backend, "fd_user_start", False)            # the option does not outlive the call
+
+
 # ----------------------------------------------------------------------------- θ-transforms (src/interface.jl:14-28)
 def _pair_t(d, nsims, prior=None, seed=77):
     """hiergauss with θ = (μ, σ), σ > 0: host problem with theta_transform=("identity","log") against the oracle's
