@@ -878,6 +878,8 @@ struct PersistShared {
     LazyLevels lazy;                  // constants of the launch's earlier passes (lazy ẑ)
     double red[kMaxTheta][32];        // CTA 0: scratch of the reduction tree
     StepCache cache;                  // CTA 0: θ, the last history row's θ, the last variance (muse_outer_dev.cuh)
+    OuterParams step;                 // CTA 0: the θ-step's parameters for the pass just executed (shared, not a copy per thread:
+    CovParams cov;                    //        the rank table is indexed per sim)
     int bad;
     int done, error, abort, timeout;  // CTA 0's message after the phase, as every CTA has read it
     int l_abort;                      // CTA 0: this phase handed units back (here or on a peer)
@@ -1004,33 +1006,29 @@ __device__ void leader_step(const PersistParams& P, PersistShared& ps, int i, un
     const OutPtrs& ob = P.slot[ph];
     if (tid == 0) {
         ps.l_abort = 0;
+        ps.step = P.step;
+        ps.step.iter = i;
+        ps.step.g_local = ob.g;
+        ps.step.status_local = ob.status;
+        ps.step.g_all = P.x.nranks > 1 ? P.x.gall[P.x.rank][ph] : ob.g + nt;
+        ps.step.dyn_next = &ctl->dyn[0];
+        ps.cov = P.cov;
+        ps.cov.dyn_fid = &ctl->dyn[0];
+        ps.cov.dyn_fd = &ctl->dyn[1];
         wait_arrivals(P, ph, ps);
         P.stamps[1 + 2 * ph] = gtime_ns();
     }
     __syncthreads();
-    const double* g_all = ob.g + nt;
     if (P.x.nranks > 1 && !ps.timeout) {
         double* dst[kMaxRanks];
         for (int q = 0; q < P.x.nranks; ++q) dst[q] = P.x.gall[q][ph];
         exchange_rows(P, ps, ob.g + nt, ob.status + 1, P.step.counts[P.x.rank] * nt, nt, dst, P.step.need, P.x.epoch0 + i);
-        g_all = P.x.gall[P.x.rank][ph];
         if (tid == 0 && ph < 2) P.stamps[11 + ph] = gtime_ns();          // diagnostics: rows of every peer are here
     }
     if (!ps.l_abort && !ps.timeout) {
-        OuterParams S = P.step;
-        S.iter = i;
-        S.g_local = ob.g;
-        S.status_local = ob.status;
-        S.g_all = g_all;
-        S.dyn_next = &ctl->dyn[0];
-        theta_step_body<V>(S, ps.red, &ps.bad, &ps.cache);
+        theta_step_body<V>(ps.step, ps.red, &ps.bad, &ps.cache);
         __syncthreads();
-        if (P.get_cov && ps.cache.done && !ps.cache.error) {
-            CovParams C = P.cov;
-            C.dyn_fid = &ctl->dyn[0];
-            C.dyn_fd = &ctl->dyn[1];
-            cov_prep_body<V>(C, ps.red, &ps.cache);
-        }
+        if (P.get_cov && ps.cache.done && !ps.cache.error) cov_prep_body<V>(ps.cov, ps.red, &ps.cache);
     }
     __syncthreads();
     if (tid == 0) {

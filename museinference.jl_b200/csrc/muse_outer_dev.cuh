@@ -122,6 +122,7 @@ __device__ inline void block_sums(const int* counts, int nranks, long long need,
     constexpr int T = kStepLanes, PT = T / V;
     const int lane = threadIdx.x & 31, pw = threadIdx.x >> 5;
     auto row_off = [&](int k) -> size_t {                 // global sim k → offset of its row
+        if (nranks == 1) return (size_t)k * nt;           // (uniform branch: one rank, rows are simply consecutive)
         int q = 0, base = 0;
         while (q + 1 < nranks && k >= base + counts[q]) { base += counts[q]; ++q; }
         return (size_t)q * (size_t)need + (size_t)(k - base) * nt;

@@ -686,6 +686,35 @@ def test_profile_splits_solver_time_by_pass_kind():
     be.close()
 
 
+@pytest.mark.parametrize("name,d", [("funnel", 512), ("hiergauss", 5000)])
+def test_get_H_keywords_user_start_and_five_point_fdm(name, d):
+    """get_H!(z₀ = …) — the fiducial solve starts from the user's vector (src/muse.jl:309, 419; muse_b200_fd_start) — and
+    get_H!(fdm = central_fdm(5, 1)) (src/muse.jl:300) on the GPU against the oracle's restatement."""
+    import museinference_jl_b200 as m
+    nsims = 20
+    oprob, fam, draws, xd = oracle_problem(name, d, nsims)
+    rng = m.BaseDraws(draws.xi, draws.nu, draws.xi_master, draws.nu_master)
+    prob = m.SimpleMuseProblem(xd, name)
+    getH = getattr(m, "get_H!")
+    th = theta_start(name)
+    step = np.full(fam.ntheta, 0.02)
+    z0 = np.sin(np.arange(d) * 0.01)
+    for kw_m, kw_o in ((dict(z0=z0), dict(z0=z0)), (dict(fdm=m.central_fdm(5, 1)), dict(fdm=O.central_fdm(5, 1))),
+                       (dict(z0=z0, fdm=m.central_fdm(5, 1), gradz_logLike_atol=1e-9), dict(z0=z0, fdm=O.central_fdm(5, 1), gradz_logLike_atol=1e-9))):
+        res, ref = m.MuseResult(theta=th.copy()), O.MuseResult(theta=th.copy())
+        getH(res, prob, rng=rng, nsims=4, step=step, **kw_m)
+        O.get_H_bang(ref, oprob, nsims=4, step=step, **kw_o)
+        scale = np.abs(np.array(ref.Hs)).max()
+        np.testing.assert_allclose(np.array(res.Hs), np.array(ref.Hs), rtol=RTOL_EST, atol=RTOL_EST * scale)
+        np.testing.assert_allclose(res.H, ref.H, rtol=RTOL_EST, atol=RTOL_EST * scale)
+    # the option does not outlive the call: the next plain get_H! starts from zero(z) again
+    res, ref = m.MuseResult(theta=th.copy()), O.MuseResult(theta=th.copy())
+    getH(res, prob, rng=rng, nsims=4, step=step)
+    O.get_H_bang(ref, oprob, nsims=4, step=step)
+    np.testing.assert_allclose(res.H, ref.H, rtol=RTOL_EST, atol=RTOL_EST * np.abs(ref.H).max())
+    prob.close()
+
+
 # ----------------------------------------------------------------------------- the whole solve in one launch (solve_persist_kernel)
 def _solve_persist(m, xd, name, pr, rng, nsims, persist, lazy=False, lean=False, **kw):
     """One solve with MUSE_PERSIST = persist (and MUSE_LAZY = lazy, MUSE_LEAN = lean); returns (result, profile, per-pass profile)."""
