@@ -231,6 +231,17 @@ int  muse_b200_fd_scores(muse_handle* h, const double* theta_eval, const double*
                          double* g_out /* nsims_H × 2·ntheta × ntheta */,
                          int32_t* status_out /* nsims_H × 2·ntheta, may be NULL */);
 
+/* The implicit-differentiation branch of get_H! (src/muse.jl:335-405, `implicit_diff = true`) for the first nsims_H sims of the
+ * shard: ẑ = MAP at theta0 from zero(z) (start = MUSE_START_ZEROS) or the user's z₀ (MUSE_START_USER) with ∇z_logLike_atol = 1e-1
+ * (hard-coded in the reference, :346); H = H1 + H2 with H1 = ∂θ_sim ∇θ′logLike at fixed ẑ (zero for the registered families) and
+ * H2 = −(∂θ ∇z logLike)ᵀ · A⁻¹ · (∂θ_sim ∇z logLike), A = ∇²z logLike — the nested-AD derivatives of the reference in closed form,
+ * A⁻¹ by conjugate gradients (`implicit_diff_cg_kwargs.maxiter`, Pl = I): exact after one iteration for the isotropic families,
+ * a batched CG on the FP64 tensor-core DGEMM for corrgauss.  cg_iters_out: CG iterations per sim and Jacobian column
+ * (nsims_H × ntheta; the reference's `implicit_diff_cg_hists`).  Not provided on handles with a separate H shard. */
+int  muse_b200_implicit_h(muse_handle* h, const double* theta0, int32_t nsims_H, int32_t start, int32_t cg_maxiter,
+                          double* Hs_out /* nsims_H × ntheta × ntheta */, int32_t* cg_iters_out /* may be NULL */,
+                          int32_t* status_out /* nsims_H, may be NULL */);
+
 /* The outer loop of muse! (src/muse.jl:159-236) for the common configuration — constant α, regularize = identity,
  * H⁻¹_update = :sims, prior flat or independent Normal(mean, sigma) per component — run inside the library so that
  * no interpreter sits between two passes: per iteration one map_score pass (data + local sims, start zeros / user z₀

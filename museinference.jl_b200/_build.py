@@ -8,7 +8,7 @@ import subprocess
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libmuse_b200.so")
-SOURCES = ["muse_api.cu", "muse_iso_solver.cu", "muse_iso_stream.cu", "muse_draws.cu", "muse_comm.cu", "muse_driver.cu", "muse_outer.cu", "muse_dgemm.cu", "muse_corr.cu"]
+SOURCES = ["muse_api.cu", "muse_iso_solver.cu", "muse_iso_stream.cu", "muse_draws.cu", "muse_comm.cu", "muse_driver.cu", "muse_outer.cu", "muse_dgemm.cu", "muse_corr.cu", "muse_implicit.cu"]
 HEADERS = ["muse_common.cuh", "muse_handle.cuh", "muse_outer_dev.cuh", "muse_group.cuh", "muse_iso_ctl.cuh", "muse_draw_tables.cuh", "muse_normal_math.cuh", os.path.join("..", "..", "include", "muse_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

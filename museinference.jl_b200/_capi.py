@@ -103,6 +103,7 @@ SIGNATURES = {
                                        C.c_int32, c_double_p, c_double_p, C.c_int32, C.c_int32, c_int32_p,
                                        C.POINTER(muse_iterate_out), C.POINTER(muse_cov_out)]),
     "muse_b200_fd_jacobian": (C.c_int, [C.c_void_p, c_double_p, c_double_p, C.c_int32, C.c_double, c_double_p, c_int32_p]),
+    "muse_b200_implicit_h": (C.c_int, [C.c_void_p, c_double_p, C.c_int32, C.c_int32, C.c_int32, c_double_p, c_int32_p, c_int32_p]),
     "muse_b200_fd_start": (C.c_int, [C.c_void_p, C.c_int32]),
     "muse_b200_fd_scores": (C.c_int, [C.c_void_p, c_double_p, c_double_p, C.c_int32, C.c_double, c_double_p, c_int32_p]),
     "muse_b200_get_maps": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, c_double_p]),

@@ -302,6 +302,15 @@ class B200Backend:
                                                     _ip(status)))
         return Hs, status
 
+    def implicit_h(self, theta0, nsims_H: int, start: int = 0, cg_maxiter: int = 100):
+        """Per-sim H of get_H!'s implicit-diff branch (include/muse_b200.h: muse_b200_implicit_h); returns (Hs, CG iterations, status)."""
+        t0 = self._theta(theta0)
+        Hs = np.zeros((nsims_H, self.ntheta, self.ntheta))
+        iters = np.zeros((nsims_H, self.ntheta), dtype=np.int32)
+        status = np.zeros(nsims_H, dtype=np.int32)
+        self._check(self._lib.muse_b200_implicit_h(self._h, _dp(t0), int(nsims_H), int(start), int(cg_maxiter), _dp(Hs), _ip(iters), _ip(status)))
+        return Hs, iters, status
+
     def fd_start(self, start: int):
         """Start of get_H!'s fiducial solve: START_ZEROS (default) or START_USER (the vector given to set_z0)."""
         self._check(self._lib.muse_b200_fd_start(self._h, int(start)))

@@ -394,6 +394,93 @@ __global__ void __launch_bounds__(kCT) corr_score_kernel(const CorrLaunch L) {
     }
 }
 
+// ---- batched conjugate gradients for the implicit-diff branch of get_H! (muse_implicit.cu) --------------------------------------
+// Per sim k solve (I + a·P) v = W_k from v = 0, all sims in lock-step: one DGEMM Q = U·P per iteration serves every sim, a CTA per
+// sim does the vector updates and the scalars — IterativeSolvers' cg as the reference calls it (src/muse.jl:376-380: maxiter, Pl = I),
+// stopped at ‖r‖ ≤ √eps·‖b‖.  (The reference hands cg the Hessian of logLike, −(I + aP), and b = ½σW: the iterates differ by the
+// factor −½σ, the iteration count is the same.)
+struct CgState {
+    double rho, tol;
+    int iters, active;
+};
+struct CgLaunch {
+    int d, ld, nrows, maxiter;
+    double a;
+    const double* W;          // right-hand sides, row k
+    double *v, *r, *u, *q;    // solution, residual, direction, Q = U·P
+    CgState* st;
+    int* active_count;
+};
+__global__ void __launch_bounds__(kCT) corr_cg_init_kernel(const CgLaunch L) {
+    __shared__ double red[kCT / 32];
+    const int k = blockIdx.x;
+    const size_t off = (size_t)k * L.ld;
+    double rr = 0.0;
+    for (int j = threadIdx.x; j < L.ld; j += kCT) {
+        const double b = j < L.d ? L.W[off + j] : 0.0;
+        L.v[off + j] = 0.0;
+        L.r[off + j] = b;
+        L.u[off + j] = b;                      // first direction: u = r + β·0
+        rr = fma(b, b, rr);
+    }
+    rr = block_sum(rr, red);
+    if (threadIdx.x == 0) {
+        CgState s;
+        s.rho = rr;
+        s.tol = 1.4901161193847656e-08 * sqrt(rr);       // √eps(Float64)·‖b‖
+        s.iters = 0;
+        s.active = sqrt(rr) <= s.tol ? 0 : 1;            // b = 0: cg returns at once
+        L.st[k] = s;
+        if (s.active) atomicAdd(L.active_count, 1);
+    }
+}
+__global__ void __launch_bounds__(kCT) corr_cg_iter_kernel(const CgLaunch L) {
+    __shared__ double red[kCT / 32];
+    const int k = blockIdx.x;
+    CgState s = L.st[k];
+    if (!s.active) return;                     // uniform over the CTA
+    const size_t off = (size_t)k * L.ld;
+    double uc = 0.0;
+    for (int j = threadIdx.x; j < L.d; j += kCT) {
+        const double u = L.u[off + j];
+        const double c = fma(L.a, L.q[off + j], u);      // c = (I + aP)u
+        L.q[off + j] = c;
+        uc = fma(u, c, uc);
+    }
+    uc = block_sum(uc, red);
+    const double alpha = s.rho / uc;
+    double rr = 0.0;
+    for (int j = threadIdx.x; j < L.d; j += kCT) {
+        L.v[off + j] = fma(alpha, L.u[off + j], L.v[off + j]);
+        const double r = fma(-alpha, L.q[off + j], L.r[off + j]);
+        L.r[off + j] = r;
+        rr = fma(r, r, rr);
+    }
+    rr = block_sum(rr, red);
+    const int iters = s.iters + 1;
+    const bool stop = sqrt(rr) <= s.tol || iters >= L.maxiter;
+    if (!stop) {
+        const double beta = rr / s.rho;
+        for (int j = threadIdx.x; j < L.d; j += kCT) L.u[off + j] = fma(beta, L.u[off + j], L.r[off + j]);
+    }
+    if (threadIdx.x == 0) {
+        s.rho = rr;
+        s.iters = iters;
+        s.active = stop ? 0 : 1;
+        L.st[k] = s;
+        if (!stop) atomicAdd(L.active_count, 1);
+    }
+}
+// out[k] = (Pẑ)_k · v_k
+__global__ void __launch_bounds__(kCT) corr_cg_dot_kernel(const double* __restrict__ pz, const double* __restrict__ v, int d, int ld, double* __restrict__ out) {
+    __shared__ double red[kCT / 32];
+    const int k = blockIdx.x;
+    double acc = 0.0;
+    for (int j = threadIdx.x; j < d; j += kCT) acc = fma(pz[(size_t)k * ld + j], v[(size_t)k * ld + j], acc);
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) out[k] = acc;
+}
+
 }  // namespace
 }  // namespace muse
 
@@ -727,3 +814,59 @@ int muse_corr_get_maps(muse_handle* h, int first_unit, int count, double* z_out)
 }
 
 bool muse_corr_have_draws(muse_handle* h, bool hshard) { return hshard ? h->corr->have_W_h : h->corr->have_W; }
+
+// implicit-diff branch of get_H! for the dense correlated Gaussian (muse_implicit.cu has the formulas):
+//   H_k = ½ a σ (Pẑ_k)·(I + aP)⁻¹ W_k,   ẑ_k the MAP of sim k at θ₀ (atol 1e-1), W_k = L ξ_k
+int muse_corr_implicit_h(muse_handle* h, const double* theta0, int nsims_H, int start, int cg_maxiter, double* Hs_out, int32_t* cg_iters_out,
+                         int32_t* status_out) {
+    muse_corr_ctx* c = h->corr;
+    // (1) MAPs of the H sims; the pass ends with Q = Ẑ·P for the score, which is exactly the Pẑ needed below
+    h->pass_kind = MUSE_PASS_COLD;
+    int rc = muse_corr_map_score(h, theta0, theta0, 1e-1, 0, start, 0, nsims_H);
+    if (rc != MUSE_OK) return rc;
+    if (status_out) CORR_TRY(h, cudaMemcpyAsync(status_out, h->status_d, (size_t)nsims_H * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    // (2) batched CG on the FD batch's arrays
+    rc = alloc_batch(h, c->fd, nsims_H);
+    if (rc != MUSE_OK) return rc;
+    CgState* st = nullptr;
+    double* dots = nullptr;
+    CORR_TRY(h, cudaMalloc(&st, (size_t)nsims_H * sizeof(CgState)));
+    if (cudaMalloc(&dots, (size_t)nsims_H * sizeof(double)) != cudaSuccess) { cudaFree(st); cudaGetLastError(); h->err = "implicit_h: allocation failed"; return MUSE_ENOMEM; }
+    auto done = [&](int code) { cudaFree(st); cudaFree(dots); return code; };
+    CgLaunch L{};
+    L.d = h->cfg.d; L.ld = c->ld; L.nrows = nsims_H; L.maxiter = cg_maxiter;
+    L.a = std::exp(-theta0[0]);
+    L.W = c->W;
+    L.v = c->fd.z; L.r = c->fd.g; L.u = c->fd.s; L.q = c->fd.q;
+    L.st = st;
+    L.active_count = c->active;
+    if (cudaMemsetAsync(c->active, 0, sizeof(int), h->stream) != cudaSuccess) return done(MUSE_ECUDA);
+    corr_cg_init_kernel<<<nsims_H, kCT, 0, h->stream>>>(L);
+    h->acc.launches += 1;
+    for (int it = 0; it <= cg_maxiter; ++it) {
+        int active = 0;
+        if (cudaMemcpyAsync(&active, c->active, sizeof(int), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
+            cudaStreamSynchronize(h->stream) != cudaSuccess) { h->err = "implicit_h: CG poll failed"; return done(MUSE_ECUDA); }
+        if (active <= 0) break;
+        if (cudaMemsetAsync(c->active, 0, sizeof(int), h->stream) != cudaSuccess) return done(MUSE_ECUDA);
+        rc = gemm_rows(h, c->fd, c->fd.s, 0, nsims_H, false);
+        if (rc != MUSE_OK) return done(rc);
+        corr_cg_iter_kernel<<<nsims_H, kCT, 0, h->stream>>>(L);
+        h->acc.launches += 1;
+    }
+    corr_cg_dot_kernel<<<nsims_H, kCT, 0, h->stream>>>(c->main.q + (size_t)c->ld, c->fd.z, h->cfg.d, c->ld, dots);
+    h->acc.launches += 1;
+    std::vector<double> dh((size_t)nsims_H);
+    std::vector<CgState> sh((size_t)nsims_H);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dh.data(), dots, dh.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(sh.data(), st, sh.size() * sizeof(CgState), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) { h->err = std::string("implicit_h: ") + cudaGetErrorString(e); return done(MUSE_ECUDA); }
+    const double sig = std::exp(0.5 * theta0[0]);
+    for (int k = 0; k < nsims_H; ++k) {
+        Hs_out[k] = 0.5 * L.a * sig * dh[k];
+        if (cg_iters_out) cg_iters_out[k] = sh[k].iters;
+    }
+    return done(MUSE_OK);
+}

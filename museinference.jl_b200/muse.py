@@ -472,9 +472,12 @@ def get_H_(result: MuseResult, prob: AbstractMuseProblem, theta0=None, **kwargs)
     skip_errors = kw.pop("skip_errors", False)
     z0 = kw.pop("z0", None)
     nsims_total = kw.pop("_nsims_total", 0)
-    if kw.pop("implicit_diff", False):
-        raise MuseBackendError(-5, "implicit_diff=true (experimental in the reference, src/muse.jl:287, 335-405) "
-                                   "is not provided by the B200 backend")
+    implicit_diff = bool(kw.pop("implicit_diff", False))                           # :310, 335-405
+    kw.pop("implicit_diff_H1_is_zero", False)          # H1 ≡ 0 for every registered family (their score does not depend on x)
+    cg_kwargs = dict(kw.pop("implicit_diff_cg_kwargs", None) or {})
+    cg_maxiter = int(cg_kwargs.pop("maxiter", 100))
+    if cg_kwargs.pop("Pl", None) is not None or cg_kwargs:
+        raise MuseBackendError(-5, "implicit_diff_cg_kwargs: only `maxiter` is provided (the reference's default preconditioner is the identity)")
     fdm = kw.pop("fdm", None)                                                      # :300; None = central_fdm(3,1)
     if fdm is not None:
         try:
@@ -497,6 +500,29 @@ def get_H_(result: MuseResult, prob: AbstractMuseProblem, theta0=None, **kwargs)
     if nsims_remaining <= 0:
         return result
     t0 = time.perf_counter()
+    if implicit_diff:
+        # H = H1 + H2 per sim, H2 = −(∂θ∇z logLike)ᵀ A⁻¹ (∂θ_sim ∇z logLike) by conjugate gradients (:340-388); the nested-AD
+        # derivatives of the reference are closed forms for the registered families (csrc/muse_implicit.cu)
+        if pool.world > 1 or prob.has_transform:
+            raise MuseBackendError(-5, "get_H!(implicit_diff=true) is provided on one GPU and for the identity θ-transform")
+        be = prob.backend_for(max(nsims_total, nsims_remaining), rng, pool, 0)
+        if not hasattr(be, "implicit_h"):
+            raise MuseBackendError(-5, "get_H!(implicit_diff=true): not provided by this backend")
+        if z0 is not None:
+            be.set_z0(z0)
+        Hs_new, iters, status = be.implicit_h(theta0, nsims_remaining, _capi.START_USER if z0 is not None else _capi.START_ZEROS, cg_maxiter)
+        bad = np.flatnonzero(status == _capi.STATUS_NONFINITE)
+        if bad.size and not skip_errors:
+            raise FloatingPointError("get_H!: MAP solution failed with a non-finite objective")
+        keep = np.setdiff1d(np.arange(nsims_remaining), bad)
+        nt = prob.ntheta
+        oldH = np.asarray(result.Hs, dtype=np.float64).reshape(-1, nt, nt)
+        result.Hs = np.concatenate([oldH, Hs_new[keep]], axis=0)
+        result.metadata.setdefault("implicit_diff_cg_hists", []).extend(iters[keep].tolist())   # :404 (iteration counts)
+        result.H = np.mean(result.Hs, axis=0)                                      # :446
+        result.time += time.perf_counter() - t0
+        finalize_result_(result, prob)
+        return result
     if step is None and len(result.gs) > 0:                                        # :411-413
         step = 0.1 / np.std(np.asarray(result.gs, dtype=np.float64).reshape(-1, prob.ntheta), axis=0, ddof=1)
     if step is None:

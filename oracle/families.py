@@ -63,6 +63,21 @@ class Funnel:
         th = float(np.asarray(theta).reshape(-1)[0])
         return x / (1.0 + np.exp(-th))
 
+    # second derivatives of logLike the implicit-diff branch of get_H! obtains by nested AD (src/muse.jl:349-375), analytic here:
+    # ∂θ ∇z logLike (d × nθ), ∂x/∂θ_sim of the sample (d × nθ; ∇z logLike depends on θ_sim only through x, with ∂∇z/∂x = I),
+    # the Hessian ∇²z logLike applied to a vector, and ∂θ_sim of the score at fixed ẑ (these families: the score does not see x → 0)
+    def dgradz_dtheta(self, x, z, theta):
+        th = float(np.asarray(theta).reshape(-1)[0])
+        return (np.exp(-th) * z)[:, None]
+
+    def dx_dtheta_sim(self, theta, xi, nu):
+        th = float(np.asarray(theta).reshape(-1)[0])
+        return (0.5 * np.exp(0.5 * th) * xi)[:, None]
+
+    def hess_z_apply(self, z, theta, w):
+        th = float(np.asarray(theta).reshape(-1)[0])
+        return -(1.0 + np.exp(-th)) * w
+
 
 class HierGauss:
     """F2: z ~ N(μ, e^{2ℓ} I_d), x ~ N(z, I_d); θ = (μ, ℓ = log σ)."""
@@ -102,6 +117,19 @@ class HierGauss:
         mu, ell = (float(t) for t in np.asarray(theta).reshape(-1))
         a = np.exp(-2.0 * ell)
         return (x + mu * a) / (1.0 + a)
+
+    def dgradz_dtheta(self, x, z, theta):          # ∇z logLike = (x − z) − a(z − μ):  ∂μ → a,  ∂ℓ → 2a(z − μ)
+        mu, ell = (float(t) for t in np.asarray(theta).reshape(-1))
+        a = np.exp(-2.0 * ell)
+        return np.stack([np.full(self.d, a), 2.0 * a * (z - mu)], axis=1)
+
+    def dx_dtheta_sim(self, theta, xi, nu):        # x = μ + e^ℓ ξ + ν
+        mu, ell = (float(t) for t in np.asarray(theta).reshape(-1))
+        return np.stack([np.ones(self.d), np.exp(ell) * xi], axis=1)
+
+    def hess_z_apply(self, z, theta, w):
+        mu, ell = (float(t) for t in np.asarray(theta).reshape(-1))
+        return -(1.0 + np.exp(-2.0 * ell)) * w
 
 
 class CorrGauss:
@@ -143,6 +171,18 @@ class CorrGauss:
         th = float(np.asarray(theta).reshape(-1)[0])
         A = np.eye(self.d) + np.exp(-th) * self.P
         return np.linalg.solve(A, x)
+
+    def dgradz_dtheta(self, x, z, theta):          # ∇z logLike = (x − z) − a P z:  ∂θ → a P z
+        th = float(np.asarray(theta).reshape(-1)[0])
+        return (np.exp(-th) * (self.P @ z))[:, None]
+
+    def dx_dtheta_sim(self, theta, xi, nu):        # x = e^{θ/2} L ξ + ν
+        th = float(np.asarray(theta).reshape(-1)[0])
+        return (0.5 * np.exp(0.5 * th) * (self.L @ xi))[:, None]
+
+    def hess_z_apply(self, z, theta, w):
+        th = float(np.asarray(theta).reshape(-1)[0])
+        return -(w + np.exp(-th) * (self.P @ w))
 
 
 class TransformedFamily:

@@ -381,8 +381,58 @@ def pjacobian(f, theta0, step, fdm=None):
     return np.stack(cols, axis=1)
 
 
+def cg(A, b, *, maxiter=100, reltol=None, abstol=0.0):
+    """[EXT IterativeSolvers 0.9] ``cg(A, b; maxiter, Pl = I, log = true)`` from a zero start: plain conjugate gradients,
+    stopped when ‖r‖ ≤ max(reltol·‖b‖, abstol), reltol = √eps.  Returns (x, iterations).  (A may be negative definite — the
+    reference hands it the Hessian of logLike: the signs cancel in α = ρ / uᵀAu.)"""
+    b = np.asarray(b, dtype=np.float64)
+    reltol = np.sqrt(np.finfo(np.float64).eps) if reltol is None else reltol
+    x = np.zeros_like(b)
+    r = b.copy()
+    u = np.zeros_like(b)
+    rho_prev = 1.0
+    residual = np.linalg.norm(r)
+    tol = max(reltol * residual, abstol)
+    it = 0
+    while not residual <= tol and it < maxiter:
+        rho = float(r @ r)
+        beta = rho / rho_prev
+        u = r + beta * u
+        c = A(u)
+        alpha = rho / float(u @ c)
+        x = x + alpha * u
+        r = r - alpha * c
+        residual = np.linalg.norm(r)
+        rho_prev = rho
+        it += 1
+    return x, it
+
+
+def implicit_diff_H(prob: OracleProblem, k, theta0, z0=None, cg_maxiter=100):
+    """One sim of the implicit-diff branch of get_H! (src/muse.jl:340-388): H = H1 + H2 with
+    H1 = ∂θ_sim[∇θ′ logLike(x(θ_sim), ẑ, θ′)] (0 for the registered families: their score does not see x) and
+    H2 = −(∂θ ∇z logLike)ᵀ · A⁻¹ · (∂θ_sim ∇z logLike), A = ∇²z logLike, solved column by column with conjugate gradients.
+    ẑ is the MAP at θ₀ with ∇z_logLike_atol = 1e-1 (hard-coded in the reference, :346).  The nested-AD derivatives of the
+    reference are the families' analytic ones (oracle/families.py; checked against finite differences in tests/test_oracle.py)."""
+    fam = prob.family
+    theta0 = np.atleast_1d(np.asarray(theta0, dtype=np.float64))
+    xi, nu = (prob.draws.xi_master, prob.draws.nu_master) if k == "master" else (prob.draws.xi[k], prob.draws.nu[k])
+    x, z = prob.sample_x_z(k, theta0)
+    zstart = np.array(z0, dtype=np.float64) if z0 is not None else prob.z_guess_from_truth(x, z, theta0)
+    zhat, _ = prob.z_at_theta(x, zstart, theta0, 1e-1)
+    dF = fam.dgradz_dtheta(x, zhat, theta0)                       # d × nθ
+    dF1 = fam.dx_dtheta_sim(theta0, xi, nu)                       # d × nθ
+    cols, iters = [], []
+    for n in range(theta0.size):
+        u, it = cg(lambda w: fam.hess_z_apply(zhat, theta0, w), dF1[:, n], maxiter=cg_maxiter)
+        cols.append(u)
+        iters.append(it)
+    H2 = -(dF.T @ np.stack(cols, axis=1))
+    return H2, iters
+
+
 def get_H_bang(result: MuseResult, prob: OracleProblem, theta0=None, *, gradz_logLike_atol=1e-2,
-               nsims=10, step=None, z0=None, fdm=None):
+               nsims=10, step=None, z0=None, fdm=None, implicit_diff=False, implicit_diff_cg_kwargs=None):
     theta0 = np.atleast_1d(np.asarray(theta0 if theta0 is not None else result.theta, dtype=np.float64))   # :315
     nsims_existing = len(result.Hs)
     nsims_remaining = nsims - nsims_existing
@@ -390,6 +440,17 @@ def get_H_bang(result: MuseResult, prob: OracleProblem, theta0=None, *, gradz_lo
         return result
     t0 = time.perf_counter()
     ks = list(range(nsims_remaining))                                     # :323 split_rng(rng, nsims_remaining)
+
+    if implicit_diff:                                                     # :335-405
+        hists = result.metadata.setdefault("implicit_diff_cg_hists", [])
+        for k in ks:
+            H, iters = implicit_diff_H(prob, k, theta0, z0, **({"cg_maxiter": implicit_diff_cg_kwargs["maxiter"]} if implicit_diff_cg_kwargs and "maxiter" in implicit_diff_cg_kwargs else {}))
+            result.Hs.append(H)
+            hists.append(iters)
+        result.H = np.mean(np.array(result.Hs), axis=0)                   # :446
+        result.time += time.perf_counter() - t0
+        finalize_result_bang(result, prob)
+        return result
 
     if step is None and len(result.gs) > 0:                               # :411-413
         step = 0.1 / np.std(np.array(result.gs), axis=0, ddof=1)

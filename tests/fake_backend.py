@@ -90,6 +90,14 @@ class FakeBackend:
         Hs = np.array(res.Hs).reshape(nsims_H, self.ntheta, self.ntheta)
         return Hs, np.zeros((nsims_H, self.ntheta, 2), dtype=np.int32)
 
+    def implicit_h(self, theta0, nsims_H, start=0, cg_maxiter=100):
+        prob = O.OracleProblem(self.fam, self.x, self.draws)
+        Hs, its = [], []
+        for k in range(nsims_H):
+            H, it = O.implicit_diff_H(prob, k, theta0, self.z0 if start == 3 else None, cg_maxiter)
+            Hs.append(H); its.append(it)
+        return np.array(Hs).reshape(nsims_H, self.ntheta, self.ntheta), np.array(its, dtype=np.int32), np.zeros(nsims_H, dtype=np.int32)
+
     def fd_scores(self, theta_eval, theta_sims, nsims_H, atol):
         if self.nsims_h:
             dr = O.Draws(self.draws_h[0], self.draws_h[1], self.draws.xi_master, self.draws.nu_master)

@@ -97,7 +97,7 @@ def test_unsupported_options_raise():
     res = m.MuseResult(theta=np.array([0.1]))
     getH = getattr(m, "get_H!")
     with pytest.raises(m.MuseBackendError):
-        getH(res, prob, rng=rng, nsims=2, implicit_diff=True)
+        getH(res, prob, rng=rng, nsims=2, implicit_diff=True, implicit_diff_cg_kwargs=dict(Pl="jacobi"))
     with pytest.raises(m.MuseBackendError):
         getH(res, prob, rng=rng, nsims=2)            # no step and no scores yet
     with pytest.raises(ValueError):
@@ -142,6 +142,44 @@ def test_keywords_of_get_J_and_get_H_covariance_method_fdm_and_user_start():
     O.get_H_bang(ref4, oprob, nsims=3, step=np.array([0.02, 0.03]), z0=z0, gradz_logLike_atol=1e-10)
     np.testing.assert_allclose(np.array(res4.Hs), np.array(ref4.Hs), rtol=1e-9, atol=1e-9)
     assert not getattr(prob._backend, "fd_user_start", False)            # the option does not outlive the call
+
+
+def test_implicit_diff_get_H_host_path_and_oracle_against_finite_differences():
+    """get_H!(implicit_diff = true) (src/muse.jl:335-405): the host driver's branch against the oracle's, and the oracle's
+    closed-form second derivatives against central differences — the implicit-diff H must be the finite-difference H."""
+    for name, d in (("funnel", 48), ("hiergauss", 60)):
+        m, oprob, prob, rng = _pair(name, d, 12, False)
+        fam = oprob.family
+        th = theta_start(name)
+        res, ref = m.MuseResult(theta=th.copy()), O.MuseResult(theta=th.copy())
+        getattr(m, "get_H!")(res, prob, rng=rng, nsims=5, implicit_diff=True, implicit_diff_cg_kwargs=dict(maxiter=50))
+        O.get_H_bang(ref, oprob, nsims=5, implicit_diff=True)
+        np.testing.assert_allclose(np.array(res.Hs), np.array(ref.Hs), rtol=1e-12)
+        assert res.metadata["implicit_diff_cg_hists"] == ref.metadata["implicit_diff_cg_hists"] == [[1] * fam.ntheta] * 5
+        fd = O.MuseResult(theta=th.copy())
+        O.get_H_bang(fd, oprob, nsims=5, step=np.full(fam.ntheta, 1e-3), gradz_logLike_atol=1e-10)
+        np.testing.assert_allclose(ref.H, fd.H, rtol=1e-5, atol=1e-5 * np.abs(fd.H).max())
+        # the closed forms the oracle uses in place of the reference's nested AD
+        x, _ = oprob.sample_x_z(0, th)
+        z = fam.exact_map(x, th) + 0.01
+        gz = lambda zz, tt, xx: -fam.neg_loglike_and_grad(xx, zz, tt)[1]
+        for n in range(fam.ntheta):
+            e = np.zeros_like(th); e[n] = 1e-6
+            np.testing.assert_allclose((gz(z, th + e, x) - gz(z, th - e, x)) / 2e-6, fam.dgradz_dtheta(x, z, th)[:, n], rtol=1e-6, atol=1e-7)
+            xp, _ = fam.sample(th + e, oprob.draws.xi[0], oprob.draws.nu[0])
+            xm, _ = fam.sample(th - e, oprob.draws.xi[0], oprob.draws.nu[0])
+            np.testing.assert_allclose((xp - xm) / 2e-6, fam.dx_dtheta_sim(th, oprob.draws.xi[0], oprob.draws.nu[0])[:, n], rtol=1e-6, atol=1e-7)
+        w = np.cos(np.arange(d))
+        np.testing.assert_allclose((gz(z + 1e-5 * w, th, x) - gz(z - 1e-5 * w, th, x)) / 2e-5, fam.hess_z_apply(z, th, w), rtol=1e-6, atol=1e-7)
+    # conjugate gradients as restated: A⁻¹b on a random SPD system, iteration count bounded by the dimension
+    rs = np.random.default_rng(3)
+    B = rs.standard_normal((20, 20)); A = B @ B.T + 20 * np.eye(20); b = rs.standard_normal(20)
+    xs, it = O.cg(lambda v: A @ v, b)
+    np.testing.assert_allclose(xs, np.linalg.solve(A, b), rtol=1e-5, atol=1e-8)        # stopped at ‖r‖ ≤ √eps·‖b‖
+    assert 1 <= it <= 20
+    xs2, it2 = O.cg(lambda v: -(A @ v), b)                     # the reference hands cg a negative definite operator
+    np.testing.assert_allclose(xs2, -xs, rtol=1e-12)
+    assert it2 == it
 
 
 # ----------------------------------------------------------------------------- θ-transforms (src/interface.jl:14-28)
