@@ -155,8 +155,8 @@ cudaError_t iso_solver_geometry(int d, int want_group, int want_cluster, int dev
 cudaError_t iso_stream_geometry(int d, int ld, int device, Geometry* geo);
 cudaError_t iso_warp_stream_geometry(int device, Geometry* geo);
 cudaError_t launch_iso_stream(SolveLaunch& L, const Geometry& geo, cudaStream_t st);
-cudaError_t launch_dgemm(const double* A, const double* B, double* C, int M, int N, int K, int lda, int ldb, int ldc,
-                         cudaStream_t st);
+cudaError_t launch_dgemm(const double* A, const double* Bt, double* C, int M, int N, int K, int lda, int ldbt, int ldc,
+                         cudaStream_t st);      // C = A·Btᵀ, Bt[N×K] (muse_dgemm.cu)
 cudaError_t launch_philox_draws(double* xi, double* nu, int rows, int d, int ld, uint64_t seed,
                                 int64_t sim_offset, int master_row, cudaStream_t st);
 

@@ -489,7 +489,8 @@ struct muse_corr_ctx {
     int ld = 0;                       // row stride = d rounded up to the GEMM tile (128)
     int draw_rows = 0, draw_pad = 0;  // nsims + 1 (last = master draw), padded to 128
     int h_rows = 0, h_pad = 0;        // separate H shard (multi-GPU)
-    double *P = nullptr, *Lt = nullptr;          // ld × ld, zero padded; Lt = Lᵀ so that W = ξ·Lᵀ = (L ξᵀ)ᵀ
+    double *P = nullptr, *Lt = nullptr;          // ld × ld, zero padded.  The GEMM computes A·Btᵀ (both operands K-contiguous, muse_dgemm.cu):
+                                                 // Q = S·P takes Bt = P (symmetric), W = ξ·Lᵀ takes Bt = L — which is what `Lt` holds
     double *W = nullptr, *nu = nullptr, *tmp = nullptr;
     double *W_h = nullptr, *nu_h = nullptr;
     double *xdat = nullptr, *z0user = nullptr;
@@ -641,10 +642,7 @@ int muse_corr_create(muse_handle* h) {
     CORR_TRY(h, cudaMemsetAsync(c->P, 0, mat, h->stream));
     CORR_TRY(h, cudaMemsetAsync(c->Lt, 0, mat, h->stream));
     CORR_TRY(h, cudaMemcpy2DAsync(c->P, ld * B, cfg.P, (size_t)d * B, (size_t)d * B, d, cudaMemcpyHostToDevice, h->stream));
-    std::vector<double> lt((size_t)d * d);
-    for (int i = 0; i < d; ++i)
-        for (int j = 0; j < d; ++j) lt[(size_t)j * d + i] = cfg.L[(size_t)i * d + j];
-    CORR_TRY(h, cudaMemcpy2DAsync(c->Lt, ld * B, lt.data(), (size_t)d * B, (size_t)d * B, d, cudaMemcpyHostToDevice, h->stream));
+    CORR_TRY(h, cudaMemcpy2DAsync(c->Lt, ld * B, cfg.L, (size_t)d * B, (size_t)d * B, d, cudaMemcpyHostToDevice, h->stream));
     const size_t dr = (size_t)c->draw_pad * ld * B;
     CORR_TRY(h, cudaMalloc(&c->W, dr));
     CORR_TRY(h, cudaMalloc(&c->nu, dr));
