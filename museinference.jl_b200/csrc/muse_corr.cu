@@ -373,19 +373,21 @@ __global__ void __launch_bounds__(kCT) corr_iter_kernel(const CorrLaunch L, cons
     for (int j = threadIdx.x; j < L.d; j += kCT) s[j] = -vec[j];
 }
 
-// ---- after Q = Ẑ·P: score and outputs --------------------------------------------------------------------------
+// ---- score and outputs --------------------------------------------------------------------------
 __global__ void __launch_bounds__(kCT) corr_score_kernel(const CorrLaunch L) {
     __shared__ double red[kCT / 32];
     const int r = L.row0 + blockIdx.x;
     const size_t off = (size_t)r * L.ld;
-    const double *z = L.b.z + off, *q = L.b.q + off;
+    // a·Pẑ needs no product of its own: the gradient the solver carries is ∇f(ẑ) = (ẑ − x) + a·Pẑ (updated exactly along every
+    // accepted step, the objective being quadratic), so a·Pẑ = g − ẑ + x — one DGEMM per pass less than "Q = Ẑ·P, then ẑ·Q"
+    const double *z = L.b.z + off, *g = L.b.g + off, *x = L.b.x + off;
     double zq = 0;
-    for (int j = threadIdx.x; j < L.d; j += kCT) zq = fma(z[j], q[j], zq);
+    for (int j = threadIdx.x; j < L.d; j += kCT) zq = fma(z[j], g[j] - z[j] + x[j], zq);
     zq = block_sum(zq, red);
     if (threadIdx.x == 0) {
         const CorrState& st = L.b.st[r];
         const int item = blockIdx.x;
-        L.g_out[item] = 0.5 * L.a * zq - L.dhalf;              // ∇θ logLike = ½ e^{−θ} zᵀPz − d/2
+        L.g_out[item] = 0.5 * zq - L.dhalf;                    // ∇θ logLike = ½ e^{−θ} zᵀPz − d/2,  e^{−θ}·Pz = g − z + x
         L.gnorm_out[item] = st.gmax;
         L.f_out[item] = st.f;
         L.iters_out[item] = st.iter;
@@ -471,12 +473,14 @@ __global__ void __launch_bounds__(kCT) corr_cg_iter_kernel(const CgLaunch L) {
         if (!stop) atomicAdd(L.active_count, 1);
     }
 }
-// out[k] = (Pẑ)_k · v_k
-__global__ void __launch_bounds__(kCT) corr_cg_dot_kernel(const double* __restrict__ pz, const double* __restrict__ v, int d, int ld, double* __restrict__ out) {
+// out[k] = (a·Pẑ)_k · v_k with a·Pẑ = g − ẑ + x of the MAP pass (see corr_score_kernel); rows 1 + k of the main batch
+__global__ void __launch_bounds__(kCT) corr_cg_dot_kernel(const double* __restrict__ g, const double* __restrict__ z, const double* __restrict__ x,
+                                                          const double* __restrict__ v, int d, int ld, double* __restrict__ out) {
     __shared__ double red[kCT / 32];
     const int k = blockIdx.x;
+    const size_t om = (size_t)(1 + k) * ld, ov = (size_t)k * ld;
     double acc = 0.0;
-    for (int j = threadIdx.x; j < d; j += kCT) acc = fma(pz[(size_t)k * ld + j], v[(size_t)k * ld + j], acc);
+    for (int j = threadIdx.x; j < d; j += kCT) acc = fma(g[om + j] - z[om + j] + x[om + j], v[ov + j], acc);
     acc = block_sum(acc, red);
     if (threadIdx.x == 0) out[k] = acc;
 }
@@ -605,8 +609,6 @@ int corr_solve(muse_handle* h, CorrBatch& b, CorrLaunch& L) {
         CORR_TRY(h, cudaGetLastError());
         h->acc.launches += 1;
     }
-    const int rc = gemm_rows(h, b, b.z, L.row0, L.nrows, L.data_row == L.row0);
-    if (rc != MUSE_OK) return rc;
     corr_score_kernel<<<L.nrows, kCT, 0, h->stream>>>(L);
     CORR_TRY(h, cudaGetLastError());
     h->acc.launches += 1;
@@ -818,7 +820,7 @@ bool muse_corr_have_draws(muse_handle* h, bool hshard) { return hshard ? h->corr
 int muse_corr_implicit_h(muse_handle* h, const double* theta0, int nsims_H, int start, int cg_maxiter, double* Hs_out, int32_t* cg_iters_out,
                          int32_t* status_out) {
     muse_corr_ctx* c = h->corr;
-    // (1) MAPs of the H sims; the pass ends with Q = Ẑ·P for the score, which is exactly the Pẑ needed below
+    // (1) MAPs of the H sims; the pass leaves ẑ, x and g = ∇f(ẑ), hence a·Pẑ = g − ẑ + x
     h->pass_kind = MUSE_PASS_COLD;
     int rc = muse_corr_map_score(h, theta0, theta0, 1e-1, 0, start, 0, nsims_H);
     if (rc != MUSE_OK) return rc;
@@ -852,7 +854,7 @@ int muse_corr_implicit_h(muse_handle* h, const double* theta0, int nsims_H, int 
         corr_cg_iter_kernel<<<nsims_H, kCT, 0, h->stream>>>(L);
         h->acc.launches += 1;
     }
-    corr_cg_dot_kernel<<<nsims_H, kCT, 0, h->stream>>>(c->main.q + (size_t)c->ld, c->fd.z, h->cfg.d, c->ld, dots);
+    corr_cg_dot_kernel<<<nsims_H, kCT, 0, h->stream>>>(c->main.g, c->main.z, c->main.x, c->fd.z, h->cfg.d, c->ld, dots);
     h->acc.launches += 1;
     std::vector<double> dh((size_t)nsims_H);
     std::vector<CgState> sh((size_t)nsims_H);
@@ -863,7 +865,7 @@ int muse_corr_implicit_h(muse_handle* h, const double* theta0, int nsims_H, int 
     if (e != cudaSuccess) { h->err = std::string("implicit_h: ") + cudaGetErrorString(e); return done(MUSE_ECUDA); }
     const double sig = std::exp(0.5 * theta0[0]);
     for (int k = 0; k < nsims_H; ++k) {
-        Hs_out[k] = 0.5 * L.a * sig * dh[k];
+        Hs_out[k] = 0.5 * sig * dh[k];                          // ½ σ (a·Pẑ)·(I + aP)⁻¹W
         if (cg_iters_out) cg_iters_out[k] = sh[k].iters;
     }
     return done(MUSE_OK);
