@@ -200,22 +200,64 @@ __device__ __forceinline__ double lazy_level(double p, double q, double z, uint3
     return fma(cspec, -g0, z);
 }
 static_assert(sizeof(LazyLevel) == 40 && offsetof(LazyLevel, cspec) == 32, "LazyLevel layout (lazy_level reads it field by field)");
+
+// ---- the funnel (F1) specialised: μ = μ_s = 0 -------------------------------------------------------------------------------
+// The same VALUES as elem3<…, LEAN> / lazy_level bit for bit — z − 0 = z, fma(a, 0, −x) = −x, fma(c, x, 0) = c·x, Σ∇f(0)² = Σx² are
+// exact identities, the sums are accumulated in the same order, Σ(z − μ) is not needed by the funnel's score — in 12 (cold) /
+// 16 (+3 or 5 per lazy level) FP64 instructions per element instead of 20 / 20 (+6): the passes are bound by the FP64 pipe (DESIGN.md
+// §3.6).  __dmul_rn / __dadd_rn keep the compiler from contracting what elem3 rounds separately.
+template <bool SIM, bool ZERO>   // ZERO: z₀ ≡ 0
+__device__ __forceinline__ double elem3_funnel(double p, double q, double z0, const IsoEval& ev, double sig, Acc& A) {
+    const double x = SIM ? __dadd_rn(__dmul_rn(sig, p), q) : p;
+    double g0;
+    if (ZERO) {
+        g0 = -x;                                            // ∇f(0) = −x
+        A.v[rR0] = fma(x, x, A.v[rR0]);
+        A.v[rGG0] = A.v[rR0];                               // Σ∇f(0)² is the same sequence of operations as Σ(x − 0)²
+    } else {
+        const double r0 = x - z0;
+        g0 = fma(ev.a, z0, -r0);
+        A.v[rR0] = fma(r0, r0, A.v[rR0]);
+        A.v[rS2_0] = fma(z0, z0, A.v[rS2_0]);
+        A.v[rGG0] = fma(g0, g0, A.v[rGG0]);
+    }
+    A.v[rGM0] = fmax(A.v[rGM0], fabs(g0));
+    const double zt = ZERO ? __dmul_rn(ev.cspec, x) : fma(ev.cspec, -g0, z0);
+    const double rt = x - zt;
+    const double gt = fma(ev.a, zt, -rt);
+    A.v[rRT] = fma(rt, rt, A.v[rRT]);
+    A.v[rS2T] = fma(zt, zt, A.v[rS2T]);
+    A.v[rDPT] = fma(gt, -g0, A.v[rDPT]);
+    A.v[rGGT] = fma(gt, gt, A.v[rGGT]);
+    A.v[rGMT] = fmax(A.v[rGMT], fabs(gt));
+    return zt;
+}
+template <bool SIM, bool ZERO>
+__device__ __forceinline__ double lazy_level_funnel(double p, double q, double z, uint32_t lev) {
+    const double sig = lds_f64(lev), a = lds_f64(lev + 16), cspec = lds_f64(lev + 32);
+    const double x = SIM ? __dadd_rn(__dmul_rn(sig, p), q) : p;
+    if (ZERO) return __dmul_rn(cspec, x);
+    const double r0 = x - z;
+    const double g0 = fma(a, z, -r0);
+    return fma(cspec, -g0, z);
+}
 // what a consumer needs of the launch's lazy description
 struct LazyView {
     uint32_t lev0;           // shared address of level 0
     int nlev;
 };
-template <bool SIM>
+template <bool SIM, bool FUNNEL, bool FROM_ZERO>
 __device__ __forceinline__ double lazy_z0(double p, double q, double zstart, const LazyView& LV, unsigned mask) {
     // no branches: a level the unit did not step at (a 0-iteration solve — rare) is evaluated and dropped by a select, so that the
     // elements of a thread stay independent instruction streams
     double z = zstart;
     if (LV.nlev >= 1) {                      // the hot case: the second pass of a solve
-        const double zn = lazy_level<SIM>(p, q, z, LV.lev0);
+        const double zn = FUNNEL ? lazy_level_funnel<SIM, FROM_ZERO>(p, q, z, LV.lev0) : lazy_level<SIM>(p, q, z, LV.lev0);
         z = (mask & 1u) ? zn : z;
     }
     for (int l = 1; l < LV.nlev; ++l) {
-        const double zn = lazy_level<SIM>(p, q, z, LV.lev0 + (uint32_t)l * (uint32_t)sizeof(LazyLevel));
+        const uint32_t lev = LV.lev0 + (uint32_t)l * (uint32_t)sizeof(LazyLevel);
+        const double zn = FUNNEL ? lazy_level_funnel<SIM, false>(p, q, z, lev) : lazy_level<SIM>(p, q, z, lev);
         z = ((mask >> l) & 1u) ? zn : z;
     }
     return z;
@@ -227,10 +269,18 @@ struct ItemRegs {
     unsigned mask;
 };
 // ZK: 0 z₀ ≡ 0 · 1 z₀ streamed · 2 z₀ = simulated latent · 3 lazy from zero · 4 lazy from a streamed start row
-template <bool SIM, int ZK, bool LEAN>
+// LEAN: 0 every trial element by element · 1 lean α = 1 trial · 2 lean + the funnel's specialised element code
+template <bool SIM, int ZK, int LEAN>
 __device__ __forceinline__ double elem_zk(double p, double q, double z0in, const IsoEval& ev, const ItemRegs& R, const LazyView& LV, Acc& A) {
-    if (ZK >= 3) return elem3<SIM, 1, LEAN>(p, q, lazy_z0<SIM>(p, q, ZK == 4 ? z0in : 0.0, LV, R.mask), ev, R.sig, R.mus, A);
-    return elem3<SIM, (ZK >= 3 ? 1 : ZK), LEAN>(p, q, z0in, ev, R.sig, R.mus, A);
+    if constexpr (LEAN == 2 && ZK != 2) {
+        if (ZK == 0) return elem3_funnel<SIM, true>(p, q, 0.0, ev, R.sig, A);
+        if (ZK == 1) return elem3_funnel<SIM, false>(p, q, z0in, ev, R.sig, A);
+        if (ZK == 3) return elem3_funnel<SIM, false>(p, q, lazy_z0<SIM, true, true>(p, q, 0.0, LV, R.mask), ev, R.sig, A);
+        return elem3_funnel<SIM, false>(p, q, lazy_z0<SIM, true, false>(p, q, z0in, LV, R.mask), ev, R.sig, A);
+    } else {
+        if (ZK >= 3) return elem3<SIM, 1, (LEAN != 0)>(p, q, lazy_z0<SIM, false, false>(p, q, ZK == 4 ? z0in : 0.0, LV, R.mask), ev, R.sig, R.mus, A);
+        return elem3<SIM, (ZK >= 3 ? 1 : ZK), (LEAN != 0)>(p, q, z0in, ev, R.sig, R.mus, A);
+    }
 }
 __device__ __forceinline__ LazyView lazy_view(const SolveLaunch& L) {
     LazyView LV;
@@ -244,7 +294,7 @@ __device__ __forceinline__ void st2_stream(double* p, double2 v, uint64_t pol) {
 }
 
 // one chunk of one item, executed by the consumer threads
-template <bool SIM, int ZK, bool LEAN>
+template <bool SIM, int ZK, int LEAN>
 __device__ __forceinline__ void consume_chunk(const double* buf, int base, int len, int d, const ItemRegs& R,
                                               const IsoEval& ev, int ct, uint64_t pol, const LazyView& LV, Acc& A) {
     constexpr bool ZROW = (ZK == 1 || ZK == 4);
@@ -420,7 +470,7 @@ struct RingPos {
     int stage;
     uint32_t phase;
 };
-template <bool SIM, int ZK, bool LEAN>
+template <bool SIM, int ZK, int LEAN>
 __device__ __forceinline__ void consume_item(const SolveLaunch& L, Shared& sh, const double* ring, int rows, int stages, int chunk0, int nch,
                                              const ItemRegs& R, const IsoEval& ev, int ct, int lane, uint64_t pol, const LazyView& LV,
                                              RingPos& rp, Acc& A) {
@@ -434,7 +484,7 @@ __device__ __forceinline__ void consume_item(const SolveLaunch& L, Shared& sh, c
         if (++rp.stage == stages) { rp.stage = 0; rp.phase ^= 1u; }
     }
 }
-template <bool LEAN>
+template <int LEAN>
 __device__ __forceinline__ void consume_item_l(const SolveLaunch& L, Shared& sh, const double* ring, int rows, int stages, const ItemDesc& it,
                                                const ItemRegs& R, const IsoEval& ev, int ct, int lane, uint64_t pol, const LazyView& LV,
                                                RingPos& rp, Acc& A) {
@@ -455,7 +505,7 @@ __device__ __forceinline__ void consume_item_l(const SolveLaunch& L, Shared& sh,
 }
 // lean evaluation and lazy ẑ exist in solve_persist_kernel only (LEAN is a parameter of that kernel): the single-pass kernels of the
 // chain of launches keep their variants
-template <bool PERSIST, bool LEAN>
+template <bool PERSIST, int LEAN>
 __device__ __forceinline__ void consume_item_any(const SolveLaunch& L, Shared& sh, const double* ring, int rows, int stages, const ItemDesc& it,
                                                  const ItemRegs& R, const IsoEval& ev, int ct, int lane, uint64_t pol, const LazyView& LV,
                                                  RingPos& rp, Acc& A) {
@@ -480,7 +530,7 @@ __device__ __forceinline__ void consume_item_any(const SolveLaunch& L, Shared& s
 __device__ __forceinline__ void lazy_item(const SolveLaunch& L, const Cmd& c, int* zs, const double* zshared, ItemDesc& it, const double*& rz) {
     const LazyLevels& LZ = *L.lazy;
     it.levmask = LZ.nlev ? (unsigned)ld_state(zs) : 0u;
-    it.zk = L.zrows ? 4 : 3;
+    it.zk = L.zrows ? 4 : (LZ.nlev ? 3 : 0);             // the launch's first pass from zero(z) is simply a cold item
     rz = L.zrows ? zshared : nullptr;
     it.zout = LZ.store ? c.zA : nullptr;
     it.zst_accept = kZA;
@@ -501,7 +551,7 @@ __device__ __forceinline__ void lazy_after_publish(const SolveLaunch& L, const I
 // of every phase of solve_persist_kernel (PERSIST: the barriers of the previous phase are invalidated and set up again, the
 // proxies are fenced around the phase — ẑ written with ordinary stores by one phase is read by bulk copies in the next —
 // and the CTA ends the phase together).
-template <bool PERSIST, bool LEAN = false>
+template <bool PERSIST, int LEAN = false>
 __device__ __forceinline__ void stream_pass(const SolveLaunch& L, Shared& sh, double* const ring, bool reinit) {
     const int rows = L.zrows ? 3 : 2;
     const int stages = L.stream_stages;
@@ -715,7 +765,7 @@ iso_stream_kernel(const __grid_constant__ SolveLaunch L) {
 constexpr int kWarpCta = 256;
 
 // one unit's sweep by one warp
-template <bool SIM, int ZK, bool LEAN>
+template <bool SIM, int ZK, int LEAN>
 __device__ __forceinline__ void warp_unit(const ItemDesc& it, const double* ra, const double* rb, const double* rz, int d,
                                           const IsoEval& ev, int lane, uint64_t pol, const LazyView& LV, Acc& A) {
     const ItemRegs R{it.sig, it.mus, it.zout, it.levmask};
@@ -749,7 +799,7 @@ __device__ __forceinline__ void warp_unit(const ItemDesc& it, const double* ra, 
     }
 }
 
-template <bool LEAN>
+template <int LEAN>
 __device__ __forceinline__ void warp_dispatch(const ItemDesc& it, const double* ra, const double* rb, const double* rz, int d,
                                               const IsoEval& ev, int lane, uint64_t pol, const LazyView& LV, Acc& A) {
     if (it.sim) {
@@ -768,7 +818,7 @@ __device__ __forceinline__ void warp_dispatch(const ItemDesc& it, const double* 
 
 // the launch's units dealt round-robin to the grid's warps (body of iso_warp_stream_kernel and of every phase of
 // solve_persist_kernel's small-d form)
-template <bool PERSIST, bool LEAN = false>
+template <bool PERSIST, int LEAN = false>
 __device__ __forceinline__ void warp_pass(const SolveLaunch& L) {
     const int lane = threadIdx.x & 31;
     const int gw = (blockIdx.x * kWarpCta + threadIdx.x) >> 5, nw = (gridDim.x * kWarpCta) >> 5;
@@ -951,7 +1001,7 @@ __device__ void phase_launch(const PersistParams& P, int ph, PersistShared& ps) 
     L.stream_stages = L.zrows ? 4 : 6;
 }
 
-template <int STREAM, bool LEAN>
+template <int STREAM, int LEAN>
 __device__ __forceinline__ void run_phase(const SolveLaunch& L, bool reinit) {
     if constexpr (STREAM == 1) {
         extern __shared__ __align__(128) unsigned char dynsm[];
@@ -1065,7 +1115,7 @@ __device__ bool wait_step(const PersistParams& P, PersistShared& ps, unsigned se
 }
 static_assert(2 * sizeof(DynConsts) / 8 + 3 <= kWarpCta, "wait_step: one word per thread");
 
-template <int STREAM, bool LEAN>
+template <int STREAM, int LEAN>
 __global__ void __launch_bounds__(STREAM == 1 ? kThreads : kWarpCta, STREAM == 1 ? 1 : 2)
 solve_persist_kernel(const __grid_constant__ PersistParams P) {
     constexpr int V = STREAM == 1 ? 2 : 4;            // lanes of the θ-step's reduction tree per thread (512 / 256 threads carry them)
@@ -1221,19 +1271,22 @@ cudaError_t iso_persist_geometry(const Geometry& geo, int device, int* grid, int
     if (e != cudaSuccess) return e;
     if (!coop || (geo.stream != 1 && geo.stream != 2)) { *grid = 0; *threads = 0; return cudaSuccess; }
     if (geo.stream == 1) {
-        e = cudaFuncSetAttribute(solve_persist_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, geo.smem_bytes);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_persist_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, geo.smem_bytes);
+        e = cudaFuncSetAttribute(solve_persist_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, geo.smem_bytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_persist_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, geo.smem_bytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_persist_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, geo.smem_bytes);
         if (e != cudaSuccess) return e;
-        int a = 0, b = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, solve_persist_kernel<1, true>, kThreads, geo.smem_bytes);
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, solve_persist_kernel<1, false>, kThreads, geo.smem_bytes);
-        per_sm = a < b ? a : b;
+        int a = 0, b = 0, c = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, solve_persist_kernel<1, 0>, kThreads, geo.smem_bytes);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, solve_persist_kernel<1, 1>, kThreads, geo.smem_bytes);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, solve_persist_kernel<1, 2>, kThreads, geo.smem_bytes);
+        per_sm = a < b ? (a < c ? a : c) : (b < c ? b : c);
         *threads = kThreads;
     } else {
-        int a = 0, b = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, solve_persist_kernel<2, true>, kWarpCta, 0);
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, solve_persist_kernel<2, false>, kWarpCta, 0);
-        per_sm = a < b ? a : b;
+        int a = 0, b = 0, c = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, solve_persist_kernel<2, 0>, kWarpCta, 0);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, solve_persist_kernel<2, 1>, kWarpCta, 0);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, solve_persist_kernel<2, 2>, kWarpCta, 0);
+        per_sm = a < b ? (a < c ? a : c) : (b < c ? b : c);
         *threads = kWarpCta;
     }
     if (e != cudaSuccess) return e;
@@ -1243,8 +1296,10 @@ cudaError_t iso_persist_geometry(const Geometry& geo, int device, int* grid, int
 
 cudaError_t launch_iso_persist(const PersistParams& P, const Geometry& geo, int grid, cudaStream_t st) {
     void* args[] = {const_cast<PersistParams*>(&P)};
-    const void* fn = geo.stream == 1 ? (P.lean ? reinterpret_cast<const void*>(&solve_persist_kernel<1, true>) : reinterpret_cast<const void*>(&solve_persist_kernel<1, false>))
-                                     : (P.lean ? reinterpret_cast<const void*>(&solve_persist_kernel<2, true>) : reinterpret_cast<const void*>(&solve_persist_kernel<2, false>));
+    const void* const fns[2][3] = {
+        {reinterpret_cast<const void*>(&solve_persist_kernel<1, 0>), reinterpret_cast<const void*>(&solve_persist_kernel<1, 1>), reinterpret_cast<const void*>(&solve_persist_kernel<1, 2>)},
+        {reinterpret_cast<const void*>(&solve_persist_kernel<2, 0>), reinterpret_cast<const void*>(&solve_persist_kernel<2, 1>), reinterpret_cast<const void*>(&solve_persist_kernel<2, 2>)}};
+    const void* fn = fns[geo.stream == 1 ? 0 : 1][P.lean < 0 || P.lean > 2 ? 0 : P.lean];
     if (geo.stream == 1) return cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kThreads), args, (size_t)geo.smem_bytes, st);
     return cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kWarpCta), args, 0, st);
 }

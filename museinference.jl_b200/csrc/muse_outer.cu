@@ -330,6 +330,7 @@ extern "C" int muse_b200_muse_solve(muse_handle* h, const double* theta0, int32_
     // 24·d / 32·d bytes per sim) gains ≈ 4 % and lean evaluation alone ≈ 5 %; together 1.48 → 1.30 ms per solve, C4 4.56 → 3.94 ms.
     const bool lazy_on = [] { const char* e = std::getenv("MUSE_LAZY"); return !e || std::atoi(e) != 0; }();
     const bool lean_on = [] { const char* e = std::getenv("MUSE_LEAN"); return !e || std::atoi(e) != 0; }();
+    const bool funnel_on = [] { const char* e = std::getenv("MUSE_FUNNEL_SPEC"); return !e || std::atoi(e) != 0; }();
     if (h->persist_grid < 0) {
         int g = 0, t = 0;
         if (iso_persist_geometry(h->geo, h->cfg.device, &g, &t) != cudaSuccess) { cudaGetLastError(); g = 0; }
@@ -375,7 +376,7 @@ extern "C" int muse_b200_muse_solve(muse_handle* h, const double* theta0, int32_
         Q.max_pass = std::min((int)maxsteps, kOuterSlots);
         Q.get_cov = get_covariance ? 1 : 0;
         Q.lazy = lazy_on ? 1 : 0;
-        Q.lean = lean_on ? 1 : 0;
+        Q.lean = lean_on ? (h->cfg.family == MUSE_FAMILY_FUNNEL && funnel_on ? 2 : 1) : 0;     // 2: + the funnel's specialised element code
         if (h->geo.stream == 1) {           // room in the segment-sum array for the fiducial unit cut into single chunks?
             const long long nchunks = (h->ld + 2047) / 2048;
             Q.fid_seg_chunks = (long long)h->out_cap * h->geo.nseg >= nchunks ? 1 : 0;

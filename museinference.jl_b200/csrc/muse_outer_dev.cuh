@@ -89,7 +89,7 @@ struct PersistParams {
     int max_pass;             // passes this launch may run (≤ kOuterSlots)
     int get_cov, nh_mine;
     int fid_seg_chunks;       // > 0: chunks per segment of the fiducial solve's one unit (finer than the passes': more CTAs share it)
-    int lean;                 // 1: SolveLaunch::lean in every phase
+    int lean;                 // SolveLaunch::lean in every phase: 0 off, 1 lean α = 1 trial, 2 lean + the funnel's specialised element code
     int lazy;                 // 1: ẑ is recomputed from the base normals instead of stored and re-read (muse_common.cuh: LazyLevels)
     const double *z0user, *xi_fd, *nu_fd;
     double *zfidA, *zfidB;
