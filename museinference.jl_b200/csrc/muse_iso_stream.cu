@@ -1022,16 +1022,16 @@ __device__ void wait_arrivals(const PersistParams& P, int ph, PersistShared& ps)
 }
 
 // The exchange step by CTA 0 (all its threads): `n` doubles of this rank (rows src, one status per `per_row` doubles; failed units
-// go out as NaN so that every rank takes the same error decision) → slot `rank` of dst[q] on EVERY rank q, then flag `ep`
+// go out as NaN so that every rank takes the same error decision) → offset my_off of dst[q] on EVERY rank q, then flag `ep`
 // there; then wait for the flags of all peers.  An abort bit rides on the flag.
 __device__ void exchange_rows(const PersistParams& P, PersistShared& ps, const double* src, const int* status, int n, int per_row,
-                              double* const* dst, long long need, unsigned long long ep) {
+                              double* const* dst, long long my_off, unsigned long long ep) {
     const XchgParams& X = P.x;
     const int tid = threadIdx.x;
     for (int e = tid; e < n; e += blockDim.x) {
         const bool bad = __ldcg(status + e / per_row) == MUSE_STATUS_NONFINITE;
         const double v = bad ? __longlong_as_double(0x7ff8000000000000LL) : __ldcg(src + e);
-        for (int q = 0; q < X.nranks; ++q) dst[q][(size_t)X.rank * need + e] = v;
+        for (int q = 0; q < X.nranks; ++q) dst[q][(size_t)my_off + e] = v;
     }
     // the rows of all threads happen-before the barrier, the barrier before the flag threads' release stores: one system-scope
     // release per peer orders everything (a __threadfence_system() in each of the CTA's 18 warps cost more than the exchange)
@@ -1061,6 +1061,7 @@ __device__ void leader_step(const PersistParams& P, PersistShared& ps, int i, un
         ps.step.g_local = ob.g;
         ps.step.status_local = ob.status;
         ps.step.g_all = P.x.nranks > 1 ? P.x.gall[P.x.rank][ph] : ob.g + nt;
+        ps.step.dense = 1;
         ps.step.dyn_next = &ctl->dyn[0];
         ps.cov = P.cov;
         ps.cov.dyn_fid = &ctl->dyn[0];
@@ -1072,7 +1073,8 @@ __device__ void leader_step(const PersistParams& P, PersistShared& ps, int i, un
     if (P.x.nranks > 1 && !ps.timeout) {
         double* dst[kMaxRanks];
         for (int q = 0; q < P.x.nranks; ++q) dst[q] = P.x.gall[q][ph];
-        exchange_rows(P, ps, ob.g + nt, ob.status + 1, P.step.counts[P.x.rank] * nt, nt, dst, P.step.need, P.x.epoch0 + i);
+        // score rows land in GLOBAL sim order (rank r's rows behind those of ranks < r): the θ-step reads them like one GPU's
+        exchange_rows(P, ps, ob.g + nt, ob.status + 1, P.step.counts[P.x.rank] * nt, nt, dst, (long long)P.x.row0 * nt, P.x.epoch0 + i);
         if (tid == 0 && ph < 2) P.stamps[11 + ph] = gtime_ns();          // diagnostics: rows of every peer are here
     }
     if (!ps.l_abort && !ps.timeout) {
@@ -1192,7 +1194,7 @@ solve_persist_kernel(const __grid_constant__ PersistParams P) {
                 double* dst[kMaxRanks];
                 for (int q = 0; q < P.x.nranks; ++q) dst[q] = P.x.fdall[q];
                 const int nt = P.step.nt;
-                exchange_rows(P, ps, P.fd.g, P.fd.status, P.nh_mine * nt * 2 * nt, nt, dst, P.x.need_fd, P.x.epoch0 + kOuterSlots + 1);
+                exchange_rows(P, ps, P.fd.g, P.fd.status, P.nh_mine * nt * 2 * nt, nt, dst, (long long)P.x.rank * P.x.need_fd, P.x.epoch0 + kOuterSlots + 1);
             }
             if (tid == 0) {
                 volatile OuterState* st = P.step.st;

@@ -282,6 +282,7 @@ extern "C" int muse_b200_muse_solve(muse_handle* h, const double* theta0, int32_
     // copy the history rows of iterations [first, upto] out of the host mirrors (state, per-pass output blocks, gathered scores)
     const double* gall_h = h->outer_gall_h;          // host mirror of the gathered score slots (multi-GPU) and its slot stride
     size_t gall_h_stride = gall_doubles;
+    bool gall_dense = false;                         // rows in global sim order (peer exchange) instead of one padded slot per rank
     auto copy_history = [&](int first, int upto, double chunk_s) {
         for (int i = first; i <= upto; ++i) {
             const int row = i - 1, slot = row % kOuterSlots;
@@ -297,7 +298,9 @@ extern "C" int muse_b200_muse_solve(muse_handle* h, const double* theta0, int32_
                 out->h_inv_post_hist[(size_t)row * nt + c] = R.h_inv_post[c];
             }
             double* gs = out->g_sims_hist + (size_t)row * nsims_total * nt;
-            if (multi) {
+            if (multi && gall_dense) {
+                std::memcpy(gs, gall_h + (size_t)slot * gall_h_stride, (size_t)nsims_total * nt * sizeof(double));
+            } else if (multi) {
                 const double* src = gall_h + (size_t)slot * gall_h_stride;
                 size_t off = 0;
                 for (int q = 0; q < P.nranks; ++q) {
@@ -401,6 +404,8 @@ extern "C" int muse_b200_muse_solve(muse_handle* h, const double* theta0, int32_
             x_blk = (size_t)h->p2p_block;
             Q.x.nranks = P.nranks;
             Q.x.rank = h->comm_rank;
+            Q.x.row0 = 0;
+            for (int q = 0; q < h->comm_rank; ++q) Q.x.row0 += counts[q];
             Q.x.epoch0 = seq * 8ULL;
             int maxh = 1;
             for (int q = 0; q < P.nranks; ++q) {
@@ -428,10 +433,18 @@ extern "C" int muse_b200_muse_solve(muse_handle* h, const double* theta0, int32_
             ea = h->persist_ev[0]; eb = h->persist_ev[1];
             OUTER_TRY(h, cudaEventRecord(ea, h->stream));
         }
-        OUTER_TRY(h, launch_iso_persist(Q, h->geo, h->persist_grid, h->stream));
+        const cudaError_t le = launch_iso_persist(Q, h->geo, h->persist_grid, h->stream);
+        const auto t_launched = std::chrono::steady_clock::now();
+        if (le != cudaSuccess) {
+            // the cooperative launch was refused (not every CTA can be resident: SMs shared with another context, MPS limits …):
+            // nothing has run — this handle uses the chain of launches from now on.  A single rank must not decide that alone.
+            cudaGetLastError();
+            if (multi) { h->err = std::string("muse_solve: cooperative launch failed on a rank of a multi-GPU solve: ") + cudaGetErrorString(le); return MUSE_ECUDA; }
+            h->persist_grid = 0;
+            goto chain_of_launches;
+        }
         if (h->prof) OUTER_TRY(h, cudaEventRecord(eb, h->stream));
         h->acc.launches += 1;
-        const auto t_launched = std::chrono::steady_clock::now();
         // results: [state | slot 0 | slot 1 | FD block] in one copy (the typical solve); slot 2 only if a third pass ran
         OUTER_TRY(h, cudaMemcpyAsync(h->outer_arena_h, h->outer_arena_d, h->outer_arena_head, cudaMemcpyDeviceToHost, h->stream));
         if (multi)
@@ -503,9 +516,9 @@ extern "C" int muse_b200_muse_solve(muse_handle* h, const double* theta0, int32_
             // lazy ẑ: the state cells hold level masks unless the last pass materialised ẑ — no resident ẑ is left behind
             if (lazy_on && !(n_now == Q.max_pass && Q.max_pass < maxsteps))
                 OUTER_TRY(h, cudaMemsetAsync(h->zstate, 0, (size_t)h->rows * sizeof(int), h->stream));
-            if (multi) { gall_h = h->p2p_host; gall_h_stride = x_blk; }
+            if (multi) { gall_h = h->p2p_host; gall_h_stride = x_blk; gall_dense = true; }
             copy_history(1, n_now, chunk_s);
-            if (multi) { gall_h = h->outer_gall_h; gall_h_stride = gall_doubles; }
+            if (multi) { gall_h = h->outer_gall_h; gall_h_stride = gall_doubles; gall_dense = false; }
             out->n_iter = n_now;
             for (int c = 0; c < nt; ++c) out->theta_final[c] = sh_->theta[c];
             if (sh_->error == 2) { h->err = "DomainError: sqrt of a negative number in the θ convergence test (src/muse.jl:165)"; return MUSE_ESTATE; }
@@ -535,6 +548,7 @@ extern "C" int muse_b200_muse_solve(muse_handle* h, const double* theta0, int32_
         }
     }
 
+chain_of_launches:
     while (!finished) {
         const auto t0 = std::chrono::steady_clock::now();
         const int first = it_done + 1;

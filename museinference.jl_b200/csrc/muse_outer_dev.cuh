@@ -22,6 +22,8 @@ struct OuterParams {
     int nranks, n_total;
     int counts[kMaxRanks];    // sims per rank
     long long need;           // doubles per rank slot of g_all
+    int dense;                // 1: g_all holds the N sims' rows consecutively in global order (the peer exchange of the one-launch
+                              //    solve writes them there); 0: rank q's rows start at q·need (NCCL all-gather slots)
     double alpha, theta_rtol;
     int have_prior;
     double prior_mean[kMaxTheta], prior_sigma[kMaxTheta];
@@ -70,6 +72,7 @@ struct OutPtrs {              // device pointers of one OutBlock
 // and stores its rows straight into every peer's region, then raises its flag there
 struct XchgParams {
     int nranks, rank;
+    int row0;                         // global index of this rank's first sim: its score rows go to offset row0·nθ of every gathered slot
     unsigned long long epoch0;        // flags of this solve: epoch0 + phase + 1
     unsigned long long* flags[kMaxRanks];   // peer q's flag array (entry [2·rank] is mine to write there); [rank] = my own region
     double* gall[kMaxRanks][kOuterSlots];   // peer q's gathered-score slot s (this solve's parity)
@@ -133,10 +136,10 @@ __device__ inline void block_sums(const int* counts, int nranks, long long need,
         for (int j = 0; j < V; ++j)
 #pragma unroll
             for (int c = 0; c < NT; ++c) acc[j][c] = 0.0;
-        // every lane walks its sims in increasing order (k = t, t + T, t + 2T, …).  The loads of four steps of ALL the thread's V
+        // every lane walks its sims in increasing order (k = t, t + T, t + 2T, …).  The loads of eight steps of ALL the thread's V
         // lanes are issued before the first addition: a lone CTA is bound by the latency of dependent round trips to the L2, not by
         // bandwidth (with the lanes one after the other a θ-step over 10⁴ sims took 29 µs)
-        constexpr int S = 4;
+        constexpr int S = 8;
         for (int k0 = 0; k0 < n_total; k0 += S * T) {
             double v[S][V][NT];
             bool ok[S][V];
@@ -184,19 +187,21 @@ __device__ inline void block_sums(const int* counts, int nranks, long long need,
 // mean and corrected variance of every component (two passes, like Statistics.mean / var)
 template <int V, int NT>
 __device__ inline void block_mean_var_nt(const double* g, const int* counts, int nranks, long long need, int nt, int n_total,
-                                         double (*sh)[32], double* mean, double* var) {
+                                         double (*sh)[32], double* mean, double* var, bool* saw_nan = nullptr) {
     auto ld = [&](size_t o, int c) { return __ldcg(g + o + c); };
-    block_sums<V, NT>(counts, nranks, need, nt, n_total, ld, [&](double v, int) { return v; }, sh, mean);
+    bool nanv = false;       // multi-GPU: a failed sim arrives as a NaN row — noticed while the mean is summed, no scan of its own
+    block_sums<V, NT>(counts, nranks, need, nt, n_total, ld, [&](double v, int) { nanv = nanv || isnan(v); return v; }, sh, mean);
+    if (saw_nan) *saw_nan = nanv;
     for (int c = 0; c < nt; ++c) mean[c] /= n_total;
     block_sums<V, NT>(counts, nranks, need, nt, n_total, ld, [&](double v, int c) { const double dlt = v - mean[c]; return dlt * dlt; }, sh, var);
     for (int c = 0; c < nt; ++c) var[c] /= (n_total - 1);
 }
 template <int V>
 __device__ inline void block_mean_var(const double* g, const int* counts, int nranks, long long need, int nt, int n_total,
-                                      double (*sh)[32], double* mean, double* var) {
-    if (nt == 1) block_mean_var_nt<V, 1>(g, counts, nranks, need, nt, n_total, sh, mean, var);
-    else if (nt == 2 || V > 1) block_mean_var_nt<V, 2>(g, counts, nranks, need, nt, n_total, sh, mean, var);   // V > 1 (one-launch solve): nθ ≤ 2 (host check)
-    else block_mean_var_nt<V, kMaxTheta>(g, counts, nranks, need, nt, n_total, sh, mean, var);
+                                      double (*sh)[32], double* mean, double* var, bool* saw_nan = nullptr) {
+    if (nt == 1) block_mean_var_nt<V, 1>(g, counts, nranks, need, nt, n_total, sh, mean, var, saw_nan);
+    else if (nt == 2 || V > 1) block_mean_var_nt<V, 2>(g, counts, nranks, need, nt, n_total, sh, mean, var, saw_nan);   // V > 1 (one-launch solve): nθ ≤ 2 (host check)
+    else block_mean_var_nt<V, kMaxTheta>(g, counts, nranks, need, nt, n_total, sh, mean, var, saw_nan);
 }
 
 // solve_persist_kernel: CTA 0 lives through the whole solve, so what one θ-step needs of the previous one (θ, the last history
@@ -221,9 +226,10 @@ __device__ inline void theta_step_body(const OuterParams& P, double (*sh)[32], i
     // of solve_persist_kernel)
     // (loads issued eight at a time: one CTA scanning 10⁴ units is bound by the latency of dependent round trips to the L2)
     bool mine = false;
+    const bool fused_nan = P.nranks > 1 && P.dense;          // the NaN rows are noticed by the mean pass below
     if (P.nranks > 1) {
         if (threadIdx.x == 0 && __ldcg(P.status_local) == MUSE_STATUS_NONFINITE) mine = true;
-        for (int q = 0; q < P.nranks; ++q) {
+        for (int q = 0; q < P.nranks && !fused_nan; ++q) {
             const double* g = P.g_all + (size_t)q * P.need;
             const int n = P.counts[q] * P.nt;
             for (int e = threadIdx.x; e < n; e += 8 * blockDim.x) {
@@ -244,6 +250,14 @@ __device__ inline void theta_step_body(const OuterParams& P, double (*sh)[32], i
             for (int u = 0; u < 8; ++u) mine = mine || v[u] == MUSE_STATUS_NONFINITE;
         }
     }
+    double mean[kMaxTheta], var[kMaxTheta];
+    if (fused_nan) {
+        // dense layout (one-launch solve): rows of all ranks are consecutive in global sim order — mean, variance and the NaN
+        // test in the two passes the statistics need anyway.  (A NaN row only poisons sums that are thrown away.)
+        bool saw = false;
+        block_mean_var<V>(P.g_all, P.counts, 1, P.need, P.nt, P.n_total, sh, mean, var, &saw);
+        mine = mine || saw;
+    }
     if (mine) *bad = 1;
     __syncthreads();
     if (*bad) {
@@ -255,8 +269,7 @@ __device__ inline void theta_step_body(const OuterParams& P, double (*sh)[32], i
         return;
     }
     const int row = P.iter - 1;
-    double mean[kMaxTheta], var[kMaxTheta];
-    block_mean_var<V>(P.g_all, P.counts, P.nranks, P.need, P.nt, P.n_total, sh, mean, var);
+    if (!fused_nan) block_mean_var<V>(P.g_all, P.counts, P.dense ? 1 : P.nranks, P.need, P.nt, P.n_total, sh, mean, var);
     if (threadIdx.x != 0) return;
     double th_new[kMaxTheta], hip[kMaxTheta];
     for (int c = 0; c < P.nt; ++c) {
