@@ -143,6 +143,7 @@ extern "C" int muse_b200_muse_solve(muse_handle* h, const double* theta0, int32_
                                     int32_t maxsteps, double theta_rtol, double atol, double alpha, int32_t first_start,
                                     const double* prior_mean, const double* prior_sigma, int32_t get_covariance,
                                     int32_t nsims_h_total, const int32_t* counts_h, muse_iterate_out* out, muse_cov_out* cov) {
+    const auto t_entry = std::chrono::steady_clock::now();
     if (!h || !theta0 || !out || maxsteps < 1 || nsims_total < 2) return MUSE_EINVAL;
     if (h->corr) { h->err = "muse_solve: the device-resident loop serves the isotropic families; corrgauss uses muse_iterate"; return MUSE_EUNSUPPORTED; }
     if (maxsteps > kOuterMaxIter) { h->err = "muse_solve: maxsteps exceeds the device history (64 rows); use muse_iterate"; return MUSE_EUNSUPPORTED; }
@@ -474,8 +475,9 @@ extern "C" int muse_b200_muse_solve(muse_handle* h, const double* theta0, int32_
             if (dbg_timing) {
                 const long long* T = sh_->stamp;
                 char line[512];
-                int off = std::snprintf(line, sizeof line, "[muse_solve persist rank %d] n_iter=%d host: set-up+launch %.1f us, until synchronised %.1f us | kernel stamps (us since start):",
-                                        h->comm_rank, n_now, std::chrono::duration<double>(t_launched - t0).count() * 1e6, chunk_s * 1e6);
+                int off = std::snprintf(line, sizeof line, "[muse_solve persist rank %d] n_iter=%d host: entry→launched %.1f us (set-up+launch %.1f), until synchronised %.1f us | kernel stamps (us since start):",
+                                        h->comm_rank, n_now, std::chrono::duration<double>(t_launched - t_entry).count() * 1e6,
+                                        std::chrono::duration<double>(t_launched - t0).count() * 1e6, chunk_s * 1e6);
                 for (int k = 1; k < 13 && off < (int)sizeof line - 16; ++k)
                     off += std::snprintf(line + off, sizeof line - off, " %.1f", T[k] ? (double)(T[k] - T[0]) * 1e-3 : -1.0);
                 std::fprintf(stderr, "%s\n", line);
@@ -642,6 +644,11 @@ chain_of_launches:
         if (!finished && n_now < last) { h->err = "muse_solve: internal error (loop stalled)"; return MUSE_ESTATE; }
     }
 
+    static const bool dbg_total = [] { const char* e = std::getenv("MUSE_DEBUG_TIMING"); return e && *e; }();
+    struct TotalTimer {
+        std::chrono::steady_clock::time_point t0; bool on;
+        ~TotalTimer() { if (on) std::fprintf(stderr, "[muse_solve] whole call %.1f us\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() * 1e6); }
+    } total_timer{t_entry, dbg_total};
     if (get_covariance) {
         // the FD scores of this rank's H shard are in the main output block; combine with the device's step (:411-413)
         std::vector<double> Hs_local((size_t)std::max(1, nh_mine) * nt * nt);

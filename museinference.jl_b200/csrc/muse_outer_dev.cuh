@@ -136,10 +136,10 @@ __device__ inline void block_sums(const int* counts, int nranks, long long need,
         for (int j = 0; j < V; ++j)
 #pragma unroll
             for (int c = 0; c < NT; ++c) acc[j][c] = 0.0;
-        // every lane walks its sims in increasing order (k = t, t + T, t + 2T, …).  The loads of eight steps of ALL the thread's V
+        // every lane walks its sims in increasing order (k = t, t + T, t + 2T, …).  The loads of four steps of ALL the thread's V
         // lanes are issued before the first addition: a lone CTA is bound by the latency of dependent round trips to the L2, not by
         // bandwidth (with the lanes one after the other a θ-step over 10⁴ sims took 29 µs)
-        constexpr int S = 8;
+        constexpr int S = 4;
         for (int k0 = 0; k0 < n_total; k0 += S * T) {
             double v[S][V][NT];
             bool ok[S][V];
