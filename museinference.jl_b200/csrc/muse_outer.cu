@@ -299,8 +299,8 @@ extern "C" int muse_b200_muse_solve(muse_handle* h, const double* theta0, int32_
                 out->h_inv_post_hist[(size_t)row * nt + c] = R.h_inv_post[c];
             }
             double* gs = out->g_sims_hist + (size_t)row * nsims_total * nt;
-            if (multi && gall_dense) {
-                std::memcpy(gs, gall_h + (size_t)slot * gall_h_stride, (size_t)nsims_total * nt * sizeof(double));
+            if (multi && gall_dense) {     // peer-exchange mirror: blocks [slot 0 | slot 1 | FD | slot 2]
+                std::memcpy(gs, gall_h + (size_t)(slot < 2 ? slot : slot + 1) * gall_h_stride, (size_t)nsims_total * nt * sizeof(double));
             } else if (multi) {
                 const double* src = gall_h + (size_t)slot * gall_h_stride;
                 size_t off = 0;
@@ -418,8 +418,9 @@ extern "C" int muse_b200_muse_solve(muse_handle* h, const double* theta0, int32_
                 unsigned char* base = h->p2p_peer[q];
                 Q.x.flags[q] = reinterpret_cast<unsigned long long*>(base);
                 double* blocks = reinterpret_cast<double*>(base + 256) + (size_t)parity * (kOuterSlots + 1) * x_blk;
-                for (int s2 = 0; s2 < kOuterSlots; ++s2) Q.x.gall[q][s2] = blocks + (size_t)s2 * x_blk;
-                Q.x.fdall[q] = blocks + (size_t)kOuterSlots * x_blk;
+                // block order [slot 0 | slot 1 | FD | slot 2]: the typical solve's results are the first three, copied back in one go
+                for (int s2 = 0; s2 < kOuterSlots; ++s2) Q.x.gall[q][s2] = blocks + (size_t)(s2 < 2 ? s2 : s2 + 1) * x_blk;
+                Q.x.fdall[q] = blocks + (size_t)2 * x_blk;
             }
             for (int s2 = 0; s2 < kOuterSlots; ++s2) Q.cov.g_all_slot[s2] = Q.x.gall[h->comm_rank][s2];
         } else {
@@ -449,8 +450,7 @@ extern "C" int muse_b200_muse_solve(muse_handle* h, const double* theta0, int32_
         // results: [state | slot 0 | slot 1 | FD block] in one copy (the typical solve); slot 2 only if a third pass ran
         OUTER_TRY(h, cudaMemcpyAsync(h->outer_arena_h, h->outer_arena_d, h->outer_arena_head, cudaMemcpyDeviceToHost, h->stream));
         if (multi)
-            OUTER_TRY(h, cudaMemcpyAsync(h->p2p_host, Q.x.gall[h->comm_rank][0], (size_t)(kOuterSlots + 1) * x_blk * sizeof(double),
-                                         cudaMemcpyDeviceToHost, h->stream));
+            OUTER_TRY(h, cudaMemcpyAsync(h->p2p_host, Q.x.gall[h->comm_rank][0], (size_t)3 * x_blk * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         OUTER_TRY(h, cudaStreamSynchronize(h->stream));
         if (sh_->error == 3) {
             cudaMemsetAsync(h->persist_ctl, 0, sizeof(PersistCtl), h->stream);
@@ -466,6 +466,8 @@ extern "C" int muse_b200_muse_solve(muse_handle* h, const double* theta0, int32_
             const int n_now = sh_->n_iter;
             if (n_now > 2) {
                 OUTER_TRY(h, cudaMemcpyAsync(h->outer_slot[2].hst, h->outer_slot[2].d, h->outer_slot[2].bytes, cudaMemcpyDeviceToHost, h->stream));
+                if (multi)
+                    OUTER_TRY(h, cudaMemcpyAsync(h->p2p_host + (size_t)3 * x_blk, Q.x.gall[h->comm_rank][2], x_blk * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
                 OUTER_TRY(h, cudaStreamSynchronize(h->stream));
             }
             const double chunk_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -529,7 +531,7 @@ extern "C" int muse_b200_muse_solve(muse_handle* h, const double* theta0, int32_
             if (finished && cov_ran) {
                 if (multi) {        // every rank's FD scores are here: combine them all, in rank order
                     Hs_all.assign((size_t)std::max(1, (int)nsims_h_total) * nt * nt, 0.0);
-                    const double* fd_h = h->p2p_host + (size_t)kOuterSlots * x_blk;
+                    const double* fd_h = h->p2p_host + (size_t)2 * x_blk;
                     size_t off = 0;
                     for (int q = 0; q < P.nranks; ++q) {
                         const double* rows = fd_h + (size_t)q * Q.x.need_fd;

@@ -1039,7 +1039,7 @@ def _nccl_worker(rank, world, port, cases, q):
     try:
         pool = m.ShardPool(device=rank)
         outs = []
-        for name, d, nsims, th0, xd, P, L, prior, fused, exchange in cases:
+        for name, d, nsims, th0, xd, P, L, prior, fused, exchange, kw in cases:
             # exchange "p2p": the one-launch solve, score rows stored into the peer's memory by the kernel; "nccl": the chain
             # of launches with ncclAllGather between pass and θ-step
             if exchange == "nccl":
@@ -1051,7 +1051,7 @@ def _nccl_worker(rank, world, port, cases, q):
             for seed in (11, 12):          # twice: the second solve of a shape goes through the library's captured graph
                 if seed == 12 and prob._backend is not None:
                     prob._backend.profile_reset(True)
-                res = m.muse(prob, th0, rng=seed, nsims=nsims, get_covariance=True, pool=pool, fused_driver=fused)
+                res = m.muse(prob, th0, rng=seed, nsims=nsims, get_covariance=True, pool=pool, fused_driver=fused, **kw)
             if prob._backend is not None:
                 launches = prob._backend.profile()["solve_launches"]
                 p2p = prob._backend.p2p_info()
@@ -1074,13 +1074,15 @@ def test_two_rank_nccl_solve_is_bit_identical_to_one_gpu():
     import torch.multiprocessing as mp
     import museinference_jl_b200 as m
     cases = []
-    for name, d, nsims, prior, fused, exchange in (("funnel", 6000, 203, True, True, "p2p"), ("funnel", 6000, 203, True, True, "nccl"),
-                                                   ("hiergauss", 5001, 120, False, True, "p2p"), ("hiergauss", 5001, 120, False, True, "nccl"),
-                                                   ("funnel", 512, 301, True, True, "p2p"), ("funnel", 512, 5, True, True, "p2p"),
-                                                   ("corrgauss", 256, 100, True, True, "p2p"),
-                                                   ("hiergauss", 700, 64, True, False, "p2p")):
+    long_loop = dict(theta_rtol=0.0, maxsteps=5)       # 3 passes in the one-launch solve, 2 more on the chain of launches
+    for name, d, nsims, prior, fused, exchange, kw in (("funnel", 6000, 203, True, True, "p2p", {}), ("funnel", 6000, 203, True, True, "nccl", {}),
+                                                       ("hiergauss", 5001, 120, False, True, "p2p", {}), ("hiergauss", 5001, 120, False, True, "nccl", {}),
+                                                       ("funnel", 512, 301, True, True, "p2p", {}), ("funnel", 512, 5, True, True, "p2p", {}),
+                                                       ("hiergauss", 300, 31, True, True, "p2p", long_loop), ("funnel", 4500, 40, True, True, "p2p", dict(maxsteps=3, theta_rtol=0.0)),
+                                                       ("corrgauss", 256, 100, True, True, "p2p", {}),
+                                                       ("hiergauss", 700, 64, True, False, "p2p", {})):
         fam, _, xd = make_inputs(name, d, 1)
-        cases.append((name, d, nsims, theta_start(name), xd, getattr(fam, "P", None), getattr(fam, "L", None), prior, fused, exchange))
+        cases.append((name, d, nsims, theta_start(name), xd, getattr(fam, "P", None), getattr(fam, "L", None), prior, fused, exchange, kw))
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
@@ -1091,9 +1093,9 @@ def test_two_rank_nccl_solve_is_bit_identical_to_one_gpu():
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
-    for i, (name, d, nsims, th0, xd, P, L, prior, fused, exchange) in enumerate(cases):
+    for i, (name, d, nsims, th0, xd, P, L, prior, fused, exchange, kw) in enumerate(cases):
         prob = m.SimpleMuseProblem(xd, name, m.NormalPrior(0, 3) if prior else None, P=P, L=L)
-        ref = m.muse(prob, th0, rng=12, nsims=nsims, get_covariance=True, fused_driver=fused)
+        ref = m.muse(prob, th0, rng=12, nsims=nsims, get_covariance=True, fused_driver=fused, **kw)
         prob.close()
         for rank in (0, 1):
             theta, gs, H, J, Sigma, nhist, launches, p2p = got[rank][i]
