@@ -684,10 +684,17 @@ __device__ __forceinline__ void stream_pass(const SolveLaunch& L, Shared& sh, do
                 __threadfence();
                 __syncwarp();
                 if (lane < kNRed) {
-                    acc = __ldcg(L.gpart + (size_t)unit * nseg * kRedPad + lane);
-                    for (int sg = 1; sg < nseg; ++sg) {
-                        const double o = __ldcg(L.gpart + ((size_t)unit * nseg + sg) * kRedPad + lane);
-                        acc = mx ? fmax(acc, o) : acc + o;
+                    // segments in index order; their partials are fetched eight at a time (independent loads), not one round trip
+                    // to the L2 per segment — the fiducial solve of the one-launch form has one segment per chunk (32 at d = 65 536)
+                    const double* gp = L.gpart + (size_t)unit * nseg * kRedPad + lane;
+                    acc = __ldcg(gp);
+                    for (int sg0 = 1; sg0 < nseg; sg0 += 8) {
+                        double o[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) o[u] = sg0 + u < nseg ? __ldcg(gp + (size_t)(sg0 + u) * kRedPad) : 0.0;
+#pragma unroll
+                        for (int u = 0; u < 8; ++u)
+                            if (sg0 + u < nseg) acc = mx ? fmax(acc, o[u]) : acc + o[u];
                     }
                 }
                 if (lane == 0) L.gcount[unit] = 0;      // ready for the next launch
