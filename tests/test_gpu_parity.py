@@ -795,6 +795,8 @@ def _assert_identical_solve(a, b, cov=True):
     ("hiergauss", 300, 30, True, dict(theta_rtol=0.0, maxsteps=7)),      # 3 passes in the launch, the rest on the chain of launches
     ("funnel", 6000, 40, True, dict(theta_rtol=1e-2, maxsteps=3)),       # the loop ends with the launch's last pass
     ("funnel", 6000, 40, True, dict(maxsteps=1)),                        # one pass, then the covariance stage
+    ("funnel", 5000, 30, True, dict(z0="user")),                         # user start vector: streamed as the lazy chain's start row
+    ("hiergauss", 700, 45, False, dict(z0="user", theta_rtol=0.0, maxsteps=4)),
 ])
 def test_one_launch_solve_is_bit_identical_to_the_chain_of_launches(name, d, nsims, prior, kw):
     """solve_persist_kernel (one cooperative launch: passes, θ updates, get_H!'s fiducial solve and FD sims) against the chain of
@@ -804,6 +806,9 @@ def test_one_launch_solve_is_bit_identical_to_the_chain_of_launches(name, d, nsi
     oprob, fam, draws, xd = oracle_problem(name, d, nsims)
     rng = m.BaseDraws(draws.xi, draws.nu, draws.xi_master, draws.nu_master)
     pr = (lambda: m.NormalPrior([0.0, 0.1][:fam.ntheta], [3.0, 2.0][:fam.ntheta])) if prior else (lambda: None)
+    kw = dict(kw)
+    if kw.get("z0") == "user":
+        kw["z0"] = 0.3 * np.cos(0.01 * np.arange(d))
     # lazy: ẑ recomputed from the base normals instead of stored and re-read; lean: the α = 1 trial from its closed form — neither
     # may change a single bit of the result
     for cov, lazy, lean in ((True, False, False), (False, False, False), (True, True, False), (True, False, True), (True, True, True), (False, True, True)):
@@ -814,7 +819,8 @@ def test_one_launch_solve_is_bit_identical_to_the_chain_of_launches(name, d, nsi
         assert pa["launches"] < pb["launches"]
         if n <= 3:
             assert pa["launches"] == 1 and pa["solve_launches"] == 1, pa
-            assert passes["cold"]["launches"] == 1 and passes["warm"]["launches"] == n - 1
+            user = "z0" in kw                           # a user start makes the first pass a "warm" one (it streams a start row)
+            assert passes["cold"]["launches"] == (0 if user else 1) and passes["warm"]["launches"] == (n if user else n - 1)
             assert passes["fd"]["launches"] == (1 if cov else 0)
             assert all(v["ms"] > 0 for v in passes.values() if v["launches"])
             assert pa["solve_units"] == pb["solve_units"]
@@ -824,7 +830,7 @@ def test_one_launch_solve_is_bit_identical_to_the_chain_of_launches(name, d, nsi
                 # lazy ẑ: a pass reads ξ, ν of every sim and the data — nothing else, and writes nothing, unless it is the third
                 # pass of a loop that may go on (which materialises ẑ)
                 stored = (nsims + 1) * 8 * d if (n == 3 and kw.get("maxsteps", 50) > 3) else 0
-                assert passes["cold"]["bytes"] + passes["warm"]["bytes"] == n * (nsims * 16 * d + 8 * d) + stored
+                assert passes["cold"]["bytes"] + passes["warm"]["bytes"] == n * (nsims * 16 * d + 8 * d + (8 * d if user else 0)) + stored
 
 
 def test_one_launch_solve_gives_way_to_the_chain_when_units_leave_the_fast_path():
