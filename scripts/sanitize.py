@@ -16,6 +16,10 @@ def run(family, d, n, **kw):
     r = m.muse(prob, th0, rng=3, nsims=n, get_covariance=True)
     be = prob._backend
     th = np.array(th0)
+    if os.environ.get("MUSE_SANITIZE_NO_GENERIC"):      # synccheck stops at the generic kernel's named barriers (profiles/r01_sanitizer.md)
+        print(family, d, n, kw, "theta", r.theta)
+        prob.close()
+        return
     o = be.map_score(th, th, 1e-300 if family != "corrgauss" else 1e-2, include_data=True, warm_start=0)   # history path / hand-back
     print(family, d, n, kw, "theta", r.theta, "iters", np.bincount(o["iters"])[:8], "redo", be.profile()["redo_units"])
     prob.close()
@@ -23,6 +27,24 @@ def run(family, d, n, **kw):
 run("funnel", 4500, 40)                 # streaming kernel, 3 chunks, ragged tail
 run("hiergauss", 20001, 24)             # streaming kernel, 2 segments, odd d
 run("funnel", 300, 50)                  # warp-per-unit generic kernel
-run("funnel", 3000, 16, kernel=1, group=256, cluster=2)   # cluster groups (DSMEM reductions)
-run("corrgauss", 200, 20)               # F3: DGEMM + lock-step kernels
+if not os.environ.get("MUSE_SANITIZE_NO_GENERIC"):
+    run("funnel", 3000, 16, kernel=1, group=256, cluster=2)   # cluster groups (DSMEM reductions)
+run("corrgauss", 256, 20)               # F3: TMA DGEMM + lock-step kernels
+# round 2: the one-launch solve in its forms (the muse() calls above already ran it with the defaults), implicit diff, user start
+for env in ({"MUSE_LAZY": "0", "MUSE_LEAN": "0"}, {"MUSE_FUNNEL_SPEC": "0"}, {"MUSE_PERSIST": "0"}):
+    os.environ.update(env)
+    run("funnel", 4500, 24)
+    for k in env:
+        os.environ.pop(k)
+x = np.random.default_rng(1).standard_normal(4100)
+prob = m.SimpleMuseProblem(x, "hiergauss")
+r = m.muse(prob, [0.5, 0.3], rng=4, nsims=20, get_covariance=True, z0=0.1 * np.ones(4100), maxsteps=4, theta_rtol=0.0)
+res = m.MuseResult(theta=r.theta.copy())
+getattr(m, "get_H!")(res, prob, rng=4, nsims=5, implicit_diff=True)
+prob.close()
+P, L = corr_consts(256)
+prob = m.SimpleMuseProblem(np.random.default_rng(2).standard_normal(256), "corrgauss", m.NormalPrior(0, 3), P=P, L=L)
+res = m.MuseResult(theta=np.array([0.4]))
+getattr(m, "get_H!")(res, prob, rng=4, nsims=6, implicit_diff=True)
+prob.close()
 print("done")

@@ -322,6 +322,32 @@ class _FlakyBackend(FakeBackend):
         return Hs, st
 
 
+def test_fused_history_behaves_like_the_list_it_stands_for(tmp_path):
+    """result.history of an in-library solve is materialised on first access (museinference.jl_b200/muse.py: FusedHistory):
+    len / truth value without building the rows, indexing, iteration, append, pickling as a plain list, resume from it."""
+    from fake_backend import FusedFakeBackend
+    import museinference_jl_b200 as m
+    oprob, fam, draws, xd = oracle_problem("funnel", 96, 20, seed=5, prior=O.NormalPrior(0, 3))
+    prob = m.SimpleMuseProblem(xd, "funnel", m.NormalPrior(0, 3), backend_factory=FusedFakeBackend)
+    rng = m.BaseDraws(draws.xi, draws.nu, draws.xi_master, draws.nu_master)
+    res = m.muse(prob, [1.0], rng=rng, nsims=20, maxsteps=3, theta_rtol=0.0)
+    h = res.history
+    assert type(h).__name__ == "FusedHistory" and h._items is None
+    assert len(h) == 3 and bool(h) and h._items is None                     # nothing built yet
+    ref = O.muse(oprob, [1.0], nsims=20, maxsteps=3, theta_rtol=0.0)
+    np.testing.assert_allclose(h[-1]["theta"], ref.history[-1]["theta"], rtol=1e-12)
+    assert [sorted(row) for row in h] == [sorted(h[0])] * 3 and "g_like_sims" in h[0]
+    blob = pickle.dumps(res)
+    back = pickle.loads(blob)
+    assert isinstance(back.history, list) and len(back.history) == 3
+    np.testing.assert_array_equal(back.history[1]["g_like"], h[1]["g_like"])
+    # resume: two more iterations on the line-by-line loop append to the same history
+    res2 = getattr(m, "muse!")(res, prob, rng=rng, nsims=20, maxsteps=5, theta_rtol=0.0)
+    assert len(res2.history) == 5
+    ref5 = O.muse(oprob, [1.0], nsims=20, maxsteps=5, theta_rtol=0.0)
+    np.testing.assert_allclose(res2.theta, ref5.theta, rtol=1e-10)
+
+
 def test_skip_errors_drops_failed_sims_and_the_default_raises():
     """src/muse.jl:515-521 / 434-441: with skip_errors a failed sim becomes `missing` and is skipped; without it the error
     propagates (src/interface.jl:170)."""
