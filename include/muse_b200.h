@@ -298,7 +298,11 @@ int  muse_b200_muse_covariance(muse_handle* h, const double* theta, const double
  * synchronises once per chunk of three passes (the typical solve: once).  Isotropic families only (corrgauss: use
  * muse_iterate), maxsteps ≤ 64.  Same outputs as the two calls it replaces; θ agrees with them to round-off (parallel
  * reductions, device libm), not bit for bit; seconds_hist holds the chunk's wall time divided by its iterations.
- * get_covariance = 0: the loop only (cov may be NULL). */
+ * get_covariance = 0: the loop only (cov may be NULL).
+ * By default the first three iterations and the covariance stage run as ONE cooperative kernel launch (csrc/muse_iso_stream.cu:
+ * solve_persist_kernel; with muse_b200_p2p_* buffers in place also across GPUs, the exchange inside the kernel); that launch keeps
+ * no resident MAPs — like muse! itself, whose ẑs do not outlive the call (src/muse.jl:151): after muse_solve, muse_b200_get_maps
+ * and warm_start = PREV see zero(z) unless the loop ran past three iterations.  Use map_score / the host driver's save_MAPs to keep ẑ. */
 int  muse_b200_muse_solve(muse_handle* h, const double* theta0, int32_t nsims_total, const int32_t* counts,
                           int32_t maxsteps, double theta_rtol, double atol, double alpha, int32_t first_start,
                           const double* prior_mean, const double* prior_sigma /* NULL: flat prior */,

@@ -943,10 +943,18 @@ struct PersistShared {
 };
 static_assert(sizeof(DynConsts) % 8 == 0, "DynConsts is copied in 8-byte words");
 
-// ps.L ← the launch description of phase ph: what muse_pass_enqueue / fd_launch (muse_api.cu) fill in on the host
+// ps.L ← the launch description of phase ph: what muse_pass_enqueue / fd_launch (muse_api.cu) fill in on the host.  Two steps:
+// every thread copies one word of the common part out of the kernel's parameter space (one thread doing the 650-byte copy took
+// ≈ 1 µs per phase), then — after a barrier — thread 0 patches the phase's own fields.
+static_assert(sizeof(SolveLaunch) % 8 == 0 && sizeof(SolveLaunch) / 8 <= kWarpCta, "phase_base: one 8-byte word per thread");
+__device__ __forceinline__ void phase_base(const PersistParams& P, PersistShared& ps) {
+    constexpr int kWords = (int)(sizeof(SolveLaunch) / 8);
+    if ((int)threadIdx.x < kWords)
+        reinterpret_cast<unsigned long long*>(&ps.L)[threadIdx.x] = reinterpret_cast<const unsigned long long*>(&P.base)[threadIdx.x];
+    __syncthreads();
+}
 __device__ void phase_launch(const PersistParams& P, int ph, PersistShared& ps) {
     SolveLaunch& L = ps.L;
-    L = P.base;
     PersistCtl* const ctl = P.ctl;
     L.redo_count = &ctl->redo[ph];
     L.work_next = &ctl->work[ph];
@@ -1150,6 +1158,7 @@ solve_persist_kernel(const __grid_constant__ PersistParams P) {
     unsigned seq = 0;
     bool reinit = false, finished = false;
     for (int i = 1; i <= P.max_pass; ++i) {
+        phase_base(P, ps);
         if (tid == 0) phase_launch(P, i - 1, ps);
         __syncthreads();
         run_phase<STREAM, LEAN>(ps.L, reinit);
@@ -1164,6 +1173,7 @@ solve_persist_kernel(const __grid_constant__ PersistParams P) {
     if (finished && P.get_cov) {
         bool ran_fd = false;
         if (P.nh_mine > 0) {
+            phase_base(P, ps);
             if (tid == 0) phase_launch(P, kPhaseFid, ps);
             __syncthreads();
             run_phase<STREAM, LEAN>(ps.L, reinit);
@@ -1182,6 +1192,7 @@ solve_persist_kernel(const __grid_constant__ PersistParams P) {
                 }
             }
             if (wait_step(P, ps, seq) && !ps.abort && !ps.error) {
+                phase_base(P, ps);
                 if (tid == 0) phase_launch(P, kPhaseFd, ps);
                 __syncthreads();
                 run_phase<STREAM, LEAN>(ps.L, reinit);
