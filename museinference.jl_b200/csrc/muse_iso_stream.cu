@@ -1028,6 +1028,19 @@ __device__ __forceinline__ void run_phase(const SolveLaunch& L, bool reinit) {
     }
 }
 
+// device → mapped pinned host memory, 16 bytes per thread and step (both 16-byte aligned; a trailing 8 bytes handled apart).
+// part / nparts: this caller's slice (a CTA of the grid, or everything for CTA 0 alone).  The data were published by other CTAs
+// before the phase barrier: read at the L2.
+__device__ void copy_to_host(unsigned char* dst, const unsigned char* src, unsigned long long bytes, int part, int nparts) {
+    const unsigned long long words = bytes / 16, per = (words + nparts - 1) / nparts;
+    const unsigned long long w0 = (unsigned long long)part * per, w1 = w0 + per < words ? w0 + per : words;
+    const uint4* s4 = reinterpret_cast<const uint4*>(src);
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    for (unsigned long long w = w0 + threadIdx.x; w < w1; w += blockDim.x) d4[w] = __ldcg(s4 + w);
+    if (part == nparts - 1 && threadIdx.x == 0 && (bytes & 8ULL))
+        *reinterpret_cast<unsigned long long*>(dst + words * 16) = __ldcg(reinterpret_cast<const unsigned long long*>(src + words * 16));
+}
+
 // thread 0 of CTA 0: until every CTA has arrived at the end of phase ph
 __device__ void wait_arrivals(const PersistParams& P, int ph, PersistShared& ps) {
     const long long t0 = gtime_ns();
@@ -1091,6 +1104,9 @@ __device__ void leader_step(const PersistParams& P, PersistShared& ps, int i, un
         // score rows land in GLOBAL sim order (rank r's rows behind those of ranks < r): the θ-step reads them like one GPU's
         exchange_rows(P, ps, ob.g + nt, ob.status + 1, P.step.counts[P.x.rank] * nt, nt, dst, (long long)P.x.row0 * nt, P.x.epoch0 + i);
         if (tid == 0 && ph < 2) P.stamps[11 + ph] = gtime_ns();          // diagnostics: rows of every peer are here
+        if (P.gall_h[ph] && !ps.timeout)
+            copy_to_host(reinterpret_cast<unsigned char*>(P.gall_h[ph]), reinterpret_cast<const unsigned char*>(P.x.gall[P.x.rank][ph]),
+                         (unsigned long long)P.step.n_total * nt * sizeof(double), 0, 1);
     }
     if (!ps.l_abort && !ps.timeout) {
         theta_step_body<V>(ps.step, ps.red, &ps.bad, &ps.cache);
@@ -1167,6 +1183,8 @@ solve_persist_kernel(const __grid_constant__ PersistParams P) {
         ++seq;
         if (lead) leader_step<V>(P, ps, i, seq);
         if (!wait_step(P, ps, seq)) break;
+        // this pass's per-unit results → the host mirror, a slice per CTA (posted writes: they overlap what follows)
+        if (P.slot_h[i - 1]) copy_to_host(P.slot_h[i - 1], P.slot_d[i - 1], P.slot_bytes, blockIdx.x, gridDim.x);
         if (ps.abort || ps.error) break;
         if (ps.done) { finished = true; break; }
     }
@@ -1222,10 +1240,26 @@ solve_persist_kernel(const __grid_constant__ PersistParams P) {
             }
         }
     }
+    // CTA 0: what is left for the host — the FD block (its units were published before the arrivals CTA 0 waited for), the
+    // gathered FD rows, and the state (header + the history rows that were written)
+    __syncthreads();
+    if (lead) {
+        if (tid == 0 && ps.timeout) { volatile OuterState* st = P.step.st; st->error = 3; }
+        __syncthreads();
+        if (P.fd_h && P.fd_bytes) copy_to_host(P.fd_h, P.fd_d, P.fd_bytes, 0, 1);
+        if (P.fdall_h && P.x.nranks > 1)
+            copy_to_host(reinterpret_cast<unsigned char*>(P.fdall_h), reinterpret_cast<const unsigned char*>(P.x.fdall[P.x.rank]),
+                         (unsigned long long)P.x.nranks * P.x.need_fd * sizeof(double), 0, 1);
+        if (P.st_h) {
+            __threadfence();           // thread 0's own state writes, before everybody reads them back
+            __syncthreads();
+            const unsigned long long nb = (offsetof(OuterState, row) + (unsigned long long)kOuterSlots * sizeof(OuterRow) + 15ULL) & ~15ULL;
+            copy_to_host(reinterpret_cast<unsigned char*>(P.st_h), reinterpret_cast<const unsigned char*>(P.step.st), nb, 0, 1);
+        }
+    }
     // the last CTA to leave clears the control block for the next launch
     __syncthreads();
     if (tid == 0) {
-        if (ps.timeout && lead) { volatile OuterState* st = P.step.st; st->error = 3; }
         __threadfence();
         if (atomicAdd(&ctl->exit_count, 1) == (int)gridDim.x - 1) {
             volatile int* w = reinterpret_cast<volatile int*>(ctl);

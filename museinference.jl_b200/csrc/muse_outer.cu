@@ -396,6 +396,15 @@ extern "C" int muse_b200_muse_solve(muse_handle* h, const double* theta0, int32_
         Q.fd = optrs(h->outer_fd);
         Q.ctl = static_cast<PersistCtl*>(h->persist_ctl);
         Q.stamps = sd->stamp;
+        // results streamed to the pinned mirrors by the kernel itself (MUSE_HOSTWRITE=0: copy nodes behind the kernel instead)
+        const bool hostwrite = [] { const char* e = std::getenv("MUSE_HOSTWRITE"); return !e || std::atoi(e) != 0; }();
+        if (hostwrite) {
+            for (int s2 = 0; s2 < kOuterSlots; ++s2) { Q.slot_d[s2] = h->outer_slot[s2].d; Q.slot_h[s2] = h->outer_slot[s2].hst; }
+            Q.slot_bytes = h->outer_slot[0].bytes;
+            Q.fd_d = h->outer_fd.d; Q.fd_h = h->outer_fd.hst;
+            Q.fd_bytes = nh_mine > 0 && get_covariance ? muse_outblock_bytes(h, fd_items) : 0;
+            Q.st_h = sh_;
+        }
         Q.x.nranks = 1;
         size_t x_blk = 0;
         int parity = 0;
@@ -423,6 +432,10 @@ extern "C" int muse_b200_muse_solve(muse_handle* h, const double* theta0, int32_
                 Q.x.fdall[q] = blocks + (size_t)2 * x_blk;
             }
             for (int s2 = 0; s2 < kOuterSlots; ++s2) Q.cov.g_all_slot[s2] = Q.x.gall[h->comm_rank][s2];
+            if (hostwrite) {
+                for (int s2 = 0; s2 < kOuterSlots; ++s2) Q.gall_h[s2] = h->p2p_host + (size_t)(s2 < 2 ? s2 : s2 + 1) * x_blk;
+                Q.fdall_h = get_covariance ? h->p2p_host + (size_t)2 * x_blk : nullptr;
+            }
         } else {
             for (int s2 = 0; s2 < kOuterSlots; ++s2) Q.cov.g_all_slot[s2] = h->outer_slot[s2].g_d + nt;
         }
@@ -447,10 +460,12 @@ extern "C" int muse_b200_muse_solve(muse_handle* h, const double* theta0, int32_
         }
         if (h->prof) OUTER_TRY(h, cudaEventRecord(eb, h->stream));
         h->acc.launches += 1;
-        // results: [state | slot 0 | slot 1 | FD block] in one copy (the typical solve); slot 2 only if a third pass ran
-        OUTER_TRY(h, cudaMemcpyAsync(h->outer_arena_h, h->outer_arena_d, h->outer_arena_head, cudaMemcpyDeviceToHost, h->stream));
-        if (multi)
-            OUTER_TRY(h, cudaMemcpyAsync(h->p2p_host, Q.x.gall[h->comm_rank][0], (size_t)3 * x_blk * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        if (!hostwrite) {
+            // results: [state | slot 0 | slot 1 | FD block] in one copy (the typical solve); slot 2 only if a third pass ran
+            OUTER_TRY(h, cudaMemcpyAsync(h->outer_arena_h, h->outer_arena_d, h->outer_arena_head, cudaMemcpyDeviceToHost, h->stream));
+            if (multi)
+                OUTER_TRY(h, cudaMemcpyAsync(h->p2p_host, Q.x.gall[h->comm_rank][0], (size_t)3 * x_blk * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        }
         OUTER_TRY(h, cudaStreamSynchronize(h->stream));
         if (sh_->error == 3) {
             cudaMemsetAsync(h->persist_ctl, 0, sizeof(PersistCtl), h->stream);
@@ -464,7 +479,7 @@ extern "C" int muse_b200_muse_solve(muse_handle* h, const double* theta0, int32_
             if (lazy_on) OUTER_TRY(h, cudaMemsetAsync(h->zstate, 0, (size_t)h->rows * sizeof(int), h->stream));
         } else {
             const int n_now = sh_->n_iter;
-            if (n_now > 2) {
+            if (n_now > 2 && !hostwrite) {
                 OUTER_TRY(h, cudaMemcpyAsync(h->outer_slot[2].hst, h->outer_slot[2].d, h->outer_slot[2].bytes, cudaMemcpyDeviceToHost, h->stream));
                 if (multi)
                     OUTER_TRY(h, cudaMemcpyAsync(h->p2p_host + (size_t)3 * x_blk, Q.x.gall[h->comm_rank][2], x_blk * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
