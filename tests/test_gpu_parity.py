@@ -850,6 +850,30 @@ def test_one_launch_solve_gives_way_to_the_chain_when_units_leave_the_fast_path(
     assert max(h["z_history_sims"]["iters"].max() for h in a.history) >= 2
 
 
+@pytest.mark.parametrize("name,d,nsims,kw", [
+    ("funnel", 512, 2500, {}),                                           # warp-per-unit phases, 2 passes
+    ("hiergauss", 5000, 50, dict(theta_rtol=0.0, maxsteps=3)),           # TMA-ring phases, all three pass blocks of the launch
+    ("funnel", 9000, 33, dict(maxsteps=1)),                              # one pass: the other pass blocks stay untouched
+])
+def test_results_stored_to_the_host_mirrors_by_the_kernel_equal_the_copied_ones(name, d, nsims, kw):
+    """The one-launch solve stores every per-unit result into the pinned host mirrors itself (copy_to_host: each CTA its slice of a
+    pass's block once the pass has ended, CTA 0 the FD block and the state at exit).  MUSE_HOSTWRITE=0 leaves them in device memory
+    and copies them behind the kernel: the host side must read the same bytes either way."""
+    import os
+    import museinference_jl_b200 as m
+    oprob, fam, draws, xd = oracle_problem(name, d, nsims)
+    rng = m.BaseDraws(draws.xi, draws.nu, draws.xi_master, draws.nu_master)
+    pr = lambda: m.NormalPrior([0.0, 0.1][:fam.ntheta], [3.0, 2.0][:fam.ntheta])
+    a, pa, _ = _solve_persist(m, xd, name, pr, rng, nsims, True, True, True, get_covariance=True, fused_driver="device", **kw)
+    os.environ["MUSE_HOSTWRITE"] = "0"
+    try:
+        b, pb, _ = _solve_persist(m, xd, name, pr, rng, nsims, True, True, True, get_covariance=True, fused_driver="device", **kw)
+    finally:
+        os.environ.pop("MUSE_HOSTWRITE", None)
+    assert pa["launches"] == pb["launches"] == 1
+    _assert_identical_solve(a, b)
+
+
 # ----------------------------------------------------------------------------- device-resident outer loop (csrc/muse_outer.cu)
 def _solve_modes(m, xd, name, pr, rng, nsims, modes, **kw):
     res = {}
