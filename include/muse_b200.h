@@ -51,6 +51,8 @@ extern "C" {
 #define MUSE_FAMILY_FUNNEL     1   /* src/simple.jl:58-76: z~N(0,e^θ I), x~N(z,I); scalar θ            */
 #define MUSE_FAMILY_HIERGAUSS  2   /* z~N(μ,e^{2ℓ} I), x~N(z,I); θ=(μ,ℓ)                               */
 #define MUSE_FAMILY_CORRGAUSS  3   /* z~N(0,e^θ Σ₀), x~N(z,I); scalar θ; P=Σ₀⁻¹, L=chol Σ₀ supplied    */
+#define MUSE_FAMILY_TWOLAYER   4   /* src/turing.jl:63-79 (docstring toy): z~N(0,e^{σ/2}I_n), w~N(z,I), x~N(w,I), y~N(x,I); scalar σ;
+                                      d = 2n even: latent (z,w), data (x,y), latent normals (ξ_z,ξ_w), noise normals (ν_x,ν_y) stacked */
 
 /* warm-start modes for the latent MAP (what the reference passes as z₀ to ẑ_at_θ) */
 #define MUSE_START_ZEROS   0   /* zero(z)                 src/muse.jl:151, src/interface.jl:184-186 */
@@ -73,7 +75,7 @@ typedef struct muse_cfg {
     int32_t abi_version;     /* MUSE_B200_ABI_VERSION */
     int32_t family;          /* MUSE_FAMILY_* */
     int32_t d;               /* latent (= data) dimension */
-    int32_t ntheta;          /* 1 (funnel, corrgauss) or 2 (hiergauss) */
+    int32_t ntheta;          /* 1 (funnel, corrgauss, twolayer) or 2 (hiergauss) */
     int32_t nsims;           /* local simulations owned by this handle (rows of the draw arrays) */
     int32_t device;          /* CUDA device ordinal */
     int64_t sim_offset;      /* global index of local simulation 0 */

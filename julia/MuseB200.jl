@@ -15,7 +15,7 @@ using Random, Statistics, LinearAlgebra
 
 const libmuse = get(ENV, "LIBMUSE_B200", "libmuse_b200.so")
 
-const FAMILY = Dict(:funnel => Cint(1), :hiergauss => Cint(2), :corrgauss => Cint(3))
+const FAMILY = Dict(:funnel => Cint(1), :hiergauss => Cint(2), :corrgauss => Cint(3), :twolayer => Cint(4))
 const START_ZEROS, START_PREV, START_TRUTH, START_USER = Cint(0), Cint(1), Cint(2), Cint(3)
 
 # mirrors `struct muse_cfg` (include/muse_b200.h)
@@ -54,7 +54,8 @@ end
     B200MuseProblem(x, family; logPriorθ = θ -> 0)
 
 The B200 counterpart of `SimpleMuseProblem` (src/simple.jl:4-12).  A GPU backend cannot introspect Julia
-closures, so the model is *named*: `:funnel` (src/simple.jl:58-76), `:hiergauss` or `:corrgauss`.
+closures, so the model is *named*: `:funnel` (src/simple.jl:58-76), `:hiergauss`, `:corrgauss` or `:twolayer` (the toy hierarchy of
+src/turing.jl:63-79 with `x = vcat(sim.x, sim.y)`, parameter σ).
 Any other `AbstractMuseProblem` (Turing, Soss, arbitrary closures) is not supported: calling `muse` on it
 through this backend throws; there is no CPU fallback.
 """
@@ -140,7 +141,7 @@ function MuseInference.muse!(result::MuseResult, prob::B200MuseProblem, θ₀ = 
     history = result.history
     # Common configuration (fresh result, constant α, identity regularize and transform, flat or Normal prior, isotropic family):
     # the loop AND the covariance stage run inside the library — one kernel launch per solve (muse_b200_muse_solve, DESIGN.md §3.6)
-    if isempty(history) && regularize === identity && α isa Real && !has_transform(prob) && prob.family !== :corrgauss &&
+    if isempty(history) && regularize === identity && α isa Real && !has_transform(prob) && prob.family !== :corrgauss && prob.family !== :twolayer &&
        maxsteps <= 64 && isempty(kwargs) && (prob.prior !== nothing || prob.logPriorθ(θ) == 0)
         return fused_solve!(result, prob, h, θ; maxsteps, θ_rtol, ∇z_logLike_atol, nsims, α, get_covariance)
     end

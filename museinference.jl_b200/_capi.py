@@ -12,7 +12,7 @@ from . import _build
 
 ABI_VERSION = 1
 
-FAMILY_FUNNEL, FAMILY_HIERGAUSS, FAMILY_CORRGAUSS = 1, 2, 3
+FAMILY_FUNNEL, FAMILY_HIERGAUSS, FAMILY_CORRGAUSS, FAMILY_TWOLAYER = 1, 2, 3, 4
 START_ZEROS, START_PREV, START_TRUTH, START_USER = 0, 1, 2, 3
 STATUS_G_CONVERGED, STATUS_XF_CONVERGED, STATUS_MAXITER, STATUS_LS_FAILED, STATUS_NONFINITE = 0, 1, 2, 3, 4
 E_NAMES = {0: "OK", -1: "EINVAL", -2: "ENODEVICE", -3: "ECUDA", -4: "ENOMEM", -5: "EUNSUPPORTED", -6: "ESTATE"}

@@ -12,8 +12,9 @@ import numpy as np
 from . import _capi
 from ._capi import MuseBackendError
 
-FAMILY_IDS = {"funnel": _capi.FAMILY_FUNNEL, "hiergauss": _capi.FAMILY_HIERGAUSS, "corrgauss": _capi.FAMILY_CORRGAUSS}
-FAMILY_NTHETA = {"funnel": 1, "hiergauss": 2, "corrgauss": 1}
+FAMILY_IDS = {"funnel": _capi.FAMILY_FUNNEL, "hiergauss": _capi.FAMILY_HIERGAUSS, "corrgauss": _capi.FAMILY_CORRGAUSS,
+              "twolayer": _capi.FAMILY_TWOLAYER}
+FAMILY_NTHETA = {"funnel": 1, "hiergauss": 2, "corrgauss": 1, "twolayer": 1}
 
 
 def _f64(a, shape=None):

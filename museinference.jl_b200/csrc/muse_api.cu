@@ -254,8 +254,9 @@ int muse_b200_create(const muse_cfg* cfg, muse_handle** out) {
     if (!cfg || !out) { g_create_err = "null argument"; return MUSE_EINVAL; }
     *out = nullptr;
     if (cfg->abi_version != MUSE_B200_ABI_VERSION) { g_create_err = "ABI version mismatch"; return MUSE_EINVAL; }
-    if (cfg->family != MUSE_FAMILY_FUNNEL && cfg->family != MUSE_FAMILY_HIERGAUSS && cfg->family != MUSE_FAMILY_CORRGAUSS) {
-        g_create_err = "model outside the registered families (funnel, hiergauss, corrgauss); "
+    if (cfg->family != MUSE_FAMILY_FUNNEL && cfg->family != MUSE_FAMILY_HIERGAUSS && cfg->family != MUSE_FAMILY_CORRGAUSS &&
+        cfg->family != MUSE_FAMILY_TWOLAYER) {
+        g_create_err = "model outside the registered families (funnel, hiergauss, corrgauss, twolayer); "
                        "Turing/Soss-defined models are not supported by the B200 backend";
         return MUSE_EUNSUPPORTED;
     }
@@ -305,8 +306,9 @@ int muse_b200_create(const muse_cfg* cfg, muse_handle** out) {
         CREATE_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         h->own_stream = true;
     }
-    if (cfg->family == MUSE_FAMILY_CORRGAUSS) {
-        // dense correlated Gaussian: its own state (muse_corr.cu); the isotropic kernels are not involved
+    if (cfg->family == MUSE_FAMILY_CORRGAUSS || cfg->family == MUSE_FAMILY_TWOLAYER) {
+        // anisotropic quadratic families (dense correlated Gaussian, two-layer hierarchy): the lock-step solver with its own state
+        // (muse_corr.cu); the isotropic kernels are not involved
         CREATE_TRY(cudaMalloc(&h->redo_total, sizeof(unsigned long long)));
         CREATE_TRY(cudaMemsetAsync(h->redo_total, 0, sizeof(unsigned long long), h->stream));
         const int rc = muse_corr_create(h);

@@ -18,6 +18,14 @@
 // ~1e-15 relative in the NumPy model of this scheme, tests/test_oracle.py::test_f3_lockstep_model).
 // Per round: DGEMM (2·units·d² flop, the bound) + one CTA-per-unit kernel doing the line search, the update of
 // z, g, the (dx, dg) history and the two-loop recursion for the next direction (≈ 2·m·d doubles read per unit).
+//
+// F4, the two-layer hierarchy of the Turing adapter's docstring (/root/reference/src/turing.jl:63-79; oracle/families.py TwoLayer):
+//   z ~ N(0, e^{σ/2} I_n), w ~ N(z, I_n), x ~ N(w, I_n), y ~ N(x, I_n);  parameter σ, data (x, y), latent u = (z, w), all stacked to d = 2n.
+//   −logLike = ½ [ b‖z‖² + ‖w − z‖² + ‖x − w‖² + ‖y − x‖² ] + nσ/4,  b = e^{−σ/2}
+//            = ½ ‖X − u‖² + ½ uᵀ(A − I)u + const,   X = (0, x),  A = [[b + 1, −1], [−1, 2]] ⊗ I_n  (two distinct eigenvalues)
+// — the same quadratic form with a = 1 and "P" = A − I, a 2 × 2 block per component: the lock-step solver runs unchanged (L-BFGS with
+// a live (dx, dg) history: 2 iterations, 6 evaluations per unit), the product per round is an elementwise kernel instead of the DGEMM
+// (pair_apply_kernel), and ∇σ logLike = ¼ b‖ẑ_z‖² − n/4.
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -42,6 +50,7 @@ struct WarpCtx0 {
 
 struct CorrState {
     double f, gmax;
+    double cst;          // F4: ½‖y − x‖² of the unit's data (constant in u, part of f)
     double rho[kMaxM], dxdg[kMaxM], dgdg[kMaxM];
     int iter, pseudo, fg, counter_f, status, active, redo, pad;
 };
@@ -57,6 +66,8 @@ struct CorrBatch {
 
 struct CorrLaunch {
     int d, ld, m, max_iters;
+    int family, n;                       // MUSE_FAMILY_CORRGAUSS | MUSE_FAMILY_TWOLAYER; n = d/2 (F4: components per layer)
+    double binv;                         // F4: b = e^{−σ/2} at θ_eval (a = 1)
     double a, half_cst, atol, dhalf;     // dhalf = d/2
     CorrBatch b;
     int row0, nrows;                     // rows [row0, row0 + nrows) take part in this pass
@@ -118,6 +129,18 @@ __global__ void __launch_bounds__(256) corr_symv_kernel(const double* __restrict
     if (lane == 0) y[j] = acc;
 }
 
+// F4: Q = V·(A − I), a 2 × 2 block per component — q_z = b·v_z − v_w, q_w = v_w − v_z — for rows [row0, row0 + nrows)
+__global__ void __launch_bounds__(256) pair_apply_kernel(const double* __restrict__ V, double* __restrict__ Q, int row0, int n, int ld, double b) {
+    const size_t off = (size_t)(row0 + blockIdx.y) * ld;
+    const double* v = V + off;
+    double* q = Q + off;
+    for (int j = blockIdx.x * 256 + threadIdx.x; j < n; j += gridDim.x * 256) {
+        const double vz = v[j], vw = v[n + j];
+        q[j] = fma(b, vz, -vw);
+        q[n + j] = vw - vz;
+    }
+}
+
 // K values at once: slot k is a max if bit k of MAXMASK is set, else a sum (fixed tree: lane butterfly, warps in order)
 template <int K, unsigned MAXMASK>
 __device__ __forceinline__ void block_reduce(double (&v)[K], double (*red)[4]) {
@@ -159,6 +182,37 @@ __global__ void __launch_bounds__(kCT) corr_init_kernel(const CorrLaunch L) {
     const double* w = L.W + (size_t)draw * L.ld;
     const double* nu = L.nu + (size_t)draw * L.ld;
     const int sk = (data && L.start_kind == kStartTruth) ? kStartZero : L.start_kind;
+    if (L.family == MUSE_FAMILY_TWOLAYER) {
+        // W rows hold ξ = (ξ_z, ξ_w), ν rows (ν_x, ν_y), xdat = (x, y); the row of the x array is X = (0, x)
+        __shared__ double red4[kCT / 32];
+        const int n = L.n;
+        double c = 0.0;
+        for (int j = threadIdx.x; j < L.ld; j += kCT) {
+            double xv = 0.0, zt = 0.0;
+            if (j < n) {
+                if (!data) zt = sig * w[j];                                   // z = e^{σ/4} ξ_z
+            } else if (j < L.d) {
+                const int i = j - n;
+                double xx, yy;
+                if (data) { xx = L.xdat[i]; yy = L.xdat[j]; }
+                else {
+                    zt = sig * w[i] + w[j];                                   // w = z + ξ_w
+                    xx = zt + nu[i];                                          // x = w + ν_x
+                    yy = xx + nu[j];                                          // y = x + ν_y
+                }
+                xv = xx;
+                const double r3 = yy - xx;
+                c = fma(r3, r3, c);
+            }
+            x[j] = xv;
+            if (sk == kStartZero) z[j] = 0.0;
+            else if (sk == kStartTruth) z[j] = zt;
+            else if (sk == kStartShared || sk == kStartSharedKeep) z[j] = j < L.d ? L.zshared[j] : 0.0;
+        }
+        c = block_sum(c, red4);
+        if (threadIdx.x == 0) L.b.st[r].cst = 0.5 * c;
+        return;
+    }
     for (int j = threadIdx.x; j < L.ld; j += kCT) {
         const bool in = j < L.d;
         double xv = 0.0, zt = 0.0;
@@ -197,6 +251,7 @@ __global__ void __launch_bounds__(kCT) corr_start_kernel(const CorrLaunch L) {
     if (threadIdx.x == 0) {
         CorrState& st = L.b.st[r];
         st.f = fma(0.5, fma(L.a, zq, rr), L.half_cst);
+        if (L.family == MUSE_FAMILY_TWOLAYER) st.f += st.cst;
         st.gmax = gm;
         st.iter = 0;
         st.pseudo = 0;
@@ -382,12 +437,17 @@ __global__ void __launch_bounds__(kCT) corr_score_kernel(const CorrLaunch L) {
     // accepted step, the objective being quadratic), so a·Pẑ = g − ẑ + x — one DGEMM per pass less than "Q = Ẑ·P, then ẑ·Q"
     const double *z = L.b.z + off, *g = L.b.g + off, *x = L.b.x + off;
     double zq = 0;
-    for (int j = threadIdx.x; j < L.d; j += kCT) zq = fma(z[j], g[j] - z[j] + x[j], zq);
+    if (L.family == MUSE_FAMILY_TWOLAYER) {
+        for (int j = threadIdx.x; j < L.n; j += kCT) zq = fma(z[j], z[j], zq);          // ‖ẑ_z‖²
+    } else {
+        for (int j = threadIdx.x; j < L.d; j += kCT) zq = fma(z[j], g[j] - z[j] + x[j], zq);
+    }
     zq = block_sum(zq, red);
     if (threadIdx.x == 0) {
         const CorrState& st = L.b.st[r];
         const int item = blockIdx.x;
-        L.g_out[item] = 0.5 * zq - L.dhalf;                    // ∇θ logLike = ½ e^{−θ} zᵀPz − d/2,  e^{−θ}·Pz = g − z + x
+        if (L.family == MUSE_FAMILY_TWOLAYER) L.g_out[item] = 0.25 * L.binv * zq - 0.25 * L.n;      // ∇σ logLike = ¼ e^{−σ/2}‖ẑ_z‖² − n/4
+        else L.g_out[item] = 0.5 * zq - L.dhalf;               // ∇θ logLike = ½ e^{−θ} zᵀPz − d/2,  e^{−θ}·Pz = g − z + x
         L.gnorm_out[item] = st.gmax;
         L.f_out[item] = st.f;
         L.iters_out[item] = st.iter;
@@ -498,6 +558,7 @@ struct muse_corr_ctx {
     double *W = nullptr, *nu = nullptr, *tmp = nullptr;
     double *W_h = nullptr, *nu_h = nullptr;
     double *xdat = nullptr, *z0user = nullptr;
+    double binv = 1.0;                // F4: e^{−σ/2} of the pass under way (pair_apply_kernel)
     bool have_W = false, have_W_h = false;
     CorrBatch main{}, fd{}, fid{};
     int* active = nullptr;
@@ -547,6 +608,14 @@ int alloc_batch(muse_handle* h, CorrBatch& b, int rows) {
 // unit (row 0 of the main batch) has that one row done by the symmetric matrix-vector kernel.
 int gemm_rows(muse_handle* h, const CorrBatch& b, const double* V, int row0, int nrows, bool split_first_row) {
     muse_corr_ctx* c = h->corr;
+    if (h->cfg.family == MUSE_FAMILY_TWOLAYER) {
+        const int n = h->cfg.d / 2;
+        dim3 grid((unsigned)std::min((n + 255) / 256, 64), (unsigned)nrows);
+        pair_apply_kernel<<<grid, 256, 0, h->stream>>>(V, b.q, row0, n, c->ld, c->binv);
+        CORR_TRY(h, cudaGetLastError());
+        h->acc.launches += 1;
+        return MUSE_OK;
+    }
     if (split_first_row && nrows > 1) {
         corr_symv_kernel<<<(c->ld + 7) / 8, 256, 0, h->stream>>>(c->P, V + (size_t)row0 * c->ld, b.q + (size_t)row0 * c->ld, c->ld);
         CORR_TRY(h, cudaGetLastError());
@@ -568,6 +637,9 @@ int corr_solve(muse_handle* h, CorrBatch& b, CorrLaunch& L) {
     muse_corr_ctx* c = h->corr;
     L.d = h->cfg.d;
     L.ld = c->ld;
+    L.family = h->cfg.family;
+    L.n = h->cfg.d / 2;
+    c->binv = L.binv;
     L.m = h->cfg.lbfgs_m;
     L.max_iters = h->cfg.max_iters;
     L.dhalf = 0.5 * h->cfg.d;
@@ -628,7 +700,9 @@ int corr_solve(muse_handle* h, CorrBatch& b, CorrLaunch& L) {
 
 int muse_corr_create(muse_handle* h) {
     const muse_cfg& cfg = h->cfg;
-    if (!cfg.P || !cfg.L) { h->err = "corrgauss needs cfg.P = Σ₀⁻¹ and cfg.L = chol(Σ₀) (d × d, row-major)"; return MUSE_EINVAL; }
+    const bool pairf = cfg.family == MUSE_FAMILY_TWOLAYER;
+    if (!pairf && (!cfg.P || !cfg.L)) { h->err = "corrgauss needs cfg.P = Σ₀⁻¹ and cfg.L = chol(Σ₀) (d × d, row-major)"; return MUSE_EINVAL; }
+    if (pairf && (cfg.d & 1)) { h->err = "twolayer: d = 2n (latent (z, w) and data (x, y) stacked) must be even"; return MUSE_EINVAL; }
     muse_corr_ctx* c = new (std::nothrow) muse_corr_ctx();
     if (!c) return MUSE_ENOMEM;
     h->corr = c;
@@ -639,12 +713,14 @@ int muse_corr_create(muse_handle* h) {
     c->h_rows = cfg.nsims_h;
     c->h_pad = round_up_i(cfg.nsims_h > 0 ? cfg.nsims_h : 1, 128);
     const size_t ld = c->ld, mat = ld * ld * sizeof(double), B = sizeof(double);
-    CORR_TRY(h, cudaMalloc(&c->P, mat));
-    CORR_TRY(h, cudaMalloc(&c->Lt, mat));
-    CORR_TRY(h, cudaMemsetAsync(c->P, 0, mat, h->stream));
-    CORR_TRY(h, cudaMemsetAsync(c->Lt, 0, mat, h->stream));
-    CORR_TRY(h, cudaMemcpy2DAsync(c->P, ld * B, cfg.P, (size_t)d * B, (size_t)d * B, d, cudaMemcpyHostToDevice, h->stream));
-    CORR_TRY(h, cudaMemcpy2DAsync(c->Lt, ld * B, cfg.L, (size_t)d * B, (size_t)d * B, d, cudaMemcpyHostToDevice, h->stream));
+    if (!pairf) {
+        CORR_TRY(h, cudaMalloc(&c->P, mat));
+        CORR_TRY(h, cudaMalloc(&c->Lt, mat));
+        CORR_TRY(h, cudaMemsetAsync(c->P, 0, mat, h->stream));
+        CORR_TRY(h, cudaMemsetAsync(c->Lt, 0, mat, h->stream));
+        CORR_TRY(h, cudaMemcpy2DAsync(c->P, ld * B, cfg.P, (size_t)d * B, (size_t)d * B, d, cudaMemcpyHostToDevice, h->stream));
+        CORR_TRY(h, cudaMemcpy2DAsync(c->Lt, ld * B, cfg.L, (size_t)d * B, (size_t)d * B, d, cudaMemcpyHostToDevice, h->stream));
+    }
     const size_t dr = (size_t)c->draw_pad * ld * B;
     CORR_TRY(h, cudaMalloc(&c->W, dr));
     CORR_TRY(h, cudaMalloc(&c->nu, dr));
@@ -684,6 +760,10 @@ void muse_corr_destroy(muse_handle* h) {
 // ξ rows (host or already on the device in c->tmp) → W = ξ·Lᵀ
 static int corr_make_W(muse_handle* h, double* Wdst, int pad_rows) {
     muse_corr_ctx* c = h->corr;
+    if (h->cfg.family == MUSE_FAMILY_TWOLAYER) {      // no mixing matrix: the rows are the latent normals themselves
+        CORR_TRY(h, cudaMemcpyAsync(Wdst, c->tmp, (size_t)pad_rows * c->ld * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+        return MUSE_OK;
+    }
     CORR_TRY(h, launch_dgemm(c->tmp, c->Lt, Wdst, pad_rows, c->ld, c->ld, c->ld, c->ld, c->ld, h->stream));
     h->acc.launches += 1;
     return MUSE_OK;
@@ -744,15 +824,30 @@ int muse_corr_seed_draws(muse_handle* h, uint64_t seed) {
     return MUSE_OK;
 }
 
+// θ-dependent constants of a pass: evaluation point (a, b, the constant of f) and the scale of the simulated latent
+static void corr_eval_consts(const muse_handle* h, double theta_eval, CorrLaunch& L) {
+    if (h->cfg.family == MUSE_FAMILY_TWOLAYER) {
+        L.a = 1.0;
+        L.binv = std::exp(-0.5 * theta_eval);
+        L.half_cst = 0.25 * (h->cfg.d / 2) * theta_eval;
+    } else {
+        L.a = std::exp(-theta_eval);
+        L.binv = 1.0;
+        L.half_cst = 0.5 * h->cfg.d * theta_eval;
+    }
+}
+static double corr_sim_scale(const muse_handle* h, double theta_sim) {
+    return std::exp((h->cfg.family == MUSE_FAMILY_TWOLAYER ? 0.25 : 0.5) * theta_sim);
+}
+
 int muse_corr_map_score(muse_handle* h, const double* theta_sim, const double* theta_eval, double atol, int include_data,
                         int warm_start, int first_sim, int count) {
     muse_corr_ctx* c = h->corr;
     if (include_data && first_sim != 0) { h->err = "corrgauss: include_data needs first_sim = 0"; return MUSE_EINVAL; }
     CorrLaunch L{};
-    L.a = std::exp(-theta_eval[0]);
-    L.half_cst = 0.5 * h->cfg.d * theta_eval[0];
+    corr_eval_consts(h, theta_eval[0], L);
     L.atol = atol;
-    L.sig[0] = L.sig[1] = std::exp(0.5 * theta_sim[0]);
+    L.sig[0] = L.sig[1] = corr_sim_scale(h, theta_sim[0]);
     L.mode = 0;
     L.data_row = include_data ? 0 : -1;
     L.row0 = include_data ? 0 : 1 + first_sim;
@@ -772,10 +867,9 @@ int muse_corr_fd_launch(muse_handle* h, const double* theta0, const double* th_p
     muse_corr_ctx* c = h->corr;
     const bool hshard = h->cfg.nsims_h > 0;
     CorrLaunch F{};
-    F.a = std::exp(-theta0[0]);
-    F.half_cst = 0.5 * h->cfg.d * theta0[0];
+    corr_eval_consts(h, theta0[0], F);
     F.atol = atol;
-    F.sig[0] = F.sig[1] = std::exp(0.5 * theta0[0]);
+    F.sig[0] = F.sig[1] = corr_sim_scale(h, theta0[0]);
     F.mode = 0;
     F.data_row = -1;
     F.row0 = 0;
@@ -790,9 +884,9 @@ int muse_corr_fd_launch(muse_handle* h, const double* theta0, const double* th_p
     rc = alloc_batch(h, c->fd, 2 * nsims_H);
     if (rc != MUSE_OK) return rc;
     CorrLaunch L{};
-    L.a = F.a; L.half_cst = F.half_cst; L.atol = atol;
-    L.sig[0] = std::exp(0.5 * th_pts[0]);      // the "−" and "+" sample points of the single column
-    L.sig[1] = std::exp(0.5 * th_pts[1]);
+    L.a = F.a; L.binv = F.binv; L.half_cst = F.half_cst; L.atol = atol;
+    L.sig[0] = corr_sim_scale(h, th_pts[0]);      // the "−" and "+" sample points of the single column
+    L.sig[1] = corr_sim_scale(h, th_pts[1]);
     L.mode = 1;
     L.data_row = -1;
     L.row0 = 0;
@@ -820,6 +914,10 @@ bool muse_corr_have_draws(muse_handle* h, bool hshard) { return hshard ? h->corr
 int muse_corr_implicit_h(muse_handle* h, const double* theta0, int nsims_H, int start, int cg_maxiter, double* Hs_out, int32_t* cg_iters_out,
                          int32_t* status_out) {
     muse_corr_ctx* c = h->corr;
+    if (h->cfg.family == MUSE_FAMILY_TWOLAYER) {
+        h->err = "twolayer: get_H!(implicit_diff = true) is not built for this family; use the finite-difference get_H!";
+        return MUSE_EUNSUPPORTED;
+    }
     // (1) MAPs of the H sims; the pass leaves ẑ, x and g = ∇f(ẑ), hence a·Pẑ = g − ẑ + x
     h->pass_kind = MUSE_PASS_COLD;
     int rc = muse_corr_map_score(h, theta0, theta0, 1e-1, 0, start, 0, nsims_H);

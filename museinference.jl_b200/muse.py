@@ -182,7 +182,7 @@ def _diagm(v):
 def _check_problem(prob):
     if not isinstance(prob, SimpleMuseProblem):
         raise MuseBackendError(-5, f"{type(prob).__name__} is not supported by the B200 backend: only "
-                                   "SimpleMuseProblem over a registered family (funnel, hiergauss, corrgauss); "
+                                   "SimpleMuseProblem over a registered family (funnel, hiergauss, corrgauss, twolayer); "
                                    "Turing/Soss-defined models raise, there is no CPU fallback")
 
 
@@ -269,7 +269,7 @@ def muse_(result: MuseResult, prob: AbstractMuseProblem, theta0=None, **kwargs):
                 pool.bind(be)
             counts = block_partition(nsims, pool.world)[1]
         mode = DEFAULT_FUSED_DRIVER if fused_driver is True else fused_driver
-        device_loop = (mode == "device" and hasattr(be, "muse_solve") and prob.family != "corrgauss" and maxsteps <= 64
+        device_loop = (mode == "device" and hasattr(be, "muse_solve") and prob.family not in ("corrgauss", "twolayer") and maxsteps <= 64
                        and pool.world <= 16)      # the limits of csrc/muse_outer.cu (history rows, rank table); else the host loop
         cdev = None
         if device_loop:

@@ -90,8 +90,8 @@ class SimpleMuseProblem(AbstractMuseProblem):
 
     Parameters
     ----------
-    x        observed data, length d            (``prob.x``, src/simple.jl:5)
-    family   "funnel" | "hiergauss" | "corrgauss"
+    x        observed data, length d            (``prob.x``, src/simple.jl:5); "twolayer": the stacked (x, y), d = 2n
+    family   "funnel" | "hiergauss" | "corrgauss" | "twolayer" (the toy hierarchy of src/turing.jl:63-79, parameter σ)
     prior    object with ``logp/grad/hess`` (``logPriorθ``); default flat
     group, cluster   solver geometry overrides (0 = auto), see DESIGN.md §3
     stream   raw cudaStream_t to launch on (e.g. ``torch.cuda.current_stream().cuda_stream``)

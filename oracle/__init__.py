@@ -36,7 +36,7 @@ split_rng never advances the master, src/util.jl:87-92, so sim k sees the same b
 at every θ).
 """
 
-from .families import Funnel, HierGauss, CorrGauss, TransformedFamily, make_family  # noqa: F401
+from .families import Funnel, HierGauss, CorrGauss, TwoLayer, TransformedFamily, make_family  # noqa: F401
 from .hagerzhang import HagerZhang, LineSearchException  # noqa: F401
 from .lbfgs import lbfgs_minimize, OptimResult  # noqa: F401
 from .muse import (  # noqa: F401

@@ -10,6 +10,7 @@ differences in tests/test_oracle_families.py.
 F1  Neal's funnel             /root/reference/src/simple.jl:58-76, docs/src/index.md:154-168
 F2  hierarchical Gaussian     SURVEY.md §8(a) row F2 (BASELINE.json config 4; not in the reference)
 F3  dense correlated Gaussian SURVEY.md §8(a) row F3 (BASELINE.json config 5; not in the reference)
+F4  two-layer hierarchy       /root/reference/src/turing.jl:63-79 (the toy model of the Turing adapter's docstring)
 
 Sampling is expressed on *base normals* (ξ, ν) so that common-random-number semantics
 (src/util.jl:85-92) are explicit: the latent draws come first, then the noise draws
@@ -185,6 +186,87 @@ class CorrGauss:
         return -(w + np.exp(-th) * (self.P @ w))
 
 
+class TwoLayer:
+    """F4: the toy hierarchy of the Turing adapter's docstring (/root/reference/src/turing.jl:63-79)
+
+        z ~ MvNormal(zeros(n), exp(σ/2)*I)      (covariance e^{σ/2} I: z = e^{σ/4} ξ_z)
+        w ~ MvNormal(z, I);  x ~ MvNormal(w, I);  y ~ MvNormal(x, I)
+
+    with σ the parameter, (x, y) the data and (z, w) the latent space, as in the docstring (`model | (;sim.x, sim.y)`).  The
+    docstring's second parameter θ ~ Normal(0, σ) has no descendants: it enters the joint density only through its own prior
+    factor, identical for the data and every simulation, so it cancels out of every MUSE quantity and is not carried here.
+    Everything is stacked to one length d = 2n: latent u = (z, w), data (x, y), latent normals ξ = (ξ_z, ξ_w), noise normals
+    ν = (ν_x, ν_y).  logLike follows the funnel's convention of dropping the 2π constants (src/simple.jl:66-68):
+
+        logLike = −½ [ e^{−σ/2} Σz² + Σ(w − z)² + Σ(x − w)² + Σ(y − x)² + n σ/2 ]
+
+    The Hessian in u is [[e^{−σ/2} + 1, −1], [−1, 2]] ⊗ I_n: two distinct eigenvalues, not a multiple of the identity — the
+    default ẑ_at_θ needs several L-BFGS iterations with a live (dx, dg) history."""
+
+    name = "twolayer"
+    family_id = 4
+    ntheta = 1
+
+    def __init__(self, d: int):
+        self.d = int(d)
+        if self.d % 2:
+            raise ValueError("twolayer: d = 2n (latent (z, w) and data (x, y) stacked) must be even")
+        self.n = self.d // 2
+
+    def sample(self, theta, xi, nu):
+        s = float(np.asarray(theta).reshape(-1)[0])
+        n = self.n
+        z = np.exp(0.25 * s) * xi[:n]
+        w = z + xi[n:]
+        x = w + nu[:n]
+        y = x + nu[n:]
+        return np.concatenate([x, y]), np.concatenate([z, w])
+
+    def neg_loglike(self, x, z, theta):
+        return self.neg_loglike_and_grad(x, z, theta)[0]
+
+    def neg_loglike_and_grad(self, x, z, theta):
+        s = float(np.asarray(theta).reshape(-1)[0])
+        n = self.n
+        b = np.exp(-0.5 * s)
+        zz, ww, xx, yy = z[:n], z[n:], x[:n], x[n:]
+        r1, r2, r3 = ww - zz, xx - ww, yy - xx
+        f = 0.5 * (b * np.dot(zz, zz) + np.dot(r1, r1) + np.dot(r2, r2) + np.dot(r3, r3) + 0.5 * n * s)
+        g = np.concatenate([b * zz - r1, r1 - r2])
+        return f, g
+
+    # ∇σ logLike = ¼ e^{−σ/2} Σ z² − n/4
+    def score(self, x, z, theta):
+        s = float(np.asarray(theta).reshape(-1)[0])
+        zz = z[:self.n]
+        return np.array([0.25 * np.exp(-0.5 * s) * np.dot(zz, zz) - 0.25 * self.n])
+
+    def exact_map(self, x, theta):
+        s = float(np.asarray(theta).reshape(-1)[0])
+        b = np.exp(-0.5 * s)
+        xx = x[:self.n]
+        return np.concatenate([xx / (2.0 * b + 1.0), (b + 1.0) * xx / (2.0 * b + 1.0)])
+
+    def dgradz_dtheta(self, x, z, theta):          # ∇u logLike = (−b z + (w − z), −(w − z) + (x − w)):  ∂σ → (½ b z, 0)
+        s = float(np.asarray(theta).reshape(-1)[0])
+        out = np.zeros((self.d, 1))
+        out[:self.n, 0] = 0.5 * np.exp(-0.5 * s) * z[:self.n]
+        return out
+
+    def dx_dtheta_sim(self, theta, xi, nu):
+        """∂θ_sim of ∇u logLike at fixed u: only the w-half sees the data (coefficient 1 on x), x = e^{σ/4} ξ_z + ξ_w + ν_x."""
+        s = float(np.asarray(theta).reshape(-1)[0])
+        out = np.zeros((self.d, 1))
+        out[self.n:, 0] = 0.25 * np.exp(0.25 * s) * xi[:self.n]
+        return out
+
+    def hess_z_apply(self, z, theta, w):
+        s = float(np.asarray(theta).reshape(-1)[0])
+        n = self.n
+        b = np.exp(-0.5 * s)
+        return -np.concatenate([(b + 1.0) * w[:n] - w[n:], 2.0 * w[n:] - w[:n]])
+
+
 class TransformedFamily:
     """A registered family whose user-facing θ has positive components: θ_user[i] = exp(θ_base[i]) where
     ``kinds[i] == "log"``.  Supplies the pair the reference's interface asks of a problem with a bounded θ
@@ -249,4 +331,6 @@ def make_family(name: str, d: int, **consts):
         return HierGauss(d)
     if name == "corrgauss":
         return CorrGauss(d, consts["P"], consts["L"])
+    if name == "twolayer":
+        return TwoLayer(d)
     raise ValueError(f"unknown family {name!r}")

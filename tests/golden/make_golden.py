@@ -23,12 +23,16 @@ CASES = [
     # θ = (μ, σ) with σ > 0: transform_θ = (μ, log σ) (oracle/families.py TransformedFamily), θ₀ = (0.5, e^0.3)
     dict(name="hiergauss_sigma_d200_n30", family="hiergauss", d=200, nsims=30, seed=2468, prior=False, atol=1e-2,
          transform=["identity", "log"]),
+    # the toy hierarchy of the Turing adapter's docstring (src/turing.jl:63-79) at its own size: n = 512 components per layer
+    dict(name="twolayer_d1024_n60", family="twolayer", d=1024, nsims=60, seed=1357, prior=True, atol=1e-2),
 ]
 
 
 def main():
     out_dir = os.path.dirname(os.path.abspath(__file__))
     for c in CASES:
+        if len(sys.argv) > 1 and c["name"] not in sys.argv[1:]:
+            continue
         prior = O.NormalPrior(0, 3) if c["prior"] else None
         prob, fam, draws, xd = oracle_problem(c["family"], c["d"], c["nsims"], seed=c["seed"], prior=prior)
         th0 = theta_start(c["family"])

@@ -20,10 +20,14 @@ def make_family(name, d):
 
 
 def theta_true(name):
+    if name == "twolayer":
+        return np.array([0.3])                   # the docstring model draws σ ~ U(0, 1)
     return np.array([0.0, 0.0]) if name == "hiergauss" else np.array([0.0])
 
 
 def theta_start(name):
+    if name == "twolayer":
+        return np.array([0.5])                   # muse(prob, (σ=0.5, θ=0)), src/turing.jl:78
     return np.array([0.5, 0.3]) if name == "hiergauss" else np.array([1.0])
 
 

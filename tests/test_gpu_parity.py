@@ -322,6 +322,102 @@ def test_corrgauss_full_muse_matches_oracle():
         prob.close()
 
 
+# ------------------------------------------------------------------------------- F4: the two-layer hierarchy of src/turing.jl:63-79
+@pytest.mark.parametrize("d,nsims", [(1024, 12), (300, 7), (9000, 5)])
+def test_twolayer_map_score_matches_oracle(d, nsims):
+    """The docstring toy model of the Turing adapter (latent (z, w), data (x, y), parameter σ) on the lock-step solver with the
+    elementwise 2 × 2-block product in place of the DGEMM (csrc/muse_corr.cu) against the oracle's L-BFGS + Hager–Zhang: the
+    same iteration and evaluation counts — 2 and 6: a live (dx, dg) history on every unit — ẑ, ‖∇f‖∞ and the score."""
+    import museinference_jl_b200 as m
+    name, atol = "twolayer", 1e-2
+    fam, draws, xd = make_inputs(name, d, nsims)
+    prob = O.OracleProblem(fam, xd, draws)
+    be = m.B200Backend(name, d, nsims)
+    be.set_data(xd)
+    be.set_draws(draws.xi, draws.nu, draws.xi_master, draws.nu_master)
+    th0 = np.array([0.5])
+    out = be.map_score(th0, th0, atol, include_data=True, warm_start=0)
+    zs = be.get_maps(0, nsims + 1)
+    ref_z = []
+    for u in range(nsims + 1):
+        x = xd if u == 0 else prob.sample_x_z(u - 1, th0)[0]
+        zh, g, soln = O.map_score_unit(prob, x, np.zeros(d), th0, atol)
+        ref_z.append(zh)
+        assert out["iters"][u] == soln.iterations == 2 and out["fg_evals"][u] == soln.f_calls == 6, (u, out["iters"][u], out["fg_evals"][u])
+        np.testing.assert_allclose(zs[u], zh, rtol=RTOL_SIM, atol=1e-11)
+        np.testing.assert_allclose(zs[u], fam.exact_map(x, th0), rtol=1e-9, atol=1e-11)
+        np.testing.assert_allclose(out["g"][u], g, rtol=RTOL_SIM)
+        assert out["status"][u] == 0 and out["gnorm"][u] <= atol
+    # warm pass at a moved σ (start = the unit's own ẑ), then the simulated latent as the start on a sub-range (get_J!)
+    th1 = th0 - 0.35
+    out = be.map_score(th1, th1, atol, include_data=True, warm_start=1)
+    zs = be.get_maps(0, nsims + 1)
+    for u in range(nsims + 1):
+        x = xd if u == 0 else prob.sample_x_z(u - 1, th1)[0]
+        zh, g, soln = O.map_score_unit(prob, x, ref_z[u], th1, atol)
+        assert out["iters"][u] == soln.iterations and out["fg_evals"][u] == soln.f_calls
+        np.testing.assert_allclose(zs[u], zh, rtol=RTOL_SIM, atol=1e-11)
+        np.testing.assert_allclose(out["g"][u], g, rtol=RTOL_SIM)
+    out = be.map_score(th1, th1, atol, include_data=False, warm_start=2, first_sim=2, count=3)
+    for i in range(3):
+        x, z = prob.sample_x_z(2 + i, th1)
+        zh, g, soln = O.map_score_unit(prob, x, z, th1, atol)
+        assert out["iters"][i] == soln.iterations and out["fg_evals"][i] == soln.f_calls
+        np.testing.assert_allclose(out["g"][i], g, rtol=RTOL_SIM)
+    be.close()
+    with pytest.raises(m.MuseBackendError):
+        m.B200Backend(name, 11, 4)                          # d = 2n must be even
+
+
+def test_twolayer_full_muse_matches_oracle_and_the_golden_fixture():
+    """muse(prob, σ₀ = 0.5; get_covariance = true) of the docstring model at its own size (n = 512 per layer): in-library host loop
+    and line-by-line Python loop against the oracle and the committed fixture; device-generated draws: partition invariance."""
+    import json
+    import os
+    import museinference_jl_b200 as m
+    with open(os.path.join(os.path.dirname(__file__), "golden", "twolayer_d1024_n60.json")) as fh:
+        fix = json.load(fh)
+    c = fix["case"]
+    name, d, nsims = c["family"], c["d"], c["nsims"]
+    oprob, fam, draws, xd = oracle_problem(name, d, nsims, seed=c["seed"], prior=O.NormalPrior(0, 3))
+    ref = O.muse(oprob, fix["theta0"], nsims=nsims, get_covariance=True)
+    rng = m.BaseDraws(draws.xi, draws.nu, draws.xi_master, draws.nu_master)
+    for fused in (True, False, "device"):                  # "device": this family keeps the host loop, like corrgauss
+        prob = m.SimpleMuseProblem(xd, name, m.NormalPrior(0, 3))
+        res = m.muse(prob, fix["theta0"], rng=rng, nsims=nsims, get_covariance=True, fused_driver=fused)
+        assert len(res.history) == len(ref.history) == fix["n_outer"]
+        for want in (ref.theta, fix["theta"]):
+            np.testing.assert_allclose(res.theta, want, rtol=RTOL_EST)
+        np.testing.assert_allclose(res.J, fix["J"], rtol=RTOL_EST)
+        np.testing.assert_allclose(res.H, fix["H"], rtol=RTOL_EST)
+        np.testing.assert_allclose(res.Sigma, fix["Sigma"], rtol=10 * RTOL_EST)
+        np.testing.assert_allclose(np.array(res.gs), np.array(ref.gs), rtol=RTOL_SIM)
+        assert (res.history[0]["z_history_sims"]["iters"] == fix["iter1"]["iters"]).all()
+        assert (res.history[0]["z_history_sims"]["fg_evals"] == fix["iter1"]["fg"]).all()
+        prob.close()
+    # get_J! / get_H! on their own, and the implicit-diff branch is refused for this family
+    prob = m.SimpleMuseProblem(xd, name, m.NormalPrior(0, 3))
+    r2, o2 = m.MuseResult(theta=np.array(fix["theta"])), O.MuseResult(theta=np.array(fix["theta"]))
+    getattr(m, "get_J!")(r2, prob, rng=rng, nsims=20)
+    O.get_J_bang(o2, oprob, nsims=20)
+    np.testing.assert_allclose(r2.J, o2.J, rtol=RTOL_EST)
+    getattr(m, "get_H!")(r2, prob, rng=rng, nsims=6)
+    O.get_H_bang(o2, oprob, nsims=6)
+    np.testing.assert_allclose(r2.H, o2.H, rtol=RTOL_EST)
+    with pytest.raises(m.MuseBackendError):
+        getattr(m, "get_H!")(m.MuseResult(theta=np.array([0.2])), prob, rng=rng, nsims=3, implicit_diff=True)
+    prob.close()
+    # device Philox draws: a handle owning sims [20, 35) reproduces those rows of the whole solve bit for bit
+    full = m.B200Backend(name, d, 50); full.set_data(xd); full.seed_draws(4242)
+    part = m.B200Backend(name, d, 15, sim_offset=20); part.set_data(xd); part.seed_draws(4242)
+    th = np.array([0.4])
+    a = full.map_score(th, th, 1e-2, include_data=False, warm_start=0)
+    b = part.map_score(th, th, 1e-2, include_data=False, warm_start=0)
+    np.testing.assert_array_equal(a["g"][20:35], b["g"])
+    np.testing.assert_array_equal(a["iters"][20:35], b["iters"])
+    full.close(); part.close()
+
+
 def test_full_size_c3_closed_form_and_partition_invariance():
     """BASELINE configs[2] at full size (funnel, d = 65 536, nsims = 2 048, device Philox draws): every per-sim score
     against the closed form g = ½ e^{-θ} s² ‖x‖² − d/2 with x = e^{θ/2} ξ + ν, iteration counts,

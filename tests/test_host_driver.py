@@ -20,7 +20,7 @@ def _pair(name, d, nsims, prior=False, seed=1234):
     return m, oprob, prob, rng
 
 
-@pytest.mark.parametrize("name,d,nsims,prior", [("funnel", 128, 40, True), ("hiergauss", 200, 30, False)])
+@pytest.mark.parametrize("name,d,nsims,prior", [("funnel", 128, 40, True), ("hiergauss", 200, 30, False), ("twolayer", 96, 30, True)])
 def test_muse_driver_matches_oracle(name, d, nsims, prior):
     m, oprob, prob, rng = _pair(name, d, nsims, prior)
     ref = O.muse(oprob, theta_start(name), nsims=nsims, get_covariance=True)
@@ -147,7 +147,7 @@ def test_keywords_of_get_J_and_get_H_covariance_method_fdm_and_user_start():
 def test_implicit_diff_get_H_host_path_and_oracle_against_finite_differences():
     """get_H!(implicit_diff = true) (src/muse.jl:335-405): the host driver's branch against the oracle's, and the oracle's
     closed-form second derivatives against central differences — the implicit-diff H must be the finite-difference H."""
-    for name, d in (("funnel", 48), ("hiergauss", 60)):
+    for name, d in (("funnel", 48), ("hiergauss", 60), ("twolayer", 40)):
         m, oprob, prob, rng = _pair(name, d, 12, False)
         fam = oprob.family
         th = theta_start(name)
@@ -155,7 +155,8 @@ def test_implicit_diff_get_H_host_path_and_oracle_against_finite_differences():
         getattr(m, "get_H!")(res, prob, rng=rng, nsims=5, implicit_diff=True, implicit_diff_cg_kwargs=dict(maxiter=50))
         O.get_H_bang(ref, oprob, nsims=5, implicit_diff=True)
         np.testing.assert_allclose(np.array(res.Hs), np.array(ref.Hs), rtol=1e-12)
-        assert res.metadata["implicit_diff_cg_hists"] == ref.metadata["implicit_diff_cg_hists"] == [[1] * fam.ntheta] * 5
+        # conjugate gradients end after as many iterations as the Hessian has distinct eigenvalues: 1 (isotropic), 2 (two-layer)
+        assert res.metadata["implicit_diff_cg_hists"] == ref.metadata["implicit_diff_cg_hists"] == [[2 if name == "twolayer" else 1] * fam.ntheta] * 5
         fd = O.MuseResult(theta=th.copy())
         O.get_H_bang(fd, oprob, nsims=5, step=np.full(fam.ntheta, 1e-3), gradz_logLike_atol=1e-10)
         np.testing.assert_allclose(ref.H, fd.H, rtol=1e-5, atol=1e-5 * np.abs(fd.H).max())
@@ -168,7 +169,8 @@ def test_implicit_diff_get_H_host_path_and_oracle_against_finite_differences():
             np.testing.assert_allclose((gz(z, th + e, x) - gz(z, th - e, x)) / 2e-6, fam.dgradz_dtheta(x, z, th)[:, n], rtol=1e-6, atol=1e-7)
             xp, _ = fam.sample(th + e, oprob.draws.xi[0], oprob.draws.nu[0])
             xm, _ = fam.sample(th - e, oprob.draws.xi[0], oprob.draws.nu[0])
-            np.testing.assert_allclose((xp - xm) / 2e-6, fam.dx_dtheta_sim(th, oprob.draws.xi[0], oprob.draws.nu[0])[:, n], rtol=1e-6, atol=1e-7)
+            # ∂θ_sim of ∇z logLike at fixed z (for F1-F3 this is ∂x/∂θ_sim itself: ∂∇z/∂x = I)
+            np.testing.assert_allclose((gz(z, th, xp) - gz(z, th, xm)) / 2e-6, fam.dx_dtheta_sim(th, oprob.draws.xi[0], oprob.draws.nu[0])[:, n], rtol=1e-6, atol=1e-7)
         w = np.cos(np.arange(d))
         np.testing.assert_allclose((gz(z + 1e-5 * w, th, x) - gz(z - 1e-5 * w, th, x)) / 2e-5, fam.hess_z_apply(z, th, w), rtol=1e-6, atol=1e-7)
     # conjugate gradients as restated: A⁻¹b on a random SPD system, iteration count bounded by the dimension

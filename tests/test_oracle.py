@@ -36,7 +36,7 @@ def _family(name, d):
     return O.make_family(name, d)
 
 
-@pytest.mark.parametrize("name", ["funnel", "hiergauss", "corrgauss"])
+@pytest.mark.parametrize("name", ["funnel", "hiergauss", "corrgauss", "twolayer"])
 def test_gradients_match_central_differences(name):
     d = 24
     fam = _family(name, d)
@@ -60,7 +60,7 @@ def test_gradients_match_central_differences(name):
         assert s[n] == pytest.approx(fd, rel=2e-7, abs=2e-7)
 
 
-@pytest.mark.parametrize("name", ["funnel", "hiergauss", "corrgauss"])
+@pytest.mark.parametrize("name", ["funnel", "hiergauss", "corrgauss", "twolayer"])
 def test_exact_map_is_stationary_and_lbfgs_reaches_it(name):
     d = 40
     fam = _family(name, d)
@@ -74,7 +74,10 @@ def test_exact_map_is_stationary_and_lbfgs_reaches_it(name):
     soln = O.lbfgs_minimize(lambda z: fam.neg_loglike_and_grad(x, z, th), np.zeros(d), g_tol=tol)
     assert soln.converged and soln.g_residual <= 10 * tol
     np.testing.assert_allclose(soln.minimizer, zstar, rtol=1e-4 if name == "corrgauss" else 1e-7, atol=1e-6 if name == "corrgauss" else 1e-9)
-    if name != "corrgauss":
+    if name == "twolayer":
+        # two distinct Hessian eigenvalues: the second iteration's two-loop recursion (one (dx, dg) pair) points at the MAP
+        assert soln.iterations == 2 and soln.f_calls == 6
+    elif name != "corrgauss":
         # isotropic Hessian: −g points at the MAP; InitialStatic(1) → bracket → secant lands exactly
         assert soln.iterations == 1 and soln.f_calls == 3
         np.testing.assert_allclose(soln.minimizer, zstar, rtol=1e-13, atol=1e-15)
@@ -229,7 +232,8 @@ def test_broyden_updates_run_and_agree_on_first_iterations():
     np.testing.assert_allclose(a.history[0]["g_like"], b.history[0]["g_like"])
 
 
-@pytest.mark.parametrize("name", ["funnel_d512_n100", "funnel_d64_n16_tight", "hiergauss_d300_n40", "hiergauss_sigma_d200_n30"])
+@pytest.mark.parametrize("name", ["funnel_d512_n100", "funnel_d64_n16_tight", "hiergauss_d300_n40", "hiergauss_sigma_d200_n30",
+                                  "twolayer_d1024_n60"])
 def test_golden_fixtures(name):
     with open(os.path.join(GOLDEN, name + ".json")) as fh:
         fix = json.load(fh)
