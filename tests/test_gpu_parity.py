@@ -3,6 +3,8 @@
 Tolerances (BASELINE.json north_star): per-sim ẑ_i and g_i within rtol 1e-8; θ̂, J, H, Σ within
 rtol 1e-6.  All FP64.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -253,6 +255,23 @@ def test_dgemm_dmma_matches_numpy():
     ref = A @ B
     np.testing.assert_allclose(Cm, ref, rtol=0, atol=1e-13 * np.abs(A).max() * np.abs(B).max() * K)
     assert lib.muse_b200_dgemm_host(dp(A), dp(B), dp(Cm), 100, N, K) != 0      # extents must be tile multiples
+
+
+def test_trimmed_draws_kernel_is_bit_identical_to_the_first_table_driven_one():
+    """philox_draws_tab2_kernel (the default: constants and table addresses held in registers, both streams of a row per iteration,
+    funnel-shift / exponent-OR integer → double steps) must produce exactly the normals of philox_draws_tab_kernel: the generator is
+    selected once per process (MUSE_DRAWS_IMPL), so each runs in its own interpreter and prints a digest of its output."""
+    import subprocess
+    import sys
+    script = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts", "draws_ab.py")
+    sha = {}
+    for impl in ("1", "2", "3"):
+        r = subprocess.run([sys.executable, script, "child"], env=dict(os.environ, MUSE_DRAWS_IMPL=impl), capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        line = r.stdout.strip().splitlines()[-1]
+        sha[impl] = line.split("sha256")[1].strip()
+        assert float(line.split("= ")[1].split(" ;")[0]) < 1e-14            # and each against the oracle's generator
+    assert sha["1"] == sha["2"] == sha["3"], sha
 
 
 # ------------------------------------------------------------------------------- F3: dense correlated Gaussian
