@@ -753,6 +753,7 @@ int muse_b200_profile_reset(muse_handle* h, int32_t enable) {
     if (!h) return MUSE_EINVAL;
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->persist_pend = false;
     for (auto& r : h->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     h->recs.clear();
     h->acc = muse_profile{};
@@ -763,6 +764,7 @@ int muse_b200_profile_reset(muse_handle* h, int32_t enable) {
 
 // fold the finished event pairs into the accumulators (stream must be idle)
 static int profile_drain(muse_handle* h) {
+    muse_persist_flush(h);
     for (auto& r : h->recs) {
         float ms = 0.f;
         CUDA_TRY(h, cudaEventElapsedTime(&ms, r.a, r.b));

@@ -111,7 +111,11 @@ struct muse_handle {
     // the whole solve in one cooperative launch (solve_persist_kernel, muse_iso_stream.cu)
     void* persist_ctl = nullptr;                         // muse::PersistCtl, device, zero between launches
     int persist_grid = -1, persist_threads = 0;          // −1: not queried yet; 0: unavailable
-    cudaEvent_t persist_ev[2] = {nullptr, nullptr};      // profiling: the launch's event pair (read right after the solve's synchronisation)
+    cudaEvent_t persist_ev[2] = {nullptr, nullptr};      // profiling: the launch's event pair, read once the launch has retired (muse_persist_flush)
+    bool persist_pend = false;                           // … an event pair not yet folded into acc
+    double persist_pend_units = 0.0, persist_pend_bytes = 0.0;
+    unsigned long long* persist_done_h = nullptr;        // pinned completion word of the launch (written by its last CTA)
+    unsigned long long persist_done_seq = 0;
     std::vector<unsigned char> persist_off_key;          // parameters with which the launch gave up (hand-backs): straight to the chain
 
     // exchange through peer-mapped memory (muse_comm.cu: muse_b200_p2p_*): this rank's region and the peers' mappings of theirs
@@ -156,6 +160,7 @@ extern "C" void muse_fd_combine_host(muse_handle* h, const double* g_h, const in
 size_t muse_outblock_bytes(const muse_handle* h, int items);
 void muse_outblock_carve(const muse_handle* h, OutBlock& ob, unsigned char* dev, unsigned char* host, int items);
 void muse_outer_release(muse_handle* h);
+void muse_persist_flush(muse_handle* h);      // folds the one-launch solve's pending event pair into the profile (waits for it if need be)
 extern "C" int  muse_comm_allgather_dev_enqueue(muse_handle* h, const double* src_dev, const int* status_dev, int ncol, const int32_t* counts, size_t* need_out);
 
 void muse_comm_release(muse_handle* h);

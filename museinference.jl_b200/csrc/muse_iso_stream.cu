@@ -1257,14 +1257,21 @@ solve_persist_kernel(const __grid_constant__ PersistParams P) {
             copy_to_host(reinterpret_cast<unsigned char*>(P.st_h), reinterpret_cast<const unsigned char*>(P.step.st), nb, 0, 1);
         }
     }
-    // the last CTA to leave clears the control block for the next launch
+    // the last CTA to leave clears the control block for the next launch — and tells the host: every CTA's stores to the host
+    // mirrors are ordered (system scope) before its exit count, so the word below is the last thing to land and the host need not wait
+    // for the launch to retire
     __syncthreads();
     if (tid == 0) {
-        __threadfence();
+        if (P.done_h) __threadfence_system(); else __threadfence();
         if (atomicAdd(&ctl->exit_count, 1) == (int)gridDim.x - 1) {
+            __threadfence();
             volatile int* w = reinterpret_cast<volatile int*>(ctl);
             for (int k = 0; k < (int)(offsetof(PersistCtl, dyn) / sizeof(int)); ++k) w[k] = 0;
             __threadfence();
+            if (P.done_h) {
+                __threadfence_system();
+                *reinterpret_cast<volatile unsigned long long*>(P.done_h) = P.done_seq;
+            }
         }
     }
 }

@@ -19,6 +19,7 @@
 // The trees are ordered by the GLOBAL sim index, and every rank of a multi-GPU job runs the identical kernel on the
 // identical gathered scores: θ stays bit-identical across ranks and for any sharding, as before.  history[i].t is the chunk's wall time divided by its iterations (no per-iteration host clock exists).
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstddef>
@@ -119,8 +120,26 @@ int outer_ensure(muse_handle* h, int units, int fd_items, size_t gall_doubles) {
 
 }  // namespace
 
+// the one-launch solve returns as soon as its completion word is in host memory; the event pair around the launch is read later —
+// at the next solve or when the profile is asked for — when the launch has long retired
+void muse_persist_flush(muse_handle* h) {
+    if (!h->persist_pend) return;
+    h->persist_pend = false;
+    float ms = 0.f;
+    cudaError_t e = cudaEventElapsedTime(&ms, h->persist_ev[0], h->persist_ev[1]);
+    if (e == cudaErrorNotReady) {
+        cudaGetLastError();
+        if (cudaEventSynchronize(h->persist_ev[1]) == cudaSuccess) e = cudaEventElapsedTime(&ms, h->persist_ev[0], h->persist_ev[1]);
+    }
+    if (e != cudaSuccess) { cudaGetLastError(); ms = 0.f; }
+    h->acc.solve_ms += ms; h->acc.solve_units += h->persist_pend_units; h->acc.solve_bytes += h->persist_pend_bytes;
+}
+
 void muse_outer_release(muse_handle* h) {
     outer_graph_release(h);
+    h->persist_pend = false;
+    cudaFreeHost(h->persist_done_h);
+    h->persist_done_h = nullptr;
     cudaFree(h->outer_arena_d);
     cudaFreeHost(h->outer_arena_h);
     cudaFreeHost(h->outer_st_stage);
@@ -404,6 +423,16 @@ extern "C" int muse_b200_muse_solve(muse_handle* h, const double* theta0, int32_
             Q.fd_d = h->outer_fd.d; Q.fd_h = h->outer_fd.hst;
             Q.fd_bytes = nh_mine > 0 && get_covariance ? muse_outblock_bytes(h, fd_items) : 0;
             Q.st_h = sh_;
+            // … and the host waits for the kernel's completion word instead of the stream (MUSE_HOSTSPIN=0: cudaStreamSynchronize)
+            static const bool spin_on = [] { const char* e = std::getenv("MUSE_HOSTSPIN"); return !e || std::atoi(e) != 0; }();
+            if (spin_on) {
+                if (!h->persist_done_h) {
+                    OUTER_TRY(h, cudaMallocHost(&h->persist_done_h, 64));
+                    *h->persist_done_h = 0ULL;
+                }
+                Q.done_h = h->persist_done_h;
+                Q.done_seq = ++h->persist_done_seq;
+            }
         }
         Q.x.nranks = 1;
         size_t x_blk = 0;
@@ -445,6 +474,7 @@ extern "C" int muse_b200_muse_solve(muse_handle* h, const double* theta0, int32_
                 OUTER_TRY(h, cudaEventCreate(&h->persist_ev[0]));
                 OUTER_TRY(h, cudaEventCreate(&h->persist_ev[1]));
             }
+            muse_persist_flush(h);                    // the pair is reused: fold the previous launch's times in first
             ea = h->persist_ev[0]; eb = h->persist_ev[1];
             OUTER_TRY(h, cudaEventRecord(ea, h->stream));
         }
@@ -466,7 +496,30 @@ extern "C" int muse_b200_muse_solve(muse_handle* h, const double* theta0, int32_
             if (multi)
                 OUTER_TRY(h, cudaMemcpyAsync(h->p2p_host, Q.x.gall[h->comm_rank][0], (size_t)3 * x_blk * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         }
-        OUTER_TRY(h, cudaStreamSynchronize(h->stream));
+        bool spun = false;
+        if (Q.done_h) {
+            // the last CTA stores done_seq after every host mirror is complete: results are readable ≈ 15 µs before the stream reports
+            // idle.  The stream is queried now and then so that a faulted launch cannot hang the caller.
+            volatile unsigned long long* flag = Q.done_h;
+            const auto t_spin = std::chrono::steady_clock::now();
+            double next_query_s = 2e-3;
+            for (unsigned n = 1;; ++n) {
+                if (*flag == Q.done_seq) { spun = true; break; }
+#if defined(__x86_64__) || defined(__i386__)
+                __builtin_ia32_pause();
+#endif
+                if ((n & 0xFFu) == 0) {
+                    const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_spin).count();
+                    if (el > next_query_s) {
+                        const cudaError_t q = cudaStreamQuery(h->stream);
+                        if (q != cudaErrorNotReady) { if (q != cudaSuccess) cudaGetLastError(); spun = (*flag == Q.done_seq); break; }
+                        next_query_s = el + 1e-3;
+                    }
+                }
+            }
+            std::atomic_thread_fence(std::memory_order_acquire);
+        }
+        if (!spun) OUTER_TRY(h, cudaStreamSynchronize(h->stream));
         if (sh_->error == 3) {
             cudaMemsetAsync(h->persist_ctl, 0, sizeof(PersistCtl), h->stream);
             h->err = "muse_solve: a rank did not arrive at the exchange step within 4 s (peer-mapped exchange of the persistent launch)";
@@ -526,10 +579,9 @@ extern "C" int muse_b200_muse_solve(muse_handle* h, const double* theta0, int32_
                     add(MUSE_PASS_FD, fd_items, fd_items * 2 * d8 + d8, T[1 + 2 * kPhaseFid], T[1 + 2 * kPhaseFd]);
                 }
                 h->acc.solve_launches += 1;
-                if (h->prof) {              // the stream has been synchronised: the launch's event pair can be read now
-                    float ms = 0.f;
-                    if (cudaEventElapsedTime(&ms, ea, eb) != cudaSuccess) { cudaGetLastError(); ms = 0.f; }
-                    h->acc.solve_ms += ms; h->acc.solve_units += units_sum; h->acc.solve_bytes += bytes_sum;
+                if (h->prof) {              // the launch's event pair: now if the stream has been synchronised, else when it has retired
+                    h->persist_pend = true; h->persist_pend_units = units_sum; h->persist_pend_bytes = bytes_sum;
+                    if (!spun) muse_persist_flush(h);
                 }
             }
             // lazy ẑ: the state cells hold level masks unless the last pass materialised ẑ — no resident ẑ is left behind

@@ -107,6 +107,8 @@ struct PersistParams {
     unsigned char* fd_h;
     unsigned long long slot_bytes, fd_bytes;
     OuterState* st_h;
+    unsigned long long* done_h;                   // pinned word: the last CTA to leave stores done_seq there once every host mirror is complete
+    unsigned long long done_seq;
     double* gall_h[kOuterSlots];                  // multi-GPU: host mirrors of this rank's gathered-score slots / FD block
     double* fdall_h;
     PersistCtl* ctl;
