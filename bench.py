@@ -56,7 +56,7 @@ def parse():
                     help="strong (default, the north-star split): --nsims sims in total, N/world per rank; weak: --nsims per rank")
     ap.add_argument("--d", "--dim", dest="d", type=int, default=D, help="latent dimension (use --dim under torchrun: its parser finds --d ambiguous)")
     ap.add_argument("--nsims", type=int, default=NSIMS, help="sims in total (strong) or per GPU (weak)")
-    ap.add_argument("--family", default="funnel", choices=["funnel", "hiergauss", "corrgauss"])
+    ap.add_argument("--family", default="funnel", choices=["funnel", "hiergauss", "corrgauss", "twolayer"])
     ap.add_argument("--group", type=int, default=0)
     ap.add_argument("--cluster", type=int, default=0)
     ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 generic solver only, 2 streaming kernel first")
@@ -79,10 +79,17 @@ def observed_data(family, d, L=None):
     """Synthetic observation at θ_true (0 for the funnel and corrgauss, (0,0) for hiergauss); host NumPy, seeded."""
     rng = np.random.Generator(np.random.Philox(DATA_SEED))
     xi, nu = rng.standard_normal(d), rng.standard_normal(d)
+    if family == "twolayer":                           # the docstring hierarchy at σ_true = 0.3: data = (x, y) stacked, d = 2n
+        n = d // 2
+        w = np.exp(0.3 / 4) * xi[:n] + xi[n:]
+        x = w + nu[:n]
+        return np.concatenate([x, x + nu[n:]])
     return (L @ xi if L is not None else xi) + nu      # sig = 1, mu = 0 at θ_true
 
 
 def theta_start(family):
+    if family == "twolayer":
+        return np.array([0.5])                         # muse(prob, (σ=0.5, θ=0)), src/turing.jl:78
     return np.array([0.5, 0.3]) if family == "hiergauss" else np.array([THETA0])
 
 
@@ -220,7 +227,8 @@ def cpu_sample_nsims(args):
 def workload_name(family, d, nsims, scaling, world):
     cfg_name = {"funnel": "BASELINE configs[2]" if d == 65536 else ("BASELINE configs[1]" if (d == 512 and nsims == 10000) else
                           ("BASELINE configs[0]" if (d == 512 and nsims == 100) else "funnel, custom shape")),
-                "hiergauss": "BASELINE configs[3]", "corrgauss": "BASELINE configs[4]"}[family]
+                "hiergauss": "BASELINE configs[3]", "corrgauss": "BASELINE configs[4]",
+                "twolayer": "the toy hierarchy of the reference's Turing docstring, src/turing.jl:63-79; not a BASELINE config"}[family]
     per = "" if world == 1 else (" per GPU" if scaling == "weak" else " in total, sharded over the GPUs")
     return (f"{family} d={d} nsims={nsims}{per}: full solve θ̂/J/H = muse(prob, θ₀={theta_start(family).tolist()}; nsims, "
             f"get_covariance=true), ∇z_logLike_atol={ATOL} ({cfg_name})")
@@ -408,6 +416,13 @@ def roofline_of(wl, mv, hbm_peak, peak_src, steps, kernel_flag):
                 e["frac_of_hbm_peak"] = e["algorithmic_gbs"] / hbm_peak
             by_pass[kind] = e
     share = mv["solve_ms_sum"] / world / (mv["ms_block"] * mv["blocks"])
+    if wl.family == "twolayer":
+        # F4 runs on the lock-step solver (a launch per round, host poll between rounds): at the docstring's size a pass is a chain
+        # of ≈ 10 short launches — latency, not bandwidth; no roofline figure is claimed for it
+        return {"bound": "hbm", "achieved": None, "peak": hbm_peak, "unit": "GB/s", "frac": None, "traffic": None, "peak_source": peak_src,
+                "kernel": "pair_apply_kernel + corr_iter_kernel (lock-step L-BFGS, elementwise 2x2-block product in place of the DGEMM)",
+                "kernel_share_of_step": share, "passes": by_pass,
+                "note": "launch-latency-bound at this size (2 L-BFGS iterations per unit, one launch per round)"}
     if wl.family == "corrgauss":
         # FP64 tensor roofline: denominator = cuBLAS DGEMM of the same shape measured here (MEASURED_PEAKS.json carries only
         # bf16), numerator = 2·rows·d² per P-product ÷ CUDA-event time of the whole solver chains
@@ -604,11 +619,14 @@ def run_b200(args):
 
 
 def extra_configs(m, torch, dist, pool, stream, args, hbm_peak, peak_src):
-    """The other BASELINE configs through the same code, one record each (single GPU): C1, C2 (latency path), C4, C5."""
+    """The other BASELINE configs through the same code, one record each (single GPU): C1, C2 (latency path), C4, C5 — and the fourth
+    registered family (F4, the docstring hierarchy of the reference's Turing adapter) at its docstring size."""
     import copy
     out = []
     for name, family, d, nsims, steps, secs in (("C1", "funnel", 512, 100, 100, 0.3), ("C2", "funnel", 512, 10000, 50, 0.3),
-                                                ("C4", "hiergauss", 100000, 4096, 5, 0.2), ("C5", "corrgauss", 4096, 8192, 2, 0.0)):
+                                                ("C4", "hiergauss", 100000, 4096, 5, 0.2), ("C5", "corrgauss", 4096, 8192, 2, 0.0),
+                                                # the reference's Turing docstring model at its own size (src/turing.jl:63-79: n = 512, nsims = 100)
+                                                ("F4", "twolayer", 1024, 100, 20, 0.2)):
         rec = {"name": name, "workload": workload_name(family, d, nsims, "weak", 1), "steps": steps}
         try:
             a = copy.copy(args)

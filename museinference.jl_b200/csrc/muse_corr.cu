@@ -545,6 +545,22 @@ __global__ void __launch_bounds__(kCT) corr_cg_dot_kernel(const double* __restri
     if (threadIdx.x == 0) out[k] = acc;
 }
 
+// F4: right-hand sides of the implicit-diff CG, row k = (0, ξ_z of sim k) — and the dot product ẑ_z · v_z with the MAPs in rows 1 + k
+__global__ void __launch_bounds__(256) pair_rhs_kernel(const double* __restrict__ W, double* __restrict__ out, int n, int d, int ld) {
+    const size_t off = (size_t)blockIdx.y * ld;
+    for (int j = blockIdx.x * 256 + threadIdx.x; j < ld; j += gridDim.x * 256) out[off + j] = (j >= n && j < d) ? W[off + j - n] : 0.0;
+}
+__global__ void __launch_bounds__(kCT) pair_cg_dot_kernel(const double* __restrict__ z, const double* __restrict__ v, int n, int ld,
+                                                          double* __restrict__ out) {
+    __shared__ double red[kCT / 32];
+    const int k = blockIdx.x;
+    const size_t om = (size_t)(1 + k) * ld, ov = (size_t)k * ld;
+    double acc = 0.0;
+    for (int j = threadIdx.x; j < n; j += kCT) acc = fma(z[om + j], v[ov + j], acc);
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) out[k] = acc;
+}
+
 }  // namespace
 }  // namespace muse
 
@@ -914,10 +930,7 @@ bool muse_corr_have_draws(muse_handle* h, bool hshard) { return hshard ? h->corr
 int muse_corr_implicit_h(muse_handle* h, const double* theta0, int nsims_H, int start, int cg_maxiter, double* Hs_out, int32_t* cg_iters_out,
                          int32_t* status_out) {
     muse_corr_ctx* c = h->corr;
-    if (h->cfg.family == MUSE_FAMILY_TWOLAYER) {
-        h->err = "twolayer: get_H!(implicit_diff = true) is not built for this family; use the finite-difference get_H!";
-        return MUSE_EUNSUPPORTED;
-    }
+    const bool pairf = h->cfg.family == MUSE_FAMILY_TWOLAYER;
     // (1) MAPs of the H sims; the pass leaves ẑ, x and g = ∇f(ẑ), hence a·Pẑ = g − ẑ + x
     h->pass_kind = MUSE_PASS_COLD;
     int rc = muse_corr_map_score(h, theta0, theta0, 1e-1, 0, start, 0, nsims_H);
@@ -933,8 +946,17 @@ int muse_corr_implicit_h(muse_handle* h, const double* theta0, int nsims_H, int 
     auto done = [&](int code) { cudaFree(st); cudaFree(dots); return code; };
     CgLaunch L{};
     L.d = h->cfg.d; L.ld = c->ld; L.nrows = nsims_H; L.maxiter = cg_maxiter;
-    L.a = std::exp(-theta0[0]);
+    L.a = pairf ? 1.0 : std::exp(-theta0[0]);
     L.W = c->W;
+    if (pairf) {
+        // F4: ∂σ_sim ∇u logLike = (0, ¼e^{σ/4} ξ_z) (only the w-half sees the data, x = e^{σ/4}ξ_z + ξ_w + ν_x); the scalar goes to the end
+        const int n = h->cfg.d / 2;
+        dim3 grid((unsigned)std::min((c->ld + 255) / 256, 64), (unsigned)nsims_H);
+        pair_rhs_kernel<<<grid, 256, 0, h->stream>>>(c->W, c->tmp, n, h->cfg.d, c->ld);
+        h->acc.launches += 1;
+        L.W = c->tmp;
+        c->binv = std::exp(-0.5 * theta0[0]);
+    }
     L.v = c->fd.z; L.r = c->fd.g; L.u = c->fd.s; L.q = c->fd.q;
     L.st = st;
     L.active_count = c->active;
@@ -952,7 +974,8 @@ int muse_corr_implicit_h(muse_handle* h, const double* theta0, int nsims_H, int 
         corr_cg_iter_kernel<<<nsims_H, kCT, 0, h->stream>>>(L);
         h->acc.launches += 1;
     }
-    corr_cg_dot_kernel<<<nsims_H, kCT, 0, h->stream>>>(c->main.g, c->main.z, c->main.x, c->fd.z, h->cfg.d, c->ld, dots);
+    if (pairf) pair_cg_dot_kernel<<<nsims_H, kCT, 0, h->stream>>>(c->main.z, c->fd.z, h->cfg.d / 2, c->ld, dots);
+    else corr_cg_dot_kernel<<<nsims_H, kCT, 0, h->stream>>>(c->main.g, c->main.z, c->main.x, c->fd.z, h->cfg.d, c->ld, dots);
     h->acc.launches += 1;
     std::vector<double> dh((size_t)nsims_H);
     std::vector<CgState> sh((size_t)nsims_H);
@@ -961,9 +984,10 @@ int muse_corr_implicit_h(muse_handle* h, const double* theta0, int nsims_H, int 
     if (e == cudaSuccess) e = cudaMemcpyAsync(sh.data(), st, sh.size() * sizeof(CgState), cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
     if (e != cudaSuccess) { h->err = std::string("implicit_h: ") + cudaGetErrorString(e); return done(MUSE_ECUDA); }
-    const double sig = std::exp(0.5 * theta0[0]);
+    // F3: ½ σ (a·Pẑ)·(I + aP)⁻¹W;   F4: (∂σ ∇u logLike)·A⁻¹·(∂σ_sim ∇u logLike) = ½b ẑ_z · [A⁻¹(0, ¼e^{σ/4} ξ_z)]_z
+    const double sig = pairf ? 0.125 * std::exp(-0.5 * theta0[0]) * std::exp(0.25 * theta0[0]) : 0.5 * std::exp(0.5 * theta0[0]);
     for (int k = 0; k < nsims_H; ++k) {
-        Hs_out[k] = 0.5 * sig * dh[k];                          // ½ σ (a·Pẑ)·(I + aP)⁻¹W
+        Hs_out[k] = sig * dh[k];
         if (cg_iters_out) cg_iters_out[k] = sh[k].iters;
     }
     return done(MUSE_OK);
