@@ -532,9 +532,12 @@ def run_b200(args):
     d2h_box = [0]
     be.profile_reset(True)
 
+    e2e_count = [0]
+
     def e2e_step(s):
+        e2e_count[0] += 1                           # counted over all blocks: consecutive steps never share a seed, whatever --steps is
         wl.prob.set_data(wl.x_host.numpy())         # H2D of the step's input from pinned host memory
-        r = wl.solve(SIM_SEED + 1 + (s % 2))        # new seed ⇒ base normals regenerated on the device
+        r = wl.solve(SIM_SEED + 1 + (e2e_count[0] % 2))   # new seed ⇒ base normals regenerated on the device
         d2h_box[0] = (len(r.gs) * th0.size + len(r.Hs) * th0.size ** 2) * 8 + (len(r.history) * (nsims_total // world + 1) * 20)
 
     blocks_e = wl.timed_blocks(args.steps, e2e_step)

@@ -43,7 +43,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
              dig.hexdigest()[:16]))
     be.close()
 else:
-    for impl in ("0", "1", "2", "3"):
+    for impl in (sys.argv[1:] or ["0", "1", "2", "3"]):
         env = dict(os.environ, MUSE_DRAWS_IMPL=impl)
         r = subprocess.run([sys.executable, os.path.abspath(__file__), "child"], env=env, capture_output=True, text=True, timeout=300)
         print(r.stdout.strip() or ("impl %s FAILED: " % impl + r.stderr[-2000:]))

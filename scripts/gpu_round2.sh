@@ -30,7 +30,7 @@ python scripts/ncu_traffic.py $out/${tag}_persist_full.ncu-rep $out/${tag}_solve
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:dgemm_tma -s 2 -c 1 -o $out/${tag}_dgemm_tma_full \
     python scripts/dgemm_bench.py > $out/${tag}_prof_dgemm.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:philox_draws -s 3 -c 1 -o $out/${tag}_draws_full \
-    python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-extra-configs > $out/${tag}_prof_draws.log 2>&1
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extra-configs > $out/${tag}_prof_draws.log 2>&1
 for cfg in "65536 2048" "512 10000" "512 100"; do set -- $cfg
   MUSE_DEBUG_TIMING=1 MUSE_K=5 MUSE_D=$1 MUSE_N=$2 timeout 120 python scripts/host_overhead.py > $out/${tag}_host_$1_$2.log 2>&1
 done
