@@ -114,7 +114,7 @@ def test_struct_layouts_and_constants_match_a_c_compilation_of_the_header(tmp_pa
         lines.append(f'  printf("sizeof {name} %zu\\n", sizeof({name}));')
         for fname, _ in st._fields_:
             lines.append(f'  printf("offsetof {name}.{fname} %zu\\n", offsetof({name}, {fname}));')
-    consts = ["MUSE_B200_ABI_VERSION", "MUSE_FAMILY_FUNNEL", "MUSE_FAMILY_HIERGAUSS", "MUSE_FAMILY_CORRGAUSS", "MUSE_START_ZEROS",
+    consts = ["MUSE_B200_ABI_VERSION", "MUSE_FAMILY_FUNNEL", "MUSE_FAMILY_HIERGAUSS", "MUSE_FAMILY_CORRGAUSS", "MUSE_FAMILY_TWOLAYER", "MUSE_START_ZEROS",
               "MUSE_START_PREV", "MUSE_START_TRUTH", "MUSE_START_USER", "MUSE_STATUS_G_CONVERGED", "MUSE_STATUS_XF_CONVERGED",
               "MUSE_STATUS_MAXITER", "MUSE_STATUS_LS_FAILED", "MUSE_STATUS_NONFINITE", "MUSE_PASS_KINDS", "MUSE_EUNSUPPORTED",
               "MUSE_ENODEVICE", "MUSE_ESTATE"]
@@ -135,8 +135,12 @@ def test_struct_layouts_and_constants_match_a_c_compilation_of_the_header(tmp_pa
         for fname, _ in st._fields_:
             assert got[("offsetof", f"{name}.{fname}")] == getattr(st, fname).offset, f"{name}.{fname}"
     assert got[("const", "MUSE_B200_ABI_VERSION")] == capi.ABI_VERSION
-    assert (got[("const", "MUSE_FAMILY_FUNNEL")], got[("const", "MUSE_FAMILY_HIERGAUSS")], got[("const", "MUSE_FAMILY_CORRGAUSS")]) == \
-        (capi.FAMILY_FUNNEL, capi.FAMILY_HIERGAUSS, capi.FAMILY_CORRGAUSS)
+    assert (got[("const", "MUSE_FAMILY_FUNNEL")], got[("const", "MUSE_FAMILY_HIERGAUSS")], got[("const", "MUSE_FAMILY_CORRGAUSS")],
+            got[("const", "MUSE_FAMILY_TWOLAYER")]) == (capi.FAMILY_FUNNEL, capi.FAMILY_HIERGAUSS, capi.FAMILY_CORRGAUSS, capi.FAMILY_TWOLAYER)
+    # the oracle's family ids are the header's
+    import oracle as O
+    assert [f.family_id for f in (O.Funnel, O.HierGauss, O.CorrGauss, O.TwoLayer)] == \
+        [got[("const", f"MUSE_FAMILY_{k}")] for k in ("FUNNEL", "HIERGAUSS", "CORRGAUSS", "TWOLAYER")]
     assert [got[("const", f"MUSE_START_{k}")] for k in ("ZEROS", "PREV", "TRUTH", "USER")] == \
         [capi.START_ZEROS, capi.START_PREV, capi.START_TRUTH, capi.START_USER]
     assert [got[("const", f"MUSE_STATUS_{k}")] for k in ("G_CONVERGED", "XF_CONVERGED", "MAXITER", "LS_FAILED", "NONFINITE")] == \
