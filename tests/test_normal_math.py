@@ -76,3 +76,41 @@ def test_normals_match_the_oracle_generator(nm, sim, stream):
     ref = O.philox_normals(seed, sim, stream, d)                 # NumPy libm log/cos/sin of the same uniforms
     np.testing.assert_allclose(out, ref, rtol=0, atol=2e-14)     # the GPU test allows 2e-13 between device and oracle
     assert abs(out.mean()) < 0.02 and abs(out.std() - 1) < 0.01
+
+
+def test_trimmed_kernel_transform_is_bit_identical_to_the_header(tmp_path):
+    """`box_muller_regs` of csrc/muse_draws.cu (the transform of philox_draws_tab2_kernel, the default draws kernel: funnel-shift
+    assembly of the 53-bit integers, exponent-OR conversion of the angle remainder, constants in registers) pasted verbatim into a
+    host build and compared BIT FOR BIT with the header's `box_muller_tab` (the round-1 kernel's transform, pinned above against
+    long-double references) on 4 million random Philox blocks and the edge cases of both uniforms."""
+    src_cu = open(os.path.join(ROOT, "museinference.jl_b200", "csrc", "muse_draws.cu")).read()
+    a, b = src_cu.index("struct NMRegs {"), src_cu.index("template <bool BOTH>")
+    block = src_cu[a:b]
+    assert "box_muller_regs" in block and "asm" not in block
+    tmpl = open(os.path.join(ROOT, "tests", "csrc", "draws_regs_host.cpp.in")).read()
+    src = os.path.join(ROOT, "tests", "csrc", "_draws_regs_host_gen.cpp")
+    try:
+        with open(src, "w") as fh:
+            fh.write(tmpl.replace("@BOX_MULLER_REGS@", block))
+        out = str(tmp_path / "libdr.so")
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", out, src], check=True)
+    finally:
+        if os.path.exists(src):
+            os.remove(src)
+    lib = C.CDLL(out)
+    rng = np.random.default_rng(2026)
+    r = rng.integers(0, 2 ** 32, size=(4_000_000, 4), dtype=np.uint64).astype(np.uint32)
+    # edge cases: v = ((r1 >> 5) << 26) + (r0 >> 6) at 0, 1, 2⁵³ − 1 (u → 1 after rounding), around 2⁵², around the √2 split of the
+    # mantissa and the cell boundaries of the angle table — for both uniforms of a block
+    edge = []
+    for hi in (0, 1, 31, 32, 2 ** 32 - 1, 2 ** 32 - 32, 2 ** 31, 2 ** 31 - 1, 0x6A09E667, 0x6A09F000, 0x6A09EFFF, 0xB504F333, 2 ** 18, 2 ** 18 - 1):
+        for lo in (0, 63, 64, 2 ** 32 - 1, 2 ** 32 - 64, 2 ** 31):
+            edge.append((lo, hi, lo ^ 0x5A5A5A5A, hi))
+            edge.append((lo ^ 0x12345678, hi ^ 0xFFFF, lo, hi))
+    r = np.ascontiguousarray(np.concatenate([r, np.array(edge, dtype=np.uint64).astype(np.uint32)]))
+    n = r.shape[0]
+    got, ref = np.empty(2 * n), np.empty(2 * n)
+    lib.muse_host_box_muller_regs(_vp(r), C.c_int(n), _vp(got))
+    lib.muse_host_box_muller_tab(_vp(r), C.c_int(n), _vp(ref))
+    assert np.isfinite(ref).all()
+    np.testing.assert_array_equal(got.view(np.uint64), ref.view(np.uint64))
