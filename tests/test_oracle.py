@@ -301,6 +301,30 @@ def test_f3_lockstep_model():
                     np.testing.assert_allclose(z, ref.minimizer, rtol=1e-12, atol=1e-13)
 
 
+def test_f4_lockstep_model():
+    """F4 (the two-layer hierarchy) on the same lock-step scheme, as csrc/muse_corr.cu runs it: ½‖X − u‖² + ½uᵀ(A − I)u + const with
+    X = (0, x), a = 1 and the 2 × 2-block matrix A − I = [[b, −1], [−1, 1]] ⊗ I in the place of P (pair_apply_kernel) — identical
+    iteration / evaluation counts to the oracle's honest L-BFGS on the family's own logLike, ẑ and the minimum to round-off."""
+    from oracle.corr_lockstep import lockstep
+    rng = np.random.default_rng(4)
+    for d in (40, 256):
+        n = d // 2
+        fam = _family("twolayer", d)
+        for s in (0.5, 0.0, -1.2, 2.0):
+            b = math.exp(-0.5 * s)
+            P4 = np.kron(np.array([[b, -1.0], [-1.0, 1.0]]), np.eye(n))
+            for k in range(3):
+                xy, utrue = fam.sample([s], rng.standard_normal(d), rng.standard_normal(d))
+                X = np.concatenate([np.zeros(n), xy[:n]])
+                r3 = xy[n:] - xy[:n]
+                for z0 in (np.zeros(d), utrue, utrue + 0.3 * rng.standard_normal(d)):
+                    ref = O.lbfgs_minimize(lambda z: fam.neg_loglike_and_grad(xy, z, [s]), z0, g_tol=1e-2)
+                    z, it, fc, gres = lockstep(P4, 1.0, 0.5 * n * s + np.dot(r3, r3), X, z0, 1e-2)
+                    assert (it, fc) == (ref.iterations, ref.f_calls), (d, s, k, it, fc, ref.iterations, ref.f_calls)
+                    np.testing.assert_allclose(z, ref.minimizer, rtol=1e-12, atol=1e-13)
+                    np.testing.assert_allclose(z, fam.exact_map(xy, [s]), rtol=1e-6, atol=2e-2)       # stopped at ‖∇f‖∞ ≤ 1e-2
+
+
 def test_c_port_correlated_gaussian():
     """The C port's F3 (dense P·z mat-vec per evaluation, L·ξ sampling) against the NumPy oracle."""
     from oracle import cport, cmuse
