@@ -32,6 +32,8 @@
 #define FAM_FUNNEL 1
 #define FAM_HIER 2
 #define FAM_CORR 3   /* dense correlated Gaussian: -logLike = ½[Σ(x-z)² + a zᵀPz] + half_cst, P = Σ₀⁻¹ */
+#define FAM_TWO 4    /* the toy hierarchy of /root/reference/src/turing.jl:63-79 (oracle/families.py TwoLayer): latent u = (z, w), data (x, y),
+                        d = 2n; -logLike = ½[bΣz² + Σ(w-z)² + Σ(x-w)² + Σ(y-x)²] + nσ/4, b = e^{-σ/2} (held in `a`) */
 
 typedef struct {
     int family, d;
@@ -43,7 +45,11 @@ typedef struct {
 static void model_at(model_t* m, int family, int d, const double* th) {
     m->family = family;
     m->d = d;
-    if (family == FAM_FUNNEL || family == FAM_CORR) {
+    if (family == FAM_TWO) {
+        m->a = exp(-0.5 * th[0]);
+        m->mu = 0.0;
+        m->half_cst = 0.25 * (d / 2) * th[0];
+    } else if (family == FAM_FUNNEL || family == FAM_CORR) {
         m->a = exp(-th[0]);
         m->mu = 0.0;
         m->half_cst = 0.5 * d * th[0];
@@ -81,6 +87,17 @@ static double fg(const model_t* m, const double* x, const double* z, double* g) 
         }
         return 0.5 * (rr + a * zPz) + m->half_cst;
     }
+    if (m->family == FAM_TWO) {                       /* x = (x, y), z = (z, w) stacked */
+        const int n = m->d / 2;
+        for (int j = 0; j < n; ++j) {
+            const double zz = z[j], ww = z[n + j], xx = x[j], yy = x[n + j];
+            const double r1 = ww - zz, r2 = xx - ww, r3 = yy - xx;
+            e += a * zz * zz + r1 * r1 + r2 * r2 + r3 * r3;
+            g[j] = a * zz - r1;
+            g[n + j] = r1 - r2;
+        }
+        return 0.5 * e + m->half_cst;
+    }
     for (int j = 0; j < m->d; ++j) {
         const double r = x[j] - z[j], w = z[j] - mu;
         e += r * r + a * w * w;
@@ -93,6 +110,12 @@ static void score(const model_t* m, const double* z, double* out, double* scratc
     double s1 = 0.0, s2 = 0.0;
     if (m->family == FAM_CORR) {                      /* ∇θ logLike = ½ e^{-θ} zᵀPz − d/2 */
         out[0] = 0.5 * m->a * apply_P(m, z, scratch) - 0.5 * m->d;
+        return;
+    }
+    if (m->family == FAM_TWO) {                       /* ∇σ logLike = ¼ e^{-σ/2} Σz² − n/4 */
+        const int n = m->d / 2;
+        for (int j = 0; j < n; ++j) s2 += z[j] * z[j];
+        out[0] = 0.25 * m->a * s2 - 0.25 * n;
         return;
     }
     for (int j = 0; j < m->d; ++j) {
@@ -416,6 +439,15 @@ static void* worker(void* arg) {
             else memset(w->x, 0, sizeof(double) * d);
         } else {
             const double *xk = J->xi + (size_t)k * d, *nk = J->nu + (size_t)k * d;
+            if (J->family == FAM_TWO) {               /* z = e^{σ/4} ξ_z, w = z + ξ_w, x = w + ν_x, y = x + ν_y */
+                const int n = d / 2;
+                for (int j = 0; j < n; ++j) {
+                    const double zt = J->sig * xk[j], wt = zt + xk[n + j];
+                    x[j] = wt + nk[j];
+                    x[n + j] = x[j] + nk[n + j];
+                    if (J->start_mode == 2) { w->x[j] = zt; w->x[n + j] = wt; }
+                }
+            } else
             for (int j = 0; j < d; ++j) {
                 double base = xk[j];
                 if (J->family == FAM_CORR) {          /* z = e^{θ/2} L ξ */
@@ -469,7 +501,8 @@ int muse_oracle_map_score_consts(int family, int d, int nsims, const double* xi,
                                  const double* theta_sim, const double* theta_eval, double atol, int include_data,
                                  int start_mode, double* z_inout, double* g_out, int* iters_out, int* fg_out,
                                  double* gnorm_out, int* status_out, int nthreads, const double* P, const double* L) {
-    if (family != FAM_FUNNEL && family != FAM_HIER && family != FAM_CORR) return -5;
+    if (family != FAM_FUNNEL && family != FAM_HIER && family != FAM_CORR && family != FAM_TWO) return -5;
+    if (family == FAM_TWO && (d & 1)) return -1;
     if (family == FAM_CORR && (!P || !L)) return -1;
     job_t J;
     memset(&J, 0, sizeof(J));
@@ -482,7 +515,7 @@ int muse_oracle_map_score_consts(int family, int d, int nsims, const double* xi,
     model_at(&J.mdl, family, d, theta_eval);
     J.mdl.P = P;
     J.mdl.L = L;
-    J.sig = family == FAM_HIER ? exp(theta_sim[1]) : exp(0.5 * theta_sim[0]);
+    J.sig = family == FAM_HIER ? exp(theta_sim[1]) : exp((family == FAM_TWO ? 0.25 : 0.5) * theta_sim[0]);
     J.smu = family == FAM_HIER ? theta_sim[0] : 0.0;
     J.z_inout = z_inout; J.g_out = g_out; J.gnorm_out = gnorm_out;
     J.iters_out = iters_out; J.fg_out = fg_out; J.status_out = status_out;

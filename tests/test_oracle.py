@@ -261,7 +261,7 @@ def test_golden_fixtures(name):
 def test_c_port_matches_numpy_oracle():
     from oracle import cport
     cport.build()
-    for name, d in (("funnel", 300), ("hiergauss", 257)):
+    for name, d in (("funnel", 300), ("hiergauss", 257), ("twolayer", 260)):
         fam, draws, xd = make_inputs(name, d, 9)
         prob = O.OracleProblem(fam, xd, draws)
         th = theta_start(name)
@@ -281,6 +281,21 @@ def test_c_port_matches_numpy_oracle():
     np.testing.assert_allclose(res.J, ref.J, rtol=1e-9)
     np.testing.assert_allclose(res.H, ref.H, rtol=1e-7)
     assert units == 2 * 51 + 1 + 2 * 5
+    # … and for the two-layer family (truth start of get_J! included)
+    prob, fam, draws, xd = oracle_problem("twolayer", 300, 40, prior=O.NormalPrior(0, 3))
+    ref = O.muse(prob, [0.5], nsims=40, get_covariance=True)
+    res, units = cmuse.muse_cpu(prob, [0.5], nsims=40)
+    assert len(res.history) == len(ref.history)
+    np.testing.assert_allclose(res.theta, ref.theta, rtol=1e-9)
+    np.testing.assert_allclose(res.J, ref.J, rtol=1e-9)
+    np.testing.assert_allclose(res.H, ref.H, rtol=1e-7)
+    th = np.array([0.2])
+    out = cport.map_score(fam.family_id, draws.xi[:6], draws.nu[:6], None, th, th, 1e-2, False, 2, nthreads=2)
+    for k in range(6):
+        x, z = prob.sample_x_z(k, th)
+        zh, g, soln = O.map_score_unit(prob, x, z, th, 1e-2)
+        np.testing.assert_allclose(out["g"][k], g, rtol=1e-11)
+        assert out["iters"][k] == soln.iterations and out["fg_evals"][k] == soln.f_calls
 
 
 def test_f3_lockstep_model():
