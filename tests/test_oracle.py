@@ -83,6 +83,43 @@ def test_exact_map_is_stationary_and_lbfgs_reaches_it(name):
         np.testing.assert_allclose(soln.minimizer, zstar, rtol=1e-13, atol=1e-15)
 
 
+def test_lbfgs_reproduces_the_run_printed_in_optims_documentation():
+    """A known answer of the UPSTREAM optimiser, not of this repository: Optim.jl's manual ("Minimizing a multivariate function")
+    prints the result of `optimize(f, [0.0, 0.0], LBFGS())` on the Rosenbrock function — L-BFGS(m = 10) + HagerZhang + InitialStatic,
+    g_tol = 1e-8, gradient by central finite differences (NLSolversBase's default: FiniteDiff, step ∛eps·max(1, |x|)) — as
+
+        Final objective value 5.3784…e-17,   Iterations: 24,   f(x) calls: 67,   ∇f(x) calls: 67.
+
+    The figures are quoted from memory of that page (no network here, the packages are not vendored under /root/reference); the
+    restatement in oracle/lbfgs.py + oracle/hagerzhang.py reproduces both counts exactly and the objective to its printed leading
+    digits (the trailing ones depend on FiniteDiff's step details).  With the analytic gradient the counts are the same, the
+    objective falls to 1e-26: the 5.38e-17 floor is the finite-difference bias, which is what makes it a fingerprint of the path."""
+    f = lambda x: (1.0 - x[0]) ** 2 + 100.0 * (x[1] - x[0] ** 2) ** 2
+    rel = np.cbrt(np.finfo(float).eps)
+
+    def fg_central(x):
+        g = np.zeros(2)
+        for i in range(2):
+            e = max(rel * abs(x[i]), rel)
+            xp, xm = x.copy(), x.copy()
+            xp[i] += e
+            xm[i] -= e
+            g[i] = (f(xp) - f(xm)) / (2 * e)
+        return f(x), g
+
+    soln = O.lbfgs_minimize(fg_central, np.zeros(2), g_tol=1e-8)
+    assert soln.converged and soln.g_converged
+    assert (soln.iterations, soln.f_calls) == (24, 67)
+    assert abs(soln.minimum - 5.3784e-17) < 3e-21
+    np.testing.assert_allclose(soln.minimizer, [1.0, 1.0], atol=2e-8)
+
+    def fg_exact(x):
+        return f(x), np.array([-2 * (1 - x[0]) - 400 * (x[1] - x[0] ** 2) * x[0], 200 * (x[1] - x[0] ** 2)])
+
+    exact = O.lbfgs_minimize(fg_exact, np.zeros(2), g_tol=1e-8)
+    assert (exact.iterations, exact.f_calls) == (24, 67) and exact.minimum < 1e-24
+
+
 def test_lbfgs_zero_iterations_when_start_satisfies_gtol():
     fam = O.Funnel(16)
     x = np.linspace(-1, 1, 16)
