@@ -40,7 +40,7 @@ from .families import Funnel, HierGauss, CorrGauss, TwoLayer, TransformedFamily,
 from .hagerzhang import HagerZhang, LineSearchException  # noqa: F401
 from .lbfgs import lbfgs_minimize, OptimResult  # noqa: F401
 from .muse import (  # noqa: F401
-    Draws, OracleProblem, MuseResult, muse, muse_bang, get_J_bang, get_H_bang, central_fdm, SimpleCovariance, cg, implicit_diff_H,
+    Draws, OracleProblem, MuseResult, muse, muse_bang, get_J_bang, get_H_bang, central_fdm, AdaptedFDM, pjacobian_adaptive, SimpleCovariance, cg, implicit_diff_H,
     finalize_result_bang, map_score_unit, NormalPrior, FlatPrior,
 )
 from .philox import philox_normals, philox4x32_10  # noqa: F401

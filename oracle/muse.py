@@ -358,6 +358,116 @@ def central_fdm(p, q=1):
     return tuple(float(g) for g in grid), tuple(float(A[k][p]) for k in range(p))
 
 
+class AdaptedFDM:
+    """[EXT FiniteDifferences 0.12] ``central_fdm(p, q; adapt = 1, condition = 10, factor = 1, max_range = Inf)`` called WITHOUT a step
+    (what ``pjacobian`` does when ``step === nothing``, src/util.jl:13): the step is estimated per call by minimising a bound on
+    round-off + truncation error,
+
+        step = (q/(p−q) · C₁/C₂)^(1/p),   C₁ = eps(|f|)·Σ|c|·factor,   C₂ = |∇ᵖf|·Σ|c·gᵖ|/p!,
+
+    where |∇ᵖf| and |f| come from the *bound estimator* — the unadapted ``central_fdm(p + 2, p)`` evaluated at ITS default step
+    (the same formula with |∇ᵖf| → condition, eps(|f|) → eps(Float64)) — as the largest magnitude over the estimates at x − h, x, x + h
+    (the same p + 2 function values with the grid shifted by ∓1) and over the components of a vector-valued f; the step is then capped
+    at max_range / max|grid| and at 1000 × the default step.  Restated from the package source as recalled (src/methods.jl:
+    ``estimate_step``, ``_estimate_magnitudes``, ``_compute_step_acc``, ``_limit_step``); the one published figure at hand —
+    ``estimate_step(central_fdm(5, 1), sin, 1.0)`` = (0.001065235154086019, 1.9541865128909085e-13) in the package's documentation,
+    quoted from memory — is reproduced to the last digit (tests/test_oracle.py); it is sensitive to the order of the floating-point
+    sum Σ fᵢcᵢ (left to right, as Julia folds a static vector): a compensated sum already moves the sixth digit."""
+
+    def __init__(self, p, q=1, adapt=1, condition=10.0, factor=1.0, max_range=math.inf):
+        from fractions import Fraction
+        self.p, self.q = int(p), int(q)
+        self.grid, self.coefs = central_fdm(p, q)
+        shift = lambda d: _fdm_coefs([g + d for g in self.grid], q)
+        self.coefs_nbhd = (shift(-1), self.coefs, shift(+1))
+        self.condition, self.factor, self.max_range = float(condition), float(factor), float(max_range)
+        self.df_mult = float(sum(abs(Fraction(c) * Fraction(g) ** self.p) for c, g in zip(self.coefs, self.grid)) / math.factorial(self.p))
+        self.ferr_mult = sum(abs(c) for c in self.coefs)
+        self.bound = AdaptedFDM(p + 2, p, adapt - 1, condition, factor, max_range) if adapt >= 1 else None
+
+    def _step_acc(self, df_magnitude, f_error):
+        P, Q = self.p, self.q
+        c1 = f_error * self.ferr_mult * self.factor
+        c2 = df_magnitude * self.df_mult
+        step = (Q / (P - Q) * (c1 / c2)) ** (1 / P)
+        return step, c1 * step ** (-Q) + c2 * step ** (P - Q)
+
+    def default_step(self):
+        return self._step_acc(self.condition, float(np.finfo(np.float64).eps))
+
+    def _limit(self, step, acc):
+        step_max = self.max_range / max(abs(g) for g in self.grid)
+        if step > step_max:
+            step, acc = step_max, math.nan
+        step_default, _ = self.default_step()
+        if step > 1000 * step_default:
+            step, acc = 1000 * step_default, math.nan
+        return step, acc
+
+    def evaluate(self, f, x, step):
+        return [np.atleast_1d(np.asarray(f(x + step * g), dtype=np.float64)).copy() for g in self.grid]
+
+    def estimate(self, fs, step, coefs=None):
+        coefs = self.coefs if coefs is None else coefs
+        acc = fs[0] * coefs[0]
+        for fk, ck in zip(fs[1:], coefs[1:]):                             # sum(fs .* coefs): left to right
+            acc = acc + fk * ck
+        return acc / step ** self.q
+
+    def magnitudes(self, fs, step):
+        """(|∇^q f|, |f|) in a neighbourhood of x from the values ``fs`` at x + step·grid (the bound estimator's rôle)."""
+        df = max(float(np.max(np.abs(self.estimate(fs, step, c)))) for c in self.coefs_nbhd)
+        return df, max(float(np.max(np.abs(v))) for v in fs)
+
+    def step_from_magnitudes(self, df_magnitude, f_magnitude):
+        if df_magnitude == 0.0 or f_magnitude == 0.0:
+            return self._limit(*self.default_step())
+        return self._limit(*self._step_acc(df_magnitude, float(np.spacing(f_magnitude))))
+
+    def estimate_step(self, f, x):
+        if self.bound is None:
+            return self._limit(*self.default_step())
+        hb = self.bound.estimate_step(f, x)[0]
+        return self.step_from_magnitudes(*self.bound.magnitudes(self.bound.evaluate(f, x, hb), hb))
+
+    def __call__(self, f, x, step=None):
+        step = self.estimate_step(f, x)[0] if step is None else step
+        return self.estimate(self.evaluate(f, x, step), step)
+
+
+def _fdm_coefs(grid, q):
+    """Coefficients c with Σᵢ cᵢ gᵢᵏ = q!·δ_{kq}, k = 0 … p−1, for an arbitrary integer grid (exact rationals → Float64)."""
+    from fractions import Fraction
+    p = len(grid)
+    A = [[Fraction(g) ** k for g in grid] + [Fraction(math.factorial(q) if k == q else 0)] for k in range(p)]
+    for c in range(p):
+        piv = next(r for r in range(c, p) if A[r][c] != 0)
+        A[c], A[piv] = A[piv], A[c]
+        A[c] = [v / A[c][c] for v in A[c]]
+        for r in range(p):
+            if r != c and A[r][c] != 0:
+                A[r] = [vr - A[r][c] * vc for vr, vc in zip(A[r], A[c])]
+    return tuple(float(A[k][p]) for k in range(p))
+
+
+def pjacobian_adaptive(f, theta0, fdm=None):
+    """src/util.jl:9-26 with ``step === nothing``: per component n, ``fdm(ε -> f(θ₀ + ε eₙ), 0.0)`` with FiniteDifferences' own
+    step estimate.  Returns (Jacobian, steps)."""
+    x = np.array(theta0, dtype=np.float64, copy=True)
+    grid, _ = fdm if fdm is not None else ((-1.0, 0.0, 1.0), None)
+    adm = AdaptedFDM(len(grid), 1)
+    cols, steps = [], []
+    for n in range(x.size):
+        def fn(eps, _n=n):
+            xx = x.copy()
+            xx[_n] = x[_n] + eps
+            return f(xx)
+        h = adm.estimate_step(fn, 0.0)[0]
+        cols.append(adm(fn, 0.0, h))
+        steps.append(h)
+    return np.stack(cols, axis=1), np.array(steps)
+
+
 def pjacobian(f, theta0, step, fdm=None):
     """src/util.jl:9-26 with an explicit step per component; fdm = (grid, coefs), default central_fdm(3,1).
     [EXT FiniteDifferences 0.12] with an explicit step the estimate is ``sum(fs .* coefs) / step`` where
@@ -454,9 +564,9 @@ def get_H_bang(result: MuseResult, prob: OracleProblem, theta0=None, *, gradz_lo
 
     if step is None and len(result.gs) > 0:                               # :411-413
         step = 0.1 / np.std(np.array(result.gs), axis=0, ddof=1)
-    if step is None:
-        raise ValueError("oracle: adaptive FiniteDifferences step not restated; pass `step` or run get_J! first")
-    step = np.atleast_1d(np.asarray(step, dtype=np.float64))
+    adaptive = step is None                                               # fdm(f, 0.0): FiniteDifferences estimates the step itself
+    if not adaptive:
+        step = np.atleast_1d(np.asarray(step, dtype=np.float64))
 
     # fiducial MAPs  :417-423  (every one is the MAP of the master stream's own draw)
     zfids = []
@@ -472,7 +582,12 @@ def get_H_bang(result: MuseResult, prob: OracleProblem, theta0=None, *, gradz_lo
             x, _ = prob.sample_x_z(_k, theta)                             # sim generated at θ
             zhat, _ = prob.z_at_theta(x, _z, theta0, gradz_logLike_atol)  # MAP at fiducial θ₀
             return prob.grad_theta(x, zhat, theta0)                       # score at fiducial θ₀
-        result.Hs.append(pjacobian(f, theta0, step, fdm))
+        if adaptive:
+            Hk, steps_k = pjacobian_adaptive(f, theta0, fdm)
+            result.metadata.setdefault("fd_adaptive_steps", []).append(steps_k)
+            result.Hs.append(Hk)
+        else:
+            result.Hs.append(pjacobian(f, theta0, step, fdm))
 
     result.H = np.mean(np.array(result.Hs), axis=0)                       # :446
     result.time += time.perf_counter() - t0

@@ -120,6 +120,43 @@ def test_lbfgs_reproduces_the_run_printed_in_optims_documentation():
     assert (exact.iterations, exact.f_calls) == (24, 67) and exact.minimum < 1e-24
 
 
+def test_adaptive_fdm_reproduces_the_step_printed_in_finitedifferences_documentation():
+    """A known answer of the upstream FiniteDifferences.jl: its documentation shows
+    `FiniteDifferences.estimate_step(central_fdm(5, 1), sin, 1.0)` returning `(0.001065235154086019, 1.9541865128909085e-13)` (step and
+    accuracy estimate; quoted from memory — nothing is fetchable here).  The restatement (oracle/muse.py: AdaptedFDM) gives both to the
+    last printed digit — the figure rests on a 7-point estimate of the fifth derivative and is sensitive to the order of a
+    floating-point sum, so a 16-digit agreement pins bound estimator, neighbourhood stencils, multipliers and step formula at once."""
+    m = O.AdaptedFDM(5, 1)
+    step, acc = m.estimate_step(math.sin, 1.0)
+    assert abs(step / 0.001065235154086019 - 1) < 4e-16 and abs(acc / 1.9541865128909085e-13 - 1) < 4e-16
+    assert abs(float(m(math.sin, 1.0)[0]) - math.cos(1.0)) < 1e-12           # the estimate itself (README: error ≈ −2.4e-14)
+    # the pieces: stencils, multipliers, default step of the unadapted bound estimator central_fdm(7, 5)
+    assert m.bound.coefs == (-0.5, 2.0, -2.5, 0.0, 2.5, -2.0, 0.5) and m.bound.bound is None
+    assert m.bound.coefs_nbhd[0] == (0.5, -4.0, 12.5, -20.0, 17.5, -8.0, 1.5)    # the 5th derivative at x − h from the same 7 values
+    assert m.bound.coefs_nbhd[2] == tuple(-c for c in reversed(m.bound.coefs_nbhd[0]))
+    assert m.ferr_mult == 1.5 and abs(m.df_mult - 1 / 18) < 1e-17             # Σ|c|, Σ|c g⁵|/5! for [1/12, −2/3, 0, 2/3, −1/12]
+    # vector-valued f: magnitudes are maxima over the components; a constant function falls back to the default step
+    f = lambda e: np.array([math.sin(1 + e), 3 * math.exp(0.5 * e)])
+    m3 = O.AdaptedFDM(3, 1)
+    np.testing.assert_allclose(m3(f, 0.0), [math.cos(1.0), 1.5], rtol=1e-9)
+    assert m3.estimate_step(lambda e: np.array([2.0]), 0.0) == m3._limit(*m3.default_step())
+
+
+def test_get_H_with_the_adaptive_step_agrees_with_an_explicit_small_step():
+    """get_H!(step = nothing) before any scores exist (src/muse.jl:411-413 leaves `step` at nothing, src/util.jl:13 then calls
+    `fdm(f, 0.0)`): per sim and per θ component FiniteDifferences estimates its own step; the Jacobians agree with an explicit
+    step to the accuracy of either."""
+    for name, d in (("funnel", 64), ("hiergauss", 80), ("twolayer", 60)):
+        prob, fam, draws, xd = oracle_problem(name, d, 12)
+        th = theta_start(name)
+        a, b = O.MuseResult(theta=th.copy()), O.MuseResult(theta=th.copy())
+        O.get_H_bang(a, prob, nsims=4, gradz_logLike_atol=1e-10)
+        O.get_H_bang(b, prob, nsims=4, step=np.full(fam.ntheta, 1e-3), gradz_logLike_atol=1e-10)
+        np.testing.assert_allclose(np.array(a.Hs), np.array(b.Hs), rtol=1e-5, atol=1e-5 * np.abs(b.H).max())
+        steps = np.array(a.metadata["fd_adaptive_steps"])
+        assert steps.shape == (4, fam.ntheta) and (steps > 0).all() and len(np.unique(steps)) > 1   # every sim its own step
+
+
 def test_lbfgs_zero_iterations_when_start_satisfies_gtol():
     fam = O.Funnel(16)
     x = np.linspace(-1, 1, 16)
