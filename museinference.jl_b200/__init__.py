@@ -10,7 +10,7 @@ from ._build import build_library                                        # noqa:
 from .backend import B200Backend                                         # noqa: F401
 from .parallel import LocalPool, ShardPool, block_partition              # noqa: F401
 from .problem import AbstractMuseProblem, SimpleMuseProblem, BaseDraws, FlatPrior, NormalPrior   # noqa: F401
-from .muse import MuseResult, muse, muse_, get_J_, get_H_, finalize_result_, central_fdm, SimpleCovariance   # noqa: F401
+from .muse import MuseResult, muse, muse_, get_J_, get_H_, finalize_result_, central_fdm, AdaptedFDM, SimpleCovariance   # noqa: F401
 
 globals()["muse!"] = muse_
 globals()["get_J!"] = get_J_

@@ -45,8 +45,9 @@ def _ascii_kwargs(kw: dict) -> dict:
 def central_fdm(p: int, q: int = 1):
     """``FiniteDifferences.central_fdm(p, q)`` as get_H!'s ``fdm`` keyword takes it (src/muse.jl:300): the symmetric integer grid
     of p points and the coefficients c with Σᵢ cᵢ gᵢᵏ = q!·δ_{kq} (exact rationals, rounded to Float64).  Only first
-    derivatives of odd-point methods (q = 1; p = 3, 5, 7, …) can be served by the backend's ± sample points; the step is always
-    explicit (``step`` or 0.1 ./ std(result.gs), src/muse.jl:411-413) — the package's adaptive step estimation is not provided."""
+    derivatives of odd-point methods (q = 1; p = 3, 5, 7, …) can be served by the backend's ± sample points.  The step is explicit
+    (``step`` or 0.1 ./ std(result.gs), src/muse.jl:411-413) or, when get_H! is called with neither, the package's own adaptive
+    estimate (``AdaptedFDM`` below)."""
     from fractions import Fraction
     from math import factorial
     if q != 1 or p < 3 or p % 2 == 0:
@@ -61,6 +62,74 @@ def central_fdm(p: int, q: int = 1):
             if r != c and A[r][c] != 0:
                 A[r] = [vr - A[r][c] * vc for vr, vc in zip(A[r], A[c])]
     return tuple(float(g) for g in grid), tuple(float(A[k][p]) for k in range(p))
+
+
+def _fdm_coefs(grid, q):
+    """Coefficients c with Σᵢ cᵢ gᵢᵏ = q!·δ_{kq}, k = 0 … p−1, on an arbitrary integer grid (exact rationals → Float64)."""
+    from fractions import Fraction
+    from math import factorial
+    p = len(grid)
+    A = [[Fraction(g) ** k for g in grid] + [Fraction(factorial(q) if k == q else 0)] for k in range(p)]
+    for c in range(p):
+        piv = next(r for r in range(c, p) if A[r][c] != 0)
+        A[c], A[piv] = A[piv], A[c]
+        A[c] = [v / A[c][c] for v in A[c]]
+        for r in range(p):
+            if r != c and A[r][c] != 0:
+                A[r] = [vr - A[r][c] * vc for vr, vc in zip(A[r], A[c])]
+    return tuple(float(A[k][p]) for k in range(p))
+
+
+class AdaptedFDM:
+    """``FiniteDifferences.central_fdm(p, q; adapt = 1)`` when it is called WITHOUT a step — what ``pjacobian`` does for
+    ``step === nothing`` (src/util.jl:13), i.e. get_H! before any scores exist (src/muse.jl:411-413).  The package picks
+    step = (q/(p−q)·C₁/C₂)^(1/p) with C₁ = eps(|f|)·Σ|c| and C₂ = |∇ᵖf|·Σ|c·gᵖ|/p!, the two magnitudes taken from the unadapted
+    ``central_fdm(p + 2, p)`` at its default step (|∇ᵖf| → 10, eps(|f|) → eps) — the largest estimate over x − h, x, x + h and
+    over the components of f — and caps it at 1000 × the default step.  ``magnitudes`` / ``step_from_magnitudes`` are split so that
+    the function values can come from batched backend calls."""
+
+    def __init__(self, p, q=1, adapt=1, condition=10.0):
+        from fractions import Fraction
+        from math import factorial
+        self.p, self.q = int(p), int(q)
+        M = self.p // 2
+        self.grid = tuple(float(g) for g in range(-M, M + 1))
+        ig = [int(g) for g in self.grid]
+        self.coefs = _fdm_coefs(ig, self.q)
+        self.coefs_nbhd = (_fdm_coefs([g - 1 for g in ig], self.q), self.coefs, _fdm_coefs([g + 1 for g in ig], self.q))
+        self.condition = float(condition)
+        self.df_mult = float(sum(abs(Fraction(c) * Fraction(g) ** self.p) for c, g in zip(self.coefs, ig)) / factorial(self.p))
+        self.ferr_mult = sum(abs(c) for c in self.coefs)
+        self.bound = AdaptedFDM(self.p + 2, self.p, adapt - 1, condition) if adapt >= 1 else None
+
+    def _step_acc(self, df_magnitude, f_error):
+        P, Q = self.p, self.q
+        c1 = f_error * self.ferr_mult
+        c2 = df_magnitude * self.df_mult
+        step = (Q / (P - Q) * (c1 / c2)) ** (1 / P)
+        return step, c1 * step ** (-Q) + c2 * step ** (P - Q)
+
+    def default_step(self):
+        return self._step_acc(self.condition, float(np.finfo(np.float64).eps))[0]
+
+    def _limit(self, step):
+        return min(step, 1000 * self.default_step())           # max_range = Inf: only the cap at 1000 × the default step applies
+
+    def estimate(self, fs, step, coefs=None):
+        coefs = self.coefs if coefs is None else coefs
+        acc = fs[0] * coefs[0]
+        for fk, ck in zip(fs[1:], coefs[1:]):                  # sum(fs .* coefs), left to right
+            acc = acc + fk * ck
+        return acc / step ** self.q
+
+    def magnitudes(self, fs, step):
+        df = max(float(np.max(np.abs(self.estimate(fs, step, c)))) for c in self.coefs_nbhd)
+        return df, max(float(np.max(np.abs(v))) for v in fs)
+
+    def step_from_magnitudes(self, df_magnitude, f_magnitude):
+        if df_magnitude == 0.0 or f_magnitude == 0.0:
+            return self._limit(self.default_step())
+        return self._limit(self._step_acc(df_magnitude, float(np.spacing(f_magnitude)))[0])
 
 
 class SimpleCovariance:
@@ -525,10 +594,12 @@ def get_H_(result: MuseResult, prob: AbstractMuseProblem, theta0=None, **kwargs)
         return result
     if step is None and len(result.gs) > 0:                                        # :411-413
         step = 0.1 / np.std(np.asarray(result.gs, dtype=np.float64).reshape(-1, prob.ntheta), axis=0, ddof=1)
-    if step is None:
-        raise MuseBackendError(-5, "get_H!: pass `step` or run get_J!/muse! first; FiniteDifferences' adaptive "
-                                   "step estimation is not provided")
-    step = prob.standardize_theta(step)
+    adaptive = step is None                    # src/util.jl:13: fdm(f, 0.0) — FiniteDifferences estimates a step per sim and component
+    if adaptive and (pool.world > 1 or prob.has_transform):
+        raise MuseBackendError(-5, "get_H!: without `step` and without scores from get_J!/muse! the finite-difference step is "
+                                   "estimated per simulation, which is provided on one GPU and for the identity θ-transform")
+    if not adaptive:
+        step = prob.standardize_theta(step)
 
     # rngs = split_rng(rng, nsims_remaining)  (:323): the first nsims_remaining child streams
     n_total = max(nsims_total, nsims_remaining)
@@ -540,7 +611,10 @@ def get_H_(result: MuseResult, prob: AbstractMuseProblem, theta0=None, **kwargs)
         be.set_z0(z0)
         be.fd_start(_capi.START_USER)
     try:
-        if not prob.has_transform and fdm is None:
+        if adaptive:
+            Hs_local, status, steps = _fd_jacobian_adaptive(be, prob, theta0, hcnt, atol, fdm)
+            result.metadata["fd_adaptive_steps"] = steps
+        elif not prob.has_transform and fdm is None:
             Hs_local, status = be.fd_jacobian(theta0, step, hcnt, atol)            # :417-442 + src/util.jl:9-26
         else:
             # pjacobian perturbs the UNtransformed θ₀ (src/util.jl:15; sims at θ, MAP and score at θ₀, :430-432); the kernels
@@ -597,6 +671,52 @@ def get_H_(result: MuseResult, prob: AbstractMuseProblem, theta0=None, **kwargs)
     result.time += time.perf_counter() - t0
     finalize_result_(result, prob)
     return result
+
+
+def _fd_jacobian_adaptive(be, prob, theta0, count, atol, fdm):
+    """The finite-difference Jacobians of get_H! with FiniteDifferences' own step (``AdaptedFDM``).  Stage 1 — the bound estimator's
+    p + 2 sample points are the same for every sim (its step is the default one): (p + 1)/2 ``fd_scores`` calls (one per grid
+    distance, both signs) and one at θ₀ serve all sims and components, and give every sim its steps.  Stage 2 — the steps differ per
+    sim, the backend takes ONE table of sample points per call: sim k is served by a call over sims 0 … k with its points, of which
+    row k is kept (n_H(n_H + 1)/2 solves per grid distance: get_H!'s default is n_H = 10).  The centre value is the one of stage 1."""
+    nt = prob.ntheta
+    grid, coefs = fdm if fdm is not None else ((-1.0, 0.0, 1.0), (-0.5, 0.0, 0.5))
+    adm = AdaptedFDM(len(grid), 1)
+    bnd = adm.bound
+    hb = bnd._limit(bnd.default_step())
+    status = np.zeros((count, nt, 2), dtype=np.int32)
+
+    def scores(offsets, n_units):
+        """offsets[n] = (ε₋, ε₊) of component n → (g at ε₋, g at ε₊), each n_units × nθ (column) × nθ."""
+        pts = np.empty((2 * nt, nt))
+        for n in range(nt):
+            for sgn in (0, 1):
+                th = theta0.copy()
+                th[n] = theta0[n] + offsets[n][sgn]
+                pts[2 * n + sgn] = th
+        g, st = be.fd_scores(theta0, pts, n_units, atol)
+        bad = np.where(st.reshape(n_units, nt, 2) == _capi.STATUS_NONFINITE, _capi.STATUS_NONFINITE, 0)
+        status[:n_units] = np.maximum(status[:n_units], bad)
+        return g[:, 0::2, :], g[:, 1::2, :]
+
+    g_b = {}
+    for m_ in range(1, len(bnd.grid) // 2 + 1):
+        g_b[-float(m_)], g_b[float(m_)] = scores([(0.0 + hb * -float(m_), 0.0 + hb * float(m_))] * nt, count)
+    g_b[0.0], _ = scores([(0.0, 0.0)] * nt, count)
+    steps = np.empty((count, nt))
+    for k in range(count):
+        for n in range(nt):
+            steps[k, n] = adm.step_from_magnitudes(*bnd.magnitudes([g_b[gp][k, n, :] for gp in bnd.grid], hb))
+    Hs = np.empty((count, nt, nt))
+    M = len(grid) // 2
+    for k in range(count):
+        vals = {0.0: g_b[0.0][k]}
+        for m_ in range(1, M + 1):
+            lo, hi = scores([(0.0 + steps[k, n] * -float(m_), 0.0 + steps[k, n] * float(m_)) for n in range(nt)], k + 1)
+            vals[-float(m_)], vals[float(m_)] = lo[k], hi[k]
+        for n in range(nt):
+            Hs[k, :, n] = adm.estimate([vals[gp][n, :] for gp in grid], steps[k, n], coefs)
+    return Hs, status, steps
 
 
 # =============================================================================== finalize_result!

@@ -828,6 +828,33 @@ def test_get_H_keywords_user_start_and_five_point_fdm(name, d):
     prob.close()
 
 
+@pytest.mark.parametrize("name,d", [("funnel", 512), ("hiergauss", 4500), ("twolayer", 400)])
+def test_get_H_with_finite_differences_own_step(name, d):
+    """get_H! with neither `step` nor scores in the result (src/muse.jl:411-413 → src/util.jl:13: fdm(f, 0.0)): FiniteDifferences'
+    adaptive step per sim and per θ component, from batched muse_b200_fd_scores calls, against the oracle's restatement.  The
+    steps rest on a five-point estimate of a third derivative (round-off amplified by 1/h³): they agree to a few 1e-3 where that
+    derivative does not vanish, the Jacobians to rtol 1e-6."""
+    import museinference_jl_b200 as m
+    oprob, fam, draws, xd = oracle_problem(name, d, 12)
+    rng = m.BaseDraws(draws.xi, draws.nu, draws.xi_master, draws.nu_master)
+    prob = m.SimpleMuseProblem(xd, name)
+    th = theta_start(name)
+    res, ref = m.MuseResult(theta=th.copy()), O.MuseResult(theta=th.copy())
+    getattr(m, "get_H!")(res, prob, rng=rng, nsims=4, gradz_logLike_atol=1e-6)
+    O.get_H_bang(ref, oprob, nsims=4, gradz_logLike_atol=1e-6)
+    steps, steps_ref = res.metadata["fd_adaptive_steps"], np.array(ref.metadata["fd_adaptive_steps"])
+    assert steps.shape == steps_ref.shape == (4, fam.ntheta)
+    if name != "hiergauss":
+        np.testing.assert_allclose(steps, steps_ref, rtol=5e-2)
+    # (hiergauss: the scores are linear / quadratic in the simulation's μ and polynomial-times-exponential in ℓ — where the third
+    # derivative vanishes identically the step is set by round-off alone and differs between any two implementations; the central
+    # difference of such a function is exact at any step)
+    assert (steps > 0).all() and (steps <= 1000 * m.AdaptedFDM(3, 1).default_step()).all()
+    scale = np.abs(np.array(ref.Hs)).max()
+    np.testing.assert_allclose(np.array(res.Hs), np.array(ref.Hs), rtol=RTOL_EST, atol=RTOL_EST * scale)
+    prob.close()
+
+
 @pytest.mark.parametrize("name,d,nsims", [("funnel", 512, 30), ("hiergauss", 5000, 20), ("corrgauss", 256, 24), ("twolayer", 1024, 16)])
 def test_implicit_diff_get_H_matches_oracle(name, d, nsims):
     """get_H!(implicit_diff = true) (src/muse.jl:335-405) on the GPU — MAP pass at ∇z_logLike_atol = 1e-1, closed-form second

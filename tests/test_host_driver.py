@@ -98,8 +98,8 @@ def test_unsupported_options_raise():
     getH = getattr(m, "get_H!")
     with pytest.raises(m.MuseBackendError):
         getH(res, prob, rng=rng, nsims=2, implicit_diff=True, implicit_diff_cg_kwargs=dict(Pl="jacobi"))
-    with pytest.raises(m.MuseBackendError):
-        getH(res, prob, rng=rng, nsims=2)            # no step and no scores yet
+    getH(res, prob, rng=rng, nsims=2)                # no step and no scores yet: FiniteDifferences' adaptive step (tested below)
+    assert res.metadata["fd_adaptive_steps"].shape == (2, 1)
     with pytest.raises(ValueError):
         m.muse(prob, [0.1, 0.2], rng=rng, nsims=10)  # wrong θ length
 
@@ -142,6 +142,38 @@ def test_keywords_of_get_J_and_get_H_covariance_method_fdm_and_user_start():
     O.get_H_bang(ref4, oprob, nsims=3, step=np.array([0.02, 0.03]), z0=z0, gradz_logLike_atol=1e-10)
     np.testing.assert_allclose(np.array(res4.Hs), np.array(ref4.Hs), rtol=1e-9, atol=1e-9)
     assert not getattr(prob._backend, "fd_user_start", False)            # the option does not outlive the call
+
+
+def test_get_H_without_step_and_scores_uses_the_adaptive_finite_difference_step():
+    """get_H!(result, prob) with neither `step` nor scores in the result (src/muse.jl:411-413 leaves step = nothing; src/util.jl:13
+    then calls fdm(f, 0.0)): FiniteDifferences estimates a step per sim and per θ component.  Host path (batched fd_scores calls:
+    common sample points for the bound estimator, per-sim points for the final stencil) against the oracle's one-function-at-a-time
+    restatement: the same steps and the same Jacobians, for the default 3-point method and for central_fdm(5, 1)."""
+    for name, d in (("funnel", 48), ("hiergauss", 60), ("twolayer", 40)):
+        m, oprob, prob, rng = _pair(name, d, 12, False)
+        getH = getattr(m, "get_H!")
+        th = theta_start(name)
+        for kw_m, kw_o in ((dict(), dict()), (dict(fdm=m.central_fdm(5, 1)), dict(fdm=O.central_fdm(5, 1)))):
+            res, ref = m.MuseResult(theta=th.copy()), O.MuseResult(theta=th.copy())
+            getH(res, prob, rng=rng, nsims=4, gradz_logLike_atol=1e-10, **kw_m)
+            O.get_H_bang(ref, oprob, nsims=4, gradz_logLike_atol=1e-10, **kw_o)
+            np.testing.assert_allclose(res.metadata["fd_adaptive_steps"], np.array(ref.metadata["fd_adaptive_steps"]), rtol=1e-12)
+            np.testing.assert_allclose(np.array(res.Hs), np.array(ref.Hs), rtol=1e-10, atol=1e-12)
+        # with scores in the result the step is 0.1 ./ std(gs), as before
+        res2 = m.MuseResult(theta=th.copy())
+        getattr(m, "get_J!")(res2, prob, rng=rng, nsims=8)
+        getH(res2, prob, rng=rng, nsims=3)
+        assert "fd_adaptive_steps" not in res2.metadata
+    # a transformed θ keeps raising without a step
+    mm, oprob_t, prob_t, rng_t, *_ = _pair_t(40, 8)
+    with pytest.raises(mm.MuseBackendError):
+        getattr(mm, "get_H!")(mm.MuseResult(theta=np.array([0.5, 1.2])), prob_t, rng=rng_t, nsims=3)
+    # the class itself: the figure of the package's documentation
+    import math
+    a = mm.AdaptedFDM(5, 1)
+    fs = [np.array([math.sin(1.0 + a.bound.default_step() * g)]) for g in a.bound.grid]
+    step = a.step_from_magnitudes(*a.bound.magnitudes(fs, a.bound.default_step()))
+    assert abs(step / 0.001065235154086019 - 1) < 4e-16
 
 
 def test_implicit_diff_get_H_host_path_and_oracle_against_finite_differences():
