@@ -260,7 +260,11 @@ function MuseInference.get_H!(result::MuseResult, prob::B200MuseProblem, θ₀ =
         return finalize_result!(result, prob)
     end
     z₀ === nothing || check(h, ccall((:muse_b200_fd_start, libmuse), Cint, (Ptr{Cvoid}, Cint), h, START_USER))
-    step = something(step, 0.1 ./ std(result.gs))                                       # :411-413
+    # :411-413.  With neither `step` nor scores the reference leaves step = nothing and FiniteDifferences estimates one per sim and
+    # component (src/util.jl:13); museinference.jl_b200/muse.py (_fd_jacobian_adaptive) does that with muse_b200_fd_scores calls — here
+    # the caller is asked for a step instead.
+    (step === nothing && isempty(result.gs)) && error("get_H!: pass `step` or run muse!/get_J! first")
+    step = something(step, 0.1 ./ std(result.gs))
     Hs = Array{Float64}(undef, nθ, nθ, remaining)     # column-major (n, i, k) == C row-major [k][i][n]
     t0, st = collect(Float64, θ₀), collect(Float64, step)
     GC.@preserve t0 st Hs check(h, ccall((:muse_b200_fd_jacobian, libmuse), Cint,
